@@ -1,0 +1,153 @@
+/* kiwi_b200 — C ABI of the B200-native replacement for Kiwi's lattice-analysis hot path.
+ *
+ * The entry points below are exactly the ones the reference's FFI for this path binds
+ * (/root/reference/include/kiwi/capi.h, implementation src/capi/kiwi_c.cpp); each declaration cites the
+ * reference declaration it replaces.  Types are plain C: pointers, sizes, opaque handles; no torch or CUDA
+ * types cross the boundary.  `kiwi_b200_*` functions are additive (batched flat-array interface, model
+ * image handling, device control); everything else keeps the reference's name, argument meaning and
+ * error convention (never throws across the ABI; NULL / KIWIERR_* + kiwi_error() per calling thread).
+ *
+ * Out of scope: builder, typo transformer handles, morphset, pretokenized spans,
+ * joiner, sub-word tokenizer, sentence splitter — passing a non-NULL handle for one of those is an error.
+ */
+#ifndef KIWI_B200_H
+#define KIWI_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KIWIERR_FAIL -1             /* capi.h:17 */
+#define KIWIERR_INVALID_HANDLE -2   /* capi.h:18 */
+#define KIWIERR_INVALID_INDEX -3    /* capi.h:19 */
+
+#define KIWI_MATCH_URL 1
+#define KIWI_MATCH_EMAIL 2
+#define KIWI_MATCH_HASHTAG 4
+#define KIWI_MATCH_MENTION 8
+#define KIWI_MATCH_SERIAL 16
+#define KIWI_MATCH_EMOJI 32
+#define KIWI_MATCH_NORMALIZE_CODA (1 << 16)
+#define KIWI_MATCH_Z_CODA (1 << 23)
+#define KIWI_MATCH_ALL (KIWI_MATCH_URL | KIWI_MATCH_EMAIL | KIWI_MATCH_HASHTAG | KIWI_MATCH_MENTION | KIWI_MATCH_SERIAL | KIWI_MATCH_EMOJI | KIWI_MATCH_Z_CODA)
+#define KIWI_MATCH_ALL_WITH_NORMALIZING (KIWI_MATCH_ALL | KIWI_MATCH_NORMALIZE_CODA)
+
+typedef struct kiwi_s* kiwi_h;                        /* capi.h:29 */
+typedef struct kiwi_res* kiwi_res_h;                  /* capi.h:31 */
+typedef struct kiwi_morphset* kiwi_morphset_h;        /* capi.h:36 */
+typedef struct kiwi_pretokenized* kiwi_pretokenized_h;/* capi.h:37 */
+typedef struct kiwi_prepared_typo* kiwi_prepared_typo_h; /* capi.h:38 */
+typedef unsigned short kchar16_t;                     /* capi.h:39 */
+
+typedef struct {                                      /* capi.h:43-61 */
+	uint32_t chr_position;
+	uint32_t word_position;
+	uint32_t sent_position;
+	uint32_t line_number;
+	uint16_t length;
+	uint8_t tag;
+	union { uint8_t sense_id; uint8_t script; };
+	float score;
+	float typo_cost;
+	uint32_t typo_form_id;
+	uint32_t paired_token;
+	uint32_t sub_sent_position;
+	uint16_t dialect;
+} kiwi_token_info_t;
+
+typedef struct {                                      /* capi.h:662-670, passed BY VALUE */
+	int match_options;
+	kiwi_morphset_h blocklist;
+	int open_ending;
+	int allowed_dialects;
+	float dialect_cost;
+	kiwi_prepared_typo_h typo_transformer;
+	float typo_threshold;
+} kiwi_analyze_option_t;
+
+typedef int (*kiwi_reader_t)(int, char*, void*);         /* capi.h:104 */
+typedef int (*kiwi_reader_w_t)(int, kchar16_t*, void*);  /* capi.h:105 */
+typedef int (*kiwi_receiver_t)(int, kiwi_res_h, void*);  /* capi.h:144 */
+
+const char* kiwi_version(void);                          /* capi.h:238 */
+const char* kiwi_error(void);                            /* capi.h:245 */
+void kiwi_clear_error(void);                             /* capi.h:252 */
+
+/* capi.h:599.  model_path: a directory holding `kiwi_b200.img` or the path of an image file.  num_threads sizes
+ * only the host-side marshalling pool; options / enabled_dialects are recorded in the image at flatten time. */
+kiwi_h kiwi_init(const char* model_path, int num_threads, int options, int enabled_dialects);
+int kiwi_close(kiwi_h handle);                           /* capi.h:771 */
+
+kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_analyze_option_t option, kiwi_pretokenized_h pretokenized);  /* capi.h:684 */
+kiwi_res_h kiwi_analyze(kiwi_h handle, const char* text, int top_n, kiwi_analyze_option_t option, kiwi_pretokenized_h pretokenized);        /* capi.h:698 */
+int kiwi_analyze_mw(kiwi_h handle, kiwi_reader_w_t reader, kiwi_receiver_t receiver, void* user_data, int top_n, kiwi_analyze_option_t option); /* capi.h:711 */
+int kiwi_analyze_m(kiwi_h handle, kiwi_reader_t reader, kiwi_receiver_t receiver, void* user_data, int top_n, kiwi_analyze_option_t option);   /* capi.h:724 */
+
+int kiwi_res_size(kiwi_res_h result);                                        /* capi.h:788 */
+float kiwi_res_prob(kiwi_res_h result, int index);                           /* capi.h:797 */
+int kiwi_res_word_num(kiwi_res_h result, int index);                         /* capi.h:806 */
+const kiwi_token_info_t* kiwi_res_token_info(kiwi_res_h result, int index, int num); /* capi.h:816 */
+int kiwi_res_morpheme_id(kiwi_res_h result, int index, int num, kiwi_h kiwi_handle); /* capi.h:827 */
+const kchar16_t* kiwi_res_form_w(kiwi_res_h result, int index, int num);     /* capi.h:837 */
+const kchar16_t* kiwi_res_tag_w(kiwi_res_h result, int index, int num);      /* capi.h:847 */
+const char* kiwi_res_form(kiwi_res_h result, int index, int num);            /* capi.h:857 */
+const char* kiwi_res_tag(kiwi_res_h result, int index, int num);             /* capi.h:867 */
+int kiwi_res_position(kiwi_res_h result, int index, int num);                /* capi.h:877 */
+int kiwi_res_length(kiwi_res_h result, int index, int num);                  /* capi.h:887 */
+float kiwi_res_score(kiwi_res_h result, int index, int num);                 /* capi.h:917 */
+int kiwi_res_close(kiwi_res_h result);                                       /* capi.h:937 */
+
+/* ---- additive batched interface (flat arrays; what kiwi_analyze_mw drains into) -------------------- */
+typedef struct {
+	uint32_t morph_id;      /* morphToId(PathNode.morph) after unifyMorpheme (PathEvaluator.hpp:1054-1058) */
+	uint32_t position;      /* original UTF-16 units (Kiwi.cpp:734-737) */
+	float score;            /* PathNode.wordScore */
+	uint16_t length;
+	uint8_t tag;            /* POSTag incl. the irregular bit, after script re-tagging (Kiwi.cpp:590-605) */
+	uint8_t flags;          /* bit0: the token carries its own surface form (OOV / special run / pattern) */
+} kiwi_b200_token_t;
+
+typedef struct {
+	int n_sentences;
+	const uint32_t* token_offsets;      /* [n_sentences + 1] into tokens */
+	const kiwi_b200_token_t* tokens;
+	const float* scores;                /* top-1 path score per sentence (sum over chunks, Kiwi.cpp:759) */
+	const uint32_t* status;             /* 0 = ok */
+	/* device timing of the last call, milliseconds (CUDA events on the engine's stream) */
+	float ms_h2d, ms_lattice, ms_viterbi, ms_pack, ms_d2h, ms_total;
+} kiwi_b200_batch_t;
+
+/* Analyze n sentences given as one UTF-16 blob + offsets[n+1].  Returns NULL and sets kiwi_error() on failure
+ * (including any sentence that overflowed even the retry capacity).  Free with kiwi_b200_batch_free. */
+const kiwi_b200_batch_t* kiwi_b200_analyze_batch(kiwi_h handle, const kchar16_t* text, const uint32_t* offsets, int n, kiwi_analyze_option_t option);
+void kiwi_b200_batch_free(const kiwi_b200_batch_t* batch);
+
+/* Same work with inputs already resident in device memory (used by bench.py's device-resident leg). The
+ * text / offsets pointers are DEVICE pointers; results stay on the device; returns elapsed device ms or < 0. */
+float kiwi_b200_analyze_device(kiwi_h handle, const void* d_text, const void* d_offsets, int n, uint64_t total_units, kiwi_analyze_option_t option, uint64_t* out_tokens, uint64_t* out_launches);
+
+/* Counters of the last batch (for the roofline arithmetic): kernel times, launches, bytes moved. */
+typedef struct {
+	uint64_t n_sentences, raw_units, norm_units, lattice_nodes, tokens, paths;
+	uint64_t h2d_bytes, d2h_bytes, kernel_launches;
+	float ms_lattice, ms_viterbi, ms_pack;
+} kiwi_b200_stats_t;
+int kiwi_b200_last_stats(kiwi_h handle, kiwi_b200_stats_t* out);
+
+/* Lattice of one sentence (stage-level parity tests): nodes as 9 x int32 rows
+ * {form, uform_off|-1, uform_len, prev, sibling, start, end, space_errors, chunk}.  Returns node count or < 0. */
+int kiwi_b200_debug_lattice(kiwi_h handle, const kchar16_t* text, int len, int32_t* out_rows, int max_rows, kiwi_analyze_option_t option);
+
+int kiwi_b200_device_count(void);
+int kiwi_b200_set_device(int device);            /* call before kiwi_init; default: current device */
+/* raw model image access so a launcher can broadcast it (NCCL) and hand it to every rank */
+int kiwi_b200_read_image(const char* model_path, void** out_bytes, uint64_t* out_size);   /* malloc'ed */
+kiwi_h kiwi_b200_init_from_image(const void* bytes, uint64_t size);
+void kiwi_b200_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,381 @@
+// kiwi_b200: extern "C" boundary (include/kiwi_b200.h).  Mirrors the error convention of the reference's
+// C API (/root/reference/src/capi/kiwi_c.cpp:84-113): nothing is thrown across the ABI, failures return
+// NULL / KIWIERR_* and leave a message for the calling thread in kiwi_error().
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/kiwi_b200.h"
+#include "engine.h"
+
+using namespace kb;
+
+struct kiwi_s
+{
+	std::unique_ptr<Engine> engine;
+	std::mutex mtx;           // one stream + one scratch arena per handle: calls on one handle are serialised
+	int numThreads = 0;
+};
+
+struct kiwi_res
+{
+	struct Tok { kiwi_token_info_t info; uint32_t morphId; std::u16string form; std::string form8; };
+	std::vector<Tok> toks;
+	float score = 0;
+	bool empty = false;
+};
+
+static thread_local std::string g_error;
+static thread_local bool g_hasError = false;
+static int g_device = -1;
+
+static void setError(const std::exception& e) { g_error = e.what(); g_hasError = true; }
+static void setError(const char* s) { g_error = s; g_hasError = true; }
+
+static const char* tagName(uint8_t t)
+{
+	static const char* tags[] = { "UN", "NNG", "NNP", "NNB", "VV", "VA", "MAG", "NR", "NP", "VX", "MM", "MAJ", "IC", "XPN", "XSN", "XSV", "XSA", "XSM", "XR",
+		"VCP", "VCN", "SF", "SP", "SS", "SSO", "SSC", "SE", "SO", "SW", "SB", "SL", "SH", "SN", "W_URL", "W_EMAIL", "W_MENTION", "W_HASHTAG", "W_SERIAL", "W_EMOJI",
+		"JKS", "JKC", "JKG", "JKO", "JKB", "JKV", "JKQ", "JX", "JC", "EP", "EF", "EC", "ETN", "ETM", "Z_CODA", "Z_SIOT", "USER0", "USER1", "USER2", "USER3", "USER4", "P", "@" };
+	if (t & 0x80)
+	{
+		switch (t & 0x7F) { case T_vv: return "VV-I"; case T_va: return "VA-I"; case T_vx: return "VX-I"; case T_xsa: return "XSA-I"; default: return "@"; }
+	}
+	return t <= T_max ? tags[t] : "@";
+}
+static const char16_t* tagNameW(uint8_t t)
+{
+	static thread_local std::u16string buf[4]; static thread_local int rot = 0;
+	const char* s = tagName(t);
+	auto& b = buf[rot++ & 3];
+	b.assign(s, s + std::strlen(s));
+	return b.c_str();
+}
+
+static std::u16string utf8To16(const char* s)
+{
+	std::u16string out;
+	const size_t n = std::strlen(s);
+	for (size_t i = 0; i < n;)
+	{
+		uint32_t c = (uint8_t)s[i]; size_t k = 1;
+		if (c >= 0xF0) { c &= 7; k = 4; } else if (c >= 0xE0) { c &= 15; k = 3; } else if (c >= 0xC0) { c &= 31; k = 2; }
+		for (size_t j = 1; j < k && i + j < n; ++j) c = (c << 6) | ((uint8_t)s[i + j] & 63);
+		i += k;
+		if (c >= 0x10000) { c -= 0x10000; out.push_back((char16_t)(0xD800 | (c >> 10))); out.push_back((char16_t)(0xDC00 | (c & 0x3FF))); }
+		else out.push_back((char16_t)c);
+	}
+	return out;
+}
+static std::string utf16To8(const std::u16string& s)
+{
+	std::string out;
+	for (size_t i = 0; i < s.size(); ++i)
+	{
+		uint32_t c = s[i];
+		if ((c & 0xFC00) == 0xD800 && i + 1 < s.size()) { c = (((c & 0x3FF) << 10) | (s[i + 1] & 0x3FF)) + 0x10000; ++i; }
+		if (c < 0x80) out.push_back((char)c);
+		else if (c < 0x800) { out.push_back((char)(0xC0 | (c >> 6))); out.push_back((char)(0x80 | (c & 63))); }
+		else if (c < 0x10000) { out.push_back((char)(0xE0 | (c >> 12))); out.push_back((char)(0x80 | ((c >> 6) & 63))); out.push_back((char)(0x80 | (c & 63))); }
+		else { out.push_back((char)(0xF0 | (c >> 18))); out.push_back((char)(0x80 | ((c >> 12) & 63))); out.push_back((char)(0x80 | ((c >> 6) & 63))); out.push_back((char)(0x80 | (c & 63))); }
+	}
+	return out;
+}
+// joinHangul (reference src/StrUtils.h): a coda jamo U+11A8..U+11C2 after a coda-less syllable folds into it
+static std::u16string joinHangul(const uint16_t* p, size_t n)
+{
+	std::u16string out;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const uint16_t c = p[i];
+		if (0x11A8 <= c && c <= 0x11C2 && !out.empty() && 0xAC00 <= out.back() && out.back() < 0xD7A4 && (out.back() - 0xAC00) % 28 == 0) out.back() = (char16_t)(out.back() + (c - 0x11A7));
+		else out.push_back((char16_t)c);
+	}
+	return out;
+}
+
+static void checkOption(const kiwi_analyze_option_t& o, int topN, kiwi_pretokenized_h pt)
+{
+	if (topN != 1) throw std::invalid_argument("kiwi_b200 implements the top_n == 1 path only");
+	if (o.blocklist) throw std::invalid_argument("blocklist is outside the kiwi_b200 hot path");
+	if (o.typo_transformer) throw std::invalid_argument("typo_transformer is outside the kiwi_b200 hot path in this build");
+	if (o.allowed_dialects) throw std::invalid_argument("dialects other than standard are outside the kiwi_b200 hot path");
+	if (o.open_ending) throw std::invalid_argument("open_ending is not supported by this build");
+	if (pt) throw std::invalid_argument("pretokenized spans are outside the kiwi_b200 hot path");
+	const uint32_t unsupported = (3u << 8) | (1u << 17) | (1u << 18) | (1u << 19) | (1u << 20) | (1u << 21) | (1u << 24) | (1u << 26) | (1u << 27) | (1u << 30);
+	if ((uint32_t)o.match_options & unsupported) throw std::invalid_argument("match_options contain a flag outside the kiwi_b200 hot path (oov models, join*, compatibleJamo, mergeSaisiot, useOldSplitter)");
+}
+
+static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, const BatchOutput& bo, uint32_t idx)
+{
+	auto* r = new kiwi_res;
+	r->score = bo.scores[idx];
+	const Model& m = h->engine->model;
+	for (uint32_t t = bo.tokOff[idx]; t < bo.tokOff[idx + 1]; ++t)
+	{
+		const DToken& d = bo.tokens[t];
+		kiwi_res::Tok k;
+		std::memset(&k.info, 0, sizeof(k.info));
+		k.info.chr_position = d.position; k.info.length = d.length; k.info.tag = d.tag; k.info.score = d.score;
+		k.info.paired_token = (uint32_t)-1;
+		k.morphId = d.morph;
+		const kb2_morph& mm = m.hMorphs[d.morph];
+		k.info.sense_id = mm.sense_id; k.info.dialect = mm.dialect;
+		if (d.flags & 1) { k.form.assign(reinterpret_cast<const char16_t*>(text) + d.position, d.length); if ((d.tag & 0x7F) == T_nng || (d.tag & 0x7F) == T_nnp) k.info.sense_id = 0xFF; }
+		else if (mm.form_idx >= 0) k.form = joinHangul(m.hFormChars + m.hForms[mm.form_idx].str_off, m.hForms[mm.form_idx].str_len);
+		k.form8 = utf16To8(k.form);
+		r->toks.push_back(std::move(k));
+	}
+	return r;
+}
+
+// Drains the reader into batches (the reference primes pool->size()*2 futures, include/kiwi/Kiwi.h:402-454);
+// results are delivered to the receiver in input order, which owns and closes them (kiwi_c.cpp:932-936).
+template<class ReadFn>
+static int analyzeMulti(kiwi_h handle, ReadFn&& readOne, kiwi_receiver_t receiver, void* user_data, int top_n, kiwi_analyze_option_t option)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	try
+	{
+		checkOption(option, top_n, nullptr);
+		const size_t maxBatch = 65536, maxUnits = 16u << 20;
+		int idx = 0, delivered = 0;
+		bool done = false;
+		while (!done)
+		{
+			std::vector<uint16_t> text; std::vector<uint32_t> off{ 0 };
+			while (off.size() - 1 < maxBatch && text.size() < maxUnits)
+			{
+				std::u16string s;
+				if (!readOne(idx, s)) { done = true; break; }
+				++idx;
+				text.insert(text.end(), s.begin(), s.end());
+				off.push_back((uint32_t)text.size());
+			}
+			const uint32_t n = (uint32_t)off.size() - 1;
+			if (!n) break;
+			BatchOutput bo;
+			{
+				std::lock_guard<std::mutex> lk(handle->mtx);
+				handle->engine->analyze(text.data(), off.data(), n, (uint32_t)option.match_options, bo);
+			}
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				kiwi_res* r = makeRes(handle, text.data() + off[i], bo, i);
+				// positions are relative to the sentence already (each sentence has its own position table)
+				(*receiver)(delivered++, r, user_data);
+			}
+		}
+		return delivered;
+	}
+	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* kiwi_version(void) { return "0.23.1-b200.1"; }
+const char* kiwi_error(void) { return g_hasError ? g_error.c_str() : nullptr; }
+void kiwi_clear_error(void) { g_hasError = false; g_error.clear(); }
+
+int kiwi_b200_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int kiwi_b200_set_device(int device) { g_device = device; return 0; }
+
+int kiwi_b200_read_image(const char* model_path, void** out_bytes, uint64_t* out_size)
+{
+	try
+	{
+		auto blob = readImageFile(model_path);
+		void* p = std::malloc(blob.size());
+		if (!p) throw std::bad_alloc();
+		std::memcpy(p, blob.data(), blob.size());
+		*out_bytes = p; *out_size = blob.size();
+		return 0;
+	}
+	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+void kiwi_b200_free(void* p) { std::free(p); }
+
+kiwi_h kiwi_b200_init_from_image(const void* bytes, uint64_t size)
+{
+	try
+	{
+		int n = 0;
+		if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw std::runtime_error("kiwi_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
+		if (g_device >= 0 && cudaSetDevice(g_device) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed");
+		auto* h = new kiwi_s;
+		h->engine.reset(new Engine(bytes, size));
+		return h;
+	}
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+kiwi_h kiwi_init(const char* model_path, int num_threads, int options, int enabled_dialects)
+{
+	(void)options; (void)enabled_dialects;
+	try
+	{
+		auto blob = readImageFile(model_path);
+		kiwi_h h = kiwi_b200_init_from_image(blob.data(), blob.size());
+		if (h) h->numThreads = num_threads;
+		return h;
+	}
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+int kiwi_close(kiwi_h handle)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	try { delete handle; return 0; }
+	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+
+kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_analyze_option_t option, kiwi_pretokenized_h pretokenized)
+{
+	if (!handle) return nullptr;
+	try
+	{
+		checkOption(option, top_n, pretokenized);
+		uint32_t len = 0;
+		while (text[len]) ++len;
+		const uint32_t off[2] = { 0, len };
+		std::lock_guard<std::mutex> lk(handle->mtx);
+		BatchOutput bo;
+		handle->engine->analyze(text, off, 1, (uint32_t)option.match_options, bo);
+		return makeRes(handle, text, bo, 0);
+	}
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+kiwi_res_h kiwi_analyze(kiwi_h handle, const char* text, int top_n, kiwi_analyze_option_t option, kiwi_pretokenized_h pretokenized)
+{
+	if (!handle) return nullptr;
+	try
+	{
+		const std::u16string w = utf8To16(text);
+		// NB: positions are reported in UTF-16 units of the converted text, as the reference does for its internal string
+		return kiwi_analyze_w(handle, reinterpret_cast<const kchar16_t*>(w.c_str()), top_n, option, pretokenized);
+	}
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+int kiwi_analyze_mw(kiwi_h handle, kiwi_reader_w_t reader, kiwi_receiver_t receiver, void* user_data, int top_n, kiwi_analyze_option_t option)
+{
+	return analyzeMulti(handle, [&](int idx, std::u16string& s)
+	{
+		const int len = (*reader)(idx, nullptr, user_data);        // kiwi_c.cpp:924-931
+		if (len <= 0) return false;
+		s.resize((size_t)len);
+		(*reader)(idx, reinterpret_cast<kchar16_t*>(&s[0]), user_data);
+		return true;
+	}, receiver, user_data, top_n, option);
+}
+
+int kiwi_analyze_m(kiwi_h handle, kiwi_reader_t reader, kiwi_receiver_t receiver, void* user_data, int top_n, kiwi_analyze_option_t option)
+{
+	return analyzeMulti(handle, [&](int idx, std::u16string& s)
+	{
+		const int len = (*reader)(idx, nullptr, user_data);
+		if (len <= 0) return false;
+		std::string buf((size_t)len, '\0');
+		(*reader)(idx, &buf[0], user_data);
+		s = utf8To16(buf.c_str());
+		return true;
+	}, receiver, user_data, top_n, option);
+}
+
+int kiwi_res_size(kiwi_res_h result) { if (!result) return KIWIERR_INVALID_HANDLE; return 1; }
+float kiwi_res_prob(kiwi_res_h result, int index) { if (!result || index != 0) return 0; return result->score; }
+int kiwi_res_word_num(kiwi_res_h result, int index) { if (!result) return KIWIERR_INVALID_HANDLE; if (index != 0) return KIWIERR_INVALID_INDEX; return (int)result->toks.size(); }
+#define KB_TOK_OR(ret) if (!result) return ret; if (index != 0 || num < 0 || num >= (int)result->toks.size()) return ret;
+const kiwi_token_info_t* kiwi_res_token_info(kiwi_res_h result, int index, int num) { KB_TOK_OR(nullptr) return &result->toks[num].info; }
+int kiwi_res_morpheme_id(kiwi_res_h result, int index, int num, kiwi_h kiwi_handle) { (void)kiwi_handle; KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].morphId; }
+const kchar16_t* kiwi_res_form_w(kiwi_res_h result, int index, int num) { KB_TOK_OR(nullptr) return reinterpret_cast<const kchar16_t*>(result->toks[num].form.c_str()); }
+const kchar16_t* kiwi_res_tag_w(kiwi_res_h result, int index, int num) { KB_TOK_OR(nullptr) return reinterpret_cast<const kchar16_t*>(tagNameW(result->toks[num].info.tag)); }
+const char* kiwi_res_form(kiwi_res_h result, int index, int num) { KB_TOK_OR(nullptr) return result->toks[num].form8.c_str(); }
+const char* kiwi_res_tag(kiwi_res_h result, int index, int num) { KB_TOK_OR(nullptr) return tagName(result->toks[num].info.tag); }
+int kiwi_res_position(kiwi_res_h result, int index, int num) { KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].info.chr_position; }
+int kiwi_res_length(kiwi_res_h result, int index, int num) { KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].info.length; }
+float kiwi_res_score(kiwi_res_h result, int index, int num) { KB_TOK_OR(0.f) return result->toks[num].info.score; }
+int kiwi_res_close(kiwi_res_h result) { if (!result) return KIWIERR_INVALID_HANDLE; delete result; return 0; }
+
+struct BatchHolder { kiwi_b200_batch_t pub; BatchOutput bo; };
+
+const kiwi_b200_batch_t* kiwi_b200_analyze_batch(kiwi_h handle, const kchar16_t* text, const uint32_t* offsets, int n, kiwi_analyze_option_t option)
+{
+	if (!handle) { setError("invalid handle"); return nullptr; }
+	try
+	{
+		checkOption(option, 1, nullptr);
+		if (n < 0) throw std::invalid_argument("n < 0");
+		auto* h = new BatchHolder;
+		try
+		{
+			std::lock_guard<std::mutex> lk(handle->mtx);
+			handle->engine->analyze(text, offsets, (uint32_t)n, (uint32_t)option.match_options, h->bo);
+		}
+		catch (...) { delete h; throw; }
+		static_assert(sizeof(kiwi_b200_token_t) == sizeof(DToken), "token layout");
+		h->pub.n_sentences = n;
+		h->pub.token_offsets = h->bo.tokOff.data();
+		h->pub.tokens = reinterpret_cast<const kiwi_b200_token_t*>(h->bo.tokens.data());
+		h->pub.scores = h->bo.scores.data();
+		h->pub.status = h->bo.status.data();
+		h->pub.ms_h2d = h->bo.msH2D; h->pub.ms_lattice = h->bo.msLattice; h->pub.ms_viterbi = h->bo.msViterbi; h->pub.ms_pack = h->bo.msPack;
+		h->pub.ms_d2h = h->bo.msD2H; h->pub.ms_total = h->bo.msTotal;
+		return &h->pub;
+	}
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+void kiwi_b200_batch_free(const kiwi_b200_batch_t* batch)
+{
+	if (!batch) return;
+	delete reinterpret_cast<BatchHolder*>(const_cast<kiwi_b200_batch_t*>(batch));
+}
+
+float kiwi_b200_analyze_device(kiwi_h handle, const void* d_text, const void* d_offsets, int n, uint64_t total_units, kiwi_analyze_option_t option, uint64_t* out_tokens, uint64_t* out_launches)
+{
+	if (!handle) { setError("invalid handle"); return -1.f; }
+	try
+	{
+		checkOption(option, 1, nullptr);
+		std::lock_guard<std::mutex> lk(handle->mtx);
+		const float ms = handle->engine->analyzeDevice(reinterpret_cast<const uint16_t*>(d_text), reinterpret_cast<const uint32_t*>(d_offsets), (uint32_t)n, total_units, (uint32_t)option.match_options, out_tokens);
+		if (out_launches) *out_launches = handle->engine->last.kernelLaunches;
+		return ms;
+	}
+	catch (const std::exception& e) { setError(e); return -1.f; }
+}
+
+int kiwi_b200_last_stats(kiwi_h handle, kiwi_b200_stats_t* out)
+{
+	if (!handle || !out) return KIWIERR_INVALID_HANDLE;
+	const Stats& s = handle->engine->last;
+	out->n_sentences = s.nSentences; out->raw_units = s.rawUnits; out->norm_units = s.normUnits; out->lattice_nodes = s.latticeNodes; out->tokens = s.tokens; out->paths = s.paths;
+	out->h2d_bytes = s.h2dBytes; out->d2h_bytes = s.d2hBytes; out->kernel_launches = s.kernelLaunches;
+	out->ms_lattice = s.msLattice; out->ms_viterbi = s.msViterbi; out->ms_pack = s.msPack;
+	return 0;
+}
+
+int kiwi_b200_debug_lattice(kiwi_h handle, const kchar16_t* text, int len, int32_t* out_rows, int max_rows, kiwi_analyze_option_t option)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	try
+	{
+		std::lock_guard<std::mutex> lk(handle->mtx);
+		std::vector<int32_t> rows;
+		const int n = handle->engine->debugLattice(text, (uint32_t)len, (uint32_t)option.match_options, rows);
+		if (n < 0) throw std::runtime_error("lattice build failed with status " + std::to_string(-n));
+		if (n > max_rows) throw std::runtime_error("lattice has more rows than the caller's buffer");
+		std::memcpy(out_rows, rows.data(), rows.size() * 4);
+		return n;
+	}
+	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+
+#pragma GCC visibility pop
+}

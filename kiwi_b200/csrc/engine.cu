@@ -1,0 +1,306 @@
+// kiwi_b200: host engine.  Owns the device-resident model, the per-batch scratch arena and the stream; turns
+// one batch of raw UTF-16 sentences into flat token arrays with exactly three compute launches
+// (lattice_kernel, viterbi_kernel, pack_kernel) plus one cub scan.
+//
+// Host role (the reference does all of this per sentence on CPU threads, src/Kiwi.cpp:1014-1158 and
+// include/kiwi/Kiwi.h:402-454): here the host only copies the text blob + offsets in and the packed
+// tokens out; normalisation, chunking, lattice, Viterbi, stitching and position mapping run on the GPU.
+// Sentences whose scratch demand exceeds the arithmetic capacity (rare, e.g. 50 x the same syllable) are
+// re-run in a second, larger-capacity pass; a sentence that still does not fit is a hard error.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <cub/device/device_scan.cuh>
+#include "engine.h"
+
+namespace kb
+{
+	cudaError_t launch_lattice(const DevModel& m, const BatchView& bv, cudaStream_t stream);
+	cudaError_t launch_viterbi(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
+
+	static void ck(cudaError_t e, const char* what)
+	{
+		if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
+	}
+
+	static constexpr uint32_t DEFAULT_PATHS_PER_UNIT = 48, DEFAULT_PATHS_CONST = 4096;
+
+	__global__ void pack_kernel(uint32_t nSent, const uint32_t* __restrict__ textOff, const uint32_t* __restrict__ nTokens,
+		const uint32_t* __restrict__ tokOff, const DToken* __restrict__ tokens, DToken* __restrict__ packed)
+	{
+		const uint32_t lane = threadIdx.x & 31;
+		const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+		if (s >= nSent) return;
+		const size_t wbase = 2 * (size_t)textOff[s] + 4 * (size_t)s;
+		const uint32_t n = nTokens[s], o = tokOff[s];
+		for (uint32_t i = lane; i < n; i += 32) packed[o + i] = tokens[wbase + i];
+	}
+
+	Engine::Engine(const void* imageBytes, size_t size)
+	{
+		model.load(imageBytes, size);
+		ck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+		for (auto& e : ev) ck(cudaEventCreate(&e), "cudaEventCreate");
+	}
+
+	Engine::~Engine()
+	{
+		freeScratch();
+		if (hPinText) cudaFreeHost(hPinText);
+		if (hPinOff) cudaFreeHost(hPinOff);
+		if (hPinOut) cudaFreeHost(hPinOut);
+		for (auto& e : ev) cudaEventDestroy(e);
+		if (stream) cudaStreamDestroy(stream);
+	}
+
+	void Engine::freeScratch()
+	{
+		for (void* p : sc.bufs) cudaFree(p);
+		sc = Scratch{};
+	}
+
+	void Engine::ensureScratch(size_t U, size_t B, uint32_t ppu, uint32_t pc)
+	{
+		const size_t T = (U - 4 * B) / 2 + 1;
+		if (U <= sc.capUnits && B <= sc.capSent && ppu == sc.pathsPerUnit && pc == sc.pathsConst && T <= sc.capText) return;
+		const size_t capU = std::max(U, sc.capUnits), capB = std::max(B, sc.capSent), capT = std::max(T, sc.capText);
+		freeScratch();
+		const uint32_t npu = KB_DEFAULT_NODES_PER_UNIT;
+		auto alloc = [&](size_t bytes) { void* p = nullptr; ck(cudaMalloc(&p, std::max<size_t>(bytes, 256)), "cudaMalloc(scratch)"); sc.bufs.push_back(p); return p; };
+		BatchView& bv = sc.bv; VitView& vv = sc.vv;
+		bv.nodes_per_unit = npu;
+		bv.norm = (uint16_t*)alloc(capU * 2 + 64);
+		bv.norm_len = (uint32_t*)alloc(capB * 4);
+		bv.pos_table = (uint32_t*)alloc((capT + capB + 1) * 4);
+		bv.ns_to_pos = (uint32_t*)alloc(capU * 4);
+		bv.pos_to_ns = (uint32_t*)alloc(capU * 4);
+		bv.end_pos_map = (uint2*)alloc(capU * 8);
+		bv.ctr = (uint32_t*)alloc(capU * 4);
+		bv.patterns = (DPattern*)alloc(capU * sizeof(DPattern));
+		bv.build_nodes = (DNode*)alloc(capU * npu * sizeof(DNode));
+		bv.nodes = (DNode*)alloc(capU * npu * sizeof(DNode));
+		bv.new_index = (uint32_t*)alloc(capU * npu * 4);
+		const size_t chunkSlots = capU / 4 + 2 * capB + 8;
+		bv.chunks = (DChunk*)alloc(chunkSlots * sizeof(DChunk));
+		bv.n_chunks = (uint32_t*)alloc(capB * 4);
+		bv.status = (uint32_t*)alloc(capB * 4);
+		vv.paths_per_unit = ppu; vv.paths_const = pc;
+		vv.paths = (DPath*)alloc(((size_t)ppu * capU + (size_t)pc * capB) * sizeof(DPath));
+		vv.node_path_off = (uint32_t*)alloc(capU * npu * 4);
+		vv.node_path_cnt = (uint32_t*)alloc(capU * npu * 4);
+		vv.reachable = (uint8_t*)alloc(capU * npu);
+		vv.recs = (DRec*)alloc(2 * chunkSlots * sizeof(DRec));
+		vv.tokens = (DToken*)alloc(capU * sizeof(DToken));
+		vv.n_tokens = (uint32_t*)alloc((capB + 1) * 4);
+		vv.score = (float*)alloc(capB * 4);
+		sc.tokOff = (uint32_t*)alloc((capB + 1) * 4);
+		sc.packed = (DToken*)alloc(capU * sizeof(DToken));
+		sc.dText = (uint16_t*)alloc(capT * 2 + 64);
+		sc.dOff = (uint32_t*)alloc((capB + 1) * 4);
+		size_t tb = 0;
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, vv.n_tokens, sc.tokOff, (int)(capB + 1), stream);
+		sc.cubTempBytes = tb; sc.cubTemp = alloc(tb);
+		sc.capUnits = capU; sc.capSent = capB; sc.capText = capT; sc.pathsPerUnit = ppu; sc.pathsConst = pc;
+	}
+
+	void Engine::bind(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions)
+	{
+		sc.bv.n_sent = n; sc.bv.text = dText; sc.bv.text_off = dOffsets; sc.bv.match_options = matchOptions;
+	}
+
+	void Engine::launchAll(uint32_t n)
+	{
+		ck(cudaEventRecord(ev[1], stream), "event");
+		ck(launch_lattice(model.dev, sc.bv, stream), "lattice_kernel launch");
+		ck(cudaEventRecord(ev[2], stream), "event");
+		ck(launch_viterbi(model.dev, sc.bv, sc.vv, stream), "viterbi_kernel launch");
+		ck(cudaEventRecord(ev[3], stream), "event");
+		ck(cudaMemsetAsync(sc.vv.n_tokens + n, 0, 4, stream), "memset");
+		size_t tb = sc.cubTempBytes;
+		ck(cub::DeviceScan::ExclusiveSum(sc.cubTemp, tb, sc.vv.n_tokens, sc.tokOff, (int)(n + 1), stream), "cub scan");
+		const uint32_t threads = 256, blocks = (n * 32 + threads - 1) / threads;
+		pack_kernel<<<blocks, threads, 0, stream>>>(n, sc.bv.text_off, sc.vv.n_tokens, sc.tokOff, sc.vv.tokens, sc.packed);
+		ck(cudaGetLastError(), "pack_kernel launch");
+		ck(cudaEventRecord(ev[4], stream), "event");
+	}
+
+	static void growPinned(void** p, size_t* cap, size_t bytes)
+	{
+		if (bytes <= *cap) return;
+		if (*p) cudaFreeHost(*p);
+		const size_t nb = std::max(bytes, *cap * 2);
+		ck(cudaMallocHost(p, nb), "cudaMallocHost");
+		*cap = nb;
+	}
+
+	void Engine::analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out)
+	{
+		out = BatchOutput{};
+		out.tokOff.assign(n + 1, 0);
+		out.scores.assign(n, 0.f);
+		out.status.assign(n, 0);
+		last = Stats{};
+		if (n == 0) return;
+		if (offsets[0] != 0) throw std::runtime_error("offsets[0] must be 0");
+		const size_t T = offsets[n];
+		for (uint32_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) throw std::runtime_error("offsets must be non-decreasing");
+		if (T >= (1ull << 31)) throw std::runtime_error("batch too large (>= 2^31 UTF-16 units); split it");
+
+		struct Pass { std::vector<uint32_t> ids; uint32_t ppu, pc; };
+		// pass 0: everything with the default capacity; pass 1: overflowed sentences with 16 x the path capacity
+		std::vector<uint32_t> failed;
+		for (int pass = 0; pass < 2; ++pass)
+		{
+			std::vector<uint16_t> subText; std::vector<uint32_t> subOff;
+			const uint16_t* ptext = text; const uint32_t* poff = offsets; uint32_t pn = n;
+			uint32_t ppu = DEFAULT_PATHS_PER_UNIT, pc = DEFAULT_PATHS_CONST;
+			if (pass == 1)
+			{
+				if (failed.empty()) break;
+				subOff.push_back(0);
+				for (uint32_t id : failed)
+				{
+					subText.insert(subText.end(), text + offsets[id], text + offsets[id + 1]);
+					subOff.push_back((uint32_t)subText.size());
+				}
+				ptext = subText.data(); poff = subOff.data(); pn = (uint32_t)failed.size();
+				ppu *= 16; pc *= 16;
+			}
+			const size_t pT = poff[pn];
+			const size_t U = 2 * pT + 4 * (size_t)pn;
+			ensureScratch(U, pn, ppu, pc);
+			growPinned((void**)&hPinText, &pinTextCap, pT * 2 + 64);
+			growPinned((void**)&hPinOff, &pinOffCap, ((size_t)pn + 1) * 4);
+			std::memcpy(hPinText, ptext, pT * 2);
+			std::memcpy(hPinOff, poff, ((size_t)pn + 1) * 4);
+			ck(cudaEventRecord(ev[0], stream), "event");
+			ck(cudaMemcpyAsync(sc.dText, hPinText, pT * 2, cudaMemcpyHostToDevice, stream), "H2D text");
+			ck(cudaMemcpyAsync(sc.dOff, hPinOff, ((size_t)pn + 1) * 4, cudaMemcpyHostToDevice, stream), "H2D offsets");
+			bind(sc.dText, sc.dOff, pn, matchOptions);
+			launchAll(pn);
+			// D2H: offsets + scores + status first, then exactly the packed tokens
+			const size_t headBytes = ((size_t)pn + 1) * 4 + (size_t)pn * 4 * 2;
+			growPinned(&hPinOut, &pinOutCap, headBytes);
+			uint32_t* hTokOff = (uint32_t*)hPinOut; float* hScore = (float*)(hTokOff + pn + 1); uint32_t* hStatus = (uint32_t*)(hScore + pn);
+			ck(cudaMemcpyAsync(hTokOff, sc.tokOff, ((size_t)pn + 1) * 4, cudaMemcpyDeviceToHost, stream), "D2H offsets");
+			ck(cudaMemcpyAsync(hScore, sc.vv.score, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H scores");
+			ck(cudaMemcpyAsync(hStatus, sc.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H status");
+			ck(cudaStreamSynchronize(stream), "sync (a kernel fault surfaces here)");
+			const uint32_t total = hTokOff[pn];
+			std::vector<DToken> toks(total);
+			std::vector<uint32_t> tokOffCopy(hTokOff, hTokOff + pn + 1);
+			std::vector<float> scoreCopy(hScore, hScore + pn);
+			std::vector<uint32_t> statusCopy(hStatus, hStatus + pn);
+			if (total)
+			{
+				growPinned(&hPinOut, &pinOutCap, (size_t)total * sizeof(DToken));
+				ck(cudaMemcpyAsync(hPinOut, sc.packed, (size_t)total * sizeof(DToken), cudaMemcpyDeviceToHost, stream), "D2H tokens");
+			}
+			ck(cudaEventRecord(ev[5], stream), "event");
+			ck(cudaStreamSynchronize(stream), "sync");
+			if (total) std::memcpy(toks.data(), hPinOut, (size_t)total * sizeof(DToken));
+			float ms;
+			cudaEventElapsedTime(&ms, ev[0], ev[1]); out.msH2D += ms;
+			cudaEventElapsedTime(&ms, ev[1], ev[2]); out.msLattice += ms;
+			cudaEventElapsedTime(&ms, ev[2], ev[3]); out.msViterbi += ms;
+			cudaEventElapsedTime(&ms, ev[3], ev[4]); out.msPack += ms;
+			cudaEventElapsedTime(&ms, ev[4], ev[5]); out.msD2H += ms;
+			cudaEventElapsedTime(&ms, ev[0], ev[5]); out.msTotal += ms;
+			last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4;
+			last.d2hBytes += headBytes + (size_t)total * sizeof(DToken);
+			last.kernelLaunches += 3;
+
+			if (pass == 0)
+			{
+				out.tokens = std::move(toks);
+				out.tokOff = std::move(tokOffCopy);
+				out.scores = std::move(scoreCopy);
+				out.status = std::move(statusCopy);
+				for (uint32_t i = 0; i < n; ++i) if (out.status[i]) failed.push_back(i);
+			}
+			else
+			{
+				// splice the re-run sentences back in order
+				std::vector<DToken> merged; merged.reserve(out.tokens.size() + toks.size());
+				std::vector<uint32_t> newOff(n + 1, 0);
+				size_t fi = 0;
+				for (uint32_t i = 0; i < n; ++i)
+				{
+					newOff[i] = (uint32_t)merged.size();
+					if (fi < failed.size() && failed[fi] == i)
+					{
+						merged.insert(merged.end(), toks.begin() + tokOffCopy[fi], toks.begin() + tokOffCopy[fi + 1]);
+						out.scores[i] = scoreCopy[fi]; out.status[i] = statusCopy[fi];
+						++fi;
+					}
+					else merged.insert(merged.end(), out.tokens.begin() + out.tokOff[i], out.tokens.begin() + out.tokOff[i + 1]);
+				}
+				newOff[n] = (uint32_t)merged.size();
+				out.tokens = std::move(merged); out.tokOff = std::move(newOff);
+			}
+		}
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			if (out.status[i])
+			{
+				throw std::runtime_error("sentence " + std::to_string(i) + " exceeded the device scratch capacity (status " + std::to_string(out.status[i]) + ")");
+			}
+		}
+		last.nSentences = n; last.rawUnits = T; last.tokens = out.tokens.size();
+		last.msLattice = out.msLattice; last.msViterbi = out.msViterbi; last.msPack = out.msPack;
+	}
+
+	float Engine::analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens)
+	{
+		const size_t U = 2 * (size_t)totalUnits + 4 * (size_t)n;
+		ensureScratch(U, n, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST);
+		bind(dText, dOffsets, n, matchOptions);
+		launchAll(n);
+		uint32_t total = 0;
+		ck(cudaMemcpyAsync(&total, sc.tokOff + n, 4, cudaMemcpyDeviceToHost, stream), "D2H total");
+		ck(cudaStreamSynchronize(stream), "sync (a kernel fault surfaces here)");
+		float ms = 0, a = 0;
+		cudaEventElapsedTime(&ms, ev[1], ev[4]);
+		cudaEventElapsedTime(&a, ev[1], ev[2]); last.msLattice = a;
+		cudaEventElapsedTime(&a, ev[2], ev[3]); last.msViterbi = a;
+		cudaEventElapsedTime(&a, ev[3], ev[4]); last.msPack = a;
+		last.nSentences = n; last.rawUnits = totalUnits; last.tokens = total; last.kernelLaunches = 3; last.h2dBytes = 0; last.d2hBytes = 4;
+		if (nTokens) *nTokens = total;
+		return ms;
+	}
+
+	int Engine::debugLattice(const uint16_t* text, uint32_t len, uint32_t matchOptions, std::vector<int32_t>& rows)
+	{
+		const uint32_t off[2] = { 0, len };
+		const size_t U = 2 * (size_t)len + 4;
+		ensureScratch(U, 1, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST);
+		ck(cudaMemcpyAsync(sc.dText, text, (size_t)len * 2, cudaMemcpyHostToDevice, stream), "H2D");
+		ck(cudaMemcpyAsync(sc.dOff, off, 8, cudaMemcpyHostToDevice, stream), "H2D");
+		bind(sc.dText, sc.dOff, 1, matchOptions);
+		ck(launch_lattice(model.dev, sc.bv, stream), "lattice launch");
+		uint32_t nChunks = 0, status = 0;
+		ck(cudaMemcpyAsync(&nChunks, sc.bv.n_chunks, 4, cudaMemcpyDeviceToHost, stream), "D2H");
+		ck(cudaMemcpyAsync(&status, sc.bv.status, 4, cudaMemcpyDeviceToHost, stream), "D2H");
+		ck(cudaStreamSynchronize(stream), "sync");
+		if (status) return -(int)status;
+		std::vector<DChunk> chunks(nChunks);
+		if (nChunks) ck(cudaMemcpy(chunks.data(), sc.bv.chunks, nChunks * sizeof(DChunk), cudaMemcpyDeviceToHost), "D2H chunks");
+		rows.clear();
+		int total = 0;
+		for (uint32_t c = 0; c < nChunks; ++c)
+		{
+			std::vector<DNode> nodes(chunks[c].n_nodes);
+			ck(cudaMemcpy(nodes.data(), sc.bv.nodes + chunks[c].node_off, nodes.size() * sizeof(DNode), cudaMemcpyDeviceToHost), "D2H nodes");
+			for (auto& nd : nodes)
+			{
+				const int32_t r[9] = { nd.form, nd.uform_len ? (int32_t)nd.uform_off : -1, (int32_t)nd.uform_len, nd.prev, nd.sibling,
+					(int32_t)nd.start_pos, (int32_t)nd.end_pos, nd.space_errors, (int32_t)c };
+				rows.insert(rows.end(), r, r + 9);
+				++total;
+			}
+		}
+		return total;
+	}
+}

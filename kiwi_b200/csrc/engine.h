@@ -1,0 +1,81 @@
+// kiwi_b200: host engine (model residency, batch marshalling, kernel launches, result packing).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "kb_model.h"
+#include "kb_batch.h"
+
+namespace kb
+{
+	std::vector<char> readImageFile(const std::string& modelPath);
+
+	struct Model
+	{
+		std::vector<char> blob;
+		kb2_header header;
+		DevModel dev;
+		std::vector<void*> owned;
+		size_t deviceBytes = 0;
+		const kb2_form* hForms = nullptr; const uint16_t* hFormChars = nullptr; const kb2_morph* hMorphs = nullptr;
+		void load(const void* bytes, size_t size);
+		~Model();
+	};
+
+	struct BatchOutput
+	{
+		std::vector<uint32_t> tokOff;      // [n + 1]
+		std::vector<DToken> tokens;
+		std::vector<float> scores;
+		std::vector<uint32_t> status;
+		float msH2D = 0, msLattice = 0, msViterbi = 0, msPack = 0, msD2H = 0, msTotal = 0;
+	};
+
+	struct Stats
+	{
+		uint64_t nSentences = 0, rawUnits = 0, normUnits = 0, latticeNodes = 0, tokens = 0, paths = 0;
+		uint64_t h2dBytes = 0, d2hBytes = 0, kernelLaunches = 0;
+		float msLattice = 0, msViterbi = 0, msPack = 0;
+	};
+
+	class Engine
+	{
+	public:
+		Model model;
+		cudaStream_t stream = nullptr;
+		Stats last;
+
+		explicit Engine(const void* imageBytes, size_t size);
+		~Engine();
+
+		// host buffers in, host buffers out (H2D / D2H inside)
+		void analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out);
+		// device-resident inputs; results stay on the device.  returns elapsed ms
+		float analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens);
+		// lattice of one sentence for stage-level parity tests
+		int debugLattice(const uint16_t* text, uint32_t len, uint32_t matchOptions, std::vector<int32_t>& rows);
+
+	private:
+		struct Scratch
+		{
+			size_t capUnits = 0, capSent = 0, capText = 0;
+			uint32_t pathsPerUnit = 0, pathsConst = 0;
+			std::vector<void*> bufs;
+			BatchView bv{};
+			VitView vv{};
+			uint32_t* tokOff = nullptr;      // [capSent + 1]
+			DToken* packed = nullptr;        // [capUnits]
+			void* cubTemp = nullptr; size_t cubTempBytes = 0;
+			uint16_t* dText = nullptr; uint32_t* dOff = nullptr;
+		} sc;
+		cudaEvent_t ev[6];
+		uint16_t* hPinText = nullptr; uint32_t* hPinOff = nullptr; size_t pinTextCap = 0, pinOffCap = 0;
+		void* hPinOut = nullptr; size_t pinOutCap = 0;
+
+		void ensureScratch(size_t totalUnits, size_t nSent, uint32_t pathsPerUnit, uint32_t pathsConst);
+		void freeScratch();
+		void bind(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions);
+		void launchAll(uint32_t n);
+	};
+}

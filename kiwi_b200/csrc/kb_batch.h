@@ -1,0 +1,90 @@
+// kiwi_b200: device batch layout.  One batch = B sentences (raw UTF-16, concatenated) + per-sentence scratch.
+// All per-sentence regions are addressed arithmetically from the raw-text offsets, so no offset tables other
+// than `text_off` travel to the device:
+//   n_s   = text_off[s+1] - text_off[s]             raw length
+//   W_s   = 2 * n_s + 4                              capacity in normalized code units (every syllable may split)
+//   wbase = 2 * text_off[s] + 4 * s                  start of the W-sized regions of sentence s
+//   NC_s  = nodes_per_unit * W_s                     lattice-node capacity; nbase = nodes_per_unit * wbase
+#pragma once
+#include <stdint.h>
+
+namespace kb
+{
+	constexpr uint32_t KB_DEFAULT_NODES_PER_UNIT = 12;
+	constexpr uint32_t KB_MAX_CHUNKS_SHIFT = 2;      // chunk capacity = W_s >> 2 (a chunk has >= 4 units) + 2
+
+	struct DNode          // 32 B lattice node (KGraphNode, /root/reference/src/KTrie.h:57-77, index based)
+	{
+		int32_t form;            // form index, -1 = none
+		uint32_t uform_off;      // offset into the sentence's normalized text (valid when uform_len > 0)
+		uint32_t uform_len;
+		uint32_t start_pos, end_pos;   // non-space coordinates while building, normalized-text offsets in the final lattice
+		uint16_t prev, sibling;  // relative offsets exactly as the reference: prev = back-offset to the first predecessor
+		uint16_t space_errors;
+		uint16_t reserved;
+		float typo_cost;
+	};
+
+	struct DChunk { uint32_t start, end, node_off, n_nodes; };   // normalized offsets [start,end), nodes in the final lattice region
+
+	struct DPattern { uint32_t end, len, tag; };
+
+	struct DPath          // 48 B search path (WordLL, /root/reference/src/BestPathContainer.hpp:21-67), index based
+	{
+		int32_t lm_state; float acc_score; float first_chunk_score; uint32_t wid;
+		int32_t morpheme; uint32_t parent; uint32_t own_off; float acc_typo_cost;
+		uint16_t own_len;        // own form (ownFormId != 0): own_off >= 0 -> normalized text offset, own_off has bit 31 -> ~form index
+		uint16_t node;           // lattice node (chunk relative) this path ends at
+		uint16_t left_last;      // last code unit of the left form seen by FormEvaluator
+		uint8_t left_pol;        // LP_* bits
+		uint8_t sp_state;        // SpecialState
+		uint8_t root_id, combine_socket, prev_root_id, morph_tag;
+		uint32_t wid_feat;       // DMorph::feat of morphemes[wid]
+	};
+	enum : uint8_t { LP_POLAR_POS = 1, LP_POLAR_NEG = 2, LP_LAST_SSC = 4, LP_EMPTY = 8, LP_MORPH_SOCKET = 128 };
+
+	struct DToken { uint32_t morph; uint32_t position; float score; uint16_t length; uint8_t tag; uint8_t flags; };
+
+	struct DRec { int32_t parent_rec; uint32_t end_parent; uint32_t chunk; float score; };
+
+	struct VitView
+	{
+		uint32_t paths_per_unit, paths_const;   // path capacity of sentence s = paths_per_unit * W_s + paths_const
+		DPath* paths;                // pool, index pbase = paths_per_unit * wbase + paths_const * s
+		uint32_t* node_path_off;     // per lattice node (nbase + chunk.node_off + i)
+		uint32_t* node_path_cnt;
+		uint8_t* reachable;          // per lattice node
+		DRec* recs;                  // 2 per chunk slot: 2 * ((wbase >> 2) + 2 * s)
+		DToken* tokens;              // output, W_s per sentence at wbase
+		uint32_t* n_tokens;          // [n_sent]
+		float* score;                // [n_sent]
+	};
+
+	enum : uint32_t { ST_OK = 0, ST_NODE_OVERFLOW = 1, ST_CHUNK_OVERFLOW = 2, ST_PATH_OVERFLOW = 3, ST_TOKEN_OVERFLOW = 4, ST_TOO_LONG = 5, ST_INTERNAL = 6 };
+
+	struct BatchView
+	{
+		uint32_t n_sent;
+		const uint16_t* text;        // raw UTF-16
+		const uint32_t* text_off;    // [n_sent + 1]
+		uint32_t match_options;      // kiwi::Match bits (include/kiwi/PatternMatcher.h:10-45)
+		uint32_t nodes_per_unit;
+		// W-sized scratch (index wbase + i)
+		uint16_t* norm;              // normalized text
+		uint32_t* norm_len;          // [n_sent]
+		uint32_t* pos_table;         // raw index -> normalized index, n_s + 1 entries at text_off[s] + s
+		uint32_t* ns_to_pos;
+		uint32_t* pos_to_ns;
+		uint2* end_pos_map;
+		uint32_t* ctr;               // counting-sort scratch
+		DPattern* patterns;
+		// node regions (index nbase + i)
+		DNode* build_nodes;          // insertion-ordered nodes of the chunk being built
+		DNode* nodes;                // final lattices of all chunks of the sentence, concatenated
+		uint32_t* new_index;         // build index -> final index
+		// chunk table: (wbase >> 2) + 2 * s
+		DChunk* chunks;
+		uint32_t* n_chunks;          // [n_sent]
+		uint32_t* status;            // [n_sent]
+	};
+}

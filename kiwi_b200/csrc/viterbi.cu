@@ -1,0 +1,1196 @@
+// kiwi_b200 kernel B: pruned Viterbi over the morpheme lattice with Knlm scoring, one warp per sentence.
+//
+// Replaces (reference file:line under /root/reference/):
+//   BestPathFinder<KnLangModel>::findBestPath (topN == 1)   src/PathEvaluator.hpp:1178-1419
+//   PathEvaluator::operator() / evalSingleMorpheme           src/PathEvaluator.hpp:347-634
+//   RuleBasedScorer, insertToPathContainer, FormEvaluator    src/PathEvaluator.hpp:88-311
+//   BucketedHashContainer (top1Small / top1Medium)           src/BestPathContainer.hpp:291-483
+//   KnLangModel::progress                                    src/Knlm.cpp:44-130
+//   UnkFormScorer::ruleBasedScore                            src/UnkFormScorer.cpp:28-51
+//   generateTokenList, isDisconnected                        src/PathEvaluator.hpp:1038-1176
+//   chunk loop + insertPathIntoResults (selection part)      src/Kiwi.cpp:1095-1141, 615-783
+//
+// Parallel mapping.  Lattice nodes are visited in index (= end position) order.  Because kernel A emits the
+// nodes that end at one position contiguously and every node appends its surviving paths to one pool, the
+// incoming paths of a node are ONE contiguous pool range.  For each candidate morpheme the lanes take the
+// incoming paths 32 at a time ("pairs"): filters, Knlm progress (a per-lane pointer chase with binary
+// searches), rule scores.  The reference's per-(node, candidate) de-duplication container is reproduced with
+// warp primitives: __match_any groups equal (lmState, prevRootId, spState) keys inside a round, a redux picks
+// the best score (earliest pair wins ties, like the reference's strict '>'), a shared-memory open-addressing
+// table finds keys inserted by earlier rounds, and new keys are appended in pair order so that the output
+// order - which fixes all later tie-breaks - is the reference's insertion order (bucket-major in the
+// 4 x 128 "medium" mode).  Pruning is a warp max-reduction followed by a ballot compaction.
+// Compile with -fmad=false: the reference's float sums are not contracted (x86-64 baseline, no FMA).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "kb_model.h"
+#include "kb_batch.h"
+
+namespace kb
+{
+	static constexpr unsigned FULL = 0xFFFFFFFFu;
+	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
+	static constexpr uint8_t COMMON_ROOT = 0xFF;
+	static constexpr uint32_t HT_SIZE = 1024, HT_MAX_ENTRIES = 768;
+	static constexpr uint32_t WARPS_PER_BLOCK = 4;
+	static constexpr uint32_t MAX_RESULTS = 16;
+
+	__device__ __forceinline__ float asFloat(int32_t v) { return __int_as_float(v); }
+
+	// ---- KnLangModel::progress, src/Knlm.cpp:44-130 (one lane) -------------------------------------
+	__device__ __forceinline__ bool knSearch(const DevModel& m, const kb2_kn_node& n, uint32_t key, int32_t& v)
+	{
+		uint32_t lo = 0, hi = n.num_nexts;
+		const uint32_t* keys = m.kn_keys + n.next_offset;
+		while (lo < hi)
+		{
+			const uint32_t mid = (lo + hi) >> 1;
+			if (keys[mid] < key) lo = mid + 1; else hi = mid;
+		}
+		if (lo == n.num_nexts || keys[lo] != key) return false;
+		v = m.kn_values[n.next_offset + lo];
+		return true;
+	}
+	__device__ __forceinline__ kb2_kn_node knNode(const DevModel& m, int32_t idx)
+	{
+		const kb2_kn_node* p = m.kn_nodes + idx;
+		kb2_kn_node n;
+		n.num_nexts = p->num_nexts; n.lower = p->lower; n.next_offset = p->next_offset; n.ll = p->ll; n.gamma = p->gamma;
+		return n;
+	}
+	__device__ float knProgress(const DevModel& m, int32_t& nodeIdx, uint32_t next)
+	{
+		float acc = 0;
+		while (true)
+		{
+			int32_t v;
+			const kb2_kn_node node = knNode(m, nodeIdx);
+			if (nodeIdx == 0)
+			{
+				v = m.kn_root[next];
+				if (v == 0)
+				{
+					if (m.kn_htx) nodeIdx = m.kn_root[m.kn_htx[next]];
+					return acc + m.kn_unk_ll;
+				}
+			}
+			else
+			{
+				if (!knSearch(m, node, next, v))
+				{
+					acc += node.gamma;
+					nodeIdx += node.lower;
+					continue;
+				}
+			}
+			if (v > 0)
+			{
+				nodeIdx += v;
+				return acc + m.kn_nodes[nodeIdx].ll;
+			}
+			// leaf: next state = deepest suffix state that continues with `next`
+			int32_t cur = nodeIdx;
+			kb2_kn_node nd = node;
+			while (nd.lower)
+			{
+				cur += nd.lower;
+				nd = knNode(m, cur);
+				int32_t lv;
+				const bool found = cur == 0 ? ((lv = m.kn_root[next]) != 0) : knSearch(m, nd, next, lv);
+				if (found && lv > 0)
+				{
+					nodeIdx = cur + lv;
+					return acc + asFloat(v);
+				}
+			}
+			nodeIdx = m.kn_htx ? m.kn_root[m.kn_htx[next]] : 0;
+			return acc + asFloat(v);
+		}
+	}
+
+	// ------------------------------------------------------------------------------------------------
+	struct PathRes { float score; uint32_t endParent; uint8_t prevState, curState; };
+
+	struct Vit
+	{
+		const DevModel& m;
+		const BatchView& bv;
+		const VitView& vv;
+		const uint32_t lane;
+		uint32_t err = 0;
+		// sentence
+		const uint16_t* norm;
+		DPath* pool; uint32_t poolCap, top;
+		// chunk
+		const DNode* nodes; uint32_t N;
+		uint32_t* npOff; uint32_t* npCnt; uint8_t* reach;
+		uint8_t uniq[2]; uint32_t nUniq;
+		uint16_t* ht; uint32_t htUsed;
+		bool splitComplex, splitSaisiot, mergeSaisiot;
+
+		__device__ Vit(const DevModel& _m, const BatchView& _bv, const VitView& _vv, uint32_t _lane) : m{ _m }, bv{ _bv }, vv{ _vv }, lane{ _lane } {}
+
+		// ---- left-form features of a path (what FormEvaluator will see), uniform per candidate ------
+		__device__ void leftFeat(uint32_t ownOff, uint32_t ownLen, uint32_t wid, int32_t morpheme, uint16_t& last, uint8_t& pol) const
+		{
+			pol = 0; last = 0;
+			if (ownLen)
+			{
+				if (ownOff & 0x80000000u)
+				{
+					const DForm f = m.forms[~ownOff];
+					last = f.last_chr;
+					pol = (f.pol & (FP_POLAR_POS | FP_POLAR_NEG | FP_LAST_SSC));
+				}
+				else
+				{
+					const uint16_t* p = norm + ownOff;
+					last = p[ownLen - 1];
+					if (ftPolar(p, ownLen, CP_positive)) pol |= LP_POLAR_POS;
+					if (ftPolar(p, ownLen, CP_negative)) pol |= LP_POLAR_NEG;
+					if (attrCls(m.chr_bmp[last]) == T_ssc) pol |= LP_LAST_SSC;
+				}
+				return;
+			}
+			int32_t fi = m.morphs[wid].form_idx;
+			if (!(fi >= 0 && m.forms[fi].str_len)) fi = m.morphs[morpheme].form_idx;
+			if (fi < 0 || m.forms[fi].str_len == 0) { pol = LP_EMPTY | LP_POLAR_POS | LP_POLAR_NEG; return; }
+			const DForm f = m.forms[fi];
+			last = f.last_chr;
+			pol = (f.pol & (FP_POLAR_POS | FP_POLAR_NEG | FP_LAST_SSC));
+		}
+
+		// ---- UnkFormScorer::ruleBasedScore, src/UnkFormScorer.cpp:28-51 ------------------------------
+		template<class Ptr>
+		__device__ float unkFormScore(Ptr form, uint32_t len) const
+		{
+			float penalty = 0;
+			if (len > 0)
+			{
+				uint32_t chrs[2] = { 0, 0 };
+				for (uint32_t i = 0, j = 0; i < len && j < 2; ++j)
+				{
+					if (isHighSurrogate(form[i])) { chrs[j] = mergeSurrogate(form[i], i + 1 < len ? form[i + 1] : 0); i += 2; }
+					else { chrs[j] = form[i]; ++i; }
+				}
+				if (isEmoji(m, chrs[0], chrs[1])) penalty = -10.f;
+			}
+			return penalty - ((float)len * m.cfg.oov_rule_scale + m.cfg.oov_rule_bias);
+		}
+
+		// PathEvaluator.hpp:22-44
+		__device__ bool hasLeftBoundary(uint32_t i) const
+		{
+			const DNode nd = nodes[i];
+			const DNode pv = nodes[i - nd.prev];
+			if (pv.end_pos == 0) return true;
+			if (pv.end_pos < nd.start_pos) return true;
+			if (pv.uform_len)
+			{
+				const uint32_t c = norm[pv.uform_off + pv.uform_len - 1];
+				const uint32_t tag = attrCls(m.chr_bmp[c]);
+				if (tag == T_ssc || c == '"' || c == '\'') return false;
+				if (T_sf <= tag && tag <= T_sb) return true;
+			}
+			return false;
+		}
+
+		__device__ void htClear()
+		{
+			if (!htUsed) return;
+			for (uint32_t i = lane; i < HT_SIZE / 2; i += 32) reinterpret_cast<uint32_t*>(ht)[i] = 0;
+			htUsed = 0;
+			__syncwarp();
+		}
+		static __device__ __forceinline__ uint32_t htHash(int32_t lm, uint32_t prevRoot, uint32_t sp)
+		{
+			uint32_t h = (uint32_t)lm * 0x9E3779B1u ^ (prevRoot * 0x85EBCA6Bu) ^ (sp * 0xC2B2AE35u);
+			h ^= h >> 15;
+			return h & (HT_SIZE - 1);
+		}
+
+		// ---- evalSingleMorpheme, PathEvaluator.hpp:514-634 -------------------------------------------
+		struct CandCtx
+		{
+			int32_t curId; DMorph cur; bool single;
+			uint32_t firstWid0, lastSeqId;
+			float additionalScore, ignoreCondScore;
+			uint32_t specialType, sbType, sbOrder; bool positiveE, snEndswithPoint, fork;
+			uint32_t ownOff, ownLen;
+			uint16_t leftLast; uint8_t leftPol; uint8_t morphTag; uint32_t widFeat; uint8_t pathSocket;
+			bool spaceBefore;
+		};
+
+		__device__ void evalCand(uint32_t nodeIdx, const DNode& node, const CandCtx& cc, uint32_t inBeg, uint32_t inEnd, uint32_t mode)
+		{
+			const uint32_t P = inEnd - inBeg;
+			const uint32_t nRoot = cc.fork ? nUniq : 1;
+			const uint32_t pairsPerRound = 32 / nRoot;
+			const uint32_t candBeg = top;
+			uint32_t E = 0;                           // entries of this candidate (all buckets)
+			uint32_t bucketCnt[4] = { 0, 0, 0, 0 };
+			uint32_t fwCarry = cc.firstWid0;
+			htClear();
+			const bool allowedSpaceBetweenChunk = m.cfg.space_tolerance > 0;
+
+			for (uint32_t qb = 0; qb < P; qb += pairsPerRound)
+			{
+				const uint32_t pr = lane / nRoot, rr = lane % nRoot;
+				const uint32_t q = qb + pr;
+				bool valid = pr < pairsPerRound && q < P;
+				DPath pp;
+				if (valid) pp = pool[inBeg + q];
+				float candScore = 0, firstChunkScore = 0;
+				bool setsFW = false; uint32_t fwVal = 0;
+				if (valid)
+				{
+					if (pp.morph_tag == T_z_siot && (!isNNClass(cc.cur.feat & MF_TAG_MASK) || cc.spaceBefore)) valid = false;
+				}
+				if (valid)
+				{
+					candScore = pp.acc_score + cc.additionalScore;
+					firstChunkScore = cc.additionalScore;
+					if (pp.combine_socket)
+					{
+						if (pp.combine_socket != cc.cur.combine_socket || cc.single) valid = false;
+						else if (cc.spaceBefore)
+						{
+							if (allowedSpaceBetweenChunk) candScore -= m.cfg.space_penalty;
+							else valid = false;
+						}
+						if (valid)
+						{
+							setsFW = true;
+							const DMorph pw = m.morphs[pp.wid];
+							fwVal = m.morphs[(int32_t)pp.wid + pw.combined].lm_id;
+						}
+					}
+				}
+				// the reference mutates `firstWid` in place (PathEvaluator.hpp:590): later pairs inherit it
+				uint32_t firstWid;
+				{
+					const unsigned smask = __ballot_sync(FULL, setsFW);
+					const unsigned le = smask & (lane == 31 ? FULL : ((2u << lane) - 1));
+					const int src = le ? 31 - __clz(le) : 0;
+					const uint32_t got = __shfl_sync(FULL, fwVal, src);
+					firstWid = le ? got : fwCarry;
+					if (smask) fwCarry = __shfl_sync(FULL, fwVal, 31 - __clz(smask));
+				}
+				if (valid)
+				{
+					// FormEvaluator, PathEvaluator.hpp:253-311
+					const bool empty = (pp.left_pol & LP_EMPTY) != 0;
+					if (pp.morph_tag == T_ssc || (pp.left_pol & LP_LAST_SSC)) {}
+					else
+					{
+						const uint32_t cv = (cc.cur.feat >> MF_VOWEL_SHIFT) & 15, cp = (cc.cur.feat >> MF_POLAR_SHIFT) & 3;
+						bool ok = ftVowel(empty, pp.left_last, (uint8_t)cv);
+						if (ok && (cp == CP_positive || cp == CP_negative))
+						{
+							ok = empty ? true : ((pp.left_pol & (cp == CP_positive ? LP_POLAR_POS : LP_POLAR_NEG)) != 0);
+						}
+						if (cc.ignoreCondScore != 0.f) candScore += ok ? 0.f : cc.ignoreCondScore;
+						else if (!ok) valid = false;
+					}
+				}
+				int32_t lmState = 0;
+				if (valid)
+				{
+					lmState = pp.lm_state;
+					if (cc.cur.combine_socket && cc.single) {}
+					else
+					{
+						if ((m.morphs[firstWid].feat & MF_TAG_MASK) == T_p) valid = false;
+						else
+						{
+							float ll = knProgress(m, lmState, firstWid);
+							candScore += ll;
+							firstChunkScore += ll;
+							if (!cc.single)
+							{
+								for (uint32_t i = 1; i < cc.cur.chunk_cnt; ++i)
+								{
+									const uint32_t wid = m.morphs[m.chunks[cc.cur.chunk_off + i].morph].lm_id;
+									if ((m.morphs[wid].feat & MF_TAG_MASK) == T_p) { valid = false; break; }
+									ll = knProgress(m, lmState, wid);
+									candScore += ll;
+								}
+							}
+						}
+					}
+				}
+				// insertToPathContainer, PathEvaluator.hpp:193-251
+				uint8_t spState = 0, rootId = COMMON_ROOT;
+				float accScore = 0, fcs = 0;
+				if (valid)
+				{
+					const bool doFork = cc.fork && pp.root_id == COMMON_ROOT;
+					if (!doFork && rr != 0) valid = false;
+					else
+					{
+						rootId = doFork ? (uint8_t)rr : COMMON_ROOT;
+						spState = doFork ? uniq[rr] : pp.sp_state;
+						// RuleBasedScorer::operator(), PathEvaluator.hpp:115-183
+						const uint32_t pf = pp.wid_feat;
+						const uint32_t ptag = pf & MF_TAG_MASK;
+						float rs = 0;
+						if ((cc.cur.feat & MF_VOWEL_E) && isIrregular((uint8_t)ptag)) rs -= 10;
+						if ((cc.cur.feat & MF_INF_J) && (pf & MF_INFL_NP)) rs -= 5;
+						if ((cc.cur.feat & MF_BADPAIR_L) && (pf & MF_VERB_L)) rs -= 7;
+						if (cc.positiveE && !(pf & MF_POS_VERB)) rs -= 100;
+						if ((cc.cur.feat & MF_CONTRACT_E) && (pf & MF_VERB_VOWEL)) rs -= 3;
+						if (((cc.cur.feat >> MF_POLAR_SHIFT) & 3) == CP_non_adj && (ptag == T_va || ptag == T_xsa)) rs -= 10;
+						const uint32_t sq = spState & 1, dq = (spState >> 1) & 1, bh = spState >> 2;
+						if (cc.specialType <= 2) { if (cc.specialType != sq) rs -= 2; }
+						else if (cc.specialType <= 5) { if (cc.specialType - 3 != dq) rs -= 2; }
+						if (cc.sbType == 5) rs -= 5;
+						if (cc.sbType && isEClass((uint8_t)ptag) && ptag != T_ef) rs -= 10;
+						if (cc.sbType && bh == hashSbTypeOrder((uint8_t)cc.sbType, (uint8_t)cc.sbOrder)) rs += 3;
+						if (cc.snEndswithPoint && (ptag == T_unknown || ptag == T_ef || ptag == T_sf)) rs -= 5;
+						accScore = candScore + rs;
+						fcs = firstChunkScore + rs;
+						if (cc.specialType == 0) spState |= 1;
+						else if (cc.specialType == 1) spState &= ~1;
+						else if (cc.specialType == 3) spState |= 2;
+						else if (cc.specialType == 4) spState &= ~2;
+						if (cc.sbType) spState = (spState & 3) | (uint8_t)(hashSbTypeOrder((uint8_t)cc.sbType, (uint8_t)(cc.sbOrder + 1)) << 2);
+						accScore = accScore - 0.f;      // curDialectCost (standard dialect only)
+						fcs = fcs - 0.f;
+					}
+				}
+
+				// ---- warp-cooperative BucketedHashContainer::insert for the (<= 32) items of this round
+				const uint32_t prevRoot = pp.root_id;
+				const unsigned vmask = __ballot_sync(FULL, valid);
+				if (!vmask) continue;
+				const unsigned long long key = valid
+					? ((unsigned long long)(uint32_t)lmState | ((unsigned long long)prevRoot << 32) | ((unsigned long long)spState << 40))
+					: (0xFFFF000000000000ull | lane);
+				const unsigned grp = __match_any_sync(FULL, key);
+				// best of the group: max score, earliest lane on ties
+				uint32_t ord = __float_as_uint(accScore);
+				ord = (ord & 0x80000000u) ? ~ord : (ord | 0x80000000u);
+				const uint32_t gmax = __reduce_max_sync(grp, ord);
+				const unsigned bestMask = __ballot_sync(FULL, valid && ord == gmax) & grp;
+				const uint32_t bestLane = __ffs(bestMask) - 1;
+				const uint32_t leader = __ffs(grp) - 1;
+				const bool isLeader = valid && lane == leader;
+				// lookup among the entries of earlier rounds
+				uint32_t found = NPOS;
+				const uint32_t bucket = mode == 1 ? ((spState ^ ((uint32_t)lmState >> 5)) & 3) : 0;
+				if (isLeader && E)
+				{
+					uint32_t slot = htHash(lmState, prevRoot, spState);
+					while (true)
+					{
+						const uint32_t e = ht[slot];
+						if (!e) break;
+						const DPath* t = pool + candBeg + (e - 1);
+						if (t->lm_state == lmState && t->prev_root_id == prevRoot && t->sp_state == spState) { found = e - 1; break; }
+						slot = (slot + 1) & (HT_SIZE - 1);
+					}
+				}
+				// new keys are appended in lane (= pair) order; a full 128-slot bucket drops the key (BestPathContainer.hpp:363-367)
+				const bool isNew = isLeader && found == NPOS;
+				uint32_t newIdx = NPOS;
+				{
+					const unsigned nmask = __ballot_sync(FULL, isNew);
+					if (mode == 2)
+					{
+						if (isNew) newIdx = E + __popc(nmask & ((1u << lane) - 1));
+					}
+					else
+					{
+						// capacity per bucket; rank inside the bucket in lane order
+						uint32_t accepted = 0;
+#pragma unroll
+						for (uint32_t b = 0; b < 4; ++b)
+						{
+							const unsigned bm = __ballot_sync(FULL, isNew && bucket == b);
+							if (isNew && bucket == b)
+							{
+								const uint32_t r = __popc(bm & ((1u << lane) - 1));
+								if (bucketCnt[b] + r < 128) accepted = 1;
+							}
+							const uint32_t add = min((uint32_t)__popc(bm), 128u - bucketCnt[b]);
+							bucketCnt[b] += add;
+						}
+						const unsigned amask = __ballot_sync(FULL, accepted != 0);
+						if (accepted) newIdx = E + __popc(amask & ((1u << lane) - 1));
+						if (isNew && !accepted) newIdx = NPOS;
+						// total new entries this round
+						const uint32_t totalNew = __popc(amask);
+						if (candBeg + E + totalNew > poolCap) { err = ST_PATH_OVERFLOW; return; }
+						if (E + totalNew > HT_MAX_ENTRIES) { err = ST_PATH_OVERFLOW; return; }
+						// insert into the hash index
+						if (accepted)
+						{
+							uint32_t slot = htHash(lmState, prevRoot, spState);
+							while (atomicCAS_u16(slot, newIdx + 1)) slot = (slot + 1) & (HT_SIZE - 1);
+						}
+						E += totalNew;
+						htUsed = 1;
+						goto inserted;
+					}
+					{
+						const uint32_t totalNew = __popc(nmask);
+						if (candBeg + E + totalNew > poolCap) { err = ST_PATH_OVERFLOW; return; }
+						if (E + totalNew > HT_MAX_ENTRIES) { err = ST_PATH_OVERFLOW; return; }
+						if (isNew)
+						{
+							uint32_t slot = htHash(lmState, prevRoot, spState);
+							while (atomicCAS_u16(slot, newIdx + 1)) slot = (slot + 1) & (HT_SIZE - 1);
+						}
+						E += totalNew;
+						htUsed = 1;
+					}
+				}
+			inserted:
+				__syncwarp();
+				// the group's best lane writes the entry: new key -> create, existing key -> strict '>' update
+				{
+					const uint32_t tgtNew = __shfl_sync(FULL, newIdx, leader);
+					const uint32_t tgtOld = __shfl_sync(FULL, found, leader);
+					if (valid && lane == bestLane)
+					{
+						uint32_t tgt = tgtOld != NPOS ? tgtOld : tgtNew;
+						bool write = tgt != NPOS;
+						if (write && tgtOld != NPOS) write = accScore > pool[candBeg + tgt].acc_score;
+						if (write)
+						{
+							DPath np;
+							np.lm_state = lmState; np.acc_score = accScore; np.first_chunk_score = fcs; np.wid = cc.lastSeqId;
+							np.morpheme = cc.curId; np.parent = inBeg + q; np.own_off = cc.single ? cc.ownOff : 0; np.acc_typo_cost = pp.acc_typo_cost + node.typo_cost;
+							np.own_len = cc.single ? (uint16_t)cc.ownLen : 0; np.node = (uint16_t)nodeIdx; np.left_last = cc.leftLast; np.left_pol = cc.leftPol;
+							np.sp_state = spState;
+							np.root_id = rootId != COMMON_ROOT ? rootId : pp.root_id;
+							np.combine_socket = cc.pathSocket; np.prev_root_id = (uint8_t)prevRoot; np.morph_tag = cc.morphTag; np.wid_feat = cc.widFeat;
+							pool[candBeg + tgt] = np;
+						}
+					}
+				}
+				__syncwarp();
+			}
+			// writeTo (BestPathContainer.hpp:451-469): bucket-major order in medium mode
+			if (mode == 1 && E > 1 && (bucketCnt[0] != E))
+			{
+				if (candBeg + 2 * E > poolCap) { err = ST_PATH_OVERFLOW; return; }
+				uint32_t base[4]; base[0] = 0; base[1] = bucketCnt[0]; base[2] = base[1] + bucketCnt[1]; base[3] = base[2] + bucketCnt[2];
+				uint32_t fill[4] = { 0, 0, 0, 0 };
+				for (uint32_t eb = 0; eb < E; eb += 32)
+				{
+					const uint32_t e = eb + lane;
+					DPath p; uint32_t b = 0xFF;
+					if (e < E) { p = pool[candBeg + e]; b = (p.sp_state ^ ((uint32_t)p.lm_state >> 5)) & 3; }
+#pragma unroll
+					for (uint32_t k = 0; k < 4; ++k)
+					{
+						const unsigned bm = __ballot_sync(FULL, b == k);
+						if (b == k) pool[candBeg + E + base[k] + fill[k] + __popc(bm & ((1u << lane) - 1))] = p;
+						fill[k] += __popc(bm);
+					}
+				}
+				__syncwarp();
+				for (uint32_t e = lane; e < E; e += 32) pool[candBeg + e] = pool[candBeg + E + e];
+				__syncwarp();
+			}
+			top = candBeg + E;
+		}
+
+		__device__ __forceinline__ bool atomicCAS_u16(uint32_t slot, uint32_t val)
+		{
+			// returns true when the slot was occupied (caller probes on).  16-bit CAS on a 32-bit word.
+			uint32_t* w = reinterpret_cast<uint32_t*>(ht) + (slot >> 1);
+			const uint32_t shift = (slot & 1) * 16;
+			while (true)
+			{
+				const uint32_t old = *reinterpret_cast<volatile uint32_t*>(w);
+				if ((old >> shift) & 0xFFFF) return true;
+				if (atomicCAS(w, old, old | (val << shift)) == old) return false;
+			}
+		}
+
+		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
+		// cands: either a form's candidate list (formCands != nullptr) or the default unknown candidates
+		__device__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const uint32_t* candList, uint32_t nCands, uint32_t unk0, uint32_t unk1,
+			float unkFormDiscount, uint32_t ownOff, uint32_t ownLen, uint32_t inBeg, uint32_t inEnd)
+		{
+			const DNode node = nodes[nodeIdx];
+			float whitespaceDiscount = 0;
+			if (node.uform_len == 0 && node.form >= 0 && m.forms[node.form].str_len && node.space_errors)
+				whitespaceDiscount = -m.cfg.space_penalty * (float)node.space_errors;
+			const float typoDiscount = -node.typo_cost * m.cfg.typo_cost_weight;
+			const float nodeLevelDiscount = whitespaceDiscount + typoDiscount + unkFormDiscount;
+			const uint32_t P = inEnd - inBeg;
+			const uint32_t mode = P <= 128 ? 0 : (P <= 512 ? 1 : 2);
+			const bool spaceBefore = nodes[nodeIdx - node.prev].end_pos < node.start_pos;
+			const bool hasLB = hasLeftBoundary(nodeIdx);
+
+			for (int ignoreCond = 0; ignoreCond < 2; ++ignoreCond)
+			{
+				for (uint32_t ci = 0; ci < nCands; ++ci)
+				{
+					const int32_t curId = (int32_t)(candList ? candList[ci] : (ci == 0 ? unk0 : unk1));
+					const DMorph cur = m.morphs[curId];
+					const uint32_t tag = cur.feat & MF_TAG_MASK;
+					const bool single = (cur.feat & MF_SINGLE) != 0;
+					if (splitComplex)
+					{
+						bool cx = false;     // Morpheme::hasComplex, Form.h:176-185 (bit 29 of reserved word marks `complex`)
+						if (m.morphs[curId + cur.combined].misc & 1u) cx = true;
+						for (uint32_t c = 0; c < cur.chunk_cnt && !cx; ++c) if (m.morphs[m.chunks[cur.chunk_off + c].morph].misc & 1u) cx = true;
+						if (cx) continue;
+					}
+					if (cur.nonstd_dialect) continue;
+					if (tag == T_z_coda || tag == T_z_siot)
+					{
+						if (tag == T_z_siot && !(splitSaisiot || mergeSaisiot)) continue;
+						// shortcut (PathEvaluator.hpp:389-432): copy qualifying incoming paths, no LM step
+						const float add = cur.user_score * m.cfg.typo_cost_weight;
+						const DMorph lmM = m.morphs[cur.lm_id];
+						for (uint32_t qb = 0; qb < P; qb += 32)
+						{
+							const uint32_t q = qb + lane;
+							DPath p; bool ok = false;
+							if (q < P)
+							{
+								p = pool[inBeg + q];
+								const uint32_t lastTag = p.wid_feat & MF_TAG_MASK;
+								ok = tag == T_z_coda ? (isJClass((uint8_t)lastTag) || isEClass((uint8_t)lastTag)) : isNNClass((uint8_t)lastTag);
+							}
+							const unsigned om = __ballot_sync(FULL, ok);
+							if (top + __popc(om) > poolCap) { err = ST_PATH_OVERFLOW; return; }
+							if (ok)
+							{
+								DPath np = p;
+								np.acc_score += add;
+								np.acc_typo_cost -= cur.user_score;
+								np.parent = inBeg + q;
+								np.morpheme = (int32_t)cur.lm_id;
+								np.wid = cur.lm_id;
+								np.node = (uint16_t)nodeIdx;
+								np.morph_tag = (uint8_t)(lmM.feat & MF_TAG_MASK);
+								np.wid_feat = lmM.feat;
+								uint16_t ll; uint8_t lp;
+								leftFeat(np.own_len ? np.own_off : 0, np.own_len, np.wid, np.morpheme, ll, lp);
+								if (lmM.combine_socket) lp |= LP_MORPH_SOCKET;
+								np.left_last = ll; np.left_pol = lp;
+								pool[top + __popc(om & ((1u << lane) - 1))] = np;
+							}
+							top += __popc(om);
+						}
+						__syncwarp();
+						continue;
+					}
+					if (!single)
+					{
+						// contracted '하다/하게/하지' after a space is not a candidate (PathEvaluator.hpp:435-448)
+						if (node.prev && spaceBefore && cur.form_idx >= 0 && m.forms[cur.form_idx].str_len == 1)
+						{
+							const uint32_t k0 = m.form_chars[m.forms_raw[cur.form_idx].str_off];
+							if (k0 == 0xB2E4 || k0 == 0xAC8C || k0 == 0xC9C0)
+							{
+								const DMorph c0 = m.morphs[m.chunks[cur.chunk_off].morph];
+								if (c0.form_idx >= 0 && m.forms[c0.form_idx].str_len == 1 && m.form_chars[m.forms_raw[c0.form_idx].str_off] == 0xD558) continue;
+							}
+						}
+					}
+					CandCtx cc;
+					cc.curId = curId; cc.cur = cur; cc.single = single;
+					int32_t lastMorph;
+					if (single) { lastMorph = cur.combined ? curId + cur.combined : curId; cc.firstWid0 = cur.lm_id; }
+					else
+					{
+						lastMorph = (int32_t)m.chunks[cur.chunk_off + cur.chunk_cnt - 1].morph;
+						cc.firstWid0 = m.morphs[m.chunks[cur.chunk_off].morph].lm_id;
+					}
+					if ((uint32_t)lastMorph >= m.lang_vocab_size && (uint32_t)lastMorph < m.n_morphs) cc.lastSeqId = (uint32_t)lastMorph;
+					else cc.lastSeqId = m.morphs[lastMorph].lm_id;
+					cc.additionalScore = cur.user_score + nodeLevelDiscount + m.tag_left_boundary[hasLB ? 1 : 0][clearIrregular((uint8_t)tag)];
+					cc.ignoreCondScore = ignoreCond ? -10.f : 0.f;
+					cc.specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7;
+					cc.sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
+					cc.sbOrder = cc.sbType ? cur.sense_id : 0;
+					cc.positiveE = isEClass((uint8_t)tag) && node.form >= 0 && (m.forms[node.form].flags & FF_FIRST_IS_A);
+					cc.snEndswithPoint = tag == T_sn && node.uform_len && norm[node.uform_off + node.uform_len - 1] == '.';
+					cc.fork = cc.sbType != 0 || cc.specialType == 0 || cc.specialType == 1 || cc.specialType == 3 || cc.specialType == 4;
+					cc.ownOff = ownOff; cc.ownLen = ownLen;
+					cc.spaceBefore = spaceBefore;
+					cc.morphTag = (uint8_t)tag;
+					cc.widFeat = m.morphs[cc.lastSeqId].feat;
+					cc.pathSocket = single ? cur.combine_socket : 0;
+					leftFeat(single ? ownOff : 0, single ? ownLen : 0, cc.lastSeqId, curId, cc.leftLast, cc.leftPol);
+					if (cur.combine_socket) cc.leftPol |= LP_MORPH_SOCKET;
+					evalCand(nodeIdx, node, cc, inBeg, inEnd, mode);
+					if (err) return;
+				}
+				if (top > nodeBeg) break;
+			}
+
+			// prune (PathEvaluator.hpp:475-511)
+			float mx[3] = { -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F };
+			const uint32_t cntAll = top - nodeBeg;
+			for (uint32_t eb = 0; eb < cntAll; eb += 32)
+			{
+				const uint32_t e = eb + lane;
+				float sc = -CUDART_INF_F; uint32_t slot = 0;
+				if (e < cntAll)
+				{
+					const DPath* p = pool + nodeBeg + e;
+					if (!(p->left_pol & LP_MORPH_SOCKET)) sc = p->acc_score;
+					slot = p->root_id == COMMON_ROOT ? 0 : p->root_id + 1;
+				}
+#pragma unroll
+				for (uint32_t k = 0; k < 3; ++k)
+				{
+					float v = slot == k ? sc : -CUDART_INF_F;
+					for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, d));
+					mx[k] = fmaxf(mx[k], v);
+				}
+			}
+			uint32_t valid = 0;
+			for (uint32_t eb = 0; eb < cntAll; eb += 32)
+			{
+				const uint32_t e = eb + lane;
+				DPath p; bool keep = false;
+				if (e < cntAll)
+				{
+					p = pool[nodeBeg + e];
+					const uint32_t slot = p.root_id == COMMON_ROOT ? 0 : p.root_id + 1;
+					const float mxs = slot == 0 ? mx[0] : (slot == 1 ? mx[1] : mx[2]);
+					keep = !(p.acc_score + m.cfg.cut_off_threshold < mxs);
+				}
+				const unsigned km = __ballot_sync(FULL, keep);
+				__syncwarp();
+				if (keep) pool[nodeBeg + valid + __popc(km & ((1u << lane) - 1))] = p;
+				valid += __popc(km);
+				__syncwarp();
+			}
+			top = nodeBeg + valid;
+		}
+
+		// PathEvaluator.hpp:1159-1176; predecessors of a node are the contiguous group [k - prev, ...] linked by sibling == 1
+		__device__ bool isDisconnected(uint32_t scanStart)
+		{
+			if (reach[scanStart - 1]) return false;
+			__syncwarp();
+			for (uint32_t k = scanStart; k < N; ++k)
+			{
+				const DNode nd = nodes[k];
+				uint32_t r = 0;
+				uint32_t q = k - nd.prev;
+				if (nd.prev)
+				{
+					while (true)
+					{
+						if (reach[q]) { r = 1; break; }
+						if (!nodes[q].sibling) break;
+						q += nodes[q].sibling;
+					}
+				}
+				if (lane == 0) reach[k] = (uint8_t)r;
+				__syncwarp();
+			}
+			return reach[N - 1] == 0;
+		}
+
+		__device__ bool anyNonSocket(uint32_t beg, uint32_t end) const
+		{
+			bool any = false;
+			for (uint32_t eb = beg; eb < end; eb += 32)
+			{
+				const uint32_t e = eb + lane;
+				const bool ok = e < end && pool[e].combine_socket == 0;
+				if (__any_sync(FULL, ok)) { any = true; break; }
+			}
+			return any;
+		}
+
+		// incoming pool range of node i
+		__device__ void incoming(uint32_t i, uint32_t& inBeg, uint32_t& inEnd) const
+		{
+			const DNode nd = nodes[i];
+			uint32_t q = i - nd.prev;
+			inBeg = npOff[q];
+			while (nodes[q].sibling) q += nodes[q].sibling;
+			inEnd = npOff[q] + npCnt[q];
+		}
+
+		// ---- one chunk: findBestPath, returns the selected results in res[] ----------------------------
+		__device__ uint32_t findBestPath(const DChunk& ch, PathRes* res, bool openEnding)
+		{
+			const uint32_t chunkBase = top;
+			// BOS path (PathEvaluator.hpp:1224-1226)
+			if (top + 1 > poolCap) { err = ST_PATH_OVERFLOW; return 0; }
+			if (lane == 0)
+			{
+				DPath b;
+				b.lm_state = m.kn_bos_node; b.acc_score = 0; b.first_chunk_score = 0; b.wid = 0; b.morpheme = 0; b.parent = NPOS; b.own_off = 0; b.acc_typo_cost = 0;
+				b.own_len = 0; b.node = 0; b.sp_state = 0; b.root_id = COMMON_ROOT; b.combine_socket = 0; b.prev_root_id = 0;
+				const DMorph m0 = m.morphs[0];
+				b.morph_tag = (uint8_t)(m0.feat & MF_TAG_MASK); b.wid_feat = m0.feat;
+				uint16_t ll; uint8_t lp;
+				leftFeat(0, 0, 0, 0, ll, lp);
+				b.left_last = ll; b.left_pol = lp;
+				pool[top] = b;
+				npOff[0] = top; npCnt[0] = 1; reach[0] = 1;
+			}
+			for (uint32_t i = lane + 1; i < N; i += 32) reach[i] = 0;
+			top += 1;
+			__syncwarp();
+			const uint32_t unkNNG = T_nng + 1u, unkNNP = T_nnp + 1u;     // getDefaultMorphemeId, Kiwi.h:64-67
+
+			for (uint32_t i = 1; i + 1 < N; ++i)
+			{
+				const DNode node = nodes[i];
+				uint32_t inBeg, inEnd;
+				incoming(i, inBeg, inEnd);
+				const uint32_t nodeBeg = top;
+				if (node.form >= 0)
+				{
+					const DForm f = m.forms[node.form];
+					evaluate(i, nodeBeg, m.form_cands + f.cand_off, f.cand_cnt, 0, 0, 0.f, node.uform_off, node.uform_len, inBeg, inEnd);
+					if (err) return 0;
+					if (node.typo_cost == 0.f && (f.flags & FF_ALL_PARTIAL))
+					{
+						const uint16_t* fs = m.form_chars + m.forms_raw[node.form].str_off;
+						const float unkScore = unkFormScore(fs, f.str_len);
+						evaluate(i, nodeBeg, nullptr, 1, unkNNP, 0, unkScore, ~(uint32_t)node.form, f.str_len, inBeg, inEnd);
+						if (err) return 0;
+					}
+					const bool r = anyNonSocket(nodeBeg, top);
+					if (lane == 0) reach[i] = r ? 1 : 0;
+					__syncwarp();
+					if (isDisconnected(i + 1))
+					{
+						const uint32_t len = node.end_pos - node.start_pos;
+						const float unkScore = unkFormScore(norm + node.start_pos, len);
+						evaluate(i, nodeBeg, nullptr, 2, unkNNG, unkNNP, unkScore, node.start_pos, len, inBeg, inEnd);
+						if (err) return 0;
+					}
+				}
+				else
+				{
+					const float unkScore = unkFormScore(norm + node.uform_off, node.uform_len);
+					evaluate(i, nodeBeg, nullptr, 2, unkNNG, unkNNP, unkScore, node.uform_off, node.uform_len, inBeg, inEnd);
+					if (err) return 0;
+				}
+				if (lane == 0) { npOff[i] = nodeBeg; npCnt[i] = top - nodeBeg; }
+				__syncwarp();
+			}
+
+			// ---- end node (PathEvaluator.hpp:1320-1357): candidates go to the pool tail as temporary records
+			uint32_t inBeg, inEnd;
+			incoming(N - 1, inBeg, inEnd);
+			const uint32_t P = inEnd - inBeg;
+			const uint32_t candBeg = top;
+			uint32_t nCand = 0;
+			const uint32_t perPath = nUniq;
+			if (top + P * perPath > poolCap) { err = ST_PATH_OVERFLOW; return 0; }
+			for (uint32_t qb = 0; qb < P; qb += 32)
+			{
+				const uint32_t q = qb + lane;
+				DPath p; bool ok = false; float c = 0;
+				if (q < P)
+				{
+					p = pool[inBeg + q];
+					ok = p.combine_socket == 0;
+					if (ok)
+					{
+						const DMorph pm = m.morphs[p.morpheme];
+						const bool single = (pm.feat & MF_SINGLE) != 0;
+						if (!single && pm.chunk_cnt <= (pm.combine_socket ? 2u : 1u) && ((pm.feat >> MF_VOWEL_SHIFT) & 15) != CV_none) ok = false;
+						if (p.morph_tag == T_z_siot) ok = false;
+					}
+					if (ok)
+					{
+						c = p.acc_score;
+						if (!openEnding)
+						{
+							int32_t st = p.lm_state;
+							c += knProgress(m, st, 1);
+							if (p.sp_state & 1) c -= 2;
+							if (p.sp_state & 2) c -= 2;
+						}
+					}
+				}
+				const unsigned om = __ballot_sync(FULL, ok);
+				const uint32_t before = __popc(om & ((1u << lane) - 1));
+				if (ok)
+				{
+					// cand record reuses DPath: acc_score = c, parent, root_id, sp_state
+					if (p.root_id == COMMON_ROOT)
+					{
+						for (uint32_t r = 0; r < nUniq; ++r)
+						{
+							DPath cnd = p; cnd.acc_score = c; cnd.parent = inBeg + q; cnd.root_id = (uint8_t)r; cnd.sp_state = uniq[r]; cnd.wid = 1;
+							pool[candBeg + (nCand + before) * perPath + r] = cnd;
+						}
+					}
+					else
+					{
+						DPath cnd = p; cnd.acc_score = c; cnd.parent = inBeg + q; cnd.wid = 1;
+						pool[candBeg + (nCand + before) * perPath] = cnd;
+						for (uint32_t r = 1; r < nUniq; ++r) { DPath z = cnd; z.wid = 0; pool[candBeg + (nCand + before) * perPath + r] = z; }
+					}
+				}
+				nCand += __popc(om);
+			}
+			__syncwarp();
+			const uint32_t nRec = nCand * perPath;      // records with wid == 1 are real candidates, in the reference's emplace order
+			// distinct (rootId, spState) groups, ascending
+			uint32_t groups[MAX_RESULTS]; uint32_t nGroups = 0;
+			for (uint32_t eb = 0; eb < nRec; eb += 32)
+			{
+				const uint32_t e = eb + lane;
+				uint32_t gk = NPOS;
+				if (e < nRec) { const DPath* r = pool + candBeg + e; if (r->wid) gk = ((uint32_t)r->root_id << 8) | r->sp_state; }
+				unsigned rem = __ballot_sync(FULL, gk != NPOS);
+				while (rem)
+				{
+					const int src = __ffs(rem) - 1;
+					const uint32_t k = __shfl_sync(FULL, gk, src);
+					bool seen = false;
+					for (uint32_t g = 0; g < nGroups; ++g) if (groups[g] == k) seen = true;
+					if (!seen)
+					{
+						if (nGroups >= MAX_RESULTS) { err = ST_INTERNAL; return 0; }
+						groups[nGroups++] = k;
+					}
+					rem &= ~__ballot_sync(FULL, gk == k);
+				}
+			}
+			if (nGroups == 0) return 0;
+			// insertion sort of the few group keys
+			for (uint32_t a = 1; a < nGroups; ++a) { const uint32_t k = groups[a]; uint32_t b = a; while (b && groups[b - 1] > k) { groups[b] = groups[b - 1]; --b; } groups[b] = k; }
+			const uint32_t perGroup = (2 + nGroups - 1) / nGroups;        // ceil(topN * 2 / numUniq), topN == 1
+			uint32_t nRes = 0;
+			for (uint32_t g = 0; g < nGroups; ++g)
+			{
+				uint32_t taken1 = NPOS;
+				for (uint32_t k = 0; k < perGroup; ++k)
+				{
+					// best remaining record of the group: max score, earliest index on ties
+					uint32_t bestOrd = 0, bestIdx = NPOS;
+					for (uint32_t eb = 0; eb < nRec; eb += 32)
+					{
+						const uint32_t e = eb + lane;
+						uint32_t ord = 0; bool ok = false;
+						if (e < nRec && e != taken1)
+						{
+							const DPath* r = pool + candBeg + e;
+							if (r->wid && ((((uint32_t)r->root_id << 8) | r->sp_state) == groups[g]))
+							{
+								ok = true;
+								ord = __float_as_uint(r->acc_score);
+								ord = (ord & 0x80000000u) ? ~ord : (ord | 0x80000000u);
+							}
+						}
+						const uint32_t mxo = __reduce_max_sync(FULL, ok ? ord : 0u);
+						if (mxo > bestOrd || (bestIdx == NPOS && mxo))
+						{
+							const unsigned bm = __ballot_sync(FULL, ok && ord == mxo);
+							if (bm && (mxo > bestOrd || bestIdx == NPOS)) { bestOrd = mxo; bestIdx = eb + __ffs(bm) - 1; }
+						}
+					}
+					if (bestIdx == NPOS) break;
+					if (nRes >= MAX_RESULTS) { err = ST_INTERNAL; return 0; }
+					const DPath* r = pool + candBeg + bestIdx;
+					res[nRes].score = r->acc_score; res[nRes].endParent = r->parent;
+					res[nRes].prevState = uniq[r->root_id]; res[nRes].curState = r->sp_state;
+					++nRes;
+					taken1 = bestIdx;
+				}
+			}
+			// sort(ret) by score desc (<= 16 elements: libstdc++ std::sort is an insertion sort -> stable)
+			for (uint32_t a = 1; a < nRes; ++a)
+			{
+				const PathRes k = res[a]; uint32_t b = a;
+				while (b && res[b - 1].score < k.score) { res[b] = res[b - 1]; --b; }
+				res[b] = k;
+			}
+			(void)chunkBase;
+			return nRes;
+		}
+	};
+
+	// position mapping of insertPathIntoResults (src/Kiwi.cpp:734-737)
+	__device__ __forceinline__ uint32_t upperBound(const uint32_t* t, uint32_t n, uint32_t v)
+	{
+		uint32_t lo = 0, hi = n;
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (t[mid] <= v) lo = mid + 1; else hi = mid; }
+		return lo;
+	}
+	__device__ __forceinline__ uint32_t lowerBound(const uint32_t* t, uint32_t n, uint32_t v)
+	{
+		uint32_t lo = 0, hi = n;
+		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (t[mid] < v) lo = mid + 1; else hi = mid; }
+		return lo;
+	}
+
+	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) viterbi_kernel(const DevModel m, const BatchView bv, const VitView vv)
+	{
+		__shared__ uint16_t htAll[WARPS_PER_BLOCK][HT_SIZE];
+		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+		const uint32_t s = blockIdx.x * WARPS_PER_BLOCK + wib;
+		if (s >= bv.n_sent) return;
+		if (bv.status[s]) { if (lane == 0) { vv.n_tokens[s] = 0; vv.score[s] = 0; } return; }
+
+		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
+		const uint32_t n = t1 - t0;
+		const uint32_t W = 2 * n + 4;
+		const size_t wbase = 2 * (size_t)t0 + 4 * (size_t)s;
+		const size_t nbase = (size_t)bv.nodes_per_unit * wbase;
+		const size_t pbase = (size_t)vv.paths_per_unit * wbase + (size_t)vv.paths_const * s;
+
+		Vit v{ m, bv, vv, lane };
+		v.norm = bv.norm + wbase;
+		v.pool = vv.paths + pbase;
+		v.poolCap = vv.paths_per_unit * W + vv.paths_const;
+		v.top = 0;
+		v.ht = htAll[wib]; v.htUsed = 1;
+		v.splitComplex = (bv.match_options >> 22) & 1; v.splitSaisiot = (bv.match_options >> 25) & 1; v.mergeSaisiot = (bv.match_options >> 26) & 1;
+		v.htClear();
+
+		const DChunk* chunks = bv.chunks + (wbase >> 2) + 2 * (size_t)s;
+		const uint32_t nChunks = bv.n_chunks[s];
+		DRec* recs = vv.recs + 2 * ((wbase >> 2) + 2 * (size_t)s);
+		const uint32_t normLen = bv.norm_len[s];
+
+		// running results of insertPathIntoResults (<= 2 survive each chunk)
+		uint32_t retN = 0; float retScore[2] = { 0, 0 }; uint8_t retSp[2] = { 0, 0 }; int32_t retRec[2] = { -1, -1 };
+		uint32_t nRecs = 0;
+
+		for (uint32_t c = 0; c < nChunks && !v.err; ++c)
+		{
+			const DChunk ch = chunks[c];
+			v.nodes = bv.nodes + nbase + ch.node_off; v.N = ch.n_nodes;
+			v.npOff = vv.node_path_off + nbase + ch.node_off; v.npCnt = vv.node_path_cnt + nbase + ch.node_off;
+			v.reach = vv.reachable + nbase + ch.node_off;
+			// uniqStates = sorted unique of spStatesByRet, or {0} (PathEvaluator.hpp:1212-1218)
+			if (retN == 0) { v.uniq[0] = 0; v.nUniq = 1; }
+			else if (retN == 1 || retSp[0] == retSp[1]) { v.uniq[0] = retSp[0]; v.nUniq = 1; }
+			else { v.uniq[0] = min(retSp[0], retSp[1]); v.uniq[1] = max(retSp[0], retSp[1]); v.nUniq = 2; }
+
+			PathRes res[MAX_RESULTS];
+			const uint32_t K = v.findBestPath(ch, res, false);
+			if (v.err) break;
+
+			// ---- insertPathIntoResults, topN == 1 (src/Kiwi.cpp:629-782), all lanes redundantly
+			struct Ret { float score; uint8_t sp; int32_t rec; uint32_t parent; };
+			Ret ret[2 + MAX_RESULTS]; uint32_t nRet = 0;
+			if (retN == 0)      // `ret.empty()` in the reference: also true again after a chunk that kept nothing
+			{
+				const uint32_t nn = min(K, 2u);
+				for (uint32_t i = 0; i < nn; ++i) ret[nRet++] = Ret{ 0.f, 0, -1, i };
+			}
+			else
+			{
+				uint8_t ppKey[4]; uint32_t ppVal[4]; uint32_t nPP = 0;      // prevParents map
+				bool selected[MAX_RESULTS];
+				for (uint32_t i = 0; i < K; ++i) selected[i] = false;
+				for (uint32_t i = 0; i < retN; ++i)
+				{
+					const uint8_t st = retSp[i];
+					uint32_t from = 0; int32_t ppi = -1;
+					for (uint32_t k = 0; k < nPP; ++k) if (ppKey[k] == st) { from = ppVal[k]; ppi = (int32_t)k; }
+					uint32_t parent = from;
+					for (; parent < K; ++parent) if (res[parent].prevState == st) break;
+					if (parent >= K && from) { for (parent = 0; parent < K; ++parent) if (res[parent].prevState == st) break; }
+					ret[nRet++] = Ret{ retScore[i], st, retRec[i], parent };
+					if (ppi < 0) { ppi = (int32_t)nPP; ppKey[nPP] = st; ppVal[nPP] = 0; ++nPP; }   // operator[] default-inserts 0
+					if (parent < K) { selected[parent] = true; ppVal[ppi] = parent + 1; }
+				}
+				for (uint32_t i = 0; i < K; ++i)
+				{
+					if (selected[i]) continue;
+					uint32_t parent = 0;
+					for (; parent < nRet; ++parent) if (ret[parent].sp == res[i].prevState) break;
+					// NB: the reference searches spStatesByRet, which grows together with ret
+					if (parent < nRet) { Ret r = ret[parent]; r.parent = i; ret[nRet++] = r; }
+					else { v.err = ST_INTERNAL; break; }
+				}
+			}
+			if (v.err) break;
+			// keep the first path per curState, accumulate, then sort by score and keep 2
+			Ret kept[2 + MAX_RESULTS]; uint32_t nKept = 0;
+			uint8_t seenSt[2 + MAX_RESULTS]; uint32_t nSeen = 0;
+			for (uint32_t i = 0; i < nRet; ++i)
+			{
+				if (!(ret[i].parent < K)) continue;
+				const PathRes& r = res[ret[i].parent];
+				bool dup = false;
+				for (uint32_t k = 0; k < nSeen; ++k) if (seenSt[k] == r.curState) dup = true;
+				if (dup) continue;
+				seenSt[nSeen++] = r.curState;
+				Ret o; o.score = ret[i].score + r.score; o.sp = r.curState; o.rec = ret[i].rec; o.parent = ret[i].parent;
+				kept[nKept++] = o;
+			}
+			for (uint32_t a = 1; a < nKept; ++a)
+			{
+				const Ret k = kept[a]; uint32_t b = a;
+				while (b && kept[b - 1].score < k.score) { kept[b] = kept[b - 1]; --b; }
+				kept[b] = k;
+			}
+			retN = min(nKept, 2u);
+			for (uint32_t i = 0; i < retN; ++i)
+			{
+				retScore[i] = kept[i].score; retSp[i] = kept[i].sp;
+				if (lane == 0) recs[nRecs] = DRec{ kept[i].rec, res[kept[i].parent].endParent, c, kept[i].score };
+				retRec[i] = (int32_t)nRecs;
+				++nRecs;
+			}
+			__syncwarp();
+		}
+
+		// ---- emit the best result (ret[0]) ------------------------------------------------------------
+		uint32_t nTok = 0; float total = 0;
+		if (!v.err && retN)
+		{
+			total = retScore[0];
+			// chain of records, last chunk first; store reversed order in the ctr scratch
+			uint32_t* chain = bv.ctr + wbase;                // W entries, free after kernel A
+			uint32_t L = 0;
+			for (int32_t r = retRec[0]; r >= 0; r = recs[r].parent_rec) { if (lane == 0) chain[L] = (uint32_t)r; ++L; }
+			__syncwarp();
+			uint32_t* steps = bv.ns_to_pos + wbase;          // backtrack scratch (W entries)
+			DToken* out = vv.tokens + wbase;
+			const uint32_t* posTable = bv.pos_table + t0 + s;
+			for (int32_t ci = (int32_t)L - 1; ci >= 0 && !v.err; --ci)
+			{
+				const DRec rec = recs[chain[ci]];
+				const DChunk ch = chunks[rec.chunk];
+				const DNode* gnodes = bv.nodes + nbase + ch.node_off;
+				// generateTokenList (PathEvaluator.hpp:1038-1157): lane 0 walks parents, then emits forward
+				uint32_t nSteps = 0;
+				for (uint32_t p = rec.end_parent; v.pool[p].parent != NPOS; p = v.pool[p].parent)
+				{
+					if (nSteps >= W) { v.err = ST_TOKEN_OVERFLOW; break; }
+					if (lane == 0) steps[nSteps] = p;
+					++nSteps;
+				}
+				__syncwarp();
+				if (v.err) break;
+				if (lane == 0)
+				{
+										DToken backTok; backTok.morph = 0; backTok.position = 0; backTok.score = 0; backTok.length = 0; backTok.tag = 0; backTok.flags = 0;
+					uint32_t backBegin = 0, backEnd = 0; bool backValid = false; bool backSkip = false;
+					auto flushBack = [&]()
+					{
+						if (!backValid) return;
+						if (!backSkip)
+						{
+							if (nTok >= W) { v.err = ST_TOKEN_OVERFLOW; return; }
+							DToken t = backTok;
+							const uint32_t beginPos = upperBound(posTable, n + 1, backBegin) - 1;
+							const uint32_t endPos = lowerBound(posTable, n + 1, backEnd);
+							t.position = beginPos; t.length = (uint16_t)(endPos - beginPos);
+							out[nTok++] = t;
+						}
+						backValid = false;
+					};
+					auto pushTok = [&](uint32_t morph, uint32_t begin, uint32_t end, float score, uint32_t ownOff, uint32_t ownLen)
+					{
+						flushBack();
+						const DMorph mm = m.morphs[morph];
+						backTok.morph = morph; backTok.tag = (uint8_t)(mm.feat & MF_TAG_MASK); backTok.score = score; backTok.flags = ownLen ? 1 : 0;
+						backBegin = begin; backEnd = end; backValid = true; backSkip = false;
+						if (ownLen)
+						{
+							const uint32_t c0 = (ownOff & 0x80000000u) ? m.form_chars[m.forms_raw[~ownOff].str_off] : v.norm[ownOff];
+							if (c0 == ' ') backSkip = true;
+							// updateTokenInfoScript (src/Kiwi.cpp:590-605)
+							const uint32_t tg = backTok.tag;
+							if ((tg == T_sl || tg == T_sh || tg == T_sw || tg == T_w_emoji) && !(mm.form_idx >= 0 && m.forms[mm.form_idx].str_len))
+							{
+								uint32_t cc = c0;
+								if (isHighSurrogate(cc))
+								{
+									const uint32_t c1 = ownLen > 1 ? ((ownOff & 0x80000000u) ? m.form_chars[m.forms_raw[~ownOff].str_off + 1] : v.norm[ownOff + 1]) : 0;
+									cc = mergeSurrogate(cc, c1);
+								}
+								if (attrScript(chrAttr(m, cc)) == m.script_latin) backTok.tag = T_sl;
+							}
+						}
+					};
+					auto unify = [&](uint32_t morph) -> uint32_t
+					{
+						if (!(morph < m.lang_vocab_size) || m.morphs[morph].combined) return morph;
+						return m.morphs[morph].lm_id;
+					};
+					uint32_t prevIdx = v.pool[steps[nSteps - 1]].parent;
+					for (int32_t si = (int32_t)nSteps - 1; si >= 0 && !v.err; --si)
+					{
+						const DPath cur = v.pool[steps[si]];
+						const DPath prev = v.pool[prevIdx];
+						const float scoreDiff = cur.acc_score - prev.acc_score;
+						const float typoCostDiff = cur.acc_typo_cost - prev.acc_typo_cost;
+						const DMorph mm = m.morphs[cur.morpheme];
+						const bool single = (mm.feat & MF_SINGLE) != 0;
+						const bool saisiot = (mm.misc & 2u) != 0;
+						const uint32_t numNewTokens = ((v.splitSaisiot && saisiot) || !single) ? mm.chunk_cnt : 1;
+						const DNode g = gnodes[cur.node];
+						const float firstScore = cur.first_chunk_score + typoCostDiff * m.cfg.typo_cost_weight;
+						const float restScores = numNewTokens > 1 ? (scoreDiff - cur.first_chunk_score) / (float)(numNewTokens - 1) : 0.f;
+						if (v.splitSaisiot && saisiot)
+						{
+							for (uint32_t chn = 0; chn < numNewTokens; ++chn)
+							{
+								const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
+								pushTok(unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, chn == 0 ? firstScore : restScores, 0, 0);
+							}
+							backEnd = g.end_pos;
+						}
+						else if (single)
+						{
+							pushTok(unify((uint32_t)cur.morpheme), g.start_pos, g.end_pos, firstScore, cur.own_off, cur.own_len);
+						}
+						else if (mm.combine_socket)
+						{
+							// ret.back() is merged with the left half (PathEvaluator.hpp:1111-1134)
+							backTok.morph = backTok.morph + m.morphs[backTok.morph].combined;
+							backTok.tag = (uint8_t)(m.morphs[backTok.morph].feat & MF_TAG_MASK);
+							backEnd = g.start_pos + m.chunks[mm.chunk_off].end;
+							backTok.score = firstScore;
+							for (uint32_t chn = 1; chn < numNewTokens; ++chn)
+							{
+								const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
+								pushTok(unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, restScores, 0, 0);
+							}
+							backEnd = g.end_pos;
+						}
+						else
+						{
+							for (uint32_t chn = 0; chn < numNewTokens; ++chn)
+							{
+								const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
+								pushTok(unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, chn == 0 ? firstScore : restScores, 0, 0);
+							}
+							backEnd = g.end_pos;
+						}
+						prevIdx = steps[si];
+					}
+					flushBack();
+				}
+				nTok = __shfl_sync(FULL, nTok, 0);
+				v.err = __shfl_sync(FULL, v.err, 0);
+				__syncwarp();
+			}
+		}
+		(void)normLen;
+		if (lane == 0)
+		{
+			vv.n_tokens[s] = v.err ? 0 : nTok;
+			vv.score[s] = v.err ? 0.f : total;
+			if (v.err) bv.status[s] = v.err;
+		}
+	}
+
+	cudaError_t launch_viterbi(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream)
+	{
+		if (bv.n_sent == 0) return cudaSuccess;
+		const uint32_t blocks = (bv.n_sent + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+		viterbi_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(m, bv, vv);
+		return cudaGetLastError();
+	}
+}

@@ -1,0 +1,82 @@
+// ORACLE C API (test infrastructure; loaded only by tests/, __graft_entry__.smoke() and bench.py's cpu legs).
+// Thin extern "C" wrapper over the CPU restatement so Python can compare it with the CUDA path through ctypes.
+#include "analyze.hpp"
+
+struct OrcHandle { orc::Image im; orc::Analyzer* an = nullptr; orc::Counters cnt; };
+
+extern "C" {
+
+void* orc_open(const char* imagePath)
+{
+	try
+	{
+		auto* h = new OrcHandle;
+		h->im.load(imagePath);
+		h->an = new orc::Analyzer{ h->im };
+		h->an->viterbi.cnt = &h->cnt;
+		return h;
+	}
+	catch (...) { return nullptr; }
+}
+
+void orc_close(void* p)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	if (!h) return;
+	delete h->an;
+	delete h;
+}
+
+// returns the token count (or -1 on error / -2 when max_tokens is too small)
+int orc_analyze(void* p, const uint16_t* text, int len, uint32_t* morph, uint8_t* tag, uint32_t* pos, uint16_t* length, float* score, int maxTokens, float* sentScore)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	try
+	{
+		h->an->keepChunks = false;
+		auto res = h->an->analyze(text, (size_t)len);
+		if ((int)res.tokens.size() > maxTokens) return -2;
+		for (size_t i = 0; i < res.tokens.size(); ++i)
+		{
+			morph[i] = res.tokens[i].morph; tag[i] = res.tokens[i].tag; pos[i] = res.tokens[i].position; length[i] = res.tokens[i].length; score[i] = res.tokens[i].score;
+		}
+		*sentScore = res.score;
+		return (int)res.tokens.size();
+	}
+	catch (...) { return -1; }
+}
+
+// lattice rows {form, uform_off|-1, uform_len, prev, sibling, start, end, space_errors, chunk}; chunks with <= 2 nodes are skipped
+int orc_lattice(void* p, const uint16_t* text, int len, int32_t* rows, int maxRows)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	try
+	{
+		h->an->keepChunks = true;
+		auto res = h->an->analyze(text, (size_t)len);
+		int n = 0, c = 0;
+		for (auto& ch : res.chunks)
+		{
+			if (ch.nodes.size() <= 2) continue;
+			for (auto& nd : ch.nodes)
+			{
+				if (n >= maxRows) return -2;
+				int32_t* r = rows + 9 * n++;
+				r[0] = nd.form; r[1] = nd.uformLen ? nd.uformOff : -1; r[2] = (int32_t)nd.uformLen; r[3] = (int32_t)nd.prev; r[4] = (int32_t)nd.sibling;
+				r[5] = (int32_t)nd.startPos; r[6] = (int32_t)nd.endPos; r[7] = (int32_t)nd.spaceErrors; r[8] = c;
+			}
+			++c;
+		}
+		return n;
+	}
+	catch (...) { return -1; }
+}
+
+// work counters accumulated since open: {lmSteps, pairs, inserts, pathsOut, candEvals, evalCalls}
+void orc_counters(void* p, uint64_t* out)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	out[0] = h->cnt.lmSteps; out[1] = h->cnt.pairs; out[2] = h->cnt.inserts; out[3] = h->cnt.pathsOut; out[4] = h->cnt.candEvals; out[5] = h->cnt.evalCalls;
+}
+
+}

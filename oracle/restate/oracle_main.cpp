@@ -40,7 +40,9 @@ int main(int argc, char** argv)
 		const auto tab = line.find('\t');
 		if (tab != line.npos) line = line.substr(0, tab);
 		auto str = utf8To16(line);
+		const uint64_t po0 = cnt.pathsOut;
 		auto res = an.analyze(str.data(), str.size());
+		{ static double maxRatio = 0; double r = (double)(cnt.pathsOut - po0) / (double)(res.normLen + 1); if (r > maxRatio) { maxRatio = r; std::cerr << "ratio " << r << " at line " << idx << " normLen " << res.normLen << "\n"; } }
 		std::fprintf(fo, "S %zu %zu %a %zu %zu\n", idx, res.tokens.size(), res.score, res.chunks.size(), res.normLen);
 		for (auto& t : res.tokens) std::fprintf(fo, "T %u %u %u %u %a\n", t.morph, (unsigned)t.tag, t.position, (unsigned)t.length, t.score);
 		for (size_t c = 0; c < res.chunks.size(); ++c)
@@ -62,6 +64,7 @@ int main(int argc, char** argv)
 	}
 	std::fclose(fo);
 	std::cerr << "oracle: " << idx << " lines; lmSteps " << cnt.lmSteps << " pairs " << cnt.pairs << " inserts " << cnt.inserts
-		<< " pathsOut " << cnt.pathsOut << " top1Mode " << cnt.top1Mode << " bucketFull " << cnt.bucketFull << std::endl;
+		<< " pathsOut " << cnt.pathsOut << " top1Mode " << cnt.top1Mode << " bucketFull " << cnt.bucketFull
+		<< " maxNodePre " << cnt.maxNodePre << " maxIncoming " << cnt.maxIncoming << " mediumMode " << cnt.mediumMode << " evalCalls " << cnt.evalCalls << " candEvals " << cnt.candEvals << " maxCont " << cnt.maxCont << std::endl;
 	return 0;
 }

@@ -32,7 +32,7 @@ namespace orc
 	struct PathTok { uint32_t morph; uint32_t begin, end; float wordScore; uint32_t nodeId; int32_t strOff; uint32_t strLen; };
 	struct PathResult { std::vector<PathTok> path; float score = 0; uint8_t prevState = 0, curState = 0; };
 
-	struct Counters { uint64_t lmSteps = 0, lmHops = 0, pairs = 0, inserts = 0, pathsOut = 0, top1Mode = 0, bucketFull = 0; };
+	struct Counters { uint64_t lmSteps = 0, lmHops = 0, pairs = 0, inserts = 0, pathsOut = 0, top1Mode = 0, bucketFull = 0, maxNodePre = 0, maxIncoming = 0, mediumMode = 0, evalCalls = 0, candEvals = 0, maxCont = 0; };
 
 	// ---- FeatureTestor, src/FeatureTestor.cpp
 	inline bool ftVowel(const u16* b, const u16* e, uint8_t vowel)                          // :6-60
@@ -366,6 +366,7 @@ namespace orc
 					insertToPathContainer(curId, cLmState, candScore, firstChunkScore, node, prevPath, pNode, (int32_t)pi, rs);
 				}
 			}
+			if (cnt) { size_t tot = 0; for (auto& b : cont.buckets) tot += b.size(); cnt->maxCont = std::max<uint64_t>(cnt->maxCont, tot); }
 			// writeTo, BestPathContainer.hpp:451-469
 			for (auto& b : cont.buckets) for (auto& p : b)
 			{
@@ -430,14 +431,16 @@ namespace orc
 							continue;
 						}
 					}
+					if (cnt) cnt->candEvals++;
 					if (totalPrevPathes <= 128) cont.mode = 0;
-					else if (totalPrevPathes <= 512) cont.mode = 1;
+					else if (totalPrevPathes <= 512) { cont.mode = 1; if (cnt) cnt->mediumMode++; }
 					else { cont.mode = 2; if (cnt) cnt->top1Mode++; }
 					evalSingleMorpheme(nCache, nodeIdx, ownFormId, curId, ignoreCond ? -10.f : 0.f, nodeLevelDiscount);
 				}
 				if (!nCache.empty()) break;
 			}
 
+			if (cnt) { cnt->maxNodePre = std::max<uint64_t>(cnt->maxNodePre, nCache.size()); cnt->maxIncoming = std::max<uint64_t>(cnt->maxIncoming, totalPrevPathes); cnt->evalCalls++; }
 			std::vector<float> maxScores(1 + uniqStates.size(), -INFINITY);
 			for (auto& c : nCache)
 			{

@@ -1,0 +1,52 @@
+"""ctypes access to the ORACLE (oracle/liboracle.so, the CPU restatement).  Test infrastructure only."""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
+IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "knlm_small.img")
+
+
+class Oracle:
+    def __init__(self, image_path=IMAGE):
+        self.lib = C.CDLL(ORACLE_LIB)
+        self.lib.orc_open.restype = C.c_void_p
+        self.lib.orc_open.argtypes = [C.c_char_p]
+        self.lib.orc_close.argtypes = [C.c_void_p]
+        self.lib.orc_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_float)]
+        self.lib.orc_lattice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self.lib.orc_counters.argtypes = [C.c_void_p, C.c_void_p]
+        self.h = self.lib.orc_open(os.fsencode(image_path))
+        if not self.h:
+            raise RuntimeError("oracle: cannot open image " + image_path)
+        self.cap = 1 << 16
+        self.morph = np.zeros(self.cap, np.uint32); self.tag = np.zeros(self.cap, np.uint8); self.pos = np.zeros(self.cap, np.uint32)
+        self.length = np.zeros(self.cap, np.uint16); self.score = np.zeros(self.cap, np.float32)
+
+    def analyze(self, text: str):
+        blob = np.ascontiguousarray(np.frombuffer(text.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
+        s = C.c_float(0)
+        n = self.lib.orc_analyze(self.h, blob.ctypes.data, len(blob), self.morph.ctypes.data, self.tag.ctypes.data, self.pos.ctypes.data,
+                                 self.length.ctypes.data, self.score.ctypes.data, self.cap, C.byref(s))
+        if n < 0:
+            raise RuntimeError("oracle analyze failed")
+        toks = [(int(self.morph[i]), int(self.tag[i]), int(self.pos[i]), int(self.length[i]), float(self.score[i])) for i in range(n)]
+        return toks, float(s.value)
+
+    def lattice(self, text: str) -> np.ndarray:
+        blob = np.ascontiguousarray(np.frombuffer(text.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
+        rows = np.zeros((1 << 16, 9), np.int32)
+        n = self.lib.orc_lattice(self.h, blob.ctypes.data, len(blob), rows.ctypes.data, len(rows))
+        if n < 0:
+            raise RuntimeError("oracle lattice failed")
+        return rows[:n].copy()
+
+    def counters(self):
+        out = np.zeros(6, np.uint64)
+        self.lib.orc_counters(self.h, out.ctypes.data)
+        return dict(zip(["lmSteps", "pairs", "inserts", "pathsOut", "candEvals", "evalCalls"], [int(x) for x in out]))
+
+    def close(self):
+        if self.h:
+            self.lib.orc_close(self.h); self.h = None
