@@ -26,6 +26,8 @@ namespace orc
 		Viterbi viterbi;
 		uint32_t matchOptions = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4) | (1u << 5) | (1u << 23) | (1u << 16);   // Match::allWithNormalizing
 		bool keepChunks = true;
+		WorkCounters work;
+		void enableWorkCounters() { splitter.wc = &work; viterbi.wc = &work; viterbi.lm.wc = &work; }
 
 		explicit Analyzer(const Image& _im) : im{ _im }, splitter{ _im }, viterbi{ _im }
 		{
@@ -75,6 +77,7 @@ namespace orc
 			normalizeHangulWithPosition(text, text + len, norm, positionTable);
 			if (matchOptions & (1u << 16)) normalizeCoda(norm);
 			res.normLen = norm.size();
+			work.sentences++; work.rawUnits += len; work.normUnits += norm.size();
 
 			std::vector<Ret> ret;
 			std::vector<uint8_t> spStatesByRet;
@@ -153,6 +156,7 @@ namespace orc
 			}
 			std::sort(ret.begin(), ret.end(), [](const Ret& a, const Ret& b) { return a.score > b.score; });
 			if (!ret.empty()) { res.tokens = std::move(ret[0].tokens); res.score = ret[0].score; }
+			work.tokens += res.tokens.size();
 			return res;
 		}
 	};

@@ -12,6 +12,17 @@
 
 namespace orc
 {
+	// work counters of the byte model; filled when a pointer is installed
+	struct WorkCounters
+	{
+		uint64_t sentences = 0, rawUnits = 0, normUnits = 0;
+		uint64_t trieVisits = 0, trieProbes = 0, trieHits = 0, candForms = 0;      // V_t, sum ceil(log2(k+1)), H_t, C
+		uint64_t nodesBuilt = 0, nodesFinal = 0;                                    // L, L'
+		uint64_t candEntries = 0, candEvals = 0;                                    // sum cand (ids read), sum C_v (morpheme records)
+		uint64_t lmSteps = 0, lmHops = 0, lmProbes = 0;                             // progress() calls, H_lm, sum ceil(log2(k+1))
+		uint64_t pairs = 0, pathsWritten = 0, pathsKept = 0, tokens = 0;           // P_read, P (container inserts), surviving, T
+	};
+	inline uint32_t ceilLog2p1(uint32_t k) { uint32_t r = 0; while ((1u << r) < k + 1) ++r; return r; }
 	// reference POSTag values used by name (include/kiwi/Types.h:195-227)
 	enum Tag : uint8_t
 	{

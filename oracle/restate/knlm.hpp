@@ -9,10 +9,12 @@ namespace orc
 	struct Knlm
 	{
 		const Image& im;
+		mutable WorkCounters* wc = nullptr;
 		explicit Knlm(const Image& _im) : im{ _im } {}
 
 		bool search(const kb2_kn_node& n, uint32_t key, int32_t& v) const
 		{
+			if (wc) wc->lmProbes += ceilLog2p1(n.num_nexts);
 			const uint32_t* keys = im.knKeys + n.next_offset;
 			const uint32_t* it = std::lower_bound(keys, keys + n.num_nexts, key);
 			if (it == keys + n.num_nexts || *it != key) return false;
@@ -32,11 +34,13 @@ namespace orc
 
 		float progress(int32_t& nodeIdx, uint32_t next) const
 		{
+			if (wc) wc->lmSteps++;
 			float acc = 0;
 			while (1)
 			{
 				int32_t v;
 				const kb2_kn_node* node = &im.knNodes[nodeIdx];
+				if (wc) wc->lmHops++;
 				if (nodeIdx == 0)
 				{
 					v = im.knRoot[next];
@@ -65,6 +69,7 @@ namespace orc
 					while (node->lower)
 					{
 						node += node->lower;
+						if (wc) wc->lmHops++;
 						int32_t lv;
 						if (search(*node, next, lv))
 						{

@@ -36,6 +36,7 @@ namespace orc
 		const u16* rawStr = nullptr; size_t rawLen = 0; size_t startOffset = 0;
 		std::vector<int32_t> candidates;
 
+		WorkCounters* wc = nullptr;
 		explicit Splitter(const Image& _im) : im{ _im }, pat{ _im } {}
 
 		static constexpr uint32_t MATCH_ZCODA = 1u << 23, MATCH_SPLIT_SAISIOT = 1u << 25, MATCH_MERGE_SAISIOT = 1u << 26;
@@ -192,6 +193,7 @@ namespace orc
 		{
 			for (const int32_t cand : candidates)
 			{
+				if (wc) wc->candForms++;
 				const size_t nBegin = endPosition - formSizeWithoutSpace(cand) + startPosOffset;
 				const size_t nEnd = endPosition;
 				const u16* fs = im.formStr(cand);
@@ -222,9 +224,11 @@ namespace orc
 		int32_t nextOpt(int32_t node, u16 c) const
 		{
 			const auto& n = im.trieNodes[node];
+			if (wc) { wc->trieVisits++; wc->trieProbes += ceilLog2p1(n.num_nexts); }
 			const u16* keys = im.trieKeys + n.next_offset;
 			const u16* it = std::lower_bound(keys, keys + n.num_nexts, c);
 			if (it == keys + n.num_nexts || *it != c) return -1;
+			if (wc) wc->trieHits++;
 			return node + im.trieDiffs[n.next_offset + (it - keys)];
 		}
 		int32_t failOf(int32_t node) const { return im.trieNodes[node].fail ? node + im.trieNodes[node].fail : -1; }
@@ -347,6 +351,7 @@ namespace orc
 					for (int32_t sub = curNode; sub >= 0; sub = failOf(sub))
 					{
 						const int32_t v = im.trieNodes[sub].value;
+						if (wc && sub != curNode) wc->trieVisits++;
 						if (v == KB2_TRIE_NONE) break;
 						else if (v != KB2_TRIE_SUBMATCH) candidates.push_back(v);    // minFormLen == 0 without typos
 					}
@@ -443,6 +448,7 @@ namespace orc
 			out.emplace_back();
 			search();
 			removeUnconnected(ret);
+			if (wc) { wc->nodesBuilt += out.size(); wc->nodesFinal += ret.size(); }
 			for (size_t i = 1; i + 1 < ret.size(); ++i)
 			{
 				auto& r = ret[i];

@@ -14,6 +14,7 @@ void* orc_open(const char* imagePath)
 		h->im.load(imagePath);
 		h->an = new orc::Analyzer{ h->im };
 		h->an->viterbi.cnt = &h->cnt;
+		h->an->enableWorkCounters();
 		return h;
 	}
 	catch (...) { return nullptr; }
@@ -70,6 +71,14 @@ int orc_lattice(void* p, const uint16_t* text, int len, int32_t* rows, int maxRo
 		return n;
 	}
 	catch (...) { return -1; }
+}
+
+// byte-model counters accumulated since open, as 18 uint64 in declaration order of orc::WorkCounters
+void orc_work_counters(void* p, uint64_t* out)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	static_assert(sizeof(orc::WorkCounters) == 18 * sizeof(uint64_t), "WorkCounters layout");
+	std::memcpy(out, &h->an->work, sizeof(orc::WorkCounters));
 }
 
 // work counters accumulated since open: {lmSteps, pairs, inserts, pathsOut, candEvals, evalCalls}

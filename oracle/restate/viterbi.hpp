@@ -108,6 +108,7 @@ namespace orc
 		Knlm lm;
 		kb2_config cfg;
 		Counters* cnt = nullptr;
+		WorkCounters* wc = nullptr;
 
 		// per-call state
 		const LNode* graph = nullptr; size_t graphSize = 0;
@@ -215,6 +216,7 @@ namespace orc
 			float accTypoCost, float accDialectCost, int32_t pNode, int32_t pIdx, uint8_t parentRootId, int32_t lmState, uint8_t spState)
 		{
 			if (cnt) cnt->inserts++;
+			if (wc) wc->pathsWritten++;
 			uint64_t h = (uint64_t)(int64_t)lmState;                                       // Knlm.hpp:1170-1178 std::hash<int32_t>
 			h = ((uint16_t)prevRootId | ((uint16_t)spState << 8)) ^ ((h << 3) | (h >> 61)); // BestPathContainer.hpp:79-84
 			const size_t bucket = cont.mode == 1 ? ((h >> 8) & 3) : 0;
@@ -309,6 +311,7 @@ namespace orc
 				{
 					const WordLL& prevPath = pc[pi];
 					if (cnt) cnt->pairs++;
+					if (wc) wc->pairs++;
 					if (M(prevPath.morpheme).tag == T_z_siot && (!isNNClass(cur.tag) || prev->endPos < node->startPos)) continue;
 					float candScore = prevPath.accScore + additionalScore;
 					float firstChunkScore = additionalScore;
@@ -432,6 +435,7 @@ namespace orc
 						}
 					}
 					if (cnt) cnt->candEvals++;
+					if (wc) wc->candEvals++;
 					if (totalPrevPathes <= 128) cont.mode = 0;
 					else if (totalPrevPathes <= 512) { cont.mode = 1; if (cnt) cnt->mediumMode++; }
 					else { cont.mode = 2; if (cnt) cnt->top1Mode++; }
@@ -589,6 +593,7 @@ namespace orc
 				if (node->form >= 0)
 				{
 					const auto& f = im.forms[node->form];
+					if (wc) wc->candEntries += f.cand_cnt;
 					evaluate(i, ownFormId, im.formCands + f.cand_off, f.cand_cnt, 0.f);
 					bool allPartial = true;
 					for (uint32_t c = 0; c < f.cand_cnt; ++c)
@@ -619,6 +624,7 @@ namespace orc
 					evaluate(i, ownFormId, unknownNodeCands, 2, unkScore);
 				}
 				if (cnt) cnt->pathsOut += cache[i].size();
+				if (wc) wc->pathsKept += cache[i].size();
 			}
 
 			// end node

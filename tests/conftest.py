@@ -1,0 +1,28 @@
+import os, sys
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from tests.orc import Oracle, IMAGE
+    if not os.path.exists(IMAGE):
+        pytest.skip("model image missing: run __graft_entry__.build() where /root/reference exists")
+    o = Oracle(IMAGE)
+    yield o
+    o.close()
+
+
+@pytest.fixture(scope="session")
+def kiwi():
+    import kiwi_b200
+    from tests.orc import IMAGE
+    kw = kiwi_b200.Kiwi(IMAGE)      # raises when the CUDA extension or the GPU is missing: no fallback
+    yield kw
+    kw.close()

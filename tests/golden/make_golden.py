@@ -1,0 +1,24 @@
+#!/usr/bin/env python3
+"""Regenerates the golden vectors from the UNMODIFIED reference (oracle/_ref/dump_golden, built by
+oracle/ref_build/Makefile from /root/reference) on the committed input files.  Run here (needs oracle/_ref);
+the .golden.txt.gz outputs are committed so that neither the CPU suite nor the GPU box needs the reference.
+Format: see oracle/ref_build/tools/dump_golden.cpp.  MANIFEST.json records the md5 of the model image the
+vectors belong to (the fabricated Knlm model is rebuilt deterministically by oracle/Makefile)."""
+import gzip, hashlib, json, os, subprocess, sys
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+IMAGE = os.path.join(REFDIR, "models", "knlm_small.img")
+manifest = {"image_md5": hashlib.md5(open(IMAGE, "rb").read()).hexdigest(), "model": "knlm_small (fabricated, see oracle/Makefile)",
+            "reference_arch": "avx2", "files": {}}
+for name in ["inputs_ref_tests", "inputs_web", "inputs_written"]:
+    src = os.path.join(HERE, name + ".txt")
+    tmp = os.path.join("/tmp", name + ".golden.txt")
+    env = dict(os.environ, KIWI_ARCH_TYPE="avx2")
+    subprocess.run([os.path.join(REFDIR, "dump_golden"), os.path.join(REFDIR, "models", "knlm_small"), src, tmp], check=True, env=env)
+    data = open(tmp, "rb").read()
+    with gzip.GzipFile(os.path.join(HERE, name + ".golden.txt.gz"), "wb", mtime=0) as f:
+        f.write(data)
+    manifest["files"][name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
+json.dump(manifest, open(os.path.join(HERE, "MANIFEST.json"), "w"), indent=1)
+print(manifest)

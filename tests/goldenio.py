@@ -1,0 +1,37 @@
+"""Reader for the golden dumps written by oracle/ref_build/tools/dump_golden.cpp (test infrastructure)."""
+import gzip, os
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def read_inputs(name):
+    with open(os.path.join(HERE, name + ".txt"), encoding="utf-8", errors="surrogatepass") as f:
+        return [l.rstrip("\n").rstrip("\r").split("\t")[0] for l in f]
+
+
+def read_golden(name):
+    """-> list of dict(tokens=[(morph, tag, pos, len, score)], score=float, lattice=[[9 ints]], chunks=[...])"""
+    out = []
+    cur = None; chunk_idx = -1; kept_chunk = -1
+    with gzip.open(os.path.join(HERE, name + ".golden.txt.gz"), "rt") as f:
+        for line in f:
+            p = line.split()
+            k = p[0]
+            if k == "S":
+                cur = dict(tokens=[], score=float.fromhex(p[3]), lattice=[], paths=[], norm_len=int(p[5]))
+                out.append(cur); kept_chunk = -1
+            elif k == "T":
+                cur["tokens"].append((int(p[1]) & 0xFFFFFFFF, int(p[2]), int(p[3]), int(p[4]), float.fromhex(p[5])))
+            elif k == "C":
+                n_nodes = int(p[4])
+                cur["_keep"] = n_nodes > 2
+                if cur["_keep"]: kept_chunk += 1
+            elif k == "N":
+                if cur["_keep"]:
+                    form, uoff, ulen, prev, sib, st, en, se = (int(x) for x in p[1:9])
+                    cur["lattice"].append([form, uoff if ulen else -1, ulen, prev, sib, st, en, se, kept_chunk])
+            elif k == "P":
+                cur["paths"].append(dict(score=float.fromhex(p[1]), prev=int(p[2]), cur=int(p[3]), toks=[]))
+            elif k == "K":
+                cur["paths"][-1]["toks"].append((int(p[1]), int(p[2]), int(p[3]), float.fromhex(p[4])))
+    return out

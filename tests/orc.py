@@ -47,6 +47,15 @@ class Oracle:
         self.lib.orc_counters(self.h, out.ctypes.data)
         return dict(zip(["lmSteps", "pairs", "inserts", "pathsOut", "candEvals", "evalCalls"], [int(x) for x in out]))
 
+    WORK_FIELDS = ["sentences", "rawUnits", "normUnits", "trieVisits", "trieProbes", "trieHits", "candForms", "nodesBuilt", "nodesFinal",
+                   "candEntries", "candEvals", "lmSteps", "lmHops", "lmProbes", "pairs", "pathsWritten", "pathsKept", "tokens"]
+
+    def work_counters(self):
+        self.lib.orc_work_counters.argtypes = [C.c_void_p, C.c_void_p]
+        out = np.zeros(18, np.uint64)
+        self.lib.orc_work_counters(self.h, out.ctypes.data)
+        return dict(zip(self.WORK_FIELDS, [int(x) for x in out]))
+
     def close(self):
         if self.h:
             self.lib.orc_close(self.h); self.h = None
