@@ -100,6 +100,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from kiwi_b200.synth import synth_batch, SEED
@@ -205,7 +206,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("viterbi_kernel_dram_bytes_per_launch")
-    cpu = run_reference_cpu(batches[0][0][:args.cpu_sample], os.cpu_count() or 1) if world == 1 else None
+    cpu = run_reference_cpu(batches[0][0][:args.cpu_sample], os.cpu_count() or 1) if (world == 1 and not args.no_cpu) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

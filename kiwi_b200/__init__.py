@@ -15,7 +15,7 @@ from typing import Iterable, List, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkiwi_b200.so")
+LIB_PATH = os.environ.get("KIWI_B200_LIB", os.path.join(_HERE, "libkiwi_b200.so"))   # env override: kernel-variant experiments only
 
 MATCH_ALL = 1 | 2 | 4 | 8 | 16 | 32 | (1 << 23)
 MATCH_ALL_WITH_NORMALIZING = MATCH_ALL | (1 << 16)

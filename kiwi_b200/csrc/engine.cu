@@ -1,6 +1,6 @@
 // kiwi_b200: host engine.  Owns the device-resident model, the per-batch scratch arena and the stream; turns
-// one batch of raw UTF-16 sentences into flat token arrays with exactly three compute launches
-// (lattice_kernel, viterbi_kernel, pack_kernel) plus one cub scan.
+// one batch of raw UTF-16 sentences into flat token arrays with exactly four compute launches
+// (lattice_kernel, viterbi_kernel, emit_kernel, pack_kernel) plus one cub scan.
 //
 // Host role (the reference does all of this per sentence on CPU threads, src/Kiwi.cpp:1014-1158 and
 // include/kiwi/Kiwi.h:402-454): here the host only copies the text blob + offsets in and the packed
@@ -19,6 +19,7 @@ namespace kb
 {
 	cudaError_t launch_lattice(const DevModel& m, const BatchView& bv, cudaStream_t stream);
 	cudaError_t launch_viterbi(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
+	cudaError_t launch_emit(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
 
 	static void ck(cudaError_t e, const char* what)
 	{
@@ -94,6 +95,7 @@ namespace kb
 		vv.recs = (DRec*)alloc(2 * chunkSlots * sizeof(DRec));
 		vv.tokens = (DToken*)alloc(capU * sizeof(DToken));
 		vv.n_tokens = (uint32_t*)alloc((capB + 1) * 4);
+		vv.best_rec = (int32_t*)alloc(capB * 4);
 		vv.score = (float*)alloc(capB * 4);
 		sc.tokOff = (uint32_t*)alloc((capB + 1) * 4);
 		sc.packed = (DToken*)alloc(capU * sizeof(DToken));
@@ -117,6 +119,7 @@ namespace kb
 		ck(cudaEventRecord(ev[2], stream), "event");
 		ck(launch_viterbi(model.dev, sc.bv, sc.vv, stream), "viterbi_kernel launch");
 		ck(cudaEventRecord(ev[3], stream), "event");
+		ck(launch_emit(model.dev, sc.bv, sc.vv, stream), "emit_kernel launch");
 		ck(cudaMemsetAsync(sc.vv.n_tokens + n, 0, 4, stream), "memset");
 		size_t tb = sc.cubTempBytes;
 		ck(cub::DeviceScan::ExclusiveSum(sc.cubTemp, tb, sc.vv.n_tokens, sc.tokOff, (int)(n + 1), stream), "cub scan");
@@ -210,7 +213,7 @@ namespace kb
 			cudaEventElapsedTime(&ms, ev[0], ev[5]); out.msTotal += ms;
 			last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4;
 			last.d2hBytes += headBytes + (size_t)total * sizeof(DToken);
-			last.kernelLaunches += 3;
+			last.kernelLaunches += 4;
 
 			if (pass == 0)
 			{
@@ -266,7 +269,7 @@ namespace kb
 		cudaEventElapsedTime(&a, ev[1], ev[2]); last.msLattice = a;
 		cudaEventElapsedTime(&a, ev[2], ev[3]); last.msViterbi = a;
 		cudaEventElapsedTime(&a, ev[3], ev[4]); last.msPack = a;
-		last.nSentences = n; last.rawUnits = totalUnits; last.tokens = total; last.kernelLaunches = 3; last.h2dBytes = 0; last.d2hBytes = 4;
+		last.nSentences = n; last.rawUnits = totalUnits; last.tokens = total; last.kernelLaunches = 4; last.h2dBytes = 0; last.d2hBytes = 4;
 		if (nTokens) *nTokens = total;
 		return ms;
 	}

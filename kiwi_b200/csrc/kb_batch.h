@@ -57,6 +57,7 @@ namespace kb
 		DRec* recs;                  // 2 per chunk slot: 2 * ((wbase >> 2) + 2 * s)
 		DToken* tokens;              // output, W_s per sentence at wbase
 		uint32_t* n_tokens;          // [n_sent]
+		int32_t* best_rec;           // [n_sent] record of the best stitched result, -1 = none
 		float* score;                // [n_sent]
 	};
 

@@ -80,6 +80,18 @@ namespace kb
 		uint32_t misc;        // MM_* bits
 	};
 
+	// static per-candidate data of evalSingleMorpheme (PathEvaluator.hpp:531-556) and of the path it creates
+	enum : uint8_t { MX_FIRST_IS_P = 1, MX_CHUNK_HAS_P = 2 };
+	struct DMorphX            // 16 B
+	{
+		uint32_t first_wid;       // isSingle ? lmMorphemeId : chunks[0]->lmMorphemeId
+		uint32_t last_seq_id;     // `lastSeqId` = wid of the created path
+		uint32_t last_seq_feat;   // DMorph::feat of morphemes[last_seq_id]
+		uint16_t left_last;       // left-form features of the created path when it has no own form
+		uint8_t left_pol;         // LP_* bits (kb_batch.h)
+		uint8_t xflags;           // MX_*
+	};
+
 	// ---- form feature record
 	enum : uint8_t
 	{
@@ -125,6 +137,8 @@ namespace kb
 		const kb2_chr_run* chr_runs;
 		// derived
 		const DMorph* morphs;
+		const DMorphX* morphx;
+		const uint32_t* chunk_lm;      // lmMorphemeId of every chunk entry (parallel to `chunks`)
 		const DForm* forms;
 		const uint32_t* chr_bmp;       // [65536] cls | script << 8 | flags << 16
 		const int32_t* trie_root_next; // [65536] child node index of the root, -1 = none

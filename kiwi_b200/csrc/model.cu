@@ -182,6 +182,38 @@ namespace kb
 			dmorphs[i] = d;
 		}
 
+		// ---- static candidate data
+		const kb2_chunk* chunksH = reinterpret_cast<const kb2_chunk*>(sec(KB2_SEC_MORPH_CHUNKS));
+		std::vector<uint32_t> chunkLm(h->n_chunks);
+		for (uint32_t i = 0; i < h->n_chunks; ++i) chunkLm[i] = morphs[chunksH[i].morph].lm_morpheme_id;
+		std::vector<DMorphX> dmx(h->n_morphs);
+		for (uint32_t i = 0; i < h->n_morphs; ++i)
+		{
+			const kb2_morph& m = morphs[i];
+			const bool single = (dmorphs[i].feat & MF_SINGLE) != 0;
+			DMorphX x;
+			int64_t lastMorph;
+			if (single) { lastMorph = m.combined ? (int64_t)i + m.combined : (int64_t)i; x.first_wid = m.lm_morpheme_id; }
+			else { lastMorph = chunksH[m.chunk_off + m.chunk_cnt - 1].morph; x.first_wid = chunkLm[m.chunk_off]; }
+			if (lastMorph < 0 || lastMorph >= (int64_t)h->n_morphs) lastMorph = i;
+			if ((uint64_t)lastMorph >= h->lang_vocab_size) x.last_seq_id = (uint32_t)lastMorph;
+			else x.last_seq_id = morphs[lastMorph].lm_morpheme_id;
+			if (x.last_seq_id >= h->n_morphs) x.last_seq_id = 0;
+			if (x.first_wid >= h->n_morphs) x.first_wid = 0;
+			x.last_seq_feat = dmorphs[x.last_seq_id].feat;
+			// left form seen by FormEvaluator when the path has no own form: kform of morphemes[wid], else of the morpheme
+			int32_t fi = morphs[x.last_seq_id].form_idx;
+			if (!(fi >= 0 && forms[fi].str_len)) fi = m.form_idx;
+			if (fi < 0 || forms[fi].str_len == 0) { x.left_last = 0; x.left_pol = LP_EMPTY | LP_POLAR_POS | LP_POLAR_NEG; }
+			else { x.left_last = dforms[fi].last_chr; x.left_pol = dforms[fi].pol & (FP_POLAR_POS | FP_POLAR_NEG | FP_LAST_SSC); }
+			if (m.combine_socket) x.left_pol |= LP_MORPH_SOCKET;
+			uint8_t xf = 0;
+			if ((dmorphs[x.first_wid].feat & MF_TAG_MASK) == T_p) xf |= MX_FIRST_IS_P;
+			if (!single) for (uint32_t c = 1; c < m.chunk_cnt; ++c) if ((dmorphs[chunkLm[m.chunk_off + c]].feat & MF_TAG_MASK) == T_p) xf |= MX_CHUNK_HAS_P;
+			x.xflags = xf;
+			dmx[i] = x;
+		}
+
 		// ---- upload
 		void* dBlob = nullptr;
 		cudaCheck(cudaMalloc(&dBlob, size), "cudaMalloc(image)");
@@ -204,6 +236,8 @@ namespace kb
 		d.kn_htx = h->kn_has_htx ? reinterpret_cast<const uint32_t*>(dsec(KB2_SEC_KN_HTX)) : nullptr;
 		d.chr_runs = reinterpret_cast<const kb2_chr_run*>(dsec(KB2_SEC_CHR_RUNS));
 		d.morphs = upload(dmorphs, owned);
+		d.morphx = upload(dmx, owned);
+		d.chunk_lm = upload(chunkLm, owned);
 		d.forms = upload(dforms, owned);
 		d.chr_bmp = upload(bmp, owned);
 		d.trie_root_next = upload(rootNext, owned);

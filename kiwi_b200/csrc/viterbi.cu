@@ -32,6 +32,25 @@ namespace kb
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
 	static constexpr uint8_t COMMON_ROOT = 0xFF;
 	static constexpr uint32_t HT_SIZE = 1024, HT_MAX_ENTRIES = 768;
+	static constexpr uint32_t STAGE_CAP = 128, ITEM_CAP = 512, CAND_CAP = 24;
+
+	// static + per-node data of one candidate morpheme, staged in shared memory for the batched fast path
+	struct CandS
+	{
+		int32_t curId; uint32_t firstWid, lastSeqId, feat, lastSeqFeat, chunkOff;
+		float additionalScore;
+		uint16_t leftLast; uint8_t leftPol, chunkCnt, flags, pathSocket, senseId, pad;
+	};
+	enum : uint8_t { CS_POSITIVE_E = 1, CS_SN_POINT = 2, CS_SINGLE = 4, CS_NO_LM = 8 };
+
+	struct WarpSmem
+	{
+		unsigned long long filt[STAGE_CAP];     // left_last | left_pol << 16 | morph_tag << 24 | combine_socket << 32 | root_id << 40 | sp_state << 48
+		float acc[STAGE_CAP]; int32_t lm[STAGE_CAP]; uint32_t widFeat[STAGE_CAP];
+		uint16_t ht[HT_SIZE];
+		uint16_t item[ITEM_CAP];                // slot << 8 | q << 1 | condFail
+		CandS cand[CAND_CAP];
+	};
 	static constexpr uint32_t WARPS_PER_BLOCK = 4;
 	static constexpr uint32_t MAX_RESULTS = 16;
 
@@ -126,6 +145,7 @@ namespace kb
 		uint32_t* npOff; uint32_t* npCnt; uint8_t* reach;
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
+		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0, nCandS = 0;
 		bool splitComplex, splitSaisiot, mergeSaisiot;
 
 		__device__ Vit(const DevModel& _m, const BatchView& _bv, const VitView& _vv, uint32_t _lane) : m{ _m }, bv{ _bv }, vv{ _vv }, lane{ _lane } {}
@@ -510,6 +530,177 @@ namespace kb
 			}
 		}
 
+
+		// ---- batched fast path (mode 0: <= 128 incoming paths, non-forking, non-socket-chunk candidates) ----
+		// The incoming paths of the node are staged once in shared memory.  For every candidate a cheap filter pass
+		// (z_siot / combine-socket / FormEvaluator conditions) appends the surviving (candidate, path) pairs to an
+		// item list; the list is drained 32 items at a time, so the expensive part - the Knlm pointer chase - runs
+		// with full lanes across candidate boundaries.  Items are in (candidate, path) order, new container
+		// entries are appended in item order, hence the output is candidate-major in first-insertion order
+		// exactly like the per-candidate containers of the reference; with <= 128 incoming paths a 128-slot
+		// container cannot overflow, so no capacity bookkeeping is needed here.
+		__device__ void stagePaths(uint32_t nodeIdx, uint32_t inBeg, uint32_t P)
+		{
+			if (stagedNode == nodeIdx) return;
+			for (uint32_t q = lane; q < P; q += 32)
+			{
+				const DPath* p = pool + inBeg + q;
+				sm->filt[q] = (unsigned long long)p->left_last | ((unsigned long long)p->left_pol << 16) | ((unsigned long long)p->morph_tag << 24)
+					| ((unsigned long long)p->combine_socket << 32) | ((unsigned long long)p->root_id << 40) | ((unsigned long long)p->sp_state << 48);
+				sm->acc[q] = p->acc_score; sm->lm[q] = p->lm_state; sm->widFeat[q] = p->wid_feat;
+			}
+			stagedNode = nodeIdx;
+			__syncwarp();
+		}
+
+		__device__ void filterCand(uint32_t slot, uint32_t curFeat, bool spaceBefore, float ignoreCondScore, uint32_t P)
+		{
+			const uint32_t curTag = curFeat & MF_TAG_MASK;
+			const uint32_t cv = (curFeat >> MF_VOWEL_SHIFT) & 15, cp = (curFeat >> MF_POLAR_SHIFT) & 3;
+			const bool curNN = isNNClass((uint8_t)curTag);
+			for (uint32_t qb = 0; qb < P; qb += 32)
+			{
+				const uint32_t q = qb + lane;
+				bool valid = q < P, condFail = false;
+				if (valid)
+				{
+					const unsigned long long f = sm->filt[q];
+					const uint32_t leftLast = (uint32_t)f & 0xFFFF, leftPol = (uint32_t)(f >> 16) & 0xFF, morphTag = (uint32_t)(f >> 24) & 0xFF, socket = (uint32_t)(f >> 32) & 0xFF;
+					if (morphTag == T_z_siot && (!curNN || spaceBefore)) valid = false;
+					else if (socket) valid = false;
+					else if (morphTag == T_ssc || (leftPol & LP_LAST_SSC)) {}
+					else
+					{
+						const bool empty = (leftPol & LP_EMPTY) != 0;
+						bool ok = ftVowel(empty, (uint16_t)leftLast, (uint8_t)cv);
+						if (ok && (cp == CP_positive || cp == CP_negative)) ok = empty ? true : ((leftPol & (cp == CP_positive ? LP_POLAR_POS : LP_POLAR_NEG)) != 0);
+						if (ignoreCondScore != 0.f) condFail = !ok;
+						else if (!ok) valid = false;
+					}
+				}
+				const unsigned vm = __ballot_sync(FULL, valid);
+				if (valid) sm->item[nItems + __popc(vm & ((1u << lane) - 1))] = (uint16_t)((slot << 8) | (q << 1) | (condFail ? 1u : 0u));
+				nItems += __popc(vm);
+			}
+			__syncwarp();
+		}
+
+		__device__ void flushItems(uint32_t nodeIdx, const DNode& node, uint32_t inBeg, float ignoreCondScore, uint32_t ownOff, uint32_t ownLen, uint16_t ownLeftLast, uint8_t ownLeftPol)
+		{
+			if (!nItems) { nCandS = 0; return; }
+			htClear();
+			const uint32_t batchBeg = top;
+			uint32_t E = 0;
+			for (uint32_t ib = 0; ib < nItems; ib += 32)
+			{
+				const uint32_t i = ib + lane;
+				const bool valid = i < nItems;
+				uint32_t slot = 0, q = 0; bool condFail = false;
+				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 8; q = (it >> 1) & 127; condFail = it & 1; }
+				const CandS cs = sm->cand[slot];
+				int32_t lmState = 0; float accScore = 0, fcs = 0; uint32_t prevRoot = 0; uint8_t spState = 0;
+				if (valid)
+				{
+					const unsigned long long f = sm->filt[q];
+					prevRoot = (uint32_t)(f >> 40) & 0xFF; spState = (uint8_t)(f >> 48);
+					float candScore = sm->acc[q] + cs.additionalScore;
+					float firstChunkScore = cs.additionalScore;
+					if (condFail) candScore += ignoreCondScore;
+					lmState = sm->lm[q];
+					if (!(cs.flags & CS_NO_LM))
+					{
+						float ll = knProgress(m, lmState, cs.firstWid);
+						candScore += ll; firstChunkScore += ll;
+						if (!(cs.flags & CS_SINGLE))
+						{
+							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = knProgress(m, lmState, m.chunk_lm[cs.chunkOff + c]); candScore += ll; }
+						}
+					}
+					// RuleBasedScorer (PathEvaluator.hpp:115-183) for a non-forking candidate: spState is the parent's
+					const uint32_t pf = sm->widFeat[q], ptag = pf & MF_TAG_MASK;
+					const uint32_t specialType = (cs.feat >> MF_SPECIAL_SHIFT) & 7;
+					float rs = 0;
+					if ((cs.feat & MF_VOWEL_E) && isIrregular((uint8_t)ptag)) rs -= 10;
+					if ((cs.feat & MF_INF_J) && (pf & MF_INFL_NP)) rs -= 5;
+					if ((cs.feat & MF_BADPAIR_L) && (pf & MF_VERB_L)) rs -= 7;
+					if ((cs.flags & CS_POSITIVE_E) && !(pf & MF_POS_VERB)) rs -= 100;
+					if ((cs.feat & MF_CONTRACT_E) && (pf & MF_VERB_VOWEL)) rs -= 3;
+					if (((cs.feat >> MF_POLAR_SHIFT) & 3) == CP_non_adj && (ptag == T_va || ptag == T_xsa)) rs -= 10;
+					if (specialType <= 2) { if (specialType != (spState & 1u)) rs -= 2; }
+					else if (specialType <= 5) { if (specialType - 3 != ((spState >> 1) & 1u)) rs -= 2; }
+					if ((cs.flags & CS_SN_POINT) && (ptag == T_unknown || ptag == T_ef || ptag == T_sf)) rs -= 5;
+					accScore = candScore + rs;
+					fcs = firstChunkScore + rs;
+					accScore = accScore - 0.f; fcs = fcs - 0.f;
+				}
+				// de-duplication by (candidate, lmState, prevRootId, spState): best score, earliest item on ties
+				const unsigned long long key = valid
+					? ((unsigned long long)(uint32_t)lmState | ((unsigned long long)prevRoot << 32) | ((unsigned long long)spState << 40) | ((unsigned long long)slot << 48))
+					: (0xFFFF000000000000ull | lane);
+				const unsigned grp = __match_any_sync(FULL, key);
+				uint32_t ord = __float_as_uint(accScore);
+				ord = (ord & 0x80000000u) ? ~ord : (ord | 0x80000000u);
+				const uint32_t gmax = __reduce_max_sync(grp, ord);
+				const unsigned bestMask = __ballot_sync(FULL, valid && ord == gmax) & grp;
+				const uint32_t bestLane = __ffs(bestMask) - 1;
+				const uint32_t leader = __ffs(grp) - 1;
+				const bool isLeader = valid && lane == leader;
+				uint32_t found = NPOS;
+				const uint32_t h0 = htHash(lmState, prevRoot | (slot << 8), spState);
+				if (isLeader && E)
+				{
+					uint32_t hs = h0;
+					while (true)
+					{
+						const uint32_t e = ht[hs];
+						if (!e) break;
+						const DPath* tp = pool + batchBeg + (e - 1);
+						if (tp->lm_state == lmState && tp->morpheme == cs.curId && tp->prev_root_id == prevRoot && tp->sp_state == spState) { found = e - 1; break; }
+						hs = (hs + 1) & (HT_SIZE - 1);
+					}
+				}
+				const bool isNew = isLeader && found == NPOS;
+				const unsigned nmask = __ballot_sync(FULL, isNew);
+				const uint32_t totalNew = __popc(nmask);
+				uint32_t newIdx = NPOS;
+				if (isNew) newIdx = E + __popc(nmask & ((1u << lane) - 1));
+				if (batchBeg + E + totalNew > poolCap || E + totalNew > HT_MAX_ENTRIES) { err = ST_PATH_OVERFLOW; return; }
+				if (isNew)
+				{
+					uint32_t hs = h0;
+					while (atomicCAS_u16(hs, newIdx + 1)) hs = (hs + 1) & (HT_SIZE - 1);
+				}
+				if (totalNew) htUsed = 1;
+				E += totalNew;
+				__syncwarp();
+				const uint32_t tgtNew = __shfl_sync(FULL, newIdx, leader);
+				const uint32_t tgtOld = __shfl_sync(FULL, found, leader);
+				if (valid && lane == bestLane)
+				{
+					const uint32_t tgt = tgtOld != NPOS ? tgtOld : tgtNew;
+					bool write = true;
+					if (tgtOld != NPOS) write = accScore > pool[batchBeg + tgt].acc_score;
+					if (write)
+					{
+						const bool single = (cs.flags & CS_SINGLE) != 0;
+						const bool own = single && ownLen;
+						DPath np;
+						np.lm_state = lmState; np.acc_score = accScore; np.first_chunk_score = fcs; np.wid = cs.lastSeqId;
+						np.morpheme = cs.curId; np.parent = inBeg + q; np.own_off = own ? ownOff : 0; np.acc_typo_cost = pool[inBeg + q].acc_typo_cost + node.typo_cost;
+						np.own_len = own ? (uint16_t)ownLen : 0; np.node = (uint16_t)nodeIdx;
+						np.left_last = own ? ownLeftLast : cs.leftLast;
+						np.left_pol = own ? (uint8_t)(ownLeftPol | (cs.leftPol & LP_MORPH_SOCKET)) : cs.leftPol;
+						np.sp_state = spState; np.root_id = (uint8_t)prevRoot; np.combine_socket = cs.pathSocket; np.prev_root_id = (uint8_t)prevRoot;
+						np.morph_tag = (uint8_t)(cs.feat & MF_TAG_MASK); np.wid_feat = cs.lastSeqFeat;
+						pool[batchBeg + tgt] = np;
+					}
+				}
+				__syncwarp();
+			}
+			top = batchBeg + E;
+			nItems = 0; nCandS = 0;
+		}
+
 		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
 		// cands: either a form's candidate list (formCands != nullptr) or the default unknown candidates
 		__device__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const uint32_t* candList, uint32_t nCands, uint32_t unk0, uint32_t unk1,
@@ -525,6 +716,14 @@ namespace kb
 			const uint32_t mode = P <= 128 ? 0 : (P <= 512 ? 1 : 2);
 			const bool spaceBefore = nodes[nodeIdx - node.prev].end_pos < node.start_pos;
 			const bool hasLB = hasLeftBoundary(nodeIdx);
+			const bool fastOK = mode == 0;
+			uint16_t ownLeftLast = 0; uint8_t ownLeftPol = 0;
+			if (fastOK)
+			{
+				stagePaths(nodeIdx, inBeg, P);
+				if (ownLen) leftFeat(ownOff, ownLen, 0, 0, ownLeftLast, ownLeftPol);
+			}
+			nItems = 0; nCandS = 0;
 
 			for (int ignoreCond = 0; ignoreCond < 2; ++ignoreCond)
 			{
@@ -545,6 +744,7 @@ namespace kb
 					if (tag == T_z_coda || tag == T_z_siot)
 					{
 						if (tag == T_z_siot && !(splitSaisiot || mergeSaisiot)) continue;
+						if (fastOK) { flushItems(nodeIdx, node, inBeg, ignoreCond ? -10.f : 0.f, ownOff, ownLen, ownLeftLast, ownLeftPol); if (err) return; }
 						// shortcut (PathEvaluator.hpp:389-432): copy qualifying incoming paths, no LM step
 						const float add = cur.user_score * m.cfg.typo_cost_weight;
 						const DMorph lmM = m.morphs[cur.lm_id];
@@ -595,6 +795,38 @@ namespace kb
 							}
 						}
 					}
+					const float additionalScore = cur.user_score + nodeLevelDiscount + m.tag_left_boundary[hasLB ? 1 : 0][clearIrregular((uint8_t)tag)];
+					const uint32_t specialType0 = (cur.feat >> MF_SPECIAL_SHIFT) & 7, sbType0 = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
+					const bool fork0 = sbType0 != 0 || specialType0 == 0 || specialType0 == 1 || specialType0 == 3 || specialType0 == 4;
+					if (fastOK && !fork0 && (cur.combine_socket == 0 || single))
+					{
+						const DMorphX mx = m.morphx[curId];
+						const bool noLm = cur.combine_socket && single;
+						if (!noLm && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) continue;      // every pair hits `goto continueFor`
+						if (nItems > ITEM_CAP - STAGE_CAP || nCandS == CAND_CAP)
+						{
+							flushItems(nodeIdx, node, inBeg, ignoreCond ? -10.f : 0.f, ownOff, ownLen, ownLeftLast, ownLeftPol);
+							if (err) return;
+						}
+						if (lane == 0)
+						{
+							CandS cs;
+							cs.curId = curId; cs.firstWid = mx.first_wid; cs.lastSeqId = mx.last_seq_id; cs.feat = cur.feat; cs.lastSeqFeat = mx.last_seq_feat;
+							cs.chunkOff = cur.chunk_off; cs.additionalScore = additionalScore; cs.leftLast = mx.left_last; cs.leftPol = mx.left_pol; cs.chunkCnt = cur.chunk_cnt;
+							uint8_t fl = 0;
+							if (isEClass((uint8_t)tag) && node.form >= 0 && (m.forms[node.form].flags & FF_FIRST_IS_A)) fl |= CS_POSITIVE_E;
+							if (tag == T_sn && node.uform_len && norm[node.uform_off + node.uform_len - 1] == '.') fl |= CS_SN_POINT;
+							if (single) fl |= CS_SINGLE;
+							if (noLm) fl |= CS_NO_LM;
+							cs.flags = fl; cs.pathSocket = single ? cur.combine_socket : 0; cs.senseId = cur.sense_id; cs.pad = 0;
+							sm->cand[nCandS] = cs;
+						}
+						__syncwarp();
+						filterCand(nCandS, cur.feat, spaceBefore, ignoreCond ? -10.f : 0.f, P);
+						++nCandS;
+						continue;
+					}
+					if (fastOK) { flushItems(nodeIdx, node, inBeg, ignoreCond ? -10.f : 0.f, ownOff, ownLen, ownLeftLast, ownLeftPol); if (err) return; }
 					CandCtx cc;
 					cc.curId = curId; cc.cur = cur; cc.single = single;
 					int32_t lastMorph;
@@ -606,7 +838,7 @@ namespace kb
 					}
 					if ((uint32_t)lastMorph >= m.lang_vocab_size && (uint32_t)lastMorph < m.n_morphs) cc.lastSeqId = (uint32_t)lastMorph;
 					else cc.lastSeqId = m.morphs[lastMorph].lm_id;
-					cc.additionalScore = cur.user_score + nodeLevelDiscount + m.tag_left_boundary[hasLB ? 1 : 0][clearIrregular((uint8_t)tag)];
+					cc.additionalScore = additionalScore;
 					cc.ignoreCondScore = ignoreCond ? -10.f : 0.f;
 					cc.specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7;
 					cc.sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
@@ -624,6 +856,7 @@ namespace kb
 					evalCand(nodeIdx, node, cc, inBeg, inEnd, mode);
 					if (err) return;
 				}
+				if (fastOK) { flushItems(nodeIdx, node, inBeg, ignoreCond ? -10.f : 0.f, ownOff, ownLen, ownLeftLast, ownLeftPol); if (err) return; }
 				if (top > nodeBeg) break;
 			}
 
@@ -720,6 +953,7 @@ namespace kb
 		__device__ uint32_t findBestPath(const DChunk& ch, PathRes* res, bool openEnding)
 		{
 			const uint32_t chunkBase = top;
+			stagedNode = NPOS;
 			// BOS path (PathEvaluator.hpp:1224-1226)
 			if (top + 1 > poolCap) { err = ST_PATH_OVERFLOW; return 0; }
 			if (lane == 0)
@@ -914,27 +1148,16 @@ namespace kb
 		}
 	};
 
-	// position mapping of insertPathIntoResults (src/Kiwi.cpp:734-737)
-	__device__ __forceinline__ uint32_t upperBound(const uint32_t* t, uint32_t n, uint32_t v)
+	#ifndef KB_VIT_MIN_BLOCKS
+#define KB_VIT_MIN_BLOCKS 4
+#endif
+	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) viterbi_kernel(const DevModel m, const BatchView bv, const VitView vv)
 	{
-		uint32_t lo = 0, hi = n;
-		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (t[mid] <= v) lo = mid + 1; else hi = mid; }
-		return lo;
-	}
-	__device__ __forceinline__ uint32_t lowerBound(const uint32_t* t, uint32_t n, uint32_t v)
-	{
-		uint32_t lo = 0, hi = n;
-		while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (t[mid] < v) lo = mid + 1; else hi = mid; }
-		return lo;
-	}
-
-	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) viterbi_kernel(const DevModel m, const BatchView bv, const VitView vv)
-	{
-		__shared__ uint16_t htAll[WARPS_PER_BLOCK][HT_SIZE];
+		__shared__ WarpSmem smAll[WARPS_PER_BLOCK];
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 		const uint32_t s = blockIdx.x * WARPS_PER_BLOCK + wib;
 		if (s >= bv.n_sent) return;
-		if (bv.status[s]) { if (lane == 0) { vv.n_tokens[s] = 0; vv.score[s] = 0; } return; }
+		if (bv.status[s]) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
 
 		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
 		const uint32_t n = t1 - t0;
@@ -948,7 +1171,7 @@ namespace kb
 		v.pool = vv.paths + pbase;
 		v.poolCap = vv.paths_per_unit * W + vv.paths_const;
 		v.top = 0;
-		v.ht = htAll[wib]; v.htUsed = 1;
+		v.sm = &smAll[wib]; v.ht = smAll[wib].ht; v.htUsed = 1;
 		v.splitComplex = (bv.match_options >> 22) & 1; v.splitSaisiot = (bv.match_options >> 25) & 1; v.mergeSaisiot = (bv.match_options >> 26) & 1;
 		v.htClear();
 
@@ -1043,145 +1266,12 @@ namespace kb
 			__syncwarp();
 		}
 
-		// ---- emit the best result (ret[0]) ------------------------------------------------------------
-		uint32_t nTok = 0; float total = 0;
-		if (!v.err && retN)
-		{
-			total = retScore[0];
-			// chain of records, last chunk first; store reversed order in the ctr scratch
-			uint32_t* chain = bv.ctr + wbase;                // W entries, free after kernel A
-			uint32_t L = 0;
-			for (int32_t r = retRec[0]; r >= 0; r = recs[r].parent_rec) { if (lane == 0) chain[L] = (uint32_t)r; ++L; }
-			__syncwarp();
-			uint32_t* steps = bv.ns_to_pos + wbase;          // backtrack scratch (W entries)
-			DToken* out = vv.tokens + wbase;
-			const uint32_t* posTable = bv.pos_table + t0 + s;
-			for (int32_t ci = (int32_t)L - 1; ci >= 0 && !v.err; --ci)
-			{
-				const DRec rec = recs[chain[ci]];
-				const DChunk ch = chunks[rec.chunk];
-				const DNode* gnodes = bv.nodes + nbase + ch.node_off;
-				// generateTokenList (PathEvaluator.hpp:1038-1157): lane 0 walks parents, then emits forward
-				uint32_t nSteps = 0;
-				for (uint32_t p = rec.end_parent; v.pool[p].parent != NPOS; p = v.pool[p].parent)
-				{
-					if (nSteps >= W) { v.err = ST_TOKEN_OVERFLOW; break; }
-					if (lane == 0) steps[nSteps] = p;
-					++nSteps;
-				}
-				__syncwarp();
-				if (v.err) break;
-				if (lane == 0)
-				{
-										DToken backTok; backTok.morph = 0; backTok.position = 0; backTok.score = 0; backTok.length = 0; backTok.tag = 0; backTok.flags = 0;
-					uint32_t backBegin = 0, backEnd = 0; bool backValid = false; bool backSkip = false;
-					auto flushBack = [&]()
-					{
-						if (!backValid) return;
-						if (!backSkip)
-						{
-							if (nTok >= W) { v.err = ST_TOKEN_OVERFLOW; return; }
-							DToken t = backTok;
-							const uint32_t beginPos = upperBound(posTable, n + 1, backBegin) - 1;
-							const uint32_t endPos = lowerBound(posTable, n + 1, backEnd);
-							t.position = beginPos; t.length = (uint16_t)(endPos - beginPos);
-							out[nTok++] = t;
-						}
-						backValid = false;
-					};
-					auto pushTok = [&](uint32_t morph, uint32_t begin, uint32_t end, float score, uint32_t ownOff, uint32_t ownLen)
-					{
-						flushBack();
-						const DMorph mm = m.morphs[morph];
-						backTok.morph = morph; backTok.tag = (uint8_t)(mm.feat & MF_TAG_MASK); backTok.score = score; backTok.flags = ownLen ? 1 : 0;
-						backBegin = begin; backEnd = end; backValid = true; backSkip = false;
-						if (ownLen)
-						{
-							const uint32_t c0 = (ownOff & 0x80000000u) ? m.form_chars[m.forms_raw[~ownOff].str_off] : v.norm[ownOff];
-							if (c0 == ' ') backSkip = true;
-							// updateTokenInfoScript (src/Kiwi.cpp:590-605)
-							const uint32_t tg = backTok.tag;
-							if ((tg == T_sl || tg == T_sh || tg == T_sw || tg == T_w_emoji) && !(mm.form_idx >= 0 && m.forms[mm.form_idx].str_len))
-							{
-								uint32_t cc = c0;
-								if (isHighSurrogate(cc))
-								{
-									const uint32_t c1 = ownLen > 1 ? ((ownOff & 0x80000000u) ? m.form_chars[m.forms_raw[~ownOff].str_off + 1] : v.norm[ownOff + 1]) : 0;
-									cc = mergeSurrogate(cc, c1);
-								}
-								if (attrScript(chrAttr(m, cc)) == m.script_latin) backTok.tag = T_sl;
-							}
-						}
-					};
-					auto unify = [&](uint32_t morph) -> uint32_t
-					{
-						if (!(morph < m.lang_vocab_size) || m.morphs[morph].combined) return morph;
-						return m.morphs[morph].lm_id;
-					};
-					uint32_t prevIdx = v.pool[steps[nSteps - 1]].parent;
-					for (int32_t si = (int32_t)nSteps - 1; si >= 0 && !v.err; --si)
-					{
-						const DPath cur = v.pool[steps[si]];
-						const DPath prev = v.pool[prevIdx];
-						const float scoreDiff = cur.acc_score - prev.acc_score;
-						const float typoCostDiff = cur.acc_typo_cost - prev.acc_typo_cost;
-						const DMorph mm = m.morphs[cur.morpheme];
-						const bool single = (mm.feat & MF_SINGLE) != 0;
-						const bool saisiot = (mm.misc & 2u) != 0;
-						const uint32_t numNewTokens = ((v.splitSaisiot && saisiot) || !single) ? mm.chunk_cnt : 1;
-						const DNode g = gnodes[cur.node];
-						const float firstScore = cur.first_chunk_score + typoCostDiff * m.cfg.typo_cost_weight;
-						const float restScores = numNewTokens > 1 ? (scoreDiff - cur.first_chunk_score) / (float)(numNewTokens - 1) : 0.f;
-						if (v.splitSaisiot && saisiot)
-						{
-							for (uint32_t chn = 0; chn < numNewTokens; ++chn)
-							{
-								const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
-								pushTok(unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, chn == 0 ? firstScore : restScores, 0, 0);
-							}
-							backEnd = g.end_pos;
-						}
-						else if (single)
-						{
-							pushTok(unify((uint32_t)cur.morpheme), g.start_pos, g.end_pos, firstScore, cur.own_off, cur.own_len);
-						}
-						else if (mm.combine_socket)
-						{
-							// ret.back() is merged with the left half (PathEvaluator.hpp:1111-1134)
-							backTok.morph = backTok.morph + m.morphs[backTok.morph].combined;
-							backTok.tag = (uint8_t)(m.morphs[backTok.morph].feat & MF_TAG_MASK);
-							backEnd = g.start_pos + m.chunks[mm.chunk_off].end;
-							backTok.score = firstScore;
-							for (uint32_t chn = 1; chn < numNewTokens; ++chn)
-							{
-								const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
-								pushTok(unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, restScores, 0, 0);
-							}
-							backEnd = g.end_pos;
-						}
-						else
-						{
-							for (uint32_t chn = 0; chn < numNewTokens; ++chn)
-							{
-								const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
-								pushTok(unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, chn == 0 ? firstScore : restScores, 0, 0);
-							}
-							backEnd = g.end_pos;
-						}
-						prevIdx = steps[si];
-					}
-					flushBack();
-				}
-				nTok = __shfl_sync(FULL, nTok, 0);
-				v.err = __shfl_sync(FULL, v.err, 0);
-				__syncwarp();
-			}
-		}
+		// the best stitched result (ret[0]); tokens are materialised by emit_kernel
 		(void)normLen;
 		if (lane == 0)
 		{
-			vv.n_tokens[s] = v.err ? 0 : nTok;
-			vv.score[s] = v.err ? 0.f : total;
+			vv.best_rec[s] = (!v.err && retN) ? retRec[0] : -1;
+			vv.score[s] = (!v.err && retN) ? retScore[0] : 0.f;
 			if (v.err) bv.status[s] = v.err;
 		}
 	}
