@@ -142,6 +142,11 @@ namespace kb
 		const DForm* forms;
 		const uint32_t* chr_bmp;       // [65536] cls | script << 8 | flags << 16
 		const int32_t* trie_root_next; // [65536] child node index of the root, -1 = none
+		// Knlm re-laid out for one-probe child lookup (model.cu): open-addressing table over all non-root edges,
+		// entry = {node, token, value, ll of the child node}; per-node backoff pair; root children via direct tables
+		const uint4* kn_hash; uint32_t kn_hash_mask;
+		const float2* kn_backoff;      // [node] {lower as int bits, gamma}
+		const float* kn_root_ll;       // [htx_vocab] ll of the root's child for token t (valid when kn_root[t] > 0)
 		// scalars
 		uint32_t n_chr_runs, n_morphs, n_forms, n_trie_nodes;
 		uint32_t default_tag_size, lang_vocab_size;
@@ -217,5 +222,6 @@ namespace kb
 		}
 		return polar == CP_negative;
 	}
+	KB_HD uint32_t knHashFn(uint32_t node, uint32_t token) { uint32_t x = node * 0x9E3779B1u ^ token * 0x85EBCA6Bu; x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 13; return x; }
 	KB_HD uint8_t hashSbTypeOrder(uint8_t type, uint8_t order) { return ((type << 1) ^ (type >> 7) ^ order) % 63 + 1; }   // PathEvaluator.hpp:83-86
 }

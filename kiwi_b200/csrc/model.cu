@@ -214,6 +214,36 @@ namespace kb
 			dmx[i] = x;
 		}
 
+		// ---- Knlm one-probe layout
+		const kb2_kn_node* knNodes = reinterpret_cast<const kb2_kn_node*>(sec(KB2_SEC_KN_NODES));
+		const uint32_t* knKeys = reinterpret_cast<const uint32_t*>(sec(KB2_SEC_KN_KEYS));
+		const int32_t* knValues = reinterpret_cast<const int32_t*>(sec(KB2_SEC_KN_VALUES));
+		const int32_t* knRoot = reinterpret_cast<const int32_t*>(sec(KB2_SEC_KN_ROOT));
+		uint32_t hashSize = 1024;
+		while (hashSize < 2 * (size_t)h->kn_num_edges + 16) hashSize <<= 1;
+		std::vector<uint4> knHash(hashSize, make_uint4(0xFFFFFFFFu, 0, 0, 0));
+		std::vector<float2> knBackoff(h->kn_num_nodes);
+		for (uint32_t i = 0; i < h->kn_num_nodes; ++i)
+		{
+			const kb2_kn_node& nd = knNodes[i];
+			float2 b; std::memcpy(&b.x, &nd.lower, 4); b.y = nd.gamma;
+			knBackoff[i] = b;
+			if (i == 0) continue;
+			for (uint32_t j = 0; j < nd.num_nexts; ++j)
+			{
+				const uint32_t key = knKeys[nd.next_offset + j];
+				const int32_t v = knValues[nd.next_offset + j];
+				float cll = 0.f;
+				if (v > 0) cll = knNodes[i + v].ll;
+				uint32_t hh = knHashFn(i, key) & (hashSize - 1);
+				while (knHash[hh].x != 0xFFFFFFFFu) hh = (hh + 1) & (hashSize - 1);
+				uint32_t cb; std::memcpy(&cb, &cll, 4);
+				knHash[hh] = make_uint4(i, key, (uint32_t)v, cb);
+			}
+		}
+		std::vector<float> knRootLl(h->kn_htx_vocab, 0.f);
+		for (uint32_t tkn = 0; tkn < h->kn_htx_vocab; ++tkn) if (knRoot[tkn] > 0 && (uint32_t)knRoot[tkn] < h->kn_num_nodes) knRootLl[tkn] = knNodes[knRoot[tkn]].ll;
+
 		// ---- upload
 		void* dBlob = nullptr;
 		cudaCheck(cudaMalloc(&dBlob, size), "cudaMalloc(image)");
@@ -238,6 +268,9 @@ namespace kb
 		d.morphs = upload(dmorphs, owned);
 		d.morphx = upload(dmx, owned);
 		d.chunk_lm = upload(chunkLm, owned);
+		d.kn_hash = upload(knHash, owned); d.kn_hash_mask = hashSize - 1;
+		d.kn_backoff = upload(knBackoff, owned);
+		d.kn_root_ll = upload(knRootLl, owned);
 		d.forms = upload(dforms, owned);
 		d.chr_bmp = upload(bmp, owned);
 		d.trie_root_next = upload(rootNext, owned);

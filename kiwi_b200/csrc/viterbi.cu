@@ -57,33 +57,26 @@ namespace kb
 	__device__ __forceinline__ float asFloat(int32_t v) { return __int_as_float(v); }
 
 	// ---- KnLangModel::progress, src/Knlm.cpp:44-130 (one lane) -------------------------------------
-	__device__ __forceinline__ bool knSearch(const DevModel& m, const kb2_kn_node& n, uint32_t key, int32_t& v)
+	// Same arithmetic (float adds in the reference's order), different table layout: the per-node sorted key
+	// arrays + binary search of the reference become ONE probe into an open-addressing table over all edges whose
+	// entry also carries the child's ll, and the root uses direct tables (model.cu "Knlm one-probe layout").
+	__device__ __forceinline__ bool knLookup(const DevModel& m, uint32_t node, uint32_t key, int32_t& v, float& childLl)
 	{
-		uint32_t lo = 0, hi = n.num_nexts;
-		const uint32_t* keys = m.kn_keys + n.next_offset;
-		while (lo < hi)
+		uint32_t h = knHashFn(node, key) & m.kn_hash_mask;
+		while (true)
 		{
-			const uint32_t mid = (lo + hi) >> 1;
-			if (keys[mid] < key) lo = mid + 1; else hi = mid;
+			const uint4 e = m.kn_hash[h];
+			if (e.x == node && e.y == key) { v = (int32_t)e.z; childLl = __uint_as_float(e.w); return true; }
+			if (e.x == 0xFFFFFFFFu) return false;
+			h = (h + 1) & m.kn_hash_mask;
 		}
-		if (lo == n.num_nexts || keys[lo] != key) return false;
-		v = m.kn_values[n.next_offset + lo];
-		return true;
-	}
-	__device__ __forceinline__ kb2_kn_node knNode(const DevModel& m, int32_t idx)
-	{
-		const kb2_kn_node* p = m.kn_nodes + idx;
-		kb2_kn_node n;
-		n.num_nexts = p->num_nexts; n.lower = p->lower; n.next_offset = p->next_offset; n.ll = p->ll; n.gamma = p->gamma;
-		return n;
 	}
 	__device__ float knProgress(const DevModel& m, int32_t& nodeIdx, uint32_t next)
 	{
 		float acc = 0;
 		while (true)
 		{
-			int32_t v;
-			const kb2_kn_node node = knNode(m, nodeIdx);
+			int32_t v; float cll;
 			if (nodeIdx == 0)
 			{
 				v = m.kn_root[next];
@@ -92,30 +85,32 @@ namespace kb
 					if (m.kn_htx) nodeIdx = m.kn_root[m.kn_htx[next]];
 					return acc + m.kn_unk_ll;
 				}
+				cll = m.kn_root_ll[next];
 			}
 			else
 			{
-				if (!knSearch(m, node, next, v))
+				const float2 bo = m.kn_backoff[nodeIdx];            // issued together with the probe
+				if (!knLookup(m, (uint32_t)nodeIdx, next, v, cll))
 				{
-					acc += node.gamma;
-					nodeIdx += node.lower;
+					acc += bo.y;
+					nodeIdx += __float_as_int(bo.x);
 					continue;
 				}
 			}
 			if (v > 0)
 			{
 				nodeIdx += v;
-				return acc + m.kn_nodes[nodeIdx].ll;
+				return acc + cll;
 			}
 			// leaf: next state = deepest suffix state that continues with `next`
 			int32_t cur = nodeIdx;
-			kb2_kn_node nd = node;
-			while (nd.lower)
+			while (true)
 			{
-				cur += nd.lower;
-				nd = knNode(m, cur);
-				int32_t lv;
-				const bool found = cur == 0 ? ((lv = m.kn_root[next]) != 0) : knSearch(m, nd, next, lv);
+				const int32_t lower = __float_as_int(m.kn_backoff[cur].x);
+				if (!lower) break;
+				cur += lower;
+				int32_t lv; float dummy;
+				const bool found = cur == 0 ? ((lv = m.kn_root[next]) != 0) : knLookup(m, (uint32_t)cur, next, lv, dummy);
 				if (found && lv > 0)
 				{
 					nodeIdx = cur + lv;
