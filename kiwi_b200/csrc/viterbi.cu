@@ -32,24 +32,25 @@ namespace kb
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
 	static constexpr uint8_t COMMON_ROOT = 0xFF;
 	static constexpr uint32_t HT_SIZE = 1024, HT_MAX_ENTRIES = 768;
-	static constexpr uint32_t STAGE_CAP = 128, ITEM_CAP = 512, CAND_CAP = 24;
+	static constexpr uint32_t STAGE_CAP = 512, ITEM_CAP = 512, GROUP = 32;
 
-	// static + per-node data of one candidate morpheme, staged in shared memory for the batched fast path
+	// static + per-node data of one candidate morpheme, written lane-parallel (lane = candidate) into shared memory
 	struct CandS
 	{
 		int32_t curId; uint32_t firstWid, lastSeqId, feat, lastSeqFeat, chunkOff;
 		float additionalScore;
-		uint16_t leftLast; uint8_t leftPol, chunkCnt, flags, pathSocket, senseId, pad;
+		uint16_t leftLast; uint8_t leftPol, chunkCnt, flags, pathSocket, senseId, cls;
 	};
-	enum : uint8_t { CS_POSITIVE_E = 1, CS_SN_POINT = 2, CS_SINGLE = 4, CS_NO_LM = 8 };
+	enum : uint8_t { CS_POSITIVE_E = 1, CS_SN_POINT = 2, CS_SINGLE = 4, CS_NO_LM = 8, CS_FORK = 16 };
+	enum : uint8_t { CLS_SKIP = 0, CLS_ITEM = 1, CLS_GENERAL = 2, CLS_SHORTCUT = 3 };
 
 	struct WarpSmem
 	{
 		unsigned long long filt[STAGE_CAP];     // left_last | left_pol << 16 | morph_tag << 24 | combine_socket << 32 | root_id << 40 | sp_state << 48
-		float acc[STAGE_CAP]; int32_t lm[STAGE_CAP]; uint32_t widFeat[STAGE_CAP];
 		uint16_t ht[HT_SIZE];
-		uint16_t item[ITEM_CAP];                // slot << 8 | q << 1 | condFail
-		CandS cand[CAND_CAP];
+		uint32_t item[ITEM_CAP];                // slot << 12 | q << 3 | doFork << 2 | r << 1 | condFail
+		CandS cand[GROUP];
+		uint32_t candNew[GROUP];                // entries created per candidate of the current group
 	};
 	static constexpr uint32_t WARPS_PER_BLOCK = 4;
 	static constexpr uint32_t MAX_RESULTS = 16;
@@ -71,7 +72,7 @@ namespace kb
 			h = (h + 1) & m.kn_hash_mask;
 		}
 	}
-	__device__ float knProgress(const DevModel& m, int32_t& nodeIdx, uint32_t next)
+	__device__ __noinline__ float knProgress(const DevModel& m, int32_t& nodeIdx, uint32_t next)
 	{
 		float acc = 0;
 		while (true)
@@ -140,13 +141,13 @@ namespace kb
 		uint32_t* npOff; uint32_t* npCnt; uint8_t* reach;
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
-		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0, nCandS = 0;
+		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0;
 		bool splitComplex, splitSaisiot, mergeSaisiot;
 
 		__device__ Vit(const DevModel& _m, const BatchView& _bv, const VitView& _vv, uint32_t _lane) : m{ _m }, bv{ _bv }, vv{ _vv }, lane{ _lane } {}
 
 		// ---- left-form features of a path (what FormEvaluator will see), uniform per candidate ------
-		__device__ void leftFeat(uint32_t ownOff, uint32_t ownLen, uint32_t wid, int32_t morpheme, uint16_t& last, uint8_t& pol) const
+		__device__ __noinline__ void leftFeat(uint32_t ownOff, uint32_t ownLen, uint32_t wid, int32_t morpheme, uint16_t& last, uint8_t& pol) const
 		{
 			pol = 0; last = 0;
 			if (ownLen)
@@ -236,7 +237,7 @@ namespace kb
 			bool spaceBefore;
 		};
 
-		__device__ void evalCand(uint32_t nodeIdx, const DNode& node, const CandCtx& cc, uint32_t inBeg, uint32_t inEnd, uint32_t mode)
+		__device__ __noinline__ void evalCand(uint32_t nodeIdx, const DNode& node, const CandCtx& cc, uint32_t inBeg, uint32_t inEnd, uint32_t mode)
 		{
 			const uint32_t P = inEnd - inBeg;
 			const uint32_t nRoot = cc.fork ? nUniq : 1;
@@ -526,94 +527,69 @@ namespace kb
 		}
 
 
-		// ---- batched fast path (mode 0: <= 128 incoming paths, non-forking, non-socket-chunk candidates) ----
-		// The incoming paths of the node are staged once in shared memory.  For every candidate a cheap filter pass
-		// (z_siot / combine-socket / FormEvaluator conditions) appends the surviving (candidate, path) pairs to an
-		// item list; the list is drained 32 items at a time, so the expensive part - the Knlm pointer chase - runs
-		// with full lanes across candidate boundaries.  Items are in (candidate, path) order, new container
-		// entries are appended in item order, hence the output is candidate-major in first-insertion order
-		// exactly like the per-candidate containers of the reference; with <= 128 incoming paths a 128-slot
-		// container cannot overflow, so no capacity bookkeeping is needed here.
-		__device__ void stagePaths(uint32_t nodeIdx, uint32_t inBeg, uint32_t P)
+		// ---- the item pipeline (containers of <= 512 incoming paths: the reference's top1Small / top1Medium) --------
+		// The incoming paths' filter words are staged once per node in shared memory.  Candidates are classified
+		// 32 at a time, one lane per candidate.  For every candidate, in order, a filter pass (z_siot / combine-socket /
+		// FormEvaluator conditions: ALU only) appends the surviving (candidate, path[, root]) items to a list that is
+		// drained 32 items at a time ACROSS candidate boundaries, so the Knlm pointer chase runs with full lanes.
+		// Items are in (candidate, path, root) order and new container entries are appended in item order, hence the
+		// pool receives them candidate-major in first-insertion order = the write-out order of the reference's
+		// per-candidate containers.  Keys are independent of each other, so the 128-slot capacity of a container
+		// bucket ("skip insertion if container is full", BestPathContainer.hpp:363-367) and the bucket-major order of
+		// the 4 x 128 medium container are applied afterwards per candidate segment (fixupGroup).
+		__device__ __noinline__ void stagePaths(uint32_t nodeIdx, uint32_t inBeg, uint32_t P)
 		{
 			if (stagedNode == nodeIdx) return;
+			#pragma unroll 1
 			for (uint32_t q = lane; q < P; q += 32)
 			{
 				const DPath* p = pool + inBeg + q;
 				sm->filt[q] = (unsigned long long)p->left_last | ((unsigned long long)p->left_pol << 16) | ((unsigned long long)p->morph_tag << 24)
 					| ((unsigned long long)p->combine_socket << 32) | ((unsigned long long)p->root_id << 40) | ((unsigned long long)p->sp_state << 48);
-				sm->acc[q] = p->acc_score; sm->lm[q] = p->lm_state; sm->widFeat[q] = p->wid_feat;
 			}
 			stagedNode = nodeIdx;
 			__syncwarp();
 		}
 
-		__device__ void filterCand(uint32_t slot, uint32_t curFeat, bool spaceBefore, float ignoreCondScore, uint32_t P)
-		{
-			const uint32_t curTag = curFeat & MF_TAG_MASK;
-			const uint32_t cv = (curFeat >> MF_VOWEL_SHIFT) & 15, cp = (curFeat >> MF_POLAR_SHIFT) & 3;
-			const bool curNN = isNNClass((uint8_t)curTag);
-			for (uint32_t qb = 0; qb < P; qb += 32)
-			{
-				const uint32_t q = qb + lane;
-				bool valid = q < P, condFail = false;
-				if (valid)
-				{
-					const unsigned long long f = sm->filt[q];
-					const uint32_t leftLast = (uint32_t)f & 0xFFFF, leftPol = (uint32_t)(f >> 16) & 0xFF, morphTag = (uint32_t)(f >> 24) & 0xFF, socket = (uint32_t)(f >> 32) & 0xFF;
-					if (morphTag == T_z_siot && (!curNN || spaceBefore)) valid = false;
-					else if (socket) valid = false;
-					else if (morphTag == T_ssc || (leftPol & LP_LAST_SSC)) {}
-					else
-					{
-						const bool empty = (leftPol & LP_EMPTY) != 0;
-						bool ok = ftVowel(empty, (uint16_t)leftLast, (uint8_t)cv);
-						if (ok && (cp == CP_positive || cp == CP_negative)) ok = empty ? true : ((leftPol & (cp == CP_positive ? LP_POLAR_POS : LP_POLAR_NEG)) != 0);
-						if (ignoreCondScore != 0.f) condFail = !ok;
-						else if (!ok) valid = false;
-					}
-				}
-				const unsigned vm = __ballot_sync(FULL, valid);
-				if (valid) sm->item[nItems + __popc(vm & ((1u << lane) - 1))] = (uint16_t)((slot << 8) | (q << 1) | (condFail ? 1u : 0u));
-				nItems += __popc(vm);
-			}
-			__syncwarp();
-		}
+		struct FlushCtx { uint32_t nodeIdx; uint32_t inBeg; float ignoreCondScore; float nodeTypoCost; uint32_t ownOff, ownLen; uint16_t ownLeftLast; uint8_t ownLeftPol; };
 
-		__device__ void flushItems(uint32_t nodeIdx, const DNode& node, uint32_t inBeg, float ignoreCondScore, uint32_t ownOff, uint32_t ownLen, uint16_t ownLeftLast, uint8_t ownLeftPol)
+		__device__ __noinline__ void flushItems(const FlushCtx& fc)
 		{
-			if (!nItems) { nCandS = 0; return; }
-			htClear();
-			const uint32_t batchBeg = top;
-			uint32_t E = 0;
+			if (!nItems) return;
+			#pragma unroll 1
 			for (uint32_t ib = 0; ib < nItems; ib += 32)
 			{
 				const uint32_t i = ib + lane;
 				const bool valid = i < nItems;
-				uint32_t slot = 0, q = 0; bool condFail = false;
-				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 8; q = (it >> 1) & 127; condFail = it & 1; }
+				uint32_t slot = 0, q = 0, r = 0; bool condFail = false, doFork = false;
+				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 12; q = (it >> 3) & 511; doFork = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
 				const CandS cs = sm->cand[slot];
-				int32_t lmState = 0; float accScore = 0, fcs = 0; uint32_t prevRoot = 0; uint8_t spState = 0;
+				int32_t lmState = 0; float accScore = 0, fcs = 0; uint32_t prevRoot = 0; uint8_t spState = 0, rootId = COMMON_ROOT;
 				if (valid)
 				{
 					const unsigned long long f = sm->filt[q];
-					prevRoot = (uint32_t)(f >> 40) & 0xFF; spState = (uint8_t)(f >> 48);
-					float candScore = sm->acc[q] + cs.additionalScore;
+					prevRoot = (uint32_t)(f >> 40) & 0xFF;
+					spState = doFork ? uniq[r] : (uint8_t)(f >> 48);
+					rootId = doFork ? (uint8_t)r : COMMON_ROOT;
+					const DPath* pp = pool + fc.inBeg + q;
+					float candScore = pp->acc_score + cs.additionalScore;
 					float firstChunkScore = cs.additionalScore;
-					if (condFail) candScore += ignoreCondScore;
-					lmState = sm->lm[q];
+					if (condFail) candScore += fc.ignoreCondScore;
+					lmState = pp->lm_state;
+					const uint32_t pf = pp->wid_feat;
 					if (!(cs.flags & CS_NO_LM))
 					{
 						float ll = knProgress(m, lmState, cs.firstWid);
 						candScore += ll; firstChunkScore += ll;
 						if (!(cs.flags & CS_SINGLE))
 						{
+							#pragma unroll 1
 							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = knProgress(m, lmState, m.chunk_lm[cs.chunkOff + c]); candScore += ll; }
 						}
 					}
-					// RuleBasedScorer (PathEvaluator.hpp:115-183) for a non-forking candidate: spState is the parent's
-					const uint32_t pf = sm->widFeat[q], ptag = pf & MF_TAG_MASK;
-					const uint32_t specialType = (cs.feat >> MF_SPECIAL_SHIFT) & 7;
+					// RuleBasedScorer::operator() + special-state update (PathEvaluator.hpp:115-183, 208-230)
+					const uint32_t ptag = pf & MF_TAG_MASK;
+					const uint32_t specialType = (cs.feat >> MF_SPECIAL_SHIFT) & 7, sbType = (cs.feat >> MF_SBTYPE_SHIFT) & 31, sbOrder = sbType ? cs.senseId : 0;
 					float rs = 0;
 					if ((cs.feat & MF_VOWEL_E) && isIrregular((uint8_t)ptag)) rs -= 10;
 					if ((cs.feat & MF_INF_J) && (pf & MF_INFL_NP)) rs -= 5;
@@ -621,12 +597,21 @@ namespace kb
 					if ((cs.flags & CS_POSITIVE_E) && !(pf & MF_POS_VERB)) rs -= 100;
 					if ((cs.feat & MF_CONTRACT_E) && (pf & MF_VERB_VOWEL)) rs -= 3;
 					if (((cs.feat >> MF_POLAR_SHIFT) & 3) == CP_non_adj && (ptag == T_va || ptag == T_xsa)) rs -= 10;
-					if (specialType <= 2) { if (specialType != (spState & 1u)) rs -= 2; }
-					else if (specialType <= 5) { if (specialType - 3 != ((spState >> 1) & 1u)) rs -= 2; }
+					const uint32_t sq = spState & 1, dq = (spState >> 1) & 1, bh = spState >> 2;
+					if (specialType <= 2) { if (specialType != sq) rs -= 2; }
+					else if (specialType <= 5) { if (specialType - 3 != dq) rs -= 2; }
+					if (sbType == 5) rs -= 5;
+					if (sbType && isEClass((uint8_t)ptag) && ptag != T_ef) rs -= 10;
+					if (sbType && bh == hashSbTypeOrder((uint8_t)sbType, (uint8_t)sbOrder)) rs += 3;
 					if ((cs.flags & CS_SN_POINT) && (ptag == T_unknown || ptag == T_ef || ptag == T_sf)) rs -= 5;
 					accScore = candScore + rs;
 					fcs = firstChunkScore + rs;
-					accScore = accScore - 0.f; fcs = fcs - 0.f;
+					if (specialType == 0) spState |= 1;
+					else if (specialType == 1) spState &= ~1;
+					else if (specialType == 3) spState |= 2;
+					else if (specialType == 4) spState &= ~2;
+					if (sbType) spState = (spState & 3) | (uint8_t)(hashSbTypeOrder((uint8_t)sbType, (uint8_t)(sbOrder + 1)) << 2);
+					accScore = accScore - 0.f; fcs = fcs - 0.f;        // curDialectCost (standard dialect only)
 				}
 				// de-duplication by (candidate, lmState, prevRootId, spState): best score, earliest item on ties
 				const unsigned long long key = valid
@@ -642,14 +627,14 @@ namespace kb
 				const bool isLeader = valid && lane == leader;
 				uint32_t found = NPOS;
 				const uint32_t h0 = htHash(lmState, prevRoot | (slot << 8), spState);
-				if (isLeader && E)
+				if (isLeader && htCount)
 				{
 					uint32_t hs = h0;
 					while (true)
 					{
 						const uint32_t e = ht[hs];
 						if (!e) break;
-						const DPath* tp = pool + batchBeg + (e - 1);
+						const DPath* tp = pool + htBase + (e - 1);
 						if (tp->lm_state == lmState && tp->morpheme == cs.curId && tp->prev_root_id == prevRoot && tp->sp_state == spState) { found = e - 1; break; }
 						hs = (hs + 1) & (HT_SIZE - 1);
 					}
@@ -658,15 +643,16 @@ namespace kb
 				const unsigned nmask = __ballot_sync(FULL, isNew);
 				const uint32_t totalNew = __popc(nmask);
 				uint32_t newIdx = NPOS;
-				if (isNew) newIdx = E + __popc(nmask & ((1u << lane) - 1));
-				if (batchBeg + E + totalNew > poolCap || E + totalNew > HT_MAX_ENTRIES) { err = ST_PATH_OVERFLOW; return; }
+				if (isNew) newIdx = htCount + __popc(nmask & ((1u << lane) - 1));
+				if (htBase + htCount + totalNew > poolCap || htCount + totalNew > HT_MAX_ENTRIES) { err = ST_PATH_OVERFLOW; return; }
 				if (isNew)
 				{
 					uint32_t hs = h0;
 					while (atomicCAS_u16(hs, newIdx + 1)) hs = (hs + 1) & (HT_SIZE - 1);
+					atomicAdd(&sm->candNew[slot], 1u);
 				}
 				if (totalNew) htUsed = 1;
-				E += totalNew;
+				htCount += totalNew;
 				__syncwarp();
 				const uint32_t tgtNew = __shfl_sync(FULL, newIdx, leader);
 				const uint32_t tgtOld = __shfl_sync(FULL, found, leader);
@@ -674,31 +660,101 @@ namespace kb
 				{
 					const uint32_t tgt = tgtOld != NPOS ? tgtOld : tgtNew;
 					bool write = true;
-					if (tgtOld != NPOS) write = accScore > pool[batchBeg + tgt].acc_score;
+					if (tgtOld != NPOS) write = accScore > pool[htBase + tgt].acc_score;
 					if (write)
 					{
 						const bool single = (cs.flags & CS_SINGLE) != 0;
-						const bool own = single && ownLen;
+						const bool own = single && fc.ownLen;
 						DPath np;
 						np.lm_state = lmState; np.acc_score = accScore; np.first_chunk_score = fcs; np.wid = cs.lastSeqId;
-						np.morpheme = cs.curId; np.parent = inBeg + q; np.own_off = own ? ownOff : 0; np.acc_typo_cost = pool[inBeg + q].acc_typo_cost + node.typo_cost;
-						np.own_len = own ? (uint16_t)ownLen : 0; np.node = (uint16_t)nodeIdx;
-						np.left_last = own ? ownLeftLast : cs.leftLast;
-						np.left_pol = own ? (uint8_t)(ownLeftPol | (cs.leftPol & LP_MORPH_SOCKET)) : cs.leftPol;
-						np.sp_state = spState; np.root_id = (uint8_t)prevRoot; np.combine_socket = cs.pathSocket; np.prev_root_id = (uint8_t)prevRoot;
+						np.morpheme = cs.curId; np.parent = fc.inBeg + q; np.own_off = own ? fc.ownOff : 0; np.acc_typo_cost = pool[fc.inBeg + q].acc_typo_cost + fc.nodeTypoCost;
+						np.own_len = own ? (uint16_t)fc.ownLen : 0; np.node = (uint16_t)fc.nodeIdx;
+						np.left_last = own ? fc.ownLeftLast : cs.leftLast;
+						np.left_pol = own ? (uint8_t)(fc.ownLeftPol | (cs.leftPol & LP_MORPH_SOCKET)) : cs.leftPol;
+						np.sp_state = spState; np.root_id = rootId != COMMON_ROOT ? rootId : (uint8_t)prevRoot; np.combine_socket = cs.pathSocket; np.prev_root_id = (uint8_t)prevRoot;
 						np.morph_tag = (uint8_t)(cs.feat & MF_TAG_MASK); np.wid_feat = cs.lastSeqFeat;
-						pool[batchBeg + tgt] = np;
+						pool[htBase + tgt] = np;
 					}
 				}
 				__syncwarp();
 			}
-			top = batchBeg + E;
-			nItems = 0; nCandS = 0;
+			top = htBase + htCount;
+			nItems = 0;
+		}
+
+		__device__ void resetIndex()
+		{
+			htClear();
+			htBase = top; htCount = 0;
+		}
+
+		// capacity + write-out order per candidate segment (see the comment above flushItems)
+		__device__ __noinline__ void fixupGroup(uint32_t groupBase, uint32_t gcount, uint32_t mode)
+		{
+			// is any fix-up needed at all?
+			bool need = false;
+			{
+				const uint32_t cnt = lane < gcount ? sm->candNew[lane] : 0;
+				const uint8_t cls = lane < gcount ? sm->cand[lane].cls : CLS_SKIP;
+				need = cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);
+			}
+			if (!__any_sync(FULL, need)) return;
+			uint32_t w = groupBase, r = groupBase;
+			const uint32_t tmp = top;
+			#pragma unroll 1
+			for (uint32_t k = 0; k < gcount; ++k)
+			{
+				const uint32_t cnt = sm->candNew[k];
+				if (!cnt) continue;
+				const bool fix = sm->cand[k].cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);
+				if (!fix)
+				{
+					if (w != r)
+					{
+						#pragma unroll 1
+						for (uint32_t e = 0; e < cnt; e += 32)
+						{
+							DPath p; const bool ok = e + lane < cnt;
+							if (ok) p = pool[r + e + lane];
+							__syncwarp();
+							if (ok) pool[w + e + lane] = p;
+							__syncwarp();
+						}
+					}
+					w += cnt; r += cnt;
+					continue;
+				}
+				if (tmp + cnt > poolCap) { err = ST_PATH_OVERFLOW; return; }
+				#pragma unroll 1
+				for (uint32_t e = lane; e < cnt; e += 32) pool[tmp + e] = pool[r + e];
+				__syncwarp();
+				const uint32_t nb = mode == 1 ? 4 : 1;
+				uint32_t kept = 0;
+				#pragma unroll 1
+				for (uint32_t b = 0; b < nb; ++b)
+				{
+					uint32_t inBucket = 0;
+					#pragma unroll 1
+					for (uint32_t e = 0; e < cnt; e += 32)
+					{
+						DPath p; bool ok = e + lane < cnt;
+						if (ok) { p = pool[tmp + e + lane]; if (mode == 1) ok = ((p.sp_state ^ ((uint32_t)p.lm_state >> 5)) & 3) == b; }
+						const unsigned bm = __ballot_sync(FULL, ok);
+						const uint32_t pos = inBucket + __popc(bm & ((1u << lane) - 1));
+						if (ok && pos < 128) pool[w + kept + pos] = p;
+						inBucket += __popc(bm);
+					}
+					kept += min(inBucket, 128u);
+				}
+				__syncwarp();
+				w += kept; r += cnt;
+			}
+			top = w;
 		}
 
 		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
 		// cands: either a form's candidate list (formCands != nullptr) or the default unknown candidates
-		__device__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const uint32_t* candList, uint32_t nCands, uint32_t unk0, uint32_t unk1,
+		__device__ __noinline__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const uint32_t* candList, uint32_t nCands, uint32_t unk0, uint32_t unk1,
 			float unkFormDiscount, uint32_t ownOff, uint32_t ownLen, uint32_t inBeg, uint32_t inEnd)
 		{
 			const DNode node = nodes[nodeIdx];
@@ -711,147 +767,217 @@ namespace kb
 			const uint32_t mode = P <= 128 ? 0 : (P <= 512 ? 1 : 2);
 			const bool spaceBefore = nodes[nodeIdx - node.prev].end_pos < node.start_pos;
 			const bool hasLB = hasLeftBoundary(nodeIdx);
-			const bool fastOK = mode == 0;
-			uint16_t ownLeftLast = 0; uint8_t ownLeftPol = 0;
-			if (fastOK)
-			{
-				stagePaths(nodeIdx, inBeg, P);
-				if (ownLen) leftFeat(ownOff, ownLen, 0, 0, ownLeftLast, ownLeftPol);
-			}
-			nItems = 0; nCandS = 0;
+			const bool itemOK = mode <= 1;
+			FlushCtx fc;
+			fc.nodeIdx = nodeIdx; fc.inBeg = inBeg; fc.nodeTypoCost = node.typo_cost; fc.ownOff = ownOff; fc.ownLen = ownLen; fc.ownLeftLast = 0; fc.ownLeftPol = 0;
+			if (itemOK) stagePaths(nodeIdx, inBeg, P);
+			if (ownLen) leftFeat(ownOff, ownLen, 0, 0, fc.ownLeftLast, fc.ownLeftPol);
+			nItems = 0;
+			const bool posE = node.form >= 0 && (m.forms[node.form].flags & FF_FIRST_IS_A);
+			const bool snPoint = node.uform_len && norm[node.uform_off + node.uform_len - 1] == '.';
 
+			#pragma unroll 1
 			for (int ignoreCond = 0; ignoreCond < 2; ++ignoreCond)
 			{
-				for (uint32_t ci = 0; ci < nCands; ++ci)
+				fc.ignoreCondScore = ignoreCond ? -10.f : 0.f;
+				#pragma unroll 1
+				for (uint32_t gb = 0; gb < nCands; gb += GROUP)
 				{
-					const int32_t curId = (int32_t)(candList ? candList[ci] : (ci == 0 ? unk0 : unk1));
-					const DMorph cur = m.morphs[curId];
-					const uint32_t tag = cur.feat & MF_TAG_MASK;
-					const bool single = (cur.feat & MF_SINGLE) != 0;
-					if (splitComplex)
+					const uint32_t gcount = min(GROUP, nCands - gb);
+					// ---- classification, one lane per candidate (PathEvaluator.hpp:382-448 + evalSingleMorpheme head 531-560)
 					{
-						bool cx = false;     // Morpheme::hasComplex, Form.h:176-185 (bit 29 of reserved word marks `complex`)
-						if (m.morphs[curId + cur.combined].misc & 1u) cx = true;
-						for (uint32_t c = 0; c < cur.chunk_cnt && !cx; ++c) if (m.morphs[m.chunks[cur.chunk_off + c].morph].misc & 1u) cx = true;
-						if (cx) continue;
-					}
-					if (cur.nonstd_dialect) continue;
-					if (tag == T_z_coda || tag == T_z_siot)
-					{
-						if (tag == T_z_siot && !(splitSaisiot || mergeSaisiot)) continue;
-						if (fastOK) { flushItems(nodeIdx, node, inBeg, ignoreCond ? -10.f : 0.f, ownOff, ownLen, ownLeftLast, ownLeftPol); if (err) return; }
-						// shortcut (PathEvaluator.hpp:389-432): copy qualifying incoming paths, no LM step
-						const float add = cur.user_score * m.cfg.typo_cost_weight;
-						const DMorph lmM = m.morphs[cur.lm_id];
-						for (uint32_t qb = 0; qb < P; qb += 32)
+						uint8_t cls = CLS_SKIP;
+						CandS cs;
+						cs.curId = 0; cs.firstWid = 0; cs.lastSeqId = 0; cs.feat = 0; cs.lastSeqFeat = 0; cs.chunkOff = 0; cs.additionalScore = 0; cs.leftLast = 0; cs.leftPol = 0;
+						cs.chunkCnt = 0; cs.flags = 0; cs.pathSocket = 0; cs.senseId = 0;
+						if (lane < gcount)
 						{
-							const uint32_t q = qb + lane;
-							DPath p; bool ok = false;
-							if (q < P)
+							const int32_t curId = (int32_t)(candList ? candList[gb + lane] : (lane == 0 ? unk0 : unk1));
+							const DMorph cur = m.morphs[curId];
+							const uint32_t tag = cur.feat & MF_TAG_MASK;
+							const bool single = (cur.feat & MF_SINGLE) != 0;
+							bool skip = cur.nonstd_dialect != 0;
+							if (!skip && splitComplex)
 							{
-								p = pool[inBeg + q];
-								const uint32_t lastTag = p.wid_feat & MF_TAG_MASK;
-								ok = tag == T_z_coda ? (isJClass((uint8_t)lastTag) || isEClass((uint8_t)lastTag)) : isNNClass((uint8_t)lastTag);
+								if (m.morphs[curId + cur.combined].misc & MM_COMPLEX) skip = true;
+								for (uint32_t c = 0; c < cur.chunk_cnt && !skip; ++c) if (m.morphs[m.chunks[cur.chunk_off + c].morph].misc & MM_COMPLEX) skip = true;
 							}
-							const unsigned om = __ballot_sync(FULL, ok);
-							if (top + __popc(om) > poolCap) { err = ST_PATH_OVERFLOW; return; }
-							if (ok)
+							if (!skip && (tag == T_z_coda || tag == T_z_siot))
 							{
-								DPath np = p;
-								np.acc_score += add;
-								np.acc_typo_cost -= cur.user_score;
-								np.parent = inBeg + q;
-								np.morpheme = (int32_t)cur.lm_id;
-								np.wid = cur.lm_id;
-								np.node = (uint16_t)nodeIdx;
-								np.morph_tag = (uint8_t)(lmM.feat & MF_TAG_MASK);
-								np.wid_feat = lmM.feat;
-								uint16_t ll; uint8_t lp;
-								leftFeat(np.own_len ? np.own_off : 0, np.own_len, np.wid, np.morpheme, ll, lp);
-								if (lmM.combine_socket) lp |= LP_MORPH_SOCKET;
-								np.left_last = ll; np.left_pol = lp;
-								pool[top + __popc(om & ((1u << lane) - 1))] = np;
+								if (tag == T_z_siot && !(splitSaisiot || mergeSaisiot)) skip = true;
+								else cls = CLS_SHORTCUT;
 							}
-							top += __popc(om);
+							else if (!skip)
+							{
+								if (!single && node.prev && spaceBefore && cur.form_idx >= 0 && m.forms[cur.form_idx].str_len == 1)
+								{
+									// contracted '하다/하게/하지' after a space is not a candidate (PathEvaluator.hpp:435-448)
+									const uint32_t k0 = m.form_chars[m.forms_raw[cur.form_idx].str_off];
+									if (k0 == 0xB2E4 || k0 == 0xAC8C || k0 == 0xC9C0)
+									{
+										const DMorph c0 = m.morphs[m.chunks[cur.chunk_off].morph];
+										if (c0.form_idx >= 0 && m.forms[c0.form_idx].str_len == 1 && m.form_chars[m.forms_raw[c0.form_idx].str_off] == 0xD558) skip = true;
+									}
+								}
+								if (!skip)
+								{
+									const uint32_t specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7, sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
+									const bool fork = sbType != 0 || specialType == 0 || specialType == 1 || specialType == 3 || specialType == 4;
+									const bool socketChunk = cur.combine_socket && !single;
+									const DMorphX mx = m.morphx[curId];
+									const bool noLm = cur.combine_socket && single;
+									if (!itemOK || socketChunk || (mode == 1 && fork)) cls = CLS_GENERAL;
+									else if (!noLm && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) cls = CLS_SKIP;     // every pair hits `goto continueFor`
+									else cls = CLS_ITEM;
+									cs.firstWid = mx.first_wid; cs.lastSeqId = mx.last_seq_id; cs.lastSeqFeat = mx.last_seq_feat; cs.leftLast = mx.left_last; cs.leftPol = mx.left_pol;
+									uint8_t fl = 0;
+									if (isEClass((uint8_t)tag) && posE) fl |= CS_POSITIVE_E;
+									if (tag == T_sn && snPoint) fl |= CS_SN_POINT;
+									if (single) fl |= CS_SINGLE;
+									if (noLm) fl |= CS_NO_LM;
+									if (fork) fl |= CS_FORK;
+									cs.flags = fl; cs.pathSocket = single ? cur.combine_socket : 0;
+								}
+							}
+							cs.curId = curId; cs.feat = cur.feat; cs.chunkOff = cur.chunk_off; cs.chunkCnt = cur.chunk_cnt; cs.senseId = cur.sense_id;
+							cs.additionalScore = cur.user_score + nodeLevelDiscount + m.tag_left_boundary[hasLB ? 1 : 0][clearIrregular((uint8_t)tag)];
 						}
-						__syncwarp();
-						continue;
+						cs.cls = cls;
+						sm->cand[lane] = cs;
+						sm->candNew[lane] = 0;
 					}
-					if (!single)
+					__syncwarp();
+					const uint32_t groupBase = top;
+					resetIndex();
+
+					// ---- ordered walk over the candidates of the group
+					#pragma unroll 1
+					for (uint32_t k = 0; k < gcount; ++k)
 					{
-						// contracted '하다/하게/하지' after a space is not a candidate (PathEvaluator.hpp:435-448)
-						if (node.prev && spaceBefore && cur.form_idx >= 0 && m.forms[cur.form_idx].str_len == 1)
+						const uint8_t cls = sm->cand[k].cls;
+						if (cls == CLS_SKIP) continue;
+						if (cls == CLS_ITEM)
 						{
-							const uint32_t k0 = m.form_chars[m.forms_raw[cur.form_idx].str_off];
-							if (k0 == 0xB2E4 || k0 == 0xAC8C || k0 == 0xC9C0)
+							if (htCount + nItems > 256) { flushItems(fc); if (err) return; resetIndex(); }
+							// filter pass (PathEvaluator.hpp:566-594): lanes = (path, root) pairs in order
+							const uint32_t curFeat = sm->cand[k].feat;
+							const bool fork = (sm->cand[k].flags & CS_FORK) != 0;
+							const uint32_t curTag = curFeat & MF_TAG_MASK;
+							const uint32_t cv = (curFeat >> MF_VOWEL_SHIFT) & 15, cp = (curFeat >> MF_POLAR_SHIFT) & 3;
+							const bool curNN = isNNClass((uint8_t)curTag);
+							const uint32_t nRoot = fork ? nUniq : 1;
+							const uint32_t perRound = 32 / nRoot;
+							#pragma unroll 1
+							for (uint32_t qb = 0; qb < P; qb += perRound)
 							{
-								const DMorph c0 = m.morphs[m.chunks[cur.chunk_off].morph];
-								if (c0.form_idx >= 0 && m.forms[c0.form_idx].str_len == 1 && m.form_chars[m.forms_raw[c0.form_idx].str_off] == 0xD558) continue;
+								if (nItems + 32 > ITEM_CAP) { flushItems(fc); if (err) return; }
+								const uint32_t pr = lane / nRoot, rr = lane % nRoot;
+								const uint32_t q = qb + pr;
+								bool valid = pr < perRound && q < P, condFail = false, doFork = false;
+								if (valid)
+								{
+									const unsigned long long f = sm->filt[q];
+									const uint32_t leftLast = (uint32_t)f & 0xFFFF, leftPol = (uint32_t)(f >> 16) & 0xFF, morphTag = (uint32_t)(f >> 24) & 0xFF, socket = (uint32_t)(f >> 32) & 0xFF;
+									const uint32_t root = (uint32_t)(f >> 40) & 0xFF;
+									doFork = fork && root == COMMON_ROOT;
+									if (!doFork && rr != 0) valid = false;
+									else if (morphTag == T_z_siot && (!curNN || spaceBefore)) valid = false;
+									else if (socket) valid = false;            // item candidates are single or socket-less: `combineSocket != cur.combineSocket || isSingle` -> continue
+									else if (morphTag == T_ssc || (leftPol & LP_LAST_SSC)) {}
+									else
+									{
+										const bool empty = (leftPol & LP_EMPTY) != 0;
+										bool ok = ftVowel(empty, (uint16_t)leftLast, (uint8_t)cv);
+										if (ok && (cp == CP_positive || cp == CP_negative)) ok = empty ? true : ((leftPol & (cp == CP_positive ? LP_POLAR_POS : LP_POLAR_NEG)) != 0);
+										if (ignoreCond) condFail = !ok;
+										else if (!ok) valid = false;
+									}
+								}
+								const unsigned vm = __ballot_sync(FULL, valid);
+								if (valid) sm->item[nItems + __popc(vm & ((1u << lane) - 1))] = (k << 12) | (q << 3) | (doFork ? 4u : 0u) | (rr << 1) | (condFail ? 1u : 0u);
+								nItems += __popc(vm);
+								__syncwarp();
 							}
+							continue;
 						}
-					}
-					const float additionalScore = cur.user_score + nodeLevelDiscount + m.tag_left_boundary[hasLB ? 1 : 0][clearIrregular((uint8_t)tag)];
-					const uint32_t specialType0 = (cur.feat >> MF_SPECIAL_SHIFT) & 7, sbType0 = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
-					const bool fork0 = sbType0 != 0 || specialType0 == 0 || specialType0 == 1 || specialType0 == 3 || specialType0 == 4;
-					if (fastOK && !fork0 && (cur.combine_socket == 0 || single))
-					{
-						const DMorphX mx = m.morphx[curId];
-						const bool noLm = cur.combine_socket && single;
-						if (!noLm && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) continue;      // every pair hits `goto continueFor`
-						if (nItems > ITEM_CAP - STAGE_CAP || nCandS == CAND_CAP)
+						// general path and shortcuts: drain the pipeline first so that entries stay candidate-major
+						flushItems(fc); if (err) return;
+						const uint32_t before = top;
+						const int32_t curId = sm->cand[k].curId;
+						const DMorph cur = m.morphs[curId];
+						const uint32_t tag = cur.feat & MF_TAG_MASK;
+						if (cls == CLS_SHORTCUT)
 						{
-							flushItems(nodeIdx, node, inBeg, ignoreCond ? -10.f : 0.f, ownOff, ownLen, ownLeftLast, ownLeftPol);
+							// shortcut (PathEvaluator.hpp:389-432): copy qualifying incoming paths, no LM step
+							const float add = cur.user_score * m.cfg.typo_cost_weight;
+							const DMorph lmM = m.morphs[cur.lm_id];
+							#pragma unroll 1
+							for (uint32_t qb = 0; qb < P; qb += 32)
+							{
+								const uint32_t q = qb + lane;
+								DPath p; bool ok = false;
+								if (q < P)
+								{
+									p = pool[inBeg + q];
+									const uint32_t lastTag = p.wid_feat & MF_TAG_MASK;
+									ok = tag == T_z_coda ? (isJClass((uint8_t)lastTag) || isEClass((uint8_t)lastTag)) : isNNClass((uint8_t)lastTag);
+								}
+								const unsigned om = __ballot_sync(FULL, ok);
+								if (top + __popc(om) > poolCap) { err = ST_PATH_OVERFLOW; return; }
+								if (ok)
+								{
+									DPath np = p;
+									np.acc_score += add;
+									np.acc_typo_cost -= cur.user_score;
+									np.parent = inBeg + q;
+									np.morpheme = (int32_t)cur.lm_id;
+									np.wid = cur.lm_id;
+									np.node = (uint16_t)nodeIdx;
+									np.morph_tag = (uint8_t)(lmM.feat & MF_TAG_MASK);
+									np.wid_feat = lmM.feat;
+									uint16_t ll; uint8_t lp;
+									leftFeat(np.own_len ? np.own_off : 0, np.own_len, np.wid, np.morpheme, ll, lp);
+									if (lmM.combine_socket) lp |= LP_MORPH_SOCKET;
+									np.left_last = ll; np.left_pol = lp;
+									pool[top + __popc(om & ((1u << lane) - 1))] = np;
+								}
+								top += __popc(om);
+							}
+							__syncwarp();
+						}
+						else
+						{
+							const bool single = (cur.feat & MF_SINGLE) != 0;
+							const CandS csk = sm->cand[k];
+							CandCtx cc;
+							cc.curId = curId; cc.cur = cur; cc.single = single;
+							cc.firstWid0 = csk.firstWid; cc.lastSeqId = csk.lastSeqId;
+							cc.additionalScore = csk.additionalScore;
+							cc.ignoreCondScore = fc.ignoreCondScore;
+							cc.specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7;
+							cc.sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
+							cc.sbOrder = cc.sbType ? cur.sense_id : 0;
+							cc.positiveE = (csk.flags & CS_POSITIVE_E) != 0;
+							cc.snEndswithPoint = (csk.flags & CS_SN_POINT) != 0;
+							cc.fork = (csk.flags & CS_FORK) != 0;
+							cc.ownOff = ownOff; cc.ownLen = ownLen;
+							cc.spaceBefore = spaceBefore;
+							cc.morphTag = (uint8_t)tag;
+							cc.widFeat = csk.lastSeqFeat;
+							cc.pathSocket = csk.pathSocket;
+							const bool own = single && ownLen;
+							cc.leftLast = own ? fc.ownLeftLast : csk.leftLast;
+							cc.leftPol = own ? (uint8_t)(fc.ownLeftPol | (csk.leftPol & LP_MORPH_SOCKET)) : csk.leftPol;
+							evalCand(nodeIdx, node, cc, inBeg, inEnd, mode);
 							if (err) return;
 						}
-						if (lane == 0)
-						{
-							CandS cs;
-							cs.curId = curId; cs.firstWid = mx.first_wid; cs.lastSeqId = mx.last_seq_id; cs.feat = cur.feat; cs.lastSeqFeat = mx.last_seq_feat;
-							cs.chunkOff = cur.chunk_off; cs.additionalScore = additionalScore; cs.leftLast = mx.left_last; cs.leftPol = mx.left_pol; cs.chunkCnt = cur.chunk_cnt;
-							uint8_t fl = 0;
-							if (isEClass((uint8_t)tag) && node.form >= 0 && (m.forms[node.form].flags & FF_FIRST_IS_A)) fl |= CS_POSITIVE_E;
-							if (tag == T_sn && node.uform_len && norm[node.uform_off + node.uform_len - 1] == '.') fl |= CS_SN_POINT;
-							if (single) fl |= CS_SINGLE;
-							if (noLm) fl |= CS_NO_LM;
-							cs.flags = fl; cs.pathSocket = single ? cur.combine_socket : 0; cs.senseId = cur.sense_id; cs.pad = 0;
-							sm->cand[nCandS] = cs;
-						}
+						if (lane == 0) sm->candNew[k] = top - before;
 						__syncwarp();
-						filterCand(nCandS, cur.feat, spaceBefore, ignoreCond ? -10.f : 0.f, P);
-						++nCandS;
-						continue;
+						resetIndex();
 					}
-					if (fastOK) { flushItems(nodeIdx, node, inBeg, ignoreCond ? -10.f : 0.f, ownOff, ownLen, ownLeftLast, ownLeftPol); if (err) return; }
-					CandCtx cc;
-					cc.curId = curId; cc.cur = cur; cc.single = single;
-					int32_t lastMorph;
-					if (single) { lastMorph = cur.combined ? curId + cur.combined : curId; cc.firstWid0 = cur.lm_id; }
-					else
-					{
-						lastMorph = (int32_t)m.chunks[cur.chunk_off + cur.chunk_cnt - 1].morph;
-						cc.firstWid0 = m.morphs[m.chunks[cur.chunk_off].morph].lm_id;
-					}
-					if ((uint32_t)lastMorph >= m.lang_vocab_size && (uint32_t)lastMorph < m.n_morphs) cc.lastSeqId = (uint32_t)lastMorph;
-					else cc.lastSeqId = m.morphs[lastMorph].lm_id;
-					cc.additionalScore = additionalScore;
-					cc.ignoreCondScore = ignoreCond ? -10.f : 0.f;
-					cc.specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7;
-					cc.sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
-					cc.sbOrder = cc.sbType ? cur.sense_id : 0;
-					cc.positiveE = isEClass((uint8_t)tag) && node.form >= 0 && (m.forms[node.form].flags & FF_FIRST_IS_A);
-					cc.snEndswithPoint = tag == T_sn && node.uform_len && norm[node.uform_off + node.uform_len - 1] == '.';
-					cc.fork = cc.sbType != 0 || cc.specialType == 0 || cc.specialType == 1 || cc.specialType == 3 || cc.specialType == 4;
-					cc.ownOff = ownOff; cc.ownLen = ownLen;
-					cc.spaceBefore = spaceBefore;
-					cc.morphTag = (uint8_t)tag;
-					cc.widFeat = m.morphs[cc.lastSeqId].feat;
-					cc.pathSocket = single ? cur.combine_socket : 0;
-					leftFeat(single ? ownOff : 0, single ? ownLen : 0, cc.lastSeqId, curId, cc.leftLast, cc.leftPol);
-					if (cur.combine_socket) cc.leftPol |= LP_MORPH_SOCKET;
-					evalCand(nodeIdx, node, cc, inBeg, inEnd, mode);
-					if (err) return;
+					flushItems(fc); if (err) return;
+					if (itemOK) { fixupGroup(groupBase, gcount, mode); if (err) return; }
 				}
-				if (fastOK) { flushItems(nodeIdx, node, inBeg, ignoreCond ? -10.f : 0.f, ownOff, ownLen, ownLeftLast, ownLeftPol); if (err) return; }
 				if (top > nodeBeg) break;
 			}
 
@@ -898,7 +1024,7 @@ namespace kb
 		}
 
 		// PathEvaluator.hpp:1159-1176; predecessors of a node are the contiguous group [k - prev, ...] linked by sibling == 1
-		__device__ bool isDisconnected(uint32_t scanStart)
+		__device__ __noinline__ bool isDisconnected(uint32_t scanStart)
 		{
 			if (reach[scanStart - 1]) return false;
 			__syncwarp();
@@ -945,7 +1071,7 @@ namespace kb
 		}
 
 		// ---- one chunk: findBestPath, returns the selected results in res[] ----------------------------
-		__device__ uint32_t findBestPath(const DChunk& ch, PathRes* res, bool openEnding)
+		__device__ __noinline__ uint32_t findBestPath(const DChunk& ch, PathRes* res, bool openEnding)
 		{
 			const uint32_t chunkBase = top;
 			stagedNode = NPOS;
