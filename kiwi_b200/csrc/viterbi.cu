@@ -41,21 +41,57 @@ namespace kb
 		float additionalScore;
 		uint16_t leftLast; uint8_t leftPol, chunkCnt, flags, pathSocket, senseId, cls;
 	};
-	enum : uint8_t { CS_POSITIVE_E = 1, CS_SN_POINT = 2, CS_SINGLE = 4, CS_NO_LM = 8, CS_FORK = 16 };
+	enum : uint8_t { CS_POSITIVE_E = 1, CS_SN_POINT = 2, CS_SINGLE = 4, CS_NO_LM = 8, CS_FORK = 16, CS_SOCKET_CHUNK = 32 };
 	enum : uint8_t { CLS_SKIP = 0, CLS_ITEM = 1, CLS_GENERAL = 2, CLS_SHORTCUT = 3 };
+
+	// filter word of an incoming path (all the filter pass needs, 4 B):
+	enum : uint32_t { FW_CLS_MASK = 7, FW_EMPTY = 8, FW_POLAR_POS = 16, FW_POLAR_NEG = 32, FW_NOCOND = 64, FW_ZSIOT = 128, FW_COMMON_ROOT = 256, FW_SOCKET_SHIFT = 16 };
+	enum : uint32_t { LC_OTHER = 0, LC_SYLLABLE = 1, LC_CODA_L = 2, LC_CODA_H = 3, LC_CODA_APPLOSIVE = 4, LC_CODA_OTHER = 5 };
+	static constexpr uint32_t FWTAB_CAP = 64;
 
 	struct WarpSmem
 	{
-		unsigned long long filt[STAGE_CAP];     // left_last | left_pol << 16 | morph_tag << 24 | combine_socket << 32 | root_id << 40 | sp_state << 48
+		uint32_t filt[STAGE_CAP];               // FW_* bits | combine_socket << 16
 		uint16_t ht[HT_SIZE];
-		uint32_t item[ITEM_CAP];                // slot << 12 | q << 3 | doFork << 2 | r << 1 | condFail
+		uint32_t item[ITEM_CAP];                // slot << 27 | fwIdx << 20 | q << 3 | spacePen << 2 | r << 1 | condFail
 		CandS cand[GROUP];
 		uint32_t candNew[GROUP];                // entries created per candidate of the current group
+		uint32_t fwTab[FWTAB_CAP];              // first-wid overrides of socket chunks (PathEvaluator.hpp:590), index 0 unused
 	};
 	static constexpr uint32_t WARPS_PER_BLOCK = 4;
 	static constexpr uint32_t MAX_RESULTS = 16;
 
 	__device__ __forceinline__ float asFloat(int32_t v) { return __int_as_float(v); }
+
+	// FeatureTestor::isMatched(CondVowel) only distinguishes these classes of the last code unit (FeatureTestor.cpp:6-60)
+	__device__ __forceinline__ uint32_t lastClass(uint32_t c)
+	{
+		if (0xAC00 <= c && c <= 0xD7A4) return LC_SYLLABLE;
+		if (!(0x11A8 <= c && c <= 0x11C2)) return LC_OTHER;
+		if (c == 0x11AF) return LC_CODA_L;
+		if (c == 0x11C2) return LC_CODA_H;
+		switch (c) { case 0x11A8: case 0x11A9: case 0x11AA: case 0x11AE: case 0x11B8: case 0x11B9: case 0x11BA: case 0x11BB: case 0x11BD: case 0x11BE: case 0x11BF: case 0x11C0: case 0x11C1: return LC_CODA_APPLOSIVE; }
+		return LC_CODA_OTHER;
+	}
+	__device__ __forceinline__ bool ftVowelCls(bool empty, uint32_t cls, uint32_t vowel)
+	{
+		if (vowel == CV_none) return true;
+		if (empty) return false;
+		if (vowel == CV_any) return true;
+		if (vowel == CV_applosive) return cls == LC_CODA_APPLOSIVE;
+		if (cls == LC_OTHER) return true;
+		const bool coda = cls >= LC_CODA_L;
+		switch (vowel)
+		{
+		case CV_vocalic_h: if (cls == LC_CODA_H) return true;
+		case CV_vocalic: if (cls == LC_CODA_L) return true;
+		case CV_vowel: return !coda;
+		case CV_non_vocalic_h: if (cls == LC_CODA_H) return false;
+		case CV_non_vocalic: if (cls == LC_CODA_L) return false;
+		case CV_non_vowel: return cls != LC_SYLLABLE;
+		default: return false;
+		}
+	}
 
 	// ---- KnLangModel::progress, src/Knlm.cpp:44-130 (one lane) -------------------------------------
 	// Same arithmetic (float adds in the reference's order), different table layout: the per-node sorted key
@@ -141,7 +177,7 @@ namespace kb
 		uint32_t* npOff; uint32_t* npCnt; uint8_t* reach;
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
-		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0;
+		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0, nFw = 1;
 		bool splitComplex, splitSaisiot, mergeSaisiot;
 
 		__device__ Vit(const DevModel& _m, const BatchView& _bv, const VitView& _vv, uint32_t _lane) : m{ _m }, bv{ _bv }, vv{ _vv }, lane{ _lane } {}
@@ -214,7 +250,7 @@ namespace kb
 		__device__ void htClear()
 		{
 			if (!htUsed) return;
-			for (uint32_t i = lane; i < HT_SIZE / 2; i += 32) reinterpret_cast<uint32_t*>(ht)[i] = 0;
+			for (uint32_t i = lane; i < HT_SIZE / 8; i += 32) reinterpret_cast<uint4*>(ht)[i] = make_uint4(0, 0, 0, 0);
 			htUsed = 0;
 			__syncwarp();
 		}
@@ -544,8 +580,16 @@ namespace kb
 			for (uint32_t q = lane; q < P; q += 32)
 			{
 				const DPath* p = pool + inBeg + q;
-				sm->filt[q] = (unsigned long long)p->left_last | ((unsigned long long)p->left_pol << 16) | ((unsigned long long)p->morph_tag << 24)
-					| ((unsigned long long)p->combine_socket << 32) | ((unsigned long long)p->root_id << 40) | ((unsigned long long)p->sp_state << 48);
+				const uint32_t lp = p->left_pol;
+				uint32_t w = lastClass(p->left_last);
+				if (lp & LP_EMPTY) w |= FW_EMPTY;
+				if (lp & LP_POLAR_POS) w |= FW_POLAR_POS;
+				if (lp & LP_POLAR_NEG) w |= FW_POLAR_NEG;
+				if ((lp & LP_LAST_SSC) || p->morph_tag == T_ssc) w |= FW_NOCOND;
+				if (p->morph_tag == T_z_siot) w |= FW_ZSIOT;
+				if (p->root_id == COMMON_ROOT) w |= FW_COMMON_ROOT;
+				w |= (uint32_t)p->combine_socket << FW_SOCKET_SHIFT;
+				sm->filt[q] = w;
 			}
 			stagedNode = nodeIdx;
 			__syncwarp();
@@ -561,25 +605,27 @@ namespace kb
 			{
 				const uint32_t i = ib + lane;
 				const bool valid = i < nItems;
-				uint32_t slot = 0, q = 0, r = 0; bool condFail = false, doFork = false;
-				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 12; q = (it >> 3) & 511; doFork = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
+				uint32_t slot = 0, q = 0, r = 0, fwIdx = 0; bool condFail = false, spacePen = false;
+				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 511; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
 				const CandS cs = sm->cand[slot];
 				int32_t lmState = 0; float accScore = 0, fcs = 0; uint32_t prevRoot = 0; uint8_t spState = 0, rootId = COMMON_ROOT;
 				if (valid)
 				{
-					const unsigned long long f = sm->filt[q];
-					prevRoot = (uint32_t)(f >> 40) & 0xFF;
-					spState = doFork ? uniq[r] : (uint8_t)(f >> 48);
-					rootId = doFork ? (uint8_t)r : COMMON_ROOT;
 					const DPath* pp = pool + fc.inBeg + q;
+					prevRoot = pp->root_id;
+					const bool doFork = (cs.flags & CS_FORK) && prevRoot == COMMON_ROOT;
+					spState = doFork ? uniq[r] : pp->sp_state;
+					rootId = doFork ? (uint8_t)r : COMMON_ROOT;
 					float candScore = pp->acc_score + cs.additionalScore;
 					float firstChunkScore = cs.additionalScore;
+					if (spacePen) candScore -= m.cfg.space_penalty;
 					if (condFail) candScore += fc.ignoreCondScore;
 					lmState = pp->lm_state;
 					const uint32_t pf = pp->wid_feat;
+					const uint32_t firstWid = fwIdx ? sm->fwTab[fwIdx] : cs.firstWid;
 					if (!(cs.flags & CS_NO_LM))
 					{
-						float ll = knProgress(m, lmState, cs.firstWid);
+						float ll = knProgress(m, lmState, firstWid);
 						candScore += ll; firstChunkScore += ll;
 						if (!(cs.flags & CS_SINGLE))
 						{
@@ -620,7 +666,8 @@ namespace kb
 				const unsigned grp = __match_any_sync(FULL, key);
 				uint32_t ord = __float_as_uint(accScore);
 				ord = (ord & 0x80000000u) ? ~ord : (ord | 0x80000000u);
-				const uint32_t gmax = __reduce_max_sync(grp, ord);
+				uint32_t gmax = ord;
+				if (grp != (1u << lane)) gmax = __reduce_max_sync(grp, ord);          // most keys are unique inside a round
 				const unsigned bestMask = __ballot_sync(FULL, valid && ord == gmax) & grp;
 				const uint32_t bestLane = __ffs(bestMask) - 1;
 				const uint32_t leader = __ffs(grp) - 1;
@@ -826,8 +873,9 @@ namespace kb
 									const bool socketChunk = cur.combine_socket && !single;
 									const DMorphX mx = m.morphx[curId];
 									const bool noLm = cur.combine_socket && single;
-									if (!itemOK || socketChunk || (mode == 1 && fork)) cls = CLS_GENERAL;
-									else if (!noLm && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) cls = CLS_SKIP;     // every pair hits `goto continueFor`
+									if (!itemOK || (mode == 1 && fork)) cls = CLS_GENERAL;
+									else if (!noLm && !socketChunk && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) cls = CLS_SKIP;     // every pair hits `goto continueFor`
+									else if (socketChunk && (mx.xflags & MX_CHUNK_HAS_P)) cls = CLS_SKIP;
 									else cls = CLS_ITEM;
 									cs.firstWid = mx.first_wid; cs.lastSeqId = mx.last_seq_id; cs.lastSeqFeat = mx.last_seq_feat; cs.leftLast = mx.left_last; cs.leftPol = mx.left_pol;
 									uint8_t fl = 0;
@@ -836,6 +884,7 @@ namespace kb
 									if (single) fl |= CS_SINGLE;
 									if (noLm) fl |= CS_NO_LM;
 									if (fork) fl |= CS_FORK;
+									if (socketChunk) fl |= CS_SOCKET_CHUNK;
 									cs.flags = fl; cs.pathSocket = single ? cur.combine_socket : 0;
 								}
 							}
@@ -849,6 +898,7 @@ namespace kb
 					__syncwarp();
 					const uint32_t groupBase = top;
 					resetIndex();
+					nFw = 1;
 
 					// ---- ordered walk over the candidates of the group
 					#pragma unroll 1
@@ -860,41 +910,90 @@ namespace kb
 						{
 							if (htCount + nItems > 256) { flushItems(fc); if (err) return; resetIndex(); }
 							// filter pass (PathEvaluator.hpp:566-594): lanes = (path, root) pairs in order
-							const uint32_t curFeat = sm->cand[k].feat;
-							const bool fork = (sm->cand[k].flags & CS_FORK) != 0;
+							const CandS ck = sm->cand[k];
+							const uint32_t curFeat = ck.feat;
+							const bool fork = (ck.flags & CS_FORK) != 0, socketChunk = (ck.flags & CS_SOCKET_CHUNK) != 0;
 							const uint32_t curTag = curFeat & MF_TAG_MASK;
 							const uint32_t cv = (curFeat >> MF_VOWEL_SHIFT) & 15, cp = (curFeat >> MF_POLAR_SHIFT) & 3;
 							const bool curNN = isNNClass((uint8_t)curTag);
-							const uint32_t nRoot = fork ? nUniq : 1;
-							const uint32_t perRound = 32 / nRoot;
+							const uint32_t rshift = (fork && nUniq == 2) ? 1 : 0;
+							const uint32_t perRound = 32u >> rshift;
+							const uint32_t curSocket = m.morphs[ck.curId].combine_socket;
+							uint32_t fwCarry = 0;                     // index into fwTab of the inherited first-wid override, 0 = none
+							const bool firstIsP = (m.morphx[ck.curId].xflags & MX_FIRST_IS_P) != 0;
 							#pragma unroll 1
 							for (uint32_t qb = 0; qb < P; qb += perRound)
 							{
 								if (nItems + 32 > ITEM_CAP) { flushItems(fc); if (err) return; }
-								const uint32_t pr = lane / nRoot, rr = lane % nRoot;
+								const uint32_t pr = lane >> rshift, rr = lane & ((1u << rshift) - 1);
 								const uint32_t q = qb + pr;
-								bool valid = pr < perRound && q < P, condFail = false, doFork = false;
+								bool valid = q < P, condFail = false, spacePen = false, setsFW = false;
+								uint32_t f = 0;
 								if (valid)
 								{
-									const unsigned long long f = sm->filt[q];
-									const uint32_t leftLast = (uint32_t)f & 0xFFFF, leftPol = (uint32_t)(f >> 16) & 0xFF, morphTag = (uint32_t)(f >> 24) & 0xFF, socket = (uint32_t)(f >> 32) & 0xFF;
-									const uint32_t root = (uint32_t)(f >> 40) & 0xFF;
-									doFork = fork && root == COMMON_ROOT;
-									if (!doFork && rr != 0) valid = false;
-									else if (morphTag == T_z_siot && (!curNN || spaceBefore)) valid = false;
-									else if (socket) valid = false;            // item candidates are single or socket-less: `combineSocket != cur.combineSocket || isSingle` -> continue
-									else if (morphTag == T_ssc || (leftPol & LP_LAST_SSC)) {}
+									f = sm->filt[q];
+									const uint32_t socket = f >> FW_SOCKET_SHIFT;
+									if (rr != 0 && !(f & FW_COMMON_ROOT)) valid = false;          // only common-root paths fork over the root states
+									else if ((f & FW_ZSIOT) && (!curNN || spaceBefore)) valid = false;
+									else if (socket)
+									{
+										// merge <v> <chunk> with only the same socket (PathEvaluator.hpp:578-591)
+										if (!socketChunk || socket != curSocket) valid = false;
+										else if (spaceBefore) { if (m.cfg.space_tolerance > 0) spacePen = true; else valid = false; }
+										if (valid) setsFW = true;
+									}
+								}
+								uint32_t fwIdx = 0;
+								if (socketChunk)
+								{
+									// the reference overwrites `firstWid` in place: every later pair inherits the latest override
+									const unsigned smask = __ballot_sync(FULL, setsFW);
+									uint32_t myIdx = 0;
+									if (smask)
+									{
+										uint32_t fwVal = 0;
+										if (setsFW) { const uint32_t pw = pool[inBeg + q].wid; fwVal = m.morphs[(int32_t)pw + m.morphs[pw].combined].lm_id; }
+										// register the override values of this round in lane order
+										unsigned rem = smask;
+										while (rem)
+										{
+											const int src = __ffs(rem) - 1;
+											const uint32_t v = __shfl_sync(FULL, fwVal, src);
+											uint32_t idx = 0;
+											for (uint32_t z = 1; z < nFw; ++z) if (sm->fwTab[z] == v) { idx = z; break; }
+											if (!idx)
+											{
+												if (nFw >= FWTAB_CAP) { err = ST_INTERNAL; return; }
+												idx = nFw++;
+												if (lane == 0) sm->fwTab[idx] = v;
+												__syncwarp();
+											}
+											if ((int)lane == src) myIdx = idx;
+											rem &= rem - 1;
+										}
+									}
+									const unsigned le = smask & (lane == 31 ? FULL : ((2u << lane) - 1));
+									const int src = le ? 31 - __clz(le) : 0;
+									const uint32_t got = __shfl_sync(FULL, myIdx, src);
+									fwIdx = le ? got : fwCarry;
+									if (smask) fwCarry = __shfl_sync(FULL, myIdx, 31 - __clz(smask));
+								}
+								if (valid)
+								{
+									if (f & FW_NOCOND) {}
 									else
 									{
-										const bool empty = (leftPol & LP_EMPTY) != 0;
-										bool ok = ftVowel(empty, (uint16_t)leftLast, (uint8_t)cv);
-										if (ok && (cp == CP_positive || cp == CP_negative)) ok = empty ? true : ((leftPol & (cp == CP_positive ? LP_POLAR_POS : LP_POLAR_NEG)) != 0);
+										const bool empty = (f & FW_EMPTY) != 0;
+										bool ok = ftVowelCls(empty, f & FW_CLS_MASK, cv);
+										if (ok && (cp == CP_positive || cp == CP_negative)) ok = empty ? true : ((f & (cp == CP_positive ? FW_POLAR_POS : FW_POLAR_NEG)) != 0);
 										if (ignoreCond) condFail = !ok;
 										else if (!ok) valid = false;
 									}
+									// prohibit <v> without <chunk>: tag P first wid (PathEvaluator.hpp:603-607)
+									if (valid && socketChunk && (fwIdx ? ((m.morphs[sm->fwTab[fwIdx]].feat & MF_TAG_MASK) == T_p) : firstIsP)) valid = false;
 								}
 								const unsigned vm = __ballot_sync(FULL, valid);
-								if (valid) sm->item[nItems + __popc(vm & ((1u << lane) - 1))] = (k << 12) | (q << 3) | (doFork ? 4u : 0u) | (rr << 1) | (condFail ? 1u : 0u);
+								if (valid) sm->item[nItems + __popc(vm & ((1u << lane) - 1))] = (k << 27) | (fwIdx << 20) | (q << 3) | (spacePen ? 4u : 0u) | (rr << 1) | (condFail ? 1u : 0u);
 								nItems += __popc(vm);
 								__syncwarp();
 							}
