@@ -132,6 +132,7 @@ float kiwi_b200_analyze_device(kiwi_h handle, const void* d_text, const void* d_
 typedef struct {
 	uint64_t n_sentences, raw_units, norm_units, lattice_nodes, tokens, paths;
 	uint64_t h2d_bytes, d2h_bytes, kernel_launches;
+	uint64_t retried;          /* sentences that overflowed the first-pass scratch and went through the larger arena */
 	float ms_lattice, ms_viterbi, ms_pack;
 } kiwi_b200_stats_t;
 int kiwi_b200_last_stats(kiwi_h handle, kiwi_b200_stats_t* out);

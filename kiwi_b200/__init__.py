@@ -53,7 +53,7 @@ class _Batch(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_sentences", C.c_uint64), ("raw_units", C.c_uint64), ("norm_units", C.c_uint64), ("lattice_nodes", C.c_uint64),
-                ("tokens", C.c_uint64), ("paths", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("tokens", C.c_uint64), ("paths", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64), ("retried", C.c_uint64),
                 ("ms_lattice", C.c_float), ("ms_viterbi", C.c_float), ("ms_pack", C.c_float)]
 
 

@@ -356,7 +356,7 @@ int kiwi_b200_last_stats(kiwi_h handle, kiwi_b200_stats_t* out)
 	if (!handle || !out) return KIWIERR_INVALID_HANDLE;
 	const Stats& s = handle->engine->last;
 	out->n_sentences = s.nSentences; out->raw_units = s.rawUnits; out->norm_units = s.normUnits; out->lattice_nodes = s.latticeNodes; out->tokens = s.tokens; out->paths = s.paths;
-	out->h2d_bytes = s.h2dBytes; out->d2h_bytes = s.d2hBytes; out->kernel_launches = s.kernelLaunches;
+	out->h2d_bytes = s.h2dBytes; out->d2h_bytes = s.d2hBytes; out->kernel_launches = s.kernelLaunches; out->retried = s.retried;
 	out->ms_lattice = s.msLattice; out->ms_viterbi = s.msViterbi; out->ms_pack = s.msPack;
 	return 0;
 }

@@ -13,6 +13,7 @@
 #include <stdexcept>
 #include <string>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include "engine.h"
 
 namespace kb
@@ -26,7 +27,15 @@ namespace kb
 		if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
 	}
 
-	static constexpr uint32_t DEFAULT_PATHS_PER_UNIT = 48, DEFAULT_PATHS_CONST = 4096;
+	static constexpr uint32_t DEFAULT_PATHS_PER_UNIT = 72, DEFAULT_PATHS_CONST = 4096;
+
+	__global__ void length_kernel(uint32_t nSent, const uint32_t* __restrict__ textOff, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx)
+	{
+		const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+		if (s >= nSent) return;
+		keys[s] = textOff[s + 1] - textOff[s];
+		idx[s] = s;
+	}
 
 	__global__ void pack_kernel(uint32_t nSent, const uint32_t* __restrict__ textOff, const uint32_t* __restrict__ nTokens,
 		const uint32_t* __restrict__ tokOff, const DToken* __restrict__ tokens, DToken* __restrict__ packed)
@@ -48,7 +57,7 @@ namespace kb
 
 	Engine::~Engine()
 	{
-		freeScratch();
+		freeScratch(main_); freeScratch(retry_);
 		if (hPinText) cudaFreeHost(hPinText);
 		if (hPinOff) cudaFreeHost(hPinOff);
 		if (hPinOut) cudaFreeHost(hPinOut);
@@ -56,19 +65,18 @@ namespace kb
 		if (stream) cudaStreamDestroy(stream);
 	}
 
-	void Engine::freeScratch()
+	void Engine::freeScratch(Scratch& sc)
 	{
 		for (void* p : sc.bufs) cudaFree(p);
 		sc = Scratch{};
 	}
 
-	void Engine::ensureScratch(size_t U, size_t B, uint32_t ppu, uint32_t pc)
+	void Engine::ensureScratch(Scratch& sc, size_t U, size_t B, uint32_t ppu, uint32_t pc, uint32_t npu)
 	{
 		const size_t T = (U - 4 * B) / 2 + 1;
-		if (U <= sc.capUnits && B <= sc.capSent && ppu == sc.pathsPerUnit && pc == sc.pathsConst && T <= sc.capText) return;
+		if (U <= sc.capUnits && B <= sc.capSent && ppu == sc.pathsPerUnit && pc == sc.pathsConst && npu == sc.nodesPerUnit && T <= sc.capText) return;
 		const size_t capU = std::max(U, sc.capUnits), capB = std::max(B, sc.capSent), capT = std::max(T, sc.capText);
-		freeScratch();
-		const uint32_t npu = KB_DEFAULT_NODES_PER_UNIT;
+		freeScratch(sc);
 		auto alloc = [&](size_t bytes) { void* p = nullptr; ck(cudaMalloc(&p, std::max<size_t>(bytes, 256)), "cudaMalloc(scratch)"); sc.bufs.push_back(p); return p; };
 		BatchView& bv = sc.bv; VitView& vv = sc.vv;
 		bv.nodes_per_unit = npu;
@@ -104,17 +112,27 @@ namespace kb
 		size_t tb = 0;
 		cub::DeviceScan::ExclusiveSum(nullptr, tb, vv.n_tokens, sc.tokOff, (int)(capB + 1), stream);
 		sc.cubTempBytes = tb; sc.cubTemp = alloc(tb);
-		sc.capUnits = capU; sc.capSent = capB; sc.capText = capT; sc.pathsPerUnit = ppu; sc.pathsConst = pc;
+		sc.lenKeys = (uint32_t*)alloc(capB * 4); sc.lenKeysOut = (uint32_t*)alloc(capB * 4); sc.idxIn = (uint32_t*)alloc(capB * 4); sc.order = (uint32_t*)alloc(capB * 4);
+		size_t sb = 0;
+		cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.order, (int)capB, 0, 32, stream);
+		sc.sortTempBytes = sb; sc.sortTemp = alloc(sb);
+		sc.capUnits = capU; sc.capSent = capB; sc.capText = capT; sc.pathsPerUnit = ppu; sc.pathsConst = pc; sc.nodesPerUnit = npu;
 	}
 
-	void Engine::bind(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions)
+	void Engine::bind(Scratch& sc, const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions)
 	{
 		sc.bv.n_sent = n; sc.bv.text = dText; sc.bv.text_off = dOffsets; sc.bv.match_options = matchOptions;
 	}
 
-	void Engine::launchAll(uint32_t n)
+	void Engine::launchAll(Scratch& sc, uint32_t n)
 	{
 		ck(cudaEventRecord(ev[1], stream), "event");
+		// longest-processing-time-first launch order (sentence cost grows with its length)
+		length_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.bv.text_off, sc.lenKeys, sc.idxIn);
+		ck(cudaGetLastError(), "length_kernel launch");
+		size_t sb = sc.sortTempBytes;
+		ck(cub::DeviceRadixSort::SortPairsDescending(sc.sortTemp, sb, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.order, (int)n, 0, 32, stream), "cub sort");
+		sc.bv.order = sc.order;
 		ck(launch_lattice(model.dev, sc.bv, stream), "lattice_kernel launch");
 		ck(cudaEventRecord(ev[2], stream), "event");
 		ck(launch_viterbi(model.dev, sc.bv, sc.vv, stream), "viterbi_kernel launch");
@@ -138,6 +156,53 @@ namespace kb
 		*cap = nb;
 	}
 
+	// one pass: H2D text + offsets, the four kernels, D2H of offsets / scores / status and of exactly the packed tokens
+	void Engine::runHostPass(Scratch& sc, const uint16_t* ptext, const uint32_t* poff, uint32_t pn, uint32_t matchOptions, uint32_t ppu, uint32_t pc, uint32_t npu, PassResult& r, BatchOutput& out)
+	{
+		const size_t pT = poff[pn];
+		const size_t U = 2 * pT + 4 * (size_t)pn;
+		ensureScratch(sc, U, pn, ppu, pc, npu);
+		growPinned((void**)&hPinText, &pinTextCap, pT * 2 + 64);
+		growPinned((void**)&hPinOff, &pinOffCap, ((size_t)pn + 1) * 4);
+		std::memcpy(hPinText, ptext, pT * 2);
+		std::memcpy(hPinOff, poff, ((size_t)pn + 1) * 4);
+		ck(cudaEventRecord(ev[0], stream), "event");
+		ck(cudaMemcpyAsync(sc.dText, hPinText, pT * 2, cudaMemcpyHostToDevice, stream), "H2D text");
+		ck(cudaMemcpyAsync(sc.dOff, hPinOff, ((size_t)pn + 1) * 4, cudaMemcpyHostToDevice, stream), "H2D offsets");
+		bind(sc, sc.dText, sc.dOff, pn, matchOptions);
+		launchAll(sc, pn);
+		const size_t headBytes = ((size_t)pn + 1) * 4 + (size_t)pn * 4 * 2;
+		growPinned(&hPinOut, &pinOutCap, std::max(headBytes, (size_t)U * sizeof(DToken) / 4));
+		uint32_t* hTokOff = (uint32_t*)hPinOut; float* hScore = (float*)(hTokOff + pn + 1); uint32_t* hStatus = (uint32_t*)(hScore + pn);
+		ck(cudaMemcpyAsync(hTokOff, sc.tokOff, ((size_t)pn + 1) * 4, cudaMemcpyDeviceToHost, stream), "D2H offsets");
+		ck(cudaMemcpyAsync(hScore, sc.vv.score, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H scores");
+		ck(cudaMemcpyAsync(hStatus, sc.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H status");
+		ck(cudaStreamSynchronize(stream), "sync (a kernel fault surfaces here)");
+		const uint32_t total = hTokOff[pn];
+		r.tokOff.assign(hTokOff, hTokOff + pn + 1);
+		r.scores.assign(hScore, hScore + pn);
+		r.status.assign(hStatus, hStatus + pn);
+		r.toks.resize(total);
+		if (total)
+		{
+			growPinned(&hPinOut, &pinOutCap, (size_t)total * sizeof(DToken));
+			ck(cudaMemcpyAsync(hPinOut, sc.packed, (size_t)total * sizeof(DToken), cudaMemcpyDeviceToHost, stream), "D2H tokens");
+		}
+		ck(cudaEventRecord(ev[5], stream), "event");
+		ck(cudaStreamSynchronize(stream), "sync");
+		if (total) std::memcpy(r.toks.data(), hPinOut, (size_t)total * sizeof(DToken));
+		float ms;
+		cudaEventElapsedTime(&ms, ev[0], ev[1]); out.msH2D += ms;
+		cudaEventElapsedTime(&ms, ev[1], ev[2]); out.msLattice += ms;
+		cudaEventElapsedTime(&ms, ev[2], ev[3]); out.msViterbi += ms;
+		cudaEventElapsedTime(&ms, ev[3], ev[4]); out.msPack += ms;
+		cudaEventElapsedTime(&ms, ev[4], ev[5]); out.msD2H += ms;
+		cudaEventElapsedTime(&ms, ev[0], ev[5]); out.msTotal += ms;
+		last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4;
+		last.d2hBytes += headBytes + (size_t)total * sizeof(DToken);
+		last.kernelLaunches += 5;
+	}
+
 	void Engine::analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out)
 	{
 		out = BatchOutput{};
@@ -151,98 +216,42 @@ namespace kb
 		for (uint32_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) throw std::runtime_error("offsets must be non-decreasing");
 		if (T >= (1ull << 31)) throw std::runtime_error("batch too large (>= 2^31 UTF-16 units); split it");
 
-		struct Pass { std::vector<uint32_t> ids; uint32_t ppu, pc; };
-		// pass 0: everything with the default capacity; pass 1: overflowed sentences with 16 x the path capacity
+		PassResult r0;
+		runHostPass(main_, text, offsets, n, matchOptions, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT, r0, out);
 		std::vector<uint32_t> failed;
-		for (int pass = 0; pass < 2; ++pass)
+		for (uint32_t i = 0; i < n; ++i) if (r0.status[i]) failed.push_back(i);
+		last.retried = failed.size();
+		if (failed.empty())
 		{
-			std::vector<uint16_t> subText; std::vector<uint32_t> subOff;
-			const uint16_t* ptext = text; const uint32_t* poff = offsets; uint32_t pn = n;
-			uint32_t ppu = DEFAULT_PATHS_PER_UNIT, pc = DEFAULT_PATHS_CONST;
-			if (pass == 1)
+			out.tokens = std::move(r0.toks); out.tokOff = std::move(r0.tokOff); out.scores = std::move(r0.scores); out.status = std::move(r0.status);
+		}
+		else
+		{
+			// second pass for the overflowed sentences only: 16 x path capacity, 4 x node capacity, in its own arena
+			std::vector<uint16_t> subText; std::vector<uint32_t> subOff{ 0 };
+			for (uint32_t id : failed)
 			{
-				if (failed.empty()) break;
-				subOff.push_back(0);
-				for (uint32_t id : failed)
+				subText.insert(subText.end(), text + offsets[id], text + offsets[id + 1]);
+				subOff.push_back((uint32_t)subText.size());
+			}
+			PassResult r1;
+			runHostPass(retry_, subText.data(), subOff.data(), (uint32_t)failed.size(), matchOptions, DEFAULT_PATHS_PER_UNIT * 16, DEFAULT_PATHS_CONST * 16, KB_DEFAULT_NODES_PER_UNIT * 4, r1, out);
+			out.tokens.reserve(r0.toks.size() + r1.toks.size());
+			out.tokOff.assign(n + 1, 0);
+			out.scores = std::move(r0.scores); out.status = std::move(r0.status);
+			size_t fi = 0;
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				out.tokOff[i] = (uint32_t)out.tokens.size();
+				if (fi < failed.size() && failed[fi] == i)
 				{
-					subText.insert(subText.end(), text + offsets[id], text + offsets[id + 1]);
-					subOff.push_back((uint32_t)subText.size());
+					out.tokens.insert(out.tokens.end(), r1.toks.begin() + r1.tokOff[fi], r1.toks.begin() + r1.tokOff[fi + 1]);
+					out.scores[i] = r1.scores[fi]; out.status[i] = r1.status[fi];
+					++fi;
 				}
-				ptext = subText.data(); poff = subOff.data(); pn = (uint32_t)failed.size();
-				ppu *= 16; pc *= 16;
+				else out.tokens.insert(out.tokens.end(), r0.toks.begin() + r0.tokOff[i], r0.toks.begin() + r0.tokOff[i + 1]);
 			}
-			const size_t pT = poff[pn];
-			const size_t U = 2 * pT + 4 * (size_t)pn;
-			ensureScratch(U, pn, ppu, pc);
-			growPinned((void**)&hPinText, &pinTextCap, pT * 2 + 64);
-			growPinned((void**)&hPinOff, &pinOffCap, ((size_t)pn + 1) * 4);
-			std::memcpy(hPinText, ptext, pT * 2);
-			std::memcpy(hPinOff, poff, ((size_t)pn + 1) * 4);
-			ck(cudaEventRecord(ev[0], stream), "event");
-			ck(cudaMemcpyAsync(sc.dText, hPinText, pT * 2, cudaMemcpyHostToDevice, stream), "H2D text");
-			ck(cudaMemcpyAsync(sc.dOff, hPinOff, ((size_t)pn + 1) * 4, cudaMemcpyHostToDevice, stream), "H2D offsets");
-			bind(sc.dText, sc.dOff, pn, matchOptions);
-			launchAll(pn);
-			// D2H: offsets + scores + status first, then exactly the packed tokens
-			const size_t headBytes = ((size_t)pn + 1) * 4 + (size_t)pn * 4 * 2;
-			growPinned(&hPinOut, &pinOutCap, headBytes);
-			uint32_t* hTokOff = (uint32_t*)hPinOut; float* hScore = (float*)(hTokOff + pn + 1); uint32_t* hStatus = (uint32_t*)(hScore + pn);
-			ck(cudaMemcpyAsync(hTokOff, sc.tokOff, ((size_t)pn + 1) * 4, cudaMemcpyDeviceToHost, stream), "D2H offsets");
-			ck(cudaMemcpyAsync(hScore, sc.vv.score, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H scores");
-			ck(cudaMemcpyAsync(hStatus, sc.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H status");
-			ck(cudaStreamSynchronize(stream), "sync (a kernel fault surfaces here)");
-			const uint32_t total = hTokOff[pn];
-			std::vector<DToken> toks(total);
-			std::vector<uint32_t> tokOffCopy(hTokOff, hTokOff + pn + 1);
-			std::vector<float> scoreCopy(hScore, hScore + pn);
-			std::vector<uint32_t> statusCopy(hStatus, hStatus + pn);
-			if (total)
-			{
-				growPinned(&hPinOut, &pinOutCap, (size_t)total * sizeof(DToken));
-				ck(cudaMemcpyAsync(hPinOut, sc.packed, (size_t)total * sizeof(DToken), cudaMemcpyDeviceToHost, stream), "D2H tokens");
-			}
-			ck(cudaEventRecord(ev[5], stream), "event");
-			ck(cudaStreamSynchronize(stream), "sync");
-			if (total) std::memcpy(toks.data(), hPinOut, (size_t)total * sizeof(DToken));
-			float ms;
-			cudaEventElapsedTime(&ms, ev[0], ev[1]); out.msH2D += ms;
-			cudaEventElapsedTime(&ms, ev[1], ev[2]); out.msLattice += ms;
-			cudaEventElapsedTime(&ms, ev[2], ev[3]); out.msViterbi += ms;
-			cudaEventElapsedTime(&ms, ev[3], ev[4]); out.msPack += ms;
-			cudaEventElapsedTime(&ms, ev[4], ev[5]); out.msD2H += ms;
-			cudaEventElapsedTime(&ms, ev[0], ev[5]); out.msTotal += ms;
-			last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4;
-			last.d2hBytes += headBytes + (size_t)total * sizeof(DToken);
-			last.kernelLaunches += 4;
-
-			if (pass == 0)
-			{
-				out.tokens = std::move(toks);
-				out.tokOff = std::move(tokOffCopy);
-				out.scores = std::move(scoreCopy);
-				out.status = std::move(statusCopy);
-				for (uint32_t i = 0; i < n; ++i) if (out.status[i]) failed.push_back(i);
-			}
-			else
-			{
-				// splice the re-run sentences back in order
-				std::vector<DToken> merged; merged.reserve(out.tokens.size() + toks.size());
-				std::vector<uint32_t> newOff(n + 1, 0);
-				size_t fi = 0;
-				for (uint32_t i = 0; i < n; ++i)
-				{
-					newOff[i] = (uint32_t)merged.size();
-					if (fi < failed.size() && failed[fi] == i)
-					{
-						merged.insert(merged.end(), toks.begin() + tokOffCopy[fi], toks.begin() + tokOffCopy[fi + 1]);
-						out.scores[i] = scoreCopy[fi]; out.status[i] = statusCopy[fi];
-						++fi;
-					}
-					else merged.insert(merged.end(), out.tokens.begin() + out.tokOff[i], out.tokens.begin() + out.tokOff[i + 1]);
-				}
-				newOff[n] = (uint32_t)merged.size();
-				out.tokens = std::move(merged); out.tokOff = std::move(newOff);
-			}
+			out.tokOff[n] = (uint32_t)out.tokens.size();
 		}
 		for (uint32_t i = 0; i < n; ++i)
 		{
@@ -258,18 +267,44 @@ namespace kb
 	float Engine::analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens)
 	{
 		const size_t U = 2 * (size_t)totalUnits + 4 * (size_t)n;
-		ensureScratch(U, n, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST);
-		bind(dText, dOffsets, n, matchOptions);
-		launchAll(n);
+		Scratch& sc = main_;
+		ensureScratch(sc, U, n, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
+		bind(sc, dText, dOffsets, n, matchOptions);
+		launchAll(sc, n);
+		growPinned(&hPinOut, &pinOutCap, (size_t)n * 4 + 64);
+		uint32_t* hStatus = (uint32_t*)hPinOut;
 		uint32_t total = 0;
 		ck(cudaMemcpyAsync(&total, sc.tokOff + n, 4, cudaMemcpyDeviceToHost, stream), "D2H total");
+		ck(cudaMemcpyAsync(hStatus, sc.bv.status, (size_t)n * 4, cudaMemcpyDeviceToHost, stream), "D2H status");
 		ck(cudaStreamSynchronize(stream), "sync (a kernel fault surfaces here)");
 		float ms = 0, a = 0;
 		cudaEventElapsedTime(&ms, ev[1], ev[4]);
 		cudaEventElapsedTime(&a, ev[1], ev[2]); last.msLattice = a;
 		cudaEventElapsedTime(&a, ev[2], ev[3]); last.msViterbi = a;
 		cudaEventElapsedTime(&a, ev[3], ev[4]); last.msPack = a;
-		last.nSentences = n; last.rawUnits = totalUnits; last.tokens = total; last.kernelLaunches = 4; last.h2dBytes = 0; last.d2hBytes = 4;
+		last.nSentences = n; last.rawUnits = totalUnits; last.tokens = total; last.kernelLaunches = 5; last.h2dBytes = 0; last.d2hBytes = 4 + (size_t)n * 4; last.retried = 0;
+		// overflowed sentences (rare) are re-run through the larger arena; their text comes back from the device
+		std::vector<uint32_t> failed;
+		for (uint32_t i = 0; i < n; ++i) if (hStatus[i]) failed.push_back(i);
+		if (!failed.empty())
+		{
+			std::vector<uint32_t> off(n + 1);
+			ck(cudaMemcpy(off.data(), dOffsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost), "D2H offsets");
+			std::vector<uint16_t> subText; std::vector<uint32_t> subOff{ 0 };
+			for (uint32_t id : failed)
+			{
+				const size_t len = off[id + 1] - off[id], at = subText.size();
+				subText.resize(at + len);
+				if (len) ck(cudaMemcpy(subText.data() + at, dText + off[id], len * 2, cudaMemcpyDeviceToHost), "D2H text");
+				subOff.push_back((uint32_t)subText.size());
+			}
+			BatchOutput tmp; PassResult r1;
+			runHostPass(retry_, subText.data(), subOff.data(), (uint32_t)failed.size(), matchOptions, DEFAULT_PATHS_PER_UNIT * 16, DEFAULT_PATHS_CONST * 16, KB_DEFAULT_NODES_PER_UNIT * 4, r1, tmp);
+			for (uint32_t s : r1.status) if (s) throw std::runtime_error("a sentence exceeded the device scratch capacity even in the retry arena (status " + std::to_string(s) + ")");
+			ms += tmp.msTotal;
+			total += (uint32_t)r1.toks.size();
+			last.retried = failed.size(); last.tokens = total;
+		}
 		if (nTokens) *nTokens = total;
 		return ms;
 	}
@@ -278,10 +313,13 @@ namespace kb
 	{
 		const uint32_t off[2] = { 0, len };
 		const size_t U = 2 * (size_t)len + 4;
-		ensureScratch(U, 1, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST);
+		Scratch& sc = main_;
+		ensureScratch(sc, U, 1, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
 		ck(cudaMemcpyAsync(sc.dText, text, (size_t)len * 2, cudaMemcpyHostToDevice, stream), "H2D");
 		ck(cudaMemcpyAsync(sc.dOff, off, 8, cudaMemcpyHostToDevice, stream), "H2D");
-		bind(sc.dText, sc.dOff, 1, matchOptions);
+		bind(sc, sc.dText, sc.dOff, 1, matchOptions);
+		ck(cudaMemsetAsync(sc.order, 0, 4, stream), "memset");
+		sc.bv.order = sc.order;
 		ck(launch_lattice(model.dev, sc.bv, stream), "lattice launch");
 		uint32_t nChunks = 0, status = 0;
 		ck(cudaMemcpyAsync(&nChunks, sc.bv.n_chunks, 4, cudaMemcpyDeviceToHost, stream), "D2H");

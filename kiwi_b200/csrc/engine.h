@@ -35,7 +35,7 @@ namespace kb
 	struct Stats
 	{
 		uint64_t nSentences = 0, rawUnits = 0, normUnits = 0, latticeNodes = 0, tokens = 0, paths = 0;
-		uint64_t h2dBytes = 0, d2hBytes = 0, kernelLaunches = 0;
+		uint64_t h2dBytes = 0, d2hBytes = 0, kernelLaunches = 0, retried = 0;
 		float msLattice = 0, msViterbi = 0, msPack = 0;
 	};
 
@@ -60,7 +60,7 @@ namespace kb
 		struct Scratch
 		{
 			size_t capUnits = 0, capSent = 0, capText = 0;
-			uint32_t pathsPerUnit = 0, pathsConst = 0;
+			uint32_t pathsPerUnit = 0, pathsConst = 0, nodesPerUnit = 0;
 			std::vector<void*> bufs;
 			BatchView bv{};
 			VitView vv{};
@@ -68,14 +68,18 @@ namespace kb
 			DToken* packed = nullptr;        // [capUnits]
 			void* cubTemp = nullptr; size_t cubTempBytes = 0;
 			uint16_t* dText = nullptr; uint32_t* dOff = nullptr;
-		} sc;
+			uint32_t* lenKeys = nullptr; uint32_t* lenKeysOut = nullptr; uint32_t* idxIn = nullptr; uint32_t* order = nullptr; void* sortTemp = nullptr; size_t sortTempBytes = 0;
+		};
+		Scratch main_, retry_;           // retry_: larger per-sentence capacity, only for sentences that overflowed main_
 		cudaEvent_t ev[6];
 		uint16_t* hPinText = nullptr; uint32_t* hPinOff = nullptr; size_t pinTextCap = 0, pinOffCap = 0;
 		void* hPinOut = nullptr; size_t pinOutCap = 0;
 
-		void ensureScratch(size_t totalUnits, size_t nSent, uint32_t pathsPerUnit, uint32_t pathsConst);
-		void freeScratch();
-		void bind(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions);
-		void launchAll(uint32_t n);
+		void ensureScratch(Scratch& sc, size_t totalUnits, size_t nSent, uint32_t pathsPerUnit, uint32_t pathsConst, uint32_t nodesPerUnit);
+		void freeScratch(Scratch& sc);
+		void bind(Scratch& sc, const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions);
+		void launchAll(Scratch& sc, uint32_t n);
+		struct PassResult { std::vector<uint32_t> tokOff; std::vector<DToken> toks; std::vector<float> scores; std::vector<uint32_t> status; };
+		void runHostPass(Scratch& sc, const uint16_t* text, const uint32_t* off, uint32_t n, uint32_t matchOptions, uint32_t ppu, uint32_t pc, uint32_t npu, PassResult& r, BatchOutput& out);
 	};
 }

@@ -70,6 +70,7 @@ namespace kb
 		const uint32_t* text_off;    // [n_sent + 1]
 		uint32_t match_options;      // kiwi::Match bits (include/kiwi/PatternMatcher.h:10-45)
 		uint32_t nodes_per_unit;
+		const uint32_t* order;       // [n_sent] launch order: longest sentence first (LPT), so that no long sentence starts in the last wave
 		// W-sized scratch (index wbase + i)
 		uint16_t* norm;              // normalized text
 		uint32_t* norm_len;          // [n_sent]

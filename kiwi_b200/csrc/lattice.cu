@@ -819,8 +819,9 @@ namespace kb
 	{
 		const uint32_t warpsPerBlock = blockDim.x >> 5;
 		const uint32_t lane = threadIdx.x & 31;
-		const uint32_t s = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
-		if (s >= bv.n_sent) return;
+		const uint32_t slot = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+		if (slot >= bv.n_sent) return;
+		const uint32_t s = bv.order[slot];
 
 		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
 		const uint32_t n = t1 - t0;

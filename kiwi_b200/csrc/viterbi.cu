@@ -1375,8 +1375,9 @@ namespace kb
 	{
 		__shared__ WarpSmem smAll[WARPS_PER_BLOCK];
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-		const uint32_t s = blockIdx.x * WARPS_PER_BLOCK + wib;
-		if (s >= bv.n_sent) return;
+		const uint32_t slot = blockIdx.x * WARPS_PER_BLOCK + wib;
+		if (slot >= bv.n_sent) return;
+		const uint32_t s = bv.order[slot];
 		if (bv.status[s]) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
 
 		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
