@@ -47,7 +47,7 @@ typedef struct kb2_section { uint64_t offset, nbytes; } kb2_section;
 #define KB2_TRIE_NONE      (-1)
 #define KB2_TRIE_SUBMATCH  (-2)
 
-typedef struct kb2_trie_node {
+typedef struct __attribute__((aligned(16))) kb2_trie_node {
 	uint32_t next_offset;   /* into TRIE_KEYS / TRIE_DIFFS                       */
 	int32_t  fail;          /* `lower`: relative index of the fail node, 0 = none */
 	int32_t  value;         /* form index, KB2_TRIE_NONE or KB2_TRIE_SUBMATCH     */

@@ -95,6 +95,8 @@ namespace kb
 		bv.chunks = (DChunk*)alloc(chunkSlots * sizeof(DChunk));
 		bv.n_chunks = (uint32_t*)alloc(capB * 4);
 		bv.status = (uint32_t*)alloc(capB * 4);
+		bv.debug = (uint32_t*)alloc(64 * 4);
+		ck(cudaMemset(bv.debug, 0, 64 * 4), "memset");
 		vv.paths_per_unit = ppu; vv.paths_const = pc;
 		vv.paths = (DPath*)alloc(((size_t)ppu * capU + (size_t)pc * capB) * sizeof(DPath));
 		vv.node_path_off = (uint32_t*)alloc(capU * npu * 4);
@@ -178,6 +180,17 @@ namespace kb
 		ck(cudaMemcpyAsync(hScore, sc.vv.score, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H scores");
 		ck(cudaMemcpyAsync(hStatus, sc.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H status");
 		ck(cudaStreamSynchronize(stream), "sync (a kernel fault surfaces here)");
+		{
+			uint32_t dbg[16];
+			ck(cudaMemcpy(dbg, sc.bv.debug, sizeof(dbg), cudaMemcpyDeviceToHost), "D2H debug");
+			if (!dbg[0]) ck(cudaMemcpy(dbg, model.dev.debug, sizeof(dbg), cudaMemcpyDeviceToHost), "D2H debug");
+			if (dbg[0])
+			{
+				std::string msg = "internal consistency failure in viterbi_kernel:";
+				for (int i = 1; i < 16; ++i) msg += " " + std::to_string(dbg[i]);
+				throw std::runtime_error(msg);
+			}
+		}
 		const uint32_t total = hTokOff[pn];
 		r.tokOff.assign(hTokOff, hTokOff + pn + 1);
 		r.scores.assign(hScore, hScore + pn);

@@ -13,7 +13,7 @@ namespace kb
 	constexpr uint32_t KB_DEFAULT_NODES_PER_UNIT = 12;
 	constexpr uint32_t KB_MAX_CHUNKS_SHIFT = 2;      // chunk capacity = W_s >> 2 (a chunk has >= 4 units) + 2
 
-	struct DNode          // 32 B lattice node (KGraphNode, /root/reference/src/KTrie.h:57-77, index based)
+	struct alignas(16) DNode          // 32 B lattice node (KGraphNode, /root/reference/src/KTrie.h:57-77, index based)
 	{
 		int32_t form;            // form index, -1 = none
 		uint32_t uform_off;      // offset into the sentence's normalized text (valid when uform_len > 0)
@@ -25,11 +25,11 @@ namespace kb
 		float typo_cost;
 	};
 
-	struct DChunk { uint32_t start, end, node_off, n_nodes; };   // normalized offsets [start,end), nodes in the final lattice region
+	struct alignas(16) DChunk { uint32_t start, end, node_off, n_nodes; };   // normalized offsets [start,end), nodes in the final lattice region
 
 	struct DPattern { uint32_t end, len, tag; };
 
-	struct DPath          // 48 B search path (WordLL, /root/reference/src/BestPathContainer.hpp:21-67), index based
+	struct alignas(16) DPath          // 48 B search path (WordLL, /root/reference/src/BestPathContainer.hpp:21-67), index based
 	{
 		int32_t lm_state; float acc_score; float first_chunk_score; uint32_t wid;
 		int32_t morpheme; uint32_t parent; uint32_t own_off; float acc_typo_cost;
@@ -43,9 +43,9 @@ namespace kb
 	};
 	enum : uint8_t { LP_POLAR_POS = 1, LP_POLAR_NEG = 2, LP_LAST_SSC = 4, LP_EMPTY = 8, LP_MORPH_SOCKET = 128 };
 
-	struct DToken { uint32_t morph; uint32_t position; float score; uint16_t length; uint8_t tag; uint8_t flags; };
+	struct alignas(16) DToken { uint32_t morph; uint32_t position; float score; uint16_t length; uint8_t tag; uint8_t flags; };
 
-	struct DRec { int32_t parent_rec; uint32_t end_parent; uint32_t chunk; float score; };
+	struct alignas(16) DRec { int32_t parent_rec; uint32_t end_parent; uint32_t chunk; float score; };
 
 	struct VitView
 	{
@@ -88,5 +88,6 @@ namespace kb
 		DChunk* chunks;
 		uint32_t* n_chunks;          // [n_sent]
 		uint32_t* status;            // [n_sent]
+		uint32_t* debug;             // [64] anomaly record of the first internal-consistency failure (diagnostics)
 	};
 }

@@ -68,7 +68,7 @@ namespace kb
 	};
 
 	enum : uint32_t { MM_COMPLEX = 1u, MM_SAISIOT = 2u };
-	struct DMorph             // 32 B, one vector load
+	struct alignas(16) DMorph             // 32 B, one vector load
 	{
 		uint32_t feat;
 		uint32_t lm_id;       // lmMorphemeId
@@ -82,7 +82,7 @@ namespace kb
 
 	// static per-candidate data of evalSingleMorpheme (PathEvaluator.hpp:531-556) and of the path it creates
 	enum : uint8_t { MX_FIRST_IS_P = 1, MX_CHUNK_HAS_P = 2 };
-	struct DMorphX            // 16 B
+	struct alignas(16) DMorphX            // 16 B
 	{
 		uint32_t first_wid;       // isSingle ? lmMorphemeId : chunks[0]->lmMorphemeId
 		uint32_t last_seq_id;     // `lastSeqId` = wid of the created path
@@ -107,7 +107,7 @@ namespace kb
 		FP_POLAR_NEG = 2,         // FeatureTestor::isMatched(form, CondPolarity::negative)
 		FP_LAST_SSC = 4,          // identifySpecialChr(form.back()) == ssc
 	};
-	struct DForm              // 16 B
+	struct alignas(16) DForm              // 16 B
 	{
 		uint32_t cand_off;
 		uint16_t cand_cnt;
@@ -152,6 +152,8 @@ namespace kb
 		uint32_t default_tag_size, lang_vocab_size;
 		uint32_t script_latin, script_variation_selectors;
 		uint32_t kn_root_num_nexts;
+		uint32_t kn_htx_vocab;
+		uint32_t* debug;               // [64] anomaly record (diagnostics)
 		int32_t kn_bos_node;
 		float kn_unk_ll;
 		uint32_t special_morph_ids[6];

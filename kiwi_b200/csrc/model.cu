@@ -277,7 +277,8 @@ namespace kb
 		d.n_chr_runs = h->n_chr_runs; d.n_morphs = h->n_morphs; d.n_forms = h->n_forms; d.n_trie_nodes = h->n_trie_nodes;
 		d.default_tag_size = h->default_tag_size; d.lang_vocab_size = h->lang_vocab_size;
 		d.script_latin = h->script_latin; d.script_variation_selectors = h->script_variation_selectors;
-		d.kn_bos_node = h->kn_bos_node; d.kn_unk_ll = h->kn_unk_ll;
+		d.kn_bos_node = h->kn_bos_node; d.kn_unk_ll = h->kn_unk_ll; d.kn_htx_vocab = h->kn_htx_vocab;
+		{ std::vector<uint32_t> z(64, 0); d.debug = upload(z, owned); }
 		for (int i = 0; i < 6; ++i) d.special_morph_ids[i] = h->special_morph_ids[i];
 		d.cfg = h->config;
 		std::memcpy(d.tag_left_boundary, h->tag_left_boundary, sizeof(d.tag_left_boundary));

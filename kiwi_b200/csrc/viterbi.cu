@@ -35,7 +35,7 @@ namespace kb
 	static constexpr uint32_t STAGE_CAP = 512, ITEM_CAP = 512, GROUP = 32;
 
 	// static + per-node data of one candidate morpheme, written lane-parallel (lane = candidate) into shared memory
-	struct CandS
+	struct alignas(8) CandS
 	{
 		int32_t curId; uint32_t firstWid, lastSeqId, feat, lastSeqFeat, chunkOff;
 		float additionalScore;
@@ -49,12 +49,17 @@ namespace kb
 	enum : uint32_t { LC_OTHER = 0, LC_SYLLABLE = 1, LC_CODA_L = 2, LC_CODA_H = 3, LC_CODA_APPLOSIVE = 4, LC_CODA_OTHER = 5 };
 	static constexpr uint32_t FWTAB_CAP = 64;
 
+	struct CandMask { uint32_t valid, condFail, sets; };
+
 	struct WarpSmem
 	{
-		uint32_t filt[STAGE_CAP];               // FW_* bits | combine_socket << 16
+		uint8_t pcls[STAGE_CAP];                // class index of every incoming path (classes = distinct filter words)
+		uint32_t fclass[32];                    // the distinct filter words: FW_* bits | combine_socket << 16
+		uint32_t classBits[32][STAGE_CAP / 32]; // per class: bitmap of the incoming paths that belong to it
 		uint16_t ht[HT_SIZE];
 		uint32_t item[ITEM_CAP];                // slot << 27 | fwIdx << 20 | q << 3 | spacePen << 2 | r << 1 | condFail
 		CandS cand[GROUP];
+		CandMask cmask[GROUP];                  // per candidate: which path classes survive the filter / fail the soft condition / override firstWid
 		uint32_t candNew[GROUP];                // entries created per candidate of the current group
 		uint32_t fwTab[FWTAB_CAP];              // first-wid overrides of socket chunks (PathEvaluator.hpp:590), index 0 unused
 	};
@@ -108,8 +113,13 @@ namespace kb
 			h = (h + 1) & m.kn_hash_mask;
 		}
 	}
-	__device__ __noinline__ float knProgress(const DevModel& m, int32_t& nodeIdx, uint32_t next)
+	__device__ __noinline__ float knProgress(const DevModel& m, int32_t& nodeIdx, uint32_t next, uint32_t site = 0)
 	{
+		if (next >= m.kn_htx_vocab || (uint32_t)nodeIdx >= 0x10000000u)
+		{
+			if (atomicCAS(&m.debug[0], 0u, 1u) == 0u) { m.debug[1] = site; m.debug[2] = next; m.debug[3] = (uint32_t)nodeIdx; m.debug[4] = blockIdx.x; m.debug[5] = threadIdx.x; }
+			return 0.f;
+		}
 		float acc = 0;
 		while (true)
 		{
@@ -178,6 +188,7 @@ namespace kb
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
 		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0, nFw = 1;
+		uint32_t nClasses = 0, classCommon = 0; bool classOverflow = false;
 		bool splitComplex, splitSaisiot, mergeSaisiot;
 
 		__device__ Vit(const DevModel& _m, const BatchView& _bv, const VitView& _vv, uint32_t _lane) : m{ _m }, bv{ _bv }, vv{ _vv }, lane{ _lane } {}
@@ -355,7 +366,7 @@ namespace kb
 						if ((m.morphs[firstWid].feat & MF_TAG_MASK) == T_p) valid = false;
 						else
 						{
-							float ll = knProgress(m, lmState, firstWid);
+							float ll = knProgress(m, lmState, firstWid, 3);
 							candScore += ll;
 							firstChunkScore += ll;
 							if (!cc.single)
@@ -364,7 +375,7 @@ namespace kb
 								{
 									const uint32_t wid = m.morphs[m.chunks[cc.cur.chunk_off + i].morph].lm_id;
 									if ((m.morphs[wid].feat & MF_TAG_MASK) == T_p) { valid = false; break; }
-									ll = knProgress(m, lmState, wid);
+									ll = knProgress(m, lmState, wid, 4);
 									candScore += ll;
 								}
 							}
@@ -576,20 +587,53 @@ namespace kb
 		__device__ __noinline__ void stagePaths(uint32_t nodeIdx, uint32_t inBeg, uint32_t P)
 		{
 			if (stagedNode == nodeIdx) return;
+			nClasses = 0; classCommon = 0; classOverflow = false;
+			uint32_t myTab = 0;
 			#pragma unroll 1
-			for (uint32_t q = lane; q < P; q += 32)
+			for (uint32_t qb = 0; qb < P; qb += 32)
 			{
-				const DPath* p = pool + inBeg + q;
-				const uint32_t lp = p->left_pol;
-				uint32_t w = lastClass(p->left_last);
-				if (lp & LP_EMPTY) w |= FW_EMPTY;
-				if (lp & LP_POLAR_POS) w |= FW_POLAR_POS;
-				if (lp & LP_POLAR_NEG) w |= FW_POLAR_NEG;
-				if ((lp & LP_LAST_SSC) || p->morph_tag == T_ssc) w |= FW_NOCOND;
-				if (p->morph_tag == T_z_siot) w |= FW_ZSIOT;
-				if (p->root_id == COMMON_ROOT) w |= FW_COMMON_ROOT;
-				w |= (uint32_t)p->combine_socket << FW_SOCKET_SHIFT;
-				sm->filt[q] = w;
+				const uint32_t q = qb + lane;
+				uint32_t w = 0xFFFFFFFFu;
+				if (q < P)
+				{
+					const DPath* p = pool + inBeg + q;
+					const uint32_t lp = p->left_pol;
+					w = lastClass(p->left_last);
+					if (lp & LP_EMPTY) w |= FW_EMPTY;
+					if (lp & LP_POLAR_POS) w |= FW_POLAR_POS;
+					if (lp & LP_POLAR_NEG) w |= FW_POLAR_NEG;
+					if ((lp & LP_LAST_SSC) || p->morph_tag == T_ssc) w |= FW_NOCOND;
+					if (p->morph_tag == T_z_siot) w |= FW_ZSIOT;
+					if (p->root_id == COMMON_ROOT) w |= FW_COMMON_ROOT;
+					w |= (uint32_t)p->combine_socket << FW_SOCKET_SHIFT;
+				}
+				// distinct filter words -> class table (a handful per node); lane z keeps class z's word for the search
+				unsigned rem = __ballot_sync(FULL, q < P);
+				uint32_t myIdx = 0;
+				const uint32_t word = qb >> 5;
+				while (rem)
+				{
+					const int src = __ffs(rem) - 1;
+					const uint32_t v = __shfl_sync(FULL, w, src);
+					const unsigned hit = __ballot_sync(FULL, lane < nClasses && myTab == v);
+					uint32_t idx;
+					if (hit) idx = __ffs(hit) - 1;
+					else if (nClasses >= 32) { classOverflow = true; idx = 0; }
+					else
+					{
+						idx = nClasses++;
+						if (lane == idx) myTab = v;
+						if (lane == 0) sm->fclass[idx] = v;
+						if (lane < STAGE_CAP / 32) sm->classBits[idx][lane] = 0;
+						if (v & FW_COMMON_ROOT) classCommon |= 1u << idx;
+						__syncwarp();
+					}
+					const unsigned same = __ballot_sync(FULL, w == v);
+					if (w == v) myIdx = idx;
+					if (lane == 0) sm->classBits[idx][word] = same;
+					rem &= ~same;
+				}
+				if (q < P) sm->pcls[q] = (uint8_t)myIdx;
 			}
 			stagedNode = nodeIdx;
 			__syncwarp();
@@ -609,6 +653,7 @@ namespace kb
 				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 511; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
 				const CandS cs = sm->cand[slot];
 				int32_t lmState = 0; float accScore = 0, fcs = 0; uint32_t prevRoot = 0; uint8_t spState = 0, rootId = COMMON_ROOT;
+				bool bad = false;
 				if (valid)
 				{
 					const DPath* pp = pool + fc.inBeg + q;
@@ -623,14 +668,24 @@ namespace kb
 					lmState = pp->lm_state;
 					const uint32_t pf = pp->wid_feat;
 					const uint32_t firstWid = fwIdx ? sm->fwTab[fwIdx] : cs.firstWid;
+					bad = firstWid >= m.n_morphs || slot >= GROUP || fc.inBeg + q >= poolCap;
+					if (bad)
+					{
+						if (atomicCAS(&bv.debug[0], 0u, 1u) == 0u)
+						{
+							bv.debug[1] = sm->item[i]; bv.debug[2] = firstWid; bv.debug[3] = slot; bv.debug[4] = q; bv.debug[5] = nItems; bv.debug[6] = i; bv.debug[7] = (uint32_t)cs.curId;
+							bv.debug[8] = cs.flags; bv.debug[9] = cs.cls; bv.debug[10] = fc.nodeIdx; bv.debug[11] = fc.inBeg; bv.debug[12] = nClasses; bv.debug[13] = htCount; bv.debug[14] = lane; bv.debug[15] = cs.firstWid;
+						}
+					}
+					else
 					if (!(cs.flags & CS_NO_LM))
 					{
-						float ll = knProgress(m, lmState, firstWid);
+						float ll = knProgress(m, lmState, firstWid, 1);
 						candScore += ll; firstChunkScore += ll;
 						if (!(cs.flags & CS_SINGLE))
 						{
 							#pragma unroll 1
-							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = knProgress(m, lmState, m.chunk_lm[cs.chunkOff + c]); candScore += ll; }
+							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = knProgress(m, lmState, m.chunk_lm[cs.chunkOff + c], 2); candScore += ll; }
 						}
 					}
 					// RuleBasedScorer::operator() + special-state update (PathEvaluator.hpp:115-183, 208-230)
@@ -659,6 +714,7 @@ namespace kb
 					if (sbType) spState = (spState & 3) | (uint8_t)(hashSbTypeOrder((uint8_t)sbType, (uint8_t)(sbOrder + 1)) << 2);
 					accScore = accScore - 0.f; fcs = fcs - 0.f;        // curDialectCost (standard dialect only)
 				}
+				if (__any_sync(FULL, bad)) { err = ST_INTERNAL; return; }
 				// de-duplication by (candidate, lmState, prevRootId, spState): best score, earliest item on ties
 				const unsigned long long key = valid
 					? ((unsigned long long)(uint32_t)lmState | ((unsigned long long)prevRoot << 32) | ((unsigned long long)spState << 40) | ((unsigned long long)slot << 48))
@@ -818,6 +874,7 @@ namespace kb
 			FlushCtx fc;
 			fc.nodeIdx = nodeIdx; fc.inBeg = inBeg; fc.nodeTypoCost = node.typo_cost; fc.ownOff = ownOff; fc.ownLen = ownLen; fc.ownLeftLast = 0; fc.ownLeftPol = 0;
 			if (itemOK) stagePaths(nodeIdx, inBeg, P);
+			const bool itemOK2 = itemOK && !classOverflow;
 			if (ownLen) leftFeat(ownOff, ownLen, 0, 0, fc.ownLeftLast, fc.ownLeftPol);
 			nItems = 0;
 			const bool posE = node.form >= 0 && (m.forms[node.form].flags & FF_FIRST_IS_A);
@@ -832,6 +889,7 @@ namespace kb
 				{
 					const uint32_t gcount = min(GROUP, nCands - gb);
 					// ---- classification, one lane per candidate (PathEvaluator.hpp:382-448 + evalSingleMorpheme head 531-560)
+					uint32_t myCls = CLS_SKIP, myValid = 0, myCondFail = 0, mySets = 0, myFlags = 0;
 					{
 						uint8_t cls = CLS_SKIP;
 						CandS cs;
@@ -873,7 +931,7 @@ namespace kb
 									const bool socketChunk = cur.combine_socket && !single;
 									const DMorphX mx = m.morphx[curId];
 									const bool noLm = cur.combine_socket && single;
-									if (!itemOK || (mode == 1 && fork)) cls = CLS_GENERAL;
+									if (!itemOK2 || (mode == 1 && fork)) cls = CLS_GENERAL;
 									else if (!noLm && !socketChunk && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) cls = CLS_SKIP;     // every pair hits `goto continueFor`
 									else if (socketChunk && (mx.xflags & MX_CHUNK_HAS_P)) cls = CLS_SKIP;
 									else cls = CLS_ITEM;
@@ -894,6 +952,44 @@ namespace kb
 						cs.cls = cls;
 						sm->cand[lane] = cs;
 						sm->candNew[lane] = 0;
+						// which path classes pass this candidate's filter (PathEvaluator.hpp:566-594), decided once per class
+						CandMask cm; cm.valid = 0; cm.condFail = 0; cm.sets = 0;
+						if (cls == CLS_ITEM)
+						{
+							const uint32_t curTag = cs.feat & MF_TAG_MASK;
+							const uint32_t cv = (cs.feat >> MF_VOWEL_SHIFT) & 15, cp = (cs.feat >> MF_POLAR_SHIFT) & 3;
+							const bool curNN = isNNClass((uint8_t)curTag);
+							const bool socketChunk = (cs.flags & CS_SOCKET_CHUNK) != 0;
+							const uint32_t curSocket = m.morphs[cs.curId].combine_socket;
+							for (uint32_t c = 0; c < nClasses; ++c)
+							{
+								const uint32_t f = sm->fclass[c];
+								const uint32_t socket = f >> FW_SOCKET_SHIFT;
+								bool valid = true;
+								if ((f & FW_ZSIOT) && (!curNN || spaceBefore)) valid = false;
+								else if (socket)
+								{
+									// merge <v> <chunk> with only the same socket (PathEvaluator.hpp:578-591)
+									if (!socketChunk || socket != curSocket) valid = false;
+									else if (spaceBefore && !(m.cfg.space_tolerance > 0)) valid = false;
+									if (valid) cm.sets |= 1u << c;
+								}
+								if (valid && !(f & FW_NOCOND))
+								{
+									const bool empty = (f & FW_EMPTY) != 0;
+									bool ok = ftVowelCls(empty, f & FW_CLS_MASK, cv);
+									if (ok && (cp == CP_positive || cp == CP_negative)) ok = empty ? true : ((f & (cp == CP_positive ? FW_POLAR_POS : FW_POLAR_NEG)) != 0);
+									if (ignoreCond) { if (!ok) cm.condFail |= 1u << c; }
+									else if (!ok) valid = false;
+								}
+								if (valid) cm.valid |= 1u << c;
+							}
+							// prohibit <v> without <chunk> (PathEvaluator.hpp:603-607): a socket chunk whose first wid is the tag-P
+							// placeholder only survives behind a path that overrides firstWid; without such a path nothing survives
+							if (socketChunk && !cm.sets && (m.morphx[cs.curId].xflags & MX_FIRST_IS_P)) cm.valid = 0;
+						}
+						sm->cmask[lane] = cm;
+						myCls = cls; myValid = cm.valid; myCondFail = cm.condFail; mySets = cm.sets; myFlags = cs.flags;
 					}
 					__syncwarp();
 					const uint32_t groupBase = top;
@@ -904,47 +1000,73 @@ namespace kb
 					#pragma unroll 1
 					for (uint32_t k = 0; k < gcount; ++k)
 					{
-						const uint8_t cls = sm->cand[k].cls;
+						const uint32_t cls = __shfl_sync(FULL, myCls, k);
 						if (cls == CLS_SKIP) continue;
 						if (cls == CLS_ITEM)
 						{
+							const uint32_t vmK = __shfl_sync(FULL, myValid, k), cfK = __shfl_sync(FULL, myCondFail, k), setsK = __shfl_sync(FULL, mySets, k);
+							const uint32_t kfl = __shfl_sync(FULL, myFlags, k);
+							if (!(vmK | setsK)) continue;
 							if (htCount + nItems > 256) { flushItems(fc); if (err) return; resetIndex(); }
-							// filter pass (PathEvaluator.hpp:566-594): lanes = (path, root) pairs in order
-							const CandS ck = sm->cand[k];
-							const uint32_t curFeat = ck.feat;
-							const bool fork = (ck.flags & CS_FORK) != 0, socketChunk = (ck.flags & CS_SOCKET_CHUNK) != 0;
-							const uint32_t curTag = curFeat & MF_TAG_MASK;
-							const uint32_t cv = (curFeat >> MF_VOWEL_SHIFT) & 15, cp = (curFeat >> MF_POLAR_SHIFT) & 3;
-							const bool curNN = isNNClass((uint8_t)curTag);
+							if (!(kfl & CS_FORK) && !setsK)
+							{
+								// common case: survivors = union of the path bitmaps of the valid classes, enumerated in path order
+								const uint32_t nW = (P + 31) >> 5;
+								uint32_t bits = 0;
+								if (lane < nW) { uint32_t mm = vmK; while (mm) { const uint32_t c = __ffs(mm) - 1; bits |= sm->classBits[c][lane]; mm &= mm - 1; } }
+								const uint32_t cnt = __popc(bits);
+								uint32_t incl = cnt;
+								if (nW > 1) { for (int d = 1; d < 16; d <<= 1) { const uint32_t tt = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += tt; } }
+								const uint32_t S = __shfl_sync(FULL, incl, nW - 1);
+								if (!S) continue;
+								if (nItems + S > ITEM_CAP) { flushItems(fc); if (err) return; }
+								const uint32_t excl = incl - cnt;
+								#pragma unroll 1
+								for (uint32_t wd = 0; wd < nW; ++wd)
+								{
+									const uint32_t wb = __shfl_sync(FULL, bits, wd);
+									if (!wb) continue;
+									const uint32_t base = __shfl_sync(FULL, excl, wd);
+									if ((wb >> lane) & 1)
+									{
+										const uint32_t q = (wd << 5) | lane;
+										const uint32_t c = sm->pcls[q];
+										sm->item[nItems + base + __popc(wb & ((1u << lane) - 1))] = (k << 27) | (q << 3) | ((cfK >> c) & 1);
+									}
+								}
+								nItems += S;
+								__syncwarp();
+								continue;
+							}
+							// filter pass (PathEvaluator.hpp:566-594): lanes = (path, root) pairs in order; the per-pair work is a
+							// table lookup because the decision only depends on (candidate, path class)
+							const CandMask cmk = sm->cmask[k];
+							if (!(cmk.valid | cmk.sets)) continue;
+							const uint8_t kflags = sm->cand[k].flags;
+							const bool fork = (kflags & CS_FORK) != 0, socketChunk = (kflags & CS_SOCKET_CHUNK) != 0;
 							const uint32_t rshift = (fork && nUniq == 2) ? 1 : 0;
 							const uint32_t perRound = 32u >> rshift;
-							const uint32_t curSocket = m.morphs[ck.curId].combine_socket;
+							const bool spacePen = socketChunk && spaceBefore;          // only socket matches survive `spaceBefore` (with tolerance) and they pay the penalty
 							uint32_t fwCarry = 0;                     // index into fwTab of the inherited first-wid override, 0 = none
-							const bool firstIsP = (m.morphx[ck.curId].xflags & MX_FIRST_IS_P) != 0;
+							const bool firstIsP = socketChunk && (m.morphx[sm->cand[k].curId].xflags & MX_FIRST_IS_P) != 0;
 							#pragma unroll 1
 							for (uint32_t qb = 0; qb < P; qb += perRound)
 							{
 								if (nItems + 32 > ITEM_CAP) { flushItems(fc); if (err) return; }
 								const uint32_t pr = lane >> rshift, rr = lane & ((1u << rshift) - 1);
 								const uint32_t q = qb + pr;
-								bool valid = q < P, condFail = false, spacePen = false, setsFW = false;
-								uint32_t f = 0;
-								if (valid)
+								bool valid = false, condFail = false, setsFW = false, isSock = false;
+								if (q < P)
 								{
-									f = sm->filt[q];
-									const uint32_t socket = f >> FW_SOCKET_SHIFT;
-									if (rr != 0 && !(f & FW_COMMON_ROOT)) valid = false;          // only common-root paths fork over the root states
-									else if ((f & FW_ZSIOT) && (!curNN || spaceBefore)) valid = false;
-									else if (socket)
-									{
-										// merge <v> <chunk> with only the same socket (PathEvaluator.hpp:578-591)
-										if (!socketChunk || socket != curSocket) valid = false;
-										else if (spaceBefore) { if (m.cfg.space_tolerance > 0) spacePen = true; else valid = false; }
-										if (valid) setsFW = true;
-									}
+									const uint32_t c = sm->pcls[q];
+									valid = (cmk.valid >> c) & 1;
+									condFail = (cmk.condFail >> c) & 1;
+									setsFW = (cmk.sets >> c) & 1;
+									isSock = setsFW;
+									if (rr != 0 && !((classCommon >> c) & 1)) valid = false;      // only common-root paths fork over the root states
 								}
 								uint32_t fwIdx = 0;
-								if (socketChunk)
+								if (cmk.sets)
 								{
 									// the reference overwrites `firstWid` in place: every later pair inherits the latest override
 									const unsigned smask = __ballot_sync(FULL, setsFW);
@@ -953,7 +1075,6 @@ namespace kb
 									{
 										uint32_t fwVal = 0;
 										if (setsFW) { const uint32_t pw = pool[inBeg + q].wid; fwVal = m.morphs[(int32_t)pw + m.morphs[pw].combined].lm_id; }
-										// register the override values of this round in lane order
 										unsigned rem = smask;
 										while (rem)
 										{
@@ -978,22 +1099,10 @@ namespace kb
 									fwIdx = le ? got : fwCarry;
 									if (smask) fwCarry = __shfl_sync(FULL, myIdx, 31 - __clz(smask));
 								}
-								if (valid)
-								{
-									if (f & FW_NOCOND) {}
-									else
-									{
-										const bool empty = (f & FW_EMPTY) != 0;
-										bool ok = ftVowelCls(empty, f & FW_CLS_MASK, cv);
-										if (ok && (cp == CP_positive || cp == CP_negative)) ok = empty ? true : ((f & (cp == CP_positive ? FW_POLAR_POS : FW_POLAR_NEG)) != 0);
-										if (ignoreCond) condFail = !ok;
-										else if (!ok) valid = false;
-									}
-									// prohibit <v> without <chunk>: tag P first wid (PathEvaluator.hpp:603-607)
-									if (valid && socketChunk && (fwIdx ? ((m.morphs[sm->fwTab[fwIdx]].feat & MF_TAG_MASK) == T_p) : firstIsP)) valid = false;
-								}
+								// prohibit <v> without <chunk>: tag P first wid (PathEvaluator.hpp:603-607)
+								if (valid && socketChunk && (fwIdx ? ((m.morphs[sm->fwTab[fwIdx]].feat & MF_TAG_MASK) == T_p) : firstIsP)) valid = false;
 								const unsigned vm = __ballot_sync(FULL, valid);
-								if (valid) sm->item[nItems + __popc(vm & ((1u << lane) - 1))] = (k << 27) | (fwIdx << 20) | (q << 3) | (spacePen ? 4u : 0u) | (rr << 1) | (condFail ? 1u : 0u);
+								if (valid) sm->item[nItems + __popc(vm & ((1u << lane) - 1))] = (k << 27) | (fwIdx << 20) | (q << 3) | ((spacePen && isSock) ? 4u : 0u) | (rr << 1) | (condFail ? 1u : 0u);
 								nItems += __popc(vm);
 								__syncwarp();
 							}
@@ -1262,7 +1371,7 @@ namespace kb
 						if (!openEnding)
 						{
 							int32_t st = p.lm_state;
-							c += knProgress(m, st, 1);
+							c += knProgress(m, st, 1, 5);
 							if (p.sp_state & 1) c -= 2;
 							if (p.sp_state & 2) c -= 2;
 						}
