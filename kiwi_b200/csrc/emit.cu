@@ -11,6 +11,7 @@
 
 namespace kb
 {
+	__constant__ DevModel c_m;
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
 
 	__device__ __forceinline__ uint32_t upperBound(const uint32_t* t, uint32_t n, uint32_t v)
@@ -28,12 +29,11 @@ namespace kb
 
 	struct Emitter
 	{
-		const DevModel& m;
 		const uint16_t* norm; const uint32_t* posTable; uint32_t n, W;
 		DToken* out; uint32_t nTok = 0; uint32_t err = 0;
 		DToken backTok; uint32_t backBegin = 0, backEnd = 0; bool backValid = false, backSkip = false;
 
-		__device__ Emitter(const DevModel& _m) : m{ _m } {}
+		__device__ Emitter() {}
 
 		__device__ void flushBack()
 		{
@@ -51,12 +51,12 @@ namespace kb
 		}
 		__device__ uint16_t ownChar(uint32_t ownOff, uint32_t k) const
 		{
-			return (ownOff & 0x80000000u) ? m.form_chars[m.forms_raw[~ownOff].str_off + k] : norm[ownOff + k];
+			return (ownOff & 0x80000000u) ? c_m.form_chars[c_m.forms_raw[~ownOff].str_off + k] : norm[ownOff + k];
 		}
 		__device__ void pushTok(uint32_t morph, uint32_t begin, uint32_t end, float score, uint32_t ownOff, uint32_t ownLen)
 		{
 			flushBack();
-			const DMorph mm = m.morphs[morph];
+			const DMorph mm = c_m.morphs[morph];
 			backTok.morph = morph; backTok.tag = (uint8_t)(mm.feat & MF_TAG_MASK); backTok.score = score; backTok.flags = ownLen ? 1 : 0;
 			backTok.position = 0; backTok.length = 0;
 			backBegin = begin; backEnd = end; backValid = true; backSkip = false;
@@ -66,22 +66,22 @@ namespace kb
 				if (c0 == ' ') backSkip = true;
 				// updateTokenInfoScript (src/Kiwi.cpp:590-605)
 				const uint32_t tg = backTok.tag;
-				if ((tg == T_sl || tg == T_sh || tg == T_sw || tg == T_w_emoji) && !(mm.form_idx >= 0 && m.forms[mm.form_idx].str_len))
+				if ((tg == T_sl || tg == T_sh || tg == T_sw || tg == T_w_emoji) && !(mm.form_idx >= 0 && c_m.forms[mm.form_idx].str_len))
 				{
 					uint32_t cc = c0;
 					if (isHighSurrogate(cc)) cc = mergeSurrogate(cc, ownLen > 1 ? ownChar(ownOff, 1) : 0);
-					if (attrScript(chrAttr(m, cc)) == m.script_latin) backTok.tag = T_sl;
+					if (attrScript(chrAttr(c_m, cc)) == c_m.script_latin) backTok.tag = T_sl;
 				}
 			}
 		}
 		__device__ uint32_t unify(uint32_t morph) const      // PathEvaluator.hpp:1054-1058
 		{
-			if (!(morph < m.lang_vocab_size) || m.morphs[morph].combined) return morph;
-			return m.morphs[morph].lm_id;
+			if (!(morph < c_m.lang_vocab_size) || c_m.morphs[morph].combined) return morph;
+			return c_m.morphs[morph].lm_id;
 		}
 	};
 
-	__global__ void __launch_bounds__(128) emit_kernel(const DevModel m, const BatchView bv, const VitView vv)
+	__global__ void __launch_bounds__(128) emit_kernel(const BatchView bv, const VitView vv)
 	{
 		const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 		if (s >= bv.n_sent) return;
@@ -98,7 +98,7 @@ namespace kb
 		const DRec* recs = vv.recs + 2 * ((wbase >> 2) + 2 * (size_t)s);
 		const bool splitSaisiot = (bv.match_options >> 25) & 1;
 
-		Emitter e{ m };
+		Emitter e;
 		e.norm = bv.norm + wbase; e.posTable = bv.pos_table + t0 + s; e.n = n; e.W = W; e.out = vv.tokens + wbase;
 
 		// record chain, last chunk first
@@ -125,18 +125,18 @@ namespace kb
 				const float prevAcc = pool[prevIdx].acc_score, prevTypo = pool[prevIdx].acc_typo_cost;
 				const float scoreDiff = cur.acc_score - prevAcc;
 				const float typoCostDiff = cur.acc_typo_cost - prevTypo;
-				const DMorph mm = m.morphs[cur.morpheme];
+				const DMorph mm = c_m.morphs[cur.morpheme];
 				const bool single = (mm.feat & MF_SINGLE) != 0;
 				const bool saisiot = (mm.misc & MM_SAISIOT) != 0;
 				const uint32_t numNewTokens = ((splitSaisiot && saisiot) || !single) ? mm.chunk_cnt : 1;
 				const DNode g = gnodes[cur.node];
-				const float firstScore = cur.first_chunk_score + typoCostDiff * m.cfg.typo_cost_weight;
+				const float firstScore = cur.first_chunk_score + typoCostDiff * c_m.cfg.typo_cost_weight;
 				const float restScores = numNewTokens > 1 ? (scoreDiff - cur.first_chunk_score) / (float)(numNewTokens - 1) : 0.f;
 				if (splitSaisiot && saisiot)
 				{
 					for (uint32_t chn = 0; chn < numNewTokens; ++chn)
 					{
-						const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
+						const kb2_chunk ck = c_m.chunks[mm.chunk_off + chn];
 						e.pushTok(e.unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, chn == 0 ? firstScore : restScores, 0, 0);
 					}
 					e.backEnd = g.end_pos;
@@ -148,13 +148,13 @@ namespace kb
 				else if (mm.combine_socket)
 				{
 					// ret.back() is merged with the left half (PathEvaluator.hpp:1111-1134)
-					e.backTok.morph = e.backTok.morph + m.morphs[e.backTok.morph].combined;
-					e.backTok.tag = (uint8_t)(m.morphs[e.backTok.morph].feat & MF_TAG_MASK);
-					e.backEnd = g.start_pos + m.chunks[mm.chunk_off].end;
+					e.backTok.morph = e.backTok.morph + c_m.morphs[e.backTok.morph].combined;
+					e.backTok.tag = (uint8_t)(c_m.morphs[e.backTok.morph].feat & MF_TAG_MASK);
+					e.backEnd = g.start_pos + c_m.chunks[mm.chunk_off].end;
 					e.backTok.score = firstScore;
 					for (uint32_t chn = 1; chn < numNewTokens; ++chn)
 					{
-						const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
+						const kb2_chunk ck = c_m.chunks[mm.chunk_off + chn];
 						e.pushTok(e.unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, restScores, 0, 0);
 					}
 					e.backEnd = g.end_pos;
@@ -163,7 +163,7 @@ namespace kb
 				{
 					for (uint32_t chn = 0; chn < numNewTokens; ++chn)
 					{
-						const kb2_chunk ck = m.chunks[mm.chunk_off + chn];
+						const kb2_chunk ck = c_m.chunks[mm.chunk_off + chn];
 						e.pushTok(e.unify(ck.morph), g.start_pos + ck.begin, g.start_pos + ck.end, chn == 0 ? firstScore : restScores, 0, 0);
 					}
 					e.backEnd = g.end_pos;
@@ -176,10 +176,12 @@ namespace kb
 		else vv.n_tokens[s] = e.nTok;
 	}
 
-	cudaError_t launch_emit(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream)
+	cudaError_t set_model_emit(const DevModel& m) { return cudaMemcpyToSymbol(c_m, &m, sizeof(DevModel)); }
+
+	cudaError_t launch_emit(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
-		emit_kernel<<<(bv.n_sent + 127) / 128, 128, 0, stream>>>(m, bv, vv);
+		emit_kernel<<<(bv.n_sent + 127) / 128, 128, 0, stream>>>(bv, vv);
 		return cudaGetLastError();
 	}
 }

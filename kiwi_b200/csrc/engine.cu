@@ -21,6 +21,9 @@ namespace kb
 	cudaError_t launch_lattice(const DevModel& m, const BatchView& bv, cudaStream_t stream);
 	cudaError_t launch_viterbi(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
 	cudaError_t launch_emit(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
+	cudaError_t set_model_lattice(const DevModel& m);
+	cudaError_t set_model_viterbi(const DevModel& m);
+	cudaError_t set_model_emit(const DevModel& m);
 
 	static void ck(cudaError_t e, const char* what)
 	{
@@ -51,6 +54,7 @@ namespace kb
 	Engine::Engine(const void* imageBytes, size_t size)
 	{
 		model.load(imageBytes, size);
+		ck(set_model_lattice(model.dev), "constant upload"); ck(set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
 		ck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
 		for (auto& e : ev) ck(cudaEventCreate(&e), "cudaEventCreate");
 	}
@@ -126,8 +130,15 @@ namespace kb
 		sc.bv.n_sent = n; sc.bv.text = dText; sc.bv.text_off = dOffsets; sc.bv.match_options = matchOptions;
 	}
 
+	static const Model* g_constantsOwner = nullptr;     // the constant-memory model view belongs to one engine at a time
+
 	void Engine::launchAll(Scratch& sc, uint32_t n)
 	{
+		if (g_constantsOwner != &model)
+		{
+			ck(set_model_lattice(model.dev), "constant upload"); ck(set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
+			g_constantsOwner = &model;
+		}
 		ck(cudaEventRecord(ev[1], stream), "event");
 		// longest-processing-time-first launch order (sentence cost grows with its length)
 		length_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.bv.text_off, sc.lenKeys, sc.idxIn);
@@ -333,6 +344,7 @@ namespace kb
 		bind(sc, sc.dText, sc.dOff, 1, matchOptions);
 		ck(cudaMemsetAsync(sc.order, 0, 4, stream), "memset");
 		sc.bv.order = sc.order;
+		if (g_constantsOwner != &model) { ck(set_model_lattice(model.dev), "constant upload"); ck(set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload"); g_constantsOwner = &model; }
 		ck(launch_lattice(model.dev, sc.bv, stream), "lattice launch");
 		uint32_t nChunks = 0, status = 0;
 		ck(cudaMemcpyAsync(&nChunks, sc.bv.n_chunks, 4, cudaMemcpyDeviceToHost, stream), "D2H");

@@ -20,6 +20,7 @@
 
 namespace kb
 {
+	__constant__ DevModel c_m;
 	static constexpr unsigned FULL = 0xFFFFFFFFu;
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
 	static constexpr uint32_t MATCH_NORMALIZE_CODA = 1u << 16, MATCH_ZCODA = 1u << 23, MATCH_SPLIT_SAISIOT = 1u << 25, MATCH_MERGE_SAISIOT = 1u << 26;
@@ -29,10 +30,9 @@ namespace kb
 	// ------------------------------------------------------------------------------------------------
 	struct PatDev
 	{
-		const DevModel& m;
 		const uint16_t* p;
 		uint32_t n;          // `last`
-		__device__ PatDev(const DevModel& _m, const uint16_t* _p, uint32_t _n) : m{ _m }, p{ _p }, n{ _n } {}
+		__device__ PatDev(const uint16_t* _p, uint32_t _n) : p{ _p }, n{ _n } {}
 
 		static __device__ bool isAlpha(uint32_t c) { return ('A' <= c && c <= 'Z') || ('a' <= c && c <= 'z'); }
 		static __device__ bool isUpperAlpha(uint32_t c) { return 'A' <= c && c <= 'Z'; }
@@ -155,7 +155,7 @@ namespace kb
 				b += 3;
 				hasComma = true;
 			}
-			if (b == n || isSpaceChr(m, p[b]) || isHangulSyllable(p[b])) return b - first;
+			if (b == n || isSpaceChr(c_m, p[b]) || isHangulSyllable(p[b])) return b - first;
 			if (p[b] == '.')
 			{
 				++b;
@@ -241,7 +241,7 @@ namespace kb
 					if (isHighSurrogate(p[b2]) && b2 + 1 < n) { c1 = mergeSurrogate(p[b2], p[b2 + 1]); b2 += 2; }
 					else c1 = p[b2++];
 				}
-				const int r = isEmoji(m, c0, c1);
+				const int r = isEmoji(c_m, c0, c1);
 				if (r == 1) b = b1;
 				else if (r == 2) b = b2;
 				else break;
@@ -295,7 +295,6 @@ namespace kb
 	// ------------------------------------------------------------------------------------------------
 	struct Builder
 	{
-		const DevModel& m;
 		const BatchView& bv;
 		const uint32_t lane;
 		// sentence
@@ -310,7 +309,7 @@ namespace kb
 		uint32_t lastEndPos;      // out.back().endPos
 		uint32_t err;
 
-		__device__ Builder(const DevModel& _m, const BatchView& _bv, uint32_t _lane) : m{ _m }, bv{ _bv }, lane{ _lane }, err{ 0 } {}
+		__device__ Builder(const BatchView& _bv, uint32_t _lane) : bv{ _bv }, lane{ _lane }, err{ 0 } {}
 
 		// ---- appendNewNode, KTrie.cpp:16-43 ---------------------------------------------------------
 		__device__ bool appendNewNode(uint32_t startPos, uint32_t endPos, int32_t form, uint32_t uoff, uint32_t ulen, float typoCost, uint32_t spaceErrors)
@@ -361,9 +360,9 @@ namespace kb
 				if (i < e.y)
 				{
 					const DNode g = out[i];
-					const uint32_t size = g.uform_len == 0 ? (uint32_t)m.forms[g.form].size_no_space : g.uform_len;
+					const uint32_t size = g.uform_len == 0 ? (uint32_t)c_m.forms[g.form].size_no_space : g.uform_len;
 					hit = g.end_pos == endPos && g.end_pos - size == startPos && g.typo_cost == 0.f
-						&& (g.form < 0 || (m.forms[g.form].flags & FF_HASFULL));
+						&& (g.form < 0 || (c_m.forms[g.form].flags & FF_HASFULL));
 				}
 				if (__any_sync(FULL, hit)) { found = true; break; }
 			}
@@ -384,7 +383,7 @@ namespace kb
 				if (i < e.y)
 				{
 					const DNode g = out[i];
-					if (g.end_pos == pos && g.form >= 0) f = m.forms[g.form].flags & (FF_ZCODA | FF_ZSIOT);
+					if (g.end_pos == pos && g.form >= 0) f = c_m.forms[g.form].flags & (FF_ZCODA | FF_ZSIOT);
 				}
 				acc |= __reduce_or_sync(FULL, f);
 			}
@@ -395,7 +394,7 @@ namespace kb
 		{
 			const uint32_t off = nsToPos[sNs];
 			uint32_t len = nsToPos[eNs - 1] + 1 - off;
-			while (len && isSpaceChr(m, raw[off + len - 1])) --len;
+			while (len && isSpaceChr(c_m, raw[off + len - 1])) --len;
 			appendNewNode(sNs, eNs, -1, startOffset + off, len, 0.f, 0);
 		}
 
@@ -410,7 +409,7 @@ namespace kb
 				if (lastPos != startPos && !hasFormAlready(lastPos, endPos)) appendRaw(lastPos, endPos);
 			}
 			const uint32_t newNodeLength = endPos - startPos;
-			const uint32_t lengthLimit = hasJClass ? m.cfg.max_unk_form_size_followed_by_jclass : m.cfg.max_unk_form_size;
+			const uint32_t lengthLimit = hasJClass ? c_m.cfg.max_unk_form_size_followed_by_jclass : c_m.cfg.max_unk_form_size;
 			if (newNodeLength <= lengthLimit) appendRaw(startPos, endPos);
 		}
 
@@ -421,7 +420,7 @@ namespace kb
 			if (size < 2) return 0;
 			// no gap inside the span -> no error can be counted
 			if (nsToPos[nEnd - 1] - nsToPos[nBegin] == size - 1) return 0;
-			const uint16_t* f = m.form_chars + m.forms_raw[form].str_off;
+			const uint16_t* f = c_m.form_chars + c_m.forms_raw[form].str_off;
 			uint32_t cnt = 0, spaceOffset = 0;
 			for (uint32_t i = 1; i < size; ++i)
 			{
@@ -436,7 +435,7 @@ namespace kb
 		// ---- one candidate of flushCandidates, KTrie.cpp:955-996 --------------------------------------
 		__device__ void flushCandidate(int32_t cand, uint32_t endPosition, uint32_t unkFormStartNsPos, uint32_t lastSpaceBoundaryNsPos)
 		{
-			const DForm f = m.forms[cand];
+			const DForm f = c_m.forms[cand];
 			const uint32_t nBegin = endPosition - f.size_no_space;
 			const uint32_t nEnd = endPosition;
 			if (!(f.flags & FF_FIRST_IS_CODA))
@@ -446,20 +445,20 @@ namespace kb
 				insertUnkForm(unkFormStartNsPos, nBegin, hj);
 			}
 			const uint32_t spaceErrors = countSpaceErrors(cand, nBegin, nEnd);
-			if (spaceErrors <= m.cfg.space_tolerance) appendNewNode(nBegin, nEnd, cand, 0, 0, 0.f, spaceErrors);
+			if (spaceErrors <= c_m.cfg.space_tolerance) appendNewNode(nBegin, nEnd, cand, 0, 0, 0.f, spaceErrors);
 		}
 
 		// ---- trie step: child of `node` for key c, -1 if none (FrozenTrie.hpp:14-22).  Root: direct table. --
 		__device__ int32_t nextOpt(int32_t node, uint32_t c) const
 		{
-			if (node == 0) return m.trie_root_next[c];
-			const kb2_trie_node nd = m.trie_nodes[node];
+			if (node == 0) return c_m.trie_root_next[c];
+			const kb2_trie_node nd = c_m.trie_nodes[node];
 			for (uint32_t base = 0; base < nd.num_nexts; base += 32)
 			{
 				const uint32_t i = base + lane;
-				const uint32_t k = i < nd.num_nexts ? (uint32_t)m.trie_keys[nd.next_offset + i] : 0x10000u;
+				const uint32_t k = i < nd.num_nexts ? (uint32_t)c_m.trie_keys[nd.next_offset + i] : 0x10000u;
 				const unsigned hit = __ballot_sync(FULL, k == c);
-				if (hit) return node + m.trie_diffs[nd.next_offset + base + (__ffs(hit) - 1)];
+				if (hit) return node + c_m.trie_diffs[nd.next_offset + base + (__ffs(hit) - 1)];
 				// keys ascend: stop when the last key of this tile is already larger than c
 				if (__any_sync(FULL, k > c)) break;
 			}
@@ -470,8 +469,8 @@ namespace kb
 		{
 			const uint32_t off = nsToPos[specialStartNsPos];
 			uint32_t len = rawEnd - off;
-			while (len && isSpaceChr(m, raw[off + len - 1])) --len;
-			appendNewNode(specialStartNsPos, endNs, m.trie_nodes[lastChrType].value, startOffset + off, len, 0.f, 0);
+			while (len && isSpaceChr(c_m, raw[off + len - 1])) --len;
+			appendNewNode(specialStartNsPos, endNs, c_m.trie_nodes[lastChrType].value, startOffset + off, len, 0.f, 0);
 		}
 
 		static __device__ bool isDiscontinuous(uint32_t prevTag, uint32_t curTag, uint32_t prevScript, uint32_t curScript)
@@ -483,7 +482,7 @@ namespace kb
 		// ---- preparePattern, KTrie.cpp:766-858.  `str` = norm + startOffset, `len` = rest of the sentence --
 		__device__ uint32_t preparePattern(const uint16_t* str, uint32_t len)
 		{
-			PatDev pat{ m, str, len };
+			PatDev pat{ str, len };
 			uint32_t n = 0, continuousNonSpaceCount = 0;
 			uint32_t lastChrType = T_unknown;
 			nPats = 0;
@@ -503,12 +502,12 @@ namespace kb
 				const uint32_t c = str[n];
 				uint32_t c32 = c;
 				if (isHighSurrogate(c32) && n + 1 < len) c32 = mergeSurrogate(c32, str[n + 1]);
-				const uint32_t chrType = attrCls(chrAttr(m, c32));
+				const uint32_t chrType = attrCls(chrAttr(c_m, c32));
 				if (chrType == T_unknown) continuousNonSpaceCount = 0;
 				else continuousNonSpaceCount++;
 				if (chrType == T_unknown && n >= (lastChrType == T_sf ? 4u : 4096u))
 				{
-					if (!isSpaceChr(m, str[n - 3]) && !isSpaceChr(m, str[n - 2])) break;
+					if (!isSpaceChr(c_m, str[n - 3]) && !isSpaceChr(c_m, str[n - 2])) break;
 				}
 				else if (continuousNonSpaceCount >= 1024) break;
 				if (c32 >= 0x10000) ++n;
@@ -526,9 +525,9 @@ namespace kb
 				if (i < n)
 				{
 					const uint16_t c = str[i];
-					keep = !isSpaceChr(m, c);
+					keep = !isSpaceChr(c_m, c);
 					// the reference never tests the unit after a non-space high surrogate (i + 1 < n)
-					if (!keep && i > 0 && isHighSurrogate(str[i - 1]) && !isSpaceChr(m, str[i - 1]))
+					if (!keep && i > 0 && isHighSurrogate(str[i - 1]) && !isSpaceChr(c_m, str[i - 1]))
 					{
 						// str[i-1] is a high surrogate that was itself consumed as a "first" unit only if it is not
 						// the second unit of an earlier pair; surrogates are never spaces, so chains resolve by parity.
@@ -570,9 +569,9 @@ namespace kb
 				const bool havePat = nextPat != nPats;
 				{
 					const bool isInPattern = havePat && j >= np.end - np.len;
-					const uint32_t attr = chrAttr(m, c32);
+					const uint32_t attr = chrAttr(c_m, c32);
 					uint32_t chrType = attrCls(attr), scriptType = attrScript(attr);
-					if (lastChrType == T_sw && (c32 == 0x200d || (0x1f3fb <= c32 && c32 <= 0x1f3ff) || scriptType == m.script_variation_selectors))
+					if (lastChrType == T_sw && (c32 == 0x200d || (0x1f3fb <= c32 && c32 <= 0x1f3ff) || scriptType == c_m.script_variation_selectors))
 					{
 						chrType = lastChrType;
 						scriptType = lastScriptType;
@@ -614,12 +613,12 @@ namespace kb
 							if (isZFollowable(posToNs[j]) & FF_ZCODA)
 							{
 								// pushed before the trie candidates of this position -> flushed first
-								zCand = (int32_t)(m.default_tag_size + (c - 0x11A8) - 1);
+								zCand = (int32_t)(c_m.default_tag_size + (c - 0x11A8) - 1);
 							}
 						}
 						else if ((opt & (MATCH_SPLIT_SAISIOT | MATCH_MERGE_SAISIOT)) && c == 0x11BA && j + 1 < rawLen && isHangulSyllable(raw[j + 1]))
 						{
-							if (isZFollowable(posToNs[j]) & FF_ZSIOT) zCand = (int32_t)(m.default_tag_size + (0x11BA - 0x11A8) - 1);
+							if (isZFollowable(posToNs[j]) & FF_ZSIOT) zCand = (int32_t)(c_m.default_tag_size + (0x11BA - 0x11A8) - 1);
 						}
 					}
 				}
@@ -633,7 +632,7 @@ namespace kb
 						const uint32_t ms = posToNs[matchedStart];
 						if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, ms, hj);
 						insertUnkForm(unkFormStartNsPos, ms, hj);
-						appendNewNode(ms, posToNs[np.end], m.trie_nodes[np.tag].value, startOffset + matchedStart, np.len, 0.f, 0);
+						appendNewNode(ms, posToNs[np.end], c_m.trie_nodes[np.tag].value, startOffset + matchedStart, np.len, 0.f, 0);
 						++nextPat;
 						if (nextPat != nPats) np = pats[nextPat];
 					}
@@ -648,7 +647,7 @@ namespace kb
 				int32_t nextNode = nextOpt(curNode, c);
 				while (nextNode < 0)
 				{
-					const int32_t fl = m.trie_nodes[curNode].fail;
+					const int32_t fl = c_m.trie_nodes[curNode].fail;
 					if (!fl) { curNode = -1; break; }
 					curNode += fl;
 					nextNode = nextOpt(curNode, c);
@@ -666,7 +665,7 @@ namespace kb
 					// equivalent to the reference's collect-then-flush because flushing never touches the trie state.
 					for (int32_t sub = curNode; ; )
 					{
-						const kb2_trie_node sn = m.trie_nodes[sub];
+						const kb2_trie_node sn = c_m.trie_nodes[sub];
 						if (sn.value == KB2_TRIE_NONE) break;
 						if (sn.value != KB2_TRIE_SUBMATCH) flushCandidate(sn.value, endPosition, unkFormStartNsPos, lastSpaceBoundaryNsPos);
 						if (!sn.fail) break;
@@ -815,7 +814,7 @@ namespace kb
 	};
 
 	// ------------------------------------------------------------------------------------------------
-	__global__ void __launch_bounds__(128) lattice_kernel(const DevModel m, const BatchView bv)
+	__global__ void __launch_bounds__(128) lattice_kernel(const BatchView bv)
 	{
 		const uint32_t warpsPerBlock = blockDim.x >> 5;
 		const uint32_t lane = threadIdx.x & 31;
@@ -833,7 +832,7 @@ namespace kb
 		uint16_t* norm = bv.norm + wbase;
 		uint32_t* posTable = bv.pos_table + t0 + s;
 
-		Builder b{ m, bv, lane };
+		Builder b{ bv, lane };
 		b.s = s; b.norm = norm; b.W = W;
 
 		// ---- normalizeHangulWithPosition (StrUtils.h:493-520), lane-parallel with a ballot prefix
@@ -907,7 +906,7 @@ namespace kb
 			uint32_t stopPos = b.preparePattern(str, len);
 			if (b.nNs == 0)
 			{
-				while (stopPos < len && isSpaceChr(m, str[stopPos])) ++stopPos;
+				while (stopPos < len && isSpaceChr(c_m, str[stopPos])) ++stopPos;
 				splitEnd += stopPos;
 				continue;       // 2-node graph: skipped by the caller (Kiwi.cpp:1119)
 			}
@@ -940,12 +939,14 @@ namespace kb
 		if (lane == 0) { bv.n_chunks[s] = nChunks; bv.status[s] = b.err; }
 	}
 
-	cudaError_t launch_lattice(const DevModel& m, const BatchView& bv, cudaStream_t stream)
+	cudaError_t set_model_lattice(const DevModel& m) { return cudaMemcpyToSymbol(c_m, &m, sizeof(DevModel)); }
+
+	cudaError_t launch_lattice(const DevModel&, const BatchView& bv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
 		const uint32_t warpsPerBlock = 4;
 		const uint32_t blocks = (bv.n_sent + warpsPerBlock - 1) / warpsPerBlock;
-		lattice_kernel<<<blocks, warpsPerBlock * 32, 0, stream>>>(m, bv);
+		lattice_kernel<<<blocks, warpsPerBlock * 32, 0, stream>>>(bv);
 		return cudaGetLastError();
 	}
 }

@@ -28,6 +28,9 @@
 
 namespace kb
 {
+	// the model view lives in constant memory: every `c_m.field` is an immediate-offset constant-bank load
+	__constant__ DevModel c_m;
+
 	static constexpr unsigned FULL = 0xFFFFFFFFu;
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
 	static constexpr uint8_t COMMON_ROOT = 0xFF;
@@ -102,22 +105,22 @@ namespace kb
 	// Same arithmetic (float adds in the reference's order), different table layout: the per-node sorted key
 	// arrays + binary search of the reference become ONE probe into an open-addressing table over all edges whose
 	// entry also carries the child's ll, and the root uses direct tables (model.cu "Knlm one-probe layout").
-	__device__ __forceinline__ bool knLookup(const DevModel& m, uint32_t node, uint32_t key, int32_t& v, float& childLl)
+	__device__ __forceinline__ bool knLookup(uint32_t node, uint32_t key, int32_t& v, float& childLl)
 	{
-		uint32_t h = knHashFn(node, key) & m.kn_hash_mask;
+		uint32_t h = knHashFn(node, key) & c_m.kn_hash_mask;
 		while (true)
 		{
-			const uint4 e = m.kn_hash[h];
+			const uint4 e = c_m.kn_hash[h];
 			if (e.x == node && e.y == key) { v = (int32_t)e.z; childLl = __uint_as_float(e.w); return true; }
 			if (e.x == 0xFFFFFFFFu) return false;
-			h = (h + 1) & m.kn_hash_mask;
+			h = (h + 1) & c_m.kn_hash_mask;
 		}
 	}
-	__device__ __noinline__ float knProgress(const DevModel& m, int32_t& nodeIdx, uint32_t next, uint32_t site = 0)
+	__device__ __noinline__ float knProgress(int32_t& nodeIdx, uint32_t next, uint32_t site = 0)
 	{
-		if (next >= m.kn_htx_vocab || (uint32_t)nodeIdx >= 0x10000000u)
+		if (next >= c_m.kn_htx_vocab || (uint32_t)nodeIdx >= 0x10000000u)
 		{
-			if (atomicCAS(&m.debug[0], 0u, 1u) == 0u) { m.debug[1] = site; m.debug[2] = next; m.debug[3] = (uint32_t)nodeIdx; m.debug[4] = blockIdx.x; m.debug[5] = threadIdx.x; }
+			if (atomicCAS(&c_m.debug[0], 0u, 1u) == 0u) { c_m.debug[1] = site; c_m.debug[2] = next; c_m.debug[3] = (uint32_t)nodeIdx; c_m.debug[4] = blockIdx.x; c_m.debug[5] = threadIdx.x; }
 			return 0.f;
 		}
 		float acc = 0;
@@ -126,18 +129,18 @@ namespace kb
 			int32_t v; float cll;
 			if (nodeIdx == 0)
 			{
-				v = m.kn_root[next];
+				v = c_m.kn_root[next];
 				if (v == 0)
 				{
-					if (m.kn_htx) nodeIdx = m.kn_root[m.kn_htx[next]];
-					return acc + m.kn_unk_ll;
+					if (c_m.kn_htx) nodeIdx = c_m.kn_root[c_m.kn_htx[next]];
+					return acc + c_m.kn_unk_ll;
 				}
-				cll = m.kn_root_ll[next];
+				cll = c_m.kn_root_ll[next];
 			}
 			else
 			{
-				const float2 bo = m.kn_backoff[nodeIdx];            // issued together with the probe
-				if (!knLookup(m, (uint32_t)nodeIdx, next, v, cll))
+				const float2 bo = c_m.kn_backoff[nodeIdx];            // issued together with the probe
+				if (!knLookup((uint32_t)nodeIdx, next, v, cll))
 				{
 					acc += bo.y;
 					nodeIdx += __float_as_int(bo.x);
@@ -153,18 +156,18 @@ namespace kb
 			int32_t cur = nodeIdx;
 			while (true)
 			{
-				const int32_t lower = __float_as_int(m.kn_backoff[cur].x);
+				const int32_t lower = __float_as_int(c_m.kn_backoff[cur].x);
 				if (!lower) break;
 				cur += lower;
 				int32_t lv; float dummy;
-				const bool found = cur == 0 ? ((lv = m.kn_root[next]) != 0) : knLookup(m, (uint32_t)cur, next, lv, dummy);
+				const bool found = cur == 0 ? ((lv = c_m.kn_root[next]) != 0) : knLookup((uint32_t)cur, next, lv, dummy);
 				if (found && lv > 0)
 				{
 					nodeIdx = cur + lv;
 					return acc + asFloat(v);
 				}
 			}
-			nodeIdx = m.kn_htx ? m.kn_root[m.kn_htx[next]] : 0;
+			nodeIdx = c_m.kn_htx ? c_m.kn_root[c_m.kn_htx[next]] : 0;
 			return acc + asFloat(v);
 		}
 	}
@@ -174,7 +177,6 @@ namespace kb
 
 	struct Vit
 	{
-		const DevModel& m;
 		const BatchView& bv;
 		const VitView& vv;
 		const uint32_t lane;
@@ -191,7 +193,7 @@ namespace kb
 		uint32_t nClasses = 0, classCommon = 0; bool classOverflow = false;
 		bool splitComplex, splitSaisiot, mergeSaisiot;
 
-		__device__ Vit(const DevModel& _m, const BatchView& _bv, const VitView& _vv, uint32_t _lane) : m{ _m }, bv{ _bv }, vv{ _vv }, lane{ _lane } {}
+		__device__ Vit(const BatchView& _bv, const VitView& _vv, uint32_t _lane) : bv{ _bv }, vv{ _vv }, lane{ _lane } {}
 
 		// ---- left-form features of a path (what FormEvaluator will see), uniform per candidate ------
 		__device__ __noinline__ void leftFeat(uint32_t ownOff, uint32_t ownLen, uint32_t wid, int32_t morpheme, uint16_t& last, uint8_t& pol) const
@@ -201,7 +203,7 @@ namespace kb
 			{
 				if (ownOff & 0x80000000u)
 				{
-					const DForm f = m.forms[~ownOff];
+					const DForm f = c_m.forms[~ownOff];
 					last = f.last_chr;
 					pol = (f.pol & (FP_POLAR_POS | FP_POLAR_NEG | FP_LAST_SSC));
 				}
@@ -211,14 +213,14 @@ namespace kb
 					last = p[ownLen - 1];
 					if (ftPolar(p, ownLen, CP_positive)) pol |= LP_POLAR_POS;
 					if (ftPolar(p, ownLen, CP_negative)) pol |= LP_POLAR_NEG;
-					if (attrCls(m.chr_bmp[last]) == T_ssc) pol |= LP_LAST_SSC;
+					if (attrCls(c_m.chr_bmp[last]) == T_ssc) pol |= LP_LAST_SSC;
 				}
 				return;
 			}
-			int32_t fi = m.morphs[wid].form_idx;
-			if (!(fi >= 0 && m.forms[fi].str_len)) fi = m.morphs[morpheme].form_idx;
-			if (fi < 0 || m.forms[fi].str_len == 0) { pol = LP_EMPTY | LP_POLAR_POS | LP_POLAR_NEG; return; }
-			const DForm f = m.forms[fi];
+			int32_t fi = c_m.morphs[wid].form_idx;
+			if (!(fi >= 0 && c_m.forms[fi].str_len)) fi = c_m.morphs[morpheme].form_idx;
+			if (fi < 0 || c_m.forms[fi].str_len == 0) { pol = LP_EMPTY | LP_POLAR_POS | LP_POLAR_NEG; return; }
+			const DForm f = c_m.forms[fi];
 			last = f.last_chr;
 			pol = (f.pol & (FP_POLAR_POS | FP_POLAR_NEG | FP_LAST_SSC));
 		}
@@ -236,9 +238,9 @@ namespace kb
 					if (isHighSurrogate(form[i])) { chrs[j] = mergeSurrogate(form[i], i + 1 < len ? form[i + 1] : 0); i += 2; }
 					else { chrs[j] = form[i]; ++i; }
 				}
-				if (isEmoji(m, chrs[0], chrs[1])) penalty = -10.f;
+				if (isEmoji(c_m, chrs[0], chrs[1])) penalty = -10.f;
 			}
-			return penalty - ((float)len * m.cfg.oov_rule_scale + m.cfg.oov_rule_bias);
+			return penalty - ((float)len * c_m.cfg.oov_rule_scale + c_m.cfg.oov_rule_bias);
 		}
 
 		// PathEvaluator.hpp:22-44
@@ -251,7 +253,7 @@ namespace kb
 			if (pv.uform_len)
 			{
 				const uint32_t c = norm[pv.uform_off + pv.uform_len - 1];
-				const uint32_t tag = attrCls(m.chr_bmp[c]);
+				const uint32_t tag = attrCls(c_m.chr_bmp[c]);
 				if (tag == T_ssc || c == '"' || c == '\'') return false;
 				if (T_sf <= tag && tag <= T_sb) return true;
 			}
@@ -294,7 +296,7 @@ namespace kb
 			uint32_t bucketCnt[4] = { 0, 0, 0, 0 };
 			uint32_t fwCarry = cc.firstWid0;
 			htClear();
-			const bool allowedSpaceBetweenChunk = m.cfg.space_tolerance > 0;
+			const bool allowedSpaceBetweenChunk = c_m.cfg.space_tolerance > 0;
 
 			for (uint32_t qb = 0; qb < P; qb += pairsPerRound)
 			{
@@ -318,14 +320,14 @@ namespace kb
 						if (pp.combine_socket != cc.cur.combine_socket || cc.single) valid = false;
 						else if (cc.spaceBefore)
 						{
-							if (allowedSpaceBetweenChunk) candScore -= m.cfg.space_penalty;
+							if (allowedSpaceBetweenChunk) candScore -= c_m.cfg.space_penalty;
 							else valid = false;
 						}
 						if (valid)
 						{
 							setsFW = true;
-							const DMorph pw = m.morphs[pp.wid];
-							fwVal = m.morphs[(int32_t)pp.wid + pw.combined].lm_id;
+							const DMorph pw = c_m.morphs[pp.wid];
+							fwVal = c_m.morphs[(int32_t)pp.wid + pw.combined].lm_id;
 						}
 					}
 				}
@@ -363,19 +365,19 @@ namespace kb
 					if (cc.cur.combine_socket && cc.single) {}
 					else
 					{
-						if ((m.morphs[firstWid].feat & MF_TAG_MASK) == T_p) valid = false;
+						if ((c_m.morphs[firstWid].feat & MF_TAG_MASK) == T_p) valid = false;
 						else
 						{
-							float ll = knProgress(m, lmState, firstWid, 3);
+							float ll = knProgress(lmState, firstWid, 3);
 							candScore += ll;
 							firstChunkScore += ll;
 							if (!cc.single)
 							{
 								for (uint32_t i = 1; i < cc.cur.chunk_cnt; ++i)
 								{
-									const uint32_t wid = m.morphs[m.chunks[cc.cur.chunk_off + i].morph].lm_id;
-									if ((m.morphs[wid].feat & MF_TAG_MASK) == T_p) { valid = false; break; }
-									ll = knProgress(m, lmState, wid, 4);
+									const uint32_t wid = c_m.morphs[c_m.chunks[cc.cur.chunk_off + i].morph].lm_id;
+									if ((c_m.morphs[wid].feat & MF_TAG_MASK) == T_p) { valid = false; break; }
+									ll = knProgress(lmState, wid, 4);
 									candScore += ll;
 								}
 							}
@@ -663,12 +665,12 @@ namespace kb
 					rootId = doFork ? (uint8_t)r : COMMON_ROOT;
 					float candScore = pp->acc_score + cs.additionalScore;
 					float firstChunkScore = cs.additionalScore;
-					if (spacePen) candScore -= m.cfg.space_penalty;
+					if (spacePen) candScore -= c_m.cfg.space_penalty;
 					if (condFail) candScore += fc.ignoreCondScore;
 					lmState = pp->lm_state;
 					const uint32_t pf = pp->wid_feat;
 					const uint32_t firstWid = fwIdx ? sm->fwTab[fwIdx] : cs.firstWid;
-					bad = firstWid >= m.n_morphs || slot >= GROUP || fc.inBeg + q >= poolCap;
+					bad = firstWid >= c_m.n_morphs || slot >= GROUP || fc.inBeg + q >= poolCap;
 					if (bad)
 					{
 						if (atomicCAS(&bv.debug[0], 0u, 1u) == 0u)
@@ -680,12 +682,12 @@ namespace kb
 					else
 					if (!(cs.flags & CS_NO_LM))
 					{
-						float ll = knProgress(m, lmState, firstWid, 1);
+						float ll = knProgress(lmState, firstWid, 1);
 						candScore += ll; firstChunkScore += ll;
 						if (!(cs.flags & CS_SINGLE))
 						{
 							#pragma unroll 1
-							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = knProgress(m, lmState, m.chunk_lm[cs.chunkOff + c], 2); candScore += ll; }
+							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = knProgress(lmState, c_m.chunk_lm[cs.chunkOff + c], 2); candScore += ll; }
 						}
 					}
 					// RuleBasedScorer::operator() + special-state update (PathEvaluator.hpp:115-183, 208-230)
@@ -862,9 +864,9 @@ namespace kb
 		{
 			const DNode node = nodes[nodeIdx];
 			float whitespaceDiscount = 0;
-			if (node.uform_len == 0 && node.form >= 0 && m.forms[node.form].str_len && node.space_errors)
-				whitespaceDiscount = -m.cfg.space_penalty * (float)node.space_errors;
-			const float typoDiscount = -node.typo_cost * m.cfg.typo_cost_weight;
+			if (node.uform_len == 0 && node.form >= 0 && c_m.forms[node.form].str_len && node.space_errors)
+				whitespaceDiscount = -c_m.cfg.space_penalty * (float)node.space_errors;
+			const float typoDiscount = -node.typo_cost * c_m.cfg.typo_cost_weight;
 			const float nodeLevelDiscount = whitespaceDiscount + typoDiscount + unkFormDiscount;
 			const uint32_t P = inEnd - inBeg;
 			const uint32_t mode = P <= 128 ? 0 : (P <= 512 ? 1 : 2);
@@ -877,7 +879,7 @@ namespace kb
 			const bool itemOK2 = itemOK && !classOverflow;
 			if (ownLen) leftFeat(ownOff, ownLen, 0, 0, fc.ownLeftLast, fc.ownLeftPol);
 			nItems = 0;
-			const bool posE = node.form >= 0 && (m.forms[node.form].flags & FF_FIRST_IS_A);
+			const bool posE = node.form >= 0 && (c_m.forms[node.form].flags & FF_FIRST_IS_A);
 			const bool snPoint = node.uform_len && norm[node.uform_off + node.uform_len - 1] == '.';
 
 			#pragma unroll 1
@@ -898,14 +900,14 @@ namespace kb
 						if (lane < gcount)
 						{
 							const int32_t curId = (int32_t)(candList ? candList[gb + lane] : (lane == 0 ? unk0 : unk1));
-							const DMorph cur = m.morphs[curId];
+							const DMorph cur = c_m.morphs[curId];
 							const uint32_t tag = cur.feat & MF_TAG_MASK;
 							const bool single = (cur.feat & MF_SINGLE) != 0;
 							bool skip = cur.nonstd_dialect != 0;
 							if (!skip && splitComplex)
 							{
-								if (m.morphs[curId + cur.combined].misc & MM_COMPLEX) skip = true;
-								for (uint32_t c = 0; c < cur.chunk_cnt && !skip; ++c) if (m.morphs[m.chunks[cur.chunk_off + c].morph].misc & MM_COMPLEX) skip = true;
+								if (c_m.morphs[curId + cur.combined].misc & MM_COMPLEX) skip = true;
+								for (uint32_t c = 0; c < cur.chunk_cnt && !skip; ++c) if (c_m.morphs[c_m.chunks[cur.chunk_off + c].morph].misc & MM_COMPLEX) skip = true;
 							}
 							if (!skip && (tag == T_z_coda || tag == T_z_siot))
 							{
@@ -914,14 +916,14 @@ namespace kb
 							}
 							else if (!skip)
 							{
-								if (!single && node.prev && spaceBefore && cur.form_idx >= 0 && m.forms[cur.form_idx].str_len == 1)
+								if (!single && node.prev && spaceBefore && cur.form_idx >= 0 && c_m.forms[cur.form_idx].str_len == 1)
 								{
 									// contracted '하다/하게/하지' after a space is not a candidate (PathEvaluator.hpp:435-448)
-									const uint32_t k0 = m.form_chars[m.forms_raw[cur.form_idx].str_off];
+									const uint32_t k0 = c_m.form_chars[c_m.forms_raw[cur.form_idx].str_off];
 									if (k0 == 0xB2E4 || k0 == 0xAC8C || k0 == 0xC9C0)
 									{
-										const DMorph c0 = m.morphs[m.chunks[cur.chunk_off].morph];
-										if (c0.form_idx >= 0 && m.forms[c0.form_idx].str_len == 1 && m.form_chars[m.forms_raw[c0.form_idx].str_off] == 0xD558) skip = true;
+										const DMorph c0 = c_m.morphs[c_m.chunks[cur.chunk_off].morph];
+										if (c0.form_idx >= 0 && c_m.forms[c0.form_idx].str_len == 1 && c_m.form_chars[c_m.forms_raw[c0.form_idx].str_off] == 0xD558) skip = true;
 									}
 								}
 								if (!skip)
@@ -929,7 +931,7 @@ namespace kb
 									const uint32_t specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7, sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
 									const bool fork = sbType != 0 || specialType == 0 || specialType == 1 || specialType == 3 || specialType == 4;
 									const bool socketChunk = cur.combine_socket && !single;
-									const DMorphX mx = m.morphx[curId];
+									const DMorphX mx = c_m.morphx[curId];
 									const bool noLm = cur.combine_socket && single;
 									if (!itemOK2 || (mode == 1 && fork)) cls = CLS_GENERAL;
 									else if (!noLm && !socketChunk && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) cls = CLS_SKIP;     // every pair hits `goto continueFor`
@@ -947,7 +949,7 @@ namespace kb
 								}
 							}
 							cs.curId = curId; cs.feat = cur.feat; cs.chunkOff = cur.chunk_off; cs.chunkCnt = cur.chunk_cnt; cs.senseId = cur.sense_id;
-							cs.additionalScore = cur.user_score + nodeLevelDiscount + m.tag_left_boundary[hasLB ? 1 : 0][clearIrregular((uint8_t)tag)];
+							cs.additionalScore = cur.user_score + nodeLevelDiscount + c_m.tag_left_boundary[hasLB ? 1 : 0][clearIrregular((uint8_t)tag)];
 						}
 						cs.cls = cls;
 						sm->cand[lane] = cs;
@@ -960,7 +962,7 @@ namespace kb
 							const uint32_t cv = (cs.feat >> MF_VOWEL_SHIFT) & 15, cp = (cs.feat >> MF_POLAR_SHIFT) & 3;
 							const bool curNN = isNNClass((uint8_t)curTag);
 							const bool socketChunk = (cs.flags & CS_SOCKET_CHUNK) != 0;
-							const uint32_t curSocket = m.morphs[cs.curId].combine_socket;
+							const uint32_t curSocket = c_m.morphs[cs.curId].combine_socket;
 							for (uint32_t c = 0; c < nClasses; ++c)
 							{
 								const uint32_t f = sm->fclass[c];
@@ -971,7 +973,7 @@ namespace kb
 								{
 									// merge <v> <chunk> with only the same socket (PathEvaluator.hpp:578-591)
 									if (!socketChunk || socket != curSocket) valid = false;
-									else if (spaceBefore && !(m.cfg.space_tolerance > 0)) valid = false;
+									else if (spaceBefore && !(c_m.cfg.space_tolerance > 0)) valid = false;
 									if (valid) cm.sets |= 1u << c;
 								}
 								if (valid && !(f & FW_NOCOND))
@@ -986,7 +988,7 @@ namespace kb
 							}
 							// prohibit <v> without <chunk> (PathEvaluator.hpp:603-607): a socket chunk whose first wid is the tag-P
 							// placeholder only survives behind a path that overrides firstWid; without such a path nothing survives
-							if (socketChunk && !cm.sets && (m.morphx[cs.curId].xflags & MX_FIRST_IS_P)) cm.valid = 0;
+							if (socketChunk && !cm.sets && (c_m.morphx[cs.curId].xflags & MX_FIRST_IS_P)) cm.valid = 0;
 						}
 						sm->cmask[lane] = cm;
 						myCls = cls; myValid = cm.valid; myCondFail = cm.condFail; mySets = cm.sets; myFlags = cs.flags;
@@ -1048,7 +1050,7 @@ namespace kb
 							const uint32_t perRound = 32u >> rshift;
 							const bool spacePen = socketChunk && spaceBefore;          // only socket matches survive `spaceBefore` (with tolerance) and they pay the penalty
 							uint32_t fwCarry = 0;                     // index into fwTab of the inherited first-wid override, 0 = none
-							const bool firstIsP = socketChunk && (m.morphx[sm->cand[k].curId].xflags & MX_FIRST_IS_P) != 0;
+							const bool firstIsP = socketChunk && (c_m.morphx[sm->cand[k].curId].xflags & MX_FIRST_IS_P) != 0;
 							#pragma unroll 1
 							for (uint32_t qb = 0; qb < P; qb += perRound)
 							{
@@ -1074,7 +1076,7 @@ namespace kb
 									if (smask)
 									{
 										uint32_t fwVal = 0;
-										if (setsFW) { const uint32_t pw = pool[inBeg + q].wid; fwVal = m.morphs[(int32_t)pw + m.morphs[pw].combined].lm_id; }
+										if (setsFW) { const uint32_t pw = pool[inBeg + q].wid; fwVal = c_m.morphs[(int32_t)pw + c_m.morphs[pw].combined].lm_id; }
 										unsigned rem = smask;
 										while (rem)
 										{
@@ -1100,7 +1102,7 @@ namespace kb
 									if (smask) fwCarry = __shfl_sync(FULL, myIdx, 31 - __clz(smask));
 								}
 								// prohibit <v> without <chunk>: tag P first wid (PathEvaluator.hpp:603-607)
-								if (valid && socketChunk && (fwIdx ? ((m.morphs[sm->fwTab[fwIdx]].feat & MF_TAG_MASK) == T_p) : firstIsP)) valid = false;
+								if (valid && socketChunk && (fwIdx ? ((c_m.morphs[sm->fwTab[fwIdx]].feat & MF_TAG_MASK) == T_p) : firstIsP)) valid = false;
 								const unsigned vm = __ballot_sync(FULL, valid);
 								if (valid) sm->item[nItems + __popc(vm & ((1u << lane) - 1))] = (k << 27) | (fwIdx << 20) | (q << 3) | ((spacePen && isSock) ? 4u : 0u) | (rr << 1) | (condFail ? 1u : 0u);
 								nItems += __popc(vm);
@@ -1112,13 +1114,13 @@ namespace kb
 						flushItems(fc); if (err) return;
 						const uint32_t before = top;
 						const int32_t curId = sm->cand[k].curId;
-						const DMorph cur = m.morphs[curId];
+						const DMorph cur = c_m.morphs[curId];
 						const uint32_t tag = cur.feat & MF_TAG_MASK;
 						if (cls == CLS_SHORTCUT)
 						{
 							// shortcut (PathEvaluator.hpp:389-432): copy qualifying incoming paths, no LM step
-							const float add = cur.user_score * m.cfg.typo_cost_weight;
-							const DMorph lmM = m.morphs[cur.lm_id];
+							const float add = cur.user_score * c_m.cfg.typo_cost_weight;
+							const DMorph lmM = c_m.morphs[cur.lm_id];
 							#pragma unroll 1
 							for (uint32_t qb = 0; qb < P; qb += 32)
 							{
@@ -1220,7 +1222,7 @@ namespace kb
 					p = pool[nodeBeg + e];
 					const uint32_t slot = p.root_id == COMMON_ROOT ? 0 : p.root_id + 1;
 					const float mxs = slot == 0 ? mx[0] : (slot == 1 ? mx[1] : mx[2]);
-					keep = !(p.acc_score + m.cfg.cut_off_threshold < mxs);
+					keep = !(p.acc_score + c_m.cfg.cut_off_threshold < mxs);
 				}
 				const unsigned km = __ballot_sync(FULL, keep);
 				__syncwarp();
@@ -1288,9 +1290,9 @@ namespace kb
 			if (lane == 0)
 			{
 				DPath b;
-				b.lm_state = m.kn_bos_node; b.acc_score = 0; b.first_chunk_score = 0; b.wid = 0; b.morpheme = 0; b.parent = NPOS; b.own_off = 0; b.acc_typo_cost = 0;
+				b.lm_state = c_m.kn_bos_node; b.acc_score = 0; b.first_chunk_score = 0; b.wid = 0; b.morpheme = 0; b.parent = NPOS; b.own_off = 0; b.acc_typo_cost = 0;
 				b.own_len = 0; b.node = 0; b.sp_state = 0; b.root_id = COMMON_ROOT; b.combine_socket = 0; b.prev_root_id = 0;
-				const DMorph m0 = m.morphs[0];
+				const DMorph m0 = c_m.morphs[0];
 				b.morph_tag = (uint8_t)(m0.feat & MF_TAG_MASK); b.wid_feat = m0.feat;
 				uint16_t ll; uint8_t lp;
 				leftFeat(0, 0, 0, 0, ll, lp);
@@ -1311,12 +1313,12 @@ namespace kb
 				const uint32_t nodeBeg = top;
 				if (node.form >= 0)
 				{
-					const DForm f = m.forms[node.form];
-					evaluate(i, nodeBeg, m.form_cands + f.cand_off, f.cand_cnt, 0, 0, 0.f, node.uform_off, node.uform_len, inBeg, inEnd);
+					const DForm f = c_m.forms[node.form];
+					evaluate(i, nodeBeg, c_m.form_cands + f.cand_off, f.cand_cnt, 0, 0, 0.f, node.uform_off, node.uform_len, inBeg, inEnd);
 					if (err) return 0;
 					if (node.typo_cost == 0.f && (f.flags & FF_ALL_PARTIAL))
 					{
-						const uint16_t* fs = m.form_chars + m.forms_raw[node.form].str_off;
+						const uint16_t* fs = c_m.form_chars + c_m.forms_raw[node.form].str_off;
 						const float unkScore = unkFormScore(fs, f.str_len);
 						evaluate(i, nodeBeg, nullptr, 1, unkNNP, 0, unkScore, ~(uint32_t)node.form, f.str_len, inBeg, inEnd);
 						if (err) return 0;
@@ -1360,7 +1362,7 @@ namespace kb
 					ok = p.combine_socket == 0;
 					if (ok)
 					{
-						const DMorph pm = m.morphs[p.morpheme];
+						const DMorph pm = c_m.morphs[p.morpheme];
 						const bool single = (pm.feat & MF_SINGLE) != 0;
 						if (!single && pm.chunk_cnt <= (pm.combine_socket ? 2u : 1u) && ((pm.feat >> MF_VOWEL_SHIFT) & 15) != CV_none) ok = false;
 						if (p.morph_tag == T_z_siot) ok = false;
@@ -1371,7 +1373,7 @@ namespace kb
 						if (!openEnding)
 						{
 							int32_t st = p.lm_state;
-							c += knProgress(m, st, 1, 5);
+							c += knProgress(st, 1, 5);
 							if (p.sp_state & 1) c -= 2;
 							if (p.sp_state & 2) c -= 2;
 						}
@@ -1480,7 +1482,7 @@ namespace kb
 	#ifndef KB_VIT_MIN_BLOCKS
 #define KB_VIT_MIN_BLOCKS 4
 #endif
-	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) viterbi_kernel(const DevModel m, const BatchView bv, const VitView vv)
+	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) viterbi_kernel(const BatchView bv, const VitView vv)
 	{
 		__shared__ WarpSmem smAll[WARPS_PER_BLOCK];
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1496,7 +1498,7 @@ namespace kb
 		const size_t nbase = (size_t)bv.nodes_per_unit * wbase;
 		const size_t pbase = (size_t)vv.paths_per_unit * wbase + (size_t)vv.paths_const * s;
 
-		Vit v{ m, bv, vv, lane };
+		Vit v{ bv, vv, lane };
 		v.norm = bv.norm + wbase;
 		v.pool = vv.paths + pbase;
 		v.poolCap = vv.paths_per_unit * W + vv.paths_const;
@@ -1606,11 +1608,13 @@ namespace kb
 		}
 	}
 
-	cudaError_t launch_viterbi(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream)
+	cudaError_t set_model_viterbi(const DevModel& m) { return cudaMemcpyToSymbol(c_m, &m, sizeof(DevModel)); }
+
+	cudaError_t launch_viterbi(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
 		const uint32_t blocks = (bv.n_sent + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-		viterbi_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(m, bv, vv);
+		viterbi_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(bv, vv);
 		return cudaGetLastError();
 	}
 }
