@@ -191,6 +191,7 @@ namespace kb
 		uint16_t* ht; uint32_t htUsed;
 		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0, nFw = 1;
 		uint32_t nClasses = 0, classCommon = 0; bool classOverflow = false;
+		volatile uint32_t* sActive = nullptr; uint32_t roundCnt = 0;       // block-level lockstep over lattice nodes (see viterbi_kernel)
 		bool splitComplex, splitSaisiot, mergeSaisiot;
 
 		__device__ Vit(const BatchView& _bv, const VitView& _vv, uint32_t _lane) : bv{ _bv }, vv{ _vv }, lane{ _lane } {}
@@ -1342,6 +1343,11 @@ namespace kb
 				}
 				if (lane == 0) { npOff[i] = nodeBeg; npCnt[i] = top - nodeBeg; }
 				__syncwarp();
+#ifdef KB_LOCKSTEP
+				// keep the warps of the block at the same lattice-node phase: they then share instruction-cache lines
+				asm volatile("bar.sync 1, %0;" :: "r"(roundCnt) : "memory");
+				roundCnt = *sActive;
+#endif
 			}
 
 			// ---- end node (PathEvaluator.hpp:1320-1357): candidates go to the pool tail as temporary records
@@ -1487,9 +1493,22 @@ namespace kb
 		__shared__ WarpSmem smAll[WARPS_PER_BLOCK];
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 		const uint32_t slot = blockIdx.x * WARPS_PER_BLOCK + wib;
+#ifdef KB_LOCKSTEP
+		__shared__ uint32_t sActiveCount;
+		if (threadIdx.x == 0) sActiveCount = 0;
+		__syncthreads();
+		const bool inRange = slot < bv.n_sent;
+		const uint32_t s = inRange ? bv.order[slot] : 0;
+		const bool failed = inRange && bv.status[s] != 0;
+		if (inRange && !failed && lane == 0) atomicAdd(&sActiveCount, 32u);
+		__syncthreads();
+		if (!inRange) return;
+		if (failed) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
+#else
 		if (slot >= bv.n_sent) return;
 		const uint32_t s = bv.order[slot];
 		if (bv.status[s]) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
+#endif
 
 		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
 		const uint32_t n = t1 - t0;
@@ -1504,6 +1523,9 @@ namespace kb
 		v.poolCap = vv.paths_per_unit * W + vv.paths_const;
 		v.top = 0;
 		v.sm = &smAll[wib]; v.ht = smAll[wib].ht; v.htUsed = 1;
+#ifdef KB_LOCKSTEP
+		v.sActive = &sActiveCount; v.roundCnt = sActiveCount;
+#endif
 		v.splitComplex = (bv.match_options >> 22) & 1; v.splitSaisiot = (bv.match_options >> 25) & 1; v.mergeSaisiot = (bv.match_options >> 26) & 1;
 		v.htClear();
 
@@ -1600,6 +1622,13 @@ namespace kb
 
 		// the best stitched result (ret[0]); tokens are materialised by emit_kernel
 		(void)normLen;
+#ifdef KB_LOCKSTEP
+		// leave the lockstep: shrink the participant count for the next round and satisfy the current one without waiting
+		if (lane == 0) atomicSub(&sActiveCount, 32u);
+		__threadfence_block();
+		__syncwarp();
+		asm volatile("bar.arrive 1, %0;" :: "r"(v.roundCnt) : "memory");
+#endif
 		if (lane == 0)
 		{
 			vv.best_rec[s] = (!v.err && retN) ? retRec[0] : -1;
