@@ -44,7 +44,7 @@ class ClockSampler(threading.Thread):
                     if v.strip().lower().startswith("active"): self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         s = sorted(self.samples)
@@ -95,7 +95,7 @@ def run_reference_cpu(texts, threads, repeats=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=8192)

@@ -30,7 +30,7 @@ namespace kb
 		if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error in ") + what + ": " + cudaGetErrorString(e));
 	}
 
-	static constexpr uint32_t DEFAULT_PATHS_PER_UNIT = 72, DEFAULT_PATHS_CONST = 4096;
+	static constexpr uint32_t DEFAULT_PATHS_PER_UNIT = 128, DEFAULT_PATHS_CONST = 8192;
 
 	__global__ void length_kernel(uint32_t nSent, const uint32_t* __restrict__ textOff, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx)
 	{
@@ -259,7 +259,7 @@ namespace kb
 				subOff.push_back((uint32_t)subText.size());
 			}
 			PassResult r1;
-			runHostPass(retry_, subText.data(), subOff.data(), (uint32_t)failed.size(), matchOptions, DEFAULT_PATHS_PER_UNIT * 16, DEFAULT_PATHS_CONST * 16, KB_DEFAULT_NODES_PER_UNIT * 4, r1, out);
+			runHostPass(retry_, subText.data(), subOff.data(), (uint32_t)failed.size(), matchOptions, DEFAULT_PATHS_PER_UNIT * 8, DEFAULT_PATHS_CONST * 8, KB_DEFAULT_NODES_PER_UNIT * 4, r1, out);
 			out.tokens.reserve(r0.toks.size() + r1.toks.size());
 			out.tokOff.assign(n + 1, 0);
 			out.scores = std::move(r0.scores); out.status = std::move(r0.status);
@@ -323,7 +323,7 @@ namespace kb
 				subOff.push_back((uint32_t)subText.size());
 			}
 			BatchOutput tmp; PassResult r1;
-			runHostPass(retry_, subText.data(), subOff.data(), (uint32_t)failed.size(), matchOptions, DEFAULT_PATHS_PER_UNIT * 16, DEFAULT_PATHS_CONST * 16, KB_DEFAULT_NODES_PER_UNIT * 4, r1, tmp);
+			runHostPass(retry_, subText.data(), subOff.data(), (uint32_t)failed.size(), matchOptions, DEFAULT_PATHS_PER_UNIT * 8, DEFAULT_PATHS_CONST * 8, KB_DEFAULT_NODES_PER_UNIT * 4, r1, tmp);
 			for (uint32_t s : r1.status) if (s) throw std::runtime_error("a sentence exceeded the device scratch capacity even in the retry arena (status " + std::to_string(s) + ")");
 			ms += tmp.msTotal;
 			total += (uint32_t)r1.toks.size();
