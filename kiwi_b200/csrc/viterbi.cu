@@ -66,7 +66,10 @@ namespace kb
 		uint32_t candNew[GROUP];                // entries created per candidate of the current group
 		uint32_t fwTab[FWTAB_CAP];              // first-wid overrides of socket chunks (PathEvaluator.hpp:590), index 0 unused
 	};
-	static constexpr uint32_t WARPS_PER_BLOCK = 4;
+#ifndef KB_VIT_WARPS
+#define KB_VIT_WARPS 4
+#endif
+	static constexpr uint32_t WARPS_PER_BLOCK = KB_VIT_WARPS;
 	static constexpr uint32_t MAX_RESULTS = 16;
 
 	__device__ __forceinline__ float asFloat(int32_t v) { return __int_as_float(v); }
@@ -1490,7 +1493,8 @@ namespace kb
 #endif
 	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) viterbi_kernel(const BatchView bv, const VitView vv)
 	{
-		__shared__ WarpSmem smAll[WARPS_PER_BLOCK];
+		extern __shared__ __align__(16) unsigned char smRaw[];
+		WarpSmem* smAll = reinterpret_cast<WarpSmem*>(smRaw);
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 		const uint32_t slot = blockIdx.x * WARPS_PER_BLOCK + wib;
 #ifdef KB_LOCKSTEP
@@ -1643,7 +1647,10 @@ namespace kb
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
 		const uint32_t blocks = (bv.n_sent + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-		viterbi_kernel<<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(bv, vv);
+		static bool attrSet = false;
+		const size_t smemBytes = sizeof(WarpSmem) * WARPS_PER_BLOCK;
+		if (!attrSet) { cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); attrSet = true; }
+		viterbi_kernel<<<blocks, WARPS_PER_BLOCK * 32, smemBytes, stream>>>(bv, vv);
 		return cudaGetLastError();
 	}
 }
