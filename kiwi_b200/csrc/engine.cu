@@ -227,24 +227,21 @@ namespace kb
 		last.kernelLaunches += 5;
 	}
 
-	void Engine::analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out)
+	void Engine::analyzeOne(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out)
 	{
 		out = BatchOutput{};
 		out.tokOff.assign(n + 1, 0);
 		out.scores.assign(n, 0.f);
 		out.status.assign(n, 0);
-		last = Stats{};
 		if (n == 0) return;
-		if (offsets[0] != 0) throw std::runtime_error("offsets[0] must be 0");
 		const size_t T = offsets[n];
-		for (uint32_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) throw std::runtime_error("offsets must be non-decreasing");
 		if (T >= (1ull << 31)) throw std::runtime_error("batch too large (>= 2^31 UTF-16 units); split it");
 
 		PassResult r0;
 		runHostPass(main_, text, offsets, n, matchOptions, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT, r0, out);
 		std::vector<uint32_t> failed;
 		for (uint32_t i = 0; i < n; ++i) if (r0.status[i]) failed.push_back(i);
-		last.retried = failed.size();
+		last.retried += failed.size();
 		if (failed.empty())
 		{
 			out.tokens = std::move(r0.toks); out.tokOff = std::move(r0.tokOff); out.scores = std::move(r0.scores); out.status = std::move(r0.status);
@@ -288,9 +285,50 @@ namespace kb
 		last.msLattice = out.msLattice; last.msViterbi = out.msViterbi; last.msPack = out.msPack;
 	}
 
+	// Public entry: batches of any size.  The scratch arena is sized per pass, so a large batch (65536 / 1 M sentences)
+	// is cut into passes of at most MAX_UNITS_PER_PASS normalised units / MAX_SENT_PER_PASS sentences, run back to back.
+	static constexpr size_t MAX_UNITS_PER_PASS = 2u << 20, MAX_SENT_PER_PASS = 16384;
+
+	void Engine::analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out)
+	{
+		last = Stats{};
+		if (n && offsets[0] != 0) throw std::runtime_error("offsets[0] must be 0");
+		for (uint32_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) throw std::runtime_error("offsets must be non-decreasing");
+		const size_t totalUnits = n ? 2 * (size_t)offsets[n] + 4 * (size_t)n : 0;
+		if (totalUnits <= MAX_UNITS_PER_PASS && n <= MAX_SENT_PER_PASS) { analyzeOne(text, offsets, n, matchOptions, out); return; }
+		out = BatchOutput{};
+		out.tokOff.assign(1, 0);
+		uint32_t i0 = 0;
+		std::vector<uint32_t> subOff;
+		while (i0 < n)
+		{
+			uint32_t i1 = i0; size_t units = 0;
+			while (i1 < n && i1 - i0 < MAX_SENT_PER_PASS)
+			{
+				const size_t u = 2 * (size_t)(offsets[i1 + 1] - offsets[i1]) + 4;
+				if (i1 > i0 && units + u > MAX_UNITS_PER_PASS) break;
+				units += u; ++i1;
+			}
+			subOff.resize(i1 - i0 + 1);
+			for (uint32_t k = 0; k <= i1 - i0; ++k) subOff[k] = offsets[i0 + k] - offsets[i0];
+			BatchOutput part;
+			analyzeOne(text + offsets[i0], subOff.data(), i1 - i0, matchOptions, part);
+			const uint32_t base = (uint32_t)out.tokens.size();
+			out.tokens.insert(out.tokens.end(), part.tokens.begin(), part.tokens.end());
+			for (uint32_t k = 1; k <= i1 - i0; ++k) out.tokOff.push_back(base + part.tokOff[k]);
+			out.scores.insert(out.scores.end(), part.scores.begin(), part.scores.end());
+			out.status.insert(out.status.end(), part.status.begin(), part.status.end());
+			out.msH2D += part.msH2D; out.msLattice += part.msLattice; out.msViterbi += part.msViterbi; out.msPack += part.msPack; out.msD2H += part.msD2H; out.msTotal += part.msTotal;
+			i0 = i1;
+		}
+		last.nSentences = n; last.rawUnits = offsets[n]; last.tokens = out.tokens.size();
+		last.msLattice = out.msLattice; last.msViterbi = out.msViterbi; last.msPack = out.msPack;
+	}
+
 	float Engine::analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens)
 	{
 		const size_t U = 2 * (size_t)totalUnits + 4 * (size_t)n;
+		if (U > 4 * MAX_UNITS_PER_PASS) throw std::runtime_error("kiwi_b200_analyze_device: batch too large for one device pass; split it (kiwi_b200_analyze_batch splits automatically)");
 		Scratch& sc = main_;
 		ensureScratch(sc, U, n, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
 		bind(sc, dText, dOffsets, n, matchOptions);

@@ -51,6 +51,7 @@ namespace kb
 
 		// host buffers in, host buffers out (H2D / D2H inside)
 		void analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out);
+		void analyzeOne(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out);
 		// device-resident inputs; results stay on the device.  returns elapsed ms
 		float analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens);
 		// lattice of one sentence for stage-level parity tests

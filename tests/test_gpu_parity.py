@@ -119,3 +119,17 @@ def test_reference_c_api_single_and_multi(kiwi, oracle):
     n = lib.kiwi_analyze_mw(kiwi._h, READER(reader), RECEIVER(receiver), None, 1, opt)
     assert n == len(texts) and order == list(range(len(texts)))
     assert counts == [len(oracle.analyze(t)[0]) for t in texts]
+
+
+def test_large_batch_is_split_into_passes(kiwi):
+    """40 000 sentences exceed one device pass (16 384 sentences / 2 Mi units): the engine cuts the batch and
+    the concatenated result must equal the per-pass results (batch-composition invariance at scale)."""
+    from kiwi_b200.synth import synth_batch
+    base = synth_batch(2000, 12345)
+    texts = (base * 20)[:40000]
+    r = kiwi.analyze_batch(texts)
+    assert len(r.token_offsets) == len(texts) + 1
+    ref = kiwi.analyze_batch(base)
+    for i in range(0, len(texts), 997):
+        j = i % len(base)
+        assert r.sentence(i).tobytes() == ref.sentence(j).tobytes() and r.scores[i] == ref.scores[j]
