@@ -11,7 +11,7 @@ REFDIR = os.path.join(ROOT, "oracle", "_ref")
 IMAGE = os.path.join(REFDIR, "models", "knlm_small.img")
 manifest = {"image_md5": hashlib.md5(open(IMAGE, "rb").read()).hexdigest(), "model": "knlm_small (fabricated, see oracle/Makefile)",
             "reference_arch": "avx2", "files": {}}
-for name in ["inputs_ref_tests", "inputs_web", "inputs_written"]:
+for name in ["inputs_ref_tests", "inputs_web", "inputs_written", "inputs_dialect_typos"]:
     src = os.path.join(HERE, name + ".txt")
     tmp = os.path.join("/tmp", name + ".golden.txt")
     env = dict(os.environ, KIWI_ARCH_TYPE="avx2")

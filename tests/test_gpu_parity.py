@@ -18,7 +18,7 @@ def _close(a, b):
     return abs(a - b) <= RTOL * max(1.0, abs(b))
 
 
-@pytest.mark.parametrize("name", ["inputs_ref_tests", "inputs_web", "inputs_written"])
+@pytest.mark.parametrize("name", ["inputs_ref_tests", "inputs_web", "inputs_written", "inputs_dialect_typos"])
 def test_tokens_and_scores_match_reference_golden(kiwi, name):
     texts = read_inputs(name); gold = read_golden(name)
     res = kiwi.analyze_batch(texts)
