@@ -8,6 +8,7 @@
  *   forms                          ... include/kiwi/Form.h:231-257
  *   morphemes / chunks             ... include/kiwi/Form.h:142-198
  *   Knlm arrays                    ... src/Knlm.hpp:28-36, include/kiwi/Knlm.h:17-24
+ *   CoNg arrays (model_type cong)  ... src/CoNgramModel.hpp:47-65,89-105, include/kiwi/CoNgramModel.h:18-43
  *   config / tag scorer / specials ... include/kiwi/Kiwi.h:150-167,187,222, include/kiwi/TagUtils.h:8-20
  */
 #ifndef KIWI_B200_IMAGE_H
@@ -19,7 +20,7 @@ extern "C" {
 #endif
 
 #define KB2_IMAGE_MAGIC   0x31474D4932424Bull /* "KB2IMG1" */
-#define KB2_IMAGE_VERSION 4u
+#define KB2_IMAGE_VERSION 5u
 #define KB2_POSTAG_MAX    64                  /* >= (int)POSTag::max of the reference (Types.h:195-227) */
 
 /* section ids */
@@ -38,6 +39,15 @@ enum kb2_section_id {
 	KB2_SEC_KN_ROOT,          /* int32_t[htx_vocab]  root direct table            */
 	KB2_SEC_KN_HTX,           /* uint32_t[vocab] history transform (may be empty) */
 	KB2_SEC_CHR_RUNS,         /* kb2_chr_run[]  code-point attribute runs over 0..0x10FFFF, ascending */
+	/* CoNg language model (empty for Knlm images) */
+	KB2_SEC_CG_NODES,         /* kb2_cg_node[]  non-leaf nodes of the context trie                 */
+	KB2_SEC_CG_KEYS,          /* uint32_t[]  ascending inside each node (VL keys, see cg_key_size) */
+	KB2_SEC_CG_VALUES,        /* int32_t[]   >0 child diff, <0 leaf: -contextIdx                   */
+	KB2_SEC_CG_ROOT,          /* int32_t[cg_root_size]  root direct table (allRootValueData)       */
+	KB2_SEC_CG_CTX_EMB,       /* rows: uint8[dim] (= s8 + 128), float scale, float bias            */
+	KB2_SEC_CG_OUT_EMB,       /* rows: int8[dim], float scale, int32 hsum (= 128 * sum)            */
+	KB2_SEC_CG_INV_VOCAB,     /* uint32_t[vocab] invertedContextVocab (may be empty)               */
+	KB2_SEC_CG_OUT_BIAS,      /* float[vocab] outputEmbBias (may be empty)                         */
 	KB2_SEC_COUNT
 };
 
@@ -100,6 +110,10 @@ typedef struct kb2_kn_node {
 	float    ll, gamma;
 } kb2_kn_node;              /* 20 B, include/kiwi/Knlm.h:17-24 */
 
+/* CoNg context-trie node after load (src/CoNgramModel.cpp:484-575): `value` = contextIdx of the node,
+ * `lower` = relative index of the longest proper suffix node. */
+typedef struct kb2_cg_node { int32_t lower; uint32_t value; uint32_t next_offset; uint32_t num_nexts; } kb2_cg_node;
+
 /* One run of consecutive code points sharing all attributes.  Extracted by calling the reference's pure
  * per-code-point functions over the whole code space: identifySpecialChr (src/Utils.cpp:76-190),
  * chr2ScriptType (src/ScriptType.cpp:5-560), isSpace (include/kiwi/Utils.h:295-326),
@@ -119,7 +133,7 @@ typedef struct kb2_config {   /* KiwiConfig defaults, include/kiwi/Kiwi.h:150-16
 typedef struct kb2_header {
 	uint64_t magic;
 	uint32_t version;
-	uint32_t model_type;          /* 2 = knlm (Types.h ModelType)                   */
+	uint32_t model_type;          /* (int)ModelType of Types.h:307: knlm or cong     */
 	uint64_t total_bytes;
 	kb2_section sec[KB2_SEC_COUNT];
 	uint32_t n_trie_nodes, n_trie_edges, n_forms, n_morphs, n_chunks;
@@ -136,6 +150,11 @@ typedef struct kb2_header {
 	uint32_t n_chr_runs;
 	uint32_t script_latin, script_variation_selectors;   /* ScriptType enum values (include/kiwi/ScriptType.h) */
 	char     model_name[64];
+	/* CoNg scalars (include/kiwi/CoNgramModel.h:18-33); all 0 for Knlm images */
+	uint32_t cg_num_nodes, cg_num_edges, cg_root_size, cg_dim, cg_context_size;
+	uint32_t cg_key_size;         /* 2: 16-bit keys, 3: 16-bit keys with surrogate pairs for ids >= tMax, 4: 32-bit keys */
+	uint32_t cg_flags;            /* CoNgramModelHeader::flags */
+	uint32_t cg_pad;
 } kb2_header;
 
 #ifdef __cplusplus

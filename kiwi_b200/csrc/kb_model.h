@@ -147,6 +147,20 @@ namespace kb
 		const uint4* kn_hash; uint32_t kn_hash_mask;
 		const float2* kn_backoff;      // [node] {lower as int bits, gamma}
 		const float* kn_root_ll;       // [htx_vocab] ll of the root's child for token t (valid when kn_root[t] > 0)
+		// CoNg (model_type cong; all null / 0 for Knlm images).  Context trie re-laid out like the Knlm one: one
+		// open-addressing table over all non-root edges, entry = {node, key, value, contextIdx of the child node};
+		// per-node {lower, value}; root children via the direct table.  Embedding rows stay in the image layout
+		// (src/CoNgramModel.hpp:89-105): context row = u8[dim] (s8 + 128), float scale, float bias;
+		// output row = s8[dim], float scale, int32 hsum.
+		const uint4* cg_hash; uint32_t cg_hash_mask;
+		const int2* cg_nodes;          // [node] {lower, value (= contextIdx)}
+		const int32_t* cg_root;        // [cg_root_size]
+		const uint8_t* cg_ctx_emb;
+		const uint8_t* cg_out_emb;
+		const uint32_t* cg_inv_vocab;  // nullptr when absent
+		const float* cg_out_bias;      // nullptr when absent
+		uint32_t cg_dim, cg_stride, cg_key_size, cg_root_size, cg_context_size;
+		uint32_t model_type;           // (int)ModelType: 2 knlm, 4 cong
 		// scalars
 		uint32_t n_chr_runs, n_morphs, n_forms, n_trie_nodes;
 		uint32_t default_tag_size, lang_vocab_size;
@@ -223,6 +237,15 @@ namespace kb
 			return polar == CP_negative;
 		}
 		return polar == CP_negative;
+	}
+	// float epilogues of the CoNg int8 scorer (see oracle/restate/cong.hpp for the reference kernels each one restates)
+	enum : uint32_t { CG_E_SCALAR = 0, CG_E_SMALL = 1, CG_E_GEMV = 2 };
+	KB_HD uint32_t cgEpilogueOf(uint32_t m, uint32_t n)      // m, n = unique contexts / outputs, saturated at 4 (qgemm.hpp:157-201)
+	{
+		if (m <= 3 && n <= 3) return CG_E_SMALL;
+		if (n == 1) return CG_E_GEMV;
+		if (m >= 4 && n == 2) return CG_E_GEMV;
+		return CG_E_SMALL;
 	}
 	KB_HD uint32_t knHashFn(uint32_t node, uint32_t token) { uint32_t x = node * 0x9E3779B1u ^ token * 0x85EBCA6Bu; x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 13; return x; }
 	KB_HD uint8_t hashSbTypeOrder(uint8_t type, uint8_t order) { return ((type << 1) ^ (type >> 7) ^ order) % 63 + 1; }   // PathEvaluator.hpp:83-86

@@ -88,7 +88,9 @@ namespace kb
 		if (h->magic != KB2_IMAGE_MAGIC) throw std::runtime_error("not a kiwi_b200 model image (bad magic)");
 		if (h->version != KB2_IMAGE_VERSION) throw std::runtime_error("model image version mismatch: rebuild the image with this build's flatten tool");
 		if (h->total_bytes != size) throw std::runtime_error("model image is truncated");
-		if (h->model_type != 2) throw std::runtime_error("only Knlm images are supported by this build");
+		if (h->model_type != 2 && h->model_type != 4) throw std::runtime_error("only Knlm and CoNg (quantized, no window) images are supported by this build");
+		const bool cong = h->model_type == 4;
+		if (cong && (h->cg_dim == 0 || h->cg_dim % 32 != 0 || h->cg_dim > 1024)) throw std::runtime_error("CoNg image: dim must be a multiple of 32 (tensor-core tile depth)");
 		header = *h;
 		auto sec = [&](int id) { return blob.data() + h->sec[id].offset; };
 		const kb2_trie_node* trieNodes = reinterpret_cast<const kb2_trie_node*>(sec(KB2_SEC_TRIE_NODES));
@@ -244,6 +246,34 @@ namespace kb
 		std::vector<float> knRootLl(h->kn_htx_vocab, 0.f);
 		for (uint32_t tkn = 0; tkn < h->kn_htx_vocab; ++tkn) if (knRoot[tkn] > 0 && (uint32_t)knRoot[tkn] < h->kn_num_nodes) knRootLl[tkn] = knNodes[knRoot[tkn]].ll;
 
+		// ---- CoNg context trie, one-probe layout (same idea as the Knlm table above)
+		std::vector<uint4> cgHash; std::vector<int2> cgNodes;
+		uint32_t cgHashSize = 0;
+		if (cong)
+		{
+			const kb2_cg_node* cn = reinterpret_cast<const kb2_cg_node*>(sec(KB2_SEC_CG_NODES));
+			const uint32_t* ck = reinterpret_cast<const uint32_t*>(sec(KB2_SEC_CG_KEYS));
+			const int32_t* cv = reinterpret_cast<const int32_t*>(sec(KB2_SEC_CG_VALUES));
+			cgHashSize = 1024;
+			while (cgHashSize < 2 * (size_t)h->cg_num_edges + 16) cgHashSize <<= 1;
+			cgHash.assign(cgHashSize, make_uint4(0xFFFFFFFFu, 0, 0, 0));
+			cgNodes.resize(h->cg_num_nodes);
+			for (uint32_t i = 0; i < h->cg_num_nodes; ++i)
+			{
+				cgNodes[i] = make_int2(cn[i].lower, (int32_t)cn[i].value);
+				if (i == 0) continue;
+				for (uint32_t j = 0; j < cn[i].num_nexts; ++j)
+				{
+					const uint32_t key = ck[cn[i].next_offset + j];
+					const int32_t v = cv[cn[i].next_offset + j];
+					const uint32_t childCtx = v > 0 ? cn[i + v].value : 0;
+					uint32_t hh = knHashFn(i, key) & (cgHashSize - 1);
+					while (cgHash[hh].x != 0xFFFFFFFFu) hh = (hh + 1) & (cgHashSize - 1);
+					cgHash[hh] = make_uint4(i, key, (uint32_t)v, childCtx);
+				}
+			}
+		}
+
 		// ---- upload
 		void* dBlob = nullptr;
 		cudaCheck(cudaMalloc(&dBlob, size), "cudaMalloc(image)");
@@ -274,6 +304,18 @@ namespace kb
 		d.forms = upload(dforms, owned);
 		d.chr_bmp = upload(bmp, owned);
 		d.trie_root_next = upload(rootNext, owned);
+		d.model_type = h->model_type;
+		if (cong)
+		{
+			d.cg_hash = upload(cgHash, owned); d.cg_hash_mask = cgHashSize - 1;
+			d.cg_nodes = upload(cgNodes, owned);
+			d.cg_root = reinterpret_cast<const int32_t*>(dsec(KB2_SEC_CG_ROOT));
+			d.cg_ctx_emb = reinterpret_cast<const uint8_t*>(dsec(KB2_SEC_CG_CTX_EMB));
+			d.cg_out_emb = reinterpret_cast<const uint8_t*>(dsec(KB2_SEC_CG_OUT_EMB));
+			d.cg_inv_vocab = h->sec[KB2_SEC_CG_INV_VOCAB].nbytes ? reinterpret_cast<const uint32_t*>(dsec(KB2_SEC_CG_INV_VOCAB)) : nullptr;
+			d.cg_out_bias = h->sec[KB2_SEC_CG_OUT_BIAS].nbytes ? reinterpret_cast<const float*>(dsec(KB2_SEC_CG_OUT_BIAS)) : nullptr;
+			d.cg_dim = h->cg_dim; d.cg_stride = h->cg_dim + 8; d.cg_key_size = h->cg_key_size; d.cg_root_size = h->cg_root_size; d.cg_context_size = h->cg_context_size;
+		}
 		d.n_chr_runs = h->n_chr_runs; d.n_morphs = h->n_morphs; d.n_forms = h->n_forms; d.n_trie_nodes = h->n_trie_nodes;
 		d.default_tag_size = h->default_tag_size; d.lang_vocab_size = h->lang_vocab_size;
 		d.script_latin = h->script_latin; d.script_variation_selectors = h->script_variation_selectors;

@@ -26,7 +26,31 @@
 #include "kb_model.h"
 #include "kb_batch.h"
 
+// This file is compiled twice (csrc/Makefile): KB_CONG=0 -> viterbi_kernel for Knlm images (the code described above),
+// KB_CONG=1 -> viterbi_cong_kernel for quantized CoNg images.  The CoNg build replaces, behind `#if KB_CONG`:
+//   * the LM step: int8 dot product of a context row and an output row with the reference's float epilogues +
+//     one context-trie transition (src/CoNgramModel.cpp:869-903, src/CoNgramModel.hpp:271-385);
+//   * the per-node evaluation order of the "transposed" evaluator (PathEvaluator.hpp:860-1035,
+//     MorphemeEvaluator<CoNgramState>::eval src/CoNgramModel.cpp:17-317): shortcuts first, then regular, left-half and
+//     right-half candidates, every candidate through the per-candidate path `evalCand`;
+//   * progressMatrix (src/CoNgramModel.cpp:1494-1611): the (unique context x candidate) int8 products of a node are
+//     computed as warp-level tensor-core tiles (mma.sync m16n8k32 u8 x s8 -> s32) into shared memory, `congGroupDots`.
+// A CoNg path keeps CoNgramState::contextIdx in the DPath::wid_feat slot (the feature word is re-read from morphs[wid]).
+#ifndef KB_CONG
+#define KB_CONG 0
+#endif
+#if KB_CONG
+#define KB_VIT_NS vit_cong
+#define P_WID_FEAT(p) (c_m.morphs[(p).wid].feat)
+#define P_CTX(p) ((p).wid_feat)
+#else
+#define KB_VIT_NS vit_knlm
+#define P_WID_FEAT(p) ((p).wid_feat)
+#endif
+
 namespace kb
+{
+namespace KB_VIT_NS
 {
 	// the model view lives in constant memory: every `c_m.field` is an immediate-offset constant-bank load
 	__constant__ DevModel c_m;
@@ -65,6 +89,13 @@ namespace kb
 		CandMask cmask[GROUP];                  // per candidate: which path classes survive the filter / fail the soft condition / override firstWid
 		uint32_t candNew[GROUP];                // entries created per candidate of the current group
 		uint32_t fwTab[FWTAB_CAP];              // first-wid overrides of socket chunks (PathEvaluator.hpp:590), index 0 unused
+#if KB_CONG
+		int32_t dots[64][33];                   // (unique context, candidate of the group) -> sum u8*s8 - hsum, from the tensor-core tiles
+		uint32_t uctx[64];                      // the node's unique context ids (regular incoming paths)
+		uint8_t pslot[STAGE_CAP];               // incoming path -> index into uctx, 0xFF = none (socket path / more than 64 contexts)
+		uint32_t colWid[GROUP];                 // first wid of every candidate of the group
+		uint32_t candOrder[256];                // the node's candidates in the transposed evaluator's order
+#endif
 	};
 #ifndef KB_VIT_WARPS
 #define KB_VIT_WARPS 4
@@ -174,6 +205,120 @@ namespace kb
 			return acc + asFloat(v);
 		}
 	}
+
+
+#if KB_CONG
+	// ---- CoNg language model ----------------------------------------------------------------------------
+	static constexpr uint32_t CG_UCAP = 64;          // unique contexts of a node held in the tensor-core tile (else per-pair dp4a)
+
+	__device__ __forceinline__ bool cgLookup(uint32_t node, uint32_t key, int32_t& v, uint32_t& childCtx)
+	{
+		uint32_t h = knHashFn(node, key) & c_m.cg_hash_mask;
+		while (true)
+		{
+			const uint4 e = c_m.cg_hash[h];
+			if (e.x == node && e.y == key) { v = (int32_t)e.z; childCtx = e.w; return true; }
+			if (e.x == 0xFFFFFFFFu) return false;
+			h = (h + 1) & c_m.cg_hash_mask;
+		}
+	}
+	// progressContextNodeVl, src/CoNgramModel.hpp:314-385 (one lane)
+	__device__ __noinline__ uint32_t cgStepVl(int32_t& nodeIdx, uint32_t next)
+	{
+		if ((uint32_t)nodeIdx >= 0x10000000u)
+		{
+			if (atomicCAS(&c_m.debug[0], 0u, 1u) == 0u) { c_m.debug[1] = 77; c_m.debug[2] = next; c_m.debug[3] = (uint32_t)nodeIdx; c_m.debug[4] = blockIdx.x; c_m.debug[5] = threadIdx.x; }
+			nodeIdx = 0; return 0;
+		}
+		while (true)
+		{
+			int32_t v; uint32_t cctx = 0;
+			if (nodeIdx != 0)
+			{
+				if (!cgLookup((uint32_t)nodeIdx, next, v, cctx))
+				{
+					const int32_t lower = c_m.cg_nodes[nodeIdx].x;
+					if (!lower) return 0;
+					nodeIdx += lower;
+					continue;
+				}
+			}
+			else
+			{
+				v = next < c_m.cg_root_size ? c_m.cg_root[next] : 0;
+				if (v == 0) return 0;
+				if (v > 0) cctx = (uint32_t)c_m.cg_nodes[v].y;
+			}
+			if (v > 0) { nodeIdx += v; return cctx; }
+			// leaf: next node = deepest suffix node that continues with `next`
+			int32_t cur = nodeIdx;
+			while (true)
+			{
+				const int32_t lower = c_m.cg_nodes[cur].x;
+				if (!lower) break;
+				cur += lower;
+				int32_t lv; uint32_t dummy;
+				bool found;
+				if (cur != 0) found = cgLookup((uint32_t)cur, next, lv, dummy);
+				else { lv = next < c_m.cg_root_size ? c_m.cg_root[next] : 0; found = lv != 0; }
+				if (found && lv > 0) { nodeIdx = cur + lv; return (uint32_t)-v; }
+			}
+			nodeIdx = 0;
+			return (uint32_t)-v;
+		}
+	}
+	// progressContextNode, src/CoNgramModel.hpp:271-297
+	__device__ __forceinline__ uint32_t cgStep(int32_t& nodeIdx, uint32_t next)
+	{
+		if (c_m.cg_inv_vocab) next = c_m.cg_inv_vocab[next];
+		if (c_m.cg_key_size != 3) return cgStepVl(nodeIdx, next);
+		const uint32_t tMax = (1u << 16) - (1u << 10) * 2;
+		if (next < tMax) return cgStepVl(nodeIdx, next);
+		next -= tMax;
+		cgStepVl(nodeIdx, tMax + (next >> 10));
+		return cgStepVl(nodeIdx, tMax + (1u << 10) + (next & 0x3FF));
+	}
+	// sum_k ctx_u8[k] * out_s8[k] - hsum  ==  sum_k (ctx_u8[k] - 128) * out_s8[k]   (hsum = 128 * sum out, CoNgramModel.cpp:672)
+	__device__ __noinline__ int32_t cgDot(uint32_t ctx, uint32_t wid)
+	{
+		const uint4* a = reinterpret_cast<const uint4*>(c_m.cg_ctx_emb + (size_t)ctx * c_m.cg_stride);
+		const uint4* b = reinterpret_cast<const uint4*>(c_m.cg_out_emb + (size_t)wid * c_m.cg_stride);
+		// rows are 8-byte aligned (stride = dim + 8): read 8 bytes at a time
+		const uint2* a2 = reinterpret_cast<const uint2*>(a); const uint2* b2 = reinterpret_cast<const uint2*>(b);
+		int32_t acc = 0;
+		const uint32_t n8 = c_m.cg_dim >> 3;
+		#pragma unroll 4
+		for (uint32_t k = 0; k < n8; ++k)
+		{
+			const uint2 x = a2[k], y = b2[k];
+			acc = __dp4a((int)(x.x ^ 0x80808080u), (int)y.x, acc);
+			acc = __dp4a((int)(x.y ^ 0x80808080u), (int)y.y, acc);
+		}
+		return acc;
+	}
+	// the three float epilogues of the reference's kernels (kb_model.h CG_E_*, oracle/restate/cong.hpp)
+	__device__ __forceinline__ float cgFinish(int32_t x, uint32_t ctx, uint32_t wid, uint32_t ep)
+	{
+		const float2 cs = *reinterpret_cast<const float2*>(c_m.cg_ctx_emb + (size_t)ctx * c_m.cg_stride + c_m.cg_dim);   // {scale, bias}
+		const float os = *reinterpret_cast<const float*>(c_m.cg_out_emb + (size_t)wid * c_m.cg_stride + c_m.cg_dim);
+		const float xf = __int2float_rn(x);
+		if (ep == CG_E_SCALAR)
+		{
+			float ll = __fadd_rn(__fmul_rn(__fmul_rn(xf, cs.x), os), cs.y);
+			if (c_m.cg_out_bias) ll = __fadd_rn(ll, c_m.cg_out_bias[wid]);
+			return ll;
+		}
+		if (ep == CG_E_SMALL) return __fmaf_rn(__fmul_rn(xf, cs.x), os, cs.y);
+		return __fmaf_rn(__fmul_rn(xf, os), cs.x, cs.y);
+	}
+	// CoNgramState::next (scalar path)
+	__device__ __forceinline__ float cgNext(int32_t& node, uint32_t& ctx, uint32_t wid)
+	{
+		const float ll = cgFinish(cgDot(ctx, wid), ctx, wid, CG_E_SCALAR);
+		ctx = cgStep(node, wid);
+		return ll;
+	}
+#endif
 
 	// ------------------------------------------------------------------------------------------------
 	struct PathRes { float score; uint32_t endParent; uint8_t prevState, curState; };
@@ -288,6 +433,10 @@ namespace kb
 			uint32_t ownOff, ownLen;
 			uint16_t leftLast; uint8_t leftPol; uint8_t morphTag; uint32_t widFeat; uint8_t pathSocket;
 			bool spaceBefore;
+#if KB_CONG
+			uint32_t epFirst;        // epilogue of the first-wid score of a regular candidate (shape of the node's gather GEMM), CG_E_*
+			int32_t dotCol;          // column of this candidate in sm->dots, -1 = not computed
+#endif
 		};
 
 		__device__ __noinline__ void evalCand(uint32_t nodeIdx, const DNode& node, const CandCtx& cc, uint32_t inBeg, uint32_t inEnd, uint32_t mode)
@@ -335,6 +484,14 @@ namespace kb
 						}
 					}
 				}
+#if KB_CONG
+				// right halves only see combining paths, and their first wid is local to the pair (CoNgramModel.cpp:248-286)
+				if (valid && cc.cur.combine_socket && !cc.single && !pp.combine_socket) valid = false;
+				const uint32_t firstWid = setsFW ? fwVal : cc.firstWid0;
+				(void)fwCarry;
+				const bool regular = cc.cur.combine_socket == 0;
+				float ignAdd = 0.f; bool ignLate = false;
+#else
 				// the reference mutates `firstWid` in place (PathEvaluator.hpp:590): later pairs inherit it
 				uint32_t firstWid;
 				{
@@ -345,6 +502,7 @@ namespace kb
 					firstWid = le ? got : fwCarry;
 					if (smask) fwCarry = __shfl_sync(FULL, fwVal, 31 - __clz(smask));
 				}
+#endif
 				if (valid)
 				{
 					// FormEvaluator, PathEvaluator.hpp:253-311
@@ -358,11 +516,55 @@ namespace kb
 						{
 							ok = empty ? true : ((pp.left_pol & (cp == CP_positive ? LP_POLAR_POS : LP_POLAR_NEG)) != 0);
 						}
+#if KB_CONG
+						// regular candidates: `score = acc + morphScore + lm` comes first, FormEvaluator adds afterwards (CoNgramModel.cpp:175-179)
+						if (cc.ignoreCondScore != 0.f) { if (regular) { ignAdd = ok ? 0.f : cc.ignoreCondScore; ignLate = true; } else candScore += ok ? 0.f : cc.ignoreCondScore; }
+						else if (!ok) valid = false;
+#else
 						if (cc.ignoreCondScore != 0.f) candScore += ok ? 0.f : cc.ignoreCondScore;
 						else if (!ok) valid = false;
+#endif
 					}
 				}
 				int32_t lmState = 0;
+#if KB_CONG
+				uint32_t ctxIdx = 0;
+				if (valid)
+				{
+					lmState = pp.lm_state; ctxIdx = P_CTX(pp);
+					if (cc.cur.combine_socket && cc.single) {}
+					else
+					{
+						if ((c_m.morphs[firstWid].feat & MF_TAG_MASK) == T_p) valid = false;
+						else
+						{
+							float ll;
+							if (regular)
+							{
+								// progressMatrix entry: tensor-core tile when this path's context is in the node's tile, else a dp4a dot
+								const uint32_t ps = q < STAGE_CAP ? sm->pslot[q] : 0xFFu;
+								const int32_t x = (cc.dotCol >= 0 && ps != 0xFFu) ? sm->dots[ps][cc.dotCol] : cgDot(ctxIdx, firstWid);
+								ll = cgFinish(x, ctxIdx, firstWid, cc.epFirst);
+								ctxIdx = cgStep(lmState, firstWid);
+							}
+							else ll = cgNext(lmState, ctxIdx, firstWid);
+							candScore += ll;
+							firstChunkScore += ll;
+							if (ignLate) candScore += ignAdd;
+							if (!cc.single)
+							{
+								for (uint32_t i = 1; i < cc.cur.chunk_cnt; ++i)
+								{
+									const uint32_t wid = c_m.morphs[c_m.chunks[cc.cur.chunk_off + i].morph].lm_id;
+									if ((c_m.morphs[wid].feat & MF_TAG_MASK) == T_p) { valid = false; break; }
+									ll = cgNext(lmState, ctxIdx, wid);
+									candScore += ll;
+								}
+							}
+						}
+					}
+				}
+#else
 				if (valid)
 				{
 					lmState = pp.lm_state;
@@ -388,6 +590,7 @@ namespace kb
 						}
 					}
 				}
+#endif
 				// insertToPathContainer, PathEvaluator.hpp:193-251
 				uint8_t spState = 0, rootId = COMMON_ROOT;
 				float accScore = 0, fcs = 0;
@@ -400,7 +603,7 @@ namespace kb
 						rootId = doFork ? (uint8_t)rr : COMMON_ROOT;
 						spState = doFork ? uniq[rr] : pp.sp_state;
 						// RuleBasedScorer::operator(), PathEvaluator.hpp:115-183
-						const uint32_t pf = pp.wid_feat;
+						const uint32_t pf = P_WID_FEAT(pp);
 						const uint32_t ptag = pf & MF_TAG_MASK;
 						float rs = 0;
 						if ((cc.cur.feat & MF_VOWEL_E) && isIrregular((uint8_t)ptag)) rs -= 10;
@@ -446,7 +649,12 @@ namespace kb
 				const bool isLeader = valid && lane == leader;
 				// lookup among the entries of earlier rounds
 				uint32_t found = NPOS;
+#if KB_CONG
+				// Hash<CoNgramState> = Hash<uint32_t>(node) = node * (2^61 - 1) ^ rol(node, 33): its bits 5-6 are those of -node (CoNgramModel.hpp:505-541)
+				const uint32_t bucket = mode == 1 ? ((spState ^ ((0u - (uint32_t)lmState) >> 5)) & 3) : 0;
+#else
 				const uint32_t bucket = mode == 1 ? ((spState ^ ((uint32_t)lmState >> 5)) & 3) : 0;
+#endif
 				if (isLeader && E)
 				{
 					uint32_t slot = htHash(lmState, prevRoot, spState);
@@ -533,7 +741,12 @@ namespace kb
 							np.own_len = cc.single ? (uint16_t)cc.ownLen : 0; np.node = (uint16_t)nodeIdx; np.left_last = cc.leftLast; np.left_pol = cc.leftPol;
 							np.sp_state = spState;
 							np.root_id = rootId != COMMON_ROOT ? rootId : pp.root_id;
-							np.combine_socket = cc.pathSocket; np.prev_root_id = (uint8_t)prevRoot; np.morph_tag = cc.morphTag; np.wid_feat = cc.widFeat;
+							np.combine_socket = cc.pathSocket; np.prev_root_id = (uint8_t)prevRoot; np.morph_tag = cc.morphTag;
+#if KB_CONG
+							P_CTX(np) = ctxIdx;
+#else
+							np.wid_feat = cc.widFeat;
+#endif
 							pool[candBeg + tgt] = np;
 						}
 					}
@@ -550,7 +763,11 @@ namespace kb
 				{
 					const uint32_t e = eb + lane;
 					DPath p; uint32_t b = 0xFF;
+#if KB_CONG
+					if (e < E) { p = pool[candBeg + e]; b = (p.sp_state ^ ((0u - (uint32_t)p.lm_state) >> 5)) & 3; }
+#else
 					if (e < E) { p = pool[candBeg + e]; b = (p.sp_state ^ ((uint32_t)p.lm_state >> 5)) & 3; }
+#endif
 #pragma unroll
 					for (uint32_t k = 0; k < 4; ++k)
 					{
@@ -861,9 +1078,185 @@ namespace kb
 			top = w;
 		}
 
+
+#if KB_CONG
+		// ---- transposed evaluator, node-level preparation ------------------------------------------------------
+		struct CongNode { uint32_t nOrdered, epFirst, nU; bool tileOK; };
+
+		// (a) the node's unique context ids among the regular (non-socket) incoming paths -> sm->uctx / sm->pslot, and
+		//     (b) the candidates in evaluation order -> sm->candOrder: z_coda shortcut, z_siot shortcut, regular, left halves,
+		//     right halves (PathEvaluator.hpp:883-963, CoNgramModel.cpp:76-121); dropped candidates are left out.
+		//     The shape (unique contexts m, unique first wids n) of the node's gather GEMM selects the float epilogue.
+		__device__ __noinline__ CongNode congPrepare(const DNode& node, bool spaceBefore, const uint32_t* candList, uint32_t nCandsIn,
+			uint32_t unk0, uint32_t unk1, uint32_t inBeg, uint32_t P)
+		{
+			CongNode cn; cn.nOrdered = 0; cn.epFirst = CG_E_SMALL; cn.nU = 0; cn.tileOK = true;
+			// ---- (a)
+			uint32_t nU = 0, nUtrue = 0, Preg = 0;
+			#pragma unroll 1
+			for (uint32_t qb = 0; qb < P; qb += 32)
+			{
+				const uint32_t q = qb + lane;
+				bool reg = false; uint32_t ctx = 0;
+				if (q < P) { const DPath* pth = pool + inBeg + q; reg = pth->combine_socket == 0; ctx = P_CTX(*pth); }
+				unsigned rem = __ballot_sync(FULL, reg);
+				Preg += __popc(rem);
+				uint32_t mySlot = 0xFFu;
+				while (rem)
+				{
+					const int src = __ffs(rem) - 1;
+					const uint32_t v = __shfl_sync(FULL, ctx, src);
+					uint32_t slot = 0xFFu;
+					for (uint32_t base = 0; base < nU; base += 32)
+					{
+						const unsigned hit = __ballot_sync(FULL, base + lane < nU && sm->uctx[base + lane] == v);
+						if (hit) { slot = base + __ffs(hit) - 1; break; }
+					}
+					if (slot == 0xFFu)
+					{
+						// not in the tile list: either new, or (list full) an overflow context that is scored per pair
+						if (nU < CG_UCAP) { slot = nU; if (lane == 0) sm->uctx[nU] = v; ++nU; ++nUtrue; __syncwarp(); }
+						else { cn.tileOK = cn.tileOK; ++nUtrue; }      // nUtrue only needs to be exact up to 4
+					}
+					const unsigned same = __ballot_sync(FULL, reg && ctx == v);
+					if (reg && ctx == v) mySlot = slot;
+					rem &= ~same;
+				}
+				if (q < P && q < STAGE_CAP) sm->pslot[q] = (uint8_t)mySlot;
+			}
+			cn.nU = nU;
+			// ---- (b)
+			if (nCandsIn > 256) { err = ST_INTERNAL; return cn; }
+			uint32_t W = 0, nDistinct = 0, known[4] = { 0, 0, 0, 0 };
+			int32_t lastCoda = -1, lastSiot = -1;
+			#pragma unroll 1
+			for (uint32_t cb = 0; cb < nCandsIn; cb += 32)
+			{
+				const uint32_t ci = cb + lane;
+				uint32_t key = 7, fw = 0;
+				if (ci < nCandsIn)
+				{
+					const int32_t curId = (int32_t)(candList ? candList[ci] : (ci == 0 ? unk0 : unk1));
+					const DMorph cur = c_m.morphs[curId];
+					const uint32_t tag = cur.feat & MF_TAG_MASK;
+					const bool single = (cur.feat & MF_SINGLE) != 0;
+					bool drop = cur.nonstd_dialect != 0;
+					if (!drop && splitComplex)
+					{
+						if (c_m.morphs[curId + cur.combined].misc & MM_COMPLEX) drop = true;
+						for (uint32_t c = 0; c < cur.chunk_cnt && !drop; ++c) if (c_m.morphs[c_m.chunks[cur.chunk_off + c].morph].misc & MM_COMPLEX) drop = true;
+					}
+					if (drop) key = 7;
+					else if (tag == T_z_coda) key = 0;
+					else if (tag == T_z_siot) key = 1;
+					else
+					{
+						if (!single && node.prev && spaceBefore && cur.form_idx >= 0 && c_m.forms[cur.form_idx].str_len == 1)
+						{
+							const uint32_t k0 = c_m.form_chars[c_m.forms_raw[cur.form_idx].str_off];
+							if (k0 == 0xB2E4 || k0 == 0xAC8C || k0 == 0xC9C0)
+							{
+								const DMorph c0 = c_m.morphs[c_m.chunks[cur.chunk_off].morph];
+								if (c0.form_idx >= 0 && c_m.forms[c0.form_idx].str_len == 1 && c_m.form_chars[c_m.forms_raw[c0.form_idx].str_off] == 0xD558) drop = true;
+							}
+						}
+						if (drop) key = 7;
+						else if (cur.combine_socket) key = single ? 3 : 4;
+						else
+						{
+							const DMorphX mx = c_m.morphx[curId];
+							if (mx.xflags & MX_FIRST_IS_P) key = 7;
+							else { key = 2; fw = mx.first_wid; }
+						}
+					}
+				}
+				sm->item[ci < ITEM_CAP ? ci : 0] = ci < nCandsIn ? key : 7u;      // nCandsIn <= 256 <= ITEM_CAP
+				const unsigned codaM = __ballot_sync(FULL, key == 0), siotM = __ballot_sync(FULL, key == 1);
+				if (codaM) lastCoda = (int32_t)(cb + 31 - __clz(codaM));
+				if (siotM) lastSiot = (int32_t)(cb + 31 - __clz(siotM));
+				unsigned rem = __ballot_sync(FULL, key == 2);
+				W += __popc(rem);
+				while (rem && nDistinct < 4)
+				{
+					const int src = __ffs(rem) - 1;
+					const uint32_t v = __shfl_sync(FULL, fw, src);
+					bool seen = false;
+					for (uint32_t z = 0; z < nDistinct; ++z) if (known[z] == v) seen = true;
+					if (!seen) known[nDistinct++] = v;
+					rem &= ~__ballot_sync(FULL, key == 2 && fw == v);
+				}
+			}
+			__syncwarp();
+			uint32_t nOut = 0;
+			#pragma unroll 1
+			for (uint32_t k = 0; k <= 4; ++k)
+			{
+				#pragma unroll 1
+				for (uint32_t cb = 0; cb < nCandsIn; cb += 32)
+				{
+					const uint32_t ci = cb + lane;
+					bool take = ci < nCandsIn && sm->item[ci] == k;
+					if (k == 0 && take && (int32_t)ci != lastCoda) take = false;       // `zCodaMorph = curMorph`: the last one wins
+					if (k == 1 && take && (int32_t)ci != lastSiot) take = false;
+					const unsigned tm = __ballot_sync(FULL, take);
+					if (take) sm->candOrder[nOut + __popc(tm & ((1u << lane) - 1))] = candList ? candList[ci] : (ci == 0 ? unk0 : unk1);
+					nOut += __popc(tm);
+				}
+			}
+			__syncwarp();
+			cn.nOrdered = nOut;
+			const uint32_t m4 = min(nUtrue, 4u), n4 = min(nDistinct, 4u);
+			cn.epFirst = (Preg == 1 && W == 1) ? (uint32_t)CG_E_SCALAR : cgEpilogueOf(m4, n4);
+			return cn;
+		}
+
+		// progressMatrix's gather GEMM for one group of <= 32 candidates (src/CoNgramModel.cpp:1575-1579, qgemm.hpp:36-87):
+		// dots[u][c] = sum_k ctx_u8[uctx[u]][k] * out_s8[colWid[c]][k] - hsum[colWid[c]] as warp-level tensor-core tiles,
+		// mma.sync.m16n8k32 (u8 x s8 -> s32); rows are gathered straight from the resident embedding tables (L2).
+		__device__ __noinline__ void congGroupDots(uint32_t nU, uint32_t colMask)
+		{
+			const uint32_t g = lane >> 2, t = lane & 3;
+			const uint32_t mTiles = (nU + 15) >> 4, kSteps = c_m.cg_dim >> 5, stride = c_m.cg_stride;
+			#pragma unroll 1
+			for (uint32_t nt = 0; nt < 4; ++nt)
+			{
+				if (!((colMask >> (nt * 8)) & 0xFFu)) continue;
+				const uint32_t col = nt * 8 + g;
+				const uint32_t wid = ((colMask >> col) & 1u) ? sm->colWid[col] : 0u;
+				const uint8_t* pb = c_m.cg_out_emb + (size_t)wid * stride;
+				// hsum of the two columns this lane's accumulators belong to (t * 2, t * 2 + 1)
+				const uint32_t c0col = nt * 8 + t * 2, c1col = c0col + 1;
+				const uint32_t w0 = ((colMask >> c0col) & 1u) ? sm->colWid[c0col] : 0u, w1 = ((colMask >> c1col) & 1u) ? sm->colWid[c1col] : 0u;
+				const int32_t h0 = *reinterpret_cast<const int32_t*>(c_m.cg_out_emb + (size_t)w0 * stride + c_m.cg_dim + 4);
+				const int32_t h1 = *reinterpret_cast<const int32_t*>(c_m.cg_out_emb + (size_t)w1 * stride + c_m.cg_dim + 4);
+				#pragma unroll 1
+				for (uint32_t mt = 0; mt < mTiles; ++mt)
+				{
+					const uint32_t r0 = mt * 16 + g, r1 = r0 + 8;
+					const uint8_t* pa0 = c_m.cg_ctx_emb + (size_t)sm->uctx[r0 < nU ? r0 : 0] * stride;
+					const uint8_t* pa1 = c_m.cg_ctx_emb + (size_t)sm->uctx[r1 < nU ? r1 : 0] * stride;
+					int32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+					#pragma unroll 2
+					for (uint32_t kk = 0; kk < kSteps; ++kk)
+					{
+						const uint32_t ko = kk * 32 + t * 4;
+						const uint32_t a0 = *reinterpret_cast<const uint32_t*>(pa0 + ko), a1 = *reinterpret_cast<const uint32_t*>(pa1 + ko);
+						const uint32_t a2 = *reinterpret_cast<const uint32_t*>(pa0 + ko + 16), a3 = *reinterpret_cast<const uint32_t*>(pa1 + ko + 16);
+						const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pb + ko), b1 = *reinterpret_cast<const uint32_t*>(pb + ko + 16);
+						asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+							: "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+					}
+					if (r0 < nU) { sm->dots[r0][c0col] = c0 - h0; sm->dots[r0][c1col] = c1 - h1; }
+					if (r1 < nU) { sm->dots[r1][c0col] = c2 - h0; sm->dots[r1][c1col] = c3 - h1; }
+				}
+			}
+			__syncwarp();
+		}
+#endif
+
 		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
 		// cands: either a form's candidate list (formCands != nullptr) or the default unknown candidates
-		__device__ __noinline__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const uint32_t* candList, uint32_t nCands, uint32_t unk0, uint32_t unk1,
+		__device__ __noinline__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const uint32_t* candList, uint32_t nCandsIn, uint32_t unk0, uint32_t unk1,
 			float unkFormDiscount, uint32_t ownOff, uint32_t ownLen, uint32_t inBeg, uint32_t inEnd)
 		{
 			const DNode node = nodes[nodeIdx];
@@ -876,7 +1269,15 @@ namespace kb
 			const uint32_t mode = P <= 128 ? 0 : (P <= 512 ? 1 : 2);
 			const bool spaceBefore = nodes[nodeIdx - node.prev].end_pos < node.start_pos;
 			const bool hasLB = hasLeftBoundary(nodeIdx);
+#if KB_CONG
+			const bool itemOK = false;           // every candidate goes through evalCand, in the transposed evaluator's order
+			const CongNode cgn = congPrepare(node, spaceBefore, candList, nCandsIn, unk0, unk1, inBeg, P);
+			if (err) return;
+			const uint32_t nCands = cgn.nOrdered;
+#else
 			const bool itemOK = mode <= 1;
+			const uint32_t nCands = nCandsIn;
+#endif
 			FlushCtx fc;
 			fc.nodeIdx = nodeIdx; fc.inBeg = inBeg; fc.nodeTypoCost = node.typo_cost; fc.ownOff = ownOff; fc.ownLen = ownLen; fc.ownLeftLast = 0; fc.ownLeftPol = 0;
 			if (itemOK) stagePaths(nodeIdx, inBeg, P);
@@ -903,7 +1304,11 @@ namespace kb
 						cs.chunkCnt = 0; cs.flags = 0; cs.pathSocket = 0; cs.senseId = 0;
 						if (lane < gcount)
 						{
+#if KB_CONG
+							const int32_t curId = (int32_t)sm->candOrder[gb + lane];
+#else
 							const int32_t curId = (int32_t)(candList ? candList[gb + lane] : (lane == 0 ? unk0 : unk1));
+#endif
 							const DMorph cur = c_m.morphs[curId];
 							const uint32_t tag = cur.feat & MF_TAG_MASK;
 							const bool single = (cur.feat & MF_SINGLE) != 0;
@@ -998,6 +1403,19 @@ namespace kb
 						myCls = cls; myValid = cm.valid; myCondFail = cm.condFail; mySets = cm.sets; myFlags = cs.flags;
 					}
 					__syncwarp();
+#if KB_CONG
+					// tensor-core tile for the regular candidates of this group
+					uint32_t dotMask = 0;
+					{
+						const CandS csl = sm->cand[lane];
+						const bool regular = lane < gcount && csl.cls == CLS_GENERAL && c_m.morphs[csl.curId].combine_socket == 0 && !(c_m.morphx[csl.curId].xflags & MX_FIRST_IS_P);
+						sm->colWid[lane] = csl.firstWid;
+						dotMask = __ballot_sync(FULL, regular);
+						__syncwarp();
+						if (dotMask && cgn.nU && cgn.epFirst != CG_E_SCALAR) congGroupDots(cgn.nU, dotMask);
+						else dotMask = 0;
+					}
+#endif
 					const uint32_t groupBase = top;
 					resetIndex();
 					nFw = 1;
@@ -1133,7 +1551,7 @@ namespace kb
 								if (q < P)
 								{
 									p = pool[inBeg + q];
-									const uint32_t lastTag = p.wid_feat & MF_TAG_MASK;
+									const uint32_t lastTag = P_WID_FEAT(p) & MF_TAG_MASK;
 									ok = tag == T_z_coda ? (isJClass((uint8_t)lastTag) || isEClass((uint8_t)lastTag)) : isNNClass((uint8_t)lastTag);
 								}
 								const unsigned om = __ballot_sync(FULL, ok);
@@ -1148,7 +1566,9 @@ namespace kb
 									np.wid = cur.lm_id;
 									np.node = (uint16_t)nodeIdx;
 									np.morph_tag = (uint8_t)(lmM.feat & MF_TAG_MASK);
+#if !KB_CONG
 									np.wid_feat = lmM.feat;
+#endif
 									uint16_t ll; uint8_t lp;
 									leftFeat(np.own_len ? np.own_off : 0, np.own_len, np.wid, np.morpheme, ll, lp);
 									if (lmM.combine_socket) lp |= LP_MORPH_SOCKET;
@@ -1182,6 +1602,10 @@ namespace kb
 							const bool own = single && ownLen;
 							cc.leftLast = own ? fc.ownLeftLast : csk.leftLast;
 							cc.leftPol = own ? (uint8_t)(fc.ownLeftPol | (csk.leftPol & LP_MORPH_SOCKET)) : csk.leftPol;
+#if KB_CONG
+							cc.epFirst = cgn.epFirst;
+							cc.dotCol = ((dotMask >> k) & 1u) ? (int32_t)k : -1;
+#endif
 							evalCand(nodeIdx, node, cc, inBeg, inEnd, mode);
 							if (err) return;
 						}
@@ -1294,10 +1718,20 @@ namespace kb
 			if (lane == 0)
 			{
 				DPath b;
-				b.lm_state = c_m.kn_bos_node; b.acc_score = 0; b.first_chunk_score = 0; b.wid = 0; b.morpheme = 0; b.parent = NPOS; b.own_off = 0; b.acc_typo_cost = 0;
+#if KB_CONG
+				b.lm_state = 0;            // CoNgramState(const ILangModel*): node 0, contextIdx 0 (CoNgramModel.hpp:479-485)
+#else
+				b.lm_state = c_m.kn_bos_node;
+#endif
+				b.acc_score = 0; b.first_chunk_score = 0; b.wid = 0; b.morpheme = 0; b.parent = NPOS; b.own_off = 0; b.acc_typo_cost = 0;
 				b.own_len = 0; b.node = 0; b.sp_state = 0; b.root_id = COMMON_ROOT; b.combine_socket = 0; b.prev_root_id = 0;
 				const DMorph m0 = c_m.morphs[0];
-				b.morph_tag = (uint8_t)(m0.feat & MF_TAG_MASK); b.wid_feat = m0.feat;
+				b.morph_tag = (uint8_t)(m0.feat & MF_TAG_MASK);
+#if KB_CONG
+				P_CTX(b) = 0;
+#else
+				b.wid_feat = m0.feat;
+#endif
 				uint16_t ll; uint8_t lp;
 				leftFeat(0, 0, 0, 0, ll, lp);
 				b.left_last = ll; b.left_pol = lp;
@@ -1382,7 +1816,12 @@ namespace kb
 						if (!openEnding)
 						{
 							int32_t st = p.lm_state;
+#if KB_CONG
+							uint32_t sctx = P_CTX(p);
+							c += cgNext(st, sctx, 1);
+#else
 							c += knProgress(st, 1, 5);
+#endif
 							if (p.sp_state & 1) c -= 2;
 							if (p.sp_state & 2) c -= 2;
 						}
@@ -1641,9 +2080,19 @@ namespace kb
 		}
 	}
 
-	cudaError_t set_model_viterbi(const DevModel& m) { return cudaMemcpyToSymbol(c_m, &m, sizeof(DevModel)); }
+}   // namespace KB_VIT_NS
+	using namespace KB_VIT_NS;
 
-	cudaError_t launch_viterbi(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
+#if KB_CONG
+#define KB_SET_MODEL set_model_viterbi_cong
+#define KB_LAUNCH launch_viterbi_cong
+#else
+#define KB_SET_MODEL set_model_viterbi
+#define KB_LAUNCH launch_viterbi
+#endif
+	cudaError_t KB_SET_MODEL(const DevModel& m) { return cudaMemcpyToSymbol(c_m, &m, sizeof(DevModel)); }
+
+	cudaError_t KB_LAUNCH(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
 		const uint32_t blocks = (bv.n_sent + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;

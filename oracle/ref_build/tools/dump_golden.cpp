@@ -12,6 +12,7 @@
 //   N <formIdx|-1> <uformOff|-1> <uformLen> <prev> <sibling> <startPos> <endPos> <spaceErrors> <typoCost>   x nNodes
 //   P <score> <prevState> <curState> <nTok>
 //   K <morphId> <begin> <end> <wordScore> <nodeId> <hasStr>                x nTok
+// The model type follows the environment variable KB_MODEL_TYPE (knlm, default, or cong).
 // usage: dump_golden <model_dir> <input.txt> <out.txt> [maxLines]
 #include <cstdio>
 #include <cstdlib>
@@ -31,7 +32,8 @@ int main(int argc, char** argv)
 	const size_t maxLines = argc > 4 ? std::stoul(argv[4]) : (size_t)-1;
 	try
 	{
-		KiwiBuilder kb{ argv[1], 1, BuildOption::default_, ModelType::knlm };
+		const char* mt = getenv("KB_MODEL_TYPE");
+		KiwiBuilder kb{ argv[1], 1, BuildOption::default_, (mt && std::string{ mt } == "cong") ? ModelType::cong : ModelType::knlm };
 		Kiwi kw = kb.build();
 		std::ifstream ifs{ argv[2] };
 		FILE* fo = std::fopen(argv[3], "w");

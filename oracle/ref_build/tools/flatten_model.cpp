@@ -6,7 +6,11 @@
 // "dumb": it copies raw fields only; every derived quantity is computed by the product at load time.
 // The Kiwi object is built with ArchType::balanced, whose nst::prepare keeps keys sorted ascending
 // (src/search.cpp:238-292), which is the order the device kernels binary-search.
-// usage: flatten_model <model_dir> <out.img> [model_name]
+// With model type "cong" the trie/forms/morphemes still come from the balanced-arch Kiwi, and the language model
+// from a second Kiwi built with ModelType::cong on ArchType::avx2 (the quantized CoNg model only exists for the
+// SIMD archs, src/ArchAvailable.h:50-66); its arch-specific key packets are read back through nst::extractKV
+// (src/search.h:94-110) and re-sorted ascending.
+// usage: flatten_model <model_dir> <out.img> [model_name] [knlm|cong]
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -16,6 +20,8 @@
 #include <kiwi/ScriptType.h>
 #include <kiwi/Utils.h>
 #include "Knlm.hpp"
+#include "CoNgramModel.hpp"
+#include <algorithm>
 #include "../../../include/kiwi_b200_image.h"
 
 using namespace kiwi;
@@ -66,6 +72,53 @@ static bool dumpKnlm(const lm::ILangModel* base, kb2_header& h,
 	return true;
 }
 
+struct CongDump
+{
+	std::vector<kb2_cg_node> nodes; std::vector<uint32_t> keys; std::vector<int32_t> values, root;
+	std::vector<uint8_t> ctxEmb, outEmb; std::vector<uint32_t> invVocab; std::vector<float> outBias;
+};
+
+template<class KeyType, class VlKeyType>
+static bool dumpCong(const lm::ILangModel* base, kb2_header& h, CongDump& d)
+{
+	using Model = lm::CoNgramModel<ArchType::avx2, KeyType, VlKeyType, 0, true>;
+	auto* m = dynamic_cast<const Model*>(base);
+	if (!m) return false;
+	const auto& hd = m->getHeader();
+	// non-leaf nodes are contiguous in DFS order: walk them while the highest reachable index grows
+	size_t count = 1;
+	for (size_t i = 0; i < count; ++i)
+	{
+		const auto& n = m->nodeData[i];
+		std::vector<std::pair<uint32_t, int32_t>> kv(n.numNexts);
+		for (size_t j = 0; j < n.numNexts; ++j)
+		{
+			auto p = nst::extractKV<ArchType::avx2, VlKeyType, int32_t>(&m->alignedKeyValueData[n.nextOffset], n.numNexts, j);
+			kv[j] = std::make_pair((uint32_t)p.first, p.second);
+			if (p.second > 0) count = std::max(count, i + (size_t)p.second + 1);
+		}
+		std::sort(kv.begin(), kv.end());
+		d.nodes.push_back(kb2_cg_node{ (int32_t)n.lower, n.value, (uint32_t)d.keys.size(), (uint32_t)n.numNexts });
+		for (auto& p : kv) { d.keys.push_back(p.first); d.values.push_back(p.second); }
+	}
+	d.root.assign(m->allRootValueData.get(), m->allRootValueData.get() + hd.vocabSize);
+	const size_t cs = m->contextEmbStride(), os = m->outputEmbStride();
+	if (cs != (size_t)hd.dim + 8 || os != (size_t)hd.dim + 8) throw std::runtime_error{ "unexpected CoNg row stride" };
+	d.ctxEmb.assign(m->contextEmbPtr, m->contextEmbPtr + hd.contextSize * cs);
+	d.outEmb.assign(m->outputEmbPtr, m->outputEmbPtr + hd.vocabSize * os);
+	if (m->invertedContextVocabPtr) for (size_t i = 0; i < hd.vocabSize; ++i) d.invVocab.push_back((uint32_t)m->invertedContextVocabPtr[i]);
+	if (m->outputEmbBiasPtr) d.outBias.assign(m->outputEmbBiasPtr, m->outputEmbBiasPtr + hd.vocabSize);
+	h.cg_num_nodes = (uint32_t)d.nodes.size();
+	h.cg_num_edges = (uint32_t)d.keys.size();
+	h.cg_root_size = (uint32_t)hd.vocabSize;
+	h.cg_dim = hd.dim;
+	h.cg_context_size = (uint32_t)hd.contextSize;
+	h.cg_key_size = hd.keySize;
+	h.cg_flags = hd.flags;
+	h.lang_vocab_size = (uint32_t)hd.vocabSize;
+	return true;
+}
+
 int main(int argc, char** argv)
 {
 	if (argc < 3) { std::cerr << "usage: flatten_model <model_dir> <out.img> [name]\n"; return 2; }
@@ -79,7 +132,8 @@ int main(int argc, char** argv)
 		std::memset(&h, 0, sizeof(h));
 		h.magic = KB2_IMAGE_MAGIC;
 		h.version = KB2_IMAGE_VERSION;
-		h.model_type = (uint32_t)ModelType::knlm;
+		const bool cong = argc > 4 && std::string{ argv[4] } == "cong";
+		h.model_type = (uint32_t)(cong ? ModelType::cong : ModelType::knlm);
 		std::strncpy(h.model_name, argc > 3 ? argv[3] : argv[1], sizeof(h.model_name) - 1);
 
 		// ---- form trie
@@ -170,6 +224,20 @@ int main(int argc, char** argv)
 		// ---- Knlm
 		std::vector<kb2_kn_node> knodes; std::vector<uint32_t> kkeys, khtx; std::vector<int32_t> kvals, kroot;
 		const auto* lmBase = kw.langMdl.get();
+		CongDump cg;
+		std::unique_ptr<Kiwi> kwCong;
+		if (cong)
+		{
+			setenv("KIWI_ARCH_TYPE", "avx2", 1);
+			KiwiBuilder kbc{ argv[1], 1, BuildOption::default_, ModelType::cong };
+			kwCong = std::make_unique<Kiwi>(kbc.build());
+			setenv("KIWI_ARCH_TYPE", "balanced", 1);
+			if (kwCong->morphemes.size() != kw.morphemes.size() || kwCong->forms.size() != kw.forms.size()) throw std::runtime_error{ "cong / knlm builds differ" };
+			const auto* cb = kwCong->langMdl.get();
+			if (!dumpCong<uint16_t, uint16_t>(cb, h, cg) && !dumpCong<uint32_t, uint16_t>(cb, h, cg) && !dumpCong<uint32_t, uint32_t>(cb, h, cg))
+				throw std::runtime_error{ "language model is not an avx2 quantized CoNgramModel without window" };
+		}
+		else
 		if (!dumpKnlm<uint16_t>(lmBase, h, knodes, kkeys, kvals, kroot, khtx)
 			&& !dumpKnlm<uint32_t>(lmBase, h, knodes, kkeys, kvals, kroot, khtx)
 			&& !dumpKnlm<uint8_t>(lmBase, h, knodes, kkeys, kvals, kroot, khtx)
@@ -225,6 +293,14 @@ int main(int argc, char** argv)
 		putSection(blob, h.sec[KB2_SEC_KN_ROOT], kroot);
 		putSection(blob, h.sec[KB2_SEC_KN_HTX], khtx);
 		putSection(blob, h.sec[KB2_SEC_CHR_RUNS], runs);
+		putSection(blob, h.sec[KB2_SEC_CG_NODES], cg.nodes);
+		putSection(blob, h.sec[KB2_SEC_CG_KEYS], cg.keys);
+		putSection(blob, h.sec[KB2_SEC_CG_VALUES], cg.values);
+		putSection(blob, h.sec[KB2_SEC_CG_ROOT], cg.root);
+		putSection(blob, h.sec[KB2_SEC_CG_CTX_EMB], cg.ctxEmb);
+		putSection(blob, h.sec[KB2_SEC_CG_OUT_EMB], cg.outEmb);
+		putSection(blob, h.sec[KB2_SEC_CG_INV_VOCAB], cg.invVocab);
+		putSection(blob, h.sec[KB2_SEC_CG_OUT_BIAS], cg.outBias);
 		while (blob.size() % 256) blob.push_back(0);
 		h.total_bytes = blob.size();
 		std::memcpy(blob.data(), &h, sizeof(h));
@@ -233,7 +309,9 @@ int main(int argc, char** argv)
 		std::cerr << "image: " << blob.size() << " bytes; trie nodes " << tnodes.size() << " edges " << tkeys.size()
 			<< "; forms " << forms.size() << "; morphemes " << morphs.size() << "; knlm nodes " << knodes.size()
 			<< " edges " << kkeys.size() << " vocab " << h.lang_vocab_size << " htxVocab " << h.kn_htx_vocab
-			<< " bos " << h.kn_bos_node << " unk_ll " << h.kn_unk_ll << std::endl;
+			<< " bos " << h.kn_bos_node << " unk_ll " << h.kn_unk_ll
+			<< "; cong nodes " << h.cg_num_nodes << " edges " << h.cg_num_edges << " dim " << h.cg_dim << " contexts " << h.cg_context_size
+			<< " keySize " << h.cg_key_size << " flags " << h.cg_flags << std::endl;
 	}
 	catch (const std::exception& e)
 	{

@@ -21,6 +21,7 @@ namespace orc
 		uint64_t candEntries = 0, candEvals = 0;                                    // sum cand (ids read), sum C_v (morpheme records)
 		uint64_t lmSteps = 0, lmHops = 0, lmProbes = 0;                             // progress() calls, H_lm, sum ceil(log2(k+1))
 		uint64_t pairs = 0, pathsWritten = 0, pathsKept = 0, tokens = 0;           // P_read, P (container inserts), surviving, T
+		uint64_t cgRows = 0, cgMacs = 0;                                            // CoNg: unique rows gathered per node, sum m*n*dim
 	};
 	inline uint32_t ceilLog2p1(uint32_t k) { uint32_t r = 0; while ((1u << r) < k + 1) ++r; return r; }
 	// reference POSTag values used by name (include/kiwi/Types.h:195-227)

@@ -77,8 +77,36 @@ int orc_lattice(void* p, const uint16_t* text, int len, int32_t* rows, int maxRo
 void orc_work_counters(void* p, uint64_t* out)
 {
 	auto* h = reinterpret_cast<OrcHandle*>(p);
-	static_assert(sizeof(orc::WorkCounters) == 18 * sizeof(uint64_t), "WorkCounters layout");
-	std::memcpy(out, &h->an->work, sizeof(orc::WorkCounters));
+	static_assert(sizeof(orc::WorkCounters) == 20 * sizeof(uint64_t), "WorkCounters layout");
+	std::memcpy(out, &h->an->work, 18 * sizeof(uint64_t));
+}
+
+// CoNg byte-model counters: {unique rows gathered (contexts + outputs), int8 MACs of the per-node gather GEMMs}
+void orc_cong_counters(void* p, uint64_t* out)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	out[0] = h->an->work.cgRows; out[1] = h->an->work.cgMacs;
+}
+
+// exact integer part and the three float epilogues of one (context row, output row) pair: {acc - hsum, E_scalar, E_small, E_gemv}
+int orc_cong_pair(void* p, uint32_t ctx, uint32_t wid, int32_t* accOut, float* eps)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	const auto& cg = h->an->viterbi.cg;
+	if (!cg.nodes || ctx >= h->im.h->cg_context_size || wid >= h->im.h->lang_vocab_size) return -1;
+	*accOut = cg.dotMinusHsum(ctx, wid);
+	eps[0] = cg.finish(ctx, wid, orc::Cong::E_scalar); eps[1] = cg.finish(ctx, wid, orc::Cong::E_small); eps[2] = cg.finish(ctx, wid, orc::Cong::E_gemv);
+	return 0;
+}
+
+// which epilogue the reference's kernel dispatch uses for m unique contexts x n unique outputs (0 scalar is never returned)
+int orc_cong_epilogue(int m, int n) { return (int)orc::Cong::epilogueOf((size_t)m, (size_t)n); }
+
+// one context-trie transition: returns the new contextIdx, *node is updated
+uint32_t orc_cong_step(void* p, int32_t* node, uint32_t wid)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	return h->an->viterbi.cg.step(*node, wid);
 }
 
 // work counters accumulated since open: {lmSteps, pairs, inserts, pathsOut, candEvals, evalCalls}

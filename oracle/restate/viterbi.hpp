@@ -12,6 +12,7 @@
 #include <cmath>
 #include "lattice.hpp"
 #include "knlm.hpp"
+#include "cong.hpp"
 
 namespace orc
 {
@@ -19,7 +20,8 @@ namespace orc
 
 	struct WordLL      // src/BestPathContainer.hpp:21-67
 	{
-		int32_t lmState = 0;
+		int32_t lmState = 0;          // Knlm: node index.  CoNg: context-trie node (the only field state equality looks at)
+		uint32_t ctxIdx = 0;          // CoNg only: CoNgramState::contextIdx, carried along but not compared (CoNgramModel.hpp:491-494)
 		uint8_t prevRootId = 0, spState = 0, rootId = 0;
 		int32_t morpheme = -1;
 		float accScore = 0, firstChunkScore = 0, accTypoCost = 0, accDialectCost = 0;
@@ -106,6 +108,8 @@ namespace orc
 	{
 		const Image& im;
 		Knlm lm;
+		Cong cg;
+		const bool cong;               // model_type == ModelType::cong: transposed evaluation (PathEvaluator.hpp:837-1036, CoNgramModel.cpp:17-317)
 		kb2_config cfg;
 		Counters* cnt = nullptr;
 		WorkCounters* wc = nullptr;
@@ -118,7 +122,7 @@ namespace orc
 		std::vector<uint8_t> uniqStates;
 		bool splitSaisiot = false, mergeSaisiot = false, splitComplex = false;
 
-		explicit Viterbi(const Image& _im) : im{ _im }, lm{ _im }, cfg{ _im.h->config } {}
+		explicit Viterbi(const Image& _im) : im{ _im }, lm{ _im }, cg{ _im }, cong{ _im.h->model_type == 4 }, cfg{ _im.h->config } {}
 
 		// --- small accessors
 		const kb2_morph& M(int32_t id) const { return im.morphs[id]; }
@@ -213,11 +217,16 @@ namespace orc
 		Container cont;
 
 		void contInsert(uint8_t prevRootId, uint8_t rootId, int32_t morph, float accScore, float firstChunkScore,
-			float accTypoCost, float accDialectCost, int32_t pNode, int32_t pIdx, uint8_t parentRootId, int32_t lmState, uint8_t spState)
+			float accTypoCost, float accDialectCost, int32_t pNode, int32_t pIdx, uint8_t parentRootId, int32_t lmState, uint8_t spState, uint32_t ctxIdx = 0)
 		{
 			if (cnt) cnt->inserts++;
 			if (wc) wc->pathsWritten++;
 			uint64_t h = (uint64_t)(int64_t)lmState;                                       // Knlm.hpp:1170-1178 std::hash<int32_t>
+			if (cong)                                                                       // CoNgramModel.hpp:505-541 Hash<uint32_t>(state.node)
+			{
+				const uint64_t v = (uint32_t)lmState;
+				h = (v * 2305843009213693951ull) ^ ((v << 33) | (v >> 31));
+			}
 			h = ((uint16_t)prevRootId | ((uint16_t)spState << 8)) ^ ((h << 3) | (h >> 61)); // BestPathContainer.hpp:79-84
 			const size_t bucket = cont.mode == 1 ? ((h >> 8) & 3) : 0;
 			auto& value = cont.buckets[bucket];
@@ -232,7 +241,7 @@ namespace orc
 				{
 					WordLL w;
 					w.morpheme = morph; w.accScore = accScore; w.firstChunkScore = firstChunkScore; w.accTypoCost = accTypoCost;
-					w.accDialectCost = accDialectCost; w.parentNode = pNode; w.parentIdx = pIdx; w.lmState = lmState; w.spState = spState;
+					w.accDialectCost = accDialectCost; w.parentNode = pNode; w.parentIdx = pIdx; w.lmState = lmState; w.spState = spState; w.ctxIdx = ctxIdx;
 					w.rootId = parentRootId;
 					w.prevRootId = prevRootId;
 					if (rootId != commonRootId) w.rootId = rootId;
@@ -246,7 +255,7 @@ namespace orc
 				if (accScore > t.accScore)
 				{
 					t.morpheme = morph; t.accScore = accScore; t.firstChunkScore = firstChunkScore; t.accTypoCost = accTypoCost;
-					t.accDialectCost = accDialectCost; t.parentNode = pNode; t.parentIdx = pIdx; t.lmState = lmState; t.spState = spState;
+					t.accDialectCost = accDialectCost; t.parentNode = pNode; t.parentIdx = pIdx; t.lmState = lmState; t.spState = spState; t.ctxIdx = ctxIdx;
 					t.rootId = parentRootId;
 					if (rootId != commonRootId) t.rootId = rootId;
 				}
@@ -255,7 +264,7 @@ namespace orc
 
 		// PathEvaluator.hpp:193-251
 		void insertToPathContainer(int32_t curId, int32_t lmState, float score, float firstChunkScore, const LNode* node,
-			const WordLL& prevPath, int32_t pNode, int32_t pIdx, const RuleScorer& rs)
+			const WordLL& prevPath, int32_t pNode, int32_t pIdx, const RuleScorer& rs, uint32_t ctxIdx = 0)
 		{
 			auto insert = [&](uint8_t rootId)
 			{
@@ -271,7 +280,7 @@ namespace orc
 				if (rs.sbType) spState = (spState & 3) | (uint8_t)(hashSbTypeOrder((uint8_t)rs.sbType, (uint8_t)(rs.sbOrder + 1)) << 2);
 				const float curDialectCost = 0.f;      // standard dialect only
 				contInsert(prevPath.rootId, rootId, curId, candScoreWithRule - curDialectCost, firstChunkScoreWithRule - curDialectCost,
-					prevPath.accTypoCost + node->typoCost, prevPath.accDialectCost + curDialectCost, pNode, pIdx, prevPath.rootId, lmState, spState);
+					prevPath.accTypoCost + node->typoCost, prevPath.accDialectCost + curDialectCost, pNode, pIdx, prevPath.rootId, lmState, spState, ctxIdx);
 			};
 			const bool quote = rs.specialType == 0 || rs.specialType == 1 || rs.specialType == 3 || rs.specialType == 4;
 			if ((rs.sbType || quote) && prevPath.rootId == commonRootId)
@@ -380,6 +389,267 @@ namespace orc
 			}
 		}
 
+
+		// FormEvaluator, PathEvaluator.hpp:253-311 (the CoNg evaluator calls it in a different place than evalSingleMorpheme)
+		bool formEval(const WordLL& prevPath, const kb2_morph& cur, float ignoreCondScore, float& score) const
+		{
+			const u16* lf; uint32_t ll;
+			const auto& pwm = M((int32_t)prevPath.wid);
+			if (prevPath.ownFormId) ownForm(prevPath.ownFormId, lf, ll);
+			else if (pwm.form_idx >= 0 && kformLen(pwm)) { lf = kformPtr(pwm); ll = kformLen(pwm); }
+			else { const auto& pm = M(prevPath.morpheme); lf = kformPtr(pm); ll = kformLen(pm); }
+			const bool leftSSC = ll && im.cls(lf[ll - 1]) == T_ssc;
+			const uint8_t prevTag = M(prevPath.morpheme).tag;
+			if (prevTag == T_ssc || leftSSC) return true;
+			const bool ok = ftVowel(lf, lf + ll, cur.vowel) && ftPolar(lf, lf + ll, cur.polar);
+			if (ignoreCondScore != 0) { score += ok ? 0 : ignoreCondScore; return true; }
+			return ok;
+		}
+
+		uint32_t lastSeqIdOf(int32_t curId) const            // CoNgramModel.cpp:147-168 (same rule as PathEvaluator.hpp:536-556)
+		{
+			const auto& cur = M(curId);
+			int32_t lastMorph;
+			if (isSingle(cur)) lastMorph = cur.combined ? curId + cur.combined : curId;
+			else lastMorph = (int32_t)im.chunks[cur.chunk_off + cur.chunk_cnt - 1].morph;
+			if ((uint32_t)lastMorph >= im.h->lang_vocab_size && (uint32_t)lastMorph < im.h->n_morphs) return (uint32_t)lastMorph;
+			return M(lastMorph).lm_morpheme_id;
+		}
+
+		void writeTo(std::vector<WordLL>& resultOut, int32_t curId, uint32_t lastSeqId, size_t ownFormId)     // BestPathContainer.hpp:451-469
+		{
+			const auto& cur = M(curId);
+			if (cnt) { size_t tot = 0; for (auto& b : cont.buckets) tot += b.size(); cnt->maxCont = std::max<uint64_t>(cnt->maxCont, tot); }
+			for (auto& b : cont.buckets) for (auto& p : b)
+			{
+				resultOut.push_back(p);
+				auto& np = resultOut.back();
+				np.wid = lastSeqId;
+				if (isSingle(cur)) { np.combineSocket = cur.combine_socket; np.ownFormId = (uint16_t)ownFormId; }
+			}
+		}
+
+		// MorphemeEvaluator<CoNgramState>::eval, src/CoNgramModel.cpp:17-317
+		void evalCong(std::vector<WordLL>& resultOut, size_t nodeIdx, size_t ownFormId, const std::vector<int32_t>& morphs,
+			float ignoreCondScore, float nodeLevelDiscount)
+		{
+			const LNode* node = graph + nodeIdx;
+			struct PP { const LNode* prev; int32_t pNode, pi; };
+			std::vector<PP> regularPrev, combiningPrev;
+			for (const LNode* prev = node->prev ? node - node->prev : nullptr; prev; prev = prev->sibling ? prev + prev->sibling : nullptr)
+			{
+				const int32_t pNode = (int32_t)(prev - graph);
+				for (size_t pi = 0; pi < cache[pNode].size(); ++pi)
+				{
+					(cache[pNode][pi].combineSocket ? combiningPrev : regularPrev).push_back(PP{ prev, pNode, (int32_t)pi });
+				}
+			}
+			std::vector<int32_t> regularMorphs, combiningL, combiningR;
+			std::vector<uint32_t> nextWids;
+			for (int32_t curId : morphs)
+			{
+				const auto& cur = M(curId);
+				if (cur.combine_socket) { (isSingle(cur) ? combiningL : combiningR).push_back(curId); continue; }
+				const uint32_t firstWid = isSingle(cur) ? cur.lm_morpheme_id : M((int32_t)im.chunks[cur.chunk_off].morph).lm_morpheme_id;
+				if (M((int32_t)firstWid).tag == T_p) continue;
+				regularMorphs.push_back(curId);
+				nextWids.push_back(firstWid);
+			}
+			// progressMatrix (CoNgramModel.cpp:124-139, 1494-1611): all (prevState x firstWid) scores and next states at once
+			const size_t P = regularPrev.size(), W = nextWids.size();
+			std::vector<float> scores(P * W);
+			std::vector<int32_t> nextNode(P * W);
+			std::vector<uint32_t> nextCtx(P * W);
+			if (P && W)
+			{
+				if (P == 1 && W == 1)
+				{
+					const WordLL& pp = cache[regularPrev[0].pNode][regularPrev[0].pi];
+					nextNode[0] = pp.lmState; nextCtx[0] = pp.ctxIdx;
+					scores[0] = cg.next(nextNode[0], nextCtx[0], nextWids[0]);
+					if (cnt) cnt->lmSteps++;
+				}
+				else
+				{
+					std::vector<uint32_t> uc, uw(nextWids);
+					for (auto& pp : regularPrev) uc.push_back(cache[pp.pNode][pp.pi].ctxIdx);
+					std::sort(uc.begin(), uc.end()); uc.erase(std::unique(uc.begin(), uc.end()), uc.end());
+					std::sort(uw.begin(), uw.end()); uw.erase(std::unique(uw.begin(), uw.end()), uw.end());
+					const auto ep = Cong::epilogueOf(uc.size(), uw.size());
+					if (wc) { wc->cgRows += uc.size() + uw.size(); wc->cgMacs += (uint64_t)uc.size() * uw.size() * cg.dim; }
+					for (size_t i = 0; i < P; ++i)
+					{
+						const WordLL& pp = cache[regularPrev[i].pNode][regularPrev[i].pi];
+						for (size_t j = 0; j < W; ++j)
+						{
+							scores[i * W + j] = cg.finish(pp.ctxIdx, nextWids[j], ep);
+							nextNode[i * W + j] = pp.lmState;
+							nextCtx[i * W + j] = cg.step(nextNode[i * W + j], nextWids[j]);
+							if (cnt) cnt->lmSteps++;
+							if (wc) wc->lmSteps++;
+						}
+					}
+				}
+			}
+			const bool allowedSpaceBetweenChunk = cfg.space_tolerance > 0;
+			const float lb = 0;
+			(void)lb;
+			for (size_t curIdx = 0; curIdx < regularMorphs.size(); ++curIdx)
+			{
+				const int32_t curId = regularMorphs[curIdx];
+				const auto& cur = M(curId);
+				cont.clear();
+				const size_t length = isSingle(cur) ? 1 : cur.chunk_cnt;
+				const RuleScorer rs = makeRuleScorer(curId, node);
+				const float morphScore = cur.user_score + nodeLevelDiscount + im.h->tag_left_boundary[hasLeftBoundary(node) ? 1 : 0][clearIrregular(cur.tag)];
+				for (size_t prevId = 0; prevId < P; ++prevId)
+				{
+					const auto& rp = regularPrev[prevId];
+					const WordLL& prevPath = cache[rp.pNode][rp.pi];
+					if (cnt) cnt->pairs++;
+					if (wc) wc->pairs++;
+					int32_t stNode = nextNode[prevId * W + curIdx]; uint32_t stCtx = nextCtx[prevId * W + curIdx];
+					float score = prevPath.accScore + morphScore + scores[prevId * W + curIdx];
+					const float firstChunkScore = morphScore + scores[prevId * W + curIdx];
+					if (!formEval(prevPath, cur, ignoreCondScore, score)) continue;
+					if (M(prevPath.morpheme).tag == T_z_siot && (!isNNClass(cur.tag) || rp.prev->endPos < node->startPos)) continue;
+					bool prohibited = false;
+					for (size_t i = 1; i < length; ++i)
+					{
+						const uint32_t wid = M((int32_t)im.chunks[cur.chunk_off + i].morph).lm_morpheme_id;
+						if (M((int32_t)wid).tag == T_p) { prohibited = true; break; }
+						score += cg.next(stNode, stCtx, wid);
+						if (cnt) cnt->lmSteps++;
+					}
+					if (prohibited) continue;
+					insertToPathContainer(curId, stNode, score, firstChunkScore, node, prevPath, rp.pNode, rp.pi, rs, stCtx);
+				}
+				writeTo(resultOut, curId, lastSeqIdOf(curId), ownFormId);
+			}
+			for (int32_t curId : combiningL)
+			{
+				const auto& cur = M(curId);
+				cont.clear();
+				const RuleScorer rs = makeRuleScorer(curId, node);
+				const float morphScore = cur.user_score + nodeLevelDiscount + im.h->tag_left_boundary[hasLeftBoundary(node) ? 1 : 0][clearIrregular(cur.tag)];
+				for (auto& rp : regularPrev)
+				{
+					const WordLL& prevPath = cache[rp.pNode][rp.pi];
+					if (cnt) cnt->pairs++;
+					if (wc) wc->pairs++;
+					float score = prevPath.accScore + morphScore;
+					const float firstChunkScore = morphScore;
+					if (!formEval(prevPath, cur, ignoreCondScore, score)) continue;
+					insertToPathContainer(curId, prevPath.lmState, score, firstChunkScore, node, prevPath, rp.pNode, rp.pi, rs, prevPath.ctxIdx);
+				}
+				writeTo(resultOut, curId, lastSeqIdOf(curId), ownFormId);
+			}
+			for (int32_t curId : combiningR)
+			{
+				const auto& cur = M(curId);
+				cont.clear();
+				const size_t length = isSingle(cur) ? 1 : cur.chunk_cnt;
+				const RuleScorer rs = makeRuleScorer(curId, node);
+				const float morphScore = cur.user_score + nodeLevelDiscount + im.h->tag_left_boundary[hasLeftBoundary(node) ? 1 : 0][clearIrregular(cur.tag)];
+				for (auto& rp : combiningPrev)
+				{
+					const WordLL& prevPath = cache[rp.pNode][rp.pi];
+					if (cnt) cnt->pairs++;
+					if (wc) wc->pairs++;
+					float score = prevPath.accScore + morphScore;
+					float firstChunkScore = 0;
+					if (prevPath.combineSocket != cur.combine_socket || isSingle(cur)) continue;
+					if (rp.prev->endPos < node->startPos)
+					{
+						if (allowedSpaceBetweenChunk) score -= cfg.space_penalty;
+						else continue;
+					}
+					const auto& pw = M((int32_t)prevPath.wid);
+					const uint32_t firstWid = M((int32_t)prevPath.wid + pw.combined).lm_morpheme_id;
+					if (!formEval(prevPath, cur, ignoreCondScore, score)) continue;
+					int32_t stNode = prevPath.lmState; uint32_t stCtx = prevPath.ctxIdx;
+					score += (firstChunkScore = cg.next(stNode, stCtx, firstWid));
+					if (cnt) cnt->lmSteps++;
+					firstChunkScore += morphScore;
+					bool prohibited = false;
+					for (size_t i = 1; i < length; ++i)
+					{
+						const uint32_t wid = M((int32_t)im.chunks[cur.chunk_off + i].morph).lm_morpheme_id;
+						if (M((int32_t)wid).tag == T_p) { prohibited = true; break; }
+						score += cg.next(stNode, stCtx, wid);
+						if (cnt) cnt->lmSteps++;
+					}
+					if (prohibited) continue;
+					insertToPathContainer(curId, stNode, score, firstChunkScore, node, prevPath, rp.pNode, rp.pi, rs, stCtx);
+				}
+				writeTo(resultOut, curId, lastSeqIdOf(curId), ownFormId);
+			}
+		}
+
+		// PathEvaluator<LmState, transposed>::operator(), PathEvaluator.hpp:860-1035
+		void evaluateCong(size_t nodeIdx, size_t ownFormId, const uint32_t* cands, size_t nCands, float nodeLevelDiscount, size_t totalPrevPathes)
+		{
+			const LNode* node = graph + nodeIdx;
+			auto& nCache = cache[nodeIdx];
+			int32_t zCodaMorph = -1, zSiotMorph = -1;
+			std::vector<int32_t> validMorphCands;
+			for (size_t ci = 0; ci < nCands; ++ci)
+			{
+				const int32_t curId = (int32_t)cands[ci];
+				const auto& cur = M(curId);
+				if (splitComplex && hasComplex(curId)) continue;
+				if (cur.dialect != 0) continue;
+				if (cur.tag == T_z_coda) { zCodaMorph = curId; continue; }
+				if (cur.tag == T_z_siot) { zSiotMorph = curId; continue; }
+				if (!isSingle(cur))
+				{
+					const u16* kf = kformPtr(cur);
+					const auto& c0 = M((int32_t)im.chunks[cur.chunk_off].morph);
+					if (node->prev && (node - node->prev)->endPos < node->startPos
+						&& kf && kformLen(cur) == 1 && (kf[0] == 0xB2E4 || kf[0] == 0xAC8C || kf[0] == 0xC9C0)
+						&& kformPtr(c0) && kformLen(c0) == 1 && kformPtr(c0)[0] == 0xD558)
+					{
+						continue;
+					}
+				}
+				validMorphCands.push_back(curId);
+			}
+			auto shortcut = [&](int32_t morphId, bool coda)
+			{
+				const auto& cur = M(morphId);
+				for (const LNode* prev = node->prev ? node - node->prev : nullptr; prev; prev = prev->sibling ? prev + prev->sibling : nullptr)
+				{
+					const int32_t pNode = (int32_t)(prev - graph);
+					for (size_t pi = 0; pi < cache[pNode].size(); ++pi)
+					{
+						const WordLL& p = cache[pNode][pi];
+						const uint8_t lastTag = M((int32_t)p.wid).tag;
+						if (coda) { if (!isJClass(lastTag) && !isEClass(lastTag)) continue; }
+						else { if (!isNNClass(lastTag)) continue; }
+						WordLL np = p;
+						np.accScore += cur.user_score * cfg.typo_cost_weight;
+						np.accTypoCost -= cur.user_score;
+						np.parentNode = pNode; np.parentIdx = (int32_t)pi;
+						np.morpheme = (int32_t)cur.lm_morpheme_id;
+						np.wid = cur.lm_morpheme_id;
+						nCache.push_back(np);
+					}
+				}
+			};
+			for (int ignoreCond = 0; ignoreCond < 2; ++ignoreCond)
+			{
+				if (zCodaMorph >= 0) shortcut(zCodaMorph, true);
+				if (zSiotMorph >= 0 && (splitSaisiot || mergeSaisiot)) shortcut(zSiotMorph, false);
+				if (cnt) cnt->candEvals += validMorphCands.size();
+				if (wc) wc->candEvals += validMorphCands.size();
+				if (totalPrevPathes <= 128) cont.mode = 0;
+				else if (totalPrevPathes <= 512) { cont.mode = 1; if (cnt) cnt->mediumMode++; }
+				else { cont.mode = 2; if (cnt) cnt->top1Mode++; }
+				evalCong(nCache, nodeIdx, ownFormId, validMorphCands, ignoreCond ? -10.f : 0.f, nodeLevelDiscount);
+				if (!nCache.empty()) break;
+			}
+		}
+
 		// PathEvaluator::operator(), PathEvaluator.hpp:347-512
 		void evaluate(size_t nodeIdx, size_t ownFormId, const uint32_t* cands, size_t nCands, float unkFormDiscount)
 		{
@@ -392,6 +662,8 @@ namespace orc
 			size_t totalPrevPathes = 0;
 			for (const LNode* prev = node->prev ? node - node->prev : nullptr; prev; prev = prev->sibling ? prev + prev->sibling : nullptr) totalPrevPathes += cache[prev - graph].size();
 
+			if (cong) evaluateCong(nodeIdx, ownFormId, cands, nCands, nodeLevelDiscount, totalPrevPathes);
+			else
 			for (int ignoreCond = 0; ignoreCond < 2; ++ignoreCond)
 			{
 				for (size_t ci = 0; ci < nCands; ++ci)
@@ -581,7 +853,7 @@ namespace orc
 
 			{
 				WordLL bos;
-				bos.morpheme = 0; bos.lmState = im.h->kn_bos_node; bos.rootId = commonRootId;
+				bos.morpheme = 0; bos.lmState = cong ? 0 : im.h->kn_bos_node; bos.ctxIdx = 0; bos.rootId = commonRootId;      // CoNgramState(const ILangModel*): node 0, contextIdx 0
 				cache[0].push_back(bos);
 				reachable[0] = 1;
 			}
@@ -648,10 +920,10 @@ namespace orc
 					if (pm.tag == T_z_siot) continue;
 					float c = p.accScore;
 					float firstChunkScore = 0;
-					int32_t st = p.lmState;
+					int32_t st = p.lmState; uint32_t stCtx = p.ctxIdx;
 					if (!openEnding)
 					{
-						c += (firstChunkScore = lmNext(st, 1));
+						c += (firstChunkScore = cong ? cg.next(st, stCtx, 1) : lmNext(st, 1));
 						if (p.spState & 1) c -= 2;
 						if (p.spState & 2) c -= 2;
 					}

@@ -20,6 +20,25 @@ def oracle():
 
 
 @pytest.fixture(scope="session")
+def oracle_cong():
+    from tests.orc import Oracle, CONG_IMAGE
+    if not os.path.exists(CONG_IMAGE):
+        pytest.skip("CoNg model image missing: run __graft_entry__.build() where /root/reference exists")
+    o = Oracle(CONG_IMAGE)
+    yield o
+    o.close()
+
+
+@pytest.fixture(scope="session")
+def kiwi_cong():
+    import kiwi_b200
+    from tests.orc import CONG_IMAGE
+    kw = kiwi_b200.Kiwi(CONG_IMAGE)
+    yield kw
+    kw.close()
+
+
+@pytest.fixture(scope="session")
 def kiwi():
     import kiwi_b200
     from tests.orc import IMAGE

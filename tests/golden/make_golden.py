@@ -9,16 +9,26 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 IMAGE = os.path.join(REFDIR, "models", "knlm_small.img")
+CONG_IMAGE = os.path.join(REFDIR, "models", "cong_small.img")
 manifest = {"image_md5": hashlib.md5(open(IMAGE, "rb").read()).hexdigest(), "model": "knlm_small (fabricated, see oracle/Makefile)",
+            "cong_image_md5": hashlib.md5(open(CONG_IMAGE, "rb").read()).hexdigest(), "cong_model": "cong_small (fabricated, see oracle/Makefile)",
             "reference_arch": "avx2", "files": {}}
-for name in ["inputs_ref_tests", "inputs_web", "inputs_written", "inputs_dialect_typos"]:
-    src = os.path.join(HERE, name + ".txt")
-    tmp = os.path.join("/tmp", name + ".golden.txt")
-    env = dict(os.environ, KIWI_ARCH_TYPE="avx2")
-    subprocess.run([os.path.join(REFDIR, "dump_golden"), os.path.join(REFDIR, "models", "knlm_small"), src, tmp], check=True, env=env)
-    data = open(tmp, "rb").read()
-    with gzip.GzipFile(os.path.join(HERE, name + ".golden.txt.gz"), "wb", mtime=0) as f:
-        f.write(data)
-    manifest["files"][name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
+# Knlm vectors: <name>.golden.txt.gz; CoNg vectors (same inputs, ModelType::cong on the cong_small model): cong_<name>.golden.txt.gz
+for model, mtype, prefix in [("knlm_small", "knlm", ""), ("cong_small", "cong", "cong_")]:
+    for name in ["inputs_ref_tests", "inputs_web", "inputs_written", "inputs_dialect_typos"]:
+        src = os.path.join(HERE, name + ".txt")
+        tmp = os.path.join("/tmp", prefix + name + ".golden.txt")
+        env = dict(os.environ, KIWI_ARCH_TYPE="avx2", KB_MODEL_TYPE=mtype)
+        subprocess.run([os.path.join(REFDIR, "dump_golden"), os.path.join(REFDIR, "models", model), src, tmp], check=True, env=env)
+        data = open(tmp, "rb").read()
+        with gzip.GzipFile(os.path.join(HERE, prefix + name + ".golden.txt.gz"), "wb", mtime=0) as f:
+            f.write(data)
+        manifest["files"][prefix + name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
+# known-answer vectors of the CoNg int8 scorer and context trie (oracle/ref_build/tools/cong_probe.cpp)
+subprocess.run([os.path.join(REFDIR, "cong_probe"), os.path.join(REFDIR, "models", "cong_small"), "/tmp/cong_qgemm.golden.txt"], check=True)
+data = open("/tmp/cong_qgemm.golden.txt", "rb").read()
+with gzip.GzipFile(os.path.join(HERE, "cong_qgemm.golden.txt.gz"), "wb", mtime=0) as f:
+    f.write(data)
+manifest["files"]["cong_qgemm"] = {"lines": data.count(b"\n"), "md5": hashlib.md5(data).hexdigest()}
 json.dump(manifest, open(os.path.join(HERE, "MANIFEST.json"), "w"), indent=1)
 print(manifest)

@@ -35,3 +35,15 @@ def read_golden(name):
             elif k == "K":
                 cur["paths"][-1]["toks"].append((int(p[1]), int(p[2]), int(p[3]), float.fromhex(p[4])))
     return out
+
+
+def read_cong_qgemm():
+    """records of tests/golden/cong_qgemm.golden.txt.gz: ("Q", m, n, ctxIds, outIds, floats) | ("P", node, ctx, wid, ll, node2, ctx2)"""
+    with gzip.open(os.path.join(HERE, "cong_qgemm.golden.txt.gz"), "rt") as f:
+        for line in f:
+            p = line.split()
+            if p[0] == "Q":
+                m, n = int(p[1]), int(p[2])
+                yield ("Q", m, n, [int(x) for x in p[3:3 + m]], [int(x) for x in p[3 + m:3 + m + n]], [float.fromhex(x) for x in p[3 + m + n:]])
+            else:
+                yield ("P", int(p[1]), int(p[2]), int(p[3]), float.fromhex(p[4]), int(p[5]), int(p[6]))

@@ -6,6 +6,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
 IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "knlm_small.img")
+CONG_IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "cong_small.img")
 
 
 class Oracle:
@@ -55,6 +56,33 @@ class Oracle:
         out = np.zeros(18, np.uint64)
         self.lib.orc_work_counters(self.h, out.ctypes.data)
         return dict(zip(self.WORK_FIELDS, [int(x) for x in out]))
+
+    # ---- CoNg scorer pieces (oracle/restate/cong.hpp)
+    def cong_pair(self, ctx: int, wid: int):
+        """-> (acc - hsum, [E_scalar, E_small, E_gemv]) for one (context row, output row) pair"""
+        self.lib.orc_cong_pair.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+        acc = C.c_int32(); eps = (C.c_float * 3)()
+        if self.lib.orc_cong_pair(self.h, ctx, wid, C.byref(acc), eps) != 0:
+            raise RuntimeError("oracle: not a CoNg image or index out of range")
+        return acc.value, [np.float32(eps[k]) for k in range(3)]
+
+    def cong_epilogue(self, m: int, n: int) -> int:
+        self.lib.orc_cong_epilogue.argtypes = [C.c_int, C.c_int]
+        return int(self.lib.orc_cong_epilogue(m, n))
+
+    def cong_step(self, node: int, wid: int):
+        """one context-trie transition -> (node', contextIdx')"""
+        self.lib.orc_cong_step.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_uint32]
+        self.lib.orc_cong_step.restype = C.c_uint32
+        nd = C.c_int32(node)
+        ctx = self.lib.orc_cong_step(self.h, C.byref(nd), wid)
+        return nd.value, int(ctx)
+
+    def cong_counters(self):
+        self.lib.orc_cong_counters.argtypes = [C.c_void_p, C.c_void_p]
+        out = np.zeros(2, np.uint64)
+        self.lib.orc_cong_counters(self.h, out.ctypes.data)
+        return {"cgRows": int(out[0]), "cgMacs": int(out[1])}
 
     def close(self):
         if self.h:
