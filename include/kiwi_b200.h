@@ -141,6 +141,15 @@ int kiwi_b200_last_stats(kiwi_h handle, kiwi_b200_stats_t* out);
  * {form, uform_off|-1, uform_len, prev, sibling, start, end, space_errors, chunk}.  Returns node count or < 0. */
 int kiwi_b200_debug_lattice(kiwi_h handle, const kchar16_t* text, int len, int32_t* out_rows, int max_rows, kiwi_analyze_option_t option);
 
+/* CoNg scorer self-test on the device (stage-level parity tests of the int8 scorer): for n
+ * (context id, output id, trie node) triples returns the integer dot product minus hsum (dp4a path), the three float
+ * epilogues (scalar / small / gemv association, src/qgemm.hpp:68-80, src/archImpl/avx2_qgemm.hpp:124,435), the context
+ * trie transition (src/CoNgramModel.hpp:271-385) and, in out_tile[min(n,64) x min(n,32)], the same integers computed by
+ * the tensor-core tile (mma.sync m16n8k32 u8 x s8) over the first contexts x first output ids. */
+int kiwi_b200_debug_cong(kiwi_h handle, int n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
+	int32_t* out_dot, float* out_eps, int32_t* out_node, uint32_t* out_ctx, int32_t* out_tile);
+int kiwi_b200_model_type(kiwi_h handle);         /* (int)ModelType of the loaded image: 2 knlm, 4 cong */
+
 int kiwi_b200_device_count(void);
 int kiwi_b200_set_device(int device);            /* call before kiwi_init; default: current device */
 /* raw model image access so a launcher can broadcast it (NCCL) and hand it to every rank */

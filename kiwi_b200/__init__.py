@@ -83,6 +83,8 @@ def load_library() -> C.CDLL:
     lib.kiwi_b200_analyze_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, AnalyzeOption, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.kiwi_b200_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     lib.kiwi_b200_debug_lattice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, AnalyzeOption]
+    lib.kiwi_b200_debug_cong.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
+    lib.kiwi_b200_model_type.argtypes = [C.c_void_p]
     lib.kiwi_b200_set_device.argtypes = [C.c_int]
     lib.kiwi_b200_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.kiwi_b200_free.argtypes = [C.c_void_p]
@@ -223,3 +225,22 @@ class Kiwi:
         if n < 0:
             raise KiwiError(_last_error(self._lib))
         return rows[:n].copy()
+
+    def model_type(self) -> int:
+        """(int)ModelType of the loaded image: 2 knlm, 4 cong"""
+        return int(self._lib.kiwi_b200_model_type(self._h))
+
+    def debug_cong(self, ctx, wid, node):
+        """CoNg scorer self-test on the device (kiwi_b200_debug_cong): arrays of context ids, output ids and trie nodes ->
+        dict(dot=int32[n], eps=float32[n,3] (scalar / small / gemv epilogue), node=int32[n], ctx=uint32[n] after one
+        context-trie step, tile=int32[min(n,64), min(n,32)] from the tensor-core tile)."""
+        ctx = np.ascontiguousarray(ctx, np.uint32); wid = np.ascontiguousarray(wid, np.uint32); node = np.ascontiguousarray(node, np.int32)
+        n = len(ctx)
+        assert len(wid) == n and len(node) == n
+        dot = np.zeros(n, np.int32); eps = np.zeros((n, 3), np.float32); onode = np.zeros(n, np.int32); octx = np.zeros(n, np.uint32)
+        tile = np.zeros((min(n, 64), min(n, 32)), np.int32)
+        rc = self._lib.kiwi_b200_debug_cong(self._h, n, ctx.ctypes.data, wid.ctypes.data, node.ctypes.data,
+                                            dot.ctypes.data, eps.ctypes.data, onode.ctypes.data, octx.ctypes.data, tile.ctypes.data)
+        if rc != 0:
+            raise KiwiError(_last_error(self._lib))
+        return dict(dot=dot, eps=eps, node=onode, ctx=octx, tile=tile)

@@ -377,5 +377,24 @@ int kiwi_b200_debug_lattice(kiwi_h handle, const kchar16_t* text, int len, int32
 	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
 }
 
+int kiwi_b200_debug_cong(kiwi_h handle, int n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
+	int32_t* out_dot, float* out_eps, int32_t* out_node, uint32_t* out_ctx, int32_t* out_tile)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	try
+	{
+		std::lock_guard<std::mutex> lk(handle->mtx);
+		handle->engine->debugCong((uint32_t)n, ctx, wid, node, out_dot, out_eps, out_node, out_ctx, out_tile);
+		return 0;
+	}
+	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+
+int kiwi_b200_model_type(kiwi_h handle)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	return (int)handle->engine->model.header.model_type;
+}
+
 #pragma GCC visibility pop
 }

@@ -23,6 +23,10 @@ namespace kb
 	cudaError_t launch_emit(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
 	cudaError_t set_model_lattice(const DevModel& m);
 	cudaError_t set_model_viterbi(const DevModel& m);
+	cudaError_t launch_viterbi_cong(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
+	cudaError_t set_model_viterbi_cong(const DevModel& m);
+	cudaError_t launch_cong_debug(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
+		int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile, cudaStream_t stream);
 	cudaError_t set_model_emit(const DevModel& m);
 
 	static void ck(cudaError_t e, const char* what)
@@ -54,7 +58,7 @@ namespace kb
 	Engine::Engine(const void* imageBytes, size_t size)
 	{
 		model.load(imageBytes, size);
-		ck(set_model_lattice(model.dev), "constant upload"); ck(set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
+		ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
 		ck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
 		for (auto& e : ev) ck(cudaEventCreate(&e), "cudaEventCreate");
 	}
@@ -136,7 +140,7 @@ namespace kb
 	{
 		if (g_constantsOwner != &model)
 		{
-			ck(set_model_lattice(model.dev), "constant upload"); ck(set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
+			ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
 			g_constantsOwner = &model;
 		}
 		ck(cudaEventRecord(ev[1], stream), "event");
@@ -148,7 +152,7 @@ namespace kb
 		sc.bv.order = sc.order;
 		ck(launch_lattice(model.dev, sc.bv, stream), "lattice_kernel launch");
 		ck(cudaEventRecord(ev[2], stream), "event");
-		ck(launch_viterbi(model.dev, sc.bv, sc.vv, stream), "viterbi_kernel launch");
+		ck(model.dev.model_type == 4 ? launch_viterbi_cong(model.dev, sc.bv, sc.vv, stream) : launch_viterbi(model.dev, sc.bv, sc.vv, stream), "viterbi_kernel launch");
 		ck(cudaEventRecord(ev[3], stream), "event");
 		ck(launch_emit(model.dev, sc.bv, sc.vv, stream), "emit_kernel launch");
 		ck(cudaMemsetAsync(sc.vv.n_tokens + n, 0, 4, stream), "memset");
@@ -371,6 +375,38 @@ namespace kb
 		return ms;
 	}
 
+	void Engine::debugCong(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
+		int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile)
+	{
+		if (model.dev.model_type != 4) throw std::runtime_error("debugCong needs a CoNg model image");
+		if (n == 0) return;
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			if (ctx[i] >= model.dev.cg_context_size || wid[i] >= model.dev.lang_vocab_size || node[i] < 0 || (uint32_t)node[i] >= model.header.cg_num_nodes)
+				throw std::runtime_error("debugCong: index out of range");
+		}
+		if (g_constantsOwner != &model) { ck(set_model_lattice(model.dev), "constant upload"); ck(set_model_viterbi_cong(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload"); g_constantsOwner = &model; }
+		const uint32_t nU = std::min(n, 64u), nW = std::min(n, 32u);
+		uint32_t* d = nullptr;
+		const size_t words = (size_t)n * 9 + (size_t)nU * nW;
+		ck(cudaMalloc(&d, words * 4), "cudaMalloc(debugCong)");
+		uint32_t* dCtx = d; uint32_t* dWid = d + n; int32_t* dNode = reinterpret_cast<int32_t*>(d + 2 * n);
+		int32_t* dDot = reinterpret_cast<int32_t*>(d + 3 * n); float* dEps = reinterpret_cast<float*>(d + 4 * n);
+		int32_t* dNodeOut = reinterpret_cast<int32_t*>(d + 7 * n); uint32_t* dCtxOut = d + 8 * n; int32_t* dTile = reinterpret_cast<int32_t*>(d + 9 * n);
+		cudaError_t e = cudaMemcpyAsync(dCtx, ctx, n * 4, cudaMemcpyHostToDevice, stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(dWid, wid, n * 4, cudaMemcpyHostToDevice, stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(dNode, node, n * 4, cudaMemcpyHostToDevice, stream);
+		if (e == cudaSuccess) e = launch_cong_debug(n, dCtx, dWid, dNode, dDot, dEps, dNodeOut, dCtxOut, dTile, stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(outDot, dDot, n * 4, cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(outEps, dEps, n * 12, cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(outNode, dNodeOut, n * 4, cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(outCtx, dCtxOut, n * 4, cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(outTile, dTile, (size_t)nU * nW * 4, cudaMemcpyDeviceToHost, stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+		cudaFree(d);
+		ck(e, "debugCong");
+	}
+
 	int Engine::debugLattice(const uint16_t* text, uint32_t len, uint32_t matchOptions, std::vector<int32_t>& rows)
 	{
 		const uint32_t off[2] = { 0, len };
@@ -382,7 +418,7 @@ namespace kb
 		bind(sc, sc.dText, sc.dOff, 1, matchOptions);
 		ck(cudaMemsetAsync(sc.order, 0, 4, stream), "memset");
 		sc.bv.order = sc.order;
-		if (g_constantsOwner != &model) { ck(set_model_lattice(model.dev), "constant upload"); ck(set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload"); g_constantsOwner = &model; }
+		if (g_constantsOwner != &model) { ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload"); g_constantsOwner = &model; }
 		ck(launch_lattice(model.dev, sc.bv, stream), "lattice launch");
 		uint32_t nChunks = 0, status = 0;
 		ck(cudaMemcpyAsync(&nChunks, sc.bv.n_chunks, 4, cudaMemcpyDeviceToHost, stream), "D2H");

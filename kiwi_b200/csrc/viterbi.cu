@@ -41,10 +41,12 @@
 #endif
 #if KB_CONG
 #define KB_VIT_NS vit_cong
+#define KB_VIT_KERNEL viterbi_cong_kernel
 #define P_WID_FEAT(p) (c_m.morphs[(p).wid].feat)
 #define P_CTX(p) ((p).wid_feat)
 #else
 #define KB_VIT_NS vit_knlm
+#define KB_VIT_KERNEL viterbi_kernel
 #define P_WID_FEAT(p) ((p).wid_feat)
 #endif
 
@@ -318,6 +320,51 @@ namespace KB_VIT_NS
 		ctx = cgStep(node, wid);
 		return ll;
 	}
+
+	// progressMatrix's gather GEMM for one group of <= 32 candidates (src/CoNgramModel.cpp:1575-1579, qgemm.hpp:36-87):
+	// dots[u][c] = sum_k ctx_u8[uctx[u]][k] * out_s8[colWid[c]][k] - hsum[colWid[c]] as warp-level tensor-core tiles,
+	// mma.sync.m16n8k32 (u8 x s8 -> s32); rows are gathered straight from the resident embedding tables (L2).
+	// Fragment layout (g = lane / 4, t = lane % 4): A row-major 16x32: a0 (row g, k 4t..4t+3), a1 (row g+8, same k), a2 (row g, k 16+4t..),
+	// a3 (row g+8, k 16+4t..); B col-major 32x8: b0 (k 4t..4t+3, col g), b1 (k 16+4t.., col g); C: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1).
+	__device__ __noinline__ void cgTileDots(const uint32_t* uctx, const uint32_t* colWid, int32_t (*dots)[33], uint32_t nU, uint32_t colMask, uint32_t lane)
+	{
+		const uint32_t g = lane >> 2, t = lane & 3;
+		const uint32_t mTiles = (nU + 15) >> 4, kSteps = c_m.cg_dim >> 5, stride = c_m.cg_stride;
+		#pragma unroll 1
+		for (uint32_t nt = 0; nt < 4; ++nt)
+		{
+			if (!((colMask >> (nt * 8)) & 0xFFu)) continue;
+			const uint32_t col = nt * 8 + g;
+			const uint32_t wid = ((colMask >> col) & 1u) ? colWid[col] : 0u;
+			const uint8_t* pb = c_m.cg_out_emb + (size_t)wid * stride;
+			// hsum of the two columns this lane's accumulators belong to (2t, 2t + 1)
+			const uint32_t c0col = nt * 8 + t * 2, c1col = c0col + 1;
+			const uint32_t w0 = ((colMask >> c0col) & 1u) ? colWid[c0col] : 0u, w1 = ((colMask >> c1col) & 1u) ? colWid[c1col] : 0u;
+			const int32_t h0 = *reinterpret_cast<const int32_t*>(c_m.cg_out_emb + (size_t)w0 * stride + c_m.cg_dim + 4);
+			const int32_t h1 = *reinterpret_cast<const int32_t*>(c_m.cg_out_emb + (size_t)w1 * stride + c_m.cg_dim + 4);
+			#pragma unroll 1
+			for (uint32_t mt = 0; mt < mTiles; ++mt)
+			{
+				const uint32_t r0 = mt * 16 + g, r1 = r0 + 8;
+				const uint8_t* pa0 = c_m.cg_ctx_emb + (size_t)uctx[r0 < nU ? r0 : 0] * stride;
+				const uint8_t* pa1 = c_m.cg_ctx_emb + (size_t)uctx[r1 < nU ? r1 : 0] * stride;
+				int32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+				#pragma unroll 2
+				for (uint32_t kk = 0; kk < kSteps; ++kk)
+				{
+					const uint32_t ko = kk * 32 + t * 4;
+					const uint32_t a0 = *reinterpret_cast<const uint32_t*>(pa0 + ko), a1 = *reinterpret_cast<const uint32_t*>(pa1 + ko);
+					const uint32_t a2 = *reinterpret_cast<const uint32_t*>(pa0 + ko + 16), a3 = *reinterpret_cast<const uint32_t*>(pa1 + ko + 16);
+					const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pb + ko), b1 = *reinterpret_cast<const uint32_t*>(pb + ko + 16);
+					asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+						: "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+				}
+				if (r0 < nU) { dots[r0][c0col] = c0 - h0; dots[r0][c1col] = c1 - h1; }
+				if (r1 < nU) { dots[r1][c0col] = c2 - h0; dots[r1][c1col] = c3 - h1; }
+			}
+		}
+		__syncwarp();
+	}
 #endif
 
 	// ------------------------------------------------------------------------------------------------
@@ -462,6 +509,10 @@ namespace KB_VIT_NS
 				bool setsFW = false; uint32_t fwVal = 0;
 				if (valid)
 				{
+#if KB_CONG
+					// only the regular-candidate loop of the transposed evaluator has the z_siot test (CoNgramModel.cpp:184-189 vs 208-246)
+					if (cc.cur.combine_socket == 0)
+#endif
 					if (pp.morph_tag == T_z_siot && (!isNNClass(cc.cur.feat & MF_TAG_MASK) || cc.spaceBefore)) valid = false;
 				}
 				if (valid)
@@ -1210,48 +1261,7 @@ namespace KB_VIT_NS
 			return cn;
 		}
 
-		// progressMatrix's gather GEMM for one group of <= 32 candidates (src/CoNgramModel.cpp:1575-1579, qgemm.hpp:36-87):
-		// dots[u][c] = sum_k ctx_u8[uctx[u]][k] * out_s8[colWid[c]][k] - hsum[colWid[c]] as warp-level tensor-core tiles,
-		// mma.sync.m16n8k32 (u8 x s8 -> s32); rows are gathered straight from the resident embedding tables (L2).
-		__device__ __noinline__ void congGroupDots(uint32_t nU, uint32_t colMask)
-		{
-			const uint32_t g = lane >> 2, t = lane & 3;
-			const uint32_t mTiles = (nU + 15) >> 4, kSteps = c_m.cg_dim >> 5, stride = c_m.cg_stride;
-			#pragma unroll 1
-			for (uint32_t nt = 0; nt < 4; ++nt)
-			{
-				if (!((colMask >> (nt * 8)) & 0xFFu)) continue;
-				const uint32_t col = nt * 8 + g;
-				const uint32_t wid = ((colMask >> col) & 1u) ? sm->colWid[col] : 0u;
-				const uint8_t* pb = c_m.cg_out_emb + (size_t)wid * stride;
-				// hsum of the two columns this lane's accumulators belong to (t * 2, t * 2 + 1)
-				const uint32_t c0col = nt * 8 + t * 2, c1col = c0col + 1;
-				const uint32_t w0 = ((colMask >> c0col) & 1u) ? sm->colWid[c0col] : 0u, w1 = ((colMask >> c1col) & 1u) ? sm->colWid[c1col] : 0u;
-				const int32_t h0 = *reinterpret_cast<const int32_t*>(c_m.cg_out_emb + (size_t)w0 * stride + c_m.cg_dim + 4);
-				const int32_t h1 = *reinterpret_cast<const int32_t*>(c_m.cg_out_emb + (size_t)w1 * stride + c_m.cg_dim + 4);
-				#pragma unroll 1
-				for (uint32_t mt = 0; mt < mTiles; ++mt)
-				{
-					const uint32_t r0 = mt * 16 + g, r1 = r0 + 8;
-					const uint8_t* pa0 = c_m.cg_ctx_emb + (size_t)sm->uctx[r0 < nU ? r0 : 0] * stride;
-					const uint8_t* pa1 = c_m.cg_ctx_emb + (size_t)sm->uctx[r1 < nU ? r1 : 0] * stride;
-					int32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-					#pragma unroll 2
-					for (uint32_t kk = 0; kk < kSteps; ++kk)
-					{
-						const uint32_t ko = kk * 32 + t * 4;
-						const uint32_t a0 = *reinterpret_cast<const uint32_t*>(pa0 + ko), a1 = *reinterpret_cast<const uint32_t*>(pa1 + ko);
-						const uint32_t a2 = *reinterpret_cast<const uint32_t*>(pa0 + ko + 16), a3 = *reinterpret_cast<const uint32_t*>(pa1 + ko + 16);
-						const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pb + ko), b1 = *reinterpret_cast<const uint32_t*>(pb + ko + 16);
-						asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-							: "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-					}
-					if (r0 < nU) { sm->dots[r0][c0col] = c0 - h0; sm->dots[r0][c1col] = c1 - h1; }
-					if (r1 < nU) { sm->dots[r1][c0col] = c2 - h0; sm->dots[r1][c1col] = c3 - h1; }
-				}
-			}
-			__syncwarp();
-		}
+		__device__ __forceinline__ void congGroupDots(uint32_t nU, uint32_t colMask) { cgTileDots(sm->uctx, sm->colWid, sm->dots, nU, colMask, lane); }
 #endif
 
 		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
@@ -1930,7 +1940,7 @@ namespace KB_VIT_NS
 	#ifndef KB_VIT_MIN_BLOCKS
 #define KB_VIT_MIN_BLOCKS 4
 #endif
-	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) viterbi_kernel(const BatchView bv, const VitView vv)
+	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) KB_VIT_KERNEL(const BatchView bv, const VitView vv)
 	{
 		extern __shared__ __align__(16) unsigned char smRaw[];
 		WarpSmem* smAll = reinterpret_cast<WarpSmem*>(smRaw);
@@ -2080,8 +2090,48 @@ namespace KB_VIT_NS
 		}
 	}
 
+#if KB_CONG
+	// ---- device self-test of the CoNg scorer pieces (kiwi_b200_debug_cong): one thread per (context, wid, node) triple for the
+	// dp4a dot, the three epilogues and one context-trie transition; warp 0 of block 0 additionally runs the tensor-core tile over
+	// the first min(n, 64) contexts x first min(n, 32) wids.
+	__global__ void cong_debug_kernel(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
+		int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile)
+	{
+		__shared__ uint32_t sU[64]; __shared__ uint32_t sW[32]; __shared__ int32_t sD[64][33];
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i < n)
+		{
+			const int32_t x = cgDot(ctx[i], wid[i]);
+			outDot[i] = x;
+			outEps[3 * i + 0] = cgFinish(x, ctx[i], wid[i], CG_E_SCALAR);
+			outEps[3 * i + 1] = cgFinish(x, ctx[i], wid[i], CG_E_SMALL);
+			outEps[3 * i + 2] = cgFinish(x, ctx[i], wid[i], CG_E_GEMV);
+			int32_t nd = node[i];
+			outCtx[i] = cgStep(nd, wid[i]);
+			outNode[i] = nd;
+		}
+		if (blockIdx.x == 0 && threadIdx.x < 32)
+		{
+			const uint32_t lane = threadIdx.x, nU = min(n, 64u), nW = min(n, 32u);
+			for (uint32_t k = lane; k < nU; k += 32) sU[k] = ctx[k];
+			if (lane < nW) sW[lane] = wid[lane];
+			__syncwarp();
+			cgTileDots(sU, sW, sD, nU, nW == 32 ? 0xFFFFFFFFu : ((1u << nW) - 1), lane);
+			for (uint32_t k = lane; k < nU * nW; k += 32) outTile[k] = sD[k / nW][k % nW];
+		}
+	}
+#endif
 }   // namespace KB_VIT_NS
 	using namespace KB_VIT_NS;
+
+#if KB_CONG
+	cudaError_t launch_cong_debug(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
+		int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile, cudaStream_t stream)
+	{
+		cong_debug_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, ctx, wid, node, outDot, outEps, outNode, outCtx, outTile);
+		return cudaGetLastError();
+	}
+#endif
 
 #if KB_CONG
 #define KB_SET_MODEL set_model_viterbi_cong
@@ -2098,8 +2148,8 @@ namespace KB_VIT_NS
 		const uint32_t blocks = (bv.n_sent + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 		static bool attrSet = false;
 		const size_t smemBytes = sizeof(WarpSmem) * WARPS_PER_BLOCK;
-		if (!attrSet) { cudaFuncSetAttribute(viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); attrSet = true; }
-		viterbi_kernel<<<blocks, WARPS_PER_BLOCK * 32, smemBytes, stream>>>(bv, vv);
+		if (!attrSet) { cudaFuncSetAttribute(KB_VIT_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); attrSet = true; }
+		KB_VIT_KERNEL<<<blocks, WARPS_PER_BLOCK * 32, smemBytes, stream>>>(bv, vv);
 		return cudaGetLastError();
 	}
 }
