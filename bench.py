@@ -51,11 +51,22 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def set_model(name):
+    """knlm (headline, BASELINE.json config[1]) or cong (config[2]: quantized CoNg model, int8 scorer on tensor-core tiles)"""
+    global IMAGE, REF_MODEL_DIR, MODEL
+    MODEL = name
+    IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", name + "_small.img")
+    REF_MODEL_DIR = os.path.join(ROOT, "oracle", "_ref", "models", name + "_small")
+
+
+MODEL = "knlm"
+
+
 def work_counters(batch_texts, batch_size, seed):
     """Per-sentence algorithmic bytes from the instrumented oracle (committed under profiles/; recomputed on a sample if absent)."""
     from kiwi_b200 import bytemodel
     path = os.path.join(ROOT, "profiles", "counters_r1.json")
-    if os.path.exists(path):
+    if MODEL == "knlm" and os.path.exists(path):
         d = json.load(open(path))
         key = "batch%d_seed%d" % (batch_size, seed)
         if key in d:
@@ -65,7 +76,9 @@ def work_counters(batch_texts, batch_size, seed):
     o = Oracle(IMAGE)
     sample = batch_texts[:256]
     for s in sample: o.analyze(s)
-    c = o.work_counters(); o.close()
+    c = o.work_counters()
+    if MODEL == "cong": c.update(o.cong_counters())
+    o.close()
     return c, bytemodel.lattice_bytes(c) / c["sentences"], bytemodel.viterbi_bytes(c) / c["sentences"], "oracle sample of 256 sentences"
 
 
@@ -76,7 +89,7 @@ def run_reference_cpu(texts, threads, repeats=1):
             for t in texts: f.write(t + "\n")
             tmp = f.name
         try:
-            env = dict(os.environ); env.setdefault("KIWI_ARCH_TYPE", "avx2")
+            env = dict(os.environ); env.setdefault("KIWI_ARCH_TYPE", "avx2"); env["KB_MODEL_TYPE"] = MODEL
             out = subprocess.run([REF_BENCH, REF_MODEL_DIR, tmp, str(threads), str(repeats)], capture_output=True, text=True, timeout=1200, env=env)
             line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
             r = json.loads(line)
@@ -101,7 +114,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments)")
+    ap.add_argument("--model", default="knlm", choices=["knlm", "cong"], help="knlm = headline config; cong = BASELINE.json config[2] (CoNg model)")
     args = ap.parse_args()
+    set_model(args.model)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from kiwi_b200.synth import synth_batch, SEED
 
@@ -120,7 +135,7 @@ def main():
         last["value"] = v
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
                           "ms_per_step": 1000.0 * len(texts) / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "batch=%d synthetic Korean sentences (web.txt length dist), fabricated Knlm model, top-1; each step = %d-sentence sample on %d host threads" % (args.batch, len(texts), threads)},
+                          "config": {"workload": "batch=%d synthetic Korean sentences (web.txt length dist), fabricated %s model, top-1; each step = %d-sentence sample on %d host threads" % (args.batch, MODEL, len(texts), threads)},
                           "cpu_baseline": last, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -204,14 +219,14 @@ def main():
     achieved = vit_b * args.batch / (vit_per_launch_ms / 1000.0) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
-    if os.path.exists(tp):
+    if MODEL == "knlm" and os.path.exists(tp):
         traffic = json.load(open(tp)).get("viterbi_kernel_dram_bytes_per_launch")
     cpu = run_reference_cpu(batches[0][0][:args.cpu_sample], os.cpu_count() or 1) if (world == 1 and not args.no_cpu) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "batch=%d synthetic Korean sentences (web.txt length dist) per GPU per step, fabricated Knlm model (knlm_small), top-1" % args.batch,
+        "config": {"workload": "batch=%d synthetic Korean sentences (web.txt length dist) per GPU per step, fabricated %s model (%s_small), top-1" % (args.batch, "Knlm" if MODEL == "knlm" else "CoNg", MODEL),
                    "l2": "per-step scratch working set (GBs) exceeds the 126 MB L2 and %d distinct input batches rotate; the read-only model stays resident as in steady state" % R,
                    "parallelism": "dp%d (sentence sharding, one NCCL broadcast of the model image at init, no steady-state collectives)" % world,
                    "wall_ms_per_step": 1000.0 * wall / args.steps,
@@ -227,6 +242,13 @@ def main():
         "tokens_per_step": tokens // args.steps,
     }
     if cpu: line["cpu_baseline"] = cpu
+    if MODEL == "cong":
+        # the int8 gather GEMMs of progressMatrix: 2 * sum(m * n * dim) integer ops per sentence (counted by the instrumented oracle)
+        ops = 2.0 * c.get("cgMacs", 0) / max(1, c["sentences"])
+        line["roofline"]["kernel"] = "viterbi_cong_kernel"
+        line["roofline"]["tensor"] = {"bound": "tensor", "unit": "TOP/s", "achieved": ops * args.batch / (vit_per_launch_ms / 1000.0) / 1e12, "peak": 4500.0,
+                                      "peak_kind": "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)", "int8_ops_per_sentence": ops,
+                                      "note": "the gather GEMMs are a small part of viterbi_cong_kernel's time; the kernel as a whole is latency / HBM-L2 bound like the Knlm one"}
     print(json.dumps(line))
     if dist: dist.destroy_process_group()
     return 0
