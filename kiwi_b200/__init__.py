@@ -65,10 +65,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("KIWI_B200_LIB", LIB_PATH)      # kernel experiments: another build of the same library
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(kiwi_b200 has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.kiwi_version.restype = C.c_char_p
     lib.kiwi_error.restype = C.c_char_p
     lib.kiwi_init.restype = C.c_void_p

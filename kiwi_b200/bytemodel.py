@@ -18,5 +18,12 @@ def viterbi_bytes(c: dict, kn_key_bytes: int = 4) -> float:
             + 40 * c["pathsWritten"] + 40 * c["pairs"] + 15 * c["tokens"])
 
 
+def cong_bytes(c: dict, dim: int = 128) -> float:
+    """CoNg scorer on top of the lattice/Viterbi record traffic: gathered embedding rows (context row dim + 16 B,
+    output row dim + 8 B in the reference, src/CoNgramModel.hpp:89-105; both dim + 8 here) and context-trie hops
+    (node 16 B + key/value packet; lmHops / lmProbes count the CoNg trie when the oracle runs a CoNg image)."""
+    return c.get("cgRows", 0) * (dim + 12)
+
+
 def total_bytes(c: dict) -> float:
     return lattice_bytes(c) + viterbi_bytes(c)

@@ -60,8 +60,19 @@ namespace KB_VIT_NS
 	static constexpr unsigned FULL = 0xFFFFFFFFu;
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
 	static constexpr uint8_t COMMON_ROOT = 0xFF;
-	static constexpr uint32_t HT_SIZE = 1024, HT_MAX_ENTRIES = 768;
-	static constexpr uint32_t STAGE_CAP = 512, ITEM_CAP = 512, GROUP = 32;
+	// Staging capacity of the item pipeline.  Containers of <= 512 incoming paths are the reference's top1Small / top1Medium
+	// modes; with KB_STAGE_CAP > 512 the unbounded `top1` mode (> 512 incoming paths, insertion order, no bucket capacity)
+	// also goes through the pipeline up to that many incoming paths - these nodes dominate the heaviest sentences of a
+	// batch, and the kernel time is the time of its heaviest sentence.
+#ifndef KB_STAGE_CAP
+#define KB_STAGE_CAP (KB_CONG ? 512 : 1536)
+#endif
+#ifndef KB_HT_SIZE
+#define KB_HT_SIZE (KB_CONG ? 1024 : 2048)
+#endif
+	static constexpr uint32_t HT_SIZE = KB_HT_SIZE, HT_MAX_ENTRIES = KB_HT_SIZE * 3 / 4;
+	static constexpr uint32_t STAGE_CAP = KB_STAGE_CAP, ITEM_CAP = 512, GROUP = 32;
+	static_assert(STAGE_CAP % 512 == 0 && STAGE_CAP <= HT_MAX_ENTRIES * 2 && (HT_SIZE & (HT_SIZE - 1)) == 0, "staging / index capacities");
 
 	// static + per-node data of one candidate morpheme, written lane-parallel (lane = candidate) into shared memory
 	struct alignas(8) CandS
@@ -898,7 +909,7 @@ namespace KB_VIT_NS
 						idx = nClasses++;
 						if (lane == idx) myTab = v;
 						if (lane == 0) sm->fclass[idx] = v;
-						if (lane < STAGE_CAP / 32) sm->classBits[idx][lane] = 0;
+						for (uint32_t w = lane; w < STAGE_CAP / 32; w += 32) sm->classBits[idx][w] = 0;
 						if (v & FW_COMMON_ROOT) classCommon |= 1u << idx;
 						__syncwarp();
 					}
@@ -924,7 +935,7 @@ namespace KB_VIT_NS
 				const uint32_t i = ib + lane;
 				const bool valid = i < nItems;
 				uint32_t slot = 0, q = 0, r = 0, fwIdx = 0; bool condFail = false, spacePen = false;
-				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 511; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
+				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 0x1FFFF; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
 				const CandS cs = sm->cand[slot];
 				int32_t lmState = 0; float accScore = 0, fcs = 0; uint32_t prevRoot = 0; uint8_t spState = 0, rootId = COMMON_ROOT;
 				bool bad = false;
@@ -1073,7 +1084,7 @@ namespace KB_VIT_NS
 			{
 				const uint32_t cnt = lane < gcount ? sm->candNew[lane] : 0;
 				const uint8_t cls = lane < gcount ? sm->cand[lane].cls : CLS_SKIP;
-				need = cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);
+				need = mode != 2 && cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);     // the top1 container has neither buckets nor a capacity
 			}
 			if (!__any_sync(FULL, need)) return;
 			uint32_t w = groupBase, r = groupBase;
@@ -1083,7 +1094,7 @@ namespace KB_VIT_NS
 			{
 				const uint32_t cnt = sm->candNew[k];
 				if (!cnt) continue;
-				const bool fix = sm->cand[k].cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);
+				const bool fix = mode != 2 && sm->cand[k].cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);
 				if (!fix)
 				{
 					if (w != r)
@@ -1285,7 +1296,7 @@ namespace KB_VIT_NS
 			if (err) return;
 			const uint32_t nCands = cgn.nOrdered;
 #else
-			const bool itemOK = mode <= 1;
+			const bool itemOK = P <= STAGE_CAP;          // modes 0 / 1 always; mode 2 (top1) up to the staging capacity
 			const uint32_t nCands = nCandsIn;
 #endif
 			FlushCtx fc;
@@ -1352,7 +1363,8 @@ namespace KB_VIT_NS
 									const bool socketChunk = cur.combine_socket && !single;
 									const DMorphX mx = c_m.morphx[curId];
 									const bool noLm = cur.combine_socket && single;
-									if (!itemOK2 || (mode == 1 && fork)) cls = CLS_GENERAL;
+									// a forking candidate creates up to 2 entries per path; medium-mode forks keep the bucket-aware general path
+									if (!itemOK2 || (mode == 1 && fork) || (mode == 2 && (fork ? 2 * P : P) > HT_MAX_ENTRIES)) cls = CLS_GENERAL;
 									else if (!noLm && !socketChunk && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) cls = CLS_SKIP;     // every pair hits `goto continueFor`
 									else if (socketChunk && (mx.xflags & MX_CHUNK_HAS_P)) cls = CLS_SKIP;
 									else cls = CLS_ITEM;
@@ -1441,35 +1453,42 @@ namespace KB_VIT_NS
 							const uint32_t vmK = __shfl_sync(FULL, myValid, k), cfK = __shfl_sync(FULL, myCondFail, k), setsK = __shfl_sync(FULL, mySets, k);
 							const uint32_t kfl = __shfl_sync(FULL, myFlags, k);
 							if (!(vmK | setsK)) continue;
-							if (htCount + nItems > 256) { flushItems(fc); if (err) return; resetIndex(); }
+							// the entry index is shared by consecutive candidates while it is small; a top1-mode candidate (up to P entries) starts with an empty one
+							if (mode == 2 ? (htCount | nItems) != 0 : htCount + nItems > 256) { flushItems(fc); if (err) return; resetIndex(); }
 							if (!(kfl & CS_FORK) && !setsK)
 							{
-								// common case: survivors = union of the path bitmaps of the valid classes, enumerated in path order
-								const uint32_t nW = (P + 31) >> 5;
-								uint32_t bits = 0;
-								if (lane < nW) { uint32_t mm = vmK; while (mm) { const uint32_t c = __ffs(mm) - 1; bits |= sm->classBits[c][lane]; mm &= mm - 1; } }
-								const uint32_t cnt = __popc(bits);
-								uint32_t incl = cnt;
-								if (nW > 1) { for (int d = 1; d < 16; d <<= 1) { const uint32_t tt = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += tt; } }
-								const uint32_t S = __shfl_sync(FULL, incl, nW - 1);
-								if (!S) continue;
-								if (nItems + S > ITEM_CAP) { flushItems(fc); if (err) return; }
-								const uint32_t excl = incl - cnt;
+								// common case: survivors = union of the path bitmaps of the valid classes, enumerated in path order,
+								// 512 paths (16 bitmap words = one item buffer) at a time
+								const uint32_t nWtot = (P + 31) >> 5;
 								#pragma unroll 1
-								for (uint32_t wd = 0; wd < nW; ++wd)
+								for (uint32_t wt = 0; wt < nWtot; wt += 16)
 								{
-									const uint32_t wb = __shfl_sync(FULL, bits, wd);
-									if (!wb) continue;
-									const uint32_t base = __shfl_sync(FULL, excl, wd);
-									if ((wb >> lane) & 1)
+									const uint32_t nW = min(16u, nWtot - wt);
+									uint32_t bits = 0;
+									if (lane < nW) { uint32_t mm = vmK; while (mm) { const uint32_t c = __ffs(mm) - 1; bits |= sm->classBits[c][wt + lane]; mm &= mm - 1; } }
+									const uint32_t cnt = __popc(bits);
+									uint32_t incl = cnt;
+									if (nW > 1) { for (int d = 1; d < 16; d <<= 1) { const uint32_t tt = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += tt; } }
+									const uint32_t S = __shfl_sync(FULL, incl, nW - 1);
+									if (!S) continue;
+									if (nItems + S > ITEM_CAP) { flushItems(fc); if (err) return; }
+									const uint32_t excl = incl - cnt;
+									#pragma unroll 1
+									for (uint32_t wd = 0; wd < nW; ++wd)
 									{
-										const uint32_t q = (wd << 5) | lane;
-										const uint32_t c = sm->pcls[q];
-										sm->item[nItems + base + __popc(wb & ((1u << lane) - 1))] = (k << 27) | (q << 3) | ((cfK >> c) & 1);
+										const uint32_t wb = __shfl_sync(FULL, bits, wd);
+										if (!wb) continue;
+										const uint32_t base = __shfl_sync(FULL, excl, wd);
+										if ((wb >> lane) & 1)
+										{
+											const uint32_t q = ((wt + wd) << 5) | lane;
+											const uint32_t c = sm->pcls[q];
+											sm->item[nItems + base + __popc(wb & ((1u << lane) - 1))] = (k << 27) | (q << 3) | ((cfK >> c) & 1);
+										}
 									}
+									nItems += S;
+									__syncwarp();
 								}
-								nItems += S;
-								__syncwarp();
 								continue;
 							}
 							// filter pass (PathEvaluator.hpp:566-594): lanes = (path, root) pairs in order; the per-pair work is a
