@@ -924,7 +924,13 @@ namespace KB_VIT_NS
 			__syncwarp();
 		}
 
-		struct FlushCtx { uint32_t nodeIdx; uint32_t inBeg; float ignoreCondScore; float nodeTypoCost; uint32_t ownOff, ownLen; uint16_t ownLeftLast; uint8_t ownLeftPol; };
+		struct FlushCtx
+		{
+			uint32_t nodeIdx; uint32_t inBeg; float ignoreCondScore; float nodeTypoCost; uint32_t ownOff, ownLen; uint16_t ownLeftLast; uint8_t ownLeftPol;
+#if KB_CONG
+			uint32_t epFirst, dotMask;      // epilogue of the node's gather GEMM; candidates of the current group that have a column in sm->dots
+#endif
+		};
 
 		__device__ __noinline__ void flushItems(const FlushCtx& fc)
 		{
@@ -938,6 +944,9 @@ namespace KB_VIT_NS
 				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 0x1FFFF; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
 				const CandS cs = sm->cand[slot];
 				int32_t lmState = 0; float accScore = 0, fcs = 0; uint32_t prevRoot = 0; uint8_t spState = 0, rootId = COMMON_ROOT;
+#if KB_CONG
+				uint32_t ctxIdx = 0;
+#endif
 				bool bad = false;
 				if (valid)
 				{
@@ -949,9 +958,16 @@ namespace KB_VIT_NS
 					float candScore = pp->acc_score + cs.additionalScore;
 					float firstChunkScore = cs.additionalScore;
 					if (spacePen) candScore -= c_m.cfg.space_penalty;
+#if KB_CONG
+					// regular candidates: FormEvaluator's soft penalty comes after `acc + morphScore + lm` (CoNgramModel.cpp:175-179)
+					const bool cgRegular = !(cs.flags & (CS_NO_LM | CS_SOCKET_CHUNK));
+					if (condFail && !cgRegular) candScore += fc.ignoreCondScore;
+					ctxIdx = P_CTX(*pp);
+#else
 					if (condFail) candScore += fc.ignoreCondScore;
+#endif
 					lmState = pp->lm_state;
-					const uint32_t pf = pp->wid_feat;
+					const uint32_t pf = P_WID_FEAT(*pp);
 					const uint32_t firstWid = fwIdx ? sm->fwTab[fwIdx] : cs.firstWid;
 					bad = firstWid >= c_m.n_morphs || slot >= GROUP || fc.inBeg + q >= poolCap;
 					if (bad)
@@ -963,6 +979,27 @@ namespace KB_VIT_NS
 						}
 					}
 					else
+#if KB_CONG
+					if (!(cs.flags & CS_NO_LM))
+					{
+						float ll;
+						if (cgRegular)
+						{
+							const uint32_t ps = q < STAGE_CAP ? sm->pslot[q] : 0xFFu;
+							const int32_t x = (((fc.dotMask >> slot) & 1u) && ps != 0xFFu) ? sm->dots[ps][slot] : cgDot(ctxIdx, firstWid);
+							ll = cgFinish(x, ctxIdx, firstWid, fc.epFirst);
+							ctxIdx = cgStep(lmState, firstWid);
+						}
+						else ll = cgNext(lmState, ctxIdx, firstWid);
+						candScore += ll; firstChunkScore += ll;
+						if (condFail && cgRegular) candScore += fc.ignoreCondScore;
+						if (!(cs.flags & CS_SINGLE))
+						{
+							#pragma unroll 1
+							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = cgNext(lmState, ctxIdx, c_m.chunk_lm[cs.chunkOff + c]); candScore += ll; }
+						}
+					}
+#else
 					if (!(cs.flags & CS_NO_LM))
 					{
 						float ll = knProgress(lmState, firstWid, 1);
@@ -973,6 +1010,7 @@ namespace KB_VIT_NS
 							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = knProgress(lmState, c_m.chunk_lm[cs.chunkOff + c], 2); candScore += ll; }
 						}
 					}
+#endif
 					// RuleBasedScorer::operator() + special-state update (PathEvaluator.hpp:115-183, 208-230)
 					const uint32_t ptag = pf & MF_TAG_MASK;
 					const uint32_t specialType = (cs.feat >> MF_SPECIAL_SHIFT) & 7, sbType = (cs.feat >> MF_SBTYPE_SHIFT) & 31, sbOrder = sbType ? cs.senseId : 0;
@@ -1060,7 +1098,12 @@ namespace KB_VIT_NS
 						np.left_last = own ? fc.ownLeftLast : cs.leftLast;
 						np.left_pol = own ? (uint8_t)(fc.ownLeftPol | (cs.leftPol & LP_MORPH_SOCKET)) : cs.leftPol;
 						np.sp_state = spState; np.root_id = rootId != COMMON_ROOT ? rootId : (uint8_t)prevRoot; np.combine_socket = cs.pathSocket; np.prev_root_id = (uint8_t)prevRoot;
-						np.morph_tag = (uint8_t)(cs.feat & MF_TAG_MASK); np.wid_feat = cs.lastSeqFeat;
+						np.morph_tag = (uint8_t)(cs.feat & MF_TAG_MASK);
+#if KB_CONG
+						P_CTX(np) = ctxIdx;
+#else
+						np.wid_feat = cs.lastSeqFeat;
+#endif
 						pool[htBase + tgt] = np;
 					}
 				}
@@ -1126,7 +1169,11 @@ namespace KB_VIT_NS
 					for (uint32_t e = 0; e < cnt; e += 32)
 					{
 						DPath p; bool ok = e + lane < cnt;
+#if KB_CONG
+						if (ok) { p = pool[tmp + e + lane]; if (mode == 1) ok = ((p.sp_state ^ ((0u - (uint32_t)p.lm_state) >> 5)) & 3) == b; }
+#else
 						if (ok) { p = pool[tmp + e + lane]; if (mode == 1) ok = ((p.sp_state ^ ((uint32_t)p.lm_state >> 5)) & 3) == b; }
+#endif
 						const unsigned bm = __ballot_sync(FULL, ok);
 						const uint32_t pos = inBucket + __popc(bm & ((1u << lane) - 1));
 						if (ok && pos < 128) pool[w + kept + pos] = p;
@@ -1291,7 +1338,10 @@ namespace KB_VIT_NS
 			const bool spaceBefore = nodes[nodeIdx - node.prev].end_pos < node.start_pos;
 			const bool hasLB = hasLeftBoundary(nodeIdx);
 #if KB_CONG
-			const bool itemOK = false;           // every candidate goes through evalCand, in the transposed evaluator's order
+#ifndef KB_CONG_PIPELINE
+#define KB_CONG_PIPELINE 1
+#endif
+			const bool itemOK = KB_CONG_PIPELINE && P <= STAGE_CAP;      // else every candidate goes through evalCand; always in the transposed evaluator's order
 			const CongNode cgn = congPrepare(node, spaceBefore, candList, nCandsIn, unk0, unk1, inBeg, P);
 			if (err) return;
 			const uint32_t nCands = cgn.nOrdered;
@@ -1399,7 +1449,14 @@ namespace KB_VIT_NS
 								const uint32_t f = sm->fclass[c];
 								const uint32_t socket = f >> FW_SOCKET_SHIFT;
 								bool valid = true;
+#if KB_CONG
+								// the z_siot test exists only in the regular-candidate loop, and right halves only see combining paths
+								// (CoNgramModel.cpp:184-189, 208-246, 248-286)
+								if ((f & FW_ZSIOT) && curSocket == 0 && (!curNN || spaceBefore)) valid = false;
+								else if (socketChunk && !socket) valid = false;
+#else
 								if ((f & FW_ZSIOT) && (!curNN || spaceBefore)) valid = false;
+#endif
 								else if (socket)
 								{
 									// merge <v> <chunk> with only the same socket (PathEvaluator.hpp:578-591)
@@ -1430,12 +1487,13 @@ namespace KB_VIT_NS
 					uint32_t dotMask = 0;
 					{
 						const CandS csl = sm->cand[lane];
-						const bool regular = lane < gcount && csl.cls == CLS_GENERAL && c_m.morphs[csl.curId].combine_socket == 0 && !(c_m.morphx[csl.curId].xflags & MX_FIRST_IS_P);
+						const bool regular = lane < gcount && (csl.cls == CLS_GENERAL || csl.cls == CLS_ITEM) && c_m.morphs[csl.curId].combine_socket == 0 && !(c_m.morphx[csl.curId].xflags & MX_FIRST_IS_P);
 						sm->colWid[lane] = csl.firstWid;
 						dotMask = __ballot_sync(FULL, regular);
 						__syncwarp();
 						if (dotMask && cgn.nU && cgn.epFirst != CG_E_SCALAR) congGroupDots(cgn.nU, dotMask);
 						else dotMask = 0;
+						fc.epFirst = cgn.epFirst; fc.dotMask = dotMask;
 					}
 #endif
 					const uint32_t groupBase = top;

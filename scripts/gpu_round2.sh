@@ -7,10 +7,12 @@ echo "pytest rc=$?" >> gpurun_out/pytest.log
 for v in s512 s1024 s1536b3; do
   ( KIWI_B200_LIB=kiwi_b200/variants/libkiwi_b200_$v.so timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu ) > gpurun_out/bench_knlm_$v.json 2> gpurun_out/bench_knlm_$v.err
 done
+( timeout 150 python bench.py --model cong --steps 10 --warmup 3 --cpu-sample 8192 ) > gpurun_out/bench_cong.json 2> gpurun_out/bench_cong.err
+( KIWI_B200_LIB=kiwi_b200/variants/libkiwi_b200_cgnopipe.so timeout 120 python bench.py --model cong --steps 10 --warmup 3 --no-cpu ) > gpurun_out/bench_cong_cgnopipe.json 2> gpurun_out/bench_cong_cgnopipe.err
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv --log-file gpurun_out/r1b_launches_cong.csv python bench.py --model cong --steps 3 --warmup 2 --no-cpu > gpurun_out/ncu_l.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:viterbi_cong_kernel -s 1 -c 1 -o gpurun_out/r1b_viterbi_cong python bench.py --model cong --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_f.log 2>&1
 tail -n 6 gpurun_out/pytest.log
-for f in gpurun_out/bench_knlm.json gpurun_out/bench_knlm_s512.json gpurun_out/bench_knlm_s1024.json gpurun_out/bench_knlm_s1536b3.json; do echo $f; python - "$f" <<'PY'
+for f in gpurun_out/bench_knlm.json gpurun_out/bench_knlm_s512.json gpurun_out/bench_knlm_s1024.json gpurun_out/bench_knlm_s1536b3.json gpurun_out/bench_cong.json gpurun_out/bench_cong_cgnopipe.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 for l in open(sys.argv[1]):
     if l.startswith("{"):
