@@ -148,7 +148,9 @@ int kiwi_b200_debug_lattice(kiwi_h handle, const kchar16_t* text, int len, int32
  * the tensor-core tile (mma.sync m16n8k32 u8 x s8) over the first contexts x first output ids. */
 int kiwi_b200_debug_cong(kiwi_h handle, int n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
 	int32_t* out_dot, float* out_eps, int32_t* out_node, uint32_t* out_ctx, int32_t* out_tile);
-int kiwi_b200_model_type(kiwi_h handle);         /* (int)ModelType of the loaded image: 2 knlm, 4 cong */
+int kiwi_b200_model_type(kiwi_h handle);
+/* Diagnostics: {start, end} of every sentence's Viterbi in the last batch launch, %globaltimer ns, out[2 * n]. */
+int kiwi_b200_debug_timing(kiwi_h handle, int n, uint64_t* out_start_end_ns);         /* (int)ModelType of the loaded image: 2 knlm, 4 cong */
 
 int kiwi_b200_device_count(void);
 int kiwi_b200_set_device(int device);            /* call before kiwi_init; default: current device */

@@ -86,6 +86,7 @@ def load_library() -> C.CDLL:
     lib.kiwi_b200_debug_lattice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, AnalyzeOption]
     lib.kiwi_b200_debug_cong.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
     lib.kiwi_b200_model_type.argtypes = [C.c_void_p]
+    lib.kiwi_b200_debug_timing.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.kiwi_b200_set_device.argtypes = [C.c_int]
     lib.kiwi_b200_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.kiwi_b200_free.argtypes = [C.c_void_p]
@@ -245,3 +246,10 @@ class Kiwi:
         if rc != 0:
             raise KiwiError(_last_error(self._lib))
         return dict(dot=dot, eps=eps, node=onode, ctx=octx, tile=tile)
+
+    def debug_timing(self, n: int) -> np.ndarray:
+        """{start, end} ns (%globaltimer) of every sentence's Viterbi in the last batch launch -> uint64[n, 2]"""
+        out = np.zeros((n, 2), np.uint64)
+        if self._lib.kiwi_b200_debug_timing(self._h, n, out.ctypes.data) != 0:
+            raise KiwiError(_last_error(self._lib))
+        return out

@@ -390,6 +390,18 @@ int kiwi_b200_debug_cong(kiwi_h handle, int n, const uint32_t* ctx, const uint32
 	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
 }
 
+int kiwi_b200_debug_timing(kiwi_h handle, int n, uint64_t* out_start_end_ns)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	try
+	{
+		std::lock_guard<std::mutex> lk(handle->mtx);
+		handle->engine->debugTiming((uint32_t)n, reinterpret_cast<unsigned long long*>(out_start_end_ns));
+		return 0;
+	}
+	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+
 int kiwi_b200_model_type(kiwi_h handle)
 {
 	if (!handle) return KIWIERR_INVALID_HANDLE;

@@ -115,6 +115,7 @@ namespace kb
 		vv.n_tokens = (uint32_t*)alloc((capB + 1) * 4);
 		vv.best_rec = (int32_t*)alloc(capB * 4);
 		vv.score = (float*)alloc(capB * 4);
+		vv.timing = (unsigned long long*)alloc(capB * 16);
 		sc.tokOff = (uint32_t*)alloc((capB + 1) * 4);
 		sc.packed = (DToken*)alloc(capU * sizeof(DToken));
 		sc.dText = (uint16_t*)alloc(capT * 2 + 64);
@@ -405,6 +406,12 @@ namespace kb
 		if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
 		cudaFree(d);
 		ck(e, "debugCong");
+	}
+
+	void Engine::debugTiming(uint32_t n, unsigned long long* out)
+	{
+		if (!main_.vv.timing || n > main_.capSent) throw std::runtime_error("debugTiming: no launch of that size yet");
+		ck(cudaMemcpy(out, main_.vv.timing, (size_t)n * 16, cudaMemcpyDeviceToHost), "debugTiming");
 	}
 
 	int Engine::debugLattice(const uint16_t* text, uint32_t len, uint32_t matchOptions, std::vector<int32_t>& rows)

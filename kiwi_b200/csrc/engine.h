@@ -56,6 +56,8 @@ namespace kb
 		float analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens);
 		// lattice of one sentence for stage-level parity tests
 		int debugLattice(const uint16_t* text, uint32_t len, uint32_t matchOptions, std::vector<int32_t>& rows);
+		// per-sentence {start, end} ns of the last Viterbi launch of the main scratch (diagnostics)
+		void debugTiming(uint32_t n, unsigned long long* out);
 		// CoNg scorer self-test on the device (see cong_debug_kernel): n triples in, per-triple results + the tensor-core tile out
 		void debugCong(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
 			int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile);

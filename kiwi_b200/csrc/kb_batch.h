@@ -59,6 +59,7 @@ namespace kb
 		uint32_t* n_tokens;          // [n_sent]
 		int32_t* best_rec;           // [n_sent] record of the best stitched result, -1 = none
 		float* score;                // [n_sent]
+		unsigned long long* timing;  // [2 * n_sent] %globaltimer at the start / end of every sentence's Viterbi (diagnostics: the kernel time is its slowest sentence)
 	};
 
 	enum : uint32_t { ST_OK = 0, ST_NODE_OVERFLOW = 1, ST_CHUNK_OVERFLOW = 2, ST_PATH_OVERFLOW = 3, ST_TOKEN_OVERFLOW = 4, ST_TOO_LONG = 5, ST_INTERNAL = 6 };

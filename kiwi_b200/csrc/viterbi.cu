@@ -2017,12 +2017,17 @@ namespace KB_VIT_NS
 	#ifndef KB_VIT_MIN_BLOCKS
 #define KB_VIT_MIN_BLOCKS 4
 #endif
+#ifndef KB_SOLO
+#define KB_SOLO 0
+#endif
 	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) KB_VIT_KERNEL(const BatchView bv, const VitView vv)
 	{
 		extern __shared__ __align__(16) unsigned char smRaw[];
 		WarpSmem* smAll = reinterpret_cast<WarpSmem*>(smRaw);
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-		const uint32_t slot = blockIdx.x * WARPS_PER_BLOCK + wib;
+		// The first KB_SOLO blocks (the longest sentences in LPT order) hold ONE sentence each: the kernel time is the time of
+		// its heaviest sentence, and alone in its block that sentence never waits at the lockstep barrier for a block mate.
+		const uint32_t slot = blockIdx.x < KB_SOLO ? (wib == 0 ? blockIdx.x : 0xFFFFFFFFu) : KB_SOLO + (blockIdx.x - KB_SOLO) * WARPS_PER_BLOCK + wib;
 #ifdef KB_LOCKSTEP
 		__shared__ uint32_t sActiveCount;
 		if (threadIdx.x == 0) sActiveCount = 0;
@@ -2040,6 +2045,7 @@ namespace KB_VIT_NS
 		if (bv.status[s]) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
 #endif
 
+		if (lane == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s] = tns; }
 		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
 		const uint32_t n = t1 - t0;
 		const uint32_t W = 2 * n + 4;
@@ -2159,6 +2165,7 @@ namespace KB_VIT_NS
 		__syncwarp();
 		asm volatile("bar.arrive 1, %0;" :: "r"(v.roundCnt) : "memory");
 #endif
+		if (lane == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s + 1] = tns; }
 		if (lane == 0)
 		{
 			vv.best_rec[s] = (!v.err && retN) ? retRec[0] : -1;
@@ -2222,7 +2229,7 @@ namespace KB_VIT_NS
 	cudaError_t KB_LAUNCH(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
-		const uint32_t blocks = (bv.n_sent + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+		const uint32_t blocks = bv.n_sent <= KB_SOLO ? bv.n_sent : KB_SOLO + (bv.n_sent - KB_SOLO + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 		static bool attrSet = false;
 		const size_t smemBytes = sizeof(WarpSmem) * WARPS_PER_BLOCK;
 		if (!attrSet) { cudaFuncSetAttribute(KB_VIT_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); attrSet = true; }

@@ -12,7 +12,7 @@
 //   N <formIdx|-1> <uformOff|-1> <uformLen> <prev> <sibling> <startPos> <endPos> <spaceErrors> <typoCost>   x nNodes
 //   P <score> <prevState> <curState> <nTok>
 //   K <morphId> <begin> <end> <wordScore> <nodeId> <hasStr>                x nTok
-// The model type follows the environment variable KB_MODEL_TYPE (knlm, default, or cong).
+// The model type follows the environment variable KB_MODEL_TYPE (knlm, default, cong or sbg).
 // usage: dump_golden <model_dir> <input.txt> <out.txt> [maxLines]
 #include <cstdio>
 #include <cstdlib>
@@ -33,7 +33,7 @@ int main(int argc, char** argv)
 	try
 	{
 		const char* mt = getenv("KB_MODEL_TYPE");
-		KiwiBuilder kb{ argv[1], 1, BuildOption::default_, (mt && std::string{ mt } == "cong") ? ModelType::cong : ModelType::knlm };
+		KiwiBuilder kb{ argv[1], 1, BuildOption::default_, (mt && std::string{ mt } == "cong") ? ModelType::cong : (mt && std::string{ mt } == "sbg") ? ModelType::sbg : ModelType::knlm };
 		Kiwi kw = kb.build();
 		std::ifstream ifs{ argv[2] };
 		FILE* fo = std::fopen(argv[3], "w");

@@ -22,8 +22,8 @@ int main(int argc, char** argv)
 	const size_t maxLines = argc > 5 ? std::stoul(argv[5]) : (size_t)-1;
 	try
 	{
-		const char* mt = getenv("KB_MODEL_TYPE");      // knlm (default) or cong
-		KiwiBuilder kb{ argv[1], threads <= 1 ? 0 : threads, BuildOption::default_, (mt && std::string{ mt } == "cong") ? ModelType::cong : ModelType::knlm };
+		const char* mt = getenv("KB_MODEL_TYPE");      // knlm (default), cong or sbg
+		KiwiBuilder kb{ argv[1], threads <= 1 ? 0 : threads, BuildOption::default_, (mt && std::string{ mt } == "cong") ? ModelType::cong : (mt && std::string{ mt } == "sbg") ? ModelType::sbg : ModelType::knlm };
 		Kiwi kw = kb.build();
 		std::vector<std::u16string> lines;
 		{
