@@ -20,7 +20,7 @@ extern "C" {
 #endif
 
 #define KB2_IMAGE_MAGIC   0x31474D4932424Bull /* "KB2IMG1" */
-#define KB2_IMAGE_VERSION 5u
+#define KB2_IMAGE_VERSION 6u
 #define KB2_POSTAG_MAX    64                  /* >= (int)POSTag::max of the reference (Types.h:195-227) */
 
 /* section ids */
@@ -48,6 +48,12 @@ enum kb2_section_id {
 	KB2_SEC_CG_OUT_EMB,       /* rows: int8[dim], float scale, int32 hsum (= 128 * sum)            */
 	KB2_SEC_CG_INV_VOCAB,     /* uint32_t[vocab] invertedContextVocab (may be empty)               */
 	KB2_SEC_CG_OUT_BIAS,      /* float[vocab] outputEmbBias (may be empty)                         */
+	/* SkipBigram model on top of the Knlm sections (empty otherwise), src/SkipBigramModel.hpp:24-32 */
+	KB2_SEC_SB_PTRS,          /* uint32_t[vocab + 1]  key range of every target token              */
+	KB2_SEC_SB_KEYS,          /* uint32_t[]  history tokens, ascending inside each target          */
+	KB2_SEC_SB_COMPS,         /* float[]     compensation(target | history), parallel to SB_KEYS   */
+	KB2_SEC_SB_DISCNTS,       /* float[vocab]                                                      */
+	KB2_SEC_SB_VALID,         /* uint8_t[vocab] vocabValidness                                     */
 	KB2_SEC_COUNT
 };
 
@@ -133,7 +139,7 @@ typedef struct kb2_config {   /* KiwiConfig defaults, include/kiwi/Kiwi.h:150-16
 typedef struct kb2_header {
 	uint64_t magic;
 	uint32_t version;
-	uint32_t model_type;          /* (int)ModelType of Types.h:307: knlm or cong     */
+	uint32_t model_type;          /* (int)ModelType of Types.h:307: knlm 2, sbg 3, cong 4 */
 	uint64_t total_bytes;
 	kb2_section sec[KB2_SEC_COUNT];
 	uint32_t n_trie_nodes, n_trie_edges, n_forms, n_morphs, n_chunks;
@@ -155,6 +161,8 @@ typedef struct kb2_header {
 	uint32_t cg_key_size;         /* 2: 16-bit keys, 3: 16-bit keys with surrogate pairs for ids >= tMax, 4: 32-bit keys */
 	uint32_t cg_flags;            /* CoNgramModelHeader::flags */
 	uint32_t cg_pad;
+	/* SkipBigram scalars (include/kiwi/SkipBigramModel.h:9-13); 0 for other images */
+	uint32_t sb_vocab_size, sb_window_size, sb_num_pairs, sb_pad;
 } kb2_header;
 
 #ifdef __cplusplus

@@ -10,7 +10,7 @@
 // from a second Kiwi built with ModelType::cong on ArchType::avx2 (the quantized CoNg model only exists for the
 // SIMD archs, src/ArchAvailable.h:50-66); its arch-specific key packets are read back through nst::extractKV
 // (src/search.h:94-110) and re-sorted ascending.
-// usage: flatten_model <model_dir> <out.img> [model_name] [knlm|cong]
+// usage: flatten_model <model_dir> <out.img> [model_name] [knlm|cong|sbg]
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -21,6 +21,7 @@
 #include <kiwi/Utils.h>
 #include "Knlm.hpp"
 #include "CoNgramModel.hpp"
+#include "SkipBigramModel.hpp"
 #include <algorithm>
 #include "../../../include/kiwi_b200_image.h"
 
@@ -119,13 +120,35 @@ static bool dumpCong(const lm::ILangModel* base, kb2_header& h, CongDump& d)
 	return true;
 }
 
+struct SbgDump { std::vector<uint32_t> ptrs, keys; std::vector<float> comps, discnts; std::vector<uint8_t> valid; };
+
+template<class KeyType>
+static const lm::ILangModel* dumpSbg(const lm::ILangModel* base, kb2_header& h, SbgDump& d)
+{
+	using Model = lm::SkipBigramModel<ArchType::balanced, KeyType, 8>;
+	auto* m = dynamic_cast<const Model*>(base);
+	if (!m) return nullptr;
+	const auto& hd = m->getHeader();
+	const size_t total = m->ptrs[hd.vocabSize];
+	for (size_t i = 0; i <= hd.vocabSize; ++i) d.ptrs.push_back((uint32_t)m->ptrs[i]);
+	for (size_t i = 0; i < total; ++i) { d.keys.push_back((uint32_t)m->keyData[i]); d.comps.push_back(m->compensations[i]); }
+	for (size_t i = 0; i < hd.vocabSize; ++i)
+	{
+		d.discnts.push_back(m->discnts[i]); d.valid.push_back(m->vocabValidness[i]);
+		for (size_t j = m->ptrs[i] + 1; j < m->ptrs[i + 1]; ++j) if (!(m->keyData[j - 1] < m->keyData[j])) throw std::runtime_error{ "sbg keys are not ascending" };
+	}
+	h.sb_vocab_size = (uint32_t)hd.vocabSize; h.sb_window_size = hd.windowSize; h.sb_num_pairs = (uint32_t)total;
+	return &m->knlm;
+}
+
 int main(int argc, char** argv)
 {
 	if (argc < 3) { std::cerr << "usage: flatten_model <model_dir> <out.img> [name]\n"; return 2; }
 	setenv("KIWI_ARCH_TYPE", "balanced", 1);
 	try
 	{
-		KiwiBuilder kb{ argv[1], 1, BuildOption::default_, ModelType::knlm };
+		const bool wantSbg = argc > 4 && std::string{ argv[4] } == "sbg";
+		KiwiBuilder kb{ argv[1], 1, BuildOption::default_, wantSbg ? ModelType::sbg : ModelType::knlm };
 		Kiwi kw = kb.build();
 
 		kb2_header h;
@@ -133,7 +156,8 @@ int main(int argc, char** argv)
 		h.magic = KB2_IMAGE_MAGIC;
 		h.version = KB2_IMAGE_VERSION;
 		const bool cong = argc > 4 && std::string{ argv[4] } == "cong";
-		h.model_type = (uint32_t)(cong ? ModelType::cong : ModelType::knlm);
+		const bool sbgModel = argc > 4 && std::string{ argv[4] } == "sbg";
+		h.model_type = (uint32_t)(cong ? ModelType::cong : sbgModel ? ModelType::sbg : ModelType::knlm);
 		std::strncpy(h.model_name, argc > 3 ? argv[3] : argv[1], sizeof(h.model_name) - 1);
 
 		// ---- form trie
@@ -224,6 +248,14 @@ int main(int argc, char** argv)
 		// ---- Knlm
 		std::vector<kb2_kn_node> knodes; std::vector<uint32_t> kkeys, khtx; std::vector<int32_t> kvals, kroot;
 		const auto* lmBase = kw.langMdl.get();
+		SbgDump sb;
+		if (sbgModel)
+		{
+			const lm::ILangModel* inner = dumpSbg<uint32_t>(lmBase, h, sb);
+			if (!inner) inner = dumpSbg<uint16_t>(lmBase, h, sb);
+			if (!inner) throw std::runtime_error{ "language model is not a balanced-arch SkipBigramModel (window 8)" };
+			lmBase = inner;
+		}
 		CongDump cg;
 		std::unique_ptr<Kiwi> kwCong;
 		if (cong)
@@ -301,6 +333,11 @@ int main(int argc, char** argv)
 		putSection(blob, h.sec[KB2_SEC_CG_OUT_EMB], cg.outEmb);
 		putSection(blob, h.sec[KB2_SEC_CG_INV_VOCAB], cg.invVocab);
 		putSection(blob, h.sec[KB2_SEC_CG_OUT_BIAS], cg.outBias);
+		putSection(blob, h.sec[KB2_SEC_SB_PTRS], sb.ptrs);
+		putSection(blob, h.sec[KB2_SEC_SB_KEYS], sb.keys);
+		putSection(blob, h.sec[KB2_SEC_SB_COMPS], sb.comps);
+		putSection(blob, h.sec[KB2_SEC_SB_DISCNTS], sb.discnts);
+		putSection(blob, h.sec[KB2_SEC_SB_VALID], sb.valid);
 		while (blob.size() % 256) blob.push_back(0);
 		h.total_bytes = blob.size();
 		std::memcpy(blob.data(), &h, sizeof(h));
@@ -311,7 +348,7 @@ int main(int argc, char** argv)
 			<< " edges " << kkeys.size() << " vocab " << h.lang_vocab_size << " htxVocab " << h.kn_htx_vocab
 			<< " bos " << h.kn_bos_node << " unk_ll " << h.kn_unk_ll
 			<< "; cong nodes " << h.cg_num_nodes << " edges " << h.cg_num_edges << " dim " << h.cg_dim << " contexts " << h.cg_context_size
-			<< " keySize " << h.cg_key_size << " flags " << h.cg_flags << std::endl;
+			<< " keySize " << h.cg_key_size << " flags " << h.cg_flags << "; sbg pairs " << h.sb_num_pairs << std::endl;
 	}
 	catch (const std::exception& e)
 	{

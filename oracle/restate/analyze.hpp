@@ -27,7 +27,7 @@ namespace orc
 		uint32_t matchOptions = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4) | (1u << 5) | (1u << 23) | (1u << 16);   // Match::allWithNormalizing
 		bool keepChunks = true;
 		WorkCounters work;
-		void enableWorkCounters() { splitter.wc = &work; viterbi.wc = &work; viterbi.lm.wc = &work; viterbi.cg.wc = &work; }
+		void enableWorkCounters() { splitter.wc = &work; viterbi.wc = &work; viterbi.lm.wc = &work; viterbi.cg.wc = &work; viterbi.sbgm.wc = &work; }
 
 		explicit Analyzer(const Image& _im) : im{ _im }, splitter{ _im }, viterbi{ _im }
 		{

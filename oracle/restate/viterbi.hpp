@@ -13,6 +13,7 @@
 #include "lattice.hpp"
 #include "knlm.hpp"
 #include "cong.hpp"
+#include "sbg.hpp"
 
 namespace orc
 {
@@ -22,6 +23,7 @@ namespace orc
 	{
 		int32_t lmState = 0;          // Knlm: node index.  CoNg: context-trie node (the only field state equality looks at)
 		uint32_t ctxIdx = 0;          // CoNg only: CoNgramState::contextIdx, carried along but not compared (CoNgramModel.hpp:491-494)
+		SbHist sb;                    // SkipBigram only: ring of the last valid tokens, part of the state's identity
 		uint8_t prevRootId = 0, spState = 0, rootId = 0;
 		int32_t morpheme = -1;
 		float accScore = 0, firstChunkScore = 0, accTypoCost = 0, accDialectCost = 0;
@@ -109,6 +111,8 @@ namespace orc
 		const Image& im;
 		Knlm lm;
 		Cong cg;
+		Sbg sbgm;
+		const bool sbg;                // model_type == ModelType::sbg: Knlm + SkipBigram (non-transposed evaluator, state = node + history ring)
 		const bool cong;               // model_type == ModelType::cong: transposed evaluation (PathEvaluator.hpp:837-1036, CoNgramModel.cpp:17-317)
 		kb2_config cfg;
 		Counters* cnt = nullptr;
@@ -122,7 +126,7 @@ namespace orc
 		std::vector<uint8_t> uniqStates;
 		bool splitSaisiot = false, mergeSaisiot = false, splitComplex = false;
 
-		explicit Viterbi(const Image& _im) : im{ _im }, lm{ _im }, cg{ _im }, cong{ _im.h->model_type == 4 }, cfg{ _im.h->config } {}
+		explicit Viterbi(const Image& _im) : im{ _im }, lm{ _im }, cg{ _im }, sbgm{ _im }, sbg{ _im.h->model_type == 3 }, cong{ _im.h->model_type == 4 }, cfg{ _im.h->config } {}
 
 		// --- small accessors
 		const kb2_morph& M(int32_t id) const { return im.morphs[id]; }
@@ -217,11 +221,15 @@ namespace orc
 		Container cont;
 
 		void contInsert(uint8_t prevRootId, uint8_t rootId, int32_t morph, float accScore, float firstChunkScore,
-			float accTypoCost, float accDialectCost, int32_t pNode, int32_t pIdx, uint8_t parentRootId, int32_t lmState, uint8_t spState, uint32_t ctxIdx = 0)
+			float accTypoCost, float accDialectCost, int32_t pNode, int32_t pIdx, uint8_t parentRootId, int32_t lmState, uint8_t spState, uint32_t ctxIdx = 0, const SbHist* sbh = nullptr)
 		{
 			if (cnt) cnt->inserts++;
 			if (wc) wc->pathsWritten++;
 			uint64_t h = (uint64_t)(int64_t)lmState;                                       // Knlm.hpp:1170-1178 std::hash<int32_t>
+			if (sbg && sbh)                                                                 // SkipBigramModel.hpp:188-203: history folded into the Knlm hash
+			{
+				for (int i = 0; i < 8; ++i) h = (uint64_t)sbh->hist[i] ^ ((h << 3) | (h >> 61));
+			}
 			if (cong)                                                                       // CoNgramModel.hpp:505-541 Hash<uint32_t>(state.node)
 			{
 				const uint64_t v = (uint32_t)lmState;
@@ -233,7 +241,7 @@ namespace orc
 			size_t it = 0;
 			for (; it < value.size(); ++it)
 			{
-				if (value[it].prevRootId == prevRootId && value[it].spState == spState && value[it].lmState == lmState) break;
+				if (value[it].prevRootId == prevRootId && value[it].spState == spState && value[it].lmState == lmState && (!(sbg && sbh) || value[it].sb == *sbh)) break;
 			}
 			if (it >= value.size())
 			{
@@ -242,6 +250,7 @@ namespace orc
 					WordLL w;
 					w.morpheme = morph; w.accScore = accScore; w.firstChunkScore = firstChunkScore; w.accTypoCost = accTypoCost;
 					w.accDialectCost = accDialectCost; w.parentNode = pNode; w.parentIdx = pIdx; w.lmState = lmState; w.spState = spState; w.ctxIdx = ctxIdx;
+					if (sbh) w.sb = *sbh;
 					w.rootId = parentRootId;
 					w.prevRootId = prevRootId;
 					if (rootId != commonRootId) w.rootId = rootId;
@@ -256,6 +265,7 @@ namespace orc
 				{
 					t.morpheme = morph; t.accScore = accScore; t.firstChunkScore = firstChunkScore; t.accTypoCost = accTypoCost;
 					t.accDialectCost = accDialectCost; t.parentNode = pNode; t.parentIdx = pIdx; t.lmState = lmState; t.spState = spState; t.ctxIdx = ctxIdx;
+					if (sbh) t.sb = *sbh;
 					t.rootId = parentRootId;
 					if (rootId != commonRootId) t.rootId = rootId;
 				}
@@ -264,7 +274,7 @@ namespace orc
 
 		// PathEvaluator.hpp:193-251
 		void insertToPathContainer(int32_t curId, int32_t lmState, float score, float firstChunkScore, const LNode* node,
-			const WordLL& prevPath, int32_t pNode, int32_t pIdx, const RuleScorer& rs, uint32_t ctxIdx = 0)
+			const WordLL& prevPath, int32_t pNode, int32_t pIdx, const RuleScorer& rs, uint32_t ctxIdx = 0, const SbHist* sbh = nullptr)
 		{
 			auto insert = [&](uint8_t rootId)
 			{
@@ -280,7 +290,7 @@ namespace orc
 				if (rs.sbType) spState = (spState & 3) | (uint8_t)(hashSbTypeOrder((uint8_t)rs.sbType, (uint8_t)(rs.sbOrder + 1)) << 2);
 				const float curDialectCost = 0.f;      // standard dialect only
 				contInsert(prevPath.rootId, rootId, curId, candScoreWithRule - curDialectCost, firstChunkScoreWithRule - curDialectCost,
-					prevPath.accTypoCost + node->typoCost, prevPath.accDialectCost + curDialectCost, pNode, pIdx, prevPath.rootId, lmState, spState, ctxIdx);
+					prevPath.accTypoCost + node->typoCost, prevPath.accDialectCost + curDialectCost, pNode, pIdx, prevPath.rootId, lmState, spState, ctxIdx, sbh);
 			};
 			const bool quote = rs.specialType == 0 || rs.specialType == 1 || rs.specialType == 3 || rs.specialType == 4;
 			if ((rs.sbType || quote) && prevPath.rootId == commonRootId)
@@ -291,6 +301,12 @@ namespace orc
 		}
 
 		float lmNext(int32_t& state, uint32_t wid) { if (cnt) cnt->lmSteps++; return lm.progress(state, wid); }
+		float lmNext(int32_t& state, SbHist& sbh, uint32_t wid)
+		{
+			if (!sbg) return lmNext(state, wid);
+			if (cnt) cnt->lmSteps++;
+			return sbgm.next(lm, state, sbh, wid);
+		}
 
 		// PathEvaluator.hpp:514-634
 		void evalSingleMorpheme(std::vector<WordLL>& resultOut, size_t nodeIdx, size_t ownFormId, int32_t curId,
@@ -355,11 +371,12 @@ namespace orc
 						}
 					}
 					int32_t cLmState = prevPath.lmState;
+					SbHist cSb = prevPath.sb;
 					if (cur.combine_socket && isSingle(cur)) {}
 					else
 					{
 						if (M((int32_t)firstWid).tag == T_p) continue;
-						float ll = lmNext(cLmState, firstWid);
+						float ll = lmNext(cLmState, cSb, firstWid);
 						candScore += ll;
 						firstChunkScore += ll;
 						if (!isSingle(cur))
@@ -369,13 +386,13 @@ namespace orc
 							{
 								const uint32_t wid = M((int32_t)im.chunks[cur.chunk_off + i].morph).lm_morpheme_id;
 								if (M((int32_t)wid).tag == T_p) { prohibited = true; break; }
-								ll = lmNext(cLmState, wid);
+								ll = lmNext(cLmState, cSb, wid);
 								candScore += ll;
 							}
 							if (prohibited) continue;
 						}
 					}
-					insertToPathContainer(curId, cLmState, candScore, firstChunkScore, node, prevPath, pNode, (int32_t)pi, rs);
+					insertToPathContainer(curId, cLmState, candScore, firstChunkScore, node, prevPath, pNode, (int32_t)pi, rs, 0, sbg ? &cSb : nullptr);
 				}
 			}
 			if (cnt) { size_t tot = 0; for (auto& b : cont.buckets) tot += b.size(); cnt->maxCont = std::max<uint64_t>(cnt->maxCont, tot); }
@@ -923,7 +940,8 @@ namespace orc
 					int32_t st = p.lmState; uint32_t stCtx = p.ctxIdx;
 					if (!openEnding)
 					{
-						c += (firstChunkScore = cong ? cg.next(st, stCtx, 1) : lmNext(st, 1));
+						SbHist stSb = p.sb;
+						c += (firstChunkScore = cong ? cg.next(st, stCtx, 1) : lmNext(st, stSb, 1));
 						if (p.spState & 1) c -= 2;
 						if (p.spState & 2) c -= 2;
 					}

@@ -30,6 +30,16 @@ def oracle_cong():
 
 
 @pytest.fixture(scope="session")
+def oracle_sbg():
+    from tests.orc import Oracle, SBG_IMAGE
+    if not os.path.exists(SBG_IMAGE):
+        pytest.skip("SkipBigram model image missing: run __graft_entry__.build() where /root/reference exists")
+    o = Oracle(SBG_IMAGE)
+    yield o
+    o.close()
+
+
+@pytest.fixture(scope="session")
 def kiwi_cong():
     import kiwi_b200
     from tests.orc import CONG_IMAGE

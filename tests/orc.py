@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
 IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "knlm_small.img")
 CONG_IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "cong_small.img")
+SBG_IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "sbg_small.img")
 
 
 class Oracle:

@@ -48,10 +48,10 @@ def test_no_cpu_fallback_without_gpu():
 def test_image_header_layout_is_stable():
     # the flatten tool (oracle side) and the loader (product side) share include/kiwi_b200_image.h only
     src = open(os.path.join(ROOT, "include", "kiwi_b200_image.h")).read()
-    assert "KB2_IMAGE_VERSION 5u" in src
+    assert "KB2_IMAGE_VERSION 6u" in src
     from tests.orc import IMAGE
     if os.path.exists(IMAGE):
         import struct
         with open(IMAGE, "rb") as f:
             magic, version = struct.unpack("<QI", f.read(12))
-        assert magic == 0x31474D4932424B and version == 5
+        assert magic == 0x31474D4932424B and version == 6
