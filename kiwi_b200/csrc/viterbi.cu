@@ -64,11 +64,20 @@ namespace KB_VIT_NS
 	// modes; with KB_STAGE_CAP > 512 the unbounded `top1` mode (> 512 incoming paths, insertion order, no bucket capacity)
 	// also goes through the pipeline up to that many incoming paths - these nodes dominate the heaviest sentences of a
 	// batch, and the kernel time is the time of its heaviest sentence.
+	// Measured (profiles/r1b_experiments.md): at 1536 the larger shared-memory footprint costs a resident block per SM and the
+	// kernel gets slower (134.7 k vs 161 k sentences/s), so the shipped default stays 512; the mode-2 pipeline is kept for a
+	// staging area outside shared memory.
+#ifndef KB_CG_UCAP
+#define KB_CG_UCAP 32
+#endif
+#ifndef KB_CG_CANDS
+#define KB_CG_CANDS 128
+#endif
 #ifndef KB_STAGE_CAP
-#define KB_STAGE_CAP (KB_CONG ? 512 : 1536)
+#define KB_STAGE_CAP 512
 #endif
 #ifndef KB_HT_SIZE
-#define KB_HT_SIZE (KB_CONG ? 1024 : 2048)
+#define KB_HT_SIZE 1024
 #endif
 	static constexpr uint32_t HT_SIZE = KB_HT_SIZE, HT_MAX_ENTRIES = KB_HT_SIZE * 3 / 4;
 	static constexpr uint32_t STAGE_CAP = KB_STAGE_CAP, ITEM_CAP = 512, GROUP = 32;
@@ -103,11 +112,11 @@ namespace KB_VIT_NS
 		uint32_t candNew[GROUP];                // entries created per candidate of the current group
 		uint32_t fwTab[FWTAB_CAP];              // first-wid overrides of socket chunks (PathEvaluator.hpp:590), index 0 unused
 #if KB_CONG
-		int32_t dots[64][33];                   // (unique context, candidate of the group) -> sum u8*s8 - hsum, from the tensor-core tiles
-		uint32_t uctx[64];                      // the node's unique context ids (regular incoming paths)
+		int32_t dots[KB_CG_UCAP][33];           // (unique context, candidate of the group) -> sum u8*s8 - hsum, from the tensor-core tiles
+		uint32_t uctx[KB_CG_UCAP];              // the node's unique context ids (regular incoming paths)
 		uint8_t pslot[STAGE_CAP];               // incoming path -> index into uctx, 0xFF = none (socket path / more than 64 contexts)
 		uint32_t colWid[GROUP];                 // first wid of every candidate of the group
-		uint32_t candOrder[256];                // the node's candidates in the transposed evaluator's order
+		uint32_t candOrder[KB_CG_CANDS];        // the node's candidates in the transposed evaluator's order
 #endif
 	};
 #ifndef KB_VIT_WARPS
@@ -222,7 +231,8 @@ namespace KB_VIT_NS
 
 #if KB_CONG
 	// ---- CoNg language model ----------------------------------------------------------------------------
-	static constexpr uint32_t CG_UCAP = 64;          // unique contexts of a node held in the tensor-core tile (else per-pair dp4a)
+	static constexpr uint32_t CG_UCAP = KB_CG_UCAP;  // unique contexts of a node held in the tensor-core tile (else per-pair dp4a); 32 keeps 4 blocks per SM
+	static constexpr uint32_t CG_CANDS = KB_CG_CANDS; // candidates of one lattice node (the largest candidate list of the test models has 90 entries)
 
 	__device__ __forceinline__ bool cgLookup(uint32_t node, uint32_t key, int32_t& v, uint32_t& childCtx)
 	{
@@ -1235,7 +1245,7 @@ namespace KB_VIT_NS
 			}
 			cn.nU = nU;
 			// ---- (b)
-			if (nCandsIn > 256) { err = ST_INTERNAL; return cn; }
+			if (nCandsIn > CG_CANDS) { err = ST_INTERNAL; return cn; }
 			uint32_t W = 0, nDistinct = 0, known[4] = { 0, 0, 0, 0 };
 			int32_t lastCoda = -1, lastSiot = -1;
 			#pragma unroll 1
@@ -1279,7 +1289,7 @@ namespace KB_VIT_NS
 						}
 					}
 				}
-				sm->item[ci < ITEM_CAP ? ci : 0] = ci < nCandsIn ? key : 7u;      // nCandsIn <= 256 <= ITEM_CAP
+				sm->item[ci < ITEM_CAP ? ci : 0] = ci < nCandsIn ? key : 7u;      // nCandsIn <= CG_CANDS <= ITEM_CAP
 				const unsigned codaM = __ballot_sync(FULL, key == 0), siotM = __ballot_sync(FULL, key == 1);
 				if (codaM) lastCoda = (int32_t)(cb + 31 - __clz(codaM));
 				if (siotM) lastSiot = (int32_t)(cb + 31 - __clz(siotM));
