@@ -1879,8 +1879,14 @@ namespace KB_VIT_NS
 				__syncwarp();
 #ifdef KB_LOCKSTEP
 				// keep the warps of the block at the same lattice-node phase: they then share instruction-cache lines
-				asm volatile("bar.sync 1, %0;" :: "r"(roundCnt) : "memory");
-				roundCnt = *sActive;
+#ifndef KB_LOCKSTEP_EVERY
+#define KB_LOCKSTEP_EVERY 1
+#endif
+				if (KB_LOCKSTEP_EVERY == 1 || (i % KB_LOCKSTEP_EVERY) == 0)
+				{
+					asm volatile("bar.sync 1, %0;" :: "r"(roundCnt) : "memory");
+					roundCnt = *sActive;
+				}
 #endif
 			}
 
@@ -2024,8 +2030,10 @@ namespace KB_VIT_NS
 		}
 	};
 
+	// registers: the Knlm kernel is fastest at 4 resident blocks (128 registers, measured against 3 / 5 / 6); the CoNg kernel's
+	// larger per-warp state spills less at 3 blocks (profiles/r1b_experiments.md)
 	#ifndef KB_VIT_MIN_BLOCKS
-#define KB_VIT_MIN_BLOCKS 4
+#define KB_VIT_MIN_BLOCKS (KB_CONG ? 3 : 4)
 #endif
 #ifndef KB_SOLO
 #define KB_SOLO 0
