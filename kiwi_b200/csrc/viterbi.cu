@@ -21,6 +21,7 @@
 // order - which fixes all later tie-breaks - is the reference's insertion order (bucket-major in the
 // 4 x 128 "medium" mode).  Pruning is a warp max-reduction followed by a ballot compaction.
 // Compile with -fmad=false: the reference's float sums are not contracted (x86-64 baseline, no FMA).
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include "kb_model.h"
@@ -80,7 +81,12 @@ namespace KB_VIT_NS
 #define KB_HT_SIZE 1024
 #endif
 	static constexpr uint32_t HT_SIZE = KB_HT_SIZE, HT_MAX_ENTRIES = KB_HT_SIZE * 3 / 4;
-	static constexpr uint32_t STAGE_CAP = KB_STAGE_CAP, ITEM_CAP = 512, GROUP = 32;
+#ifndef KB_ITEM_CAP
+#define KB_ITEM_CAP 512
+#endif
+	static constexpr uint32_t STAGE_CAP = KB_STAGE_CAP, ITEM_CAP = KB_ITEM_CAP, GROUP = 32;
+	static constexpr uint32_t TILE_W = ITEM_CAP / 32 < 16 ? ITEM_CAP / 32 : 16;      // bitmap words (of 32 paths) enumerated per pass: one item buffer
+	static_assert(ITEM_CAP % 32 == 0 && ITEM_CAP >= 256, "item buffer");
 	static_assert(STAGE_CAP % 512 == 0 && STAGE_CAP <= HT_MAX_ENTRIES * 2 && (HT_SIZE & (HT_SIZE - 1)) == 0, "staging / index capacities");
 
 	// static + per-node data of one candidate morpheme, written lane-parallel (lane = candidate) into shared memory
@@ -1529,9 +1535,9 @@ namespace KB_VIT_NS
 								// 512 paths (16 bitmap words = one item buffer) at a time
 								const uint32_t nWtot = (P + 31) >> 5;
 								#pragma unroll 1
-								for (uint32_t wt = 0; wt < nWtot; wt += 16)
+								for (uint32_t wt = 0; wt < nWtot; wt += TILE_W)
 								{
-									const uint32_t nW = min(16u, nWtot - wt);
+									const uint32_t nW = min(TILE_W, nWtot - wt);
 									uint32_t bits = 0;
 									if (lane < nW) { uint32_t mm = vmK; while (mm) { const uint32_t c = __ffs(mm) - 1; bits |= sm->classBits[c][wt + lane]; mm &= mm - 1; } }
 									const uint32_t cnt = __popc(bits);
@@ -2250,7 +2256,13 @@ namespace KB_VIT_NS
 		const uint32_t blocks = bv.n_sent <= KB_SOLO ? bv.n_sent : KB_SOLO + (bv.n_sent - KB_SOLO + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 		static bool attrSet = false;
 		const size_t smemBytes = sizeof(WarpSmem) * WARPS_PER_BLOCK;
-		if (!attrSet) { cudaFuncSetAttribute(KB_VIT_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); attrSet = true; }
+		if (!attrSet)
+		{
+			cudaFuncSetAttribute(KB_VIT_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+			// kernel experiments: KIWI_B200_CARVEOUT=<percent> overrides the shared-memory / L1 split the driver picks
+			if (const char* co = getenv("KIWI_B200_CARVEOUT")) cudaFuncSetAttribute(KB_VIT_KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
+			attrSet = true;
+		}
 		KB_VIT_KERNEL<<<blocks, WARPS_PER_BLOCK * 32, smemBytes, stream>>>(bv, vv);
 		return cudaGetLastError();
 	}
