@@ -218,9 +218,9 @@ def main():
     vit_per_launch_ms = ms_vit / args.steps
     achieved = vit_b * args.batch / (vit_per_launch_ms / 1000.0) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
-    if MODEL == "knlm" and os.path.exists(tp):
-        traffic = json.load(open(tp)).get("viterbi_kernel_dram_bytes_per_launch")
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("viterbi_kernel_dram_bytes_per_launch" if MODEL == "knlm" else "viterbi_cong_kernel_dram_bytes_per_launch")
     cpu = run_reference_cpu(batches[0][0][:args.cpu_sample], os.cpu_count() or 1) if (world == 1 and not args.no_cpu) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
