@@ -113,6 +113,19 @@ static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, const BatchOutput& bo,
 	auto* r = new kiwi_res;
 	r->score = bo.scores[idx];
 	const Model& m = h->engine->model;
+	// word index of every raw position: getWordPositions, src/Kiwi.cpp:464-485 (a run of spaces ends one word)
+	uint32_t textLen = 0;
+	for (uint32_t t = bo.tokOff[idx]; t < bo.tokOff[idx + 1]; ++t) textLen = std::max<uint32_t>(textLen, bo.tokens[t].position + bo.tokens[t].length);
+	std::vector<uint16_t> wordPos(textLen + 1, 0);
+	{
+		uint32_t position = 0; bool continuousSpace = false;
+		for (uint32_t i = 0; i <= textLen; ++i)
+		{
+			wordPos[i] = (uint16_t)position;
+			if (i < textLen && attrSpace(m.hostChrAttr(text[i]))) { if (!continuousSpace) ++position; continuousSpace = true; }
+			else continuousSpace = false;
+		}
+	}
 	for (uint32_t t = bo.tokOff[idx]; t < bo.tokOff[idx + 1]; ++t)
 	{
 		const DToken& d = bo.tokens[t];
@@ -120,6 +133,7 @@ static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, const BatchOutput& bo,
 		std::memset(&k.info, 0, sizeof(k.info));
 		k.info.chr_position = d.position; k.info.length = d.length; k.info.tag = d.tag; k.info.score = d.score;
 		k.info.paired_token = (uint32_t)-1;
+		k.info.word_position = wordPos[d.position];
 		k.morphId = d.morph;
 		const kb2_morph& mm = m.hMorphs[d.morph];
 		k.info.sense_id = mm.sense_id; k.info.dialect = mm.dialect;

@@ -19,6 +19,8 @@ namespace kb
 		std::vector<void*> owned;
 		size_t deviceBytes = 0;
 		const kb2_form* hForms = nullptr; const uint16_t* hFormChars = nullptr; const kb2_morph* hMorphs = nullptr;
+		std::vector<uint32_t> hChrBmp;      // host copy of chr_bmp (cls | script << 8 | flags << 16) for result assembly
+		uint32_t hostChrAttr(uint16_t c) const { return hChrBmp[c]; }
 		void load(const void* bytes, size_t size);
 		~Model();
 	};

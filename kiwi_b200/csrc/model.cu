@@ -110,6 +110,7 @@ namespace kb
 			const uint32_t s = runs[i].start, e = i + 1 < h->n_chr_runs ? runs[i + 1].start : 0x110000u;
 			for (uint32_t c = s; c < e && c < 0x10000; ++c) bmp[c] = (uint32_t)runs[i].cls | ((uint32_t)runs[i].script << 8) | ((uint32_t)runs[i].flags << 16);
 		}
+		hChrBmp = bmp;
 		// ---- root direct table
 		std::vector<int32_t> rootNext(0x10000, -1);
 		for (uint32_t i = 0; i < trieNodes[0].num_nexts; ++i) rootNext[trieKeys[trieNodes[0].next_offset + i]] = trieDiffs[trieNodes[0].next_offset + i];

@@ -7,7 +7,7 @@
 //
 // Output (text, floats as C99 hex so they round-trip bit-exactly):
 //   S <idx> <nTokens> <score> <nChunks> <normLen>
-//   T <morphId> <tag> <position> <length> <wordScore>                      x nTokens
+//   T <morphId> <tag> <position> <length> <wordScore> <wordPosition> <form utf-8>   x nTokens
 //   C <chunkIdx> <startOffset> <endOffset> <nNodes> <nPaths>
 //   N <formIdx|-1> <uformOff|-1> <uformLen> <prev> <sibling> <startPos> <endPos> <spaceErrors> <typoCost>   x nNodes
 //   P <score> <prevState> <curState> <nTok>
@@ -24,6 +24,23 @@
 #include "PathEvaluator.h"
 
 using namespace kiwi;
+
+// UTF-8 for the dump; unpaired surrogates (edge-case inputs) become U+FFFD instead of an exception
+static std::string toUtf8Lenient(const std::u16string& s)
+{
+	std::string out;
+	for (size_t i = 0; i < s.size(); ++i)
+	{
+		uint32_t c = s[i];
+		if (0xD800 <= c && c < 0xDC00 && i + 1 < s.size() && 0xDC00 <= s[i + 1] && s[i + 1] < 0xE000) { c = 0x10000 + ((c - 0xD800) << 10) + (s[i + 1] - 0xDC00); ++i; }
+		else if (0xD800 <= c && c < 0xE000) c = 0xFFFD;
+		if (c < 0x80) out.push_back((char)c);
+		else if (c < 0x800) { out.push_back((char)(0xC0 | (c >> 6))); out.push_back((char)(0x80 | (c & 63))); }
+		else if (c < 0x10000) { out.push_back((char)(0xE0 | (c >> 12))); out.push_back((char)(0x80 | ((c >> 6) & 63))); out.push_back((char)(0x80 | (c & 63))); }
+		else { out.push_back((char)(0xF0 | (c >> 18))); out.push_back((char)(0x80 | ((c >> 12) & 63))); out.push_back((char)(0x80 | ((c >> 6) & 63))); out.push_back((char)(0x80 | (c & 63))); }
+	}
+	return out;
+}
 
 int main(int argc, char** argv)
 {
@@ -146,7 +163,8 @@ int main(int argc, char** argv)
 			std::fprintf(fo, "S %zu %zu %a %zu %zu\n", idx, tokens.size(), res[0].second, chunks.size(), normalizedStr.size());
 			for (auto& t : tokens)
 			{
-				std::fprintf(fo, "T %zu %u %u %u %a\n", t.morph ? kw.morphToId(t.morph) : (size_t)-1, (unsigned)t.tag, t.position, (unsigned)t.length, t.score);
+				std::fprintf(fo, "T %zu %u %u %u %a %u %s\n", t.morph ? kw.morphToId(t.morph) : (size_t)-1, (unsigned)t.tag, t.position, (unsigned)t.length, t.score,
+					(unsigned)t.wordPosition, toUtf8Lenient(t.str).c_str());
 			}
 			for (size_t c = 0; c < chunks.size(); ++c)
 			{

@@ -133,3 +133,43 @@ def test_large_batch_is_split_into_passes(kiwi):
     for i in range(0, len(texts), 997):
         j = i % len(base)
         assert r.sentence(i).tobytes() == ref.sentence(j).tobytes() and r.scores[i] == ref.scores[j]
+
+
+class _TokenInfo(__import__("ctypes").Structure):      # kiwi_token_info_t, include/kiwi_b200.h (capi.h:43-61)
+    import ctypes as _C
+    _fields_ = [("chr_position", _C.c_uint32), ("word_position", _C.c_uint32), ("sent_position", _C.c_uint32), ("line_number", _C.c_uint32),
+                ("length", _C.c_uint16), ("tag", _C.c_uint8), ("sense_id", _C.c_uint8), ("score", _C.c_float), ("typo_cost", _C.c_float),
+                ("typo_form_id", _C.c_uint32), ("paired_token", _C.c_uint32), ("sub_sent_position", _C.c_uint32), ("dialect", _C.c_uint16)]
+
+
+@pytest.mark.parametrize("name", ["inputs_web", "inputs_written"])
+def test_result_assembly_forms_and_word_positions(kiwi, name):
+    """SURVEY 8f-1 (result assembly): kiwi_res_form and kiwi_token_info_t.word_position of every token, through
+    kiwi_analyze_mw, against TokenInfo::str / wordPosition of the unmodified reference (insertPathIntoResults,
+    src/Kiwi.cpp:696-756; getWordPositions 464-485)."""
+    import ctypes as C
+    lib = kiwi_b200.load_library()
+    texts = read_inputs(name); gold = read_golden(name)
+    READER = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_uint16), C.c_void_p)
+    RECEIVER = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_void_p)
+    lib.kiwi_res_token_info.restype = C.POINTER(_TokenInfo)
+    lib.kiwi_res_token_info.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.kiwi_res_form.restype = C.c_char_p
+    got = {}
+
+    def reader(idx, out, ud):
+        if idx >= len(texts): return 0
+        enc = np.frombuffer(texts[idx].encode("utf-16-le"), dtype="<u2")
+        if out:
+            for k, v in enumerate(enc): out[k] = int(v)
+        return len(enc)
+
+    def receiver(idx, res, ud):
+        n = lib.kiwi_res_word_num(res, 0)
+        got[idx] = [(int(lib.kiwi_res_token_info(res, 0, i).contents.word_position), lib.kiwi_res_form(res, 0, i).decode("utf-8")) for i in range(n)]
+        lib.kiwi_res_close(res); return 0
+
+    lib.kiwi_analyze_mw.argtypes = [C.c_void_p, READER, RECEIVER, C.c_void_p, C.c_int, kiwi_b200.AnalyzeOption]
+    assert lib.kiwi_analyze_mw(kiwi._h, READER(reader), RECEIVER(receiver), None, 1, kiwi_b200.default_option()) == len(texts)
+    for i, g in enumerate(gold):
+        assert got[i] == g["forms"], (i, texts[i], got[i], g["forms"])
