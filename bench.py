@@ -94,7 +94,7 @@ def run_reference_cpu(texts, threads, repeats=1):
             line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
             r = json.loads(line)
             return {"value": r["sent_per_s"], "unit": UNIT, "cores": threads, "kind": "reference",
-                    "sample": "%d sentences of the bench batch, reference Kiwi::analyze batch mode on %d threads, KIWI_ARCH_TYPE=%s, %.2f s" % (r["sentences"], threads, r["arch"], r["seconds"])}
+                    "sample": "%d sentences of the bench batch, reference Kiwi::analyze batch mode on %d threads, KIWI_ARCH_TYPE=%s, best of %d passes: %.2f s" % (r["sentences"], threads, r["arch"], r["repeats"], r["seconds"])}
         finally:
             os.unlink(tmp)
     from tests.orc import Oracle
@@ -112,7 +112,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=8192)
-    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments)")
     ap.add_argument("--model", default="knlm", choices=["knlm", "cong"], help="knlm = headline config; cong = BASELINE.json config[2] (CoNg model)")
     args = ap.parse_args()
@@ -221,7 +221,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("viterbi_kernel_dram_bytes_per_launch" if MODEL == "knlm" else "viterbi_cong_kernel_dram_bytes_per_launch")
-    cpu = run_reference_cpu(batches[0][0][:args.cpu_sample], os.cpu_count() or 1) if (world == 1 and not args.no_cpu) else None
+    cpu = run_reference_cpu(batches[0][0][:args.cpu_sample], os.cpu_count() or 1, repeats=5) if (world == 1 and not args.no_cpu) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

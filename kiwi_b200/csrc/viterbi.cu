@@ -1206,7 +1206,7 @@ namespace KB_VIT_NS
 
 #if KB_CONG
 		// ---- transposed evaluator, node-level preparation ------------------------------------------------------
-		struct CongNode { uint32_t nOrdered, epFirst, nU; bool tileOK; };
+		struct CongNode { uint32_t nOrdered, epFirst, nU; };
 
 		// (a) the node's unique context ids among the regular (non-socket) incoming paths -> sm->uctx / sm->pslot, and
 		//     (b) the candidates in evaluation order -> sm->candOrder: z_coda shortcut, z_siot shortcut, regular, left halves,
@@ -1215,7 +1215,7 @@ namespace KB_VIT_NS
 		__device__ __noinline__ CongNode congPrepare(const DNode& node, bool spaceBefore, const uint32_t* candList, uint32_t nCandsIn,
 			uint32_t unk0, uint32_t unk1, uint32_t inBeg, uint32_t P)
 		{
-			CongNode cn; cn.nOrdered = 0; cn.epFirst = CG_E_SMALL; cn.nU = 0; cn.tileOK = true;
+			CongNode cn; cn.nOrdered = 0; cn.epFirst = CG_E_SMALL; cn.nU = 0;
 			// ---- (a)
 			uint32_t nU = 0, nUtrue = 0, Preg = 0;
 			#pragma unroll 1
@@ -1241,7 +1241,7 @@ namespace KB_VIT_NS
 					{
 						// not in the tile list: either new, or (list full) an overflow context that is scored per pair
 						if (nU < CG_UCAP) { slot = nU; if (lane == 0) sm->uctx[nU] = v; ++nU; ++nUtrue; __syncwarp(); }
-						else { cn.tileOK = cn.tileOK; ++nUtrue; }      // nUtrue only needs to be exact up to 4
+						else ++nUtrue;      // nUtrue only needs to be exact up to 4
 					}
 					const unsigned same = __ballot_sync(FULL, reg && ctx == v);
 					if (reg && ctx == v) mySlot = slot;
