@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../include/kiwi_b200.h"
 #include "engine.h"
+#include "assemble.h"
 
 using namespace kb;
 
@@ -108,14 +109,13 @@ static void checkOption(const kiwi_analyze_option_t& o, int topN, kiwi_pretokeni
 	if ((uint32_t)o.match_options & unsupported) throw std::invalid_argument("match_options contain a flag outside the kiwi_b200 hot path (oov models, join*, compatibleJamo, mergeSaisiot, useOldSplitter)");
 }
 
-static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, const BatchOutput& bo, uint32_t idx)
+static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, uint32_t rawLen, const BatchOutput& bo, uint32_t idx)
 {
 	auto* r = new kiwi_res;
 	r->score = bo.scores[idx];
 	const Model& m = h->engine->model;
 	// word index of every raw position: getWordPositions, src/Kiwi.cpp:464-485 (a run of spaces ends one word)
-	uint32_t textLen = 0;
-	for (uint32_t t = bo.tokOff[idx]; t < bo.tokOff[idx + 1]; ++t) textLen = std::max<uint32_t>(textLen, bo.tokens[t].position + bo.tokens[t].length);
+	const uint32_t textLen = rawLen;
 	std::vector<uint16_t> wordPos(textLen + 1, 0);
 	{
 		uint32_t position = 0; bool continuousSpace = false;
@@ -141,6 +141,26 @@ static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, const BatchOutput& bo,
 		else if (mm.form_idx >= 0) k.form = joinHangul(m.hFormChars + m.hForms[mm.form_idx].str_off, m.hForms[mm.form_idx].str_len);
 		k.form8 = utf16To8(k.form);
 		r->toks.push_back(std::move(k));
+	}
+	// paired brackets / bullets, sentence / line / sub-sentence numbers, sentence-relative word index
+	// (fillPairedTokenInfo + fillSentLineInfo, src/Kiwi.cpp:1149-1154; restated in assemble.h)
+	{
+		std::vector<AsmTok> at(r->toks.size());
+		for (size_t i = 0; i < at.size(); ++i)
+		{
+			const auto& k = r->toks[i];
+			at[i].position = k.info.chr_position; at[i].length = k.info.length; at[i].tag = k.info.tag; at[i].form = k.form; at[i].wordPosition = k.info.word_position;
+			const kb2_morph& mm = m.hMorphs[k.morphId];
+			at[i].kformIsYo = mm.form_idx >= 0 && m.hForms[mm.form_idx].str_len == 1 && m.hFormChars[m.hForms[mm.form_idx].str_off] == 0xC694;
+		}
+		fillPaired(at);
+		fillSentLine(at, newlinePositions(text, rawLen));
+		for (size_t i = 0; i < at.size(); ++i)
+		{
+			auto& info = r->toks[i].info;
+			info.word_position = at[i].wordPosition; info.sent_position = at[i].sentPosition; info.line_number = at[i].lineNumber;
+			info.sub_sent_position = at[i].subSentPosition; info.paired_token = at[i].pairedToken;
+		}
 	}
 	return r;
 }
@@ -177,7 +197,7 @@ static int analyzeMulti(kiwi_h handle, ReadFn&& readOne, kiwi_receiver_t receive
 			}
 			for (uint32_t i = 0; i < n; ++i)
 			{
-				kiwi_res* r = makeRes(handle, text.data() + off[i], bo, i);
+				kiwi_res* r = makeRes(handle, text.data() + off[i], off[i + 1] - off[i], bo, i);
 				// positions are relative to the sentence already (each sentence has its own position table)
 				(*receiver)(delivered++, r, user_data);
 			}
@@ -259,7 +279,7 @@ kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_
 		std::lock_guard<std::mutex> lk(handle->mtx);
 		BatchOutput bo;
 		handle->engine->analyze(text, off, 1, (uint32_t)option.match_options, bo);
-		return makeRes(handle, text, bo, 0);
+		return makeRes(handle, text, len, bo, 0);
 	}
 	catch (const std::exception& e) { setError(e); return nullptr; }
 }

@@ -7,7 +7,7 @@
 //
 // Output (text, floats as C99 hex so they round-trip bit-exactly):
 //   S <idx> <nTokens> <score> <nChunks> <normLen>
-//   T <morphId> <tag> <position> <length> <wordScore> <wordPosition> <form utf-8>   x nTokens
+//   T <morphId> <tag> <position> <length> <wordScore> <wordPosition>,<sentPosition>,<lineNumber>,<subSentPosition>,<pairedToken> <form utf-8>   x nTokens
 //   C <chunkIdx> <startOffset> <endOffset> <nNodes> <nPaths>
 //   N <formIdx|-1> <uformOff|-1> <uformLen> <prev> <sibling> <startPos> <endPos> <spaceErrors> <typoCost>   x nNodes
 //   P <score> <prevState> <curState> <nTok>
@@ -163,8 +163,8 @@ int main(int argc, char** argv)
 			std::fprintf(fo, "S %zu %zu %a %zu %zu\n", idx, tokens.size(), res[0].second, chunks.size(), normalizedStr.size());
 			for (auto& t : tokens)
 			{
-				std::fprintf(fo, "T %zu %u %u %u %a %u %s\n", t.morph ? kw.morphToId(t.morph) : (size_t)-1, (unsigned)t.tag, t.position, (unsigned)t.length, t.score,
-					(unsigned)t.wordPosition, toUtf8Lenient(t.str).c_str());
+				std::fprintf(fo, "T %zu %u %u %u %a %u,%u,%u,%u,%d %s\n", t.morph ? kw.morphToId(t.morph) : (size_t)-1, (unsigned)t.tag, t.position, (unsigned)t.length, t.score,
+					(unsigned)t.wordPosition, (unsigned)t.sentPosition, (unsigned)t.lineNumber, (unsigned)t.subSentPosition, (int)t.pairedToken, toUtf8Lenient(t.str).c_str());
 			}
 			for (size_t c = 0; c < chunks.size(); ++c)
 			{

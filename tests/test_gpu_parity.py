@@ -144,9 +144,9 @@ class _TokenInfo(__import__("ctypes").Structure):      # kiwi_token_info_t, incl
 
 @pytest.mark.parametrize("name", ["inputs_web", "inputs_written"])
 def test_result_assembly_forms_and_word_positions(kiwi, name):
-    """SURVEY 8f-1 (result assembly): kiwi_res_form and kiwi_token_info_t.word_position of every token, through
-    kiwi_analyze_mw, against TokenInfo::str / wordPosition of the unmodified reference (insertPathIntoResults,
-    src/Kiwi.cpp:696-756; getWordPositions 464-485)."""
+    """SURVEY 8f-1 (result assembly): kiwi_res_form and the kiwi_token_info_t fields word / sentence / line / sub-sentence
+    position and paired token of every token, through kiwi_analyze_mw, against TokenInfo of the unmodified reference
+    (insertPathIntoResults src/Kiwi.cpp:696-756, fillPairedTokenInfo 98-143, fillSentLineInfo 322-415)."""
     import ctypes as C
     lib = kiwi_b200.load_library()
     texts = read_inputs(name); gold = read_golden(name)
@@ -166,7 +166,11 @@ def test_result_assembly_forms_and_word_positions(kiwi, name):
 
     def receiver(idx, res, ud):
         n = lib.kiwi_res_word_num(res, 0)
-        got[idx] = [(int(lib.kiwi_res_token_info(res, 0, i).contents.word_position), lib.kiwi_res_form(res, 0, i).decode("utf-8")) for i in range(n)]
+        got[idx] = []
+        for i in range(n):
+            ti = lib.kiwi_res_token_info(res, 0, i).contents
+            paired = int(ti.paired_token); paired = -1 if paired == 0xFFFFFFFF else paired
+            got[idx].append(((int(ti.word_position), int(ti.sent_position), int(ti.line_number), int(ti.sub_sent_position), paired), lib.kiwi_res_form(res, 0, i).decode("utf-8")))
         lib.kiwi_res_close(res); return 0
 
     lib.kiwi_analyze_mw.argtypes = [C.c_void_p, READER, RECEIVER, C.c_void_p, C.c_int, kiwi_b200.AnalyzeOption]
