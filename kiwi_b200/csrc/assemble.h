@@ -64,6 +64,86 @@ namespace kb
 		return format | (group << 2);
 	}
 
+	// ---- surface form of a token that keeps its own substring (TokenInfo::str = joinHangul(PathNode::str), src/Kiwi.cpp:721):
+	// the substring is taken from the NORMALISED text (normalizeHangulWithPosition src/StrUtils.h:493-520, then normalizeCoda
+	// 636-710 when Match::normalizeCoda is set), whose codas are separate units; a token may begin at the coda of a raw
+	// character or end before it.  The device reports raw positions only, but tokens tile the text, so such a split shows
+	// as two tokens sharing one raw character.
+	struct NormText { std::u16string norm; std::vector<uint32_t> pos; };      // pos[i] = first normalised unit of raw unit i, pos[n] = size
+
+	inline NormText normalizeWithPosition(const uint16_t* text, size_t n, bool normalizeCodaOpt)
+	{
+		NormText nt;
+		nt.pos.reserve(n + 1); nt.norm.reserve(n * 2);
+		for (size_t i = 0; i < n; ++i)
+		{
+			uint32_t c = text[i];
+			nt.pos.push_back((uint32_t)nt.norm.size());
+			if (c == 0xB42C) c = 0xB410;
+			if (0xAC00 <= c && c < 0xD7A4)
+			{
+				const uint32_t coda = (c - 0xAC00) % 28;
+				nt.norm.push_back((char16_t)(c - coda));
+				if (coda) nt.norm.push_back((char16_t)(coda + 0x11A7));
+			}
+			else nt.norm.push_back((char16_t)c);
+		}
+		nt.pos.push_back((uint32_t)nt.norm.size());
+		if (normalizeCodaOpt)
+		{
+			// a coda followed by the compatibility jamo of the same consonant ("몈ㅋㅋ") becomes that jamo, or the first half of a double coda
+			static const char16_t toOnset[27] = { 0x3131, 0x3131, 0x3145, 0x3134, 0x3148, 0x314E, 0x3137, 0x3139, 0x3131, 0x3141, 0x3142, 0x3145, 0x314C, 0x314D,
+				0x314E, 0x3141, 0x3142, 0x3145, 0x3145, 0x3145, 0x3147, 0x3148, 0x314A, 0x314B, 0x314C, 0x314D, 0x314E };
+			static const char16_t reduced[27] = { 0, 0x11A8, 0x11A8, 0, 0x11AB, 0x11AB, 0, 0, 0x11AF, 0x11AF, 0x11AF, 0x11AF, 0x11AF, 0x11AF, 0x11AF, 0, 0, 0x11B8, 0, 0x11BA,
+				0, 0, 0, 0, 0, 0, 0 };
+			char16_t before = 0;
+			for (size_t i = 0; i < nt.norm.size(); ++i)
+			{
+				const char16_t cur = nt.norm[i];
+				if (0x11A8 <= before && before <= 0x11C2 && cur == toOnset[before - 0x11A8])
+				{
+					const char16_t r = reduced[before - 0x11A8];
+					nt.norm[i - 1] = r ? r : cur;
+				}
+				before = cur;
+			}
+		}
+		return nt;
+	}
+
+	// joinHangul, include/kiwi/Utils.h:167-205
+	inline std::u16string joinHangulUnits(const char16_t* p, size_t n)
+	{
+		std::u16string ret;
+		ret.reserve(n);
+		for (size_t i = 0; i < n; ++i)
+		{
+			const char16_t c = p[i];
+			if (!ret.empty() && 0xAC00 <= ret.back() && ret.back() < 0xD7A4 && (ret.back() - 0xAC00) % 28 == 0)
+			{
+				if (0x11A8 <= c && c < 0x11A8 + 27) ret.back() = (char16_t)(ret.back() + (c - 0x11A7));
+				else if ((0x11A8 <= c && c < 0x1200) || (0xD7CB <= c && c < 0xD800))
+				{
+					const uint32_t onset = (ret.back() - 0xAC00) / 28 / 21, vowel = (ret.back() - 0xAC00) / 28 % 21;
+					ret.back() = (char16_t)(0x1100 + onset);
+					ret.push_back((char16_t)(0x1161 + vowel));
+					ret.push_back(c);
+				}
+				else ret.push_back(c);
+			}
+			else ret.push_back(c);
+		}
+		return ret;
+	}
+
+	inline std::u16string ownSubstringForm(const NormText& nt, uint32_t position, uint32_t length, bool beginsAtCoda, bool endsBeforeCoda)
+	{
+		if ((size_t)position + length >= nt.pos.size()) return {};
+		uint32_t b = nt.pos[position] + (beginsAtCoda ? 1u : 0u), e = nt.pos[position + length] - (endsBeforeCoda ? 1u : 0u);
+		if (e < b) e = b;
+		return joinHangulUnits(nt.norm.data() + b, e - b);
+	}
+
 	inline std::vector<size_t> newlinePositions(const uint16_t* text, size_t n)
 	{
 		std::vector<size_t> ret;

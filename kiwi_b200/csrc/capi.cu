@@ -84,19 +84,6 @@ static std::string utf16To8(const std::u16string& s)
 	}
 	return out;
 }
-// joinHangul (reference src/StrUtils.h): a coda jamo U+11A8..U+11C2 after a coda-less syllable folds into it
-static std::u16string joinHangul(const uint16_t* p, size_t n)
-{
-	std::u16string out;
-	for (size_t i = 0; i < n; ++i)
-	{
-		const uint16_t c = p[i];
-		if (0x11A8 <= c && c <= 0x11C2 && !out.empty() && 0xAC00 <= out.back() && out.back() < 0xD7A4 && (out.back() - 0xAC00) % 28 == 0) out.back() = (char16_t)(out.back() + (c - 0x11A7));
-		else out.push_back((char16_t)c);
-	}
-	return out;
-}
-
 static void checkOption(const kiwi_analyze_option_t& o, int topN, kiwi_pretokenized_h pt)
 {
 	if (topN != 1) throw std::invalid_argument("kiwi_b200 implements the top_n == 1 path only");
@@ -109,7 +96,7 @@ static void checkOption(const kiwi_analyze_option_t& o, int topN, kiwi_pretokeni
 	if ((uint32_t)o.match_options & unsupported) throw std::invalid_argument("match_options contain a flag outside the kiwi_b200 hot path (oov models, join*, compatibleJamo, mergeSaisiot, useOldSplitter)");
 }
 
-static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, uint32_t rawLen, const BatchOutput& bo, uint32_t idx)
+static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, uint32_t rawLen, const BatchOutput& bo, uint32_t idx, uint32_t matchOptions)
 {
 	auto* r = new kiwi_res;
 	r->score = bo.scores[idx];
@@ -126,6 +113,7 @@ static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, uint32_t rawLen, const
 			else continuousSpace = false;
 		}
 	}
+	const NormText nt = normalizeWithPosition(text, rawLen, (matchOptions & KIWI_MATCH_NORMALIZE_CODA) != 0);
 	for (uint32_t t = bo.tokOff[idx]; t < bo.tokOff[idx + 1]; ++t)
 	{
 		const DToken& d = bo.tokens[t];
@@ -137,8 +125,15 @@ static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, uint32_t rawLen, const
 		k.morphId = d.morph;
 		const kb2_morph& mm = m.hMorphs[d.morph];
 		k.info.sense_id = mm.sense_id; k.info.dialect = mm.dialect;
-		if (d.flags & 1) { k.form.assign(reinterpret_cast<const char16_t*>(text) + d.position, d.length); if ((d.tag & 0x7F) == T_nng || (d.tag & 0x7F) == T_nnp) k.info.sense_id = 0xFF; }
-		else if (mm.form_idx >= 0) k.form = joinHangul(m.hFormChars + m.hForms[mm.form_idx].str_off, m.hForms[mm.form_idx].str_len);
+		if (d.flags & 1)
+		{
+			// own substring: two tokens sharing a raw character = that character's syllable body / coda split (assemble.h)
+			const bool beginsAtCoda = t > bo.tokOff[idx] && bo.tokens[t - 1].position + bo.tokens[t - 1].length > d.position;
+			const bool endsBeforeCoda = t + 1 < bo.tokOff[idx + 1] && bo.tokens[t + 1].position < d.position + d.length;
+			k.form = ownSubstringForm(nt, d.position, d.length, beginsAtCoda, endsBeforeCoda);
+			if ((d.tag & 0x7F) == T_nng || (d.tag & 0x7F) == T_nnp) k.info.sense_id = 0xFF;
+		}
+		else if (mm.form_idx >= 0) k.form = joinHangulUnits(reinterpret_cast<const char16_t*>(m.hFormChars + m.hForms[mm.form_idx].str_off), m.hForms[mm.form_idx].str_len);
 		k.form8 = utf16To8(k.form);
 		r->toks.push_back(std::move(k));
 	}
@@ -197,7 +192,7 @@ static int analyzeMulti(kiwi_h handle, ReadFn&& readOne, kiwi_receiver_t receive
 			}
 			for (uint32_t i = 0; i < n; ++i)
 			{
-				kiwi_res* r = makeRes(handle, text.data() + off[i], off[i + 1] - off[i], bo, i);
+				kiwi_res* r = makeRes(handle, text.data() + off[i], off[i + 1] - off[i], bo, i, (uint32_t)option.match_options);
 				// positions are relative to the sentence already (each sentence has its own position table)
 				(*receiver)(delivered++, r, user_data);
 			}
@@ -279,7 +274,7 @@ kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_
 		std::lock_guard<std::mutex> lk(handle->mtx);
 		BatchOutput bo;
 		handle->engine->analyze(text, off, 1, (uint32_t)option.match_options, bo);
-		return makeRes(handle, text, len, bo, 0);
+		return makeRes(handle, text, len, bo, 0, (uint32_t)option.match_options);
 	}
 	catch (const std::exception& e) { setError(e); return nullptr; }
 }

@@ -24,3 +24,14 @@ extern "C" int kb_asm_run(int n, const uint32_t* pos, const uint32_t* len, const
 	}
 	return 0;
 }
+
+// surface form of an own-substring token: returns the number of UTF-16 units written to out
+extern "C" int kb_own_form(const uint16_t* text, uint32_t textLen, int normalizeCoda, uint32_t position, uint32_t length, int beginsAtCoda, int endsBeforeCoda,
+	uint16_t* out, int cap)
+{
+	const kb::NormText nt = kb::normalizeWithPosition(text, textLen, normalizeCoda != 0);
+	const std::u16string f = kb::ownSubstringForm(nt, position, length, beginsAtCoda != 0, endsBeforeCoda != 0);
+	if ((int)f.size() > cap) return -1;
+	for (size_t i = 0; i < f.size(); ++i) out[i] = (uint16_t)f[i];
+	return (int)f.size();
+}

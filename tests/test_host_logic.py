@@ -42,3 +42,23 @@ def test_round_robin_shards_restore_order():
     assert all(p == list(range(r, n, w)) for r, p in enumerate(parts))
     results = [[("res", i) for i in p] for p in parts]
     assert shard.merge_round_robin(results, n) == [("res", i) for i in range(n)]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the reference's own CPU path, oracle/_ref/ref_bench) must print ONE JSON line with the
+    contract's keys for both model types; runs here on a tiny sample."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "ref_bench")):
+        import pytest
+        pytest.skip("oracle/_ref/ref_bench missing: run __graft_entry__.build() where /root/reference exists")
+    for model in ("knlm", "cong"):
+        out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", model, "--steps", "1", "--warmup", "1",
+                              "--cpu-sample", "128"], capture_output=True, text=True, timeout=600).stdout
+        lines = [l for l in out.splitlines() if l.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["unit"] == "sentences/s" and d["higher_is_better"] is True and d["value"] > 0
+        assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+        assert d["e2e"] == {"value": d["value"], "unit": "sentences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert "workload" in d["config"] and model in d["config"]["workload"].lower()

@@ -55,3 +55,34 @@ def test_assembly_matches_reference_token_info(name):
         assert [tuple(int(v) for v in r) for r in out] == [f[0] for f in forms], (t, out.tolist(), [f[0] for f in forms])
         checked += 1
     assert checked > 0.9 * len(gold)
+
+
+@pytest.mark.parametrize("name", ["inputs_web", "inputs_written", "inputs_dialect_typos"])
+def test_own_substring_forms(name):
+    """Tokens that keep their own substring (symbols, foreign words, numbers, unknown nouns) take it from the NORMALISED text;
+    a token may start at the coda of a raw character ("몈ㅋㅋㅋ" -> "며" + "ㅋㅋㅋㅋ").  The host reconstruction
+    (assemble.h ownSubstringForm) must reproduce TokenInfo::str of the reference for every such token."""
+    if not os.path.exists(LIB):
+        pytest.skip("tests/hostsim/libassemble_check.so missing: run __graft_entry__.build()")
+    lib = C.CDLL(LIB)
+    lib.kb_own_form.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    OWN_TAGS = set(range(21, 39)) | {0}      # sf..w_emoji and unknown: never dictionary forms in these inputs
+    texts = read_inputs(name); gold = read_golden(name)
+    checked = split = 0
+    buf = np.zeros(4096, np.uint16)
+    for t, g in zip(texts, gold):
+        toks = g["tokens"]; forms = g.get("forms")
+        units = np.ascontiguousarray(np.frombuffer(t.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
+        if not toks or forms is None or any(0xD800 <= int(u) < 0xE000 for u in units):
+            continue
+        for i, (tok, f) in enumerate(zip(toks, forms)):
+            if (tok[1] & 0x7F) not in OWN_TAGS:
+                continue
+            begins = i > 0 and toks[i - 1][2] + toks[i - 1][3] > tok[2]
+            ends = i + 1 < len(toks) and toks[i + 1][2] < tok[2] + tok[3]
+            n = lib.kb_own_form(units.ctypes.data, len(units), 1, tok[2], tok[3], int(begins), int(ends), buf.ctypes.data, len(buf))
+            got = bytes(buf[:n].astype("<u2").tobytes()).decode("utf-16-le")
+            assert got == f[1], (t, tok, got, f[1])
+            checked += 1; split += int(begins or ends)
+    assert checked > 100
+    print("%s: %d own-substring tokens, %d of them split a raw character" % (name, checked, split))
