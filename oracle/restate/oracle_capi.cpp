@@ -81,6 +81,13 @@ void orc_work_counters(void* p, uint64_t* out)
 	std::memcpy(out, &h->an->work, 18 * sizeof(uint64_t));
 }
 
+// forget the growth history of the `top1` container (= what a fresh reference process starts with)
+void orc_reset_history(void* p)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	h->an->viterbi.resetHistory();
+}
+
 // CoNg byte-model counters: {unique rows gathered (contexts + outputs), int8 MACs of the per-node gather GEMMs}
 void orc_cong_counters(void* p, uint64_t* out)
 {

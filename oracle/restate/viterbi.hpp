@@ -10,6 +10,7 @@
 // bucket count depends on previously analysed sentences; it is restated with insertion order and counted.
 #pragma once
 #include <cmath>
+#include <unordered_set>
 #include "lattice.hpp"
 #include "knlm.hpp"
 #include "cong.hpp"
@@ -24,6 +25,8 @@ namespace orc
 		int32_t lmState = 0;          // Knlm: node index.  CoNg: context-trie node (the only field state equality looks at)
 		uint32_t ctxIdx = 0;          // CoNg only: CoNgramState::contextIdx, carried along but not compared (CoNgramModel.hpp:491-494)
 		SbHist sb;                    // SkipBigram only: ring of the last valid tokens, part of the state's identity
+		uint64_t hashv = 0;           // Hash<WordLL> of the reference, kept for the `top1` container (an std::unordered_set there)
+		uint8_t cmpSb = 0;
 		uint8_t prevRootId = 0, spState = 0, rootId = 0;
 		int32_t morpheme = -1;
 		float accScore = 0, firstChunkScore = 0, accTypoCost = 0, accDialectCost = 0;
@@ -212,13 +215,27 @@ namespace orc
 		}
 
 		// ---- BucketedHashContainer, src/BestPathContainer.hpp:291-483
+		// The `top1` mode (> 512 incoming paths, BestPathContainer.hpp:229-276) is an std::unordered_set in the reference and a
+		// thread_local one: its iteration order is libstdc++'s bucket order, and its bucket count only ever grows, so the order
+		// depends on the largest container seen so far in the process.  The restatement uses the same library container with the
+		// reference's hash and equality and keeps it alive across sentences (resetHistory() = a fresh process).
+		struct WHash { size_t operator()(const WordLL& w) const { return (size_t)w.hashv; } };
+		struct WEq
+		{
+			bool operator()(const WordLL& a, const WordLL& b) const
+			{
+				return a.prevRootId == b.prevRootId && a.spState == b.spState && a.lmState == b.lmState && (!a.cmpSb || a.sb == b.sb);
+			}
+		};
 		struct Container
 		{
 			std::vector<WordLL> buckets[4];
-			int mode = 0;   // 0 small (1 bucket), 1 medium (4 buckets), 2 "top1" (unbounded, insertion order)
-			void clear() { for (auto& b : buckets) b.clear(); }
+			std::unordered_set<WordLL, WHash, WEq> top1;
+			int mode = 0;   // 0 small (1 bucket), 1 medium (4 buckets), 2 "top1" (unordered_set)
+			void clear() { for (auto& b : buckets) b.clear(); top1.clear(); }
 		};
 		Container cont;
+		void resetHistory() { cont.top1 = std::unordered_set<WordLL, WHash, WEq>{}; }
 
 		void contInsert(uint8_t prevRootId, uint8_t rootId, int32_t morph, float accScore, float firstChunkScore,
 			float accTypoCost, float accDialectCost, int32_t pNode, int32_t pIdx, uint8_t parentRootId, int32_t lmState, uint8_t spState, uint32_t ctxIdx = 0, const SbHist* sbh = nullptr)
@@ -236,6 +253,24 @@ namespace orc
 				h = (v * 2305843009213693951ull) ^ ((v << 33) | (v >> 31));
 			}
 			h = ((uint16_t)prevRootId | ((uint16_t)spState << 8)) ^ ((h << 3) | (h >> 61)); // BestPathContainer.hpp:79-84
+			if (cont.mode == 2)
+			{
+				WordLL w;
+				w.morpheme = morph; w.accScore = accScore; w.firstChunkScore = firstChunkScore; w.accTypoCost = accTypoCost;
+				w.accDialectCost = accDialectCost; w.parentNode = pNode; w.parentIdx = pIdx; w.lmState = lmState; w.spState = spState; w.ctxIdx = ctxIdx;
+				if (sbh) { w.sb = *sbh; w.cmpSb = sbg ? 1 : 0; }
+				w.rootId = parentRootId;
+				w.prevRootId = prevRootId;
+				if (rootId != commonRootId) w.rootId = rootId;
+				w.hashv = h;
+				auto ins = cont.top1.emplace(w);
+				if (!ins.second)
+				{
+					auto& target = const_cast<WordLL&>(*ins.first);      // as the reference does: the key fields are equal
+					if (accScore > target.accScore) target = w;
+				}
+				return;
+			}
 			const size_t bucket = cont.mode == 1 ? ((h >> 8) & 3) : 0;
 			auto& value = cont.buckets[bucket];
 			size_t it = 0;
@@ -397,13 +432,15 @@ namespace orc
 			}
 			if (cnt) { size_t tot = 0; for (auto& b : cont.buckets) tot += b.size(); cnt->maxCont = std::max<uint64_t>(cnt->maxCont, tot); }
 			// writeTo, BestPathContainer.hpp:451-469
-			for (auto& b : cont.buckets) for (auto& p : b)
+			auto emit = [&](const WordLL& p)
 			{
 				resultOut.push_back(p);
 				auto& np = resultOut.back();
 				np.wid = lastSeqId;
 				if (isSingle(cur)) { np.combineSocket = cur.combine_socket; np.ownFormId = (uint16_t)ownFormId; }
-			}
+			};
+			if (cont.mode == 2) { for (auto& p : cont.top1) emit(p); }      // libstdc++ iteration order, as in the reference
+			else for (auto& bk : cont.buckets) for (auto& p : bk) emit(p);
 		}
 
 
@@ -437,13 +474,15 @@ namespace orc
 		{
 			const auto& cur = M(curId);
 			if (cnt) { size_t tot = 0; for (auto& b : cont.buckets) tot += b.size(); cnt->maxCont = std::max<uint64_t>(cnt->maxCont, tot); }
-			for (auto& b : cont.buckets) for (auto& p : b)
+			auto emit = [&](const WordLL& p)
 			{
 				resultOut.push_back(p);
 				auto& np = resultOut.back();
 				np.wid = lastSeqId;
 				if (isSingle(cur)) { np.combineSocket = cur.combine_socket; np.ownFormId = (uint16_t)ownFormId; }
-			}
+			};
+			if (cont.mode == 2) { for (auto& p : cont.top1) emit(p); }      // libstdc++ iteration order, as in the reference
+			else for (auto& bk : cont.buckets) for (auto& p : bk) emit(p);
 		}
 
 		// MorphemeEvaluator<CoNgramState>::eval, src/CoNgramModel.cpp:17-317

@@ -85,6 +85,11 @@ class Oracle:
         self.lib.orc_cong_counters(self.h, out.ctypes.data)
         return {"cgRows": int(out[0]), "cgMacs": int(out[1])}
 
+    def reset_history(self):
+        """fresh `top1` container (the reference's thread_local unordered_set of a new process)"""
+        self.lib.orc_reset_history.argtypes = [C.c_void_p]
+        self.lib.orc_reset_history(self.h)
+
     def close(self):
         if self.h:
             self.lib.orc_close(self.h); self.h = None
