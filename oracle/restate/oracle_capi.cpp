@@ -1,6 +1,7 @@
 // ORACLE C API (test infrastructure; loaded only by tests/, __graft_entry__.smoke() and bench.py's cpu legs).
 // Thin extern "C" wrapper over the CPU restatement so Python can compare it with the CUDA path through ctypes.
 #include "analyze.hpp"
+#include "typo.hpp"
 
 struct OrcHandle { orc::Image im; orc::Analyzer* an = nullptr; orc::Counters cnt; };
 
@@ -121,6 +122,41 @@ void orc_counters(void* p, uint64_t* out)
 {
 	auto* h = reinterpret_cast<OrcHandle*>(p);
 	out[0] = h->cnt.lmSteps; out[1] = h->cnt.pairs; out[2] = h->cnt.inserts; out[3] = h->cnt.pathsOut; out[4] = h->cnt.candEvals; out[5] = h->cnt.evalCalls;
+}
+
+
+// ---- typo graph: restated PreparedTypoTransformer::generateGraph over a flat typo image
+struct OrcTypo { orc::TypoImage im; };
+
+void* orc_typo_open(const char* path)
+{
+	try { auto* t = new OrcTypo; t->im.load(path); return t; }
+	catch (...) { return nullptr; }
+}
+void orc_typo_close(void* p) { delete reinterpret_cast<OrcTypo*>(p); }
+
+// raw UTF-16 text -> normalizeHangul -> graph; rows of 9 int32 {endPos, typoCost bits, prevOffset, siblingOffset, continualTypoIdx, dialect,
+// fromPool, off, len}; returns the node count (or -1 / -2), *normLen = length of the normalised string
+int orc_typo_graph(void* p, const uint16_t* text, int len, int32_t* rows, int maxRows, int* normLen)
+{
+	try
+	{
+		auto* t = reinterpret_cast<OrcTypo*>(p);
+		const std::u16string norm = orc::normalizeHangulPlain(std::u16string(reinterpret_cast<const char16_t*>(text), (size_t)len));
+		*normLen = (int)norm.size();
+		orc::TypoGraph tg{ t->im };
+		const auto g = tg.generate(norm);
+		if ((int)g.size() > maxRows) return -2;
+		for (size_t i = 0; i < g.size(); ++i)
+		{
+			int32_t* r = rows + 9 * i;
+			int32_t bits; std::memcpy(&bits, &g[i].typoCost, 4);
+			r[0] = (int32_t)g[i].endPos; r[1] = bits; r[2] = (int32_t)g[i].prevOffset; r[3] = (int32_t)g[i].siblingOffset; r[4] = g[i].continualTypoIdx;
+			r[5] = g[i].dialect; r[6] = g[i].fromPool ? 1 : 0; r[7] = (int32_t)g[i].off; r[8] = (int32_t)g[i].len;
+		}
+		return (int)g.size();
+	}
+	catch (...) { return -1; }
 }
 
 }

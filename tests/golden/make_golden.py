@@ -30,6 +30,18 @@ for model, mtype, prefix in [("knlm_small", "knlm", ""), ("cong_small", "cong", 
         with gzip.GzipFile(os.path.join(HERE, prefix + name + ".golden.txt.gz"), "wb", mtime=0) as f:
             f.write(data)
         manifest["files"][prefix + name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
+# typo graphs (PreparedTypoTransformer::generateGraph of the unmodified reference, node for node): the rules and sentence of the
+# reference's own test KiwiTypo.GenerateGraph (test/test_typo.cpp:8-22, 11 nodes) and the default basic typo set on real text
+for tset, name in [("kat", "inputs_typo_kat"), ("basic", "inputs_typo_kat"), ("basic", "inputs_web"), ("basic", "inputs_written"), ("basic", "inputs_dialect_typos")]:
+    tmp = "/tmp/typo_%s_%s.golden.txt" % (tset, name)
+    subprocess.run([os.path.join(REFDIR, "typo_tool"), "graphs", tset, os.path.join(HERE, name + ".txt"), tmp], check=True, timeout=300)
+    data = open(tmp, "rb").read()
+    key = "typo_%s_%s" % (tset, name)
+    with gzip.GzipFile(os.path.join(HERE, key + ".golden.txt.gz"), "wb", mtime=0) as f:
+        f.write(data)
+    manifest["files"][key] = {"lines": data.count(b"\nG ") + (1 if data.startswith(b"G ") else 0), "md5": hashlib.md5(data).hexdigest()}
+for tset in ["kat", "basic"]:
+    manifest["typo_%s_image_md5" % tset] = hashlib.md5(open(os.path.join(REFDIR, "models", "typo_%s.img" % tset), "rb").read()).hexdigest()
 # known-answer vectors of the CoNg int8 scorer and context trie (oracle/ref_build/tools/cong_probe.cpp)
 subprocess.run([os.path.join(REFDIR, "cong_probe"), os.path.join(REFDIR, "models", "cong_small"), "/tmp/cong_qgemm.golden.txt"], check=True)
 data = open("/tmp/cong_qgemm.golden.txt", "rb").read()

@@ -49,3 +49,18 @@ def read_cong_qgemm():
                 yield ("Q", m, n, [int(x) for x in p[3:3 + m]], [int(x) for x in p[3 + m:3 + m + n]], [float.fromhex(x) for x in p[3 + m + n:]])
             else:
                 yield ("P", int(p[1]), int(p[2]), int(p[3]), float.fromhex(p[4]), int(p[5]), int(p[6]))
+
+
+def read_typo_graphs(key):
+    """tests/golden/<key>.golden.txt.gz -> list of (normLen, [rows of 9 ints {endPos, typoCost bits, prev, sibling, continualTypoIdx, dialect, fromPool, off, len}])"""
+    import struct
+    out = []
+    with gzip.open(os.path.join(HERE, key + ".golden.txt.gz"), "rt") as f:
+        for line in f:
+            p = line.split()
+            if p[0] == "G":
+                out.append((int(p[2]), []))
+            else:
+                bits = struct.unpack("<i", struct.pack("<f", float.fromhex(p[2])))[0]
+                out[-1][1].append([int(p[1]), bits, int(p[3]), int(p[4]), int(p[5]), int(p[6]), 1 if p[7] == "R" else 0, int(p[8]), int(p[9])])
+    return out

@@ -10,6 +10,34 @@ CONG_IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "cong_small.img")
 SBG_IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "sbg_small.img")
 
 
+TYPO_IMAGES = {"kat": os.path.join(ROOT, "oracle", "_ref", "models", "typo_kat.img"), "basic": os.path.join(ROOT, "oracle", "_ref", "models", "typo_basic.img")}
+
+
+class TypoOracle:
+    """restated PreparedTypoTransformer::generateGraph over a flat typo image (oracle/restate/typo.hpp)"""
+    def __init__(self, image_path):
+        self.lib = C.CDLL(ORACLE_LIB)
+        self.lib.orc_typo_open.restype = C.c_void_p
+        self.lib.orc_typo_open.argtypes = [C.c_char_p]
+        self.lib.orc_typo_close.argtypes = [C.c_void_p]
+        self.lib.orc_typo_graph.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        self.h = self.lib.orc_typo_open(os.fsencode(image_path))
+        if not self.h:
+            raise RuntimeError("oracle: cannot open typo image " + image_path)
+
+    def graph(self, text: str):
+        u = np.ascontiguousarray(np.frombuffer(text.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
+        rows = np.zeros((8192, 9), np.int32); nl = C.c_int(0)
+        n = self.lib.orc_typo_graph(self.h, u.ctypes.data, len(u), rows.ctypes.data, len(rows), C.byref(nl))
+        if n < 0:
+            raise RuntimeError("oracle typo graph failed")
+        return nl.value, rows[:n].tolist()
+
+    def close(self):
+        if self.h:
+            self.lib.orc_typo_close(self.h); self.h = None
+
+
 class Oracle:
     def __init__(self, image_path=IMAGE):
         self.lib = C.CDLL(ORACLE_LIB)
