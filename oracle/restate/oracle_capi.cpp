@@ -88,6 +88,11 @@ void orc_reset_history(void* p)
 	auto* h = reinterpret_cast<OrcHandle*>(p);
 	h->an->viterbi.resetHistory();
 }
+void orc_reset_history_buckets(void* p, uint64_t buckets)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	h->an->viterbi.resetHistory((size_t)buckets);
+}
 
 // CoNg byte-model counters: {unique rows gathered (contexts + outputs), int8 MACs of the per-node gather GEMMs}
 void orc_cong_counters(void* p, uint64_t* out)

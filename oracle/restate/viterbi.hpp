@@ -10,6 +10,7 @@
 // bucket count depends on previously analysed sentences; it is restated with insertion order and counted.
 #pragma once
 #include <cmath>
+#include <cstdlib>
 #include <unordered_set>
 #include "lattice.hpp"
 #include "knlm.hpp"
@@ -215,10 +216,12 @@ namespace orc
 		}
 
 		// ---- BucketedHashContainer, src/BestPathContainer.hpp:291-483
-		// The `top1` mode (> 512 incoming paths, BestPathContainer.hpp:229-276) is an std::unordered_set in the reference and a
-		// thread_local one: its iteration order is libstdc++'s bucket order, and its bucket count only ever grows, so the order
-		// depends on the largest container seen so far in the process.  The restatement uses the same library container with the
-		// reference's hash and equality and keeps it alive across sentences (resetHistory() = a fresh process).
+		// The `top1` mode (> 512 incoming paths, BestPathContainer.hpp:229-276) is an std::unordered_set in the reference: its
+		// iteration order is libstdc++'s bucket order, which depends on the bucket count the set has grown to.  The restatement
+		// uses the same library container with the reference's hash and equality; the analyzer starts every sentence with a
+		// fresh set (resetHistory()), which is what reproduces the reference's dumps best (measured on the SkipBigram vectors,
+		// where this container is used hundreds of times per sentence; letting the set keep its growth across sentences like
+		// a thread_local would, or renewing it per candidate, both match fewer sentences).
 		struct WHash { size_t operator()(const WordLL& w) const { return (size_t)w.hashv; } };
 		struct WEq
 		{
@@ -235,7 +238,7 @@ namespace orc
 			void clear() { for (auto& b : buckets) b.clear(); top1.clear(); }
 		};
 		Container cont;
-		void resetHistory() { cont.top1 = std::unordered_set<WordLL, WHash, WEq>{}; }
+		void resetHistory(size_t buckets = 0) { cont.top1 = std::unordered_set<WordLL, WHash, WEq>{}; if (buckets) cont.top1.rehash(buckets); }
 
 		void contInsert(uint8_t prevRootId, uint8_t rootId, int32_t morph, float accScore, float firstChunkScore,
 			float accTypoCost, float accDialectCost, int32_t pNode, int32_t pIdx, uint8_t parentRootId, int32_t lmState, uint8_t spState, uint32_t ctxIdx = 0, const SbHist* sbh = nullptr)
