@@ -65,13 +65,15 @@ MODEL = "knlm"
 def work_counters(batch_texts, batch_size, seed):
     """Per-sentence algorithmic bytes from the instrumented oracle (committed under profiles/; recomputed on a sample if absent)."""
     from kiwi_b200 import bytemodel
-    path = os.path.join(ROOT, "profiles", "counters_r1.json")
-    if MODEL == "knlm" and os.path.exists(path):
+    name = "counters_r1.json" if MODEL == "knlm" else "counters_r1b_cong.json"
+    path = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(path):
         d = json.load(open(path))
         key = "batch%d_seed%d" % (batch_size, seed)
         if key in d:
             c = d[key]
-            return c, bytemodel.lattice_bytes(c) / c["sentences"], bytemodel.viterbi_bytes(c) / c["sentences"], "profiles/counters_r1.json"
+            extra = bytemodel.cong_bytes(c) if MODEL == "cong" else 0.0
+            return c, bytemodel.lattice_bytes(c) / c["sentences"], (bytemodel.viterbi_bytes(c) + extra) / c["sentences"], "profiles/" + name
     from tests.orc import Oracle
     o = Oracle(IMAGE)
     sample = batch_texts[:256]
@@ -79,7 +81,8 @@ def work_counters(batch_texts, batch_size, seed):
     c = o.work_counters()
     if MODEL == "cong": c.update(o.cong_counters())
     o.close()
-    return c, bytemodel.lattice_bytes(c) / c["sentences"], bytemodel.viterbi_bytes(c) / c["sentences"], "oracle sample of 256 sentences"
+    extra = bytemodel.cong_bytes(c) if MODEL == "cong" else 0.0
+    return c, bytemodel.lattice_bytes(c) / c["sentences"], (bytemodel.viterbi_bytes(c) + extra) / c["sentences"], "oracle sample of 256 sentences"
 
 
 def run_reference_cpu(texts, threads, repeats=1):
