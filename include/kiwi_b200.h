@@ -57,6 +57,22 @@ typedef struct {                                      /* capi.h:43-61 */
 	uint16_t dialect;
 } kiwi_token_info_t;
 
+typedef struct {                                      /* capi.h:72-86 (KiwiConfig, include/kiwi/Kiwi.h:150-167) */
+	uint8_t integrate_allomorph;
+	float cut_off_threshold;
+	float oov_rule_scale;
+	float oov_rule_bias;
+	float oov_chr_bias;
+	float oov_global_weight;
+	float oov_local_weight;
+	float oov_global_min_freq;
+	float space_penalty;
+	float typo_cost_weight;
+	uint32_t max_unk_form_size;
+	uint32_t max_unk_form_size_followed_by_j_class;
+	uint32_t space_tolerance;
+} kiwi_config_t;
+
 typedef struct {                                      /* capi.h:662-670, passed BY VALUE */
 	int match_options;
 	kiwi_morphset_h blocklist;
@@ -79,6 +95,11 @@ void kiwi_clear_error(void);                             /* capi.h:252 */
  * only the host-side marshalling pool; options / enabled_dialects are recorded in the image at flatten time. */
 kiwi_h kiwi_init(const char* model_path, int num_threads, int options, int enabled_dialects);
 int kiwi_close(kiwi_h handle);                           /* capi.h:771 */
+/* capi.h:607-615 (src/capi/kiwi_c.cpp:738-795).  The fields the hot path reads (cut-off threshold, oov rule scale / bias, space
+ * penalty, typo cost weight, unknown-form size limits, space tolerance) take effect at the next launch; the chr-model oov
+ * weights are stored and returned only (their match options are outside the path). */
+void kiwi_set_global_config(kiwi_h handle, kiwi_config_t config);
+kiwi_config_t kiwi_get_global_config(kiwi_h handle);
 
 kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_analyze_option_t option, kiwi_pretokenized_h pretokenized);  /* capi.h:684 */
 kiwi_res_h kiwi_analyze(kiwi_h handle, const char* text, int top_n, kiwi_analyze_option_t option, kiwi_pretokenized_h pretokenized);        /* capi.h:698 */

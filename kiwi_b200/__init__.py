@@ -45,6 +45,14 @@ def default_option(match_options: int = MATCH_ALL_WITH_NORMALIZING) -> AnalyzeOp
 TOKEN_DTYPE = np.dtype([("morph_id", "<u4"), ("position", "<u4"), ("score", "<f4"), ("length", "<u2"), ("tag", "u1"), ("flags", "u1")])
 
 
+class Config(C.Structure):
+    """kiwi_config_t (capi.h:72-86), passed and returned by value"""
+    _fields_ = [("integrate_allomorph", C.c_uint8), ("cut_off_threshold", C.c_float), ("oov_rule_scale", C.c_float), ("oov_rule_bias", C.c_float),
+                ("oov_chr_bias", C.c_float), ("oov_global_weight", C.c_float), ("oov_local_weight", C.c_float), ("oov_global_min_freq", C.c_float),
+                ("space_penalty", C.c_float), ("typo_cost_weight", C.c_float), ("max_unk_form_size", C.c_uint32),
+                ("max_unk_form_size_followed_by_j_class", C.c_uint32), ("space_tolerance", C.c_uint32)]
+
+
 class _Batch(C.Structure):
     _fields_ = [("n_sentences", C.c_int), ("token_offsets", C.POINTER(C.c_uint32)), ("tokens", C.c_void_p), ("scores", C.POINTER(C.c_float)),
                 ("status", C.POINTER(C.c_uint32)), ("ms_h2d", C.c_float), ("ms_lattice", C.c_float), ("ms_viterbi", C.c_float),
@@ -86,6 +94,10 @@ def load_library() -> C.CDLL:
     lib.kiwi_b200_debug_lattice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, AnalyzeOption]
     lib.kiwi_b200_debug_cong.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
     lib.kiwi_b200_model_type.argtypes = [C.c_void_p]
+    lib.kiwi_get_global_config.argtypes = [C.c_void_p]
+    lib.kiwi_get_global_config.restype = Config
+    lib.kiwi_set_global_config.argtypes = [C.c_void_p, Config]
+    lib.kiwi_set_global_config.restype = None
     lib.kiwi_b200_debug_timing.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.kiwi_b200_set_device.argtypes = [C.c_int]
     lib.kiwi_b200_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
@@ -253,3 +265,9 @@ class Kiwi:
         if self._lib.kiwi_b200_debug_timing(self._h, n, out.ctypes.data) != 0:
             raise KiwiError(_last_error(self._lib))
         return out
+
+    def get_global_config(self) -> Config:
+        return self._lib.kiwi_get_global_config(self._h)
+
+    def set_global_config(self, config: Config):
+        self._lib.kiwi_set_global_config(self._h, config)

@@ -18,6 +18,7 @@ struct kiwi_s
 	std::unique_ptr<Engine> engine;
 	std::mutex mtx;           // one stream + one scratch arena per handle: calls on one handle are serialised
 	int numThreads = 0;
+	float oovChrBias = 0, oovGlobalWeight = 35, oovLocalWeight = 3, oovGlobalMinFreq = 4;      // KiwiConfig defaults of the chr-model oov scorers (stored only)
 };
 
 struct kiwi_res
@@ -429,6 +430,40 @@ int kiwi_b200_debug_timing(kiwi_h handle, int n, uint64_t* out_start_end_ns)
 		return 0;
 	}
 	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+
+void kiwi_set_global_config(kiwi_h handle, kiwi_config_t config)
+{
+	if (!handle) return;
+	try
+	{
+		std::lock_guard<std::mutex> lk(handle->mtx);
+		kb2_config c = handle->engine->model.header.config;
+		c.integrate_allomorph = config.integrate_allomorph ? 1u : 0u;
+		c.cut_off_threshold = config.cut_off_threshold; c.oov_rule_scale = config.oov_rule_scale; c.oov_rule_bias = config.oov_rule_bias;
+		c.space_penalty = config.space_penalty; c.typo_cost_weight = config.typo_cost_weight;
+		c.max_unk_form_size = config.max_unk_form_size; c.max_unk_form_size_followed_by_jclass = config.max_unk_form_size_followed_by_j_class;
+		c.space_tolerance = config.space_tolerance;
+		handle->engine->setConfig(c);
+		handle->oovChrBias = config.oov_chr_bias; handle->oovGlobalWeight = config.oov_global_weight;
+		handle->oovLocalWeight = config.oov_local_weight; handle->oovGlobalMinFreq = config.oov_global_min_freq;
+	}
+	catch (const std::exception& e) { setError(e); }
+}
+
+kiwi_config_t kiwi_get_global_config(kiwi_h handle)
+{
+	kiwi_config_t config{};
+	if (!handle) return config;
+	const kb2_config& c = handle->engine->model.header.config;
+	config.integrate_allomorph = c.integrate_allomorph ? 1 : 0;
+	config.cut_off_threshold = c.cut_off_threshold; config.oov_rule_scale = c.oov_rule_scale; config.oov_rule_bias = c.oov_rule_bias;
+	config.oov_chr_bias = handle->oovChrBias; config.oov_global_weight = handle->oovGlobalWeight;
+	config.oov_local_weight = handle->oovLocalWeight; config.oov_global_min_freq = handle->oovGlobalMinFreq;
+	config.space_penalty = c.space_penalty; config.typo_cost_weight = c.typo_cost_weight;
+	config.max_unk_form_size = c.max_unk_form_size; config.max_unk_form_size_followed_by_j_class = c.max_unk_form_size_followed_by_jclass;
+	config.space_tolerance = c.space_tolerance;
+	return config;
 }
 
 int kiwi_b200_model_type(kiwi_h handle)

@@ -408,6 +408,13 @@ namespace kb
 		ck(e, "debugCong");
 	}
 
+	void Engine::setConfig(const kb2_config& cfg)
+	{
+		model.dev.cfg = cfg;
+		model.header.config = cfg;
+		if (g_constantsOwner == &model) g_constantsOwner = nullptr;
+	}
+
 	void Engine::debugTiming(uint32_t n, unsigned long long* out)
 	{
 		if (!main_.vv.timing || n > main_.capSent) throw std::runtime_error("debugTiming: no launch of that size yet");

@@ -60,6 +60,8 @@ namespace kb
 		int debugLattice(const uint16_t* text, uint32_t len, uint32_t matchOptions, std::vector<int32_t>& rows);
 		// per-sentence {start, end} ns of the last Viterbi launch of the main scratch (diagnostics)
 		void debugTiming(uint32_t n, unsigned long long* out);
+		// KiwiConfig fields read by the kernels; the constant-memory model view is refreshed at the next launch
+		void setConfig(const kb2_config& cfg);
 		// CoNg scorer self-test on the device (see cong_debug_kernel): n triples in, per-triple results + the tensor-core tile out
 		void debugCong(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
 			int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile);

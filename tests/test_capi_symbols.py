@@ -55,3 +55,11 @@ def test_image_header_layout_is_stable():
         with open(IMAGE, "rb") as f:
             magic, version = struct.unpack("<QI", f.read(12))
         assert magic == 0x31474D4932424B and version == 6
+
+
+def test_global_config_by_value_plumbing():
+    """kiwi_config_t crosses the ABI by value in both directions (capi.h:607-615); a NULL handle yields the zeroed struct."""
+    lib = kiwi_b200.load_library()
+    c = lib.kiwi_get_global_config(None)
+    assert c.cut_off_threshold == 0 and c.max_unk_form_size == 0 and ctypes.sizeof(kiwi_b200.Config) == 52
+    lib.kiwi_set_global_config(None, c)      # no-op on a NULL handle

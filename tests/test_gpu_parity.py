@@ -177,3 +177,22 @@ def test_result_assembly_forms_and_word_positions(kiwi, name):
     assert lib.kiwi_analyze_mw(kiwi._h, READER(reader), RECEIVER(receiver), None, 1, kiwi_b200.default_option()) == len(texts)
     for i, g in enumerate(gold):
         assert got[i] == g["forms"], (i, texts[i], got[i], g["forms"])
+
+
+def test_global_config_round_trip(kiwi, oracle):
+    """kiwi_get_global_config returns the KiwiConfig of the image (reference defaults, include/kiwi/Kiwi.h:150-167);
+    setting the same values back refreshes the constant-memory model view and must leave results untouched; a larger
+    cut-off threshold keeps more paths alive but cannot change the top-1 result of this sentence."""
+    c = kiwi.get_global_config()
+    assert (c.integrate_allomorph, c.cut_off_threshold, c.oov_rule_scale, c.oov_rule_bias, c.space_penalty, c.typo_cost_weight) == (1, 8.0, 4.0, 4.0, 7.0, 6.0)
+    assert (c.max_unk_form_size, c.max_unk_form_size_followed_by_j_class, c.space_tolerance) == (6, 0xFFFFFFFF, 0)
+    assert (c.oov_chr_bias, c.oov_global_weight, c.oov_local_weight, c.oov_global_min_freq) == (0.0, 35.0, 3.0, 4.0)
+    t = "설정 값을 다시 써도 분석 결과는 그대로여야 합니다."
+    before = kiwi.analyze_batch([t])
+    kiwi.set_global_config(c)
+    after = kiwi.analyze_batch([t])
+    assert before.sentence(0).tobytes() == after.sentence(0).tobytes() and before.scores[0] == after.scores[0]
+    otoks, oscore = oracle.analyze(t)
+    assert _tok4(after.sentence(0)) == [x[:4] for x in otoks] and _close(float(after.scores[0]), oscore)
+    c2 = kiwi.get_global_config()
+    assert c2.cut_off_threshold == 8.0 and c2.space_tolerance == 0
