@@ -12,13 +12,16 @@
 //   N <formIdx|-1> <uformOff|-1> <uformLen> <prev> <sibling> <startPos> <endPos> <spaceErrors> <typoCost>   x nNodes
 //   P <score> <prevState> <curState> <nTok>
 //   K <morphId> <begin> <end> <wordScore> <nodeId> <hasStr>                x nTok
-// The model type follows the environment variable KB_MODEL_TYPE (knlm, default, cong or sbg).
+// The model type follows the environment variable KB_MODEL_TYPE (knlm, default, cong or sbg).  KB_TYPO=basic analyses with the
+// default basic typo set prepared as the evaluator's `--typo` does (tools/Evaluator.cpp:79-144): option.typoTransformer =
+// getDefaultTypoSet(basicTypoSet).prepare(true), typoThreshold 2.5, KiwiConfig::typoCostWeight 6 (BASELINE.json config 4).
 // usage: dump_golden <model_dir> <input.txt> <out.txt> [maxLines]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <kiwi/Kiwi.h>
+#include <kiwi/TypoTransformer.h>
 #include "StrUtils.h"
 #include "KTrie.h"
 #include "PathEvaluator.h"
@@ -57,6 +60,13 @@ int main(int argc, char** argv)
 		std::string line;
 		size_t idx = 0;
 		AnalyzeOption option;
+		PreparedTypoTransformer ptt;
+		if (const char* ty = getenv("KB_TYPO"))
+		{
+			if (std::string{ ty } != "basic") throw std::runtime_error{ "KB_TYPO: only `basic` is known" };
+			ptt = getDefaultTypoSet(DefaultTypoSet::basicTypoSet).prepare(true);
+			option.typoTransformer = &ptt;
+		}
 		const KiwiConfig config = kw.globalConfig;
 		while (std::getline(ifs, line) && idx < maxLines)
 		{
@@ -91,7 +101,7 @@ int main(int argc, char** argv)
 					U16StringView{ normalizedStr.data() + splitEnd, normalizedStr.size() - splitEnd },
 					splitEnd, option.match, option.allowedDialects,
 					config.maxUnkFormSize, config.maxUnkFormSizeFollowedByJClass, config.spaceTolerance,
-					nullptr, option.typoThreshold, kw.continualTypoCost, kw.lengtheningTypoCost,
+					option.typoTransformer, option.typoThreshold, kw.continualTypoCost, kw.lengtheningTypoCost,
 					ptFirst, ptFirst);
 				ch.end = splitEnd;
 				if (ch.nodes.size() > 2)

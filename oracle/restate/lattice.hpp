@@ -4,6 +4,7 @@
 // Works on the flat model image; node order, prev/sibling offsets and positions follow the reference exactly.
 #pragma once
 #include "prep.hpp"
+#include "typo.hpp"
 
 namespace orc
 {
@@ -37,6 +38,9 @@ namespace orc
 		std::vector<int32_t> candidates;
 
 		WorkCounters* wc = nullptr;
+		// typo lattice (AnalyzeOption::typoTransformer / typoThreshold): a flat typo image, or nullptr for the plain 2-node graph
+		const TypoImage* typoImg = nullptr;
+		float typoThreshold = 2.5f;
 		explicit Splitter(const Image& _im) : im{ _im }, pat{ _im } {}
 
 		static constexpr uint32_t MATCH_ZCODA = 1u << 23, MATCH_SPLIT_SAISIOT = 1u << 25, MATCH_MERGE_SAISIOT = 1u << 26;
@@ -383,6 +387,219 @@ namespace orc
 			out.back().endPos = (uint32_t)nsToPos.size();
 		}
 
+
+		// ---- the general search over a typo graph (KTrie.cpp:998-1452, lengtheningTypoTolerant == false, no continual typos, no
+		// pretokenized spans).  One SearchState per (typo-graph node, surviving trie state); `search()` above is this loop for the
+		// 2-node graph.  Differences that matter: special-character runs are flushed at the end of EVERY zero-cost graph node,
+		// trie candidates of a replaced segment are only collected at its last character and must span it (`minFormLen`), and
+		// a candidate's start is shifted by the length difference of the replacements it crossed (`startPosOffset`).
+		struct SState
+		{
+			int32_t node = 0; float accumulatedCost = 0; uint32_t minFormLen = 0; int32_t startPosOffset = 0;
+			uint32_t specialStartNsPos = 0, unkFormStartNsPos = 0, lastSpaceBoundaryNsPos = 0; uint32_t lastChr = 0;
+		};
+
+		void progressTypoNode(const TypoNode& prevT, const TypoNode& tn, const SState& state, std::vector<SState>& curStates)
+		{
+			float typoCost = state.accumulatedCost + tn.typoCost;
+			if (typoCost > typoThreshold) return;
+			const u16* form = tn.fromPool ? typoImg->pool + tn.off : rawStr + tn.off;
+			const size_t formSize = tn.len;
+			uint32_t prevChr = state.lastChr;
+			uint8_t lastChrType = prevChr ? im.cls(prevChr) : (uint8_t)T_unknown;
+			uint8_t lastScriptType = prevChr ? im.script(prevChr) : 0;
+			size_t specialStartNsPos = state.specialStartNsPos, unkFormStartNsPos = state.unkFormStartNsPos, lastSpaceBoundaryNsPos = state.lastSpaceBoundaryNsPos;
+			size_t minFormLen = state.minFormLen;
+			int32_t startPosOffset = state.startPosOffset;
+			if (tn.typoCost > 0) startPosOffset += (int32_t)((ptrdiff_t)formSize - (ptrdiff_t)(tn.endPos - prevT.endPos));
+			int32_t curNode = state.node;
+			for (size_t j = 0; j < formSize; ++j)
+			{
+				const u16 c = form[j];
+				uint32_t c32 = c;
+				if (isHighSurrogate(c32) && j + 1 < formSize) c32 = mergeSurrogate(c32, form[j + 1]);
+				const size_t pos = tn.endPos + j - formSize;
+				if (typoCost == 0)
+				{
+					const bool isInPattern = nextMatchedPattern != matchedPatterns.size() &&
+						pos >= matchedPatterns[nextMatchedPattern].end - matchedPatterns[nextMatchedPattern].len;
+					uint8_t chrType = im.cls(c32);
+					uint8_t scriptType = im.script(c32);
+					if (lastChrType == T_sw && (c32 == 0x200d || (0x1f3fb <= c32 && c32 <= 0x1f3ff) || scriptType == im.h->script_variation_selectors))
+					{
+						chrType = lastChrType;
+						scriptType = lastScriptType;
+					}
+					if (isDiscontinuous(lastChrType, isInPattern ? (uint8_t)T_unknown : chrType, lastScriptType, scriptType)
+						|| lastChrType == T_sso || lastChrType == T_ssc)
+					{
+						if (lastChrType != T_max && lastChrType != T_unknown)
+						{
+							if (lastChrType != T_ss)
+							{
+								const bool hj = T_sf <= lastChrType && lastChrType <= T_sw;
+								if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, specialStartNsPos, hj);
+								insertUnkForm(unkFormStartNsPos, specialStartNsPos, hj);
+								specialRunNode(specialStartNsPos, pos, posToNs[pos], lastChrType);
+							}
+						}
+						unkFormStartNsPos = specialStartNsPos;
+						specialStartNsPos = posToNs[pos];
+						if (T_sf <= lastChrType && lastChrType <= T_sw) lastSpaceBoundaryNsPos = specialStartNsPos;
+					}
+					else if (chrType == T_max)
+					{
+						unkFormStartNsPos = specialStartNsPos;
+					}
+					lastChrType = isInPattern ? (uint8_t)T_unknown : chrType;
+					lastScriptType = scriptType;
+					if (c32 >= 0x10000) {}
+					else
+					{
+						if (chrType == T_unknown)   // whitespace
+						{
+							if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, posToNs[pos + 1], true);
+							insertUnkForm(unkFormStartNsPos, posToNs[pos + 1], true);
+							lastSpaceBoundaryNsPos = specialStartNsPos = unkFormStartNsPos = posToNs[pos + 1];
+							prevChr = c32;
+							continue;
+						}
+						const auto zf = isZFollowable(posToNs[pos]);
+						if ((matchOptions & MATCH_ZCODA) && zf.first && isHangulCoda(c) && (pos + 1 >= rawLen || !isHangulSyllable(rawStr[pos + 1])))
+						{
+							candidates.push_back((int32_t)(im.h->default_tag_size + (c - 0x11A8) - 1));
+						}
+						else if ((matchOptions & (MATCH_SPLIT_SAISIOT | MATCH_MERGE_SAISIOT)) && zf.second && c == 0x11BA && pos + 1 < rawLen && isHangulSyllable(rawStr[pos + 1]))
+						{
+							candidates.push_back((int32_t)(im.h->default_tag_size + (0x11BA - 0x11A8) - 1));
+						}
+					}
+				}
+				else
+				{
+					if (im.isSpace((u16)c32) && c32 < 0x10000)
+					{
+						lastSpaceBoundaryNsPos = specialStartNsPos = unkFormStartNsPos = posToNs[pos + 1];
+						prevChr = c32;
+						continue;
+					}
+				}
+				if (tn.typoCost == 0 && nextMatchedPattern != matchedPatterns.size())
+				{
+					const size_t currentEnd = pos + (c32 >= 0x10000 ? 2 : 1);
+					while (nextMatchedPattern != matchedPatterns.size() && matchedPatterns[nextMatchedPattern].end == currentEnd)
+					{
+						const auto mp = matchedPatterns[nextMatchedPattern];
+						const size_t matchedStart = mp.end - mp.len;
+						const bool hj = T_w_url <= mp.tag && mp.tag <= T_w_emoji;
+						if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, posToNs[matchedStart], hj);
+						insertUnkForm(unkFormStartNsPos, posToNs[matchedStart], hj);
+						if (appendNewNode(posToNs[matchedStart], posToNs[mp.end], -1, (int32_t)(startOffset + matchedStart), (uint32_t)(mp.end - matchedStart)))
+						{
+							out.back().form = im.trieNodes[mp.tag].value;
+						}
+						++nextMatchedPattern;
+					}
+				}
+				if (c32 >= 0x10000)
+				{
+					++j;
+					prevChr = c32;
+					continue;
+				}
+				prevChr = c32;
+
+				if (minFormLen > 0 || tn.typoCost > 0) ++minFormLen;
+				int32_t nextNode = nextOpt(curNode, c);
+				while (nextNode < 0)
+				{
+					curNode = failOf(curNode);
+					if (curNode < 0) break;
+					nextNode = nextOpt(curNode, c);
+				}
+				if (nextNode >= 0)
+				{
+					curNode = nextNode;
+					// with a typo only candidates that cover the whole replaced segment are searched, at its last character
+					if (tn.typoCost == 0 || j == formSize - 1)
+					{
+						if (typoCost > 0 && im.trieNodes[curNode].depth < minFormLen) {}      // early pruning
+						else
+						{
+							for (int32_t sub = curNode; sub >= 0; sub = failOf(sub))
+							{
+								const int32_t v = im.trieNodes[sub].value;
+								if (wc && sub != curNode) wc->trieVisits++;
+								if (v == KB2_TRIE_NONE) break;
+								else if (v != KB2_TRIE_SUBMATCH)
+								{
+									if (im.formLen(v) < minFormLen) break;
+									candidates.push_back(v);
+								}
+							}
+						}
+					}
+				}
+				else
+				{
+					if (typoCost == 0) curNode = 0;
+					else return;
+				}
+				flushCandidates(posToNs[pos + 1], startPosOffset, unkFormStartNsPos, lastSpaceBoundaryNsPos, typoCost);
+			}
+			if (typoCost == 0 && lastChrType != T_max && lastChrType != T_unknown)
+			{
+				if (lastChrType != T_ss)
+				{
+					const bool hj = T_sf <= lastChrType && lastChrType <= T_sw;
+					if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, specialStartNsPos, hj);
+					insertUnkForm(unkFormStartNsPos, specialStartNsPos, hj);
+					specialRunNode(specialStartNsPos, tn.endPos, posToNs[tn.endPos], lastChrType);
+					unkFormStartNsPos = specialStartNsPos;
+					if (hj) lastSpaceBoundaryNsPos = posToNs[tn.endPos];
+				}
+			}
+			if (typoCost > 0 && im.trieNodes[curNode].depth < minFormLen) {}      // early pruning
+			else
+			{
+				SState ns;
+				ns.node = curNode; ns.accumulatedCost = typoCost; ns.minFormLen = (uint32_t)minFormLen; ns.startPosOffset = startPosOffset;
+				ns.specialStartNsPos = (uint32_t)specialStartNsPos; ns.unkFormStartNsPos = (uint32_t)unkFormStartNsPos; ns.lastSpaceBoundaryNsPos = (uint32_t)lastSpaceBoundaryNsPos;
+				ns.lastChr = prevChr;
+				curStates.push_back(ns);
+			}
+		}
+
+		void searchTypo(const std::vector<TypoNode>& graph)
+		{
+			const size_t totEndPos = nsToPos.back() + 1;
+			std::vector<std::vector<SState>> states(graph.size());
+			states[0].emplace_back();
+			for (size_t i = 1; i < graph.size(); ++i)
+			{
+				const TypoNode& tn = graph[i];
+				auto& curStates = states[i];
+				if (tn.prevOffset)
+				{
+					for (size_t p = i - tn.prevOffset;; p += graph[p].siblingOffset)
+					{
+						for (const auto& st : states[p]) progressTypoNode(graph[p], tn, st, curStates);
+						if (!graph[p].siblingOffset) break;
+					}
+				}
+				if (tn.typoCost == 0 && tn.endPos == totEndPos)
+				{
+					for (const auto& st : curStates)
+					{
+						if (st.lastSpaceBoundaryNsPos < st.unkFormStartNsPos) insertUnkForm(st.lastSpaceBoundaryNsPos, posToNs[totEndPos], true);
+						insertUnkForm(st.unkFormStartNsPos, posToNs[totEndPos], true);
+					}
+				}
+			}
+			appendNewNode(nsToPos.size(), nsToPos.size() + 1, -1, -1, 0);
+			out.back().endPos = (uint32_t)nsToPos.size();
+		}
+
 		// KTrie.cpp:240-299
 		void removeUnconnected(std::vector<LNode>& ret) const
 		{
@@ -446,7 +663,14 @@ namespace orc
 			endPosMap.assign(nsToPos.size() + 1, std::make_pair((uint32_t)-1, (uint32_t)-1));
 			endPosMap[0] = std::make_pair(0u, 1u);
 			out.emplace_back();
-			search();
+			if (typoImg)
+			{
+				// buildTypoGraph (KTrie.cpp:873-895): the graph over the chunk [0, stopPos)
+				TypoGraph tg{ *typoImg };
+				const auto graph = tg.generate(std::u16string(reinterpret_cast<const char16_t*>(str), stopPos));
+				searchTypo(graph);
+			}
+			else search();
 			removeUnconnected(ret);
 			if (wc) { wc->nodesBuilt += out.size(); wc->nodesFinal += ret.size(); }
 			for (size_t i = 1; i + 1 < ret.size(); ++i)

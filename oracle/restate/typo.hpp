@@ -17,7 +17,7 @@
 #include <unordered_map>
 #include <vector>
 #include "../../include/kiwi_b200_typo.h"
-#include "viterbi.hpp"      // ftVowel (FeatureTestor::isMatched(CondVowel)), isHangulSyllable
+#include "feature.hpp"      // ftVowel (FeatureTestor::isMatched(CondVowel)), isHangulSyllable
 
 namespace orc
 {
