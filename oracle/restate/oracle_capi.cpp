@@ -140,6 +140,15 @@ void* orc_typo_open(const char* path)
 }
 void orc_typo_close(void* p) { delete reinterpret_cast<OrcTypo*>(p); }
 
+// AnalyzeOption::withTypoTransformer (include/kiwi/Kiwi.h:127-133): analyse with a typo lattice from now on (typo == nullptr: off).
+// The typo handle must outlive the analyzer's use of it.
+void orc_set_typo(void* p, void* typo, float threshold)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	h->an->splitter.typoImg = typo ? &reinterpret_cast<OrcTypo*>(typo)->im : nullptr;
+	h->an->splitter.typoThreshold = threshold;
+}
+
 // raw UTF-16 text -> normalizeHangul -> graph; rows of 9 int32 {endPos, typoCost bits, prevOffset, siblingOffset, continualTypoIdx, dialect,
 // fromPool, off, len}; returns the node count (or -1 / -2), *normLen = length of the normalised string
 int orc_typo_graph(void* p, const uint16_t* text, int len, int32_t* rows, int maxRows, int* normLen)

@@ -30,6 +30,16 @@ for model, mtype, prefix in [("knlm_small", "knlm", ""), ("cong_small", "cong", 
         with gzip.GzipFile(os.path.join(HERE, prefix + name + ".golden.txt.gz"), "wb", mtime=0) as f:
             f.write(data)
         manifest["files"][prefix + name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
+# typo-tolerant analysis (BASELINE.json config 4: AnalyzeOption::typoTransformer = basicTypoSet.prepare(true), typoThreshold 2.5,
+# typoCostWeight 6) with the Knlm model: typo6_<name>.golden.txt.gz
+for name in ["inputs_ref_tests", "inputs_web", "inputs_written", "inputs_dialect_typos"]:
+    tmp = os.path.join("/tmp", "typo6_" + name + ".golden.txt")
+    env = dict(os.environ, KIWI_ARCH_TYPE="avx2", KB_MODEL_TYPE="knlm", KB_TYPO="basic")
+    subprocess.run([os.path.join(REFDIR, "dump_golden"), os.path.join(REFDIR, "models", "knlm_small"), os.path.join(HERE, name + ".txt"), tmp], check=True, env=env, timeout=600)
+    data = open(tmp, "rb").read()
+    with gzip.GzipFile(os.path.join(HERE, "typo6_" + name + ".golden.txt.gz"), "wb", mtime=0) as f:
+        f.write(data)
+    manifest["files"]["typo6_" + name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
 # typo graphs (PreparedTypoTransformer::generateGraph of the unmodified reference, node for node): the rules and sentence of the
 # reference's own test KiwiTypo.GenerateGraph (test/test_typo.cpp:8-22, 11 nodes) and the default basic typo set on real text
 for tset, name in [("kat", "inputs_typo_kat"), ("basic", "inputs_typo_kat"), ("basic", "inputs_web"), ("basic", "inputs_written"), ("basic", "inputs_dialect_typos")]:

@@ -113,6 +113,12 @@ class Oracle:
         self.lib.orc_cong_counters(self.h, out.ctypes.data)
         return {"cgRows": int(out[0]), "cgMacs": int(out[1])}
 
+    def set_typo(self, typo, threshold: float = 2.5):
+        """analyse with a typo lattice (AnalyzeOption::withTypoTransformer); `typo` is a TypoOracle or None"""
+        self.lib.orc_set_typo.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        self._typo = typo       # keep the image alive
+        self.lib.orc_set_typo(self.h, typo.h if typo else None, threshold)
+
     def reset_history(self):
         """fresh `top1` container (the reference's thread_local unordered_set of a new process)"""
         self.lib.orc_reset_history.argtypes = [C.c_void_p]
