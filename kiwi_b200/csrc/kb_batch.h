@@ -7,6 +7,7 @@
 //   NC_s  = nodes_per_unit * W_s                     lattice-node capacity; nbase = nodes_per_unit * wbase
 #pragma once
 #include <stdint.h>
+#include "../../include/kiwi_b200_typo.h"
 
 namespace kb
 {
@@ -62,7 +63,36 @@ namespace kb
 		unsigned long long* timing;  // [2 * n_sent] %globaltimer at the start / end of every sentence's Viterbi (diagnostics: the kernel time is its slowest sentence)
 	};
 
-	enum : uint32_t { ST_OK = 0, ST_NODE_OVERFLOW = 1, ST_CHUNK_OVERFLOW = 2, ST_PATH_OVERFLOW = 3, ST_TOKEN_OVERFLOW = 4, ST_TOO_LONG = 5, ST_INTERNAL = 6 };
+	enum : uint32_t { ST_OK = 0, ST_NODE_OVERFLOW = 1, ST_CHUNK_OVERFLOW = 2, ST_PATH_OVERFLOW = 3, ST_TOKEN_OVERFLOW = 4, ST_TOO_LONG = 5, ST_INTERNAL = 6, ST_TYPO_OVERFLOW = 7 };
+
+	// ---- typo lattice (AnalyzeOption::typoTransformer, BASELINE.json config 4) -------------------------------
+	struct alignas(8) DTypoNode       // 24 B typo-graph node (TypoGraphNode, /root/reference/include/kiwi/TypoTransformer.h:130-156)
+	{
+		uint32_t end_pos; float typo_cost;
+		uint32_t prev, sibling;       // relative offsets in the final graph (absolute ids while it is being built)
+		uint32_t off; uint16_t len;   // form: chunk[off, off+len) or pool[off, off+len)
+		uint8_t from_pool, continual_idx;
+	};
+	struct alignas(16) DTypoState     // 32 B search state (Splitter::SearchState, /root/reference/src/KTrie.cpp:672-707)
+	{
+		int32_t node; float acc_cost; uint32_t min_form_len; int32_t start_pos_offset;
+		uint32_t special_start, unk_form_start, last_space_boundary, last_chr;
+	};
+	struct DTypoMatch { uint32_t end_pos, repl_off, size, pat_len; };
+
+	struct TypoView
+	{
+		// prepared typo transformer, device resident (include/kiwi_b200_typo.h); nodes == nullptr: no typo lattice
+		const kb2_typo_node* nodes; const uint16_t* keys; const int32_t* diffs; const kb2_typo_pat* pats; const kb2_typo_repl* repls; const uint16_t* pool;
+		float threshold;              // AnalyzeOption::typoThreshold
+		float continual_threshold;    // PreparedTypoTransformer::continualTypoThreshold, INFINITY = off
+		// per-sentence scratch: graph-node regions at graph_per_unit * wbase (capacity graph_per_unit * W_s), states at states_per_unit * wbase
+		uint32_t graph_per_unit, states_per_unit;
+		DTypoNode* tmp; DTypoNode* graph; uint32_t* remap;      // insertion-ordered nodes, final graph, old -> new index
+		uint2* state_range;           // per final graph node: [first, last) in `states`
+		DTypoState* states;
+		DTypoMatch* matches;          // graph_per_unit * W_s as well
+	};
 
 	struct BatchView
 	{
@@ -90,5 +120,6 @@ namespace kb
 		uint32_t* n_chunks;          // [n_sent]
 		uint32_t* status;            // [n_sent]
 		uint32_t* debug;             // [64] anomaly record of the first internal-consistency failure (diagnostics)
+		TypoView typo;
 	};
 }

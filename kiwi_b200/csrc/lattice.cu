@@ -21,6 +21,13 @@
 namespace kb
 {
 	__constant__ DevModel c_m;
+	// lanes per sentence.  tests/hostsim compiles this file as plain C++ with a one-lane "warp" (KB_HOSTSIM, see
+	// tests/hostsim/shim/cuda_runtime.h) to check the kernel's logic against the golden lattices without a GPU.
+#ifdef KB_HOSTSIM
+	static constexpr uint32_t KB_W = 1;
+#else
+	static constexpr uint32_t KB_W = 32;
+#endif
 	static constexpr unsigned FULL = 0xFFFFFFFFu;
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
 	static constexpr uint32_t MATCH_NORMALIZE_CODA = 1u << 16, MATCH_ZCODA = 1u << 23, MATCH_SPLIT_SAISIOT = 1u << 25, MATCH_MERGE_SAISIOT = 1u << 26;
@@ -353,7 +360,7 @@ namespace kb
 			if (e.x == NPOS) return false;
 			const uint32_t scanStart = e.x > 1u ? e.x : 1u;
 			bool found = false;
-			for (uint32_t base = scanStart; base < e.y; base += 32)
+			for (uint32_t base = scanStart; base < e.y; base += KB_W)
 			{
 				const uint32_t i = base + lane;
 				bool hit = false;
@@ -376,7 +383,7 @@ namespace kb
 			const uint2 e = endPosMap[pos];
 			if (e.x == NPOS) return 0;
 			uint32_t acc = 0;
-			for (uint32_t base = e.x; base < e.y; base += 32)
+			for (uint32_t base = e.x; base < e.y; base += KB_W)
 			{
 				const uint32_t i = base + lane;
 				uint32_t f = 0;
@@ -433,10 +440,11 @@ namespace kb
 		}
 
 		// ---- one candidate of flushCandidates, KTrie.cpp:955-996 --------------------------------------
-		__device__ void flushCandidate(int32_t cand, uint32_t endPosition, uint32_t unkFormStartNsPos, uint32_t lastSpaceBoundaryNsPos)
+		__device__ void flushCandidate(int32_t cand, uint32_t endPosition, uint32_t unkFormStartNsPos, uint32_t lastSpaceBoundaryNsPos,
+			int32_t startPosOffset = 0, float typoCost = 0.f)
 		{
 			const DForm f = c_m.forms[cand];
-			const uint32_t nBegin = endPosition - f.size_no_space;
+			const uint32_t nBegin = endPosition - f.size_no_space + (uint32_t)startPosOffset;
 			const uint32_t nEnd = endPosition;
 			if (!(f.flags & FF_FIRST_IS_CODA))
 			{
@@ -445,7 +453,7 @@ namespace kb
 				insertUnkForm(unkFormStartNsPos, nBegin, hj);
 			}
 			const uint32_t spaceErrors = countSpaceErrors(cand, nBegin, nEnd);
-			if (spaceErrors <= c_m.cfg.space_tolerance) appendNewNode(nBegin, nEnd, cand, 0, 0, 0.f, spaceErrors);
+			if (spaceErrors <= c_m.cfg.space_tolerance) appendNewNode(nBegin, nEnd, cand, 0, 0, typoCost, spaceErrors);
 		}
 
 		// ---- trie step: child of `node` for key c, -1 if none (FrozenTrie.hpp:14-22).  Root: direct table. --
@@ -453,7 +461,7 @@ namespace kb
 		{
 			if (node == 0) return c_m.trie_root_next[c];
 			const kb2_trie_node nd = c_m.trie_nodes[node];
-			for (uint32_t base = 0; base < nd.num_nexts; base += 32)
+			for (uint32_t base = 0; base < nd.num_nexts; base += KB_W)
 			{
 				const uint32_t i = base + lane;
 				const uint32_t k = i < nd.num_nexts ? (uint32_t)c_m.trie_keys[nd.next_offset + i] : 0x10000u;
@@ -518,7 +526,7 @@ namespace kb
 			// nsToPos / posToNs (837-854), lane-parallel: a unit is "non-space" unless isSpace; a low unit that
 			// follows a high surrogate is always kept with it.
 			uint32_t nsCount = 0;
-			for (uint32_t base = 0; base < n; base += 32)
+			for (uint32_t base = 0; base < n; base += KB_W)
 			{
 				const uint32_t i = base + lane;
 				bool keep = false;
@@ -696,6 +704,436 @@ namespace kb
 		}
 		int32_t zCand = -1;
 
+		// =================================================================================================
+		// Typo lattice (BASELINE config 4).  (1) the typo graph of the chunk, PreparedTypoTransformer::generateGraph
+		// (src/TypoTransformer.cpp:810-1039, appendNewNode 594-629) for the standard dialect; (2) the general walk of
+		// Splitter::search / progressNode (src/KTrie.cpp:998-1452) with one search state per (graph node, surviving trie
+		// state).  search() above is (2) for the 2-node graph.  Without continual / lengthening typo sets and
+		// pretokenized spans, as the rest of this kernel.
+		// The graph is built by lane 0 alone (a sequential Aho-Corasick walk with data-dependent appends); the walk
+		// over it is warp-uniform like search() and shares its lane-parallel helpers.
+		// =================================================================================================
+		DTypoNode* tg; DTypoNode* tgTmp; uint32_t* tgRemap; uint2* tgRange; DTypoState* tgStates; DTypoMatch* tgMatches;
+		uint32_t tgCap, tgStateCap, nTg;
+
+		__device__ int32_t typoNext(int32_t node, uint32_t c) const
+		{
+			const kb2_typo_node nd = bv.typo.nodes[node];
+			uint32_t lo = 0, hi = nd.num_nexts;
+			const uint16_t* k = bv.typo.keys + nd.next_offset;
+			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (k[mid] < c) lo = mid + 1; else hi = mid; }
+			if (lo == nd.num_nexts || k[lo] != c) return -1;
+			return node + bv.typo.diffs[nd.next_offset + lo];
+		}
+
+		// appendNewNode of the typo graph (TypoTransformer.cpp:594-629); `map` = endPosMap over [mapOffset, mapOffset + mapSize)
+		// holding {first, last} node ids per end position, NPOS = none.  startPos == NPOS: link to the previous node.
+		__device__ bool tgAppend(uint32_t& n, uint2* map, uint32_t mapSize, uint32_t mapOffset, bool fromPool, uint32_t off, uint32_t len,
+			uint32_t startPos, uint32_t endPos, float cost)
+		{
+			if (startPos != NPOS && (startPos < mapOffset || map[startPos - mapOffset].x == NPOS)) return false;
+			if (n >= tgCap) { err = ST_TYPO_OVERFLOW; return false; }
+			DTypoNode nn;
+			nn.end_pos = endPos; nn.typo_cost = cost; nn.sibling = 0; nn.off = off; nn.len = (uint16_t)len; nn.from_pool = fromPool ? 1 : 0; nn.continual_idx = 0;
+			nn.prev = startPos == NPOS ? n - 1 : map[startPos - mapOffset].x;
+			const uint32_t newId = n++;
+			tgTmp[newId] = nn;
+			if (endPos >= mapSize + mapOffset) return true;
+			uint2 slot = map[endPos - mapOffset];
+			if (slot.x == NPOS) slot.x = newId;
+			else tgTmp[slot.y].sibling = newId;
+			slot.y = newId;
+			map[endPos - mapOffset] = slot;
+			return true;
+		}
+
+		// insertBranch (TypoTransformer.cpp:842-1002): the matches [0, nM) overlap transitively
+		__device__ void tgInsertBranch(uint32_t& n, uint2* map, uint2& mapBack, uint32_t& last, uint32_t nM, const uint16_t* str)
+		{
+			DTypoMatch* M = tgMatches;
+			const uint32_t totStartPos = M[0].end_pos - M[0].pat_len;
+			const uint32_t totEndPos = M[nM - 1].end_pos;
+			const uint32_t mapSize = totEndPos - last + 1;
+			for (uint32_t i = 0; i < mapSize; ++i) map[i] = make_uint2(NPOS, NPOS);
+			map[0] = mapBack;
+			// break points: the branch start and every match end, ascending and unique (flags over [last, totEndPos] in ctr)
+			uint32_t* flag = ctr;
+			for (uint32_t i = 0; i < mapSize; ++i) flag[i] = 0;
+			flag[totStartPos - last] = 1;
+			for (uint32_t i = 0; i < nM; ++i) flag[M[i].end_pos - last] = 1;
+			// sort the matches by start position (ties carry different ends, whose relative order cannot reach the sorted graph)
+			for (uint32_t i = 1; i < nM; ++i)
+			{
+				const DTypoMatch m = M[i];
+				const uint32_t ms = m.end_pos - m.pat_len;
+				uint32_t j = i;
+				while (j > 0 && M[j - 1].end_pos - M[j - 1].pat_len > ms) { M[j] = M[j - 1]; --j; }
+				M[j] = m;
+			}
+			if (last < totStartPos) tgAppend(n, map, mapSize, last, false, last, totStartPos - last, last, totStartPos, 0.f);
+			{
+				uint32_t prevBp = totStartPos;
+				for (uint32_t q = totStartPos + 1; q <= totEndPos; ++q)
+				{
+					if (!flag[q - last]) continue;
+					tgAppend(n, map, mapSize, last, false, prevBp, q - prevBp, prevBp, q, 0.f);
+					prevBp = q;
+				}
+			}
+			const float continualThr = bv.typo.continual_threshold;
+			for (uint32_t mi = 0; mi < nM && !err; ++mi)
+			{
+				const DTypoMatch m = M[mi];
+				const uint32_t e = m.end_pos, s = e - m.pat_len;
+				// continualIdx: first unit of the replacement -> (index, node) (TypoTransformer.cpp:905-960)
+				uint16_t ckey[8]; uint32_t cnode[8]; uint32_t nCont = 0;
+				for (uint32_t j = 0; j < m.size; ++j)
+				{
+					const kb2_typo_repl repl = bv.typo.repls[m.repl_off + j];
+					if (repl.dialect != 0) continue;      // allowedDialect == standard
+					if (repl.left_cond == 2 /* CondVowel::vowel */)
+					{
+						if (s == 0 || !isHangulSyllable(str[s - 1])) continue;
+					}
+					else if (repl.left_cond == 1 /* any */)
+					{
+						if (s == 0) continue;
+					}
+					else if (repl.left_cond == 9 /* continual */ || repl.left_cond == 10 /* boundary */)
+					{
+						const bool continual = repl.left_cond == 9;
+						if (continual && (s == 0 || !isHangulSyllable(str[s - 1]))) continue;
+						if (continual && !(continualThr < 3.0e38f)) continue;
+						const float scale = continual ? continualThr : 1.f;
+						const uint16_t key = bv.typo.pool[repl.str_off];
+						uint32_t k = 0;
+						while (k < nCont && ckey[k] != key) ++k;
+						if (k == nCont)
+						{
+							if (nCont == 8) { err = ST_TYPO_OVERFLOW; break; }
+							if (tgAppend(n, map, mapSize, last, true, repl.str_off, 1, s, NPOS, repl.cost * scale / 2))
+							{
+								tgTmp[n - 1].end_pos = e;
+								tgTmp[n - 1].continual_idx = (uint8_t)(nCont + 1);
+								ckey[nCont] = key; cnode[nCont] = n - 1; ++nCont;
+								if (tgAppend(n, map, mapSize, last, true, repl.str_off + 1, repl.length - 1, NPOS, e, repl.cost * scale / 2)) tgTmp[n - 1].prev = cnode[k];
+							}
+						}
+						else
+						{
+							if (tgAppend(n, map, mapSize, last, true, repl.str_off + 1, repl.length - 1, NPOS, e, repl.cost * scale / 2)) tgTmp[n - 1].prev = cnode[k];
+						}
+						continue;
+					}
+					else
+					{
+						if (!ftVowel(s == 0, s ? str[s - 1] : 0, repl.left_cond)) continue;
+					}
+					tgAppend(n, map, mapSize, last, true, repl.str_off, repl.length, s, e, repl.cost);
+				}
+			}
+			mapBack = map[mapSize - 1];
+			last = totEndPos;
+		}
+
+		// generateGraph over raw[0, rawLen) -> tg[0, nTg), sorted by end position with relative prev / sibling offsets
+		__device__ void genTypoGraph()
+		{
+			uint32_t n = 0;
+			if (lane == 0)
+			{
+				uint2* map = endPosMap;        // free until search() (re)initialises it; rawLen + 2 <= W entries
+				const uint16_t* str = raw;
+				uint2 mapBack = make_uint2(0, 0);
+				uint32_t last = 0, nM = 0;
+				{
+					DTypoNode bos; bos.end_pos = 0; bos.typo_cost = 0.f; bos.prev = 0; bos.sibling = 0; bos.off = 0; bos.len = 0; bos.from_pool = 0; bos.continual_idx = 0;
+					tgTmp[n++] = bos;
+				}
+				int32_t node = typoNext(0, 0);
+				if (node < 0) err = ST_INTERNAL;
+				for (uint32_t i = 0; i < rawLen && !err; ++i)
+				{
+					const uint32_t c = str[i];
+					int32_t nnode = typoNext(node, c);
+					while (nnode < 0)
+					{
+						const int32_t fl = bv.typo.nodes[node].fail;
+						if (fl) { node += fl; nnode = typoNext(node, c); }
+						else { node = 0; break; }
+					}
+					if (nnode < 0) continue;
+					node = nnode;
+					const int32_t v = bv.typo.nodes[node].value;
+					if (v == -1) continue;
+					const uint32_t endPos = i + 1;
+					// a sub-match-only node carries patLength = -1 in the reference: its start wraps far beyond any end position
+					if (nM && (v < 0 || tgMatches[nM - 1].end_pos < endPos - bv.typo.pats[v].pat_len))
+					{
+						tgInsertBranch(n, map, mapBack, last, nM, str);
+						nM = 0;
+					}
+					for (int32_t sub = node; ; )
+					{
+						const kb2_typo_node sn = bv.typo.nodes[sub];
+						if (sn.value == -1) break;
+						if (sn.value != -2)
+						{
+							if (nM >= tgCap) { err = ST_TYPO_OVERFLOW; break; }
+							const kb2_typo_pat pt = bv.typo.pats[sn.value];
+							tgMatches[nM++] = DTypoMatch{ endPos, pt.repl_off, pt.size, pt.pat_len };
+						}
+						if (!sn.fail) break;
+						sub += sn.fail;
+					}
+				}
+				if (nM && !err) tgInsertBranch(n, map, mapBack, last, nM, str);
+				if (!err)
+				{
+					// the tail segment: registered nowhere, its end position becomes the chunk length (TypoTransformer.cpp:1014-1018)
+					map[0] = mapBack;
+					if (tgAppend(n, map, 1, last, false, last, rawLen - last, last, rawLen + 1, 0.f)) tgTmp[n - 1].end_pos = rawLen;
+				}
+				if (!err)
+				{
+					// stable sort by end position (a counting sort over [0, rawLen]) and renumbering of the links (1020-1036)
+					uint32_t* cnt = ctr;
+					for (uint32_t i = 0; i <= rawLen + 1; ++i) cnt[i] = 0;
+					for (uint32_t i = 0; i < n; ++i) cnt[tgTmp[i].end_pos + 1]++;
+					for (uint32_t i = 1; i <= rawLen + 1; ++i) cnt[i] += cnt[i - 1];
+					for (uint32_t i = 0; i < n; ++i) tgRemap[i] = cnt[tgTmp[i].end_pos]++;
+					for (uint32_t i = 0; i < n; ++i)
+					{
+						DTypoNode nd = tgTmp[i];
+						const uint32_t ni = tgRemap[i];
+						nd.prev = ni - tgRemap[nd.prev];
+						if (nd.sibling) nd.sibling = tgRemap[nd.sibling] - ni;
+						tg[ni] = nd;
+					}
+				}
+			}
+			__syncwarp();
+			nTg = __shfl_sync(FULL, n, 0);
+			err = __shfl_sync(FULL, err, 0);
+		}
+
+		// progressNode (KTrie.cpp:998-1412) for one (graph node, incoming state); returns false when the state dies
+		__device__ bool progressTypoNode(const DTypoNode& prevT, const DTypoNode& tn, const DTypoState& state, DTypoState& outState)
+		{
+			const uint32_t opt = bv.match_options;
+			const float typoCost = state.acc_cost + tn.typo_cost;
+			if (typoCost > bv.typo.threshold) return false;
+			const uint16_t* form = tn.from_pool ? bv.typo.pool + tn.off : raw + tn.off;
+			const uint32_t formSize = tn.len;
+			uint32_t prevChr = state.last_chr;
+			uint32_t lastChrType = T_unknown, lastScriptType = 0;
+			if (prevChr) { const uint32_t a = chrAttr(c_m, prevChr); lastChrType = attrCls(a); lastScriptType = attrScript(a); }
+			uint32_t specialStartNsPos = state.special_start, unkFormStartNsPos = state.unk_form_start, lastSpaceBoundaryNsPos = state.last_space_boundary;
+			uint32_t minFormLen = state.min_form_len;
+			int32_t startPosOffset = state.start_pos_offset;
+			if (tn.typo_cost > 0.f) startPosOffset += (int32_t)formSize - (int32_t)(tn.end_pos - prevT.end_pos);
+			int32_t curNode = state.node;
+			for (uint32_t j = 0; j < formSize; ++j)
+			{
+				const uint32_t c = form[j];
+				uint32_t c32 = c;
+				if (isHighSurrogate(c32) && j + 1 < formSize) c32 = mergeSurrogate(c32, form[j + 1]);
+				const uint32_t pos = tn.end_pos + j - formSize;
+				int32_t zc = -1;
+				if (typoCost == 0.f)
+				{
+					const bool isInPattern = nextPat != nPats && pos >= pats[nextPat].end - pats[nextPat].len;
+					const uint32_t attr = chrAttr(c_m, c32);
+					uint32_t chrType = attrCls(attr), scriptType = attrScript(attr);
+					if (lastChrType == T_sw && (c32 == 0x200d || (0x1f3fb <= c32 && c32 <= 0x1f3ff) || scriptType == c_m.script_variation_selectors))
+					{
+						chrType = lastChrType;
+						scriptType = lastScriptType;
+					}
+					if (isDiscontinuous(lastChrType, isInPattern ? (uint32_t)T_unknown : chrType, lastScriptType, scriptType)
+						|| lastChrType == T_sso || lastChrType == T_ssc)
+					{
+						if (lastChrType != T_max && lastChrType != T_unknown && lastChrType != T_ss)
+						{
+							const bool hj = T_sf <= lastChrType && lastChrType <= T_sw;
+							if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, specialStartNsPos, hj);
+							insertUnkForm(unkFormStartNsPos, specialStartNsPos, hj);
+							specialRunNode(specialStartNsPos, pos, posToNs[pos], lastChrType);
+						}
+						unkFormStartNsPos = specialStartNsPos;
+						specialStartNsPos = posToNs[pos];
+						if (T_sf <= lastChrType && lastChrType <= T_sw) lastSpaceBoundaryNsPos = specialStartNsPos;
+					}
+					else if (chrType == T_max)
+					{
+						unkFormStartNsPos = specialStartNsPos;
+					}
+					lastChrType = isInPattern ? (uint32_t)T_unknown : chrType;
+					lastScriptType = scriptType;
+					if (c32 < 0x10000)
+					{
+						if (chrType == T_unknown)      // whitespace
+						{
+							const uint32_t nx = posToNs[pos + 1];
+							if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, nx, true);
+							insertUnkForm(unkFormStartNsPos, nx, true);
+							lastSpaceBoundaryNsPos = specialStartNsPos = unkFormStartNsPos = nx;
+							prevChr = c32;
+							continue;
+						}
+						if ((opt & MATCH_ZCODA) && isHangulCoda(c) && (pos + 1 >= rawLen || !isHangulSyllable(raw[pos + 1])))
+						{
+							if (isZFollowable(posToNs[pos]) & FF_ZCODA) zc = (int32_t)(c_m.default_tag_size + (c - 0x11A8) - 1);
+						}
+						else if ((opt & (MATCH_SPLIT_SAISIOT | MATCH_MERGE_SAISIOT)) && c == 0x11BA && pos + 1 < rawLen && isHangulSyllable(raw[pos + 1]))
+						{
+							if (isZFollowable(posToNs[pos]) & FF_ZSIOT) zc = (int32_t)(c_m.default_tag_size + (0x11BA - 0x11A8) - 1);
+						}
+					}
+				}
+				else
+				{
+					if (c32 < 0x10000 && isSpaceChr(c_m, (uint16_t)c32))
+					{
+						lastSpaceBoundaryNsPos = specialStartNsPos = unkFormStartNsPos = posToNs[pos + 1];
+						prevChr = c32;
+						continue;
+					}
+				}
+				if (tn.typo_cost == 0.f && nextPat != nPats)
+				{
+					const uint32_t currentEnd = pos + (c32 >= 0x10000 ? 2 : 1);
+					while (nextPat != nPats && pats[nextPat].end == currentEnd)
+					{
+						const DPattern np = pats[nextPat];
+						const uint32_t matchedStart = np.end - np.len;
+						const bool hj = T_w_url <= np.tag && np.tag <= T_w_emoji;
+						const uint32_t ms = posToNs[matchedStart];
+						if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, ms, hj);
+						insertUnkForm(unkFormStartNsPos, ms, hj);
+						appendNewNode(ms, posToNs[np.end], c_m.trie_nodes[np.tag].value, startOffset + matchedStart, np.len, 0.f, 0);
+						++nextPat;
+					}
+				}
+				if (c32 >= 0x10000)
+				{
+					++j;
+					prevChr = c32;
+					continue;
+				}
+				prevChr = c32;
+
+				if (minFormLen > 0 || tn.typo_cost > 0.f) ++minFormLen;
+				int32_t nextNode = nextOpt(curNode, c);
+				while (nextNode < 0)
+				{
+					const int32_t fl = c_m.trie_nodes[curNode].fail;
+					if (!fl) { curNode = -1; break; }
+					curNode += fl;
+					nextNode = nextOpt(curNode, c);
+				}
+				const uint32_t endPosition = posToNs[pos + 1];
+				// the built-in z-coda / saisiot form is pushed before the trie candidates of this position (1126-1135) -> flushed first
+				if (zc >= 0) flushCandidate(zc, endPosition, unkFormStartNsPos, lastSpaceBoundaryNsPos, startPosOffset, typoCost);
+				if (nextNode >= 0)
+				{
+					curNode = nextNode;
+					// with a typo only the forms that cover the whole replaced segment are collected, at its last character (1291-1311)
+					if ((tn.typo_cost == 0.f || j == formSize - 1) && !(typoCost > 0.f && c_m.trie_nodes[curNode].depth < minFormLen))
+					{
+						for (int32_t sub = curNode; ; )
+						{
+							const kb2_trie_node sn = c_m.trie_nodes[sub];
+							if (sn.value == KB2_TRIE_NONE) break;
+							if (sn.value != KB2_TRIE_SUBMATCH)
+							{
+								if ((uint32_t)c_m.forms_raw[sn.value].str_len < minFormLen) break;
+								flushCandidate(sn.value, endPosition, unkFormStartNsPos, lastSpaceBoundaryNsPos, startPosOffset, typoCost);
+							}
+							if (!sn.fail) break;
+							sub += sn.fail;
+						}
+					}
+				}
+				else
+				{
+					if (typoCost == 0.f) curNode = 0;
+					else return false;
+				}
+			}
+			if (typoCost == 0.f && lastChrType != T_max && lastChrType != T_unknown && lastChrType != T_ss)
+			{
+				const bool hj = T_sf <= lastChrType && lastChrType <= T_sw;
+				if (lastSpaceBoundaryNsPos < unkFormStartNsPos) insertUnkForm(lastSpaceBoundaryNsPos, specialStartNsPos, hj);
+				insertUnkForm(unkFormStartNsPos, specialStartNsPos, hj);
+				specialRunNode(specialStartNsPos, tn.end_pos, posToNs[tn.end_pos], lastChrType);
+				unkFormStartNsPos = specialStartNsPos;
+				if (hj) lastSpaceBoundaryNsPos = posToNs[tn.end_pos];
+			}
+			if (typoCost > 0.f && c_m.trie_nodes[curNode].depth < minFormLen) return false;      // early pruning (1404)
+			outState.node = curNode; outState.acc_cost = typoCost; outState.min_form_len = minFormLen; outState.start_pos_offset = startPosOffset;
+			outState.special_start = specialStartNsPos; outState.unk_form_start = unkFormStartNsPos; outState.last_space_boundary = lastSpaceBoundaryNsPos;
+			outState.last_chr = prevChr;
+			return true;
+		}
+
+		// Splitter::search (KTrie.cpp:1414-1452) over tg[0, nTg)
+		__device__ void searchTypo()
+		{
+			const uint32_t totEndPos = nsToPos[nNs - 1] + 1;
+			uint32_t nStates = 0;
+			if (lane == 0)
+			{
+				DTypoState s0; s0.node = 0; s0.acc_cost = 0.f; s0.min_form_len = 0; s0.start_pos_offset = 0;
+				s0.special_start = 0; s0.unk_form_start = 0; s0.last_space_boundary = 0; s0.last_chr = 0;
+				tgStates[0] = s0;
+				tgRange[0] = make_uint2(0, 1);
+			}
+			nStates = 1;
+			__syncwarp();
+			for (uint32_t i = 1; i < nTg && !err; ++i)
+			{
+				const DTypoNode tn = tg[i];
+				const uint32_t first = nStates;
+				if (tn.prev)
+				{
+					for (uint32_t p = i - tn.prev; !err; )
+					{
+						const DTypoNode pt = tg[p];
+						const uint2 r = tgRange[p];
+						for (uint32_t si = r.x; si < r.y; ++si)
+						{
+							const DTypoState st = tgStates[si];
+							DTypoState ns;
+							if (!progressTypoNode(pt, tn, st, ns)) continue;
+							if (err) break;
+							if (nStates >= tgStateCap) { err = ST_TYPO_OVERFLOW; break; }
+							if (lane == 0) tgStates[nStates] = ns;
+							++nStates;
+							__syncwarp();
+						}
+						if (!pt.sibling) break;
+						p += pt.sibling;
+					}
+				}
+				if (lane == 0) tgRange[i] = make_uint2(first, nStates);
+				__syncwarp();
+				if (tn.typo_cost == 0.f && tn.end_pos == totEndPos)
+				{
+					for (uint32_t si = first; si < nStates; ++si)
+					{
+						const DTypoState st = tgStates[si];
+						if (st.last_space_boundary < st.unk_form_start) insertUnkForm(st.last_space_boundary, posToNs[totEndPos], true);
+						insertUnkForm(st.unk_form_start, posToNs[totEndPos], true);
+					}
+				}
+			}
+			// EOS node, as search()
+			appendNewNode(nNs, nNs + 1, -1, 0, 0, 0.f, 0);
+			if (lane == 0) out[nOut - 1].end_pos = nNs;
+			__syncwarp();
+		}
+
 		// ---- removeUnconnected + writeResult (240-299, 1454-1464), see DESIGN.md "lattice ordering" ------
 		// A node is connected iff it is the last node or it ends at a position where a connected node starts;
 		// all nodes ending at one position share that fate, so the stable sort by (connected, endPos) equals a
@@ -704,7 +1142,7 @@ namespace kb
 		__device__ uint32_t finalize(DNode* dst, uint32_t dstCap, uint32_t* newIndex, uint32_t stopPos)
 		{
 			uint32_t* needed = ctr;                     // [nNs + 2] : 0/1 flags, later counts / bases
-			for (uint32_t i = lane; i < nNs + 2; i += 32) needed[i] = 0;
+			for (uint32_t i = lane; i < nNs + 2; i += KB_W) needed[i] = 0;
 			__syncwarp();
 			const uint32_t lastId = nOut - 1;
 			const DNode lastNode = out[lastId];
@@ -716,7 +1154,7 @@ namespace kb
 				if (!needed[p]) continue;
 				const uint2 e = endPosMap[p];
 				if (e.x == NPOS) continue;
-				for (uint32_t base = e.x; base < e.y; base += 32)
+				for (uint32_t base = e.x; base < e.y; base += KB_W)
 				{
 					const uint32_t i = base + lane;
 					if (i < e.y)
@@ -729,9 +1167,9 @@ namespace kb
 			}
 			// count connected nodes per end position (the last node is handled separately: it is always last)
 			uint32_t* cnt = posToNs;                     // posToNs is dead after search(); [nNs + 2]
-			for (uint32_t i = lane; i < nNs + 2; i += 32) cnt[i] = 0;
+			for (uint32_t i = lane; i < nNs + 2; i += KB_W) cnt[i] = 0;
 			__syncwarp();
-			for (uint32_t base = 0; base < lastId; base += 32)
+			for (uint32_t base = 0; base < lastId; base += KB_W)
 			{
 				const uint32_t i = base + lane;
 				if (i < lastId)
@@ -743,14 +1181,14 @@ namespace kb
 			__syncwarp();
 			// exclusive prefix over positions -> base index of each end position
 			uint32_t running = 0;
-			for (uint32_t base = 0; base < nNs + 1; base += 32)
+			for (uint32_t base = 0; base < nNs + 1; base += KB_W)
 			{
 				const uint32_t i = base + lane;
 				const uint32_t v = i < nNs + 1 ? cnt[i] : 0;
 				uint32_t incl = v;
-				for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += t; }
+				for (int d = 1; d < (int)KB_W; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += t; }
 				if (i < nNs + 1) cnt[i] = running + incl - v;
-				running += __shfl_sync(FULL, incl, 31);
+				running += __shfl_sync(FULL, incl, KB_W - 1);
 			}
 			const uint32_t connectedCnt = running + 1;    // + the last node
 			__syncwarp();
@@ -758,9 +1196,9 @@ namespace kb
 			// `fill[p]` = next free slot among the nodes ending at p, in original index order
 			uint32_t* fill = needed;                      // reuse: store base+taken; we still need "needed" -> encode: needed stays in high bit
 			// copy needed flag into bit 31 of cnt-based fill array
-			for (uint32_t i = lane; i < nNs + 1; i += 32) fill[i] = (needed[i] ? 0x80000000u : 0u) | cnt[i];
+			for (uint32_t i = lane; i < nNs + 1; i += KB_W) fill[i] = (needed[i] ? 0x80000000u : 0u) | cnt[i];
 			__syncwarp();
-			for (uint32_t base = 0; base < lastId; base += 32)
+			for (uint32_t base = 0; base < lastId; base += KB_W)
 			{
 				const uint32_t i = base + lane;
 				DNode g;
@@ -814,12 +1252,8 @@ namespace kb
 	};
 
 	// ------------------------------------------------------------------------------------------------
-	__global__ void __launch_bounds__(128) lattice_kernel(const BatchView bv)
+	static __device__ void lattice_sentence(const BatchView& bv, const uint32_t slot, const uint32_t lane)
 	{
-		const uint32_t warpsPerBlock = blockDim.x >> 5;
-		const uint32_t lane = threadIdx.x & 31;
-		const uint32_t slot = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
-		if (slot >= bv.n_sent) return;
 		const uint32_t s = bv.order[slot];
 
 		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
@@ -837,7 +1271,7 @@ namespace kb
 
 		// ---- normalizeHangulWithPosition (StrUtils.h:493-520), lane-parallel with a ballot prefix
 		uint32_t outPos = 0;
-		for (uint32_t base = 0; base < n; base += 32)
+		for (uint32_t base = 0; base < n; base += KB_W)
 		{
 			const uint32_t i = base + lane;
 			uint32_t c = i < n ? text[i] : 0;
@@ -853,7 +1287,7 @@ namespace kb
 				norm[o] = (uint16_t)(c - coda);
 				if (coda) norm[o + 1] = (uint16_t)(coda + 0x11A7);
 			}
-			const uint32_t valid = min(32u, n - base);
+			const uint32_t valid = min(KB_W, n - base);
 			outPos += valid + __popc(two);
 		}
 		const uint32_t normLen = outPos;
@@ -869,7 +1303,7 @@ namespace kb
 			const uint32_t codaConv[27] = {
 				0, 0x11A8, 0x11A8, 0, 0x11AB, 0x11AB, 0, 0, 0x11AF, 0x11AF, 0x11AF, 0x11AF, 0x11AF, 0x11AF,
 				0x11AF, 0, 0, 0x11B8, 0, 0x11BA, 0, 0, 0, 0, 0, 0, 0 };
-			for (uint32_t base = 1; base < normLen; base += 32)
+			for (uint32_t base = 1; base < normLen; base += KB_W)
 			{
 				const uint32_t i = base + lane;
 				uint32_t nv = 0; bool wr = false;
@@ -896,6 +1330,14 @@ namespace kb
 		b.nsToPos = bv.ns_to_pos + wbase; b.posToNs = bv.pos_to_ns + wbase; b.endPosMap = bv.end_pos_map + wbase;
 		b.ctr = bv.ctr + wbase; b.pats = bv.patterns + wbase;
 		b.out = bv.build_nodes + nbase; b.outCap = nodeCap;
+		const bool typo = bv.typo.nodes != nullptr;
+		if (typo)
+		{
+			const size_t gbase = (size_t)bv.typo.graph_per_unit * wbase, sbase = (size_t)bv.typo.states_per_unit * wbase;
+			b.tgCap = bv.typo.graph_per_unit * W; b.tgStateCap = bv.typo.states_per_unit * W;
+			b.tgTmp = bv.typo.tmp + gbase; b.tg = bv.typo.graph + gbase; b.tgRemap = bv.typo.remap + gbase; b.tgRange = bv.typo.state_range + gbase;
+			b.tgMatches = bv.typo.matches + gbase; b.tgStates = bv.typo.states + sbase;
+		}
 		DNode* finalNodes = bv.nodes + nbase;
 		uint32_t* newIndex = bv.new_index + nbase;
 		while (splitEnd < normLen && !b.err)
@@ -911,7 +1353,12 @@ namespace kb
 				continue;       // 2-node graph: skipped by the caller (Kiwi.cpp:1119)
 			}
 			b.raw = str; b.rawLen = stopPos;
-			for (uint32_t i = lane; i < b.nNs + 1; i += 32) b.endPosMap[i] = make_uint2(NPOS, NPOS);
+			if (typo)
+			{
+				b.genTypoGraph();      // uses endPosMap / ctr as scratch: before they are initialised for the walk
+				if (b.err) break;
+			}
+			for (uint32_t i = lane; i < b.nNs + 1; i += KB_W) b.endPosMap[i] = make_uint2(NPOS, NPOS);
 			__syncwarp();
 			if (lane == 0)
 			{
@@ -922,7 +1369,8 @@ namespace kb
 			}
 			b.nOut = 1; b.lastEndPos = 0;
 			__syncwarp();
-			b.search();
+			if (typo) b.searchTypo();
+			else b.search();
 			if (b.err) break;
 			const uint32_t cnt = b.finalize(finalNodes + nodeOff, nodeCap - nodeOff, newIndex, stopPos);
 			if (b.err) break;
@@ -939,14 +1387,30 @@ namespace kb
 		if (lane == 0) { bv.n_chunks[s] = nChunks; bv.status[s] = b.err; }
 	}
 
+#ifndef KB_HOSTSIM
+	__global__ void __launch_bounds__(128) lattice_kernel(const BatchView bv)
+	{
+		const uint32_t warpsPerBlock = blockDim.x >> 5;
+		const uint32_t slot = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
+		if (slot >= bv.n_sent) return;
+		lattice_sentence(bv, slot, threadIdx.x & 31);
+	}
+#endif
+
 	cudaError_t set_model_lattice(const DevModel& m) { return cudaMemcpyToSymbol(c_m, &m, sizeof(DevModel)); }
 
 	cudaError_t launch_lattice(const DevModel&, const BatchView& bv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
+#ifdef KB_HOSTSIM
+		for (uint32_t slot = 0; slot < bv.n_sent; ++slot) lattice_sentence(bv, slot, 0);
+		(void)stream;
+		return cudaSuccess;
+#else
 		const uint32_t warpsPerBlock = 4;
 		const uint32_t blocks = (bv.n_sent + warpsPerBlock - 1) / warpsPerBlock;
 		lattice_kernel<<<blocks, warpsPerBlock * 32, 0, stream>>>(bv);
 		return cudaGetLastError();
+#endif
 	}
 }
