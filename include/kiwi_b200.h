@@ -39,6 +39,7 @@ typedef struct kiwi_res* kiwi_res_h;                  /* capi.h:31 */
 typedef struct kiwi_morphset* kiwi_morphset_h;        /* capi.h:36 */
 typedef struct kiwi_pretokenized* kiwi_pretokenized_h;/* capi.h:37 */
 typedef struct kiwi_prepared_typo* kiwi_prepared_typo_h; /* capi.h:38 */
+typedef struct kiwi_typo* kiwi_typo_h;                   /* capi.h:35 */
 typedef unsigned short kchar16_t;                     /* capi.h:39 */
 
 typedef struct {                                      /* capi.h:43-61 */
@@ -100,6 +101,21 @@ int kiwi_close(kiwi_h handle);                           /* capi.h:771 */
  * weights are stored and returned only (their match options are outside the path). */
 void kiwi_set_global_config(kiwi_h handle, kiwi_config_t config);
 kiwi_config_t kiwi_get_global_config(kiwi_h handle);
+
+/* Typo-tolerant analysis (BASELINE.json config 4): kiwi_analyze_option_t::typo_transformer / typo_threshold.
+ * kiwi_typo_get_default (capi.h:501; sets capi.h:484-492), kiwi_typo_get_basic (capi.h:480), kiwi_typo_prepare (capi.h:580),
+ * kiwi_prepared_typo_close (capi.h:588), kiwi_typo_close (capi.h:570).  A default set is prepared by loading the flat image
+ * typo_<set>.img (include/kiwi_b200_typo.h; <set> = basic, continual, ...; written by oracle/ref_build/tools/typo_tool.cpp
+ * from the reference's own prepared transformer) from the directory of the model opened last, or from $KIWI_B200_TYPO_DIR;
+ * kiwi_typo_init/add/copy/update/scale_cost (user-defined rule sets) are not provided.  Lengthening typo sets are refused. */
+kiwi_typo_h kiwi_typo_get_default(int kiwi_typo_set);
+kiwi_typo_h kiwi_typo_get_basic(void);
+int kiwi_typo_close(kiwi_typo_h handle);
+kiwi_prepared_typo_h kiwi_typo_prepare(kiwi_typo_h handle);
+int kiwi_prepared_typo_close(kiwi_prepared_typo_h handle);
+/* additive: a prepared transformer straight from a flat typo image (file / memory) */
+kiwi_prepared_typo_h kiwi_b200_typo_load(const char* typo_image_path);
+kiwi_prepared_typo_h kiwi_b200_typo_from_image(const void* bytes, size_t size);
 
 kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_analyze_option_t option, kiwi_pretokenized_h pretokenized);  /* capi.h:684 */
 kiwi_res_h kiwi_analyze(kiwi_h handle, const char* text, int top_n, kiwi_analyze_option_t option, kiwi_pretokenized_h pretokenized);        /* capi.h:698 */

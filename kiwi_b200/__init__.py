@@ -38,8 +38,41 @@ class AnalyzeOption(C.Structure):
                 ("dialect_cost", C.c_float), ("typo_transformer", C.c_void_p), ("typo_threshold", C.c_float)]
 
 
-def default_option(match_options: int = MATCH_ALL_WITH_NORMALIZING) -> AnalyzeOption:
-    return AnalyzeOption(match_options, None, 0, 0, 3.0, None, 2.5)
+def default_option(match_options: int = MATCH_ALL_WITH_NORMALIZING, typo: "PreparedTypo" = None, typo_threshold: float = 2.5) -> AnalyzeOption:
+    """AnalyzeOption{match} / .withTypoTransformer(typo, typo_threshold) (include/kiwi/Kiwi.h:69-133); keep `typo` alive while the option is used"""
+    return AnalyzeOption(match_options, None, 0, 0, 3.0, typo.handle if typo is not None else None, typo_threshold)
+
+
+TYPO_WITHOUT, TYPO_BASIC, TYPO_CONTINUAL, TYPO_BASIC_WITH_CONTINUAL, TYPO_LENGTHENING, TYPO_BASIC_WITH_CONTINUAL_AND_LENGTHENING, TYPO_DIALECT = range(7)   # capi.h:484-492
+
+
+class PreparedTypo:
+    """kiwi_prepared_typo_h: a prepared typo transformer resident on the device.  `PreparedTypo(path=...)` loads a flat typo image
+    (include/kiwi_b200_typo.h); `PreparedTypo(default_set=TYPO_BASIC)` is kiwi_typo_prepare(kiwi_typo_get_default(set))."""
+
+    def __init__(self, path: str = None, default_set: int = None, image_bytes: bytes = None):
+        self._lib = load_library()
+        if image_bytes is not None:
+            buf = (C.c_char * len(image_bytes)).from_buffer_copy(image_bytes)
+            self.handle = self._lib.kiwi_b200_typo_from_image(buf, len(image_bytes))
+        elif path is not None:
+            self.handle = self._lib.kiwi_b200_typo_load(os.fsencode(path))
+        else:
+            t = self._lib.kiwi_typo_get_default(TYPO_BASIC if default_set is None else default_set)
+            self.handle = self._lib.kiwi_typo_prepare(t) if t else None
+        if not self.handle:
+            raise KiwiError(_last_error(self._lib))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.kiwi_prepared_typo_close(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 TOKEN_DTYPE = np.dtype([("morph_id", "<u4"), ("position", "<u4"), ("score", "<f4"), ("length", "<u2"), ("tag", "u1"), ("flags", "u1")])
@@ -102,6 +135,14 @@ def load_library() -> C.CDLL:
     lib.kiwi_b200_set_device.argtypes = [C.c_int]
     lib.kiwi_b200_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.kiwi_b200_free.argtypes = [C.c_void_p]
+    for fn in ("kiwi_typo_get_default", "kiwi_typo_get_basic", "kiwi_typo_prepare", "kiwi_b200_typo_load", "kiwi_b200_typo_from_image"):
+        getattr(lib, fn).restype = C.c_void_p
+    lib.kiwi_typo_get_default.argtypes = [C.c_int]
+    lib.kiwi_typo_prepare.argtypes = [C.c_void_p]
+    lib.kiwi_typo_close.argtypes = [C.c_void_p]
+    lib.kiwi_b200_typo_load.argtypes = [C.c_char_p]
+    lib.kiwi_b200_typo_from_image.argtypes = [C.c_void_p, C.c_uint64]
+    lib.kiwi_prepared_typo_close.argtypes = [C.c_void_p]
     lib.kiwi_analyze_w.restype = C.c_void_p
     lib.kiwi_analyze_w.argtypes = [C.c_void_p, C.c_void_p, C.c_int, AnalyzeOption, C.c_void_p]
     lib.kiwi_res_close.argtypes = [C.c_void_p]

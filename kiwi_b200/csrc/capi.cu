@@ -21,6 +21,21 @@ struct kiwi_s
 	float oovChrBias = 0, oovGlobalWeight = 35, oovLocalWeight = 3, oovGlobalMinFreq = 4;      // KiwiConfig defaults of the chr-model oov scorers (stored only)
 };
 
+// typo handles (capi.h:35-38).  A kiwi_typo names one of the reference's default typo sets; preparing it loads the flat image
+// of that set as the reference prepared it (oracle/ref_build/tools/typo_tool.cpp writes typo_<set>.img): building a
+// PreparedTypoTransformer from rules natively is a host-side "next" row.
+struct kiwi_typo { int set; };
+struct kiwi_prepared_typo { kb::TypoDev dev; };
+static kiwi_typo g_defaultTypos[7] = { {0}, {1}, {2}, {3}, {4}, {5}, {6} };
+static std::string g_typoDir;      // directory of the last model image opened by kiwi_init
+
+struct TypoScope      // AnalyzeOption::typoTransformer for the calls made while the handle's mutex is held
+{
+	Engine* e;
+	TypoScope(Engine* _e, const kiwi_analyze_option_t& o) : e{ _e } { e->setTypo(o.typo_transformer ? &o.typo_transformer->dev : nullptr, o.typo_threshold); }
+	~TypoScope() { e->setTypo(nullptr, 2.5f); }
+};
+
 struct kiwi_res
 {
 	struct Tok { kiwi_token_info_t info; uint32_t morphId; std::u16string form; std::string form8; };
@@ -89,7 +104,6 @@ static void checkOption(const kiwi_analyze_option_t& o, int topN, kiwi_pretokeni
 {
 	if (topN != 1) throw std::invalid_argument("kiwi_b200 implements the top_n == 1 path only");
 	if (o.blocklist) throw std::invalid_argument("blocklist is outside the kiwi_b200 hot path");
-	if (o.typo_transformer) throw std::invalid_argument("typo_transformer is outside the kiwi_b200 hot path in this build");
 	if (o.allowed_dialects) throw std::invalid_argument("dialects other than standard are outside the kiwi_b200 hot path");
 	if (o.open_ending) throw std::invalid_argument("open_ending is not supported by this build");
 	if (pt) throw std::invalid_argument("pretokenized spans are outside the kiwi_b200 hot path");
@@ -189,6 +203,7 @@ static int analyzeMulti(kiwi_h handle, ReadFn&& readOne, kiwi_receiver_t receive
 			BatchOutput bo;
 			{
 				std::lock_guard<std::mutex> lk(handle->mtx);
+				TypoScope ts{ handle->engine.get(), option };
 				handle->engine->analyze(text.data(), off.data(), n, (uint32_t)option.match_options, bo);
 			}
 			for (uint32_t i = 0; i < n; ++i)
@@ -251,9 +266,79 @@ kiwi_h kiwi_init(const char* model_path, int num_threads, int options, int enabl
 		auto blob = readImageFile(model_path);
 		kiwi_h h = kiwi_b200_init_from_image(blob.data(), blob.size());
 		if (h) h->numThreads = num_threads;
+		if (h)
+		{
+			// typo_<set>.img files are looked up next to the model image (or inside the model directory)
+			std::string p = model_path;
+			FILE* probe = std::fopen((p + "/kiwi_b200.img").c_str(), "rb");
+			if (probe) std::fclose(probe);
+			else { const size_t sl = p.find_last_of('/'); p = sl == std::string::npos ? "." : p.substr(0, sl); }
+			g_typoDir = p;
+		}
 		return h;
 	}
 	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+// ---- typo transformers (capi.h:469-588, the subset the analysis option needs) -------------------------------------
+kiwi_typo_h kiwi_typo_get_default(int kiwi_typo_set)
+{
+	if (kiwi_typo_set < 0 || kiwi_typo_set > 6) { setError("kiwi_typo_get_default: unknown typo set"); return nullptr; }
+	return &g_defaultTypos[kiwi_typo_set];
+}
+
+kiwi_typo_h kiwi_typo_get_basic() { return &g_defaultTypos[1]; }
+
+int kiwi_typo_close(kiwi_typo_h handle)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	if (handle >= g_defaultTypos && handle < g_defaultTypos + 7) { setError("default typo sets must not be closed"); return KIWIERR_FAIL; }
+	return KIWIERR_INVALID_HANDLE;      // no other kiwi_typo is ever created by this build
+}
+
+kiwi_prepared_typo_h kiwi_b200_typo_from_image(const void* bytes, size_t size)
+{
+	try
+	{
+		auto* t = new kiwi_prepared_typo;
+		try { t->dev.load(bytes, size); }
+		catch (...) { delete t; throw; }
+		return t;
+	}
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+kiwi_prepared_typo_h kiwi_b200_typo_load(const char* path)
+{
+	try
+	{
+		FILE* f = std::fopen(path, "rb");
+		if (!f) throw std::runtime_error(std::string("cannot open typo image '") + path + "'");
+		std::fseek(f, 0, SEEK_END); const long n = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+		std::vector<char> blob((size_t)std::max(n, 0l));
+		const bool ok = std::fread(blob.data(), 1, blob.size(), f) == blob.size();
+		std::fclose(f);
+		if (!ok) throw std::runtime_error(std::string("short read on ") + path);
+		return kiwi_b200_typo_from_image(blob.data(), blob.size());
+	}
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+kiwi_prepared_typo_h kiwi_typo_prepare(kiwi_typo_h handle)
+{
+	if (!handle) { setError("invalid handle"); return nullptr; }
+	static const char* names[7] = { "none", "basic", "continual", "basic_continual", "lengthening", "basic_continual_lengthening", "dialect" };
+	const char* env = std::getenv("KIWI_B200_TYPO_DIR");
+	const std::string dir = env ? env : g_typoDir;
+	if (dir.empty()) { setError("kiwi_typo_prepare: open a model with kiwi_init first or set KIWI_B200_TYPO_DIR (typo_<set>.img is looked up there)"); return nullptr; }
+	return kiwi_b200_typo_load((dir + "/typo_" + names[handle->set] + ".img").c_str());
+}
+
+int kiwi_prepared_typo_close(kiwi_prepared_typo_h handle)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	delete handle;
+	return 0;
 }
 
 int kiwi_close(kiwi_h handle)
@@ -274,6 +359,7 @@ kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_
 		const uint32_t off[2] = { 0, len };
 		std::lock_guard<std::mutex> lk(handle->mtx);
 		BatchOutput bo;
+		TypoScope ts{ handle->engine.get(), option };
 		handle->engine->analyze(text, off, 1, (uint32_t)option.match_options, bo);
 		return makeRes(handle, text, len, bo, 0, (uint32_t)option.match_options);
 	}
@@ -345,6 +431,7 @@ const kiwi_b200_batch_t* kiwi_b200_analyze_batch(kiwi_h handle, const kchar16_t*
 		try
 		{
 			std::lock_guard<std::mutex> lk(handle->mtx);
+			TypoScope ts{ handle->engine.get(), option };
 			handle->engine->analyze(text, offsets, (uint32_t)n, (uint32_t)option.match_options, h->bo);
 		}
 		catch (...) { delete h; throw; }
@@ -374,6 +461,7 @@ float kiwi_b200_analyze_device(kiwi_h handle, const void* d_text, const void* d_
 	{
 		checkOption(option, 1, nullptr);
 		std::lock_guard<std::mutex> lk(handle->mtx);
+		TypoScope ts{ handle->engine.get(), option };
 		const float ms = handle->engine->analyzeDevice(reinterpret_cast<const uint16_t*>(d_text), reinterpret_cast<const uint32_t*>(d_offsets), (uint32_t)n, total_units, (uint32_t)option.match_options, out_tokens);
 		if (out_launches) *out_launches = handle->engine->last.kernelLaunches;
 		return ms;
@@ -398,6 +486,7 @@ int kiwi_b200_debug_lattice(kiwi_h handle, const kchar16_t* text, int len, int32
 	{
 		std::lock_guard<std::mutex> lk(handle->mtx);
 		std::vector<int32_t> rows;
+		TypoScope ts{ handle->engine.get(), option };
 		const int n = handle->engine->debugLattice(text, (uint32_t)len, (uint32_t)option.match_options, rows);
 		if (n < 0) throw std::runtime_error("lattice build failed with status " + std::to_string(-n));
 		if (n > max_rows) throw std::runtime_error("lattice has more rows than the caller's buffer");

@@ -8,6 +8,7 @@
 // Sentences whose scratch demand exceeds the arithmetic capacity (rare, e.g. 50 x the same syllable) are
 // re-run in a second, larger-capacity pass; a sentence that still does not fit is a hard error.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -35,6 +36,9 @@ namespace kb
 	}
 
 	static constexpr uint32_t DEFAULT_PATHS_PER_UNIT = 128, DEFAULT_PATHS_CONST = 8192;
+	// typo graph nodes / search states per normalised-unit slot (W_s = 2 n + 4 slots per sentence): the basic typo set needs < 4
+	// on the reference's evaluation texts (tests/test_hostsim_lattice.py); overflow -> ST_TYPO_OVERFLOW -> retry arena
+	static constexpr uint32_t DEFAULT_TYPO_GRAPH_PER_UNIT = 6, DEFAULT_TYPO_STATES_PER_UNIT = 6;
 
 	__global__ void length_kernel(uint32_t nSent, const uint32_t* __restrict__ textOff, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx)
 	{
@@ -76,7 +80,49 @@ namespace kb
 	void Engine::freeScratch(Scratch& sc)
 	{
 		for (void* p : sc.bufs) cudaFree(p);
+		for (void* p : sc.typoBufs) cudaFree(p);
 		sc = Scratch{};
+	}
+
+	// ---- typo lattice: the device-resident transformer and the per-sentence graph / state scratch ----------------
+	void TypoDev::load(const void* bytes, size_t size)
+	{
+		if (size < sizeof(kb2_typo_header)) throw std::runtime_error("typo image: too small");
+		blob.assign(reinterpret_cast<const char*>(bytes), reinterpret_cast<const char*>(bytes) + size);
+		const auto* h = reinterpret_cast<const kb2_typo_header*>(blob.data());
+		if (h->magic != KB2_TYPO_MAGIC) throw std::runtime_error("typo image: bad magic");
+		size_t o = sizeof(kb2_typo_header);
+		auto take = [&](size_t bytesOf) { o = (o + 15) / 16 * 16; const size_t at = o; o += bytesOf; return at; };
+		const size_t oNodes = take(sizeof(kb2_typo_node) * h->n_nodes), oKeys = take(2 * (size_t)h->n_edges), oDiffs = take(4 * (size_t)h->n_edges);
+		const size_t oPats = take(sizeof(kb2_typo_pat) * h->n_pats), oRepls = take(sizeof(kb2_typo_repl) * h->n_repls), oPool = take(2 * (size_t)h->n_pool);
+		if (o > size) throw std::runtime_error("typo image: truncated");
+		if (std::isfinite(h->lengthening_typo_threshold)) throw std::runtime_error("typo image: lengthening typo sets are outside the kiwi_b200 hot path");
+		ck(cudaMalloc(&dBlob, size), "cudaMalloc(typo image)");
+		ck(cudaMemcpy(dBlob, blob.data(), size, cudaMemcpyHostToDevice), "cudaMemcpy(typo image)");
+		const char* d = reinterpret_cast<const char*>(dBlob);
+		view = TypoView{};
+		view.nodes = reinterpret_cast<const kb2_typo_node*>(d + oNodes); view.keys = reinterpret_cast<const uint16_t*>(d + oKeys);
+		view.diffs = reinterpret_cast<const int32_t*>(d + oDiffs); view.pats = reinterpret_cast<const kb2_typo_pat*>(d + oPats);
+		view.repls = reinterpret_cast<const kb2_typo_repl*>(d + oRepls); view.pool = reinterpret_cast<const uint16_t*>(d + oPool);
+		view.continual_threshold = h->continual_typo_threshold;
+	}
+
+	TypoDev::~TypoDev() { if (dBlob) cudaFree(dBlob); }
+
+	void Engine::ensureTypoScratch(Scratch& sc, uint32_t gpu, uint32_t spu)
+	{
+		if (sc.typoCapUnits >= sc.capUnits && sc.typoGraphPerUnit == gpu && sc.typoStatesPerUnit == spu) return;
+		for (void* p : sc.typoBufs) cudaFree(p);
+		sc.typoBufs.clear();
+		auto alloc = [&](size_t bytes) { void* p = nullptr; ck(cudaMalloc(&p, std::max<size_t>(bytes, 256)), "cudaMalloc(typo scratch)"); sc.typoBufs.push_back(p); return p; };
+		const size_t G = sc.capUnits * gpu, S = sc.capUnits * spu;
+		TypoView& t = sc.typoScratch;
+		t = TypoView{};
+		t.graph_per_unit = gpu; t.states_per_unit = spu;
+		t.tmp = (DTypoNode*)alloc(G * sizeof(DTypoNode)); t.graph = (DTypoNode*)alloc(G * sizeof(DTypoNode));
+		t.remap = (uint32_t*)alloc(G * 4); t.state_range = (uint2*)alloc(G * 8); t.matches = (DTypoMatch*)alloc(G * sizeof(DTypoMatch));
+		t.states = (DTypoState*)alloc(S * sizeof(DTypoState));
+		sc.typoCapUnits = sc.capUnits; sc.typoGraphPerUnit = gpu; sc.typoStatesPerUnit = spu;
 	}
 
 	void Engine::ensureScratch(Scratch& sc, size_t U, size_t B, uint32_t ppu, uint32_t pc, uint32_t npu)
@@ -133,6 +179,17 @@ namespace kb
 	void Engine::bind(Scratch& sc, const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions)
 	{
 		sc.bv.n_sent = n; sc.bv.text = dText; sc.bv.text_off = dOffsets; sc.bv.match_options = matchOptions;
+		sc.bv.typo = TypoView{};
+		if (typo_)
+		{
+			// the retry arena carries 4 x the graph / state capacity, like its node capacity
+			const uint32_t mul = &sc == &retry_ ? 4 : 1;
+			ensureTypoScratch(sc, DEFAULT_TYPO_GRAPH_PER_UNIT * mul, DEFAULT_TYPO_STATES_PER_UNIT * mul);
+			TypoView v = sc.typoScratch;
+			v.nodes = typo_->view.nodes; v.keys = typo_->view.keys; v.diffs = typo_->view.diffs; v.pats = typo_->view.pats; v.repls = typo_->view.repls; v.pool = typo_->view.pool;
+			v.continual_threshold = typo_->view.continual_threshold; v.threshold = typoThreshold_;
+			sc.bv.typo = v;
+		}
 	}
 
 	static const Model* g_constantsOwner = nullptr;     // the constant-memory model view belongs to one engine at a time

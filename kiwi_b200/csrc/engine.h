@@ -25,6 +25,17 @@ namespace kb
 		~Model();
 	};
 
+	// a prepared typo transformer resident on the device (flat typo image, include/kiwi_b200_typo.h); an analysis option
+	// (kiwi_analyze_option_t::typo_transformer), shared read-only by any number of engines
+	struct TypoDev
+	{
+		std::vector<char> blob;
+		void* dBlob = nullptr;
+		TypoView view{};             // device pointers of the image sections + continual threshold; no scratch
+		void load(const void* bytes, size_t size);
+		~TypoDev();
+	};
+
 	struct BatchOutput
 	{
 		std::vector<uint32_t> tokOff;      // [n + 1]
@@ -62,6 +73,8 @@ namespace kb
 		void debugTiming(uint32_t n, unsigned long long* out);
 		// KiwiConfig fields read by the kernels; the constant-memory model view is refreshed at the next launch
 		void setConfig(const kb2_config& cfg);
+		// AnalyzeOption::typoTransformer / typoThreshold for the following analyze* calls (nullptr: plain lattice)
+		void setTypo(const TypoDev* typo, float threshold) { typo_ = typo; typoThreshold_ = threshold; }
 		// CoNg scorer self-test on the device (see cong_debug_kernel): n triples in, per-triple results + the tensor-core tile out
 		void debugCong(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
 			int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile);
@@ -72,6 +85,8 @@ namespace kb
 			size_t capUnits = 0, capSent = 0, capText = 0;
 			uint32_t pathsPerUnit = 0, pathsConst = 0, nodesPerUnit = 0;
 			std::vector<void*> bufs;
+			std::vector<void*> typoBufs; size_t typoCapUnits = 0; uint32_t typoGraphPerUnit = 0, typoStatesPerUnit = 0;
+			TypoView typoScratch{};
 			BatchView bv{};
 			VitView vv{};
 			uint32_t* tokOff = nullptr;      // [capSent + 1]
@@ -80,6 +95,8 @@ namespace kb
 			uint16_t* dText = nullptr; uint32_t* dOff = nullptr;
 			uint32_t* lenKeys = nullptr; uint32_t* lenKeysOut = nullptr; uint32_t* idxIn = nullptr; uint32_t* order = nullptr; void* sortTemp = nullptr; size_t sortTempBytes = 0;
 		};
+		const TypoDev* typo_ = nullptr; float typoThreshold_ = 2.5f;
+		void ensureTypoScratch(Scratch& sc, uint32_t graphPerUnit, uint32_t statesPerUnit);
 		Scratch main_, retry_;           // retry_: larger per-sentence capacity, only for sentences that overflowed main_
 		cudaEvent_t ev[6];
 		uint16_t* hPinText = nullptr; uint32_t* hPinOff = nullptr; size_t pinTextCap = 0, pinOffCap = 0;

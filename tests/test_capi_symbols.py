@@ -63,3 +63,21 @@ def test_global_config_by_value_plumbing():
     c = lib.kiwi_get_global_config(None)
     assert c.cut_off_threshold == 0 and c.max_unk_form_size == 0 and ctypes.sizeof(kiwi_b200.Config) == 52
     lib.kiwi_set_global_config(None, c)      # no-op on a NULL handle
+
+
+def test_typo_handle_conventions_without_gpu():
+    """kiwi_typo_get_default returns shared handles that must not be closed (capi.h:499,568); a flat typo image is uploaded to
+    the device on preparation, so without a GPU preparing fails loudly; a missing file is an error, not a fallback."""
+    lib = kiwi_b200.load_library()
+    h = lib.kiwi_typo_get_default(kiwi_b200.TYPO_BASIC)
+    assert h and h == lib.kiwi_typo_get_basic()
+    assert not lib.kiwi_typo_get_default(99)
+    assert lib.kiwi_typo_close(h) == -1
+    lib.kiwi_clear_error()
+    assert not lib.kiwi_b200_typo_load(b"/nonexistent/typo.img")
+    assert b"cannot open typo image" in lib.kiwi_error()
+    import torch
+    from tests.orc import TYPO_IMAGES
+    if not torch.cuda.is_available() and os.path.exists(TYPO_IMAGES["basic"]):
+        with pytest.raises(kiwi_b200.KiwiError, match="CUDA error"):
+            kiwi_b200.PreparedTypo(path=TYPO_IMAGES["basic"])
