@@ -7,7 +7,7 @@
  * image handling, device control); everything else keeps the reference's name, argument meaning and
  * error convention (never throws across the ABI; NULL / KIWIERR_* + kiwi_error() per calling thread).
  *
- * Out of scope: builder, typo transformer handles, morphset, pretokenized spans,
+ * Out of scope: builder, user-defined typo rule sets, morphset, pretokenized spans,
  * joiner, sub-word tokenizer, sentence splitter — passing a non-NULL handle for one of those is an error.
  */
 #ifndef KIWI_B200_H
