@@ -181,7 +181,14 @@ namespace kb
 	cudaError_t launch_emit(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
+#ifdef KB_HOSTSIM
+		(void)stream;
+		if (bv.n_sent != 1) return 1;
+		simt::launch(1, 1, [&] { emit_kernel(bv, vv); });      // thread-per-sentence kernel: one lane
+		return cudaSuccess;
+#else
 		emit_kernel<<<(bv.n_sent + 127) / 128, 128, 0, stream>>>(bv, vv);
 		return cudaGetLastError();
+#endif
 	}
 }

@@ -23,10 +23,15 @@ namespace kb
 	__constant__ DevModel c_m;
 	// lanes per sentence.  tests/hostsim compiles this file as plain C++ with a one-lane "warp" (KB_HOSTSIM, see
 	// tests/hostsim/shim/cuda_runtime.h) to check the kernel's logic against the golden lattices without a GPU.
-#ifdef KB_HOSTSIM
+#if defined(KB_HOSTSIM) && KB_HOSTSIM == 1
 	static constexpr uint32_t KB_W = 1;
 #else
 	static constexpr uint32_t KB_W = 32;
+#endif
+#if defined(KB_HOSTSIM) && KB_HOSTSIM == 32
+#define KB_CHECK_UNIFORM(v) simt::check_uniform((uint32_t)(v), __LINE__)      // tests/hostsim: warp-uniform state really is uniform
+#else
+#define KB_CHECK_UNIFORM(v) ((void)0)
 #endif
 	static constexpr unsigned FULL = 0xFFFFFFFFu;
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
@@ -325,6 +330,9 @@ namespace kb
 			if (es.x == es.y) return false;
 			const uint32_t newId = nOut;
 			if (newId >= outCap) { err = ST_NODE_OVERFLOW; return false; }
+			// the scans that decided this append (hasFormAlready / isZFollowable / `es`) read endPosMap and out[]: every lane
+			// must be past them before lane 0 changes those arrays (found by the 32-lane host simulation, tests/hostsim)
+			__syncwarp();
 			if (lane == 0)
 			{
 				DNode nd;
@@ -1402,7 +1410,11 @@ namespace kb
 	cudaError_t launch_lattice(const DevModel&, const BatchView& bv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
-#ifdef KB_HOSTSIM
+#if defined(KB_HOSTSIM) && KB_HOSTSIM == 32
+		(void)stream;
+		for (uint32_t slot = 0; slot < bv.n_sent; ++slot) simt::launch(1, 32, [&] { lattice_sentence(bv, slot, simt::lane); });
+		return cudaSuccess;
+#elif defined(KB_HOSTSIM)
 		for (uint32_t slot = 0; slot < bv.n_sent; ++slot) lattice_sentence(bv, slot, 0);
 		(void)stream;
 		return cudaSuccess;

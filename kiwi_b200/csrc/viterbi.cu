@@ -2046,7 +2046,11 @@ namespace KB_VIT_NS
 #endif
 	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) KB_VIT_KERNEL(const BatchView bv, const VitView vv)
 	{
+#ifdef KB_HOSTSIM
+		alignas(16) static unsigned char smRaw[sizeof(WarpSmem) * WARPS_PER_BLOCK];      // tests/hostsim: one static arena
+#else
 		extern __shared__ __align__(16) unsigned char smRaw[];
+#endif
 		WarpSmem* smAll = reinterpret_cast<WarpSmem*>(smRaw);
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 		// The first KB_SOLO blocks (the longest sentences in LPT order) hold ONE sentence each: the kernel time is the time of
@@ -2069,7 +2073,9 @@ namespace KB_VIT_NS
 		if (bv.status[s]) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
 #endif
 
+#ifndef KB_HOSTSIM
 		if (lane == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s] = tns; }
+#endif
 		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
 		const uint32_t n = t1 - t0;
 		const uint32_t W = 2 * n + 4;
@@ -2189,7 +2195,9 @@ namespace KB_VIT_NS
 		__syncwarp();
 		asm volatile("bar.arrive 1, %0;" :: "r"(v.roundCnt) : "memory");
 #endif
+#ifndef KB_HOSTSIM
 		if (lane == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s + 1] = tns; }
+#endif
 		if (lane == 0)
 		{
 			vv.best_rec[s] = (!v.err && retN) ? retRec[0] : -1;
@@ -2263,7 +2271,15 @@ namespace KB_VIT_NS
 			if (const char* co = getenv("KIWI_B200_CARVEOUT")) cudaFuncSetAttribute(KB_VIT_KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
 			attrSet = true;
 		}
+#ifdef KB_HOSTSIM
+		// tests/hostsim (32 threads = one warp per block): blocks of one warp own the slots blockIdx * WARPS_PER_BLOCK only
+		if (bv.n_sent != 1) return 1;
+		(void)stream; (void)smemBytes;
+		simt::launch(blocks, 32, [&] { KB_VIT_KERNEL(bv, vv); });
+		return cudaSuccess;
+#else
 		KB_VIT_KERNEL<<<blocks, WARPS_PER_BLOCK * 32, smemBytes, stream>>>(bv, vv);
 		return cudaGetLastError();
+#endif
 	}
 }

@@ -90,6 +90,19 @@ int hs_lattice(void* p, const uint16_t* text, int len, uint32_t matchOptions, in
 		}
 		set_model_lattice(s.model.dev);
 		launch_lattice(s.model.dev, bv, nullptr);
+		if (std::getenv("HS_DUMP"))
+		{
+			std::fprintf(stderr, "[hs] status %u normLen %u nChunks %u norm:", status[0], normLen[0], nChunks[0]);
+			for (uint32_t i = 0; i < normLen[0]; ++i) std::fprintf(stderr, " %04x", norm[i]);
+			std::fprintf(stderr, "\n[hs] posTable:");
+			for (int i = 0; i <= len; ++i) std::fprintf(stderr, " %u", posTable[i]);
+			std::fprintf(stderr, "\n[hs] nsToPos:");
+			for (uint32_t i = 0; i < normLen[0]; ++i) std::fprintf(stderr, " %u", nsToPos[i]);
+			std::fprintf(stderr, "\n[hs] pats[0]: end %u len %u tag %u\n", pats[0].end, pats[0].len, pats[0].tag);
+			for (uint32_t i = 0; i < 24; ++i) std::fprintf(stderr, "[hs] build %u: form %d u(%u,%u) pos [%u,%u) prev %u sib %u newIndex %d\n", i, build[i].form, build[i].uform_off, build[i].uform_len,
+				build[i].start_pos, build[i].end_pos, build[i].prev, build[i].sibling, (int)newIndex[i]);
+			for (uint32_t c = 0; c < nChunks[0]; ++c) std::fprintf(stderr, "[hs] chunk %u: [%u,%u) nodes %u\n", c, chunks[c].start, chunks[c].end, chunks[c].n_nodes);
+		}
 		if (status[0]) return -(int)status[0];
 		int total = 0;
 		for (uint32_t c = 0; c < nChunks[0]; ++c)

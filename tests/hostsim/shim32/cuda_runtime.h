@@ -1,0 +1,262 @@
+// HOST SIMULATION shim, 32-lane variant (test infrastructure, tests/ only).  The kernel SOURCES of kiwi_b200/csrc compile
+// as plain C++; a warp is 32 OS threads that run the kernel body in parallel and meet at a std::barrier for every warp
+// collective (__ballot_sync, __shfl_sync, __match_any_sync, __syncwarp, ...), so lane arithmetic, ballots, shuffles,
+// shared memory and the __syncwarp-ordered lane-0 stores behave as on the device (full-mask collectives by all lanes, as the
+// kernels use them).  What it cannot show: timing, instruction-cache effects, real memory-model races between collectives,
+// multi-warp blocks (one warp per block here; the lockstep barrier is compiled out), tensor-core PTX (Knlm build only).
+// Slow (two barrier phases per collective): used on a sample of sentences.  Never linked into the product.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <dlfcn.h>
+#include <mutex>
+#include <chrono>
+#include <cstdio>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <type_traits>
+#include <vector>
+#if !defined(KB_HOSTSIM) || KB_HOSTSIM != 32
+#error "this shim is for -DKB_HOSTSIM=32 builds"
+#endif
+#define __device__
+#define __host__
+#define __global__
+#define __constant__ static
+#define __shared__ static
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+#define __restrict__
+#define __align__(n) alignas(n)
+
+struct uint2 { uint32_t x, y; };
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+struct alignas(8) int2 { int32_t x, y; };
+struct alignas(8) float2 { float x, y; };
+inline int2 make_int2(int32_t x, int32_t y) { return int2{ x, y }; }
+inline float2 make_float2(float x, float y) { return float2{ x, y }; }
+inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{ x, y }; }
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{ x, y, z, w }; }
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize, cudaFuncAttributePreferredSharedMemoryCarveout };
+inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaGetLastError() { return 0; }
+inline const char* cudaGetErrorString(cudaError_t) { return "host simulation"; }
+template<class T> inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* src, size_t n) { std::memcpy(&sym, src, n); return 0; }
+template<class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
+
+namespace simt
+{
+	constexpr uint32_t W = 32;
+	struct Dim { uint32_t x = 0, y = 0, z = 0; };
+	inline thread_local uint32_t lane = 0;
+	inline thread_local Dim threadIdx, blockIdx;
+	inline Dim blockDim, gridDim;
+
+	// Cooperative scheduler: exactly one lane runs at a time, always the HIGHEST runnable lane, and a lane runs until its next
+	// collective.  Between two collectives the lanes therefore execute in the order 31, 30, ..., 0: lane 0 — the lane that issues
+	// the kernels' single-lane stores — runs last, so the other lanes' loads of that segment come first, as on a converged warp
+	// (loads of an earlier instruction precede a later instruction's store).  Deterministic; a collective that not all lanes
+	// reach (or that they reach from different call sites) is reported with the call sites instead of hanging.
+	enum St : uint8_t { RUN, WAIT_FULL, WAIT_PART, DONE };
+	struct Sched
+	{
+		std::mutex m;
+		std::condition_variable cv[W];
+		int current = -1;
+		uint32_t nLanes = W;
+		St st[W];
+		void* site[W];
+		uint64_t fullVal[W], fullRes[W];
+		uint64_t partTag[W]; unsigned partGrp[W]; uint32_t partVal[W]; uint32_t partSnap[W][W];
+		uint64_t collectives = 0; uint64_t ep[W];
+	};
+	inline Sched* sched = nullptr;
+	inline const bool ascending = std::getenv("HS32_ASCENDING") != nullptr;      // experiment: lowest runnable lane first
+	inline thread_local uint64_t epoch = 0, subEpoch = 0, subCount = 0;
+
+	[[noreturn]] inline void die(Sched& sc, const char* what)
+	{
+		std::fprintf(stderr, "[simt] %s; lane:state@site (addr2line the sites):", what);
+		for (uint32_t l = 0; l < sc.nLanes; ++l)
+		{
+			Dl_info di; uintptr_t off = (uintptr_t)sc.site[l];
+			if (sc.site[l] && dladdr(sc.site[l], &di) && di.dli_fbase) off -= (uintptr_t)di.dli_fbase;      // offset inside the shared object
+			std::fprintf(stderr, " %u:%d@0x%zx#%llu", l, (int)sc.st[l], (size_t)off, (unsigned long long)sc.ep[l]);
+		}
+		std::fprintf(stderr, "\n");
+		std::abort();
+	}
+
+	// lock held.  Releases complete collectives, then hands the processor to the highest runnable lane.
+	inline void reschedule(Sched& sc)
+	{
+		bool allFull = true, any = false;
+		for (uint32_t l = 0; l < sc.nLanes; ++l) if (sc.st[l] != DONE) { any = true; if (sc.st[l] != WAIT_FULL) allFull = false; }
+		if (any && allFull)
+		{
+			// (call sites are not compared: the compiler duplicates one source-level collective into several branches)
+			for (uint32_t l = 0; l < sc.nLanes; ++l) sc.fullRes[l] = sc.fullVal[l];
+			for (uint32_t l = 0; l < sc.nLanes; ++l) if (sc.st[l] == WAIT_FULL) sc.st[l] = RUN;
+			++sc.collectives;
+		}
+		for (uint32_t l = 0; l < sc.nLanes; ++l)
+		{
+			if (sc.st[l] != WAIT_PART) continue;
+			bool ready = true;
+			for (uint32_t k = 0; k < W; ++k) if ((sc.partGrp[l] >> k & 1) && !(k < sc.nLanes && sc.st[k] == WAIT_PART && sc.partTag[k] == sc.partTag[l])) ready = false;
+			if (!ready) continue;
+			const unsigned grp = sc.partGrp[l];
+			for (uint32_t k = 0; k < W; ++k) if (grp >> k & 1) for (uint32_t j = 0; j < W; ++j) if (grp >> j & 1) sc.partSnap[k][j] = sc.partVal[j];
+			for (uint32_t k = 0; k < W; ++k) if (grp >> k & 1) sc.st[k] = RUN;
+		}
+		int next = -1;
+		if (ascending) { for (int l = 0; l < (int)sc.nLanes; ++l) if (sc.st[l] == RUN) { next = l; break; } }
+		else for (int l = (int)sc.nLanes - 1; l >= 0; --l) if (sc.st[l] == RUN) { next = l; break; }
+		if (next < 0)
+		{
+			bool allDone = true;
+			for (uint32_t l = 0; l < sc.nLanes; ++l) if (sc.st[l] != DONE) allDone = false;
+			if (!allDone) die(sc, "deadlock: no lane can run (a collective that some lanes never reach)");
+		}
+		sc.current = next;
+		if (next >= 0) sc.cv[next].notify_one();
+	}
+
+	inline void blockAs(St state, void* site)
+	{
+		Sched& sc = *sched;
+		std::unique_lock<std::mutex> lk(sc.m);
+		sc.st[lane] = state; sc.site[lane] = site; sc.ep[lane] = epoch;
+		reschedule(sc);
+		sc.cv[lane].wait(lk, [&] { return sc.current == (int)lane && sc.st[lane] == RUN; });
+	}
+
+	template<class T> __attribute__((noinline)) void exchange(T v, T* out)
+	{
+		static_assert(sizeof(T) <= 8, "exchange of <= 8-byte values");
+		uint64_t raw = 0; std::memcpy(&raw, &v, sizeof(T));
+		sched->fullVal[lane] = raw;
+		++epoch;
+		blockAs(WAIT_FULL, __builtin_return_address(0));
+		for (uint32_t i = 0; i < W; ++i) std::memcpy(&out[i], &sched->fullRes[i], sizeof(T));
+	}
+
+	__attribute__((noinline)) inline void sync()
+	{
+		sched->fullVal[lane] = 0;
+		++epoch;
+		blockAs(WAIT_FULL, __builtin_return_address(0));
+	}
+
+	// partial-mask collectives: a lane calls with the mask of ITS group; lanes outside any multi-member group may skip the call.
+	// The members of a group execute the same sequence of partial collectives between two full-warp collectives.
+	template<class Fn> inline uint32_t groupReduce(unsigned grp, uint32_t v, uint32_t init, Fn&& fn)
+	{
+		if (grp == 0xFFFFFFFFu)
+		{
+			uint32_t o[W]; exchange<uint32_t>(v, o);
+			uint32_t r = init;
+			for (uint32_t l = 0; l < W; ++l) r = fn(r, o[l]);
+			return r;
+		}
+		if (subEpoch != epoch) { subEpoch = epoch; subCount = 0; }
+		sched->partTag[lane] = ((epoch + 1) << 16) | ++subCount;
+		sched->partGrp[lane] = grp; sched->partVal[lane] = v;
+		blockAs(WAIT_PART, __builtin_return_address(0));
+		uint32_t r = init;
+		for (uint32_t l = 0; l < W; ++l) if (grp >> l & 1) r = fn(r, sched->partSnap[lane][l]);
+		return r;
+	}
+
+	// debugging aid for kernels: all lanes must hold the same value here (warp-uniform state)
+	inline void check_uniform(uint32_t v, int line)
+	{
+		uint32_t o[W]; exchange<uint32_t>(v, o);
+		for (uint32_t i = 0; i < W; ++i) if (o[i] != v && lane == 0)
+		{
+			std::fprintf(stderr, "[simt] non-uniform value at line %d: lane 0 has %u, lane %u has %u\n", line, v, i, o[i]);
+			std::abort();
+		}
+	}
+
+	// one warp per block; blockDimX <= 32 lanes run (thread-per-item kernels pass 1)
+	template<class F> inline void launch(uint32_t blocks, uint32_t blockDimX, F&& body)
+	{
+		const uint32_t lanes = std::min(blockDimX, W);
+		blockDim.x = blockDimX; gridDim.x = blocks;
+		for (uint32_t b = 0; b < blocks; ++b)
+		{
+			Sched sc; sc.nLanes = lanes;
+			for (uint32_t l = 0; l < W; ++l) { sc.st[l] = l < lanes ? RUN : DONE; sc.site[l] = nullptr; sc.partTag[l] = 0; }
+			sc.current = ascending ? 0 : (int)lanes - 1;
+			sched = &sc;
+			std::vector<std::thread> ts;
+			for (uint32_t l = 0; l < lanes; ++l) ts.emplace_back([&, l, b]
+			{
+				lane = l; threadIdx.x = l; blockIdx.x = b; epoch = 0; subEpoch = 0; subCount = 0;
+				{
+					std::unique_lock<std::mutex> lk(sc.m);
+					sc.cv[l].wait(lk, [&] { return sc.current == (int)l && sc.st[l] == RUN; });
+				}
+				body();
+				std::unique_lock<std::mutex> lk(sc.m);
+				sc.st[l] = DONE; sc.site[l] = nullptr;
+				reschedule(sc);
+			});
+			for (auto& t : ts) t.join();
+			if (std::getenv("HS32_TRACE")) std::fprintf(stderr, "[simt] block %u: %llu full-warp collectives\n", b, (unsigned long long)sc.collectives);
+			sched = nullptr;
+		}
+	}
+}
+using simt::threadIdx; using simt::blockIdx; using simt::blockDim; using simt::gridDim;
+
+inline unsigned __ballot_sync(unsigned, bool p) { uint32_t o[32]; simt::exchange<uint32_t>(p ? 1u : 0u, o); unsigned m = 0; for (int i = 0; i < 32; ++i) m |= o[i] << i; return m; }
+inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
+inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xFFFFFFFFu; }
+template<class T> inline T __shfl_sync(unsigned, T v, int src) { T o[32]; simt::exchange<T>(v, o); return o[src & 31]; }
+template<class T> inline T __shfl_up_sync(unsigned, T v, int d) { T o[32]; simt::exchange<T>(v, o); return (int)simt::lane >= d ? o[simt::lane - d] : v; }
+template<class T> inline T __shfl_down_sync(unsigned, T v, int d) { T o[32]; simt::exchange<T>(v, o); return simt::lane + d < 32 ? o[simt::lane + d] : v; }
+template<class T> inline T __shfl_xor_sync(unsigned, T v, int d) { T o[32]; simt::exchange<T>(v, o); return o[(simt::lane ^ d) & 31]; }
+template<class T> inline unsigned __match_any_sync(unsigned, T key) { T o[32]; simt::exchange<T>(key, o); unsigned m = 0; for (int i = 0; i < 32; ++i) if (o[i] == key) m |= 1u << i; return m; }
+inline uint32_t __reduce_max_sync(unsigned grp, uint32_t v) { return simt::groupReduce(grp, v, 0u, [](uint32_t a, uint32_t b) { return std::max(a, b); }); }
+inline uint32_t __reduce_min_sync(unsigned grp, uint32_t v) { return simt::groupReduce(grp, v, 0xFFFFFFFFu, [](uint32_t a, uint32_t b) { return std::min(a, b); }); }
+inline uint32_t __reduce_or_sync(unsigned grp, uint32_t v) { return simt::groupReduce(grp, v, 0u, [](uint32_t a, uint32_t b) { return a | b; }); }
+inline uint32_t __reduce_add_sync(unsigned grp, uint32_t v) { return simt::groupReduce(grp, v, 0u, [](uint32_t a, uint32_t b) { return a + b; }); }
+inline void __syncwarp(unsigned = 0xFFFFFFFFu) { simt::sync(); }
+inline void __syncthreads() { simt::sync(); }      // one warp per block
+inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __int2float_rn(int v) { return (float)v; }
+inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline int32_t __float_as_int(float f) { int32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float __int_as_float(int32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline int __dp4a(int a, int b, int c) { for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i)); return c; }
+inline int __dp4a(unsigned a, int b, int c) { for (int i = 0; i < 4; ++i) c += (int)(uint8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i)); return c; }
+template<class T> inline T atomicAdd(T* p, T v) { return __sync_fetch_and_add(p, v); }
+template<class T> inline T atomicSub(T* p, T v) { return __sync_fetch_and_sub(p, v); }
+template<class T> inline T atomicCAS(T* p, T cmp, T val) { return __sync_val_compare_and_swap(p, cmp, val); }
+template<class T> inline T atomicOr(T* p, T v) { return __sync_fetch_and_or(p, v); }
+template<class T> inline T atomicMax(T* p, T v) { T o = *p; while (o < v && !__sync_bool_compare_and_swap(p, o, v)) o = *p; return o; }
+template<class T> inline T __ldg(const T* p) { return *p; }
+template<class A, class B> inline std::common_type_t<A, B> min(A a, B b) { return a < b ? a : b; }
+template<class A, class B> inline std::common_type_t<A, B> max(A a, B b) { return a < b ? b : a; }

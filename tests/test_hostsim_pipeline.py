@@ -1,0 +1,86 @@
+"""CPU: host simulation of the WHOLE device pipeline with 32-lane warps.  tests/hostsim/libpipeline_sim32.so is lattice.cu +
+viterbi.cu (Knlm build) + emit.cu + model.cu — the device SOURCES — compiled as C++ (tests/hostsim/shim32/cuda_runtime.h): each
+kernel is run by 32 OS threads, one per lane, under a cooperative scheduler that switches lanes at every warp collective
+(ballot / shuffle / match_any / reduce / __syncwarp), so lane arithmetic, ballots, shared memory and lane-0 stores behave as
+in a warp.  Tokens and scores are compared with the golden vectors of the UNMODIFIED reference, plain and with the typo
+lattice (BASELINE config 4) — the only check of the typo path's Viterbi / emit side that runs without a GPU.
+
+What it is not: a proof for the hardware build (timing, real memory-model races, multi-warp blocks — the lockstep barrier is
+compiled out —, tensor-core PTX of the CoNg build).  It is slow (one condition-variable hand-over per lane and collective),
+hence a SAMPLE of short sentences.  Known open disagreements of the simulator with the hardware (both pass on the B200 in
+plain mode): inputs_dialect_typos[98] and [469] (plain) end with a truncated back-trace in the simulator; not understood yet.
+History: the first, free-running version of this simulator exposed a write-after-read hazard in lattice.cu's appendNewNode
+(lane 0 could change endPosMap / out[] while slower lanes were still in the scans that decided the append); fixed with one
+__syncwarp()."""
+import ctypes as C, os
+import numpy as np
+import pytest
+from tests.goldenio import read_golden, read_inputs
+from tests.orc import IMAGE, TYPO_IMAGES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "tests", "hostsim", "libpipeline_sim32.so")
+MATCH_ALL_WITH_NORMALIZING = (1 << 0) | (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4) | (1 << 5) | (1 << 23) | (1 << 16)
+# (input file, line): short sentences; the typo list holds sentences whose analysis the typo lattice really changes
+PLAIN = [("inputs_ref_tests", 5), ("inputs_ref_tests", 162), ("inputs_dialect_typos", 573), ("inputs_written", 0)]
+TYPO = [("inputs_dialect_typos", 201), ("inputs_dialect_typos", 438), ("inputs_dialect_typos", 573), ("inputs_dialect_typos", 75),
+        ("inputs_ref_tests", 259), ("inputs_ref_tests", 60), ("inputs_ref_tests", 361), ("inputs_ref_tests", 367), ("inputs_ref_tests", 5),
+        ("inputs_ref_tests", 162)]
+
+
+@pytest.fixture(scope="module")
+def sim():
+    if not os.path.exists(LIB) or not os.path.exists(IMAGE):
+        pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
+    lib = C.CDLL(LIB)
+    lib.hs32_open.restype = C.c_void_p; lib.hs32_open.argtypes = [C.c_char_p]
+    lib.hs32_close.argtypes = [C.c_void_p]
+    lib.hs32_set_typo.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
+    lib.hs32_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    h = lib.hs32_open(os.fsencode(IMAGE))
+    assert h
+    cap = 4096
+    morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
+
+    def analyze(text):
+        u = np.ascontiguousarray(np.frombuffer(text.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
+        s = C.c_float(0); nn = C.c_int(0)
+        n = lib.hs32_analyze(h, u.ctypes.data, len(u), MATCH_ALL_WITH_NORMALIZING, morph.ctypes.data, tag.ctypes.data, pos.ctypes.data, ln.ctypes.data,
+                             sc.ctypes.data, cap, C.byref(s), C.byref(nn))
+        assert n >= 0, (n, text)
+        return [(int(morph[k]), int(tag[k]), int(pos[k]), int(ln[k]), np.float32(sc[k])) for k in range(n)], np.float32(s.value)
+
+    def set_typo(path):
+        assert lib.hs32_set_typo(h, os.fsencode(path) if path else None, 2.5) == 0
+
+    yield analyze, set_typo
+    lib.hs32_close(h)
+
+
+def _check(analyze, cases, prefix):
+    for name, i in cases:
+        t = read_inputs(name)[i]; g = read_golden(prefix + name)[i]
+        toks, score = analyze(t)
+        assert [x[:4] for x in toks] == [x[:4] for x in g["tokens"]], (name, i, t)
+        assert [x[4] for x in toks] == [np.float32(x[4]) for x in g["tokens"]], (name, i, t)      # bit exact
+        assert score == np.float32(g["score"]), (name, i, t)
+
+
+def test_simulated_pipeline_matches_reference(sim):
+    analyze, set_typo = sim
+    set_typo(None)
+    _check(analyze, PLAIN, "")
+
+
+def test_simulated_pipeline_matches_reference_with_typo_lattice(sim):
+    if not os.path.exists(TYPO_IMAGES["basic"]):
+        pytest.skip("typo image missing")
+    analyze, set_typo = sim
+    set_typo(TYPO_IMAGES["basic"])
+    try:
+        _check(analyze, TYPO, "typo6_")
+        # every sentence of the list is one the typo lattice corrects or re-segments
+        changed = sum([x[:4] for x in read_golden("typo6_" + n)[i]["tokens"]] != [x[:4] for x in read_golden(n)[i]["tokens"]] for n, i in TYPO)
+        assert changed >= len(TYPO) - 2
+    finally:
+        set_typo(None)
