@@ -120,6 +120,24 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 		for (uint32_t c = 0; c < nChunks[0]; ++c) *nNodes += (int)chunks[c].n_nodes;
 		if (launch_viterbi(s.model.dev, bv, vv, nullptr)) return -100;
 		if (trace) { std::fprintf(stderr, "[hs32] paths per node:"); for (int i = 0; i < *nNodes; ++i) std::fprintf(stderr, " %u", npCnt[i]); std::fprintf(stderr, "\n"); }
+		if (trace && bestRec[0] >= 0)
+		{
+			const DRec r = recs[bestRec[0]];
+			std::fprintf(stderr, "[hs32] best rec %d: parent_rec %d end_parent %u chunk %u score %f\n", bestRec[0], r.parent_rec, r.end_parent, r.chunk, r.score);
+			uint32_t pi = r.end_parent;
+			for (int k = 0; k < 64 && pi != 0xFFFFFFFFu; ++k)
+			{
+				const DPath& q = paths[pi];
+				std::fprintf(stderr, "[hs32]   path %u: node %u morph %d acc %f parent %u wid %u lm %d root %u sp %u\n", pi, q.node, q.morpheme, q.acc_score, q.parent, q.wid, q.lm_state, q.root_id, q.sp_state);
+				pi = q.parent;
+			}
+			for (int i = 1; i < *nNodes; ++i)
+			{
+				std::fprintf(stderr, "[hs32] node %d: paths [%u, +%u) holes:", i, npOff[i], npCnt[i]);
+				for (uint32_t k = 0; k < npCnt[i]; ++k) { const DPath& q = paths[npOff[i] + k]; if (q.node != (uint32_t)i) std::fprintf(stderr, " %u(node %u)", npOff[i] + k, q.node); }
+				std::fprintf(stderr, "\n");
+			}
+		}
 		if (trace) std::fprintf(stderr, "[hs32] viterbi done: status %u best_rec %d score %f paths@node1 %u\n", status[0], bestRec[0], sc[0], npCnt[1]);
 		if (status[0]) return -(int)status[0];
 		if (s.model.dev.debug[0] || debug[0]) return -101;
