@@ -1200,6 +1200,9 @@ namespace KB_VIT_NS
 				__syncwarp();
 				w += kept; r += cnt;
 			}
+			// every lane has read sm->cand / sm->candNew of this group: the caller overwrites them for the next group
+			// (found by the 32-lane host simulation, tests/hostsim: a lane that leaves this loop early must not race ahead)
+			__syncwarp();
 			top = w;
 		}
 

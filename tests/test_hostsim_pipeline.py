@@ -5,13 +5,15 @@ kernel is run by 32 OS threads, one per lane, under a cooperative scheduler that
 in a warp.  Tokens and scores are compared with the golden vectors of the UNMODIFIED reference, plain and with the typo
 lattice (BASELINE config 4) — the only check of the typo path's Viterbi / emit side that runs without a GPU.
 
-What it is not: a proof for the hardware build (timing, real memory-model races, multi-warp blocks — the lockstep barrier is
+What it is not: a proof for the hardware build (timing, real memory-model behaviour, multi-warp blocks — the lockstep barrier is
 compiled out —, tensor-core PTX of the CoNg build).  It is slow (one condition-variable hand-over per lane and collective),
-hence a SAMPLE of short sentences.  Known open disagreements of the simulator with the hardware (both pass on the B200 in
-plain mode): inputs_dialect_typos[98] and [469] (plain) end with a truncated back-trace in the simulator; not understood yet.
-History: the first, free-running version of this simulator exposed a write-after-read hazard in lattice.cu's appendNewNode
-(lane 0 could change endPosMap / out[] while slower lanes were still in the scans that decided the append); fixed with one
-__syncwarp()."""
+hence a SAMPLE of short sentences.
+Because a lane runs alone until its next collective, the simulator is harsher than a converged warp on shared state that is
+read by all lanes and rewritten later without a barrier in between.  It found two such write-after-read hazards (harmless
+while the warp stays converged, races by the CUDA memory model), both fixed with one __syncwarp():
+  * lattice.cu appendNewNode: lane 0 changed endPosMap / out[] while slower lanes were still in the scans that decided the append;
+  * viterbi.cu fixupGroup: a lane that left the per-candidate loop early returned to the caller, which re-initialises
+    sm->cand / sm->candNew for the next group, while other lanes were still reading them (inputs_dialect_typos[98], [469])."""
 import ctypes as C, os
 import numpy as np
 import pytest
@@ -22,7 +24,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "tests", "hostsim", "libpipeline_sim32.so")
 MATCH_ALL_WITH_NORMALIZING = (1 << 0) | (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4) | (1 << 5) | (1 << 23) | (1 << 16)
 # (input file, line): short sentences; the typo list holds sentences whose analysis the typo lattice really changes
-PLAIN = [("inputs_ref_tests", 5), ("inputs_ref_tests", 162), ("inputs_dialect_typos", 573), ("inputs_written", 0)]
+PLAIN = [("inputs_ref_tests", 5), ("inputs_ref_tests", 162), ("inputs_dialect_typos", 573), ("inputs_written", 0),
+         ("inputs_dialect_typos", 98), ("inputs_dialect_typos", 469)]      # the last two: medium-mode containers (> 128 incoming paths)
 TYPO = [("inputs_dialect_typos", 201), ("inputs_dialect_typos", 438), ("inputs_dialect_typos", 573), ("inputs_dialect_typos", 75),
         ("inputs_ref_tests", 259), ("inputs_ref_tests", 60), ("inputs_ref_tests", 361), ("inputs_ref_tests", 367), ("inputs_ref_tests", 5),
         ("inputs_ref_tests", 162)]
