@@ -845,7 +845,7 @@ namespace kb
 		}
 
 		// generateGraph over raw[0, rawLen) -> tg[0, nTg), sorted by end position with relative prev / sibling offsets
-		__device__ void genTypoGraph()
+		__device__ __noinline__ void genTypoGraph()      // out of line: the plain walk keeps its register allocation
 		{
 			uint32_t n = 0;
 			if (lane == 0)
@@ -1086,7 +1086,7 @@ namespace kb
 		}
 
 		// Splitter::search (KTrie.cpp:1414-1452) over tg[0, nTg)
-		__device__ void searchTypo()
+		__device__ __noinline__ void searchTypo()
 		{
 			const uint32_t totEndPos = nsToPos[nNs - 1] + 1;
 			uint32_t nStates = 0;

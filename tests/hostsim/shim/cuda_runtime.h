@@ -5,7 +5,14 @@
 // __syncwarp, 32-lane arithmetic are NOT exercised: the -m gpu parity tests stay the proof for the device build).
 // Never linked into the product: libkiwi_b200.so is built by nvcc from the same sources with the real CUDA runtime.
 #pragma once
+// (every standard header the kernel sources and harnesses use comes first: libstdc++ spells __attribute__((__noinline__)) itself)
 #include <algorithm>
+#include <cstdio>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -17,6 +24,7 @@
 #define __global__
 #define __constant__ static
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __restrict__
 

@@ -6,7 +6,14 @@
 // multi-warp blocks (one warp per block here; the lockstep barrier is compiled out), tensor-core PTX (Knlm build only).
 // Slow (two barrier phases per collective): used on a sample of sentences.  Never linked into the product.
 #pragma once
+// (every standard header the kernel sources and harnesses use comes first: libstdc++ spells __attribute__((__noinline__)) itself)
 #include <algorithm>
+#include <cstdio>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
 #include <atomic>
 #include <condition_variable>
 #include <dlfcn.h>
