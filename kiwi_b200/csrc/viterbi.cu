@@ -383,8 +383,12 @@ namespace KB_VIT_NS
 					const uint32_t a0 = *reinterpret_cast<const uint32_t*>(pa0 + ko), a1 = *reinterpret_cast<const uint32_t*>(pa1 + ko);
 					const uint32_t a2 = *reinterpret_cast<const uint32_t*>(pa0 + ko + 16), a3 = *reinterpret_cast<const uint32_t*>(pa1 + ko + 16);
 					const uint32_t b0 = *reinterpret_cast<const uint32_t*>(pb + ko), b1 = *reinterpret_cast<const uint32_t*>(pb + ko + 16);
+#ifdef KB_HOSTSIM
+					simt::mma_m16n8k32_u8s8(c0, c1, c2, c3, a0, a1, a2, a3, b0, b1);      // tests/hostsim: the fragment semantics in C++
+#else
 					asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
 						: "+r"(c0), "+r"(c1), "+r"(c2), "+r"(c3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+#endif
 				}
 				if (r0 < nU) { dots[r0][c0col] = c0 - h0; dots[r0][c1col] = c1 - h1; }
 				if (r1 < nU) { dots[r1][c0col] = c2 - h0; dots[r1][c1col] = c3 - h1; }
@@ -2243,7 +2247,7 @@ namespace KB_VIT_NS
 }   // namespace KB_VIT_NS
 	using namespace KB_VIT_NS;
 
-#if KB_CONG
+#if KB_CONG && !defined(KB_HOSTSIM)
 	cudaError_t launch_cong_debug(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
 		int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile, cudaStream_t stream)
 	{

@@ -17,6 +17,8 @@ namespace kb
 	cudaError_t set_model_lattice(const DevModel& m);
 	cudaError_t set_model_viterbi(const DevModel& m);
 	cudaError_t set_model_emit(const DevModel& m);
+	cudaError_t launch_viterbi_cong(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
+	cudaError_t set_model_viterbi_cong(const DevModel& m);
 }
 
 namespace
@@ -41,7 +43,7 @@ void* hs32_open(const char* imagePath)
 		auto blob = kb::readImageFile(imagePath);
 		auto* s = new Sim;
 		s->model.load(blob.data(), blob.size());
-		if (s->model.dev.model_type != 2) { delete s; return nullptr; }      // Knlm build of viterbi.cu only
+		if (s->model.dev.model_type != 2 && s->model.dev.model_type != 4) { delete s; return nullptr; }      // Knlm and CoNg builds of viterbi.cu
 		return s;
 	}
 	catch (...) { return nullptr; }
@@ -110,7 +112,9 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 			tgMatches.resize(U * s.graphPerUnit); tgStates.resize(U * s.statesPerUnit);
 			tv.tmp = tgTmp.data(); tv.graph = tg.data(); tv.remap = tgRemap.data(); tv.state_range = tgRange.data(); tv.matches = tgMatches.data(); tv.states = tgStates.data();
 		}
-		set_model_lattice(s.model.dev); set_model_viterbi(s.model.dev); set_model_emit(s.model.dev);
+		const bool cong = s.model.dev.model_type == 4;
+		set_model_lattice(s.model.dev); set_model_emit(s.model.dev);
+		if (cong) set_model_viterbi_cong(s.model.dev); else set_model_viterbi(s.model.dev);
 		const bool trace = std::getenv("HS32_TRACE") != nullptr;
 		if (trace) std::fprintf(stderr, "[hs32] lattice\n");
 		if (launch_lattice(s.model.dev, bv, nullptr)) return -100;
@@ -118,7 +122,7 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 		if (status[0]) return -(int)status[0];
 		*nNodes = 0;
 		for (uint32_t c = 0; c < nChunks[0]; ++c) *nNodes += (int)chunks[c].n_nodes;
-		if (launch_viterbi(s.model.dev, bv, vv, nullptr)) return -100;
+		if (cong ? launch_viterbi_cong(s.model.dev, bv, vv, nullptr) : launch_viterbi(s.model.dev, bv, vv, nullptr)) return -100;
 		if (trace) { std::fprintf(stderr, "[hs32] paths per node:"); for (int i = 0; i < *nNodes; ++i) std::fprintf(stderr, " %u", npCnt[i]); std::fprintf(stderr, "\n"); }
 		if (trace && bestRec[0] >= 0)
 		{

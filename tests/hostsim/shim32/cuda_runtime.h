@@ -188,6 +188,26 @@ namespace simt
 		return r;
 	}
 
+	// mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 (D = A * B + C) from its fragment layout (g = lane / 4, t = lane % 4):
+	// A 16x32 u8 row-major: a0 = (row g, k 4t..4t+3), a1 = (row g+8, same k), a2 = (row g, k 16+4t..), a3 = (row g+8, k 16+4t..);
+	// B 32x8 s8 col-major: b0 = (k 4t..4t+3, col g), b1 = (k 16+4t.., col g); C/D: c0 = (g, 2t), c1 = (g, 2t+1), c2 = (g+8, 2t), c3 = (g+8, 2t+1)
+	inline void mma_m16n8k32_u8s8(int32_t& c0, int32_t& c1, int32_t& c2, int32_t& c3, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+	{
+		uint32_t A0[W], A1[W], A2[W], A3[W], B0[W], B1[W];
+		exchange<uint32_t>(a0, A0); exchange<uint32_t>(a1, A1); exchange<uint32_t>(a2, A2); exchange<uint32_t>(a3, A3);
+		exchange<uint32_t>(b0, B0); exchange<uint32_t>(b1, B1);
+		auto dot = [](uint32_t ua, uint32_t sb) { int32_t s = 0; for (int j = 0; j < 4; ++j) s += (int32_t)(uint8_t)(ua >> (8 * j)) * (int32_t)(int8_t)(sb >> (8 * j)); return s; };
+		const uint32_t g = lane >> 2, t = lane & 3;
+		for (uint32_t tt = 0; tt < 4; ++tt)
+		{
+			const uint32_t la = g * 4 + tt, lb0 = (2 * t) * 4 + tt, lb1 = (2 * t + 1) * 4 + tt;
+			c0 += dot(A0[la], B0[lb0]) + dot(A2[la], B1[lb0]);
+			c1 += dot(A0[la], B0[lb1]) + dot(A2[la], B1[lb1]);
+			c2 += dot(A1[la], B0[lb0]) + dot(A3[la], B1[lb0]);
+			c3 += dot(A1[la], B0[lb1]) + dot(A3[la], B1[lb1]);
+		}
+	}
+
 	// debugging aid for kernels: all lanes must hold the same value here (warp-uniform state)
 	inline void check_uniform(uint32_t v, int line)
 	{

@@ -1,5 +1,5 @@
 """CPU: host simulation of the WHOLE device pipeline with 32-lane warps.  tests/hostsim/libpipeline_sim32.so is lattice.cu +
-viterbi.cu (Knlm build) + emit.cu + model.cu — the device SOURCES — compiled as C++ (tests/hostsim/shim32/cuda_runtime.h): each
+viterbi.cu (Knlm and CoNg builds) + emit.cu + model.cu — the device SOURCES — compiled as C++ (tests/hostsim/shim32/cuda_runtime.h): each
 kernel is run by 32 OS threads, one per lane, under a cooperative scheduler that switches lanes at every warp collective
 (ballot / shuffle / match_any / reduce / __syncwarp), so lane arithmetic, ballots, shared memory and lane-0 stores behave as
 in a warp.  Tokens and scores are compared with the golden vectors of the UNMODIFIED reference, plain and with the typo
@@ -18,7 +18,7 @@ import ctypes as C, os
 import numpy as np
 import pytest
 from tests.goldenio import read_golden, read_inputs
-from tests.orc import IMAGE, TYPO_IMAGES
+from tests.orc import IMAGE, TYPO_IMAGES, CONG_IMAGE
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "tests", "hostsim", "libpipeline_sim32.so")
@@ -31,16 +31,18 @@ TYPO = [("inputs_dialect_typos", 201), ("inputs_dialect_typos", 438), ("inputs_d
         ("inputs_ref_tests", 162)]
 
 
-@pytest.fixture(scope="module")
-def sim():
-    if not os.path.exists(LIB) or not os.path.exists(IMAGE):
+CONG = [("inputs_written", 0), ("inputs_dialect_typos", 98), ("inputs_dialect_typos", 201), ("inputs_ref_tests", 5)]
+
+
+def _open(image):
+    if not os.path.exists(LIB) or not os.path.exists(image):
         pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
     lib = C.CDLL(LIB)
     lib.hs32_open.restype = C.c_void_p; lib.hs32_open.argtypes = [C.c_char_p]
     lib.hs32_close.argtypes = [C.c_void_p]
     lib.hs32_set_typo.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
     lib.hs32_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
-    h = lib.hs32_open(os.fsencode(IMAGE))
+    h = lib.hs32_open(os.fsencode(image))
     assert h
     cap = 4096
     morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
@@ -56,8 +58,14 @@ def sim():
     def set_typo(path):
         assert lib.hs32_set_typo(h, os.fsencode(path) if path else None, 2.5) == 0
 
+    return analyze, set_typo, lambda: lib.hs32_close(h)
+
+
+@pytest.fixture(scope="module")
+def sim():
+    analyze, set_typo, close = _open(IMAGE)
     yield analyze, set_typo
-    lib.hs32_close(h)
+    close()
 
 
 def _check(analyze, cases, prefix):
@@ -87,3 +95,15 @@ def test_simulated_pipeline_matches_reference_with_typo_lattice(sim):
         assert changed >= len(TYPO) - 2
     finally:
         set_typo(None)
+
+
+def test_simulated_cong_pipeline_matches_reference():
+    """the CoNg build of viterbi.cu (viterbi_cong_kernel): context trie, dp4a rows and the tensor-core tiles, whose
+    mma.sync.m16n8k32 PTX is replaced by its fragment semantics in C++ (shim32 mma_m16n8k32_u8s8) — bit-exact scores against
+    the reference's CoNg vectors"""
+    analyze, set_typo, close = _open(CONG_IMAGE)
+    try:
+        set_typo(None)
+        _check(analyze, CONG, "cong_")
+    finally:
+        close()
