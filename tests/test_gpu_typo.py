@@ -28,7 +28,7 @@ def _close(a, b):
 def typo(kiwi):
     if not os.path.exists(TYPO_IMAGES["basic"]):
         pytest.skip("typo image missing: run __graft_entry__.build() where /root/reference exists")
-    t = kiwi_b200.PreparedTypo(default_set=kiwi_b200.TYPO_BASIC)      # typo_basic.img next to the model image opened by `kiwi`
+    t = kiwi_b200.PreparedTypo(path=TYPO_IMAGES["basic"])             # kiwi_b200_typo_load
     yield t
     t.close()
 
@@ -70,3 +70,16 @@ def test_typo_threshold_zero_equals_plain_tokens(kiwi, typo):
     res_p = kiwi.analyze_batch(texts)
     for i in range(len(texts)):
         assert _tok4(res_t.sentence(i)) == _tok4(res_p.sentence(i)), texts[i]
+
+
+def test_typo_prepare_default_set(kiwi, typo):
+    """kiwi_typo_prepare(kiwi_typo_get_default(KIWI_TYPO_BASIC_TYPO_SET)) finds typo_basic.img next to the model image opened
+    by kiwi_init and gives the same analysis as the explicitly loaded image"""
+    t2 = kiwi_b200.PreparedTypo(default_set=kiwi_b200.TYPO_BASIC)
+    try:
+        texts = read_inputs("inputs_dialect_typos")[:64]
+        a = kiwi.analyze_batch(texts, kiwi_b200.default_option(typo=typo))
+        b = kiwi.analyze_batch(texts, kiwi_b200.default_option(typo=t2))
+        assert a.tokens.tobytes() == b.tokens.tobytes() and (a.scores == b.scores).all()
+    finally:
+        t2.close()
