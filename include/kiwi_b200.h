@@ -134,6 +134,7 @@ const char* kiwi_res_tag(kiwi_res_h result, int index, int num);             /* 
 int kiwi_res_position(kiwi_res_h result, int index, int num);                /* capi.h:877 */
 int kiwi_res_length(kiwi_res_h result, int index, int num);                  /* capi.h:887 */
 float kiwi_res_score(kiwi_res_h result, int index, int num);                 /* capi.h:917 */
+float kiwi_res_typo_cost(kiwi_res_h result, int index, int num);             /* capi.h:927 */
 int kiwi_res_close(kiwi_res_h result);                                       /* capi.h:937 */
 
 /* ---- additive batched interface (flat arrays; what kiwi_analyze_mw drains into) -------------------- */
@@ -143,7 +144,9 @@ typedef struct {
 	float score;            /* PathNode.wordScore */
 	uint16_t length;
 	uint8_t tag;            /* POSTag incl. the irregular bit, after script re-tagging (Kiwi.cpp:590-605) */
-	uint8_t flags;          /* bit0: the token carries its own surface form (OOV / special run / pattern) */
+	uint8_t flags;          /* bit0: the token carries its own surface form (OOV / special run / pattern);
+	                         * bits 1-3: typo cost of the token's lattice node in units of 0.5, bits 4-7: tokens of that node - 1;
+	                         * TokenInfo::typoCost = cost / tokens (0 without a typo transformer) */
 } kiwi_b200_token_t;
 
 typedef struct {

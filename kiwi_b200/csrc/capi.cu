@@ -136,6 +136,8 @@ static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, uint32_t rawLen, const
 		std::memset(&k.info, 0, sizeof(k.info));
 		k.info.chr_position = d.position; k.info.length = d.length; k.info.tag = d.tag; k.info.score = d.score;
 		k.info.paired_token = (uint32_t)-1;
+		// TokenInfo::typoCost (src/Kiwi.cpp:739) = node cost / tokens of the node (PathEvaluator.hpp:1074), both in the device row's flags
+		k.info.typo_cost = ((d.flags >> 1) & 7) ? (float)((d.flags >> 1) & 7) * 0.5f / (float)((d.flags >> 4) + 1) : 0.f;
 		k.info.word_position = wordPos[d.position];
 		k.morphId = d.morph;
 		const kb2_morph& mm = m.hMorphs[d.morph];
@@ -416,6 +418,7 @@ const char* kiwi_res_tag(kiwi_res_h result, int index, int num) { KB_TOK_OR(null
 int kiwi_res_position(kiwi_res_h result, int index, int num) { KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].info.chr_position; }
 int kiwi_res_length(kiwi_res_h result, int index, int num) { KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].info.length; }
 float kiwi_res_score(kiwi_res_h result, int index, int num) { KB_TOK_OR(0.f) return result->toks[num].info.score; }
+float kiwi_res_typo_cost(kiwi_res_h result, int index, int num) { KB_TOK_OR(0.f) return result->toks[num].info.typo_cost; }
 int kiwi_res_close(kiwi_res_h result) { if (!result) return KIWIERR_INVALID_HANDLE; delete result; return 0; }
 
 struct BatchHolder { kiwi_b200_batch_t pub; BatchOutput bo; };

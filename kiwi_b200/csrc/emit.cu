@@ -53,11 +53,22 @@ namespace kb
 		{
 			return (ownOff & 0x80000000u) ? c_m.form_chars[c_m.forms_raw[~ownOff].str_off + k] : norm[ownOff + k];
 		}
+		// PathNode::typoCost = the node's typo cost / the number of tokens the node yields (PathEvaluator.hpp:1066-1074) travels in
+		// DToken::flags: bits 1-3 the node's cost in units of 0.5 (the default typo sets use 1, 1.5 and 2; saturates at 3.5),
+		// bits 4-7 the token count - 1; the host divides as the reference does
+		uint8_t typoBits = 0;
+		__device__ void setTypoCost(float typoCostDiff, uint32_t numNewTokens)
+		{
+			const float q = typoCostDiff * 2.f + 0.5f;
+			const uint32_t v = q <= 0.f ? 0u : (q >= 7.f ? 7u : (uint32_t)q);
+			const uint32_t n1 = (numNewTokens > 16 ? 16u : numNewTokens) - 1;
+			typoBits = v ? (uint8_t)((v << 1) | (n1 << 4)) : 0;
+		}
 		__device__ void pushTok(uint32_t morph, uint32_t begin, uint32_t end, float score, uint32_t ownOff, uint32_t ownLen)
 		{
 			flushBack();
 			const DMorph mm = c_m.morphs[morph];
-			backTok.morph = morph; backTok.tag = (uint8_t)(mm.feat & MF_TAG_MASK); backTok.score = score; backTok.flags = ownLen ? 1 : 0;
+			backTok.morph = morph; backTok.tag = (uint8_t)(mm.feat & MF_TAG_MASK); backTok.score = score; backTok.flags = (uint8_t)((ownLen ? 1 : 0) | typoBits);
 			backTok.position = 0; backTok.length = 0;
 			backBegin = begin; backEnd = end; backValid = true; backSkip = false;
 			if (ownLen)
@@ -132,6 +143,7 @@ namespace kb
 				const DNode g = gnodes[cur.node];
 				const float firstScore = cur.first_chunk_score + typoCostDiff * c_m.cfg.typo_cost_weight;
 				const float restScores = numNewTokens > 1 ? (scoreDiff - cur.first_chunk_score) / (float)(numNewTokens - 1) : 0.f;
+				e.setTypoCost(typoCostDiff, numNewTokens);
 				if (splitSaisiot && saisiot)
 				{
 					for (uint32_t chn = 0; chn < numNewTokens; ++chn)
@@ -152,6 +164,7 @@ namespace kb
 					e.backTok.tag = (uint8_t)(c_m.morphs[e.backTok.morph].feat & MF_TAG_MASK);
 					e.backEnd = g.start_pos + c_m.chunks[mm.chunk_off].end;
 					e.backTok.score = firstScore;
+					e.backTok.flags = (uint8_t)((e.backTok.flags & 1) | e.typoBits);
 					for (uint32_t chn = 1; chn < numNewTokens; ++chn)
 					{
 						const kb2_chunk ck = c_m.chunks[mm.chunk_off + chn];

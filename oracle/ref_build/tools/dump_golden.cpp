@@ -176,6 +176,12 @@ int main(int argc, char** argv)
 				std::fprintf(fo, "T %zu %u %u %u %a %u,%u,%u,%u,%d %s\n", t.morph ? kw.morphToId(t.morph) : (size_t)-1, (unsigned)t.tag, t.position, (unsigned)t.length, t.score,
 					(unsigned)t.wordPosition, (unsigned)t.sentPosition, (unsigned)t.lineNumber, (unsigned)t.subSentPosition, (int)t.pairedToken, toUtf8Lenient(t.str).c_str());
 			}
+			if (getenv("KB_TYPO"))      // typo-tolerant dumps only: TokenInfo::typoCost of every token
+			{
+				std::fprintf(fo, "Y");
+				for (auto& t : tokens) std::fprintf(fo, " %a", t.typoCost);
+				std::fprintf(fo, "\n");
+			}
 			for (size_t c = 0; c < chunks.size(); ++c)
 			{
 				auto& ch = chunks[c];

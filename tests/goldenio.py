@@ -24,6 +24,8 @@ def read_golden(name):
                 cur["tokens"].append((int(p[1]) & 0xFFFFFFFF, int(p[2]), int(p[3]), int(p[4]), float.fromhex(p[5])))
                 if len(p) > 6:      # (wordPosition, sentPosition, lineNumber, subSentPosition, pairedToken) and the surface form (TokenInfo::str)
                     cur.setdefault("forms", []).append((tuple(int(x) for x in p[6].split(",")), line.rstrip("\n").split(" ", 7)[7] if len(p) > 7 else ""))
+            elif k == "Y":      # typo-tolerant dumps: TokenInfo::typoCost per token
+                cur["typo_costs"] = [float.fromhex(x) for x in p[1:]]
             elif k == "C":
                 n_nodes = int(p[4])
                 cur["_keep"] = n_nodes > 2

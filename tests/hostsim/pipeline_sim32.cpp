@@ -69,7 +69,7 @@ int hs32_set_typo(void* p, const char* path, float threshold)
 // one sentence through lattice -> viterbi -> emit; tokens as (morph, tag, position, length, score); returns the token count,
 // -status on a kernel status, -100 on an error.  nodes = number of lattice nodes (all chunks)
 int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, uint32_t* morph, uint8_t* tag, uint32_t* pos, uint16_t* length, float* score,
-	int maxTokens, float* sentScore, int* nNodes)
+	int maxTokens, float* sentScore, int* nNodes, uint8_t* flags)
 {
 	try
 	{
@@ -152,6 +152,7 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 		for (int i = 0; i < n; ++i)
 		{
 			morph[i] = toks[i].morph; tag[i] = toks[i].tag; pos[i] = toks[i].position; length[i] = toks[i].length; score[i] = toks[i].score;
+			if (flags) flags[i] = toks[i].flags;
 		}
 		*sentScore = sc[0];
 		return n;

@@ -54,6 +54,9 @@ def test_typo_tokens_and_scores_match_reference_golden(kiwi, typo, name):
         for k, x in zip(got, g["tokens"]):
             assert _close(float(k["score"]), x[4]), (i, t)
         exact += int(np.float32(res.scores[i]) == np.float32(g["score"]))
+        # TokenInfo::typoCost: node cost (flags bits 1-3, units of 0.5) / tokens of the node (bits 4-7, minus 1)
+        costs = [np.float32(((int(k["flags"]) >> 1) & 7) * 0.5) / np.float32((int(k["flags"]) >> 4) + 1) if (int(k["flags"]) >> 1) & 7 else np.float32(0) for k in got]
+        assert costs == [np.float32(x) for x in g["typo_costs"]], (i, t)
         corrected += [x[:4] for x in g["tokens"]] != [x[:4] for x in p["tokens"]]
     print("%s: %d/%d sentence scores bit-exact, %d sentences corrected by the typo lattice" % (name, exact, len(texts), corrected))
     assert exact >= 0.99 * len(texts)

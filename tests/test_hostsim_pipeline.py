@@ -28,7 +28,7 @@ PLAIN = [("inputs_ref_tests", 5), ("inputs_ref_tests", 162), ("inputs_dialect_ty
          ("inputs_dialect_typos", 98), ("inputs_dialect_typos", 469)]      # the last two: medium-mode containers (> 128 incoming paths)
 TYPO = [("inputs_dialect_typos", 201), ("inputs_dialect_typos", 438), ("inputs_dialect_typos", 573), ("inputs_dialect_typos", 75),
         ("inputs_ref_tests", 259), ("inputs_ref_tests", 60), ("inputs_ref_tests", 361), ("inputs_ref_tests", 367), ("inputs_ref_tests", 5),
-        ("inputs_ref_tests", 162)]
+        ("inputs_ref_tests", 162), ("inputs_dialect_typos", 131), ("inputs_dialect_typos", 162)]      # 131 / 162: typo cost split over 4 / 2 tokens
 
 
 CONG = [("inputs_written", 0), ("inputs_dialect_typos", 98), ("inputs_dialect_typos", 201), ("inputs_ref_tests", 5)]
@@ -41,18 +41,20 @@ def _open(image):
     lib.hs32_open.restype = C.c_void_p; lib.hs32_open.argtypes = [C.c_char_p]
     lib.hs32_close.argtypes = [C.c_void_p]
     lib.hs32_set_typo.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
-    lib.hs32_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    lib.hs32_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p]
     h = lib.hs32_open(os.fsencode(image))
     assert h
     cap = 4096
-    morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
+    morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32); fl = np.zeros(cap, np.uint8)
 
     def analyze(text):
         u = np.ascontiguousarray(np.frombuffer(text.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
         s = C.c_float(0); nn = C.c_int(0)
         n = lib.hs32_analyze(h, u.ctypes.data, len(u), MATCH_ALL_WITH_NORMALIZING, morph.ctypes.data, tag.ctypes.data, pos.ctypes.data, ln.ctypes.data,
-                             sc.ctypes.data, cap, C.byref(s), C.byref(nn))
+                             sc.ctypes.data, cap, C.byref(s), C.byref(nn), fl.ctypes.data)
         assert n >= 0, (n, text)
+        # TokenInfo::typoCost from the device row's flags: node cost (bits 1-3, units of 0.5) / tokens of the node (bits 4-7, minus 1)
+        analyze.typo_costs = [float(np.float32(((int(fl[k]) >> 1) & 7) * 0.5) / np.float32((int(fl[k]) >> 4) + 1)) if (int(fl[k]) >> 1) & 7 else 0.0 for k in range(n)]
         return [(int(morph[k]), int(tag[k]), int(pos[k]), int(ln[k]), np.float32(sc[k])) for k in range(n)], np.float32(s.value)
 
     def set_typo(path):
@@ -75,6 +77,8 @@ def _check(analyze, cases, prefix):
         assert [x[:4] for x in toks] == [x[:4] for x in g["tokens"]], (name, i, t)
         assert [x[4] for x in toks] == [np.float32(x[4]) for x in g["tokens"]], (name, i, t)      # bit exact
         assert score == np.float32(g["score"]), (name, i, t)
+        if "typo_costs" in g:
+            assert [np.float32(x) for x in analyze.typo_costs] == [np.float32(x) for x in g["typo_costs"]], (name, i, t)
 
 
 def test_simulated_pipeline_matches_reference(sim):
