@@ -86,3 +86,28 @@ def test_typo_prepare_default_set(kiwi, typo):
         assert a.tokens.tobytes() == b.tokens.tobytes() and (a.scores == b.scores).all()
     finally:
         t2.close()
+
+
+def test_kiwi_res_typo_cost_through_the_reference_calls(kiwi, typo):
+    """kiwi_analyze_w with kiwi_analyze_option_t::typo_transformer, then kiwi_res_typo_cost (capi.h:927) per token: the
+    reference's TokenInfo::typoCost (node cost / tokens of the node, PathEvaluator.hpp:1066-1074) from the golden dump"""
+    import ctypes as C
+    lib = kiwi._lib
+    lib.kiwi_res_typo_cost.restype = C.c_float
+    lib.kiwi_res_typo_cost.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    opt = kiwi_b200.default_option(typo=typo, typo_threshold=2.5)
+    texts = read_inputs("inputs_dialect_typos"); gold = read_golden("typo6_inputs_dialect_typos")
+    nonzero = 0
+    for i in (11, 131, 162, 201, 438):
+        u = np.frombuffer((texts[i] + "\0").encode("utf-16-le"), dtype="<u2").copy()
+        res = lib.kiwi_analyze_w(kiwi._h, u.ctypes.data, 1, opt, None)
+        assert res, lib.kiwi_error()
+        try:
+            n = lib.kiwi_res_word_num(res, 0)
+            assert n == len(gold[i]["tokens"])
+            costs = [np.float32(lib.kiwi_res_typo_cost(res, 0, k)) for k in range(n)]
+            assert costs == [np.float32(x) for x in gold[i]["typo_costs"]], (i, texts[i])
+            nonzero += sum(1 for c in costs if c != 0)
+        finally:
+            lib.kiwi_res_close(res)
+    assert nonzero >= 5
