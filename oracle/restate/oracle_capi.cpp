@@ -3,7 +3,7 @@
 #include "analyze.hpp"
 #include "typo.hpp"
 
-struct OrcHandle { orc::Image im; orc::Analyzer* an = nullptr; orc::Counters cnt; };
+struct OrcHandle { orc::Image im; orc::Analyzer* an = nullptr; orc::Counters cnt; orc::EvalStats es; };
 
 extern "C" {
 
@@ -80,6 +80,16 @@ void orc_work_counters(void* p, uint64_t* out)
 	auto* h = reinterpret_cast<OrcHandle*>(p);
 	static_assert(sizeof(orc::WorkCounters) == 20 * sizeof(uint64_t), "WorkCounters layout");
 	std::memcpy(out, &h->an->work, 18 * sizeof(uint64_t));
+}
+
+// per-evaluate() shape rows {P, nCands, lmSteps, flags, pathsBeforePrune}: enable, then fetch (returns the row count; copies at most maxRows)
+void orc_eval_stats_enable(void* p) { auto* h = reinterpret_cast<OrcHandle*>(p); h->an->viterbi.es = &h->es; }
+uint64_t orc_eval_stats(void* p, uint32_t* out, uint64_t maxRows)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	const uint64_t n = h->es.rows.size() / 5;
+	std::memcpy(out, h->es.rows.data(), std::min(n, maxRows) * 5 * sizeof(uint32_t));
+	return n;
 }
 
 // forget the growth history of the `top1` container (= what a fresh reference process starts with)

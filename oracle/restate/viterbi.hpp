@@ -43,6 +43,13 @@ namespace orc
 
 	struct Counters { uint64_t lmSteps = 0, lmHops = 0, pairs = 0, inserts = 0, pathsOut = 0, top1Mode = 0, bucketFull = 0, maxNodePre = 0, maxIncoming = 0, mediumMode = 0, evalCalls = 0, candEvals = 0, maxCont = 0; };
 
+	// per-evaluate() shape statistics (design input for the CUDA kernel's fast path; enabled by the oracle C API on request)
+	struct EvalStats
+	{
+		// rows: one per evaluate() call -> {P, nCands, lmSteps, flags}; flags: 1 fork cand, 2 socket path, 4 shortcut cand, 8 second (ignoreCond) pass, 16 left-half cand, 32 socket-chunk cand
+		std::vector<uint32_t> rows;
+	};
+
 	inline uint8_t hashSbTypeOrder(uint8_t type, uint8_t order) { return ((type << 1) ^ (type >> 7) ^ order) % 63 + 1; }   // PathEvaluator.hpp:83-86
 
 	inline size_t getSBType(const u16* form, size_t len)      // src/Utils.cpp:264-298 (on the un-joined kform)
@@ -80,6 +87,7 @@ namespace orc
 		kb2_config cfg;
 		Counters* cnt = nullptr;
 		WorkCounters* wc = nullptr;
+		EvalStats* es = nullptr;
 
 		// per-call state
 		const LNode* graph = nullptr; size_t graphSize = 0;
@@ -680,10 +688,25 @@ namespace orc
 			size_t totalPrevPathes = 0;
 			for (const LNode* prev = node->prev ? node - node->prev : nullptr; prev; prev = prev->sibling ? prev + prev->sibling : nullptr) totalPrevPathes += cache[prev - graph].size();
 
+			uint32_t esFlags = 0; const uint64_t esLm0 = cnt ? cnt->lmSteps : 0;
+			if (es)
+			{
+				for (const LNode* prev = node->prev ? node - node->prev : nullptr; prev; prev = prev->sibling ? prev + prev->sibling : nullptr)
+					for (auto& pp : cache[prev - graph]) if (pp.combineSocket) esFlags |= 2;
+				for (size_t ci = 0; ci < nCands; ++ci)
+				{
+					const auto& cur = M((int32_t)cands[ci]);
+					if (cur.tag == T_z_coda || cur.tag == T_z_siot) esFlags |= 4;
+					if (cur.combine_socket) esFlags |= isSingle(cur) ? 16 : 32;
+					const RuleScorer r = makeRuleScorer((int32_t)cands[ci], node);
+					if (r.sbType || r.specialType == 0 || r.specialType == 1 || r.specialType == 3 || r.specialType == 4) esFlags |= 1;
+				}
+			}
 			if (cong) evaluateCong(nodeIdx, ownFormId, cands, nCands, nodeLevelDiscount, totalPrevPathes);
 			else
 			for (int ignoreCond = 0; ignoreCond < 2; ++ignoreCond)
 			{
+				if (ignoreCond) esFlags |= 8;
 				for (size_t ci = 0; ci < nCands; ++ci)
 				{
 					const int32_t curId = (int32_t)cands[ci];
@@ -734,6 +757,7 @@ namespace orc
 				if (!nCache.empty()) break;
 			}
 
+			if (es) { es->rows.push_back((uint32_t)totalPrevPathes); es->rows.push_back((uint32_t)nCands); es->rows.push_back((uint32_t)((cnt ? cnt->lmSteps : 0) - esLm0)); es->rows.push_back(esFlags); es->rows.push_back((uint32_t)nCache.size()); }
 			if (cnt) { cnt->maxNodePre = std::max<uint64_t>(cnt->maxNodePre, nCache.size()); cnt->maxIncoming = std::max<uint64_t>(cnt->maxIncoming, totalPrevPathes); cnt->evalCalls++; }
 			std::vector<float> maxScores(1 + uniqStates.size(), -INFINITY);
 			for (auto& c : nCache)

@@ -1,0 +1,77 @@
+#!/usr/bin/env python3
+"""Parallel sweep of the 32-lane host simulation over golden sentences (no GPU): every sentence of the named golden input
+files through lattice.cu + viterbi.cu + emit.cu compiled as C++ (tests/hostsim), tokens and bit-exact scores against the
+unmodified reference's vectors.  The CPU-side regression net for kernel edits.
+
+  python scripts/hostsim_sweep.py [plain|typo|cong] [--files inputs_web,inputs_written,...] [--stride K] [--jobs J]"""
+import ctypes as C, os, sys, time, argparse
+import numpy as np
+from concurrent.futures import ProcessPoolExecutor
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests.goldenio import read_golden, read_inputs
+from tests.orc import IMAGE, TYPO_IMAGES, CONG_IMAGE
+
+MATCH_ALL = (1 << 0) | (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4) | (1 << 5) | (1 << 23) | (1 << 16)
+
+
+_H = {}      # one simulator handle per worker process and mode (opening the 135 MB image is the expensive part)
+
+
+def _handle(mode):
+    if mode in _H: return _H[mode]
+    lib = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libpipeline_sim32.so"))
+    lib.hs32_open.restype = C.c_void_p; lib.hs32_open.argtypes = [C.c_char_p]
+    lib.hs32_set_typo.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
+    lib.hs32_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p]
+    h = lib.hs32_open(os.fsencode(CONG_IMAGE if mode == "cong" else IMAGE))
+    assert h
+    if mode == "typo": assert lib.hs32_set_typo(h, os.fsencode(TYPO_IMAGES["basic"]), 2.5) == 0
+    _H[mode] = (lib, h)
+    return _H[mode]
+
+
+def work(args):
+    mode, name, idxs = args
+    cong = mode == "cong"; typo = mode == "typo"
+    lib, h = _handle(mode)
+    cap = 8192
+    morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
+    texts = read_inputs(name); gold = read_golden(("cong_" if cong else "") + ("typo6_" if typo else "") + name)
+    bad = []
+    for i in idxs:
+        t, g = texts[i], gold[i]
+        u = np.ascontiguousarray(np.frombuffer(t.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
+        s = C.c_float(0); nn = C.c_int(0)
+        n = lib.hs32_analyze(h, u.ctypes.data, len(u), MATCH_ALL, morph.ctypes.data, tag.ctypes.data, pos.ctypes.data, ln.ctypes.data, sc.ctypes.data, cap, C.byref(s), C.byref(nn), None)
+        if n < 0: bad.append((name, i, "status %d" % n)); continue
+        got = [(int(morph[k]), int(tag[k]), int(pos[k]), int(ln[k])) for k in range(n)]
+        if got != [x[:4] for x in g["tokens"]]: bad.append((name, i, "tokens")); continue
+        if not (all(np.float32(sc[k]) == np.float32(g["tokens"][k][4]) for k in range(n)) and np.float32(s.value) == np.float32(g["score"])): bad.append((name, i, "scores"))
+    return len(idxs), bad
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", nargs="?", default="plain", choices=["plain", "typo", "cong"])
+    ap.add_argument("--files", default="inputs_web,inputs_written,inputs_ref_tests,inputs_dialect_typos")
+    ap.add_argument("--stride", type=int, default=1)
+    ap.add_argument("--maxlen", type=int, default=400, help="skip longer inputs (the pathological reference tests take minutes)")
+    ap.add_argument("--jobs", type=int, default=os.cpu_count() or 4)
+    a = ap.parse_args()
+    tasks = []
+    for name in a.files.split(","):
+        texts = read_inputs(name)
+        idx = [i for i in range(0, len(texts), a.stride) if len(texts[i]) <= a.maxlen]
+        per = max(1, len(idx) // (a.jobs * 4))
+        for k in range(0, len(idx), per): tasks.append((a.mode, name, idx[k:k + per]))
+    t0 = time.time(); total = 0; bad = []
+    with ProcessPoolExecutor(a.jobs) as ex:
+        for n, b in ex.map(work, tasks): total += n; bad += b
+    print("%s: %d sentences, %d mismatches, %.1f s" % (a.mode, total, len(bad), time.time() - t0))
+    for b in bad[:40]: print("  MISMATCH", b)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

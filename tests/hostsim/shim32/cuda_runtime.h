@@ -1,10 +1,10 @@
 // HOST SIMULATION shim, 32-lane variant (test infrastructure, tests/ only).  The kernel SOURCES of kiwi_b200/csrc compile
-// as plain C++; a warp is 32 OS threads that run the kernel body in parallel and meet at a std::barrier for every warp
+// as plain C++; a warp is 32 fibers (one per lane, one OS thread) that run the kernel body and hand over at every warp
 // collective (__ballot_sync, __shfl_sync, __match_any_sync, __syncwarp, ...), so lane arithmetic, ballots, shuffles,
 // shared memory and the __syncwarp-ordered lane-0 stores behave as on the device (full-mask collectives by all lanes, as the
 // kernels use them).  What it cannot show: timing, instruction-cache effects, real memory-model races between collectives,
 // multi-warp blocks (one warp per block here; the lockstep barrier is compiled out), tensor-core PTX (Knlm build only).
-// Slow (two barrier phases per collective): used on a sample of sentences.  Never linked into the product.
+// Two context switches per lane and collective: a few hundred sentences per minute.  Never linked into the product.
 #pragma once
 // (every standard header the kernel sources and harnesses use comes first: libstdc++ spells __attribute__((__noinline__)) itself)
 #include <algorithm>
@@ -68,8 +68,9 @@ namespace simt
 {
 	constexpr uint32_t W = 32;
 	struct Dim { uint32_t x = 0, y = 0, z = 0; };
-	inline thread_local uint32_t lane = 0;
-	inline thread_local Dim threadIdx, blockIdx;
+	// one fiber per lane inside ONE OS thread: the per-lane "registers" below are swapped by the scheduler at every switch
+	inline uint32_t lane = 0;
+	inline Dim threadIdx, blockIdx;
 	inline Dim blockDim, gridDim;
 
 	// Cooperative scheduler: exactly one lane runs at a time, always the HIGHEST runnable lane, and a lane runs until its next
@@ -77,22 +78,54 @@ namespace simt
 	// the kernels' single-lane stores — runs last, so the other lanes' loads of that segment come first, as on a converged warp
 	// (loads of an earlier instruction precede a later instruction's store).  Deterministic; a collective that not all lanes
 	// reach (or that they reach from different call sites) is reported with the call sites instead of hanging.
+	// Lanes are fibers (round 2; round 1 used 32 OS threads and condition variables, ~100x slower per collective).
+	// minimal x86-64 System V context switch (callee-saved registers + stack pointer; no signal-mask system call as in swapcontext)
+	struct Ctx { void* sp = nullptr; };
+	extern "C" void kb_simt_switch(void** saveSp, void* loadSp);
+	asm(R"(
+	.text
+	.weak kb_simt_switch
+	.type kb_simt_switch,@function
+kb_simt_switch:
+	pushq %rbp
+	pushq %rbx
+	pushq %r12
+	pushq %r13
+	pushq %r14
+	pushq %r15
+	subq $8, %rsp
+	stmxcsr (%rsp)
+	fnstcw 4(%rsp)
+	movq %rsp, (%rdi)
+	movq %rsi, %rsp
+	ldmxcsr (%rsp)
+	fldcw 4(%rsp)
+	addq $8, %rsp
+	popq %r15
+	popq %r14
+	popq %r13
+	popq %r12
+	popq %rbx
+	popq %rbp
+	ret
+	.size kb_simt_switch,.-kb_simt_switch
+)");
 	enum St : uint8_t { RUN, WAIT_FULL, WAIT_PART, DONE };
 	struct Sched
 	{
-		std::mutex m;
-		std::condition_variable cv[W];
-		int current = -1;
+		Ctx mainCtx; Ctx ctx[W];
+		std::vector<char> stacks;
 		uint32_t nLanes = W;
 		St st[W];
 		void* site[W];
 		uint64_t fullVal[W], fullRes[W];
 		uint64_t partTag[W]; unsigned partGrp[W]; uint32_t partVal[W]; uint32_t partSnap[W][W];
 		uint64_t collectives = 0; uint64_t ep[W];
+		uint64_t epochOf[W], subEpochOf[W], subCountOf[W];
 	};
 	inline Sched* sched = nullptr;
 	inline const bool ascending = std::getenv("HS32_ASCENDING") != nullptr;      // experiment: lowest runnable lane first
-	inline thread_local uint64_t epoch = 0, subEpoch = 0, subCount = 0;
+	inline uint64_t epoch = 0, subEpoch = 0, subCount = 0;
 
 	[[noreturn]] inline void die(Sched& sc, const char* what)
 	{
@@ -107,8 +140,8 @@ namespace simt
 		std::abort();
 	}
 
-	// lock held.  Releases complete collectives, then hands the processor to the highest runnable lane.
-	inline void reschedule(Sched& sc)
+	// main context.  Releases complete collectives, then returns the highest runnable lane (-1: all lanes done).
+	inline int reschedule(Sched& sc)
 	{
 		bool allFull = true, any = false;
 		for (uint32_t l = 0; l < sc.nLanes; ++l) if (sc.st[l] != DONE) { any = true; if (sc.st[l] != WAIT_FULL) allFull = false; }
@@ -138,17 +171,17 @@ namespace simt
 			for (uint32_t l = 0; l < sc.nLanes; ++l) if (sc.st[l] != DONE) allDone = false;
 			if (!allDone) die(sc, "deadlock: no lane can run (a collective that some lanes never reach)");
 		}
-		sc.current = next;
-		if (next >= 0) sc.cv[next].notify_one();
+		return next;
 	}
 
+	// lane context: park this lane in `state` and give the processor back to the scheduler
 	inline void blockAs(St state, void* site)
 	{
 		Sched& sc = *sched;
-		std::unique_lock<std::mutex> lk(sc.m);
-		sc.st[lane] = state; sc.site[lane] = site; sc.ep[lane] = epoch;
-		reschedule(sc);
-		sc.cv[lane].wait(lk, [&] { return sc.current == (int)lane && sc.st[lane] == RUN; });
+		const uint32_t me = lane;
+		sc.st[me] = state; sc.site[me] = site; sc.ep[me] = epoch;
+		sc.epochOf[me] = epoch; sc.subEpochOf[me] = subEpoch; sc.subCountOf[me] = subCount;
+		kb_simt_switch(&sc.ctx[me].sp, sc.mainCtx.sp);
 	}
 
 	template<class T> __attribute__((noinline)) void exchange(T v, T* out)
@@ -220,30 +253,50 @@ namespace simt
 	}
 
 	// one warp per block; blockDimX <= 32 lanes run (thread-per-item kernels pass 1)
+	inline void (*fiberBody)(void*) = nullptr;
+	inline void* fiberArg = nullptr;
+	inline void fiberEntry()
+	{
+		fiberBody(fiberArg);
+		sched->st[lane] = DONE; sched->site[lane] = nullptr;
+		kb_simt_switch(&sched->ctx[lane].sp, sched->mainCtx.sp);
+		std::abort();      // a finished lane is never resumed
+	}
 	template<class F> inline void launch(uint32_t blocks, uint32_t blockDimX, F&& body)
 	{
 		const uint32_t lanes = std::min(blockDimX, W);
 		blockDim.x = blockDimX; gridDim.x = blocks;
+		constexpr size_t STACK = 1u << 20;
+		static Sched* scp = new Sched;          // lane stacks are allocated once per process and reused by every launch
+		Sched& sc = *scp;
+		if (sc.stacks.size() < STACK * W) sc.stacks.resize(STACK * W);
+		using Fn = std::remove_reference_t<F>;
+		fiberBody = [](void* a) { (*reinterpret_cast<Fn*>(a))(); };
+		fiberArg = (void*)&body;
 		for (uint32_t b = 0; b < blocks; ++b)
 		{
-			Sched sc; sc.nLanes = lanes;
-			for (uint32_t l = 0; l < W; ++l) { sc.st[l] = l < lanes ? RUN : DONE; sc.site[l] = nullptr; sc.partTag[l] = 0; }
-			sc.current = ascending ? 0 : (int)lanes - 1;
-			sched = &sc;
-			std::vector<std::thread> ts;
-			for (uint32_t l = 0; l < lanes; ++l) ts.emplace_back([&, l, b]
+			sc.nLanes = lanes; sc.collectives = 0;
+			for (uint32_t l = 0; l < W; ++l) { sc.st[l] = l < lanes ? RUN : DONE; sc.site[l] = nullptr; sc.partTag[l] = 0; sc.epochOf[l] = sc.subEpochOf[l] = sc.subCountOf[l] = 0; }
+			for (uint32_t l = 0; l < lanes; ++l)
 			{
-				lane = l; threadIdx.x = l; blockIdx.x = b; epoch = 0; subEpoch = 0; subCount = 0;
-				{
-					std::unique_lock<std::mutex> lk(sc.m);
-					sc.cv[l].wait(lk, [&] { return sc.current == (int)l && sc.st[l] == RUN; });
-				}
-				body();
-				std::unique_lock<std::mutex> lk(sc.m);
-				sc.st[l] = DONE; sc.site[l] = nullptr;
-				reschedule(sc);
-			});
-			for (auto& t : ts) t.join();
+				// initial frame: [mxcsr/fpcw][r15 r14 r13 r12 rbx rbp][return address = fiberEntry][alignment slot]
+				uintptr_t top = (uintptr_t)(sc.stacks.data() + STACK * (l + 1)); top &= ~(uintptr_t)15;
+				uint64_t* sp = reinterpret_cast<uint64_t*>(top) - 11;
+				uint32_t csr[2] = { 0x1F80u, 0x037Fu };
+				std::memcpy(&sp[0], csr, 8);
+				for (int k = 1; k <= 6; ++k) sp[k] = 0;
+				sp[7] = (uint64_t)(uintptr_t)&fiberEntry; sp[8] = 0; sp[9] = 0; sp[10] = 0;      // after `ret`, rsp = &sp[8] = top - 24: 8 mod 16 as at a call boundary
+				sc.ctx[l].sp = sp;
+			}
+			sched = &sc;
+			while (true)
+			{
+				const int next = reschedule(sc);
+				if (next < 0) break;
+				lane = (uint32_t)next; threadIdx.x = (uint32_t)next; blockIdx.x = b;
+				epoch = sc.epochOf[next]; subEpoch = sc.subEpochOf[next]; subCount = sc.subCountOf[next];
+				kb_simt_switch(&sc.mainCtx.sp, sc.ctx[next].sp);
+			}
 			if (std::getenv("HS32_TRACE")) std::fprintf(stderr, "[simt] block %u: %llu full-warp collectives\n", b, (unsigned long long)sc.collectives);
 			sched = nullptr;
 		}

@@ -111,3 +111,15 @@ def test_simulated_cong_pipeline_matches_reference():
         _check(analyze, CONG, "cong_")
     finally:
         close()
+
+
+@pytest.mark.parametrize("mode", ["plain", "typo", "cong"])
+def test_hostsim_full_golden_sweep(mode):
+    """Round 2: with fibers instead of OS threads the simulator is fast enough for EVERY golden sentence (1273 per mode):
+    tokens identical and scores bit-exact against the unmodified reference's vectors, for the Knlm, typo-lattice and CoNg builds."""
+    import subprocess, sys
+    if not os.path.exists(LIB) or not os.path.exists(IMAGE):
+        pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), mode], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "1273 sentences, 0 mismatches" in r.stdout, r.stdout
