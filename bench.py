@@ -1,22 +1,54 @@
 #!/usr/bin/env python3
-"""bench.py — sentences/sec of top-1 analysis at batch 8192 (BASELINE.json config[1]) on N B200s.
+"""bench.py — sentences/sec of top-1 analysis (BASELINE.json metric) on N B200s.
 
-One "step" = one pass of the hot path (lattice kernel + Viterbi kernel + pack) over one batch of 8192 synthetic
-Korean sentences with the web.txt length distribution (kiwi_b200/synth.py), fabricated Knlm model.
+  --config 2 (default) : batch=8192 synthetic Korean sentences (web.txt length dist), Knlm model, top-1        [BASELINE.json configs[1]]
+  --config 3           : batch=65536, CoNg model (int8 scorer on tensor-core tiles)                            [configs[2]]
+  --config 4           : batch=65536, Knlm model + typo lattice (basic typo set, cost weight 6, threshold 2.5), 30 % web_with_typos eojeols [configs[3]]
+  --config 5           : 1 M sentences sharded round-robin (sentence i -> GPU i mod N), CoNg model, STRONG scaling   [configs[4]]
+One "step" = one pass of the hot path (lattice kernel + Viterbi kernel + emit + pack) over the configuration's batch.
   value  : inputs already resident in HBM, device-timed (CUDA events on the engine stream), whole job.
   e2e    : the same batch through the public C-ABI call kiwi_b200_analyze_batch with HOST buffers
            (pinned staging, H2D of text+offsets and D2H of the packed tokens inside the timed region).
-  --impl reference : the reference's own CPU implementation (oracle/_ref, all host threads) on a bounded sample.
-Launch: python bench.py --gpus N --steps K --warmup W   (N > 1: under torchrun, one rank per GPU)."""
-import argparse, json, os, subprocess, sys, tempfile, threading, time
+  --impl reference : the UNMODIFIED reference's CPU implementation (oracle/_ref/ref_bench, all host threads, >= 5 passes in ONE
+           process, median) on a bounded sample of the same workload; also reports the 1-thread figure (tools/Evaluator.cpp:315-329).
+Launch: python bench.py --gpus N --steps K --warmup W   (N > 1: under torchrun, one rank per GPU; or --inproc: ONE process driving
+N GPUs through kiwi_b200_init_multi, the library's own ordered fan-out)."""
+import argparse, json, math, os, subprocess, sys, tempfile, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", "knlm_small.img")
-REF_MODEL_DIR = os.path.join(ROOT, "oracle", "_ref", "models", "knlm_small")
 REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
 METRIC = "sentences/sec (top-1 analyze, batch=8192)"
 UNIT = "sentences/s"
+CONFIGS = {
+    2: dict(model="knlm", batch=8192, typo=None, typo_frac=0.0, rotate=4, steps=20, scaling="weak"),
+    3: dict(model="cong", batch=65536, typo=None, typo_frac=0.0, rotate=1, steps=5, scaling="weak"),
+    4: dict(model="knlm", batch=65536, typo="basic", typo_frac=0.3, rotate=1, steps=5, scaling="weak"),
+    5: dict(model="cong", batch=1 << 20, typo=None, typo_frac=0.0, rotate=1, steps=3, scaling="strong"),
+}
+BLOCK = 8192      # synthetic sentences are generated in seeded blocks of 8192 (block b: seed SEED + b)
+
+
+def image_path(model): return os.path.join(ROOT, "oracle", "_ref", "models", model + "_small.img")
+def ref_model_dir(model): return os.path.join(ROOT, "oracle", "_ref", "models", model + "_small")
+
+
+def workload_string(cfg, cid):
+    s = "config %d: batch=%d synthetic Korean sentences (web.txt length dist), fabricated %s model (%s_small), top-1" % (
+        cid, cfg["batch"], "Knlm" if cfg["model"] == "knlm" else "CoNg", cfg["model"])
+    if cfg["typo"]: s += ", typo lattice (%s typo set, typoCostWeight 6, threshold 2.5), %d %% of the sentences from web_with_typos eojeols" % (cfg["typo"], round(100 * cfg["typo_frac"]))
+    if cfg["scaling"] == "strong": s += ", sharded round-robin (sentence i -> GPU i mod N)"
+    return s
+
+
+def gen_sentences(cfg, first_block, n, seed_base):
+    from kiwi_b200.synth import synth_batch
+    out = []
+    b = first_block
+    while len(out) < n:
+        out += synth_batch(min(BLOCK, n - len(out)), seed_base + b, cfg["typo_frac"])
+        b += 1
+    return out
 
 
 def load_peaks():
@@ -24,6 +56,19 @@ def load_peaks():
     if os.path.exists(p):
         return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
     return 6650.0, "fallback"
+
+
+def host_cpus():
+    """usable host threads: affinity mask, capped by the cgroup CPU quota when there is one"""
+    try: n = len(os.sched_getaffinity(0))
+    except Exception: n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max": quota = float(q) / float(period)
+    except Exception:
+        pass
+    return n, quota
 
 
 class ClockSampler(threading.Thread):
@@ -51,57 +96,54 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def set_model(name):
-    """knlm (headline, BASELINE.json config[1]) or cong (config[2]: quantized CoNg model, int8 scorer on tensor-core tiles)"""
-    global IMAGE, REF_MODEL_DIR, MODEL
-    MODEL = name
-    IMAGE = os.path.join(ROOT, "oracle", "_ref", "models", name + "_small.img")
-    REF_MODEL_DIR = os.path.join(ROOT, "oracle", "_ref", "models", name + "_small")
-
-
-MODEL = "knlm"
-
-
-def work_counters(batch_texts, batch_size, seed):
-    """Per-sentence algorithmic bytes from the instrumented oracle (committed under profiles/; recomputed on a sample if absent)."""
+def work_counters(cfg, cid, texts, seed):
+    """Per-sentence algorithmic bytes from the instrumented oracle: committed under profiles/counters_r2.json for the bench batches
+    (scripts/make_counters.py, every rotating seed); recomputed on a 256-sentence sample when absent."""
     from kiwi_b200 import bytemodel
-    name = "counters_r1.json" if MODEL == "knlm" else "counters_r1b_cong.json"
-    path = os.path.join(ROOT, "profiles", name)
+    path = os.path.join(ROOT, "profiles", "counters_r2.json")
+    key = "cfg%d" % cid
     if os.path.exists(path):
         d = json.load(open(path))
-        key = "batch%d_seed%d" % (batch_size, seed)
         if key in d:
             c = d[key]
-            extra = bytemodel.cong_bytes(c) if MODEL == "cong" else 0.0
-            return c, bytemodel.lattice_bytes(c) / c["sentences"], (bytemodel.viterbi_bytes(c) + extra) / c["sentences"], "profiles/" + name
-    from tests.orc import Oracle
-    o = Oracle(IMAGE)
-    sample = batch_texts[:256]
-    for s in sample: o.analyze(s)
+            return c, c["lattice_bytes_per_sentence"], c["viterbi_bytes_per_sentence"], "profiles/counters_r2.json[%s] (%s)" % (key, c.get("coverage", ""))
+    from tests.orc import Oracle, TypoOracle, TYPO_IMAGES
+    o = Oracle(image_path(cfg["model"]))
+    if cfg["typo"]: o.set_typo(TypoOracle(TYPO_IMAGES[cfg["typo"]]))
+    for s in texts[:256]: o.analyze(s)
     c = o.work_counters()
-    if MODEL == "cong": c.update(o.cong_counters())
+    if cfg["model"] == "cong": c.update(o.cong_counters())
     o.close()
-    extra = bytemodel.cong_bytes(c) if MODEL == "cong" else 0.0
+    extra = bytemodel.cong_bytes(c) if cfg["model"] == "cong" else 0.0
     return c, bytemodel.lattice_bytes(c) / c["sentences"], (bytemodel.viterbi_bytes(c) + extra) / c["sentences"], "oracle sample of 256 sentences"
 
 
-def run_reference_cpu(texts, threads, repeats=1):
-    """Times the unmodified reference (oracle/_ref) when it travelled with the repo, else the oracle port."""
-    if os.path.exists(REF_BENCH) and os.path.exists(REF_MODEL_DIR):
+def run_reference_cpu(cfg, texts, threads, repeats, single_sample=0, dump=None):
+    """Times the unmodified reference (oracle/_ref/ref_bench) when it travelled with the repo, else the oracle port (1 thread)."""
+    if os.path.exists(REF_BENCH) and os.path.exists(ref_model_dir(cfg["model"])):
         with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False, encoding="utf-8") as f:
             for t in texts: f.write(t + "\n")
             tmp = f.name
         try:
-            env = dict(os.environ); env.setdefault("KIWI_ARCH_TYPE", "avx2"); env["KB_MODEL_TYPE"] = MODEL
-            out = subprocess.run([REF_BENCH, REF_MODEL_DIR, tmp, str(threads), str(repeats)], capture_output=True, text=True, timeout=1200, env=env)
-            line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
-            r = json.loads(line)
-            return {"value": r["sent_per_s"], "unit": UNIT, "cores": threads, "kind": "reference",
-                    "sample": "%d sentences of the bench batch, reference Kiwi::analyze batch mode on %d threads, KIWI_ARCH_TYPE=%s, best of %d passes: %.2f s" % (r["sentences"], threads, r["arch"], r["repeats"], r["seconds"])}
+            env = dict(os.environ); env.setdefault("KIWI_ARCH_TYPE", "avx2"); env["KB_MODEL_TYPE"] = cfg["model"]
+            if cfg["typo"]: env["KB_TYPO"] = cfg["typo"]
+            if single_sample: env["KB_SINGLE_SAMPLE"] = str(single_sample)
+            if dump: env["KB_DUMP"] = dump
+            out = subprocess.run([REF_BENCH, ref_model_dir(cfg["model"]), tmp, str(threads), str(repeats)], capture_output=True, text=True, timeout=3000, env=env)
+            lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+            if not lines: raise RuntimeError("ref_bench failed: " + out.stderr[-500:])
+            r = json.loads(lines[-1])
+            n, quota = host_cpus()
+            return {"value": r["sent_per_s_median"], "unit": UNIT, "cores": threads, "kind": "reference",
+                    "best": r["sent_per_s"], "single_thread": r["single_thread_sent_per_s"] or None, "single_thread_sample": r["single_thread_sample"],
+                    "host": {"affinity_cpus": n, "cgroup_cpu_quota": quota},
+                    "sample": "%d sentences of the bench batch, reference Kiwi::analyze batch mode on %d threads, KIWI_ARCH_TYPE=%s, median of %d passes in one process (best %.2f s, median %.2f s)%s" % (
+                        r["sentences"], threads, r["arch"], r["repeats"], r["seconds"], r["seconds_median"], "; single thread on the first %d" % r["single_thread_sample"] if r["single_thread_sample"] else "")}
         finally:
             os.unlink(tmp)
-    from tests.orc import Oracle
-    o = Oracle(IMAGE)
+    from tests.orc import Oracle, TypoOracle, TYPO_IMAGES
+    o = Oracle(image_path(cfg["model"]))
+    if cfg["typo"]: o.set_typo(TypoOracle(TYPO_IMAGES[cfg["typo"]]))
     t0 = time.time()
     for t in texts: o.analyze(t)
     dt = time.time() - t0
@@ -111,34 +153,41 @@ def run_reference_cpu(texts, threads, repeats=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="override the configuration's batch size (experiments)")
+    ap.add_argument("--model", default=None, choices=["knlm", "cong"], help="override the configuration's model (experiments)")
+    ap.add_argument("--typo", default=None, choices=["basic", "none"], help="override the configuration's typo set (experiments)")
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments)")
-    ap.add_argument("--model", default="knlm", choices=["knlm", "cong"], help="knlm = headline config; cong = BASELINE.json config[2] (CoNg model)")
+    ap.add_argument("--inproc", action="store_true", help="one process, --gpus N devices behind ONE handle (kiwi_b200_init_multi) instead of torchrun ranks")
     args = ap.parse_args()
-    set_model(args.model)
+    cfg = dict(CONFIGS[args.config])
+    if args.batch: cfg["batch"] = args.batch
+    if args.model: cfg["model"] = args.model
+    if args.typo: cfg["typo"] = None if args.typo == "none" else args.typo
+    steps = args.steps if args.steps is not None else cfg["steps"]
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    from kiwi_b200.synth import synth_batch, SEED
+    from kiwi_b200.synth import SEED
+    workload = workload_string(cfg, args.config)
+    strong = cfg["scaling"] == "strong"
 
     if args.impl == "reference":
         if rank != 0: return 0
-        threads = os.cpu_count() or 1
-        texts = synth_batch(args.batch, SEED)[:args.cpu_sample]
-        vals = []
-        for _ in range(max(1, args.warmup > 0)): run_reference_cpu(texts[:256], threads)
-        last = None
-        t0 = time.time()
-        for _ in range(args.steps):
-            last = run_reference_cpu(texts, threads); vals.append(last["value"])
-            if time.time() - t0 > 240: break
-        v = sum(vals) / len(vals)
-        last["value"] = v
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-                          "ms_per_step": 1000.0 * len(texts) / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": {"workload": "batch=%d synthetic Korean sentences (web.txt length dist), fabricated %s model, top-1; each step = %d-sentence sample on %d host threads" % (args.batch, MODEL, len(texts), threads)},
+        ncpu, quota = host_cpus()
+        threads = max(1, min(ncpu, int(math.ceil(quota)) if quota else ncpu))
+        texts = gen_sentences(cfg, 0, min(cfg["batch"], args.cpu_sample), SEED)
+        # warm-up: one short pass (page cache, model build) that also sizes the run: >= 5 passes, <= ~4 minutes
+        w = run_reference_cpu(cfg, texts[:512], threads, 1)
+        est = len(texts) / max(w["value"], 1.0)
+        repeats = max(5, min(max(steps, 5), int(200 / max(est, 1e-3))))
+        last = run_reference_cpu(cfg, texts, threads, repeats, single_sample=min(len(texts), 1024))
+        v = last["value"]
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": repeats, "warmup": 1,
+                          "ms_per_step": 1000.0 * len(texts) / v, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": workload, "sample": "each step = the first %d sentences of the batch on %d host threads" % (len(texts), threads)},
                           "cpu_baseline": last, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -147,12 +196,15 @@ def main():
     import kiwi_b200
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU: kiwi_b200 has no CPU fallback")
+    inproc = args.inproc and args.gpus > 1
+    if inproc: world, rank, local_rank = 1, 0, 0
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # ---- model: rank 0 reads the image, one NCCL broadcast puts it on every GPU (no collectives afterwards)
+    IMAGE = image_path(cfg["model"])
     if rank == 0:
         img = np.fromfile(IMAGE, dtype=np.uint8)
         size = torch.tensor([img.size], dtype=torch.int64, device="cuda")
@@ -163,48 +215,91 @@ def main():
     if world > 1: dist.broadcast(buf, 0)
     image_bytes = buf.cpu().numpy().tobytes()
     del buf
-    kw = kiwi_b200.Kiwi(image_bytes=image_bytes, device=local_rank)
+    ndev = args.gpus if inproc else world
+    kw = kiwi_b200.Kiwi(image_bytes=image_bytes, devices=list(range(args.gpus))) if inproc else kiwi_b200.Kiwi(image_bytes=image_bytes, device=local_rank)
+    typo = None
+    if cfg["typo"]:
+        from tests.orc import TYPO_IMAGES
+        typo = kiwi_b200.PreparedTypo(path=TYPO_IMAGES[cfg["typo"]])
+    option = kiwi_b200.default_option(typo=typo)
 
-    # ---- per-rank synthetic batches (weak scaling: every rank works on `batch` sentences per step)
-    R = 4
+    # ---- synthetic batches.  weak scaling: every rank works on `batch` sentences per step (its own seeds);
+    #      strong scaling (config 5): ONE job of `batch` sentences, rank r owns the sentences i = r (mod N)
+    R = cfg["rotate"]
     batches = []
-    for r in range(R):
-        texts = synth_batch(args.batch, SEED + 1000 * rank + r)
-        blob, off = kiwi_b200.encode_batch(texts)
-        d_blob = torch.from_numpy(blob.view(np.int16)).cuda(); d_off = torch.from_numpy(off.view(np.int32)).cuda()
-        batches.append((texts, blob, off, d_blob, d_off))
+    if strong:
+        from kiwi_b200.shard import shard_indices
+        all_texts = gen_sentences(cfg, 0, cfg["batch"], SEED)
+        mine = [all_texts[i] for i in shard_indices(len(all_texts), rank, world)] if world > 1 else all_texts
+        blob, off = kiwi_b200.encode_batch(mine)
+        batches.append((mine, blob, off, torch.from_numpy(blob.view(np.int16)).cuda(), torch.from_numpy(off.view(np.int32)).cuda()))
+    else:
+        nblk = (cfg["batch"] + BLOCK - 1) // BLOCK
+        for r in range(R):
+            texts = gen_sentences(cfg, (1000 * rank + r) * nblk if (rank or r) else 0, cfg["batch"], SEED)
+            blob, off = kiwi_b200.encode_batch(texts)
+            batches.append((texts, blob, off, torch.from_numpy(blob.view(np.int16)).cuda(), torch.from_numpy(off.view(np.int32)).cuda()))
     torch.cuda.synchronize()
+    n_local = len(batches[0][0])
 
     def step_device(i):
         _, blob, off, d_blob, d_off = batches[i % R]
-        return kw.analyze_device(d_blob.data_ptr(), d_off.data_ptr(), args.batch, int(blob.size))
+        return kw.analyze_device(d_blob.data_ptr(), d_off.data_ptr(), len(off) - 1, int(blob.size), option)
 
-    for i in range(args.warmup): step_device(i)
-    sampler = ClockSampler(local_rank); sampler.start()
-    if dist: dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.time()
-    dev_ms = 0.0; ms_vit = 0.0; ms_lat = 0.0; launches = 0; tokens = 0; retried = 0
-    for i in range(args.steps):
-        ms, nt, nl = step_device(i)
-        st = kw.last_stats()
-        dev_ms += ms; ms_vit += st.ms_viterbi; ms_lat += st.ms_lattice; launches += st.kernel_launches; tokens += nt; retried += st.retried
-    torch.cuda.synchronize()
-    if dist: dist.barrier()
-    wall = time.time() - t0
-    sampler.stop_flag = True; sampler.join(timeout=2)
+    dev_ms = 0.0; ms_vit = 0.0; ms_lat = 0.0; launches = 0; tokens = 0; retried = 0; wall = 0.0
+    sampler = ClockSampler(local_rank)
+    if not inproc:
+        for i in range(args.warmup): step_device(i)
+        sampler.start()
+        if dist: dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for i in range(steps):
+            ms, nt, nl = step_device(i)
+            st = kw.last_stats()
+            dev_ms += ms; ms_vit += st.ms_viterbi; ms_lat += st.ms_lattice; launches += st.kernel_launches; tokens += nt; retried += st.retried
+        torch.cuda.synchronize()
+        if dist: dist.barrier()
+        wall = time.time() - t0
+    else:
+        sampler.start()
 
     # ---- end to end through the public API with host buffers
-    for i in range(min(2, args.warmup)): kw.analyze_batch_arrays(batches[i % R][1], batches[i % R][2])
+    for i in range(min(2, args.warmup)): kw.analyze_batch_arrays(batches[i % R][1], batches[i % R][2], option)
     if dist: dist.barrier()
     torch.cuda.synchronize()
-    t1 = time.time(); h2d = d2h = 0
-    for i in range(args.steps):
-        kw.analyze_batch_arrays(batches[i % R][1], batches[i % R][2])
-        st = kw.last_stats(); h2d += st.h2d_bytes; d2h += st.d2h_bytes
+    t1 = time.time(); h2d = d2h = 0; e2e_launches = 0; order_ok = None
+    res = None
+    for i in range(steps):
+        res = kw.analyze_batch_arrays(batches[i % R][1], batches[i % R][2], option)
+        st = kw.last_stats(); h2d += st.h2d_bytes; d2h += st.d2h_bytes; e2e_launches += st.kernel_launches
+        if strong and dist:
+            # ordered delivery of the sharded job: every rank contributes its per-sentence token counts; rank 0 restores input order
+            cnt = torch.from_numpy(np.diff(res.token_offsets.astype(np.int64)).astype(np.int32)).cuda()
+            pad = torch.zeros((len(all_texts) + world - 1) // world, dtype=torch.int32, device="cuda"); pad[:cnt.numel()] = cnt
+            gathered = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad, gathered, 0)
+            if rank == 0:
+                from kiwi_b200.shard import merge_round_robin
+                per_rank = [g.cpu().numpy()[:len(range(r, len(all_texts), world))] for r, g in enumerate(gathered)]
+                merged = merge_round_robin(per_rank, len(all_texts)) if i == steps - 1 else None
     torch.cuda.synchronize()
     if dist: dist.barrier()
     e2e_wall = time.time() - t1
+    if not sampler.stop_flag:
+        sampler.stop_flag = True; sampler.join(timeout=2)
+    if strong and rank == 0:
+        # order check of the merged job on a sample: sentence i of the merged result must be sentence i of the input
+        if dist:
+            sample = list(range(0, len(all_texts), 997))
+            chk = kw.analyze_batch([all_texts[i] for i in sample], option)
+            order_ok = bool(all(int(merged[i]) == int(chk.token_offsets[k + 1] - chk.token_offsets[k]) for k, i in enumerate(sample)))
+        elif inproc:
+            single = kiwi_b200.Kiwi(image_bytes=image_bytes, device=0)
+            sample = list(range(0, len(all_texts), 997))
+            chk = single.analyze_batch([all_texts[i] for i in sample], option)
+            order_ok = bool(all(np.array_equal(res.sentence(i), chk.sentence(k)) for k, i in enumerate(sample)))
+            single.close()
 
     t = torch.tensor([dev_ms, wall, e2e_wall, ms_vit, ms_lat], dtype=torch.float64, device="cuda")
     if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -213,45 +308,55 @@ def main():
         if dist: dist.destroy_process_group()
         return 0
 
-    total_sent = args.batch * args.steps * world
-    value = total_sent / (dev_ms / 1000.0)
+    total_sent = (cfg["batch"] if strong else cfg["batch"] * ndev) * steps
     e2e = total_sent / e2e_wall
+    if inproc: dev_ms = e2e_wall * 1000.0; launches = e2e_launches      # (one handle over N devices has no single device timeline: value = the host-timed job)
+    value = total_sent / (dev_ms / 1000.0)
     peak, peak_kind = load_peaks()
-    c, lat_b, vit_b, csrc = work_counters(batches[0][0], args.batch, SEED)
-    vit_per_launch_ms = ms_vit / args.steps
-    achieved = vit_b * args.batch / (vit_per_launch_ms / 1000.0) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic_r1b.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("viterbi_kernel_dram_bytes_per_launch" if MODEL == "knlm" else "viterbi_cong_kernel_dram_bytes_per_launch")
-    cpu = run_reference_cpu(batches[0][0][:args.cpu_sample], os.cpu_count() or 1, repeats=5) if (world == 1 and not args.no_cpu) else None
+    c, lat_b, vit_b, csrc = work_counters(cfg, args.config, batches[0][0], SEED)
+    kernel = "viterbi_kernel" if cfg["model"] == "knlm" else "viterbi_cong_kernel"
+    vit_per_step_ms = ms_vit / steps if steps else 0.0
+    achieved = vit_b * n_local / (vit_per_step_ms / 1000.0) / 1e9 if vit_per_step_ms else None
+    prof = {}
+    pp = os.path.join(ROOT, "profiles", "ncu_r2.json")
+    if os.path.exists(pp): prof = json.load(open(pp)).get(kernel, {})
+    cpu = None
+    if world == 1 and not inproc and not args.no_cpu:
+        ncpu, quota = host_cpus()
+        threads = max(1, min(ncpu, int(math.ceil(quota)) if quota else ncpu))
+        cpu = run_reference_cpu(cfg, batches[0][0][:args.cpu_sample], threads, 5, single_sample=512)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ndev, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "batch=%d synthetic Korean sentences (web.txt length dist) per GPU per step, fabricated %s model (%s_small), top-1" % (args.batch, "Knlm" if MODEL == "knlm" else "CoNg", MODEL),
-                   "l2": "per-step scratch working set (GBs) exceeds the 126 MB L2 and %d distinct input batches rotate; the read-only model stays resident as in steady state" % R,
-                   "parallelism": "dp%d (sentence sharding, one NCCL broadcast of the model image at init, no steady-state collectives)" % world,
-                   "wall_ms_per_step": 1000.0 * wall / args.steps,
-                   "retried_sentences_per_step": retried / args.steps},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps},
+        "config": {"workload": workload,
+                   "l2": "per-step scratch working set (GBs) exceeds the 126 MB L2%s; the read-only model stays resident as in steady state" % (" and %d distinct input batches rotate" % R if R > 1 else ""),
+                   "parallelism": ("one process, one handle over %d devices (kiwi_b200_init_multi): round-robin shards, one host thread per device, ordered merge" % ndev) if inproc else
+                                  "dp%d (sentence sharding, one NCCL broadcast of the model image at init, no steady-state collectives)" % world,
+                   "wall_ms_per_step": 1000.0 * wall / steps if steps else None,
+                   "retried_sentences_per_step": retried / steps if steps else None,
+                   "sentences_per_gpu_per_step": n_local if not inproc else cfg["batch"] // ndev},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // steps, "d2h_bytes_per_step": d2h // steps},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "roofline": {"bound": "hbm", "kernel": "viterbi_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                     "traffic": prof.get("dram_bytes_per_launch"),
                      "peak_kind": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650",
                      "algorithmic_bytes_per_sentence": vit_b, "lattice_kernel_bytes_per_sentence": lat_b, "counters": csrc,
-                     "kernel_ms_per_launch": vit_per_launch_ms, "lattice_ms_per_launch": ms_lat / args.steps,
-                     "kernel_share_of_step": ms_vit / dev_ms if dev_ms else None},
-        "tokens_per_step": tokens // args.steps,
+                     "kernel_ms_per_step": vit_per_step_ms, "lattice_ms_per_step": ms_lat / steps if steps else None,
+                     "kernel_share_of_step": ms_vit / dev_ms if dev_ms and not inproc else None,
+                     # the kernels keep their working set in L2: DRAM is not the limiter, so the ncu capture's L2 and issue-slot figures ride along
+                     "l2": prof.get("l2"), "issue": prof.get("issue"), "profile": prof.get("source")},
+        "tokens_per_step": tokens // steps if steps else None,
     }
+    if order_ok is not None: line["config"]["ordered_merge_check"] = order_ok
     if cpu: line["cpu_baseline"] = cpu
-    if MODEL == "cong":
+    if cfg["model"] == "cong":
         # the int8 gather GEMMs of progressMatrix: 2 * sum(m * n * dim) integer ops per sentence (counted by the instrumented oracle)
         ops = 2.0 * c.get("cgMacs", 0) / max(1, c["sentences"])
-        line["roofline"]["kernel"] = "viterbi_cong_kernel"
-        line["roofline"]["tensor"] = {"bound": "tensor", "unit": "TOP/s", "achieved": ops * args.batch / (vit_per_launch_ms / 1000.0) / 1e12, "peak": 4500.0,
+        line["roofline"]["tensor"] = {"bound": "tensor", "unit": "TOP/s", "achieved": ops * n_local / (vit_per_step_ms / 1000.0) / 1e12 if vit_per_step_ms else None, "peak": 4500.0,
                                       "peak_kind": "nominal dense int8 (no measured int8 peak in MEASURED_PEAKS.json)", "int8_ops_per_sentence": ops,
-                                      "note": "the gather GEMMs are a small part of viterbi_cong_kernel's time; the kernel as a whole is latency / HBM-L2 bound like the Knlm one"}
+                                      "note": "the gather GEMMs are a small part of viterbi_cong_kernel's time; the kernel as a whole is latency / L2 bound like the Knlm one"}
     print(json.dumps(line))
     if dist: dist.destroy_process_group()
     return 0

@@ -133,6 +133,8 @@ const char* kiwi_res_form(kiwi_res_h result, int index, int num);            /* 
 const char* kiwi_res_tag(kiwi_res_h result, int index, int num);             /* capi.h:867 */
 int kiwi_res_position(kiwi_res_h result, int index, int num);                /* capi.h:877 */
 int kiwi_res_length(kiwi_res_h result, int index, int num);                  /* capi.h:887 */
+int kiwi_res_word_position(kiwi_res_h result, int index, int num);          /* capi.h:897 */
+int kiwi_res_sent_position(kiwi_res_h result, int index, int num);          /* capi.h:907 */
 float kiwi_res_score(kiwi_res_h result, int index, int num);                 /* capi.h:917 */
 float kiwi_res_typo_cost(kiwi_res_h result, int index, int num);             /* capi.h:927 */
 int kiwi_res_close(kiwi_res_h result);                                       /* capi.h:937 */
@@ -197,6 +199,11 @@ int kiwi_b200_set_device(int device);            /* call before kiwi_init; defau
 /* raw model image access so a launcher can broadcast it (NCCL) and hand it to every rank */
 int kiwi_b200_read_image(const char* model_path, void** out_bytes, uint64_t* out_size);   /* malloc'ed */
 kiwi_h kiwi_b200_init_from_image(const void* bytes, uint64_t size);
+/* One handle over several GPUs of one box: the read-only model is made resident on every listed device; kiwi_analyze_m[w] and
+ * kiwi_b200_analyze_batch shard each batch round-robin (sentence i -> devices[i mod n]), one host thread per device, and deliver
+ * results in input order (the reference's ordered pool, include/kiwi/Kiwi.h:402-454).  No collective in steady state. */
+kiwi_h kiwi_b200_init_multi(const void* bytes, uint64_t size, const int* devices, int n_devices);
+int kiwi_b200_num_devices(kiwi_h handle);
 void kiwi_b200_free(void* p);
 
 #ifdef __cplusplus

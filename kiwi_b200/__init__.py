@@ -118,6 +118,9 @@ def load_library() -> C.CDLL:
     lib.kiwi_close.argtypes = [C.c_void_p]
     lib.kiwi_b200_init_from_image.restype = C.c_void_p
     lib.kiwi_b200_init_from_image.argtypes = [C.c_void_p, C.c_uint64]
+    lib.kiwi_b200_init_multi.restype = C.c_void_p
+    lib.kiwi_b200_init_multi.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int), C.c_int]
+    lib.kiwi_b200_num_devices.argtypes = [C.c_void_p]
     lib.kiwi_b200_analyze_batch.restype = C.POINTER(_Batch)
     lib.kiwi_b200_analyze_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, AnalyzeOption]
     lib.kiwi_b200_batch_free.argtypes = [C.POINTER(_Batch)]
@@ -181,12 +184,27 @@ def encode_batch(texts: Sequence[str]) -> Tuple[np.ndarray, np.ndarray]:
     return np.ascontiguousarray(blob), offsets
 
 
+class _BatchOwner:
+    """keeps the C-side batch (kiwi_b200_batch_t) alive while numpy views of its arrays are in use"""
+    def __init__(self, lib, p):
+        self.lib, self.p = lib, p
+
+    def __del__(self):
+        try:
+            if self.p:
+                self.lib.kiwi_b200_batch_free(self.p); self.p = None
+        except Exception:
+            pass
+
+
 @dataclass
 class BatchResult:
     token_offsets: np.ndarray      # uint32 [n + 1]
     tokens: np.ndarray             # TOKEN_DTYPE
     scores: np.ndarray             # float32 [n]
     timings_ms: dict
+    status: np.ndarray = None      # uint32 [n]: 0 = analysed; non-zero = the sentence exceeded even the escalated device capacity (no tokens)
+    _owner: object = None          # the arrays above are views into the library's result buffers (no copy)
 
     def sentence(self, i: int) -> np.ndarray:
         return self.tokens[self.token_offsets[i]:self.token_offsets[i + 1]]
@@ -195,11 +213,20 @@ class BatchResult:
 class Kiwi:
     """Analysis handle.  `model_path` is a kiwi_b200 model image (or a directory containing kiwi_b200.img)."""
 
-    def __init__(self, model_path: str = None, num_threads: int = 0, device: int = None, image_bytes: bytes = None):
+    def __init__(self, model_path: str = None, num_threads: int = 0, device: int = None, image_bytes: bytes = None, devices: Sequence[int] = None):
+        """`devices=[0, 1, ...]`: ONE handle over several GPUs of the box (kiwi_b200_init_multi): batches are sharded round-robin,
+        one host thread per device, results in input order."""
         self._lib = load_library()
         if device is not None:
             self._lib.kiwi_b200_set_device(int(device))
-        if image_bytes is not None:
+        if devices is not None:
+            if image_bytes is None:
+                with open(model_path if not os.path.isdir(model_path) else os.path.join(model_path, "kiwi_b200.img"), "rb") as f:
+                    image_bytes = f.read()
+            buf = (C.c_char * len(image_bytes)).from_buffer_copy(image_bytes)
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self._h = self._lib.kiwi_b200_init_multi(C.cast(buf, C.c_void_p), len(image_bytes), arr, len(devices))
+        elif image_bytes is not None:
             buf = (C.c_char * len(image_bytes)).from_buffer_copy(image_bytes)
             self._h = self._lib.kiwi_b200_init_from_image(C.cast(buf, C.c_void_p), len(image_bytes))
         else:
@@ -225,20 +252,19 @@ class Kiwi:
         p = self._lib.kiwi_b200_analyze_batch(self._h, blob.ctypes.data, offsets.ctypes.data, n, option)
         if not p:
             raise KiwiError(_last_error(self._lib))
-        try:
-            b = p.contents
-            tok_off = np.ctypeslib.as_array(b.token_offsets, shape=(n + 1,)).copy()
-            total = int(tok_off[n])
-            if total:
-                raw = (C.c_char * (total * TOKEN_DTYPE.itemsize)).from_address(b.tokens)
-                tokens = np.frombuffer(raw, dtype=TOKEN_DTYPE).copy()
-            else:
-                tokens = np.zeros(0, dtype=TOKEN_DTYPE)
-            scores = np.ctypeslib.as_array(b.scores, shape=(n,)).copy() if n else np.zeros(0, np.float32)
-            tm = dict(h2d=b.ms_h2d, lattice=b.ms_lattice, viterbi=b.ms_viterbi, pack=b.ms_pack, d2h=b.ms_d2h, total=b.ms_total)
-        finally:
-            self._lib.kiwi_b200_batch_free(p)
-        return BatchResult(tok_off, tokens, scores, tm)
+        owner = _BatchOwner(self._lib, p)
+        b = p.contents
+        tok_off = np.ctypeslib.as_array(b.token_offsets, shape=(n + 1,))
+        total = int(tok_off[n])
+        if total:
+            raw = (C.c_char * (total * TOKEN_DTYPE.itemsize)).from_address(b.tokens)
+            tokens = np.frombuffer(raw, dtype=TOKEN_DTYPE)
+        else:
+            tokens = np.zeros(0, dtype=TOKEN_DTYPE)
+        scores = np.ctypeslib.as_array(b.scores, shape=(n,)) if n else np.zeros(0, np.float32)
+        status = np.ctypeslib.as_array(b.status, shape=(n,)) if n else np.zeros(0, np.uint32)
+        tm = dict(h2d=b.ms_h2d, lattice=b.ms_lattice, viterbi=b.ms_viterbi, pack=b.ms_pack, d2h=b.ms_d2h, total=b.ms_total)
+        return BatchResult(tok_off, tokens, scores, tm, status, owner)
 
     def analyze_batch(self, texts: Sequence[str], option: AnalyzeOption = None) -> BatchResult:
         blob, offsets = encode_batch(texts)

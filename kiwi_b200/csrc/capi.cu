@@ -2,8 +2,10 @@
 // C API (/root/reference/src/capi/kiwi_c.cpp:84-113): nothing is thrown across the ABI, failures return
 // NULL / KIWIERR_* and leave a message for the calling thread in kiwi_error().
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -15,8 +17,9 @@ using namespace kb;
 
 struct kiwi_s
 {
-	std::unique_ptr<Engine> engine;
-	std::mutex mtx;           // one stream + one scratch arena per handle: calls on one handle are serialised
+	std::unique_ptr<Engine> engine;                      // primary engine (device of kiwi_init / first device of kiwi_b200_init_multi)
+	std::vector<std::unique_ptr<Engine>> extra;          // kiwi_b200_init_multi: one more engine per further device; batches are sharded round-robin
+	std::mutex mtx;           // scratch arenas and streams belong to the handle: calls on one handle are serialised
 	int numThreads = 0;
 	float oovChrBias = 0, oovGlobalWeight = 35, oovLocalWeight = 3, oovGlobalMinFreq = 4;      // KiwiConfig defaults of the chr-model oov scorers (stored only)
 };
@@ -25,14 +28,31 @@ struct kiwi_s
 // of that set as the reference prepared it (oracle/ref_build/tools/typo_tool.cpp writes typo_<set>.img): building a
 // PreparedTypoTransformer from rules natively is a host-side "next" row.
 struct kiwi_typo { int set; };
-struct kiwi_prepared_typo { kb::TypoDev dev; };
+struct kiwi_prepared_typo
+{
+	std::vector<char> blob;
+	std::mutex m;
+	std::map<int, std::unique_ptr<kb::TypoDev>> perDevice;      // the flat typo image resident on every device that used it
+	const kb::TypoDev* forDevice(int device)
+	{
+		std::lock_guard<std::mutex> lk(m);
+		auto& p = perDevice[device];
+		if (!p)
+		{
+			kb::DeviceGuard g{ device };
+			p.reset(new kb::TypoDev);
+			p->load(blob.data(), blob.size());
+		}
+		return p.get();
+	}
+};
 static kiwi_typo g_defaultTypos[7] = { {0}, {1}, {2}, {3}, {4}, {5}, {6} };
 static std::string g_typoDir;      // directory of the last model image opened by kiwi_init
 
 struct TypoScope      // AnalyzeOption::typoTransformer for the calls made while the handle's mutex is held
 {
 	Engine* e;
-	TypoScope(Engine* _e, const kiwi_analyze_option_t& o) : e{ _e } { e->setTypo(o.typo_transformer ? &o.typo_transformer->dev : nullptr, o.typo_threshold); }
+	TypoScope(Engine* _e, const kiwi_analyze_option_t& o) : e{ _e } { e->setTypo(o.typo_transformer ? o.typo_transformer->forDevice(e->device) : nullptr, o.typo_threshold); }
 	~TypoScope() { e->setTypo(nullptr, 2.5f); }
 };
 
@@ -177,6 +197,78 @@ static kiwi_res* makeRes(kiwi_s* h, const uint16_t* text, uint32_t rawLen, const
 	return r;
 }
 
+// One batch through the handle's engine(s).  With several devices (kiwi_b200_init_multi) sentence i goes to device i mod N
+// (BASELINE.json config 5); one host thread per device gathers its shard, runs it, and scatters its rows back into the batch's
+// output arrays in input order - the reference's ordered delivery (include/kiwi/Kiwi.h:402-454) without a collective.
+static void analyzeSharded(kiwi_s* h, const uint16_t* text, const uint32_t* offsets, uint32_t n, const kiwi_analyze_option_t& option, BatchOutput& out)
+{
+	const uint32_t N = 1 + (uint32_t)h->extra.size();
+	if (N == 1 || n < 2 * N)
+	{
+		TypoScope ts{ h->engine.get(), option };
+		h->engine->analyze(text, offsets, n, (uint32_t)option.match_options, out);
+		return;
+	}
+	std::vector<BatchOutput> part(N);
+	std::vector<std::string> errors(N);
+	std::vector<Stats> stats(N);
+	auto work = [&](uint32_t r)
+	{
+		try
+		{
+			Engine* e = r == 0 ? h->engine.get() : h->extra[r - 1].get();
+			std::vector<uint16_t> sub; std::vector<uint32_t> off{ 0 };
+			size_t units = 0;
+			for (uint32_t i = r; i < n; i += N) units += offsets[i + 1] - offsets[i];
+			sub.reserve(units); off.reserve(n / N + 2);
+			for (uint32_t i = r; i < n; i += N) { sub.insert(sub.end(), text + offsets[i], text + offsets[i + 1]); off.push_back((uint32_t)sub.size()); }
+			TypoScope ts{ e, option };
+			e->analyze(sub.data(), off.data(), (uint32_t)off.size() - 1, (uint32_t)option.match_options, part[r]);
+			stats[r] = e->last;
+		}
+		catch (const std::exception& ex) { errors[r] = ex.what(); if (errors[r].empty()) errors[r] = "error"; }
+	};
+	std::vector<std::thread> th;
+	for (uint32_t r = 1; r < N; ++r) th.emplace_back(work, r);
+	work(0);
+	for (auto& t : th) t.join();
+	for (auto& e : errors) if (!e.empty()) throw std::runtime_error(e);
+	// ordered merge: token offsets by prefix sum over the round-robin order, then every shard scatters its rows
+	out = BatchOutput{};
+	out.tokOff.assign((size_t)n + 1, 0); out.scores.resize(n); out.status.resize(n);
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const BatchOutput& p = part[i % N]; const uint32_t k = i / N;
+		out.tokOff[i + 1] = out.tokOff[i] + (p.tokOff[k + 1] - p.tokOff[k]);
+		out.scores[i] = p.scores[k]; out.status[i] = p.status[k];
+	}
+	out.tokens.resize(out.tokOff[n]);
+	auto scatter = [&](uint32_t r)
+	{
+		const BatchOutput& p = part[r];
+		for (uint32_t i = r, k = 0; i < n; i += N, ++k)
+		{
+			const uint32_t cnt = p.tokOff[k + 1] - p.tokOff[k];
+			if (cnt) std::memcpy(out.tokens.data() + out.tokOff[i], p.tokens.data() + p.tokOff[k], (size_t)cnt * sizeof(DToken));
+		}
+	};
+	th.clear();
+	for (uint32_t r = 1; r < N; ++r) th.emplace_back(scatter, r);
+	scatter(0);
+	for (auto& t : th) t.join();
+	Stats agg{};
+	for (uint32_t r = 0; r < N; ++r)
+	{
+		const BatchOutput& p = part[r];
+		out.msH2D = std::max(out.msH2D, p.msH2D); out.msLattice = std::max(out.msLattice, p.msLattice); out.msViterbi = std::max(out.msViterbi, p.msViterbi);
+		out.msPack = std::max(out.msPack, p.msPack); out.msD2H = std::max(out.msD2H, p.msD2H); out.msTotal = std::max(out.msTotal, p.msTotal);
+		agg.h2dBytes += stats[r].h2dBytes; agg.d2hBytes += stats[r].d2hBytes; agg.kernelLaunches += stats[r].kernelLaunches; agg.retried += stats[r].retried;
+		agg.rawUnits += stats[r].rawUnits;
+	}
+	agg.nSentences = n; agg.tokens = out.tokens.size(); agg.msLattice = out.msLattice; agg.msViterbi = out.msViterbi; agg.msPack = out.msPack;
+	h->engine->last = agg;
+}
+
 // Drains the reader into batches (the reference primes pool->size()*2 futures, include/kiwi/Kiwi.h:402-454);
 // results are delivered to the receiver in input order, which owns and closes them (kiwi_c.cpp:932-936).
 template<class ReadFn>
@@ -205,8 +297,7 @@ static int analyzeMulti(kiwi_h handle, ReadFn&& readOne, kiwi_receiver_t receive
 			BatchOutput bo;
 			{
 				std::lock_guard<std::mutex> lk(handle->mtx);
-				TypoScope ts{ handle->engine.get(), option };
-				handle->engine->analyze(text.data(), off.data(), n, (uint32_t)option.match_options, bo);
+				analyzeSharded(handle, text.data(), off.data(), n, option, bo);
 			}
 			for (uint32_t i = 0; i < n; ++i)
 			{
@@ -260,6 +351,37 @@ kiwi_h kiwi_b200_init_from_image(const void* bytes, uint64_t size)
 	catch (const std::exception& e) { setError(e); return nullptr; }
 }
 
+kiwi_h kiwi_b200_init_multi(const void* bytes, uint64_t size, const int* devices, int n_devices)
+{
+	try
+	{
+		int n = 0;
+		if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw std::runtime_error("kiwi_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
+		if (n_devices < 1) throw std::invalid_argument("kiwi_b200_init_multi: n_devices < 1");
+		for (int i = 0; i < n_devices; ++i) if (devices[i] < 0 || devices[i] >= n) throw std::invalid_argument("kiwi_b200_init_multi: no such device");
+		auto h = std::unique_ptr<kiwi_s>(new kiwi_s);
+		int prev = 0; cudaGetDevice(&prev);
+		// one resident copy of the read-only model per device; the copies are made concurrently (one host thread per device)
+		std::vector<std::unique_ptr<Engine>> eng((size_t)n_devices);
+		std::vector<std::string> errors((size_t)n_devices);
+		std::vector<std::thread> th;
+		for (int i = 0; i < n_devices; ++i) th.emplace_back([&, i]
+		{
+			try { if (cudaSetDevice(devices[i]) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed"); eng[i].reset(new Engine(bytes, size)); }
+			catch (const std::exception& e) { errors[i] = e.what(); }
+		});
+		for (auto& t : th) t.join();
+		cudaSetDevice(prev);
+		for (auto& e : errors) if (!e.empty()) throw std::runtime_error(e);
+		h->engine = std::move(eng[0]);
+		for (int i = 1; i < n_devices; ++i) h->extra.push_back(std::move(eng[i]));
+		return h.release();
+	}
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+int kiwi_b200_num_devices(kiwi_h handle) { return handle ? 1 + (int)handle->extra.size() : KIWIERR_INVALID_HANDLE; }
+
 kiwi_h kiwi_init(const char* model_path, int num_threads, int options, int enabled_dialects)
 {
 	(void)options; (void)enabled_dialects;
@@ -303,7 +425,13 @@ kiwi_prepared_typo_h kiwi_b200_typo_from_image(const void* bytes, size_t size)
 	try
 	{
 		auto* t = new kiwi_prepared_typo;
-		try { t->dev.load(bytes, size); }
+		try
+		{
+			t->blob.assign(reinterpret_cast<const char*>(bytes), reinterpret_cast<const char*>(bytes) + size);
+			int dev = 0;
+			if (g_device >= 0) dev = g_device; else cudaGetDevice(&dev);
+			t->forDevice(dev);      // validates the image and makes it resident on the current device
+		}
 		catch (...) { delete t; throw; }
 		return t;
 	}
@@ -417,6 +545,8 @@ const char* kiwi_res_form(kiwi_res_h result, int index, int num) { KB_TOK_OR(nul
 const char* kiwi_res_tag(kiwi_res_h result, int index, int num) { KB_TOK_OR(nullptr) return tagName(result->toks[num].info.tag); }
 int kiwi_res_position(kiwi_res_h result, int index, int num) { KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].info.chr_position; }
 int kiwi_res_length(kiwi_res_h result, int index, int num) { KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].info.length; }
+int kiwi_res_word_position(kiwi_res_h result, int index, int num) { KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].info.word_position; }
+int kiwi_res_sent_position(kiwi_res_h result, int index, int num) { KB_TOK_OR(KIWIERR_INVALID_INDEX) return (int)result->toks[num].info.sent_position; }
 float kiwi_res_score(kiwi_res_h result, int index, int num) { KB_TOK_OR(0.f) return result->toks[num].info.score; }
 float kiwi_res_typo_cost(kiwi_res_h result, int index, int num) { KB_TOK_OR(0.f) return result->toks[num].info.typo_cost; }
 int kiwi_res_close(kiwi_res_h result) { if (!result) return KIWIERR_INVALID_HANDLE; delete result; return 0; }
@@ -434,8 +564,7 @@ const kiwi_b200_batch_t* kiwi_b200_analyze_batch(kiwi_h handle, const kchar16_t*
 		try
 		{
 			std::lock_guard<std::mutex> lk(handle->mtx);
-			TypoScope ts{ handle->engine.get(), option };
-			handle->engine->analyze(text, offsets, (uint32_t)n, (uint32_t)option.match_options, h->bo);
+			analyzeSharded(handle, text, offsets, (uint32_t)n, option, h->bo);
 		}
 		catch (...) { delete h; throw; }
 		static_assert(sizeof(kiwi_b200_token_t) == sizeof(DToken), "token layout");
@@ -537,6 +666,7 @@ void kiwi_set_global_config(kiwi_h handle, kiwi_config_t config)
 		c.max_unk_form_size = config.max_unk_form_size; c.max_unk_form_size_followed_by_jclass = config.max_unk_form_size_followed_by_j_class;
 		c.space_tolerance = config.space_tolerance;
 		handle->engine->setConfig(c);
+		for (auto& e : handle->extra) e->setConfig(c);
 		handle->oovChrBias = config.oov_chr_bias; handle->oovGlobalWeight = config.oov_global_weight;
 		handle->oovLocalWeight = config.oov_local_weight; handle->oovGlobalMinFreq = config.oov_global_min_freq;
 	}

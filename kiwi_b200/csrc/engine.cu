@@ -6,11 +6,15 @@
 // include/kiwi/Kiwi.h:402-454): here the host only copies the text blob + offsets in and the packed
 // tokens out; normalisation, chunking, lattice, Viterbi, stitching and position mapping run on the GPU.
 // Sentences whose scratch demand exceeds the arithmetic capacity (rare, e.g. 50 x the same syllable) are
-// re-run in a second, larger-capacity pass; a sentence that still does not fit is a hard error.
+// re-run in a larger-capacity retry arena (two escalation rounds); a sentence that still does not fit keeps its
+// status and comes back without tokens - the batch itself never fails on input text.
+// Batches larger than one pass alternate between two arenas on two streams (H2D / kernels / D2H of neighbouring
+// passes overlap); one lock per CUDA device serialises engines that share the device's constant-memory model view.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <cub/device/device_scan.cuh>
@@ -59,22 +63,53 @@ namespace kb
 		for (uint32_t i = lane; i < n; i += 32) packed[o + i] = tokens[wbase + i];
 	}
 
+	// ---- per-device state: one lock and one owner of the kernels' __constant__ model view per CUDA device --------------
+	namespace
+	{
+		struct DevState { std::recursive_mutex mtx; const Model* owner = nullptr; };
+		DevState g_devState[64];
+	}
+	DeviceGuard::DeviceGuard(int device) : dev{ device < 0 || device >= 64 ? 0 : device }
+	{
+		g_devState[dev].mtx.lock();
+		if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+		if (prev != dev) cudaSetDevice(dev);
+	}
+	DeviceGuard::~DeviceGuard()
+	{
+		if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+		g_devState[dev].mtx.unlock();
+	}
+
 	Engine::Engine(const void* imageBytes, size_t size)
 	{
+		ck(cudaGetDevice(&device), "cudaGetDevice");
+		DeviceGuard g{ device };
 		model.load(imageBytes, size);
-		ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
-		ck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
-		for (auto& e : ev) ck(cudaEventCreate(&e), "cudaEventCreate");
+		// (the constant-memory model view is uploaded by the first launch: uploading here would overwrite the view of another
+		// engine on this device without it noticing)
+		for (auto& sl : slot_)
+		{
+			ck(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+			for (auto& e : sl.ev) ck(cudaEventCreate(&e), "cudaEventCreate");
+		}
+		stream = slot_[0].stream;
 	}
 
 	Engine::~Engine()
 	{
-		freeScratch(main_); freeScratch(retry_);
-		if (hPinText) cudaFreeHost(hPinText);
-		if (hPinOff) cudaFreeHost(hPinOff);
-		if (hPinOut) cudaFreeHost(hPinOut);
-		for (auto& e : ev) cudaEventDestroy(e);
-		if (stream) cudaStreamDestroy(stream);
+		DeviceGuard g{ device };
+		if (g_devState[g.dev].owner == &model) g_devState[g.dev].owner = nullptr;
+		for (auto& sl : slot_)
+		{
+			freeScratch(sl.sc);
+			if (sl.hPinText) cudaFreeHost(sl.hPinText);
+			if (sl.hPinOff) cudaFreeHost(sl.hPinOff);
+			if (sl.hPinOut) cudaFreeHost(sl.hPinOut);
+			for (auto& e : sl.ev) if (e) cudaEventDestroy(e);
+			if (sl.stream) cudaStreamDestroy(sl.stream);
+		}
+		freeScratch(retry_);
 	}
 
 	void Engine::freeScratch(Scratch& sc)
@@ -109,8 +144,9 @@ namespace kb
 
 	TypoDev::~TypoDev() { if (dBlob) cudaFree(dBlob); }
 
-	void Engine::ensureTypoScratch(Scratch& sc, uint32_t gpu, uint32_t spu)
+	void Engine::ensureTypoScratch(Scratch& sc, uint32_t gpu0, uint32_t spu0, uint32_t mul)
 	{
+		const uint32_t gpu = gpu0 * mul, spu = spu0 * mul;
 		if (sc.typoCapUnits >= sc.capUnits && sc.typoGraphPerUnit == gpu && sc.typoStatesPerUnit == spu) return;
 		for (void* p : sc.typoBufs) cudaFree(p);
 		sc.typoBufs.clear();
@@ -125,7 +161,7 @@ namespace kb
 		sc.typoCapUnits = sc.capUnits; sc.typoGraphPerUnit = gpu; sc.typoStatesPerUnit = spu;
 	}
 
-	void Engine::ensureScratch(Scratch& sc, size_t U, size_t B, uint32_t ppu, uint32_t pc, uint32_t npu)
+	void Engine::ensureScratch(Scratch& sc, cudaStream_t st, size_t U, size_t B, uint32_t ppu, uint32_t pc, uint32_t npu)
 	{
 		const size_t T = (U - 4 * B) / 2 + 1;
 		if (U <= sc.capUnits && B <= sc.capSent && ppu == sc.pathsPerUnit && pc == sc.pathsConst && npu == sc.nodesPerUnit && T <= sc.capText) return;
@@ -167,24 +203,23 @@ namespace kb
 		sc.dText = (uint16_t*)alloc(capT * 2 + 64);
 		sc.dOff = (uint32_t*)alloc((capB + 1) * 4);
 		size_t tb = 0;
-		cub::DeviceScan::ExclusiveSum(nullptr, tb, vv.n_tokens, sc.tokOff, (int)(capB + 1), stream);
+		cub::DeviceScan::ExclusiveSum(nullptr, tb, vv.n_tokens, sc.tokOff, (int)(capB + 1), st);
 		sc.cubTempBytes = tb; sc.cubTemp = alloc(tb);
 		sc.lenKeys = (uint32_t*)alloc(capB * 4); sc.lenKeysOut = (uint32_t*)alloc(capB * 4); sc.idxIn = (uint32_t*)alloc(capB * 4); sc.order = (uint32_t*)alloc(capB * 4);
 		size_t sb = 0;
-		cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.order, (int)capB, 0, 32, stream);
+		cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.order, (int)capB, 0, 32, st);
 		sc.sortTempBytes = sb; sc.sortTemp = alloc(sb);
 		sc.capUnits = capU; sc.capSent = capB; sc.capText = capT; sc.pathsPerUnit = ppu; sc.pathsConst = pc; sc.nodesPerUnit = npu;
 	}
 
-	void Engine::bind(Scratch& sc, const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions)
+	void Engine::bind(Scratch& sc, const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions, uint32_t capMul)
 	{
 		sc.bv.n_sent = n; sc.bv.text = dText; sc.bv.text_off = dOffsets; sc.bv.match_options = matchOptions;
 		sc.bv.typo = TypoView{};
 		if (typo_)
 		{
-			// the retry arena carries 4 x the graph / state capacity, like its node capacity
-			const uint32_t mul = &sc == &retry_ ? 4 : 1;
-			ensureTypoScratch(sc, DEFAULT_TYPO_GRAPH_PER_UNIT * mul, DEFAULT_TYPO_STATES_PER_UNIT * mul);
+			// a retry arena carries capMul x the graph / state capacity, like its node capacity
+			ensureTypoScratch(sc, DEFAULT_TYPO_GRAPH_PER_UNIT, DEFAULT_TYPO_STATES_PER_UNIT, capMul);
 			TypoView v = sc.typoScratch;
 			v.nodes = typo_->view.nodes; v.keys = typo_->view.keys; v.diffs = typo_->view.diffs; v.pats = typo_->view.pats; v.repls = typo_->view.repls; v.pool = typo_->view.pool;
 			v.continual_threshold = typo_->view.continual_threshold; v.threshold = typoThreshold_;
@@ -192,34 +227,38 @@ namespace kb
 		}
 	}
 
-	static const Model* g_constantsOwner = nullptr;     // the constant-memory model view belongs to one engine at a time
-
-	void Engine::launchAll(Scratch& sc, uint32_t n)
+	// caller holds the device lock and no kernel of another engine is in flight on this device (every public entry point
+	// synchronises its streams before it releases the lock)
+	void Engine::uploadConstants()
 	{
-		if (g_constantsOwner != &model)
-		{
-			ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
-			g_constantsOwner = &model;
-		}
-		ck(cudaEventRecord(ev[1], stream), "event");
+		DevState& ds = g_devState[device < 0 || device >= 64 ? 0 : device];
+		if (ds.owner == &model) return;
+		ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
+		ds.owner = &model;
+	}
+
+	void Engine::launchAll(Scratch& sc, cudaStream_t st, cudaEvent_t* ev, uint32_t n)
+	{
+		uploadConstants();
+		ck(cudaEventRecord(ev[1], st), "event");
 		// longest-processing-time-first launch order (sentence cost grows with its length)
-		length_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, sc.bv.text_off, sc.lenKeys, sc.idxIn);
+		length_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, sc.bv.text_off, sc.lenKeys, sc.idxIn);
 		ck(cudaGetLastError(), "length_kernel launch");
 		size_t sb = sc.sortTempBytes;
-		ck(cub::DeviceRadixSort::SortPairsDescending(sc.sortTemp, sb, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.order, (int)n, 0, 32, stream), "cub sort");
+		ck(cub::DeviceRadixSort::SortPairsDescending(sc.sortTemp, sb, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.order, (int)n, 0, 32, st), "cub sort");
 		sc.bv.order = sc.order;
-		ck(launch_lattice(model.dev, sc.bv, stream), "lattice_kernel launch");
-		ck(cudaEventRecord(ev[2], stream), "event");
-		ck(model.dev.model_type == 4 ? launch_viterbi_cong(model.dev, sc.bv, sc.vv, stream) : launch_viterbi(model.dev, sc.bv, sc.vv, stream), "viterbi_kernel launch");
-		ck(cudaEventRecord(ev[3], stream), "event");
-		ck(launch_emit(model.dev, sc.bv, sc.vv, stream), "emit_kernel launch");
-		ck(cudaMemsetAsync(sc.vv.n_tokens + n, 0, 4, stream), "memset");
+		ck(launch_lattice(model.dev, sc.bv, st), "lattice_kernel launch");
+		ck(cudaEventRecord(ev[2], st), "event");
+		ck(model.dev.model_type == 4 ? launch_viterbi_cong(model.dev, sc.bv, sc.vv, st) : launch_viterbi(model.dev, sc.bv, sc.vv, st), "viterbi_kernel launch");
+		ck(cudaEventRecord(ev[3], st), "event");
+		ck(launch_emit(model.dev, sc.bv, sc.vv, st), "emit_kernel launch");
+		ck(cudaMemsetAsync(sc.vv.n_tokens + n, 0, 4, st), "memset");
 		size_t tb = sc.cubTempBytes;
-		ck(cub::DeviceScan::ExclusiveSum(sc.cubTemp, tb, sc.vv.n_tokens, sc.tokOff, (int)(n + 1), stream), "cub scan");
+		ck(cub::DeviceScan::ExclusiveSum(sc.cubTemp, tb, sc.vv.n_tokens, sc.tokOff, (int)(n + 1), st), "cub scan");
 		const uint32_t threads = 256, blocks = (n * 32 + threads - 1) / threads;
-		pack_kernel<<<blocks, threads, 0, stream>>>(n, sc.bv.text_off, sc.vv.n_tokens, sc.tokOff, sc.vv.tokens, sc.packed);
+		pack_kernel<<<blocks, threads, 0, st>>>(n, sc.bv.text_off, sc.vv.n_tokens, sc.tokOff, sc.vv.tokens, sc.packed);
 		ck(cudaGetLastError(), "pack_kernel launch");
-		ck(cudaEventRecord(ev[4], stream), "event");
+		ck(cudaEventRecord(ev[4], st), "event");
 	}
 
 	static void growPinned(void** p, size_t* cap, size_t bytes)
@@ -231,206 +270,321 @@ namespace kb
 		*cap = nb;
 	}
 
-	// one pass: H2D text + offsets, the four kernels, D2H of offsets / scores / status and of exactly the packed tokens
-	void Engine::runHostPass(Scratch& sc, const uint16_t* ptext, const uint32_t* poff, uint32_t pn, uint32_t matchOptions, uint32_t ppu, uint32_t pc, uint32_t npu, PassResult& r, BatchOutput& out)
+	void Engine::checkDebug(Scratch& sc)
 	{
-		const size_t pT = poff[pn];
+		uint32_t dbg[16];
+		ck(cudaMemcpy(dbg, sc.bv.debug, sizeof(dbg), cudaMemcpyDeviceToHost), "D2H debug");
+		if (!dbg[0]) ck(cudaMemcpy(dbg, model.dev.debug, sizeof(dbg), cudaMemcpyDeviceToHost), "D2H debug");
+		if (dbg[0])
+		{
+			std::string msg = "internal consistency failure in viterbi_kernel:";
+			for (int i = 1; i < 16; ++i) msg += " " + std::to_string(dbg[i]);
+			throw std::runtime_error(msg);
+		}
+	}
+
+	// Layout of a slot's pinned output buffer: [tokOff n+1][scores n][status n][debug flag 2 words][tokens ...].  Everything is
+	// enqueued behind the kernels in ONE go: the head arrays and an ESTIMATE of the packed tokens (3/4 token per raw UTF-16 unit
+	// + 16 per sentence; web text needs ~0.55), so a pass normally needs a single stream synchronisation.  finishPass fetches
+	// the rest when the estimate was too small.
+	static size_t tokenEstimate(size_t rawUnits, uint32_t n) { return rawUnits * 3 / 4 + 16 * (size_t)n + 64; }
+
+	void Engine::submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t pn, uint32_t matchOptions)
+	{
+		const size_t t0 = off[i0], pT = off[i0 + pn] - t0;
 		const size_t U = 2 * pT + 4 * (size_t)pn;
-		ensureScratch(sc, U, pn, ppu, pc, npu);
-		growPinned((void**)&hPinText, &pinTextCap, pT * 2 + 64);
-		growPinned((void**)&hPinOff, &pinOffCap, ((size_t)pn + 1) * 4);
-		std::memcpy(hPinText, ptext, pT * 2);
-		std::memcpy(hPinOff, poff, ((size_t)pn + 1) * 4);
-		ck(cudaEventRecord(ev[0], stream), "event");
-		ck(cudaMemcpyAsync(sc.dText, hPinText, pT * 2, cudaMemcpyHostToDevice, stream), "H2D text");
-		ck(cudaMemcpyAsync(sc.dOff, hPinOff, ((size_t)pn + 1) * 4, cudaMemcpyHostToDevice, stream), "H2D offsets");
-		bind(sc, sc.dText, sc.dOff, pn, matchOptions);
-		launchAll(sc, pn);
-		const size_t headBytes = ((size_t)pn + 1) * 4 + (size_t)pn * 4 * 2;
-		growPinned(&hPinOut, &pinOutCap, std::max(headBytes, (size_t)U * sizeof(DToken) / 4));
-		uint32_t* hTokOff = (uint32_t*)hPinOut; float* hScore = (float*)(hTokOff + pn + 1); uint32_t* hStatus = (uint32_t*)(hScore + pn);
-		ck(cudaMemcpyAsync(hTokOff, sc.tokOff, ((size_t)pn + 1) * 4, cudaMemcpyDeviceToHost, stream), "D2H offsets");
-		ck(cudaMemcpyAsync(hScore, sc.vv.score, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H scores");
-		ck(cudaMemcpyAsync(hStatus, sc.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, stream), "D2H status");
-		ck(cudaStreamSynchronize(stream), "sync (a kernel fault surfaces here)");
-		{
-			uint32_t dbg[16];
-			ck(cudaMemcpy(dbg, sc.bv.debug, sizeof(dbg), cudaMemcpyDeviceToHost), "D2H debug");
-			if (!dbg[0]) ck(cudaMemcpy(dbg, model.dev.debug, sizeof(dbg), cudaMemcpyDeviceToHost), "D2H debug");
-			if (dbg[0])
-			{
-				std::string msg = "internal consistency failure in viterbi_kernel:";
-				for (int i = 1; i < 16; ++i) msg += " " + std::to_string(dbg[i]);
-				throw std::runtime_error(msg);
-			}
-		}
-		const uint32_t total = hTokOff[pn];
-		r.tokOff.assign(hTokOff, hTokOff + pn + 1);
-		r.scores.assign(hScore, hScore + pn);
-		r.status.assign(hStatus, hStatus + pn);
-		r.toks.resize(total);
-		if (total)
-		{
-			growPinned(&hPinOut, &pinOutCap, (size_t)total * sizeof(DToken));
-			ck(cudaMemcpyAsync(hPinOut, sc.packed, (size_t)total * sizeof(DToken), cudaMemcpyDeviceToHost, stream), "D2H tokens");
-		}
-		ck(cudaEventRecord(ev[5], stream), "event");
-		ck(cudaStreamSynchronize(stream), "sync");
-		if (total) std::memcpy(r.toks.data(), hPinOut, (size_t)total * sizeof(DToken));
-		float ms;
-		cudaEventElapsedTime(&ms, ev[0], ev[1]); out.msH2D += ms;
-		cudaEventElapsedTime(&ms, ev[1], ev[2]); out.msLattice += ms;
-		cudaEventElapsedTime(&ms, ev[2], ev[3]); out.msViterbi += ms;
-		cudaEventElapsedTime(&ms, ev[3], ev[4]); out.msPack += ms;
-		cudaEventElapsedTime(&ms, ev[4], ev[5]); out.msD2H += ms;
-		cudaEventElapsedTime(&ms, ev[0], ev[5]); out.msTotal += ms;
+		ensureScratch(s.sc, s.stream, U, pn, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
+		growPinned((void**)&s.hPinText, &s.pinTextCap, pT * 2 + 64);
+		growPinned((void**)&s.hPinOff, &s.pinOffCap, ((size_t)pn + 1) * 4);
+		std::memcpy(s.hPinText, text + t0, pT * 2);
+		for (uint32_t k = 0; k <= pn; ++k) s.hPinOff[k] = off[i0 + k] - (uint32_t)t0;
+		ck(cudaEventRecord(s.ev[0], s.stream), "event");
+		ck(cudaMemcpyAsync(s.sc.dText, s.hPinText, pT * 2, cudaMemcpyHostToDevice, s.stream), "H2D text");
+		ck(cudaMemcpyAsync(s.sc.dOff, s.hPinOff, ((size_t)pn + 1) * 4, cudaMemcpyHostToDevice, s.stream), "H2D offsets");
+		bind(s.sc, s.sc.dText, s.sc.dOff, pn, matchOptions, 1);
+		launchAll(s.sc, s.stream, s.ev, pn);
+		const size_t headWords = ((size_t)pn + 1) + 2 * (size_t)pn + 2;
+		const size_t est = std::min(tokenEstimate(pT, pn), (size_t)U);
+		growPinned(&s.hPinOut, &s.pinOutCap, headWords * 4 + 16 + est * sizeof(DToken));
+		uint32_t* hTokOff = (uint32_t*)s.hPinOut; float* hScore = (float*)(hTokOff + pn + 1); uint32_t* hStatus = (uint32_t*)(hScore + pn); uint32_t* hDbg = hStatus + pn;
+		ck(cudaMemcpyAsync(hTokOff, s.sc.tokOff, ((size_t)pn + 1) * 4, cudaMemcpyDeviceToHost, s.stream), "D2H offsets");
+		ck(cudaMemcpyAsync(hScore, s.sc.vv.score, (size_t)pn * 4, cudaMemcpyDeviceToHost, s.stream), "D2H scores");
+		ck(cudaMemcpyAsync(hStatus, s.sc.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, s.stream), "D2H status");
+		ck(cudaMemcpyAsync(hDbg, s.sc.bv.debug, 4, cudaMemcpyDeviceToHost, s.stream), "D2H debug");
+		ck(cudaMemcpyAsync(hDbg + 1, model.dev.debug, 4, cudaMemcpyDeviceToHost, s.stream), "D2H debug");
+		char* hTok = (char*)s.hPinOut + ((headWords * 4 + 15) & ~(size_t)15);
+		ck(cudaMemcpyAsync(hTok, s.sc.packed, est * sizeof(DToken), cudaMemcpyDeviceToHost, s.stream), "D2H tokens");
+		ck(cudaEventRecord(s.ev[5], s.stream), "event");
+		s.busy = true; s.i0 = i0; s.n = pn; s.rawUnits = pT; s.units = U; s.tokCopied = est;
 		last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4;
-		last.d2hBytes += headBytes + (size_t)total * sizeof(DToken);
 		last.kernelLaunches += 5;
 	}
 
-	void Engine::analyzeOne(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out)
+	// waits for the slot's pass, appends its sentences (they are the next ones in input order) to `out`
+	void Engine::finishPass(Slot& s, BatchOutput& out, std::vector<uint32_t>& failed)
 	{
-		out = BatchOutput{};
-		out.tokOff.assign(n + 1, 0);
-		out.scores.assign(n, 0.f);
-		out.status.assign(n, 0);
-		if (n == 0) return;
-		const size_t T = offsets[n];
-		if (T >= (1ull << 31)) throw std::runtime_error("batch too large (>= 2^31 UTF-16 units); split it");
-
-		PassResult r0;
-		runHostPass(main_, text, offsets, n, matchOptions, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT, r0, out);
-		std::vector<uint32_t> failed;
-		for (uint32_t i = 0; i < n; ++i) if (r0.status[i]) failed.push_back(i);
-		last.retried += failed.size();
-		if (failed.empty())
+		if (!s.busy) return;
+		ck(cudaStreamSynchronize(s.stream), "sync (a kernel fault surfaces here)");
+		s.busy = false;
+		const uint32_t pn = s.n;
+		const size_t headWords = ((size_t)pn + 1) + 2 * (size_t)pn + 2;
+		const uint32_t* hTokOff = (const uint32_t*)s.hPinOut; const float* hScore = (const float*)(hTokOff + pn + 1); const uint32_t* hStatus = (const uint32_t*)(hScore + pn); const uint32_t* hDbg = hStatus + pn;
+		if (hDbg[0] || hDbg[1]) checkDebug(s.sc);
+		const uint32_t total = hTokOff[pn];
+		const char* hTok = (const char*)s.hPinOut + ((headWords * 4 + 15) & ~(size_t)15);
+		const size_t base = out.tokens.size();
+		out.tokens.resize(base + total);
+		const size_t first = std::min<size_t>(total, s.tokCopied);
+		if (first) std::memcpy(out.tokens.data() + base, hTok, first * sizeof(DToken));
+		if (total > first)
 		{
-			out.tokens = std::move(r0.toks); out.tokOff = std::move(r0.tokOff); out.scores = std::move(r0.scores); out.status = std::move(r0.status);
+			ck(cudaMemcpyAsync(out.tokens.data() + base + first, s.sc.packed + first, (size_t)(total - first) * sizeof(DToken), cudaMemcpyDeviceToHost, s.stream), "D2H tokens (rest)");
+			ck(cudaStreamSynchronize(s.stream), "sync");
 		}
-		else
+		for (uint32_t k = 0; k < pn; ++k)
 		{
-			// second pass for the overflowed sentences only: 16 x path capacity, 4 x node capacity, in its own arena
-			std::vector<uint16_t> subText; std::vector<uint32_t> subOff{ 0 };
-			for (uint32_t id : failed)
-			{
-				subText.insert(subText.end(), text + offsets[id], text + offsets[id + 1]);
-				subOff.push_back((uint32_t)subText.size());
-			}
-			PassResult r1;
-			runHostPass(retry_, subText.data(), subOff.data(), (uint32_t)failed.size(), matchOptions, DEFAULT_PATHS_PER_UNIT * 8, DEFAULT_PATHS_CONST * 8, KB_DEFAULT_NODES_PER_UNIT * 4, r1, out);
-			out.tokens.reserve(r0.toks.size() + r1.toks.size());
-			out.tokOff.assign(n + 1, 0);
-			out.scores = std::move(r0.scores); out.status = std::move(r0.status);
-			size_t fi = 0;
-			for (uint32_t i = 0; i < n; ++i)
-			{
-				out.tokOff[i] = (uint32_t)out.tokens.size();
-				if (fi < failed.size() && failed[fi] == i)
-				{
-					out.tokens.insert(out.tokens.end(), r1.toks.begin() + r1.tokOff[fi], r1.toks.begin() + r1.tokOff[fi + 1]);
-					out.scores[i] = r1.scores[fi]; out.status[i] = r1.status[fi];
-					++fi;
-				}
-				else out.tokens.insert(out.tokens.end(), r0.toks.begin() + r0.tokOff[i], r0.toks.begin() + r0.tokOff[i + 1]);
-			}
-			out.tokOff[n] = (uint32_t)out.tokens.size();
+			out.tokOff.push_back((uint32_t)(base + hTokOff[k + 1]));
+			out.scores.push_back(hScore[k]); out.status.push_back(hStatus[k]);
+			if (hStatus[k]) failed.push_back(s.i0 + k);
 		}
-		for (uint32_t i = 0; i < n; ++i)
-		{
-			if (out.status[i])
-			{
-				throw std::runtime_error("sentence " + std::to_string(i) + " exceeded the device scratch capacity (status " + std::to_string(out.status[i]) + ")");
-			}
-		}
-		last.nSentences = n; last.rawUnits = T; last.tokens = out.tokens.size();
-		last.msLattice = out.msLattice; last.msViterbi = out.msViterbi; last.msPack = out.msPack;
+		float ms;
+		cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); out.msH2D += ms;
+		cudaEventElapsedTime(&ms, s.ev[1], s.ev[2]); out.msLattice += ms;
+		cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); out.msViterbi += ms;
+		cudaEventElapsedTime(&ms, s.ev[3], s.ev[4]); out.msPack += ms;
+		cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]); out.msD2H += ms;
+		cudaEventElapsedTime(&ms, s.ev[0], s.ev[5]); out.msTotal += ms;
+		last.d2hBytes += headWords * 4 + (size_t)std::max<size_t>(total, s.tokCopied) * sizeof(DToken);
 	}
 
-	// Public entry: batches of any size.  The scratch arena is sized per pass, so a large batch (65536 / 1 M sentences)
-	// is cut into passes of at most MAX_UNITS_PER_PASS normalised units / MAX_SENT_PER_PASS sentences, run back to back.
+	// Sentences that overflowed the arithmetic capacity of a main arena are re-run in the retry arena with 8 x the path and 4 x the
+	// node capacity, then (what still fails) with 64 x / 16 x; every round is cut into sub-passes that fit a memory budget.  What
+	// fails even then keeps its status: the caller reports it per sentence instead of failing the whole batch.
+	void Engine::runRetry(const uint16_t* text, const uint32_t* offsets, const std::vector<uint32_t>& failedIn, uint32_t matchOptions, BatchOutput& out,
+		std::vector<PassResult>& results, std::vector<uint32_t>& resultOf)
+	{
+		std::vector<uint32_t> failed = failedIn;
+		static const uint32_t pathMul[2] = { 8, 64 }, nodeMul[2] = { 4, 16 };
+		const size_t budget = (size_t)24 << 30;      // bytes of path pool per sub-pass
+		Slot& s = slot_[0];
+		for (int round = 0; round < 2 && !failed.empty(); ++round)
+		{
+			const uint32_t ppu = DEFAULT_PATHS_PER_UNIT * pathMul[round], pc = DEFAULT_PATHS_CONST * pathMul[round], npu = KB_DEFAULT_NODES_PER_UNIT * nodeMul[round];
+			std::vector<uint32_t> still;
+			size_t f0 = 0;
+			while (f0 < failed.size())
+			{
+				size_t f1 = f0, units = 0;
+				while (f1 < failed.size())
+				{
+					const size_t u = 2 * (size_t)(offsets[failed[f1] + 1] - offsets[failed[f1]]) + 4;
+					if (f1 > f0 && ((units + u) * ppu + (f1 - f0 + 1) * (size_t)pc) * sizeof(DPath) > budget) break;
+					units += u; ++f1;
+				}
+				std::vector<uint16_t> subText; std::vector<uint32_t> subOff{ 0 };
+				for (size_t k = f0; k < f1; ++k)
+				{
+					const uint32_t id = failed[k];
+					subText.insert(subText.end(), text + offsets[id], text + offsets[id + 1]);
+					subOff.push_back((uint32_t)subText.size());
+				}
+				const uint32_t pn = (uint32_t)(f1 - f0);
+				const size_t pT = subText.size(), U = 2 * pT + 4 * (size_t)pn;
+				ensureScratch(retry_, s.stream, U, pn, ppu, pc, npu);
+				ck(cudaMemcpyAsync(retry_.dText, subText.data(), pT * 2, cudaMemcpyHostToDevice, s.stream), "H2D text");
+				ck(cudaMemcpyAsync(retry_.dOff, subOff.data(), ((size_t)pn + 1) * 4, cudaMemcpyHostToDevice, s.stream), "H2D offsets");
+				bind(retry_, retry_.dText, retry_.dOff, pn, matchOptions, nodeMul[round]);
+				launchAll(retry_, s.stream, s.ev, pn);
+				PassResult r;
+				r.tokOff.resize(pn + 1); r.scores.resize(pn); r.status.resize(pn);
+				ck(cudaMemcpyAsync(r.tokOff.data(), retry_.tokOff, ((size_t)pn + 1) * 4, cudaMemcpyDeviceToHost, s.stream), "D2H offsets");
+				ck(cudaMemcpyAsync(r.scores.data(), retry_.vv.score, (size_t)pn * 4, cudaMemcpyDeviceToHost, s.stream), "D2H scores");
+				ck(cudaMemcpyAsync(r.status.data(), retry_.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, s.stream), "D2H status");
+				ck(cudaStreamSynchronize(s.stream), "sync (retry pass)");
+				checkDebug(retry_);
+				r.toks.resize(r.tokOff[pn]);
+				if (!r.toks.empty()) ck(cudaMemcpy(r.toks.data(), retry_.packed, r.toks.size() * sizeof(DToken), cudaMemcpyDeviceToHost), "D2H tokens");
+				float ms = 0; cudaEventElapsedTime(&ms, s.ev[1], s.ev[4]); out.msTotal += ms;
+				last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4; last.d2hBytes += ((size_t)pn * 3 + 1) * 4 + r.toks.size() * sizeof(DToken); last.kernelLaunches += 5;
+				const uint32_t ri = (uint32_t)results.size();
+				for (uint32_t k = 0; k < pn; ++k)
+				{
+					const uint32_t id = failed[f0 + k];
+					out.status[id] = r.status[k];
+					if (r.status[k]) still.push_back(id);
+					else resultOf[id] = (ri << 16) | k;          // sub-passes hold < 65536 sentences (MAX_SENT_PER_PASS)
+				}
+				results.push_back(std::move(r));
+				f0 = f1;
+			}
+			failed.swap(still);
+		}
+	}
+
+	// Public entry: batches of any size.  The scratch arenas are sized per pass, so a large batch (65536 / 1 M sentences)
+	// is cut into passes of at most MAX_UNITS_PER_PASS normalised units / MAX_SENT_PER_PASS sentences.
 	static constexpr size_t MAX_UNITS_PER_PASS = 2u << 20, MAX_SENT_PER_PASS = 16384;
+	static size_t passSentLimit()
+	{
+		// KIWI_B200_PASS_SENT: sentences per pass (experiments with the overlap of small passes); default 16384
+		static const size_t v = [] { const char* e = std::getenv("KIWI_B200_PASS_SENT"); const long x = e ? std::atol(e) : 0; return x > 0 ? std::min<size_t>((size_t)x, MAX_SENT_PER_PASS) : MAX_SENT_PER_PASS; }();
+		return v;
+	}
 
 	void Engine::analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out)
 	{
+		DeviceGuard g{ device };
 		last = Stats{};
-		if (n && offsets[0] != 0) throw std::runtime_error("offsets[0] must be 0");
-		for (uint32_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) throw std::runtime_error("offsets must be non-decreasing");
-		const size_t totalUnits = n ? 2 * (size_t)offsets[n] + 4 * (size_t)n : 0;
-		if (totalUnits <= MAX_UNITS_PER_PASS && n <= MAX_SENT_PER_PASS) { analyzeOne(text, offsets, n, matchOptions, out); return; }
 		out = BatchOutput{};
 		out.tokOff.assign(1, 0);
-		uint32_t i0 = 0;
-		std::vector<uint32_t> subOff;
-		while (i0 < n)
+		if (n == 0) return;
+		if (offsets[0] != 0) throw std::runtime_error("offsets[0] must be 0");
+		for (uint32_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) throw std::runtime_error("offsets must be non-decreasing");
+		out.tokOff.reserve((size_t)n + 1); out.scores.reserve(n); out.status.reserve(n);
+		out.tokens.reserve(tokenEstimate(offsets[n], n) * 3 / 4);
+		std::vector<uint32_t> failed;
+		const size_t sentLimit = passSentLimit();
+		uint32_t i0 = 0, k = 0;
+		try
 		{
-			uint32_t i1 = i0; size_t units = 0;
-			while (i1 < n && i1 - i0 < MAX_SENT_PER_PASS)
+			while (i0 < n)
 			{
-				const size_t u = 2 * (size_t)(offsets[i1 + 1] - offsets[i1]) + 4;
-				if (i1 > i0 && units + u > MAX_UNITS_PER_PASS) break;
-				units += u; ++i1;
+				uint32_t i1 = i0; size_t units = 0;
+				while (i1 < n && i1 - i0 < sentLimit)
+				{
+					const size_t u = 2 * (size_t)(offsets[i1 + 1] - offsets[i1]) + 4;
+					if (i1 > i0 && units + u > MAX_UNITS_PER_PASS) break;
+					units += u; ++i1;
+				}
+				Slot& s = slot_[k & 1];
+				// results are appended in input order: the slot's previous pass (k - 2) is older than the other slot's (k - 1)
+				finishPass(s, out, failed);
+				submitPass(s, text, offsets, i0, i1 - i0, matchOptions);
+				i0 = i1; ++k;
 			}
-			subOff.resize(i1 - i0 + 1);
-			for (uint32_t k = 0; k <= i1 - i0; ++k) subOff[k] = offsets[i0 + k] - offsets[i0];
-			BatchOutput part;
-			analyzeOne(text + offsets[i0], subOff.data(), i1 - i0, matchOptions, part);
-			const uint32_t base = (uint32_t)out.tokens.size();
-			out.tokens.insert(out.tokens.end(), part.tokens.begin(), part.tokens.end());
-			for (uint32_t k = 1; k <= i1 - i0; ++k) out.tokOff.push_back(base + part.tokOff[k]);
-			out.scores.insert(out.scores.end(), part.scores.begin(), part.scores.end());
-			out.status.insert(out.status.end(), part.status.begin(), part.status.end());
-			out.msH2D += part.msH2D; out.msLattice += part.msLattice; out.msViterbi += part.msViterbi; out.msPack += part.msPack; out.msD2H += part.msD2H; out.msTotal += part.msTotal;
-			i0 = i1;
+			finishPass(slot_[k & 1], out, failed);
+			finishPass(slot_[(k + 1) & 1], out, failed);
+		}
+		catch (...)
+		{
+			for (auto& sl : slot_) { if (sl.busy) { cudaStreamSynchronize(sl.stream); sl.busy = false; } }
+			throw;
+		}
+		last.retried += failed.size();
+		if (!failed.empty())
+		{
+			std::vector<PassResult> results; std::vector<uint32_t> resultOf(n, 0xFFFFFFFFu);
+			runRetry(text, offsets, failed, matchOptions, out, results, resultOf);
+			// splice the retried sentences into the token stream (rare path: rebuild)
+			std::vector<DToken> toks; std::vector<uint32_t> tokOff(1, 0);
+			toks.reserve(out.tokens.size());
+			for (uint32_t i = 0; i < n; ++i)
+			{
+				if (resultOf[i] != 0xFFFFFFFFu)
+				{
+					const PassResult& r = results[resultOf[i] >> 16]; const uint32_t kk = resultOf[i] & 0xFFFF;
+					toks.insert(toks.end(), r.toks.begin() + r.tokOff[kk], r.toks.begin() + r.tokOff[kk + 1]);
+					out.scores[i] = r.scores[kk];
+				}
+				else if (!out.status[i]) toks.insert(toks.end(), out.tokens.begin() + out.tokOff[i], out.tokens.begin() + out.tokOff[i + 1]);
+				else out.scores[i] = 0.f;      // failed even in the escalated arena: no tokens, status kept
+				tokOff.push_back((uint32_t)toks.size());
+			}
+			out.tokens.swap(toks); out.tokOff.swap(tokOff);
 		}
 		last.nSentences = n; last.rawUnits = offsets[n]; last.tokens = out.tokens.size();
 		last.msLattice = out.msLattice; last.msViterbi = out.msViterbi; last.msPack = out.msPack;
 	}
 
+	__global__ void rebase_kernel(uint32_t n, const uint32_t* __restrict__ off, uint32_t i0, uint32_t* __restrict__ out)
+	{
+		const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+		if (k <= n) out[k] = off[i0 + k] - off[i0];
+	}
+
+	// Device-resident inputs (bench.py's `value`): passes run back to back on ONE stream so that every kernel's CUDA-event time is
+	// its own; sentences that overflow the arena are re-run through the host retry path (their text comes back from the device).
 	float Engine::analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens)
 	{
-		const size_t U = 2 * (size_t)totalUnits + 4 * (size_t)n;
-		if (U > 4 * MAX_UNITS_PER_PASS) throw std::runtime_error("kiwi_b200_analyze_device: batch too large for one device pass; split it (kiwi_b200_analyze_batch splits automatically)");
-		Scratch& sc = main_;
-		ensureScratch(sc, U, n, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
-		bind(sc, dText, dOffsets, n, matchOptions);
-		launchAll(sc, n);
-		growPinned(&hPinOut, &pinOutCap, (size_t)n * 4 + 64);
-		uint32_t* hStatus = (uint32_t*)hPinOut;
-		uint32_t total = 0;
-		ck(cudaMemcpyAsync(&total, sc.tokOff + n, 4, cudaMemcpyDeviceToHost, stream), "D2H total");
-		ck(cudaMemcpyAsync(hStatus, sc.bv.status, (size_t)n * 4, cudaMemcpyDeviceToHost, stream), "D2H status");
-		ck(cudaStreamSynchronize(stream), "sync (a kernel fault surfaces here)");
-		float ms = 0, a = 0;
-		cudaEventElapsedTime(&ms, ev[1], ev[4]);
-		cudaEventElapsedTime(&a, ev[1], ev[2]); last.msLattice = a;
-		cudaEventElapsedTime(&a, ev[2], ev[3]); last.msViterbi = a;
-		cudaEventElapsedTime(&a, ev[3], ev[4]); last.msPack = a;
-		last.nSentences = n; last.rawUnits = totalUnits; last.tokens = total; last.kernelLaunches = 5; last.h2dBytes = 0; last.d2hBytes = 4 + (size_t)n * 4; last.retried = 0;
-		// overflowed sentences (rare) are re-run through the larger arena; their text comes back from the device
+		DeviceGuard g{ device };
+		last = Stats{};
+		if (nTokens) *nTokens = 0;
+		if (n == 0) return 0.f;
+		Slot& s = slot_[0];
+		std::vector<uint32_t> off;
+		const size_t Uall = 2 * (size_t)totalUnits + 4 * (size_t)n;
+		const bool single = Uall <= 4 * MAX_UNITS_PER_PASS && n <= 4 * MAX_SENT_PER_PASS;      // (one launch set keeps the longest-first order over the whole batch)
+		if (!single)
+		{
+			off.resize((size_t)n + 1);
+			ck(cudaMemcpy(off.data(), dOffsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost), "D2H offsets");
+		}
+		float msTotal = 0; uint64_t total = 0;
 		std::vector<uint32_t> failed;
-		for (uint32_t i = 0; i < n; ++i) if (hStatus[i]) failed.push_back(i);
+		uint32_t i0 = 0;
+		while (i0 < n)
+		{
+			uint32_t i1 = n; size_t pT = totalUnits;
+			if (!single)
+			{
+				i1 = i0; size_t units = 0;
+				while (i1 < n && i1 - i0 < 4 * MAX_SENT_PER_PASS)
+				{
+					const size_t u = 2 * (size_t)(off[i1 + 1] - off[i1]) + 4;
+					if (i1 > i0 && units + u > 4 * MAX_UNITS_PER_PASS) break;
+					units += u; ++i1;
+				}
+				pT = off[i1] - off[i0];
+			}
+			const uint32_t pn = i1 - i0;
+			const size_t U = 2 * pT + 4 * (size_t)pn;
+			ensureScratch(s.sc, s.stream, U, pn, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
+			const uint16_t* pText = dText; const uint32_t* pOff = dOffsets;
+			if (!single)
+			{
+				rebase_kernel<<<(pn + 256) / 256, 256, 0, s.stream>>>(pn, dOffsets, i0, s.sc.dOff);
+				ck(cudaGetLastError(), "rebase_kernel launch");
+				pText = dText + off[i0]; pOff = s.sc.dOff;
+			}
+			bind(s.sc, pText, pOff, pn, matchOptions, 1);
+			launchAll(s.sc, s.stream, s.ev, pn);
+			growPinned(&s.hPinOut, &s.pinOutCap, (size_t)pn * 4 + 64);
+			uint32_t* hStatus = (uint32_t*)s.hPinOut; uint32_t* hTotal = hStatus + pn;
+			ck(cudaMemcpyAsync(hTotal, s.sc.tokOff + pn, 4, cudaMemcpyDeviceToHost, s.stream), "D2H total");
+			ck(cudaMemcpyAsync(hStatus, s.sc.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, s.stream), "D2H status");
+			ck(cudaStreamSynchronize(s.stream), "sync (a kernel fault surfaces here)");
+			float a = 0;
+			cudaEventElapsedTime(&a, s.ev[1], s.ev[4]); msTotal += a;
+			cudaEventElapsedTime(&a, s.ev[1], s.ev[2]); last.msLattice += a;
+			cudaEventElapsedTime(&a, s.ev[2], s.ev[3]); last.msViterbi += a;
+			cudaEventElapsedTime(&a, s.ev[3], s.ev[4]); last.msPack += a;
+			total += *hTotal;
+			last.kernelLaunches += 5; last.d2hBytes += 4 + (size_t)pn * 4;
+			for (uint32_t k = 0; k < pn; ++k) if (hStatus[k]) failed.push_back(i0 + k);
+			i0 = i1;
+		}
+		last.nSentences = n; last.rawUnits = totalUnits; last.retried = failed.size();
 		if (!failed.empty())
 		{
-			std::vector<uint32_t> off(n + 1);
-			ck(cudaMemcpy(off.data(), dOffsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost), "D2H offsets");
-			std::vector<uint16_t> subText; std::vector<uint32_t> subOff{ 0 };
+			// overflowed sentences (rare) go through the escalating retry arena; their text comes back from the device
+			if (off.empty()) { off.resize((size_t)n + 1); ck(cudaMemcpy(off.data(), dOffsets, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost), "D2H offsets"); }
+			std::vector<uint16_t> subText; std::vector<uint32_t> subOff{ 0 }, ids;
 			for (uint32_t id : failed)
 			{
 				const size_t len = off[id + 1] - off[id], at = subText.size();
 				subText.resize(at + len);
 				if (len) ck(cudaMemcpy(subText.data() + at, dText + off[id], len * 2, cudaMemcpyDeviceToHost), "D2H text");
-				subOff.push_back((uint32_t)subText.size());
+				subOff.push_back((uint32_t)subText.size()); ids.push_back((uint32_t)ids.size());
 			}
-			BatchOutput tmp; PassResult r1;
-			runHostPass(retry_, subText.data(), subOff.data(), (uint32_t)failed.size(), matchOptions, DEFAULT_PATHS_PER_UNIT * 8, DEFAULT_PATHS_CONST * 8, KB_DEFAULT_NODES_PER_UNIT * 4, r1, tmp);
-			for (uint32_t s : r1.status) if (s) throw std::runtime_error("a sentence exceeded the device scratch capacity even in the retry arena (status " + std::to_string(s) + ")");
-			ms += tmp.msTotal;
-			total += (uint32_t)r1.toks.size();
-			last.retried = failed.size(); last.tokens = total;
+			BatchOutput tmp; tmp.status.assign(failed.size(), 1); tmp.scores.assign(failed.size(), 0.f);
+			std::vector<PassResult> results; std::vector<uint32_t> resultOf(failed.size(), 0xFFFFFFFFu);
+			runRetry(subText.data(), subOff.data(), ids, matchOptions, tmp, results, resultOf);
+			msTotal += tmp.msTotal;
+			for (auto& r : results) total += r.toks.size();
 		}
+		last.tokens = total;
 		if (nTokens) *nTokens = total;
-		return ms;
+		return msTotal;
 	}
 
 	void Engine::debugCong(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
@@ -443,7 +597,8 @@ namespace kb
 			if (ctx[i] >= model.dev.cg_context_size || wid[i] >= model.dev.lang_vocab_size || node[i] < 0 || (uint32_t)node[i] >= model.header.cg_num_nodes)
 				throw std::runtime_error("debugCong: index out of range");
 		}
-		if (g_constantsOwner != &model) { ck(set_model_lattice(model.dev), "constant upload"); ck(set_model_viterbi_cong(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload"); g_constantsOwner = &model; }
+		DeviceGuard g{ device };
+		uploadConstants();
 		const uint32_t nU = std::min(n, 64u), nW = std::min(n, 32u);
 		uint32_t* d = nullptr;
 		const size_t words = (size_t)n * 9 + (size_t)nU * nW;
@@ -467,29 +622,33 @@ namespace kb
 
 	void Engine::setConfig(const kb2_config& cfg)
 	{
+		DeviceGuard g{ device };
 		model.dev.cfg = cfg;
 		model.header.config = cfg;
-		if (g_constantsOwner == &model) g_constantsOwner = nullptr;
+		if (g_devState[g.dev].owner == &model) g_devState[g.dev].owner = nullptr;
 	}
 
 	void Engine::debugTiming(uint32_t n, unsigned long long* out)
 	{
-		if (!main_.vv.timing || n > main_.capSent) throw std::runtime_error("debugTiming: no launch of that size yet");
-		ck(cudaMemcpy(out, main_.vv.timing, (size_t)n * 16, cudaMemcpyDeviceToHost), "debugTiming");
+		DeviceGuard g{ device };
+		const Scratch& sc = slot_[0].sc;
+		if (!sc.vv.timing || n > sc.capSent) throw std::runtime_error("debugTiming: no launch of that size yet");
+		ck(cudaMemcpy(out, sc.vv.timing, (size_t)n * 16, cudaMemcpyDeviceToHost), "debugTiming");
 	}
 
 	int Engine::debugLattice(const uint16_t* text, uint32_t len, uint32_t matchOptions, std::vector<int32_t>& rows)
 	{
 		const uint32_t off[2] = { 0, len };
 		const size_t U = 2 * (size_t)len + 4;
-		Scratch& sc = main_;
-		ensureScratch(sc, U, 1, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
+		DeviceGuard g{ device };
+		Scratch& sc = slot_[0].sc;
+		ensureScratch(sc, stream, U, 1, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
 		ck(cudaMemcpyAsync(sc.dText, text, (size_t)len * 2, cudaMemcpyHostToDevice, stream), "H2D");
 		ck(cudaMemcpyAsync(sc.dOff, off, 8, cudaMemcpyHostToDevice, stream), "H2D");
-		bind(sc, sc.dText, sc.dOff, 1, matchOptions);
+		bind(sc, sc.dText, sc.dOff, 1, matchOptions, 1);
 		ck(cudaMemsetAsync(sc.order, 0, 4, stream), "memset");
 		sc.bv.order = sc.order;
-		if (g_constantsOwner != &model) { ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload"); g_constantsOwner = &model; }
+		uploadConstants();
 		ck(launch_lattice(model.dev, sc.bv, stream), "lattice launch");
 		uint32_t nChunks = 0, status = 0;
 		ck(cudaMemcpyAsync(&nChunks, sc.bv.n_chunks, 4, cudaMemcpyDeviceToHost, stream), "D2H");

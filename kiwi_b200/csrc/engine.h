@@ -56,16 +56,18 @@ namespace kb
 	{
 	public:
 		Model model;
-		cudaStream_t stream = nullptr;
+		cudaStream_t stream = nullptr;      // stream of pass slot 0 (single-pass calls, debug entry points)
 		Stats last;
+		int device = 0;                     // CUDA device the model and the scratch arenas live on
 
 		explicit Engine(const void* imageBytes, size_t size);
 		~Engine();
 
-		// host buffers in, host buffers out (H2D / D2H inside)
+		// host buffers in, host buffers out (H2D / D2H inside).  Batches larger than one pass are cut into passes that alternate
+		// between two scratch arenas on two streams: pass k+1's H2D and kernels overlap pass k's tail and D2H.
+		// A sentence that overflows even the escalated retry capacity keeps a non-zero status and an empty token list (no throw).
 		void analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out);
-		void analyzeOne(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out);
-		// device-resident inputs; results stay on the device.  returns elapsed ms
+		// device-resident inputs; results stay on the device.  returns elapsed ms (CUDA events on the engine stream)
 		float analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens);
 		// lattice of one sentence for stage-level parity tests
 		int debugLattice(const uint16_t* text, uint32_t len, uint32_t matchOptions, std::vector<int32_t>& rows);
@@ -95,18 +97,40 @@ namespace kb
 			uint16_t* dText = nullptr; uint32_t* dOff = nullptr;
 			uint32_t* lenKeys = nullptr; uint32_t* lenKeysOut = nullptr; uint32_t* idxIn = nullptr; uint32_t* order = nullptr; void* sortTemp = nullptr; size_t sortTempBytes = 0;
 		};
+		// one in-flight pass: its own scratch arena, stream, events and pinned staging
+		struct Slot
+		{
+			Scratch sc;
+			cudaStream_t stream = nullptr;
+			cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+			uint16_t* hPinText = nullptr; uint32_t* hPinOff = nullptr; size_t pinTextCap = 0, pinOffCap = 0;
+			void* hPinOut = nullptr; size_t pinOutCap = 0;
+			// the pass in flight
+			bool busy = false; uint32_t i0 = 0, n = 0; size_t rawUnits = 0, units = 0, tokCopied = 0;
+		};
 		const TypoDev* typo_ = nullptr; float typoThreshold_ = 2.5f;
-		void ensureTypoScratch(Scratch& sc, uint32_t graphPerUnit, uint32_t statesPerUnit);
-		Scratch main_, retry_;           // retry_: larger per-sentence capacity, only for sentences that overflowed main_
-		cudaEvent_t ev[6];
-		uint16_t* hPinText = nullptr; uint32_t* hPinOff = nullptr; size_t pinTextCap = 0, pinOffCap = 0;
-		void* hPinOut = nullptr; size_t pinOutCap = 0;
+		void ensureTypoScratch(Scratch& sc, uint32_t graphPerUnit, uint32_t statesPerUnit, uint32_t mul);
+		Slot slot_[2];
+		Scratch retry_;                  // larger per-sentence capacity, only for sentences that overflowed a main arena
 
-		void ensureScratch(Scratch& sc, size_t totalUnits, size_t nSent, uint32_t pathsPerUnit, uint32_t pathsConst, uint32_t nodesPerUnit);
+		void ensureScratch(Scratch& sc, cudaStream_t st, size_t totalUnits, size_t nSent, uint32_t pathsPerUnit, uint32_t pathsConst, uint32_t nodesPerUnit);
 		void freeScratch(Scratch& sc);
-		void bind(Scratch& sc, const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions);
-		void launchAll(Scratch& sc, uint32_t n);
+		void bind(Scratch& sc, const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions, uint32_t capMul);
+		void uploadConstants();
+		void launchAll(Scratch& sc, cudaStream_t st, cudaEvent_t* ev, uint32_t n);
 		struct PassResult { std::vector<uint32_t> tokOff; std::vector<DToken> toks; std::vector<float> scores; std::vector<uint32_t> status; };
-		void runHostPass(Scratch& sc, const uint16_t* text, const uint32_t* off, uint32_t n, uint32_t matchOptions, uint32_t ppu, uint32_t pc, uint32_t npu, PassResult& r, BatchOutput& out);
+		void submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t n, uint32_t matchOptions);
+		void finishPass(Slot& s, BatchOutput& out, std::vector<uint32_t>& failed);
+		void runRetry(const uint16_t* text, const uint32_t* offsets, const std::vector<uint32_t>& failed, uint32_t matchOptions, BatchOutput& out, std::vector<PassResult>& results, std::vector<uint32_t>& resultOf);
+		void checkDebug(Scratch& sc);
+	};
+
+	// one lock per CUDA device: the kernels' model view lives in __constant__ memory (one copy per device and module), so
+	// engines that share a device take turns; engines on different devices run concurrently
+	struct DeviceGuard
+	{
+		int dev; int prev = -1;
+		explicit DeviceGuard(int device);
+		~DeviceGuard();
 	};
 }

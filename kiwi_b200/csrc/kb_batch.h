@@ -30,19 +30,38 @@ namespace kb
 
 	struct DPattern { uint32_t end, len, tag; };
 
+	// filter word of a path: everything the per-(candidate, path) filter of evalSingleMorpheme (PathEvaluator.hpp:566-594) and the
+	// pruning rule need to know about the path's left context, computed ONCE when the path is created
+	enum : uint32_t
+	{
+		FW_CLS_MASK = 7,            // class of the last code unit of the left form (LC_*): all FeatureTestor::isMatched(CondVowel) distinguishes
+		FW_EMPTY = 8, FW_POLAR_POS = 16, FW_POLAR_NEG = 32,
+		FW_NOCOND = 64,             // FormEvaluator skips the conditions: the left form ends in a closing bracket, or the morpheme's tag is SSC
+		FW_ZSIOT = 128,             // morpheme tag is Z_SIOT
+		FW_COMMON_ROOT = 256,       // rootId == commonRootId
+		FW_MORPH_SOCKET = 512,      // the path's morpheme has a combine socket (excluded from the pruning maximum, PathEvaluator.hpp:480)
+		FW_SOCKET_SHIFT = 16,       // 8 bits: WordLL::combineSocket
+		FW_PATH_MASK = 0x00FFFFFFu,
+	};
+	enum : uint32_t { LC_OTHER = 0, LC_SYLLABLE = 1, LC_CODA_L = 2, LC_CODA_H = 3, LC_CODA_APPLOSIVE = 4, LC_CODA_OTHER = 5 };
+
 	struct alignas(16) DPath          // 48 B search path (WordLL, /root/reference/src/BestPathContainer.hpp:21-67), index based
 	{
-		int32_t lm_state; float acc_score; float first_chunk_score; uint32_t wid;
-		int32_t morpheme; uint32_t parent; uint32_t own_off; float acc_typo_cost;
+		// segment 0: what a successor's LM step and score need (one 16-byte load)
+		int32_t lm_state; float acc_score; float acc_typo_cost;
+		uint32_t wid_feat;       // Knlm build: DMorph::feat of morphemes[wid]; CoNg build: CoNgramState::contextIdx
+		// segment 1
+		uint8_t sp_state;        // SpecialState
+		uint8_t root_id, prev_root_id, morph_tag;
+		uint32_t fw;             // FW_* filter word (combine socket in bits 16-23)
+		float first_chunk_score; uint32_t wid;
+		// segment 2: what the back-trace (emit_kernel) needs
+		int32_t morpheme; uint32_t parent; uint32_t own_off;
 		uint16_t own_len;        // own form (ownFormId != 0): own_off >= 0 -> normalized text offset, own_off has bit 31 -> ~form index
 		uint16_t node;           // lattice node (chunk relative) this path ends at
-		uint16_t left_last;      // last code unit of the left form seen by FormEvaluator
-		uint8_t left_pol;        // LP_* bits
-		uint8_t sp_state;        // SpecialState
-		uint8_t root_id, combine_socket, prev_root_id, morph_tag;
-		uint32_t wid_feat;       // DMorph::feat of morphemes[wid]
 	};
-	enum : uint8_t { LP_POLAR_POS = 1, LP_POLAR_NEG = 2, LP_LAST_SSC = 4, LP_EMPTY = 8, LP_MORPH_SOCKET = 128 };
+	static_assert(sizeof(DPath) == 48, "DPath is three 16-byte segments");
+	enum : uint8_t { LP_POLAR_POS = 1, LP_POLAR_NEG = 2, LP_LAST_SSC = 4, LP_EMPTY = 8, LP_MORPH_SOCKET = 128 };   // leftFeat()'s intermediate form
 
 	struct alignas(16) DToken { uint32_t morph; uint32_t position; float score; uint16_t length; uint8_t tag; uint8_t flags; };
 

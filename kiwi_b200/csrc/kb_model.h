@@ -9,6 +9,7 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/kiwi_b200_image.h"
+#include "kb_batch.h"
 
 #if defined(__CUDACC__)
 #define KB_HD __host__ __device__ __forceinline__
@@ -87,15 +88,45 @@ namespace kb
 		uint32_t first_wid;       // isSingle ? lmMorphemeId : chunks[0]->lmMorphemeId
 		uint32_t last_seq_id;     // `lastSeqId` = wid of the created path
 		uint32_t last_seq_feat;   // DMorph::feat of morphemes[last_seq_id]
-		uint16_t left_last;       // left-form features of the created path when it has no own form
-		uint8_t left_pol;         // LP_* bits (kb_batch.h)
-		uint8_t xflags;           // MX_*
+		uint32_t fw_x;            // bits 0-23: filter word (kb_batch.h FW_*) of the created path when it has no own form, without FW_COMMON_ROOT; bits 24-31: MX_*
 	};
+
+	// Static record of ONE candidate entry of a form (parallel to form_cands[], + 2 trailing records for the default unknown
+	// morphemes NNG / NNP): everything PathEvaluator::operator() and evalSingleMorpheme derive from the candidate morpheme alone
+	// (PathEvaluator.hpp:382-448, 531-560, RuleBasedScorer ctor 88-113), resolved at model load.  The candidates of a form are
+	// contiguous, so a lattice node's candidate block is ONE bulk copy (cp.async.bulk) into shared memory.
+	enum : uint8_t
+	{
+		DK_DIALECT = 1,           // non-standard dialect morpheme: never a candidate
+		DK_COMPLEX = 2,           // hasComplex(): dropped when Match::splitComplex
+		DK_SHORTCUT_CODA = 4, DK_SHORTCUT_SIOT = 8,
+		DK_HA = 16,               // contracted 하+다/게/지: dropped after a space (PathEvaluator.hpp:435-448)
+		DK_FIRST_IS_P = 32, DK_CHUNK_HAS_P = 64,
+		DK_IS_SN = 128,           // tag SN: snEndswithPoint is decided per node
+	};
+	enum : uint8_t { CS_POSITIVE_E = 1, CS_SN_POINT = 2, CS_SINGLE = 4, CS_NO_LM = 8, CS_FORK = 16, CS_SOCKET_CHUNK = 32 };
+	struct alignas(16) DCand              // 48 B
+	{
+		int32_t cur_id; uint32_t first_wid; uint32_t last_seq_id; uint32_t last_seq_feat;
+		uint32_t feat; float user_score; uint32_t chunk_off;
+		uint32_t fw_new;          // filter word of the created path (no own form, FW_COMMON_ROOT clear)
+		uint8_t chunk_cnt;
+		uint8_t flags;            // CS_* known statically (CS_POSITIVE_E uses the form's first character)
+		uint8_t path_socket;      // combineSocket of the created path (single morphemes only)
+		uint8_t sense_id;
+		uint8_t cur_socket;       // the morpheme's own combine socket
+		uint8_t kind;             // DK_*
+		uint8_t tag_clean;        // clearIrregular(tag): index into tag_left_boundary
+		uint8_t pad0;
+		uint32_t pad1[2];
+	};
+	static_assert(sizeof(DCand) == 48, "DCand rows are bulk-copied: a multiple of 16 bytes");
 
 	// ---- form feature record
 	enum : uint8_t
 	{
 		FF_ZCODA = 1, FF_ZSIOT = 2, FF_HASFULL = 8,
+		FF_HAS_SPECIAL = 4,       // a candidate is a z_coda / z_siot shortcut or a forking (quote / bullet) morpheme: the node takes the general evaluation path
 		FF_HASJ_OR_STAG = 16,     // form.hasJClass || (len == 1 && sf <= cls(form[0]) <= sw)     KTrie.cpp:970-972
 		FF_FIRST_IS_CODA = 32,    // isHangulCoda(form[0])                                       KTrie.cpp:968
 		FF_ALL_PARTIAL = 64,      // every candidate is combineSocket or chunked non-single      PathEvaluator.hpp:1277-1280
@@ -138,6 +169,8 @@ namespace kb
 		// derived
 		const DMorph* morphs;
 		const DMorphX* morphx;
+		const DCand* cands;            // [n_form_cands + 2]: static candidate records parallel to form_cands, then the unknown NNG / NNP records
+		uint32_t cand_unk;             // index of the NNG record (NNP follows)
 		const uint32_t* chunk_lm;      // lmMorphemeId of every chunk entry (parallel to `chunks`)
 		const DForm* forms;
 		const uint32_t* chr_bmp;       // [65536] cls | script << 8 | flags << 16
@@ -237,6 +270,35 @@ namespace kb
 			return polar == CP_negative;
 		}
 		return polar == CP_negative;
+	}
+	// FeatureTestor::isMatched(CondVowel) only distinguishes these classes of the last code unit (FeatureTestor.cpp:6-60)
+	KB_HD uint32_t lastClass(uint32_t c)
+	{
+		if (0xAC00 <= c && c <= 0xD7A4) return LC_SYLLABLE;
+		if (!(0x11A8 <= c && c <= 0x11C2)) return LC_OTHER;
+		if (c == 0x11AF) return LC_CODA_L;
+		if (c == 0x11C2) return LC_CODA_H;
+		switch (c) { case 0x11A8: case 0x11A9: case 0x11AA: case 0x11AE: case 0x11B8: case 0x11B9: case 0x11BA: case 0x11BB: case 0x11BD: case 0x11BE: case 0x11BF: case 0x11C0: case 0x11C1: return LC_CODA_APPLOSIVE; }
+		return LC_CODA_OTHER;
+	}
+	// left-form part of a path's filter word from (last code unit, LP_* bits)
+	KB_HD uint32_t fwOfLeft(uint16_t last, uint8_t lp)
+	{
+		uint32_t w = lastClass(last);
+		if (lp & LP_EMPTY) w |= FW_EMPTY;
+		if (lp & LP_POLAR_POS) w |= FW_POLAR_POS;
+		if (lp & LP_POLAR_NEG) w |= FW_POLAR_NEG;
+		if (lp & LP_LAST_SSC) w |= FW_NOCOND;
+		if (lp & LP_MORPH_SOCKET) w |= FW_MORPH_SOCKET;
+		return w;
+	}
+	// tag / socket part: SSC tag switches the conditions off, Z_SIOT is filtered by its successors, the path's combine socket
+	KB_HD uint32_t fwOfTag(uint8_t morphTag, uint8_t pathSocket)
+	{
+		uint32_t w = (uint32_t)pathSocket << FW_SOCKET_SHIFT;
+		if (morphTag == T_ssc) w |= FW_NOCOND;
+		if (morphTag == T_z_siot) w |= FW_ZSIOT;
+		return w;
 	}
 	// float epilogues of the CoNg int8 scorer (see oracle/restate/cong.hpp for the reference kernels each one restates)
 	enum : uint32_t { CG_E_SCALAR = 0, CG_E_SMALL = 1, CG_E_GEMV = 2 };

@@ -207,15 +207,82 @@ namespace kb
 			// left form seen by FormEvaluator when the path has no own form: kform of morphemes[wid], else of the morpheme
 			int32_t fi = morphs[x.last_seq_id].form_idx;
 			if (!(fi >= 0 && forms[fi].str_len)) fi = m.form_idx;
-			if (fi < 0 || forms[fi].str_len == 0) { x.left_last = 0; x.left_pol = LP_EMPTY | LP_POLAR_POS | LP_POLAR_NEG; }
-			else { x.left_last = dforms[fi].last_chr; x.left_pol = dforms[fi].pol & (FP_POLAR_POS | FP_POLAR_NEG | FP_LAST_SSC); }
-			if (m.combine_socket) x.left_pol |= LP_MORPH_SOCKET;
+			uint16_t leftLast; uint8_t leftPol;
+			if (fi < 0 || forms[fi].str_len == 0) { leftLast = 0; leftPol = LP_EMPTY | LP_POLAR_POS | LP_POLAR_NEG; }
+			else { leftLast = dforms[fi].last_chr; leftPol = dforms[fi].pol & (FP_POLAR_POS | FP_POLAR_NEG | FP_LAST_SSC); }
+			if (m.combine_socket) leftPol |= LP_MORPH_SOCKET;
 			uint8_t xf = 0;
 			if ((dmorphs[x.first_wid].feat & MF_TAG_MASK) == T_p) xf |= MX_FIRST_IS_P;
 			if (!single) for (uint32_t c = 1; c < m.chunk_cnt; ++c) if ((dmorphs[chunkLm[m.chunk_off + c]].feat & MF_TAG_MASK) == T_p) xf |= MX_CHUNK_HAS_P;
-			x.xflags = xf;
+			// the created path: morph_tag = the candidate's tag, combineSocket only for single morphemes (BestPathContainer.hpp:451-469)
+			x.fw_x = fwOfLeft(leftLast, leftPol) | fwOfTag(m.tag, single ? m.combine_socket : 0) | ((uint32_t)xf << 24);
 			dmx[i] = x;
 		}
+
+		// ---- static candidate records, parallel to form_cands (+ the unknown NNG / NNP records): kb_model.h DCand
+		const uint32_t nFormCands = (uint32_t)(h->sec[KB2_SEC_FORM_CANDS].nbytes / 4);
+		std::vector<DCand> dcands(nFormCands + 2);
+		auto makeCand = [&](uint32_t curId, bool formStartsWithA)
+		{
+			DCand c; std::memset(&c, 0, sizeof(c));
+			const kb2_morph& m = morphs[curId];
+			const DMorph& dm = dmorphs[curId];
+			const DMorphX& mx = dmx[curId];
+			const bool single = (dm.feat & MF_SINGLE) != 0;
+			const uint32_t tag = dm.feat & MF_TAG_MASK;
+			c.cur_id = (int32_t)curId; c.first_wid = mx.first_wid; c.last_seq_id = mx.last_seq_id; c.last_seq_feat = mx.last_seq_feat;
+			c.feat = dm.feat; c.user_score = m.user_score; c.chunk_off = m.chunk_off; c.fw_new = mx.fw_x & FW_PATH_MASK;
+			c.chunk_cnt = m.chunk_cnt; c.sense_id = m.sense_id; c.cur_socket = m.combine_socket; c.path_socket = single ? m.combine_socket : 0;
+			c.tag_clean = clearIrregular((uint8_t)tag);
+			uint8_t kind = 0;
+			if (m.dialect != 0) kind |= DK_DIALECT;
+			{
+				bool cx = (dmorphs[(int64_t)curId + m.combined].misc & MM_COMPLEX) != 0;
+				for (uint32_t k = 0; k < m.chunk_cnt && !cx; ++k) if (dmorphs[chunksH[m.chunk_off + k].morph].misc & MM_COMPLEX) cx = true;
+				if (cx) kind |= DK_COMPLEX;
+			}
+			if (tag == T_z_coda) kind |= DK_SHORTCUT_CODA;
+			if (tag == T_z_siot) kind |= DK_SHORTCUT_SIOT;
+			if (!single && m.form_idx >= 0 && forms[m.form_idx].str_len == 1)
+			{
+				const uint16_t k0 = formChars[forms[m.form_idx].str_off];
+				if (k0 == 0xB2E4 || k0 == 0xAC8C || k0 == 0xC9C0)
+				{
+					const kb2_morph& c0 = morphs[chunksH[m.chunk_off].morph];
+					if (c0.form_idx >= 0 && forms[c0.form_idx].str_len == 1 && formChars[forms[c0.form_idx].str_off] == 0xD558) kind |= DK_HA;
+				}
+			}
+			const uint8_t xf = (uint8_t)(mx.fw_x >> 24);
+			if (xf & MX_FIRST_IS_P) kind |= DK_FIRST_IS_P;
+			if (xf & MX_CHUNK_HAS_P) kind |= DK_CHUNK_HAS_P;
+			if (tag == T_sn) kind |= DK_IS_SN;
+			c.kind = kind;
+			const uint32_t specialType = (dm.feat >> MF_SPECIAL_SHIFT) & 7, sbType = (dm.feat >> MF_SBTYPE_SHIFT) & 31;
+			const bool fork = sbType != 0 || specialType == 0 || specialType == 1 || specialType == 3 || specialType == 4;
+			uint8_t fl = 0;
+			if (isEClass((uint8_t)tag) && formStartsWithA) fl |= CS_POSITIVE_E;
+			if (single) fl |= CS_SINGLE;
+			if (m.combine_socket && single) fl |= CS_NO_LM;
+			if (fork) fl |= CS_FORK;
+			if (m.combine_socket && !single) fl |= CS_SOCKET_CHUNK;
+			c.flags = fl;
+			return c;
+		};
+		for (uint32_t i = 0; i < h->n_forms; ++i)
+		{
+			const kb2_form& f = forms[i];
+			const bool startsA = f.str_len && formChars[f.str_off] == 0xC544;
+			bool special = false;
+			for (uint32_t c = 0; c < f.cand_cnt; ++c)
+			{
+				const DCand dc = makeCand(formCands[f.cand_off + c], startsA);
+				dcands[f.cand_off + c] = dc;
+				if ((dc.kind & (DK_SHORTCUT_CODA | DK_SHORTCUT_SIOT)) || (dc.flags & CS_FORK)) special = true;
+			}
+			if (special) dforms[i].flags |= FF_HAS_SPECIAL;
+		}
+		dcands[nFormCands] = makeCand(T_nng + 1u, false);          // getDefaultMorphemeId, Kiwi.h:64-67
+		dcands[nFormCands + 1] = makeCand(T_nnp + 1u, false);
 
 		// ---- Knlm one-probe layout
 		const kb2_kn_node* knNodes = reinterpret_cast<const kb2_kn_node*>(sec(KB2_SEC_KN_NODES));
@@ -298,6 +365,7 @@ namespace kb
 		d.chr_runs = reinterpret_cast<const kb2_chr_run*>(dsec(KB2_SEC_CHR_RUNS));
 		d.morphs = upload(dmorphs, owned);
 		d.morphx = upload(dmx, owned);
+		d.cands = upload(dcands, owned); d.cand_unk = nFormCands;
 		d.chunk_lm = upload(chunkLm, owned);
 		d.kn_hash = upload(knHash, owned); d.kn_hash_mask = hashSize - 1;
 		d.kn_backoff = upload(knBackoff, owned);

@@ -89,31 +89,21 @@ namespace KB_VIT_NS
 	static_assert(ITEM_CAP % 32 == 0 && ITEM_CAP >= 256, "item buffer");
 	static_assert(STAGE_CAP % 512 == 0 && STAGE_CAP <= HT_MAX_ENTRIES * 2 && (HT_SIZE & (HT_SIZE - 1)) == 0, "staging / index capacities");
 
-	// static + per-node data of one candidate morpheme, written lane-parallel (lane = candidate) into shared memory
-	struct alignas(8) CandS
-	{
-		int32_t curId; uint32_t firstWid, lastSeqId, feat, lastSeqFeat, chunkOff;
-		float additionalScore;
-		uint16_t leftLast; uint8_t leftPol, chunkCnt, flags, pathSocket, senseId, cls;
-	};
-	enum : uint8_t { CS_POSITIVE_E = 1, CS_SN_POINT = 2, CS_SINGLE = 4, CS_NO_LM = 8, CS_FORK = 16, CS_SOCKET_CHUNK = 32 };
+	// per-node data of one candidate of the current group of 32 (the static part is the DCand row next to it in shared memory)
+	struct alignas(8) CandDyn { float additionalScore; uint8_t flags, cls, pad0, pad1; };
 	enum : uint8_t { CLS_SKIP = 0, CLS_ITEM = 1, CLS_GENERAL = 2, CLS_SHORTCUT = 3 };
-
-	// filter word of an incoming path (all the filter pass needs, 4 B):
-	enum : uint32_t { FW_CLS_MASK = 7, FW_EMPTY = 8, FW_POLAR_POS = 16, FW_POLAR_NEG = 32, FW_NOCOND = 64, FW_ZSIOT = 128, FW_COMMON_ROOT = 256, FW_SOCKET_SHIFT = 16 };
-	enum : uint32_t { LC_OTHER = 0, LC_SYLLABLE = 1, LC_CODA_L = 2, LC_CODA_H = 3, LC_CODA_APPLOSIVE = 4, LC_CODA_OTHER = 5 };
 	static constexpr uint32_t FWTAB_CAP = 64;
 
 	struct CandMask { uint32_t valid, condFail, sets; };
 
 	struct WarpSmem
 	{
+		alignas(16) DCand dcand[GROUP];         // static candidate rows of the current group (bulk copy of the form's contiguous block, or lane stores)
+		CandDyn cdyn[GROUP];
 		uint8_t pcls[STAGE_CAP];                // class index of every incoming path (classes = distinct filter words)
 		uint32_t fclass[32];                    // the distinct filter words: FW_* bits | combine_socket << 16
-		uint32_t classBits[32][STAGE_CAP / 32]; // per class: bitmap of the incoming paths that belong to it
 		uint16_t ht[HT_SIZE];
 		uint32_t item[ITEM_CAP];                // slot << 27 | fwIdx << 20 | q << 3 | spacePen << 2 | r << 1 | condFail
-		CandS cand[GROUP];
 		CandMask cmask[GROUP];                  // per candidate: which path classes survive the filter / fail the soft condition / override firstWid
 		uint32_t candNew[GROUP];                // entries created per candidate of the current group
 		uint32_t fwTab[FWTAB_CAP];              // first-wid overrides of socket chunks (PathEvaluator.hpp:590), index 0 unused
@@ -122,7 +112,7 @@ namespace KB_VIT_NS
 		uint32_t uctx[KB_CG_UCAP];              // the node's unique context ids (regular incoming paths)
 		uint8_t pslot[STAGE_CAP];               // incoming path -> index into uctx, 0xFF = none (socket path / more than 64 contexts)
 		uint32_t colWid[GROUP];                 // first wid of every candidate of the group
-		uint32_t candOrder[KB_CG_CANDS];        // the node's candidates in the transposed evaluator's order
+		uint32_t candOrder[KB_CG_CANDS];        // the node's candidates in the transposed evaluator's order (indices into the node's candidate block)
 #endif
 	};
 #ifndef KB_VIT_WARPS
@@ -133,16 +123,6 @@ namespace KB_VIT_NS
 
 	__device__ __forceinline__ float asFloat(int32_t v) { return __int_as_float(v); }
 
-	// FeatureTestor::isMatched(CondVowel) only distinguishes these classes of the last code unit (FeatureTestor.cpp:6-60)
-	__device__ __forceinline__ uint32_t lastClass(uint32_t c)
-	{
-		if (0xAC00 <= c && c <= 0xD7A4) return LC_SYLLABLE;
-		if (!(0x11A8 <= c && c <= 0x11C2)) return LC_OTHER;
-		if (c == 0x11AF) return LC_CODA_L;
-		if (c == 0x11C2) return LC_CODA_H;
-		switch (c) { case 0x11A8: case 0x11A9: case 0x11AA: case 0x11AE: case 0x11B8: case 0x11B9: case 0x11BA: case 0x11BB: case 0x11BD: case 0x11BE: case 0x11BF: case 0x11C0: case 0x11C1: return LC_CODA_APPLOSIVE; }
-		return LC_CODA_OTHER;
-	}
 	__device__ __forceinline__ bool ftVowelCls(bool empty, uint32_t cls, uint32_t vowel)
 	{
 		if (vowel == CV_none) return true;
@@ -180,11 +160,7 @@ namespace KB_VIT_NS
 	}
 	__device__ __noinline__ float knProgress(int32_t& nodeIdx, uint32_t next, uint32_t site = 0)
 	{
-		if (next >= c_m.kn_htx_vocab || (uint32_t)nodeIdx >= 0x10000000u)
-		{
-			if (atomicCAS(&c_m.debug[0], 0u, 1u) == 0u) { c_m.debug[1] = site; c_m.debug[2] = next; c_m.debug[3] = (uint32_t)nodeIdx; c_m.debug[4] = blockIdx.x; c_m.debug[5] = threadIdx.x; }
-			return 0.f;
-		}
+		(void)site;
 		float acc = 0;
 		while (true)
 		{
@@ -509,7 +485,7 @@ namespace KB_VIT_NS
 			float additionalScore, ignoreCondScore;
 			uint32_t specialType, sbType, sbOrder; bool positiveE, snEndswithPoint, fork;
 			uint32_t ownOff, ownLen;
-			uint16_t leftLast; uint8_t leftPol; uint8_t morphTag; uint32_t widFeat; uint8_t pathSocket;
+			uint32_t fwNew; uint8_t morphTag; uint32_t widFeat;      // fwNew: filter word of the created path (own form resolved, FW_COMMON_ROOT clear)
 			bool spaceBefore;
 #if KB_CONG
 			uint32_t epFirst;        // epilogue of the first-wid score of a regular candidate (shape of the node's gather GEMM), CG_E_*
@@ -550,9 +526,9 @@ namespace KB_VIT_NS
 				{
 					candScore = pp.acc_score + cc.additionalScore;
 					firstChunkScore = cc.additionalScore;
-					if (pp.combine_socket)
+					if (pp.fw >> FW_SOCKET_SHIFT)
 					{
-						if (pp.combine_socket != cc.cur.combine_socket || cc.single) valid = false;
+						if ((pp.fw >> FW_SOCKET_SHIFT) != cc.cur.combine_socket || cc.single) valid = false;
 						else if (cc.spaceBefore)
 						{
 							if (allowedSpaceBetweenChunk) candScore -= c_m.cfg.space_penalty;
@@ -568,7 +544,7 @@ namespace KB_VIT_NS
 				}
 #if KB_CONG
 				// right halves only see combining paths, and their first wid is local to the pair (CoNgramModel.cpp:248-286)
-				if (valid && cc.cur.combine_socket && !cc.single && !pp.combine_socket) valid = false;
+				if (valid && cc.cur.combine_socket && !cc.single && !(pp.fw >> FW_SOCKET_SHIFT)) valid = false;
 				const uint32_t firstWid = setsFW ? fwVal : cc.firstWid0;
 				(void)fwCarry;
 				const bool regular = cc.cur.combine_socket == 0;
@@ -588,15 +564,15 @@ namespace KB_VIT_NS
 				if (valid)
 				{
 					// FormEvaluator, PathEvaluator.hpp:253-311
-					const bool empty = (pp.left_pol & LP_EMPTY) != 0;
-					if (pp.morph_tag == T_ssc || (pp.left_pol & LP_LAST_SSC)) {}
+					const bool empty = (pp.fw & FW_EMPTY) != 0;
+					if (pp.fw & FW_NOCOND) {}      // SSC tag or a left form ending in a closing bracket
 					else
 					{
 						const uint32_t cv = (cc.cur.feat >> MF_VOWEL_SHIFT) & 15, cp = (cc.cur.feat >> MF_POLAR_SHIFT) & 3;
-						bool ok = ftVowel(empty, pp.left_last, (uint8_t)cv);
+						bool ok = ftVowelCls(empty, pp.fw & FW_CLS_MASK, cv);
 						if (ok && (cp == CP_positive || cp == CP_negative))
 						{
-							ok = empty ? true : ((pp.left_pol & (cp == CP_positive ? LP_POLAR_POS : LP_POLAR_NEG)) != 0);
+							ok = empty ? true : ((pp.fw & (cp == CP_positive ? FW_POLAR_POS : FW_POLAR_NEG)) != 0);
 						}
 #if KB_CONG
 						// regular candidates: `score = acc + morphScore + lm` comes first, FormEvaluator adds afterwards (CoNgramModel.cpp:175-179)
@@ -820,10 +796,11 @@ namespace KB_VIT_NS
 							DPath np;
 							np.lm_state = lmState; np.acc_score = accScore; np.first_chunk_score = fcs; np.wid = cc.lastSeqId;
 							np.morpheme = cc.curId; np.parent = inBeg + q; np.own_off = cc.single ? cc.ownOff : 0; np.acc_typo_cost = pp.acc_typo_cost + node.typo_cost;
-							np.own_len = cc.single ? (uint16_t)cc.ownLen : 0; np.node = (uint16_t)nodeIdx; np.left_last = cc.leftLast; np.left_pol = cc.leftPol;
+							np.own_len = cc.single ? (uint16_t)cc.ownLen : 0; np.node = (uint16_t)nodeIdx;
 							np.sp_state = spState;
 							np.root_id = rootId != COMMON_ROOT ? rootId : pp.root_id;
-							np.combine_socket = cc.pathSocket; np.prev_root_id = (uint8_t)prevRoot; np.morph_tag = cc.morphTag;
+							np.fw = cc.fwNew | (np.root_id == COMMON_ROOT ? (uint32_t)FW_COMMON_ROOT : 0u);
+							np.prev_root_id = (uint8_t)prevRoot; np.morph_tag = cc.morphTag;
 #if KB_CONG
 							P_CTX(np) = ctxIdx;
 #else
@@ -880,10 +857,12 @@ namespace KB_VIT_NS
 
 
 		// ---- the item pipeline (containers of <= 512 incoming paths: the reference's top1Small / top1Medium) --------
-		// The incoming paths' filter words are staged once per node in shared memory.  Candidates are classified
-		// 32 at a time, one lane per candidate.  For every candidate, in order, a filter pass (z_siot / combine-socket /
-		// FormEvaluator conditions: ALU only) appends the surviving (candidate, path[, root]) items to a list that is
-		// drained 32 items at a time ACROSS candidate boundaries, so the Knlm pointer chase runs with full lanes.
+		// Every path carries its filter word (DPath::fw, computed when the path was created); the distinct words of a node's
+		// incoming paths become "path classes" (a handful per node).  Candidates are classified 32 at a time, one lane per
+		// candidate, from their static DCand rows; each lane decides per path class whether a pair survives the reference's
+		// filter (z_siot / combine socket / FormEvaluator conditions), so the per-pair filter is a bit test.  For every
+		// candidate, in order, the survivors are compacted by ballot into an item list that is drained 32 items at a time
+		// ACROSS candidate boundaries, so the Knlm pointer chase runs with full lanes.
 		// Items are in (candidate, path, root) order and new container entries are appended in item order, hence the
 		// pool receives them candidate-major in first-insertion order = the write-out order of the reference's
 		// per-candidate containers.  Keys are independent of each other, so the 128-slot capacity of a container
@@ -893,29 +872,14 @@ namespace KB_VIT_NS
 		{
 			if (stagedNode == nodeIdx) return;
 			nClasses = 0; classCommon = 0; classOverflow = false;
-			uint32_t myTab = 0;
+			uint32_t myTab = 0;      // lane z keeps class z's filter word
 			#pragma unroll 1
 			for (uint32_t qb = 0; qb < P; qb += 32)
 			{
 				const uint32_t q = qb + lane;
-				uint32_t w = 0xFFFFFFFFu;
-				if (q < P)
-				{
-					const DPath* p = pool + inBeg + q;
-					const uint32_t lp = p->left_pol;
-					w = lastClass(p->left_last);
-					if (lp & LP_EMPTY) w |= FW_EMPTY;
-					if (lp & LP_POLAR_POS) w |= FW_POLAR_POS;
-					if (lp & LP_POLAR_NEG) w |= FW_POLAR_NEG;
-					if ((lp & LP_LAST_SSC) || p->morph_tag == T_ssc) w |= FW_NOCOND;
-					if (p->morph_tag == T_z_siot) w |= FW_ZSIOT;
-					if (p->root_id == COMMON_ROOT) w |= FW_COMMON_ROOT;
-					w |= (uint32_t)p->combine_socket << FW_SOCKET_SHIFT;
-				}
-				// distinct filter words -> class table (a handful per node); lane z keeps class z's word for the search
+				const uint32_t w = q < P ? pool[inBeg + q].fw : 0xFFFFFFFFu;
 				unsigned rem = __ballot_sync(FULL, q < P);
 				uint32_t myIdx = 0;
-				const uint32_t word = qb >> 5;
 				while (rem)
 				{
 					const int src = __ffs(rem) - 1;
@@ -928,25 +892,23 @@ namespace KB_VIT_NS
 					{
 						idx = nClasses++;
 						if (lane == idx) myTab = v;
-						if (lane == 0) sm->fclass[idx] = v;
-						for (uint32_t w = lane; w < STAGE_CAP / 32; w += 32) sm->classBits[idx][w] = 0;
 						if (v & FW_COMMON_ROOT) classCommon |= 1u << idx;
-						__syncwarp();
 					}
 					const unsigned same = __ballot_sync(FULL, w == v);
 					if (w == v) myIdx = idx;
-					if (lane == 0) sm->classBits[idx][word] = same;
 					rem &= ~same;
 				}
 				if (q < P) sm->pcls[q] = (uint8_t)myIdx;
 			}
+			if (lane < nClasses) sm->fclass[lane] = myTab;
 			stagedNode = nodeIdx;
 			__syncwarp();
 		}
 
 		struct FlushCtx
 		{
-			uint32_t nodeIdx; uint32_t inBeg; float ignoreCondScore; float nodeTypoCost; uint32_t ownOff, ownLen; uint16_t ownLeftLast; uint8_t ownLeftPol;
+			uint32_t nodeIdx; uint32_t inBeg; float ignoreCondScore; float nodeTypoCost; uint32_t ownOff, ownLen;
+			uint32_t ownFw;      // left-form part of the filter word of a path that keeps the node's own form
 #if KB_CONG
 			uint32_t epFirst, dotMask;      // epilogue of the node's gather GEMM; candidates of the current group that have a column in sm->dots
 #endif
@@ -955,6 +917,7 @@ namespace KB_VIT_NS
 		__device__ __noinline__ void flushItems(const FlushCtx& fc)
 		{
 			if (!nItems) return;
+			__syncwarp();
 			#pragma unroll 1
 			for (uint32_t ib = 0; ib < nItems; ib += 32)
 			{
@@ -962,45 +925,41 @@ namespace KB_VIT_NS
 				const bool valid = i < nItems;
 				uint32_t slot = 0, q = 0, r = 0, fwIdx = 0; bool condFail = false, spacePen = false;
 				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 0x1FFFF; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
-				const CandS cs = sm->cand[slot];
-				int32_t lmState = 0; float accScore = 0, fcs = 0; uint32_t prevRoot = 0; uint8_t spState = 0, rootId = COMMON_ROOT;
+				const DCand* cs = &sm->dcand[slot];
+				const CandDyn cd = sm->cdyn[slot];
+				const uint32_t csFeat = cs->feat;
+				const int32_t csCurId = cs->cur_id;
+				int32_t lmState = 0; float accScore = 0, fcs = 0, typoAcc = 0; uint32_t prevRoot = 0; uint8_t spState = 0, rootId = COMMON_ROOT;
 #if KB_CONG
 				uint32_t ctxIdx = 0;
 #endif
-				bool bad = false;
 				if (valid)
 				{
 					const DPath* pp = pool + fc.inBeg + q;
-					prevRoot = pp->root_id;
-					const bool doFork = (cs.flags & CS_FORK) && prevRoot == COMMON_ROOT;
-					spState = doFork ? uniq[r] : pp->sp_state;
+					const uint4 s0 = *reinterpret_cast<const uint4*>(&pp->lm_state);      // lm_state, acc_score, acc_typo_cost, wid_feat
+					const uint32_t meta = *reinterpret_cast<const uint32_t*>(&pp->sp_state);   // sp_state | root_id << 8 | prev_root_id << 16 | morph_tag << 24
+					prevRoot = (meta >> 8) & 0xFF;
+					const bool doFork = (cd.flags & CS_FORK) && prevRoot == COMMON_ROOT;
+					spState = doFork ? uniq[r] : (uint8_t)(meta & 0xFF);
 					rootId = doFork ? (uint8_t)r : COMMON_ROOT;
-					float candScore = pp->acc_score + cs.additionalScore;
-					float firstChunkScore = cs.additionalScore;
+					typoAcc = __uint_as_float(s0.z);
+					float candScore = __uint_as_float(s0.y) + cd.additionalScore;
+					float firstChunkScore = cd.additionalScore;
 					if (spacePen) candScore -= c_m.cfg.space_penalty;
 #if KB_CONG
 					// regular candidates: FormEvaluator's soft penalty comes after `acc + morphScore + lm` (CoNgramModel.cpp:175-179)
-					const bool cgRegular = !(cs.flags & (CS_NO_LM | CS_SOCKET_CHUNK));
+					const bool cgRegular = !(cd.flags & (CS_NO_LM | CS_SOCKET_CHUNK));
 					if (condFail && !cgRegular) candScore += fc.ignoreCondScore;
-					ctxIdx = P_CTX(*pp);
+					ctxIdx = s0.w;
+					const uint32_t pf = c_m.morphs[pp->wid].feat;
 #else
 					if (condFail) candScore += fc.ignoreCondScore;
+					const uint32_t pf = s0.w;
 #endif
-					lmState = pp->lm_state;
-					const uint32_t pf = P_WID_FEAT(*pp);
-					const uint32_t firstWid = fwIdx ? sm->fwTab[fwIdx] : cs.firstWid;
-					bad = firstWid >= c_m.n_morphs || slot >= GROUP || fc.inBeg + q >= poolCap;
-					if (bad)
-					{
-						if (atomicCAS(&bv.debug[0], 0u, 1u) == 0u)
-						{
-							bv.debug[1] = sm->item[i]; bv.debug[2] = firstWid; bv.debug[3] = slot; bv.debug[4] = q; bv.debug[5] = nItems; bv.debug[6] = i; bv.debug[7] = (uint32_t)cs.curId;
-							bv.debug[8] = cs.flags; bv.debug[9] = cs.cls; bv.debug[10] = fc.nodeIdx; bv.debug[11] = fc.inBeg; bv.debug[12] = nClasses; bv.debug[13] = htCount; bv.debug[14] = lane; bv.debug[15] = cs.firstWid;
-						}
-					}
-					else
+					lmState = (int32_t)s0.x;
+					const uint32_t firstWid = fwIdx ? sm->fwTab[fwIdx] : cs->first_wid;
 #if KB_CONG
-					if (!(cs.flags & CS_NO_LM))
+					if (!(cd.flags & CS_NO_LM))
 					{
 						float ll;
 						if (cgRegular)
@@ -1013,51 +972,56 @@ namespace KB_VIT_NS
 						else ll = cgNext(lmState, ctxIdx, firstWid);
 						candScore += ll; firstChunkScore += ll;
 						if (condFail && cgRegular) candScore += fc.ignoreCondScore;
-						if (!(cs.flags & CS_SINGLE))
+						if (!(cd.flags & CS_SINGLE))
 						{
+							const uint32_t co = cs->chunk_off, cc = cs->chunk_cnt;
 							#pragma unroll 1
-							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = cgNext(lmState, ctxIdx, c_m.chunk_lm[cs.chunkOff + c]); candScore += ll; }
+							for (uint32_t c = 1; c < cc; ++c) { ll = cgNext(lmState, ctxIdx, c_m.chunk_lm[co + c]); candScore += ll; }
 						}
 					}
 #else
-					if (!(cs.flags & CS_NO_LM))
+					if (!(cd.flags & CS_NO_LM))
 					{
 						float ll = knProgress(lmState, firstWid, 1);
 						candScore += ll; firstChunkScore += ll;
-						if (!(cs.flags & CS_SINGLE))
+						if (!(cd.flags & CS_SINGLE))
 						{
+							const uint32_t co = cs->chunk_off, cc = cs->chunk_cnt;
 							#pragma unroll 1
-							for (uint32_t c = 1; c < cs.chunkCnt; ++c) { ll = knProgress(lmState, c_m.chunk_lm[cs.chunkOff + c], 2); candScore += ll; }
+							for (uint32_t c = 1; c < cc; ++c) { ll = knProgress(lmState, c_m.chunk_lm[co + c], 2); candScore += ll; }
 						}
 					}
 #endif
 					// RuleBasedScorer::operator() + special-state update (PathEvaluator.hpp:115-183, 208-230)
 					const uint32_t ptag = pf & MF_TAG_MASK;
-					const uint32_t specialType = (cs.feat >> MF_SPECIAL_SHIFT) & 7, sbType = (cs.feat >> MF_SBTYPE_SHIFT) & 31, sbOrder = sbType ? cs.senseId : 0;
+					const uint32_t specialType = (csFeat >> MF_SPECIAL_SHIFT) & 7, sbType = (csFeat >> MF_SBTYPE_SHIFT) & 31;
 					float rs = 0;
-					if ((cs.feat & MF_VOWEL_E) && isIrregular((uint8_t)ptag)) rs -= 10;
-					if ((cs.feat & MF_INF_J) && (pf & MF_INFL_NP)) rs -= 5;
-					if ((cs.feat & MF_BADPAIR_L) && (pf & MF_VERB_L)) rs -= 7;
-					if ((cs.flags & CS_POSITIVE_E) && !(pf & MF_POS_VERB)) rs -= 100;
-					if ((cs.feat & MF_CONTRACT_E) && (pf & MF_VERB_VOWEL)) rs -= 3;
-					if (((cs.feat >> MF_POLAR_SHIFT) & 3) == CP_non_adj && (ptag == T_va || ptag == T_xsa)) rs -= 10;
-					const uint32_t sq = spState & 1, dq = (spState >> 1) & 1, bh = spState >> 2;
+					if ((csFeat & MF_VOWEL_E) && isIrregular((uint8_t)ptag)) rs -= 10;
+					if ((csFeat & MF_INF_J) && (pf & MF_INFL_NP)) rs -= 5;
+					if ((csFeat & MF_BADPAIR_L) && (pf & MF_VERB_L)) rs -= 7;
+					if ((cd.flags & CS_POSITIVE_E) && !(pf & MF_POS_VERB)) rs -= 100;
+					if ((csFeat & MF_CONTRACT_E) && (pf & MF_VERB_VOWEL)) rs -= 3;
+					if (((csFeat >> MF_POLAR_SHIFT) & 3) == CP_non_adj && (ptag == T_va || ptag == T_xsa)) rs -= 10;
+					const uint32_t sq = spState & 1, dq = (spState >> 1) & 1;
 					if (specialType <= 2) { if (specialType != sq) rs -= 2; }
 					else if (specialType <= 5) { if (specialType - 3 != dq) rs -= 2; }
-					if (sbType == 5) rs -= 5;
-					if (sbType && isEClass((uint8_t)ptag) && ptag != T_ef) rs -= 10;
-					if (sbType && bh == hashSbTypeOrder((uint8_t)sbType, (uint8_t)sbOrder)) rs += 3;
-					if ((cs.flags & CS_SN_POINT) && (ptag == T_unknown || ptag == T_ef || ptag == T_sf)) rs -= 5;
+					if (sbType)
+					{
+						const uint32_t sbOrder = cs->sense_id, bh = spState >> 2;
+						if (sbType == 5) rs -= 5;
+						if (isEClass((uint8_t)ptag) && ptag != T_ef) rs -= 10;
+						if (bh == hashSbTypeOrder((uint8_t)sbType, (uint8_t)sbOrder)) rs += 3;
+					}
+					if ((cd.flags & CS_SN_POINT) && (ptag == T_unknown || ptag == T_ef || ptag == T_sf)) rs -= 5;
 					accScore = candScore + rs;
 					fcs = firstChunkScore + rs;
 					if (specialType == 0) spState |= 1;
 					else if (specialType == 1) spState &= ~1;
 					else if (specialType == 3) spState |= 2;
 					else if (specialType == 4) spState &= ~2;
-					if (sbType) spState = (spState & 3) | (uint8_t)(hashSbTypeOrder((uint8_t)sbType, (uint8_t)(sbOrder + 1)) << 2);
+					if (sbType) spState = (spState & 3) | (uint8_t)(hashSbTypeOrder((uint8_t)sbType, (uint8_t)(cs->sense_id + 1)) << 2);
 					accScore = accScore - 0.f; fcs = fcs - 0.f;        // curDialectCost (standard dialect only)
 				}
-				if (__any_sync(FULL, bad)) { err = ST_INTERNAL; return; }
 				// de-duplication by (candidate, lmState, prevRootId, spState): best score, earliest item on ties
 				const unsigned long long key = valid
 					? ((unsigned long long)(uint32_t)lmState | ((unsigned long long)prevRoot << 32) | ((unsigned long long)spState << 40) | ((unsigned long long)slot << 48))
@@ -1081,7 +1045,7 @@ namespace KB_VIT_NS
 						const uint32_t e = ht[hs];
 						if (!e) break;
 						const DPath* tp = pool + htBase + (e - 1);
-						if (tp->lm_state == lmState && tp->morpheme == cs.curId && tp->prev_root_id == prevRoot && tp->sp_state == spState) { found = e - 1; break; }
+						if (tp->lm_state == lmState && tp->morpheme == csCurId && tp->prev_root_id == prevRoot && tp->sp_state == spState) { found = e - 1; break; }
 						hs = (hs + 1) & (HT_SIZE - 1);
 					}
 				}
@@ -1109,21 +1073,21 @@ namespace KB_VIT_NS
 					if (tgtOld != NPOS) write = accScore > pool[htBase + tgt].acc_score;
 					if (write)
 					{
-						const bool single = (cs.flags & CS_SINGLE) != 0;
-						const bool own = single && fc.ownLen;
+						const bool own = (cd.flags & CS_SINGLE) && fc.ownLen;
+						const uint8_t tag = (uint8_t)(csFeat & MF_TAG_MASK);
 						DPath np;
-						np.lm_state = lmState; np.acc_score = accScore; np.first_chunk_score = fcs; np.wid = cs.lastSeqId;
-						np.morpheme = cs.curId; np.parent = fc.inBeg + q; np.own_off = own ? fc.ownOff : 0; np.acc_typo_cost = pool[fc.inBeg + q].acc_typo_cost + fc.nodeTypoCost;
-						np.own_len = own ? (uint16_t)fc.ownLen : 0; np.node = (uint16_t)fc.nodeIdx;
-						np.left_last = own ? fc.ownLeftLast : cs.leftLast;
-						np.left_pol = own ? (uint8_t)(fc.ownLeftPol | (cs.leftPol & LP_MORPH_SOCKET)) : cs.leftPol;
-						np.sp_state = spState; np.root_id = rootId != COMMON_ROOT ? rootId : (uint8_t)prevRoot; np.combine_socket = cs.pathSocket; np.prev_root_id = (uint8_t)prevRoot;
-						np.morph_tag = (uint8_t)(cs.feat & MF_TAG_MASK);
+						np.lm_state = lmState; np.acc_score = accScore; np.acc_typo_cost = typoAcc + fc.nodeTypoCost;
 #if KB_CONG
 						P_CTX(np) = ctxIdx;
 #else
-						np.wid_feat = cs.lastSeqFeat;
+						np.wid_feat = cs->last_seq_feat;
 #endif
+						np.sp_state = spState; np.root_id = rootId != COMMON_ROOT ? rootId : (uint8_t)prevRoot; np.prev_root_id = (uint8_t)prevRoot; np.morph_tag = tag;
+						const uint32_t fwNew = cs->fw_new;
+						np.fw = (own ? (fc.ownFw | (fwNew & FW_MORPH_SOCKET) | fwOfTag(tag, cs->path_socket)) : fwNew) | (np.root_id == COMMON_ROOT ? (uint32_t)FW_COMMON_ROOT : 0u);
+						np.first_chunk_score = fcs; np.wid = cs->last_seq_id;
+						np.morpheme = csCurId; np.parent = fc.inBeg + q; np.own_off = own ? fc.ownOff : 0;
+						np.own_len = own ? (uint16_t)fc.ownLen : 0; np.node = (uint16_t)fc.nodeIdx;
 						pool[htBase + tgt] = np;
 					}
 				}
@@ -1139,14 +1103,14 @@ namespace KB_VIT_NS
 			htBase = top; htCount = 0;
 		}
 
-		// capacity + write-out order per candidate segment (see the comment above flushItems)
+		// capacity + write-out order per candidate segment (see the comment above stagePaths)
 		__device__ __noinline__ void fixupGroup(uint32_t groupBase, uint32_t gcount, uint32_t mode)
 		{
 			// is any fix-up needed at all?
 			bool need = false;
 			{
 				const uint32_t cnt = lane < gcount ? sm->candNew[lane] : 0;
-				const uint8_t cls = lane < gcount ? sm->cand[lane].cls : CLS_SKIP;
+				const uint8_t cls = lane < gcount ? sm->cdyn[lane].cls : CLS_SKIP;
 				need = mode != 2 && cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);     // the top1 container has neither buckets nor a capacity
 			}
 			if (!__any_sync(FULL, need)) return;
@@ -1157,7 +1121,7 @@ namespace KB_VIT_NS
 			{
 				const uint32_t cnt = sm->candNew[k];
 				if (!cnt) continue;
-				const bool fix = mode != 2 && sm->cand[k].cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);
+				const bool fix = mode != 2 && sm->cdyn[k].cls == CLS_ITEM && ((mode == 1 && cnt > 1) || cnt > 128);
 				if (!fix)
 				{
 					if (w != r)
@@ -1204,7 +1168,7 @@ namespace KB_VIT_NS
 				__syncwarp();
 				w += kept; r += cnt;
 			}
-			// every lane has read sm->cand / sm->candNew of this group: the caller overwrites them for the next group
+			// every lane has read sm->cdyn / sm->candNew of this group: the caller overwrites them for the next group
 			// (found by the 32-lane host simulation, tests/hostsim: a lane that leaves this loop early must not race ahead)
 			__syncwarp();
 			top = w;
@@ -1216,11 +1180,11 @@ namespace KB_VIT_NS
 		struct CongNode { uint32_t nOrdered, epFirst, nU; };
 
 		// (a) the node's unique context ids among the regular (non-socket) incoming paths -> sm->uctx / sm->pslot, and
-		//     (b) the candidates in evaluation order -> sm->candOrder: z_coda shortcut, z_siot shortcut, regular, left halves,
-		//     right halves (PathEvaluator.hpp:883-963, CoNgramModel.cpp:76-121); dropped candidates are left out.
+		//     (b) the candidates in evaluation order -> sm->candOrder (indices into the node's candidate block): z_coda shortcut,
+		//     z_siot shortcut, regular, left halves, right halves (PathEvaluator.hpp:883-963, CoNgramModel.cpp:76-121); dropped
+		//     candidates are left out.
 		//     The shape (unique contexts m, unique first wids n) of the node's gather GEMM selects the float epilogue.
-		__device__ __noinline__ CongNode congPrepare(const DNode& node, bool spaceBefore, const uint32_t* candList, uint32_t nCandsIn,
-			uint32_t unk0, uint32_t unk1, uint32_t inBeg, uint32_t P)
+		__device__ __noinline__ CongNode congPrepare(const DNode& node, bool spaceBefore, const DCand* candBase, uint32_t nCandsIn, uint32_t inBeg, uint32_t P)
 		{
 			CongNode cn; cn.nOrdered = 0; cn.epFirst = CG_E_SMALL; cn.nU = 0;
 			// ---- (a)
@@ -1230,7 +1194,7 @@ namespace KB_VIT_NS
 			{
 				const uint32_t q = qb + lane;
 				bool reg = false; uint32_t ctx = 0;
-				if (q < P) { const DPath* pth = pool + inBeg + q; reg = pth->combine_socket == 0; ctx = P_CTX(*pth); }
+				if (q < P) { const DPath* pth = pool + inBeg + q; reg = (pth->fw >> FW_SOCKET_SHIFT) == 0; ctx = P_CTX(*pth); }
 				unsigned rem = __ballot_sync(FULL, reg);
 				Preg += __popc(rem);
 				uint32_t mySlot = 0xFFu;
@@ -1268,38 +1232,19 @@ namespace KB_VIT_NS
 				uint32_t key = 7, fw = 0;
 				if (ci < nCandsIn)
 				{
-					const int32_t curId = (int32_t)(candList ? candList[ci] : (ci == 0 ? unk0 : unk1));
-					const DMorph cur = c_m.morphs[curId];
-					const uint32_t tag = cur.feat & MF_TAG_MASK;
-					const bool single = (cur.feat & MF_SINGLE) != 0;
-					bool drop = cur.nonstd_dialect != 0;
-					if (!drop && splitComplex)
-					{
-						if (c_m.morphs[curId + cur.combined].misc & MM_COMPLEX) drop = true;
-						for (uint32_t c = 0; c < cur.chunk_cnt && !drop; ++c) if (c_m.morphs[c_m.chunks[cur.chunk_off + c].morph].misc & MM_COMPLEX) drop = true;
-					}
+					const DCand* dc = candBase + ci;
+					const uint32_t kind = dc->kind;
+					bool drop = (kind & DK_DIALECT) || (splitComplex && (kind & DK_COMPLEX));
 					if (drop) key = 7;
-					else if (tag == T_z_coda) key = 0;
-					else if (tag == T_z_siot) key = 1;
+					else if (kind & DK_SHORTCUT_CODA) key = 0;
+					else if (kind & DK_SHORTCUT_SIOT) key = 1;
 					else
 					{
-						if (!single && node.prev && spaceBefore && cur.form_idx >= 0 && c_m.forms[cur.form_idx].str_len == 1)
-						{
-							const uint32_t k0 = c_m.form_chars[c_m.forms_raw[cur.form_idx].str_off];
-							if (k0 == 0xB2E4 || k0 == 0xAC8C || k0 == 0xC9C0)
-							{
-								const DMorph c0 = c_m.morphs[c_m.chunks[cur.chunk_off].morph];
-								if (c0.form_idx >= 0 && c_m.forms[c0.form_idx].str_len == 1 && c_m.form_chars[c_m.forms_raw[c0.form_idx].str_off] == 0xD558) drop = true;
-							}
-						}
+						if ((kind & DK_HA) && node.prev && spaceBefore) drop = true;
 						if (drop) key = 7;
-						else if (cur.combine_socket) key = single ? 3 : 4;
-						else
-						{
-							const DMorphX mx = c_m.morphx[curId];
-							if (mx.xflags & MX_FIRST_IS_P) key = 7;
-							else { key = 2; fw = mx.first_wid; }
-						}
+						else if (dc->cur_socket) key = (dc->flags & CS_SINGLE) ? 3 : 4;
+						else if (kind & DK_FIRST_IS_P) key = 7;
+						else { key = 2; fw = dc->first_wid; }
 					}
 				}
 				sm->item[ci < ITEM_CAP ? ci : 0] = ci < nCandsIn ? key : 7u;      // nCandsIn <= CG_CANDS <= ITEM_CAP
@@ -1331,7 +1276,7 @@ namespace KB_VIT_NS
 					if (k == 0 && take && (int32_t)ci != lastCoda) take = false;       // `zCodaMorph = curMorph`: the last one wins
 					if (k == 1 && take && (int32_t)ci != lastSiot) take = false;
 					const unsigned tm = __ballot_sync(FULL, take);
-					if (take) sm->candOrder[nOut + __popc(tm & ((1u << lane) - 1))] = candList ? candList[ci] : (ci == 0 ? unk0 : unk1);
+					if (take) sm->candOrder[nOut + __popc(tm & ((1u << lane) - 1))] = ci;
 					nOut += __popc(tm);
 				}
 			}
@@ -1345,9 +1290,92 @@ namespace KB_VIT_NS
 		__device__ __forceinline__ void congGroupDots(uint32_t nU, uint32_t colMask) { cgTileDots(sm->uctx, sm->colWid, sm->dots, nU, colMask, lane); }
 #endif
 
+		// ---- candidates that do not go through the item pipeline: the z_coda / z_siot shortcuts (PathEvaluator.hpp:389-432) and
+		// the per-candidate path evalCand (> 512 incoming paths, medium-mode forks, class-table overflow).  Cold: kept out of line.
+		struct GenCtx
+		{
+			uint32_t nodeIdx, inBeg, inEnd, mode, ownOff, ownLen, ownFw; float ignoreCondScore; bool spaceBefore;
+#if KB_CONG
+			uint32_t epFirst; int32_t dotCol;
+#endif
+		};
+		__device__ __noinline__ void evalGeneralCand(uint32_t k, const DNode& node, const GenCtx& g)
+		{
+			const uint32_t P = g.inEnd - g.inBeg, inBeg = g.inBeg;
+			const DCand dk = sm->dcand[k];
+			const CandDyn cd = sm->cdyn[k];
+			const int32_t curId = dk.cur_id;
+			const DMorph cur = c_m.morphs[curId];
+			const uint32_t tag = cur.feat & MF_TAG_MASK;
+			if (cd.cls == CLS_SHORTCUT)
+			{
+				// shortcut (PathEvaluator.hpp:389-432): copy qualifying incoming paths, no LM step
+				const float add = cur.user_score * c_m.cfg.typo_cost_weight;
+				const DMorph lmM = c_m.morphs[cur.lm_id];
+				#pragma unroll 1
+				for (uint32_t qb = 0; qb < P; qb += 32)
+				{
+					const uint32_t q = qb + lane;
+					DPath p; bool ok = false;
+					if (q < P)
+					{
+						p = pool[inBeg + q];
+						const uint32_t lastTag = P_WID_FEAT(p) & MF_TAG_MASK;
+						ok = tag == T_z_coda ? (isJClass((uint8_t)lastTag) || isEClass((uint8_t)lastTag)) : isNNClass((uint8_t)lastTag);
+					}
+					const unsigned om = __ballot_sync(FULL, ok);
+					if (top + __popc(om) > poolCap) { err = ST_PATH_OVERFLOW; return; }
+					if (ok)
+					{
+						DPath np = p;
+						np.acc_score += add;
+						np.acc_typo_cost -= cur.user_score;
+						np.parent = inBeg + q;
+						np.morpheme = (int32_t)cur.lm_id;
+						np.wid = cur.lm_id;
+						np.node = (uint16_t)g.nodeIdx;
+						np.morph_tag = (uint8_t)(lmM.feat & MF_TAG_MASK);
+#if !KB_CONG
+						np.wid_feat = lmM.feat;
+#endif
+						uint16_t ll; uint8_t lp;
+						leftFeat(np.own_len ? np.own_off : 0, np.own_len, np.wid, np.morpheme, ll, lp);
+						if (lmM.combine_socket) lp |= LP_MORPH_SOCKET;
+						np.fw = fwOfLeft(ll, lp) | fwOfTag(np.morph_tag, (uint8_t)(p.fw >> FW_SOCKET_SHIFT)) | (p.fw & FW_COMMON_ROOT);
+						pool[top + __popc(om & ((1u << lane) - 1))] = np;
+					}
+					top += __popc(om);
+				}
+				__syncwarp();
+				return;
+			}
+			const bool single = (cur.feat & MF_SINGLE) != 0;
+			CandCtx cc;
+			cc.curId = curId; cc.cur = cur; cc.single = single;
+			cc.firstWid0 = dk.first_wid; cc.lastSeqId = dk.last_seq_id;
+			cc.additionalScore = cd.additionalScore;
+			cc.ignoreCondScore = g.ignoreCondScore;
+			cc.specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7;
+			cc.sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
+			cc.sbOrder = cc.sbType ? cur.sense_id : 0;
+			cc.positiveE = (cd.flags & CS_POSITIVE_E) != 0;
+			cc.snEndswithPoint = (cd.flags & CS_SN_POINT) != 0;
+			cc.fork = (cd.flags & CS_FORK) != 0;
+			cc.ownOff = g.ownOff; cc.ownLen = g.ownLen;
+			cc.spaceBefore = g.spaceBefore;
+			cc.morphTag = (uint8_t)tag;
+			cc.widFeat = dk.last_seq_feat;
+			const bool own = single && g.ownLen;
+			cc.fwNew = own ? (g.ownFw | (dk.fw_new & FW_MORPH_SOCKET) | fwOfTag((uint8_t)tag, dk.path_socket)) : dk.fw_new;
+#if KB_CONG
+			cc.epFirst = g.epFirst; cc.dotCol = g.dotCol;
+#endif
+			evalCand(g.nodeIdx, node, cc, g.inBeg, g.inEnd, g.mode);
+		}
+
 		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
-		// cands: either a form's candidate list (formCands != nullptr) or the default unknown candidates
-		__device__ __noinline__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const uint32_t* candList, uint32_t nCandsIn, uint32_t unk0, uint32_t unk1,
+		// candBase: the node's static candidate rows (a form's block of c_m.cands, or the unknown NNG / NNP rows)
+		__device__ __noinline__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const DCand* candBase, uint32_t nCandsIn,
 			float unkFormDiscount, uint32_t ownOff, uint32_t ownLen, uint32_t inBeg, uint32_t inEnd)
 		{
 			const DNode node = nodes[nodeIdx];
@@ -1365,7 +1393,7 @@ namespace KB_VIT_NS
 #define KB_CONG_PIPELINE 1
 #endif
 			const bool itemOK = KB_CONG_PIPELINE && P <= STAGE_CAP;      // else every candidate goes through evalCand; always in the transposed evaluator's order
-			const CongNode cgn = congPrepare(node, spaceBefore, candList, nCandsIn, unk0, unk1, inBeg, P);
+			const CongNode cgn = congPrepare(node, spaceBefore, candBase, nCandsIn, inBeg, P);
 			if (err) return;
 			const uint32_t nCands = cgn.nOrdered;
 #else
@@ -1373,13 +1401,13 @@ namespace KB_VIT_NS
 			const uint32_t nCands = nCandsIn;
 #endif
 			FlushCtx fc;
-			fc.nodeIdx = nodeIdx; fc.inBeg = inBeg; fc.nodeTypoCost = node.typo_cost; fc.ownOff = ownOff; fc.ownLen = ownLen; fc.ownLeftLast = 0; fc.ownLeftPol = 0;
+			fc.nodeIdx = nodeIdx; fc.inBeg = inBeg; fc.nodeTypoCost = node.typo_cost; fc.ownOff = ownOff; fc.ownLen = ownLen; fc.ownFw = 0;
 			if (itemOK) stagePaths(nodeIdx, inBeg, P);
 			const bool itemOK2 = itemOK && !classOverflow;
-			if (ownLen) leftFeat(ownOff, ownLen, 0, 0, fc.ownLeftLast, fc.ownLeftPol);
+			if (ownLen) { uint16_t ol; uint8_t op; leftFeat(ownOff, ownLen, 0, 0, ol, op); fc.ownFw = fwOfLeft(ol, op); }
 			nItems = 0;
-			const bool posE = node.form >= 0 && (c_m.forms[node.form].flags & FF_FIRST_IS_A);
 			const bool snPoint = node.uform_len && norm[node.uform_off + node.uform_len - 1] == '.';
+			const uint32_t nWords = (P + 31) >> 5;
 
 			#pragma unroll 1
 			for (int ignoreCond = 0; ignoreCond < 2; ++ignoreCond)
@@ -1389,84 +1417,59 @@ namespace KB_VIT_NS
 				for (uint32_t gb = 0; gb < nCands; gb += GROUP)
 				{
 					const uint32_t gcount = min(GROUP, nCands - gb);
-					// ---- classification, one lane per candidate (PathEvaluator.hpp:382-448 + evalSingleMorpheme head 531-560)
-					uint32_t myCls = CLS_SKIP, myValid = 0, myCondFail = 0, mySets = 0, myFlags = 0;
+					// ---- classification, one lane per candidate (PathEvaluator.hpp:382-448 + evalSingleMorpheme head 531-560), from the static rows
+					uint32_t myPack = CLS_SKIP, myValid = 0, myCondFail = 0, mySets = 0;
 					{
-						uint8_t cls = CLS_SKIP;
-						CandS cs;
-						cs.curId = 0; cs.firstWid = 0; cs.lastSeqId = 0; cs.feat = 0; cs.lastSeqFeat = 0; cs.chunkOff = 0; cs.additionalScore = 0; cs.leftLast = 0; cs.leftPol = 0;
-						cs.chunkCnt = 0; cs.flags = 0; cs.pathSocket = 0; cs.senseId = 0;
+						uint8_t cls = CLS_SKIP, flags = 0;
+						float additionalScore = 0;
+						uint32_t feat = 0, kind = 0, curSocket = 0;
 						if (lane < gcount)
 						{
 #if KB_CONG
-							const int32_t curId = (int32_t)sm->candOrder[gb + lane];
+							const DCand* src = candBase + sm->candOrder[gb + lane];
 #else
-							const int32_t curId = (int32_t)(candList ? candList[gb + lane] : (lane == 0 ? unk0 : unk1));
+							const DCand* src = candBase + gb + lane;
 #endif
-							const DMorph cur = c_m.morphs[curId];
-							const uint32_t tag = cur.feat & MF_TAG_MASK;
-							const bool single = (cur.feat & MF_SINGLE) != 0;
-							bool skip = cur.nonstd_dialect != 0;
-							if (!skip && splitComplex)
+							const uint4 r0 = reinterpret_cast<const uint4*>(src)[0], r1 = reinterpret_cast<const uint4*>(src)[1], r2 = reinterpret_cast<const uint4*>(src)[2];
+							uint4* dst = reinterpret_cast<uint4*>(&sm->dcand[lane]);
+							dst[0] = r0; dst[1] = r1; dst[2] = r2;
+							feat = r1.x;
+							flags = (uint8_t)(r2.x >> 8); curSocket = r2.y & 0xFF; kind = (r2.y >> 8) & 0xFF;
+							const uint32_t tagClean = (r2.y >> 16) & 0xFF;
+							bool skip = (kind & DK_DIALECT) || (splitComplex && (kind & DK_COMPLEX));
+							if (!skip && (kind & (DK_SHORTCUT_CODA | DK_SHORTCUT_SIOT)))
 							{
-								if (c_m.morphs[curId + cur.combined].misc & MM_COMPLEX) skip = true;
-								for (uint32_t c = 0; c < cur.chunk_cnt && !skip; ++c) if (c_m.morphs[c_m.chunks[cur.chunk_off + c].morph].misc & MM_COMPLEX) skip = true;
-							}
-							if (!skip && (tag == T_z_coda || tag == T_z_siot))
-							{
-								if (tag == T_z_siot && !(splitSaisiot || mergeSaisiot)) skip = true;
+								if ((kind & DK_SHORTCUT_SIOT) && !(splitSaisiot || mergeSaisiot)) skip = true;
 								else cls = CLS_SHORTCUT;
 							}
 							else if (!skip)
 							{
-								if (!single && node.prev && spaceBefore && cur.form_idx >= 0 && c_m.forms[cur.form_idx].str_len == 1)
-								{
-									// contracted '하다/하게/하지' after a space is not a candidate (PathEvaluator.hpp:435-448)
-									const uint32_t k0 = c_m.form_chars[c_m.forms_raw[cur.form_idx].str_off];
-									if (k0 == 0xB2E4 || k0 == 0xAC8C || k0 == 0xC9C0)
-									{
-										const DMorph c0 = c_m.morphs[c_m.chunks[cur.chunk_off].morph];
-										if (c0.form_idx >= 0 && c_m.forms[c0.form_idx].str_len == 1 && c_m.form_chars[c_m.forms_raw[c0.form_idx].str_off] == 0xD558) skip = true;
-									}
-								}
+								// contracted '하다/하게/하지' after a space is not a candidate (PathEvaluator.hpp:435-448)
+								if ((kind & DK_HA) && node.prev && spaceBefore) skip = true;
 								if (!skip)
 								{
-									const uint32_t specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7, sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
-									const bool fork = sbType != 0 || specialType == 0 || specialType == 1 || specialType == 3 || specialType == 4;
-									const bool socketChunk = cur.combine_socket && !single;
-									const DMorphX mx = c_m.morphx[curId];
-									const bool noLm = cur.combine_socket && single;
+									const bool fork = (flags & CS_FORK) != 0, socketChunk = (flags & CS_SOCKET_CHUNK) != 0, noLm = (flags & CS_NO_LM) != 0;
 									// a forking candidate creates up to 2 entries per path; medium-mode forks keep the bucket-aware general path
 									if (!itemOK2 || (mode == 1 && fork) || (mode == 2 && (fork ? 2 * P : P) > HT_MAX_ENTRIES)) cls = CLS_GENERAL;
-									else if (!noLm && !socketChunk && (mx.xflags & (MX_FIRST_IS_P | MX_CHUNK_HAS_P))) cls = CLS_SKIP;     // every pair hits `goto continueFor`
-									else if (socketChunk && (mx.xflags & MX_CHUNK_HAS_P)) cls = CLS_SKIP;
+									else if (!noLm && !socketChunk && (kind & (DK_FIRST_IS_P | DK_CHUNK_HAS_P))) cls = CLS_SKIP;     // every pair hits `goto continueFor`
+									else if (socketChunk && (kind & DK_CHUNK_HAS_P)) cls = CLS_SKIP;
 									else cls = CLS_ITEM;
-									cs.firstWid = mx.first_wid; cs.lastSeqId = mx.last_seq_id; cs.lastSeqFeat = mx.last_seq_feat; cs.leftLast = mx.left_last; cs.leftPol = mx.left_pol;
-									uint8_t fl = 0;
-									if (isEClass((uint8_t)tag) && posE) fl |= CS_POSITIVE_E;
-									if (tag == T_sn && snPoint) fl |= CS_SN_POINT;
-									if (single) fl |= CS_SINGLE;
-									if (noLm) fl |= CS_NO_LM;
-									if (fork) fl |= CS_FORK;
-									if (socketChunk) fl |= CS_SOCKET_CHUNK;
-									cs.flags = fl; cs.pathSocket = single ? cur.combine_socket : 0;
+									if ((kind & DK_IS_SN) && snPoint) flags |= CS_SN_POINT;
 								}
 							}
-							cs.curId = curId; cs.feat = cur.feat; cs.chunkOff = cur.chunk_off; cs.chunkCnt = cur.chunk_cnt; cs.senseId = cur.sense_id;
-							cs.additionalScore = cur.user_score + nodeLevelDiscount + c_m.tag_left_boundary[hasLB ? 1 : 0][clearIrregular((uint8_t)tag)];
+							additionalScore = __uint_as_float(r1.y) + nodeLevelDiscount + c_m.tag_left_boundary[hasLB ? 1 : 0][tagClean];
 						}
-						cs.cls = cls;
-						sm->cand[lane] = cs;
+						CandDyn cd; cd.additionalScore = additionalScore; cd.flags = flags; cd.cls = cls; cd.pad0 = 0; cd.pad1 = 0;
+						sm->cdyn[lane] = cd;
 						sm->candNew[lane] = 0;
 						// which path classes pass this candidate's filter (PathEvaluator.hpp:566-594), decided once per class
 						CandMask cm; cm.valid = 0; cm.condFail = 0; cm.sets = 0;
 						if (cls == CLS_ITEM)
 						{
-							const uint32_t curTag = cs.feat & MF_TAG_MASK;
-							const uint32_t cv = (cs.feat >> MF_VOWEL_SHIFT) & 15, cp = (cs.feat >> MF_POLAR_SHIFT) & 3;
+							const uint32_t curTag = feat & MF_TAG_MASK;
+							const uint32_t cv = (feat >> MF_VOWEL_SHIFT) & 15, cp = (feat >> MF_POLAR_SHIFT) & 3;
 							const bool curNN = isNNClass((uint8_t)curTag);
-							const bool socketChunk = (cs.flags & CS_SOCKET_CHUNK) != 0;
-							const uint32_t curSocket = c_m.morphs[cs.curId].combine_socket;
+							const bool socketChunk = (flags & CS_SOCKET_CHUNK) != 0;
 							for (uint32_t c = 0; c < nClasses; ++c)
 							{
 								const uint32_t f = sm->fclass[c];
@@ -1499,19 +1502,19 @@ namespace KB_VIT_NS
 							}
 							// prohibit <v> without <chunk> (PathEvaluator.hpp:603-607): a socket chunk whose first wid is the tag-P
 							// placeholder only survives behind a path that overrides firstWid; without such a path nothing survives
-							if (socketChunk && !cm.sets && (c_m.morphx[cs.curId].xflags & MX_FIRST_IS_P)) cm.valid = 0;
+							if (socketChunk && !cm.sets && (kind & DK_FIRST_IS_P)) cm.valid = 0;
 						}
 						sm->cmask[lane] = cm;
-						myCls = cls; myValid = cm.valid; myCondFail = cm.condFail; mySets = cm.sets; myFlags = cs.flags;
+						myPack = cls | ((uint32_t)flags << 8); myValid = cm.valid; myCondFail = cm.condFail; mySets = cm.sets;
 					}
 					__syncwarp();
 #if KB_CONG
 					// tensor-core tile for the regular candidates of this group
 					uint32_t dotMask = 0;
 					{
-						const CandS csl = sm->cand[lane];
-						const bool regular = lane < gcount && (csl.cls == CLS_GENERAL || csl.cls == CLS_ITEM) && c_m.morphs[csl.curId].combine_socket == 0 && !(c_m.morphx[csl.curId].xflags & MX_FIRST_IS_P);
-						sm->colWid[lane] = csl.firstWid;
+						const CandDyn cdl = sm->cdyn[lane];
+						const bool regular = lane < gcount && (cdl.cls == CLS_GENERAL || cdl.cls == CLS_ITEM) && sm->dcand[lane].cur_socket == 0 && !(sm->dcand[lane].kind & DK_FIRST_IS_P);
+						sm->colWid[lane] = lane < gcount ? sm->dcand[lane].first_wid : 0u;
 						dotMask = __ballot_sync(FULL, regular);
 						__syncwarp();
 						if (dotMask && cgn.nU && cgn.epFirst != CG_E_SCALAR) congGroupDots(cgn.nU, dotMask);
@@ -1527,62 +1530,42 @@ namespace KB_VIT_NS
 					#pragma unroll 1
 					for (uint32_t k = 0; k < gcount; ++k)
 					{
-						const uint32_t cls = __shfl_sync(FULL, myCls, k);
+						const uint32_t packK = __shfl_sync(FULL, myPack, k);
+						const uint32_t cls = packK & 0xFF, kfl = packK >> 8;
 						if (cls == CLS_SKIP) continue;
 						if (cls == CLS_ITEM)
 						{
-							const uint32_t vmK = __shfl_sync(FULL, myValid, k), cfK = __shfl_sync(FULL, myCondFail, k), setsK = __shfl_sync(FULL, mySets, k);
-							const uint32_t kfl = __shfl_sync(FULL, myFlags, k);
+							const uint32_t vmK = __shfl_sync(FULL, myValid, k), setsK = __shfl_sync(FULL, mySets, k);
 							if (!(vmK | setsK)) continue;
+							const uint32_t cfK = __shfl_sync(FULL, myCondFail, k);
 							// the entry index is shared by consecutive candidates while it is small; a top1-mode candidate (up to P entries) starts with an empty one
 							if (mode == 2 ? (htCount | nItems) != 0 : htCount + nItems > 256) { flushItems(fc); if (err) return; resetIndex(); }
 							if (!(kfl & CS_FORK) && !setsK)
 							{
-								// common case: survivors = union of the path bitmaps of the valid classes, enumerated in path order,
-								// 512 paths (16 bitmap words = one item buffer) at a time
-								const uint32_t nWtot = (P + 31) >> 5;
+								// common case: the survivors of every 32 incoming paths are compacted by one ballot, in path order
 								#pragma unroll 1
-								for (uint32_t wt = 0; wt < nWtot; wt += TILE_W)
+								for (uint32_t w = 0; w < nWords; ++w)
 								{
-									const uint32_t nW = min(TILE_W, nWtot - wt);
-									uint32_t bits = 0;
-									if (lane < nW) { uint32_t mm = vmK; while (mm) { const uint32_t c = __ffs(mm) - 1; bits |= sm->classBits[c][wt + lane]; mm &= mm - 1; } }
-									const uint32_t cnt = __popc(bits);
-									uint32_t incl = cnt;
-									if (nW > 1) { for (int d = 1; d < 16; d <<= 1) { const uint32_t tt = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += tt; } }
-									const uint32_t S = __shfl_sync(FULL, incl, nW - 1);
-									if (!S) continue;
-									if (nItems + S > ITEM_CAP) { flushItems(fc); if (err) return; }
-									const uint32_t excl = incl - cnt;
-									#pragma unroll 1
-									for (uint32_t wd = 0; wd < nW; ++wd)
-									{
-										const uint32_t wb = __shfl_sync(FULL, bits, wd);
-										if (!wb) continue;
-										const uint32_t base = __shfl_sync(FULL, excl, wd);
-										if ((wb >> lane) & 1)
-										{
-											const uint32_t q = ((wt + wd) << 5) | lane;
-											const uint32_t c = sm->pcls[q];
-											sm->item[nItems + base + __popc(wb & ((1u << lane) - 1))] = (k << 27) | (q << 3) | ((cfK >> c) & 1);
-										}
-									}
-									nItems += S;
-									__syncwarp();
+									const uint32_t q = (w << 5) | lane;
+									const uint32_t c = q < P ? sm->pcls[q] : 31u;
+									const bool on = q < P && ((vmK >> c) & 1u);
+									const unsigned m = __ballot_sync(FULL, on);
+									if (!m) continue;
+									const uint32_t cnt = __popc(m);
+									if (nItems + cnt > ITEM_CAP) { flushItems(fc); if (err) return; }
+									if (on) sm->item[nItems + __popc(m & ((1u << lane) - 1))] = (k << 27) | (q << 3) | ((cfK >> c) & 1u);
+									nItems += cnt;
 								}
 								continue;
 							}
 							// filter pass (PathEvaluator.hpp:566-594): lanes = (path, root) pairs in order; the per-pair work is a
 							// table lookup because the decision only depends on (candidate, path class)
-							const CandMask cmk = sm->cmask[k];
-							if (!(cmk.valid | cmk.sets)) continue;
-							const uint8_t kflags = sm->cand[k].flags;
-							const bool fork = (kflags & CS_FORK) != 0, socketChunk = (kflags & CS_SOCKET_CHUNK) != 0;
+							const bool fork = (kfl & CS_FORK) != 0, socketChunk = (kfl & CS_SOCKET_CHUNK) != 0;
 							const uint32_t rshift = (fork && nUniq == 2) ? 1 : 0;
 							const uint32_t perRound = 32u >> rshift;
 							const bool spacePen = socketChunk && spaceBefore;          // only socket matches survive `spaceBefore` (with tolerance) and they pay the penalty
 							uint32_t fwCarry = 0;                     // index into fwTab of the inherited first-wid override, 0 = none
-							const bool firstIsP = socketChunk && (c_m.morphx[sm->cand[k].curId].xflags & MX_FIRST_IS_P) != 0;
+							const bool firstIsP = socketChunk && (sm->dcand[k].kind & DK_FIRST_IS_P) != 0;
 							#pragma unroll 1
 							for (uint32_t qb = 0; qb < P; qb += perRound)
 							{
@@ -1593,14 +1576,14 @@ namespace KB_VIT_NS
 								if (q < P)
 								{
 									const uint32_t c = sm->pcls[q];
-									valid = (cmk.valid >> c) & 1;
-									condFail = (cmk.condFail >> c) & 1;
-									setsFW = (cmk.sets >> c) & 1;
+									valid = (vmK >> c) & 1;
+									condFail = (cfK >> c) & 1;
+									setsFW = (setsK >> c) & 1;
 									isSock = setsFW;
 									if (rr != 0 && !((classCommon >> c) & 1)) valid = false;      // only common-root paths fork over the root states
 								}
 								uint32_t fwIdx = 0;
-								if (cmk.sets)
+								if (setsK)
 								{
 									// the reference overwrites `firstWid` in place: every later pair inherits the latest override
 									const unsigned smask = __ballot_sync(FULL, setsFW);
@@ -1645,80 +1628,14 @@ namespace KB_VIT_NS
 						// general path and shortcuts: drain the pipeline first so that entries stay candidate-major
 						flushItems(fc); if (err) return;
 						const uint32_t before = top;
-						const int32_t curId = sm->cand[k].curId;
-						const DMorph cur = c_m.morphs[curId];
-						const uint32_t tag = cur.feat & MF_TAG_MASK;
-						if (cls == CLS_SHORTCUT)
-						{
-							// shortcut (PathEvaluator.hpp:389-432): copy qualifying incoming paths, no LM step
-							const float add = cur.user_score * c_m.cfg.typo_cost_weight;
-							const DMorph lmM = c_m.morphs[cur.lm_id];
-							#pragma unroll 1
-							for (uint32_t qb = 0; qb < P; qb += 32)
-							{
-								const uint32_t q = qb + lane;
-								DPath p; bool ok = false;
-								if (q < P)
-								{
-									p = pool[inBeg + q];
-									const uint32_t lastTag = P_WID_FEAT(p) & MF_TAG_MASK;
-									ok = tag == T_z_coda ? (isJClass((uint8_t)lastTag) || isEClass((uint8_t)lastTag)) : isNNClass((uint8_t)lastTag);
-								}
-								const unsigned om = __ballot_sync(FULL, ok);
-								if (top + __popc(om) > poolCap) { err = ST_PATH_OVERFLOW; return; }
-								if (ok)
-								{
-									DPath np = p;
-									np.acc_score += add;
-									np.acc_typo_cost -= cur.user_score;
-									np.parent = inBeg + q;
-									np.morpheme = (int32_t)cur.lm_id;
-									np.wid = cur.lm_id;
-									np.node = (uint16_t)nodeIdx;
-									np.morph_tag = (uint8_t)(lmM.feat & MF_TAG_MASK);
-#if !KB_CONG
-									np.wid_feat = lmM.feat;
-#endif
-									uint16_t ll; uint8_t lp;
-									leftFeat(np.own_len ? np.own_off : 0, np.own_len, np.wid, np.morpheme, ll, lp);
-									if (lmM.combine_socket) lp |= LP_MORPH_SOCKET;
-									np.left_last = ll; np.left_pol = lp;
-									pool[top + __popc(om & ((1u << lane) - 1))] = np;
-								}
-								top += __popc(om);
-							}
-							__syncwarp();
-						}
-						else
-						{
-							const bool single = (cur.feat & MF_SINGLE) != 0;
-							const CandS csk = sm->cand[k];
-							CandCtx cc;
-							cc.curId = curId; cc.cur = cur; cc.single = single;
-							cc.firstWid0 = csk.firstWid; cc.lastSeqId = csk.lastSeqId;
-							cc.additionalScore = csk.additionalScore;
-							cc.ignoreCondScore = fc.ignoreCondScore;
-							cc.specialType = (cur.feat >> MF_SPECIAL_SHIFT) & 7;
-							cc.sbType = (cur.feat >> MF_SBTYPE_SHIFT) & 31;
-							cc.sbOrder = cc.sbType ? cur.sense_id : 0;
-							cc.positiveE = (csk.flags & CS_POSITIVE_E) != 0;
-							cc.snEndswithPoint = (csk.flags & CS_SN_POINT) != 0;
-							cc.fork = (csk.flags & CS_FORK) != 0;
-							cc.ownOff = ownOff; cc.ownLen = ownLen;
-							cc.spaceBefore = spaceBefore;
-							cc.morphTag = (uint8_t)tag;
-							cc.widFeat = csk.lastSeqFeat;
-							cc.pathSocket = csk.pathSocket;
-							const bool own = single && ownLen;
-							cc.leftLast = own ? fc.ownLeftLast : csk.leftLast;
-							cc.leftPol = own ? (uint8_t)(fc.ownLeftPol | (csk.leftPol & LP_MORPH_SOCKET)) : csk.leftPol;
+						GenCtx g;
+						g.nodeIdx = nodeIdx; g.inBeg = inBeg; g.inEnd = inEnd; g.mode = mode; g.ownOff = ownOff; g.ownLen = ownLen; g.ownFw = fc.ownFw;
+						g.ignoreCondScore = fc.ignoreCondScore; g.spaceBefore = spaceBefore;
 #if KB_CONG
-							cc.epFirst = cgn.epFirst;
-							cc.dotCol = ((dotMask >> k) & 1u) ? (int32_t)k : -1;
+						g.epFirst = cgn.epFirst; g.dotCol = ((dotMask >> k) & 1u) ? (int32_t)k : -1;
 #endif
-							evalCand(nodeIdx, node, cc, inBeg, inEnd, mode);
-							if (err) return;
-						}
+						evalGeneralCand(k, node, g);
+						if (err) return;
 						if (lane == 0) sm->candNew[k] = top - before;
 						__syncwarp();
 						resetIndex();
@@ -1729,44 +1646,58 @@ namespace KB_VIT_NS
 				if (top > nodeBeg) break;
 			}
 
-			// prune (PathEvaluator.hpp:475-511)
-			float mx[3] = { -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F };
+			// prune (PathEvaluator.hpp:475-511): per root slot the best score of the paths whose morpheme has no combine socket;
+			// scores are compared as order-preserving unsigned keys, the threshold test itself stays a float comparison
 			const uint32_t cntAll = top - nodeBeg;
+			const uint32_t NEG_INF_ORD = 0x007FFFFFu;      // key of -inf
+			uint32_t mxo0 = NEG_INF_ORD, mxo1 = NEG_INF_ORD, mxo2 = NEG_INF_ORD;
+			#pragma unroll 1
 			for (uint32_t eb = 0; eb < cntAll; eb += 32)
 			{
 				const uint32_t e = eb + lane;
-				float sc = -CUDART_INF_F; uint32_t slot = 0;
+				uint32_t o = 0, slot = 3;
 				if (e < cntAll)
 				{
 					const DPath* p = pool + nodeBeg + e;
-					if (!(p->left_pol & LP_MORPH_SOCKET)) sc = p->acc_score;
-					slot = p->root_id == COMMON_ROOT ? 0 : p->root_id + 1;
+					const uint32_t meta = *reinterpret_cast<const uint32_t*>(&p->sp_state);
+					const uint32_t root = (meta >> 8) & 0xFF;
+					slot = root == COMMON_ROOT ? 0 : root + 1;
+					o = NEG_INF_ORD;
+					if (!(p->fw & FW_MORPH_SOCKET)) { const uint32_t u = __float_as_uint(p->acc_score); o = (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 				}
-#pragma unroll
-				for (uint32_t k = 0; k < 3; ++k)
-				{
-					float v = slot == k ? sc : -CUDART_INF_F;
-					for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, d));
-					mx[k] = fmaxf(mx[k], v);
-				}
+				mxo0 = max(mxo0, __reduce_max_sync(FULL, slot == 0 ? o : 0u));
+				if (nUniq > 0) mxo1 = max(mxo1, __reduce_max_sync(FULL, slot == 1 ? o : 0u));
+				if (nUniq > 1) mxo2 = max(mxo2, __reduce_max_sync(FULL, slot == 2 ? o : 0u));
 			}
+			const float mx0 = __uint_as_float((mxo0 & 0x80000000u) ? (mxo0 ^ 0x80000000u) : ~mxo0);
+			const float mx1 = __uint_as_float((mxo1 & 0x80000000u) ? (mxo1 ^ 0x80000000u) : ~mxo1);
+			const float mx2 = __uint_as_float((mxo2 & 0x80000000u) ? (mxo2 ^ 0x80000000u) : ~mxo2);
 			uint32_t valid = 0;
+			#pragma unroll 1
 			for (uint32_t eb = 0; eb < cntAll; eb += 32)
 			{
 				const uint32_t e = eb + lane;
-				DPath p; bool keep = false;
+				bool keep = false;
 				if (e < cntAll)
 				{
-					p = pool[nodeBeg + e];
-					const uint32_t slot = p.root_id == COMMON_ROOT ? 0 : p.root_id + 1;
-					const float mxs = slot == 0 ? mx[0] : (slot == 1 ? mx[1] : mx[2]);
-					keep = !(p.acc_score + c_m.cfg.cut_off_threshold < mxs);
+					const DPath* p = pool + nodeBeg + e;
+					const uint32_t root = p->root_id;
+					const float mxs = root == COMMON_ROOT ? mx0 : (root == 0 ? mx1 : mx2);
+					keep = !(p->acc_score + c_m.cfg.cut_off_threshold < mxs);
 				}
 				const unsigned km = __ballot_sync(FULL, keep);
-				__syncwarp();
-				if (keep) pool[nodeBeg + valid + __popc(km & ((1u << lane) - 1))] = p;
+				const uint32_t dst = valid + __popc(km & ((1u << lane) - 1));
+				const uint32_t remE = cntAll - eb;
+				if (valid != eb || km != (remE >= 32 ? FULL : ((1u << remE) - 1)))
+				{
+					// something was dropped at or before this round: move the survivors down (read all, then write)
+					uint4 a, b, c;
+					if (keep) { const uint4* sp = reinterpret_cast<const uint4*>(pool + nodeBeg + e); a = sp[0]; b = sp[1]; c = sp[2]; }
+					__syncwarp();
+					if (keep && dst != e) { uint4* dp = reinterpret_cast<uint4*>(pool + nodeBeg + dst); dp[0] = a; dp[1] = b; dp[2] = c; }
+					__syncwarp();
+				}
 				valid += __popc(km);
-				__syncwarp();
 			}
 			top = nodeBeg + valid;
 		}
@@ -1802,7 +1733,7 @@ namespace KB_VIT_NS
 			for (uint32_t eb = beg; eb < end; eb += 32)
 			{
 				const uint32_t e = eb + lane;
-				const bool ok = e < end && pool[e].combine_socket == 0;
+				const bool ok = e < end && (pool[e].fw >> FW_SOCKET_SHIFT) == 0;
 				if (__any_sync(FULL, ok)) { any = true; break; }
 			}
 			return any;
@@ -1834,7 +1765,7 @@ namespace KB_VIT_NS
 				b.lm_state = c_m.kn_bos_node;
 #endif
 				b.acc_score = 0; b.first_chunk_score = 0; b.wid = 0; b.morpheme = 0; b.parent = NPOS; b.own_off = 0; b.acc_typo_cost = 0;
-				b.own_len = 0; b.node = 0; b.sp_state = 0; b.root_id = COMMON_ROOT; b.combine_socket = 0; b.prev_root_id = 0;
+				b.own_len = 0; b.node = 0; b.sp_state = 0; b.root_id = COMMON_ROOT; b.prev_root_id = 0;
 				const DMorph m0 = c_m.morphs[0];
 				b.morph_tag = (uint8_t)(m0.feat & MF_TAG_MASK);
 #if KB_CONG
@@ -1844,14 +1775,13 @@ namespace KB_VIT_NS
 #endif
 				uint16_t ll; uint8_t lp;
 				leftFeat(0, 0, 0, 0, ll, lp);
-				b.left_last = ll; b.left_pol = lp;
+				b.fw = fwOfLeft(ll, lp) | fwOfTag(b.morph_tag, 0) | FW_COMMON_ROOT;
 				pool[top] = b;
 				npOff[0] = top; npCnt[0] = 1; reach[0] = 1;
 			}
 			for (uint32_t i = lane + 1; i < N; i += 32) reach[i] = 0;
 			top += 1;
 			__syncwarp();
-			const uint32_t unkNNG = T_nng + 1u, unkNNP = T_nnp + 1u;     // getDefaultMorphemeId, Kiwi.h:64-67
 
 			for (uint32_t i = 1; i + 1 < N; ++i)
 			{
@@ -1862,13 +1792,13 @@ namespace KB_VIT_NS
 				if (node.form >= 0)
 				{
 					const DForm f = c_m.forms[node.form];
-					evaluate(i, nodeBeg, c_m.form_cands + f.cand_off, f.cand_cnt, 0, 0, 0.f, node.uform_off, node.uform_len, inBeg, inEnd);
+					evaluate(i, nodeBeg, c_m.cands + f.cand_off, f.cand_cnt, 0.f, node.uform_off, node.uform_len, inBeg, inEnd);
 					if (err) return 0;
 					if (node.typo_cost == 0.f && (f.flags & FF_ALL_PARTIAL))
 					{
 						const uint16_t* fs = c_m.form_chars + c_m.forms_raw[node.form].str_off;
 						const float unkScore = unkFormScore(fs, f.str_len);
-						evaluate(i, nodeBeg, nullptr, 1, unkNNP, 0, unkScore, ~(uint32_t)node.form, f.str_len, inBeg, inEnd);
+						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk + 1, 1, unkScore, ~(uint32_t)node.form, f.str_len, inBeg, inEnd);
 						if (err) return 0;
 					}
 					const bool r = anyNonSocket(nodeBeg, top);
@@ -1878,14 +1808,14 @@ namespace KB_VIT_NS
 					{
 						const uint32_t len = node.end_pos - node.start_pos;
 						const float unkScore = unkFormScore(norm + node.start_pos, len);
-						evaluate(i, nodeBeg, nullptr, 2, unkNNG, unkNNP, unkScore, node.start_pos, len, inBeg, inEnd);
+						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.start_pos, len, inBeg, inEnd);
 						if (err) return 0;
 					}
 				}
 				else
 				{
 					const float unkScore = unkFormScore(norm + node.uform_off, node.uform_len);
-					evaluate(i, nodeBeg, nullptr, 2, unkNNG, unkNNP, unkScore, node.uform_off, node.uform_len, inBeg, inEnd);
+					evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.uform_off, node.uform_len, inBeg, inEnd);
 					if (err) return 0;
 				}
 				if (lane == 0) { npOff[i] = nodeBeg; npCnt[i] = top - nodeBeg; }
@@ -1918,7 +1848,7 @@ namespace KB_VIT_NS
 				if (q < P)
 				{
 					p = pool[inBeg + q];
-					ok = p.combine_socket == 0;
+					ok = (p.fw >> FW_SOCKET_SHIFT) == 0;
 					if (ok)
 					{
 						const DMorph pm = c_m.morphs[p.morpheme];
@@ -2269,7 +2199,12 @@ namespace KB_VIT_NS
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
 		const uint32_t blocks = bv.n_sent <= KB_SOLO ? bv.n_sent : KB_SOLO + (bv.n_sent - KB_SOLO + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-		static bool attrSet = false;
+		static bool attrSetOn[64] = {};      // function attributes are per device (the caller holds that device's lock)
+		int devId = 0;
+#ifndef KB_HOSTSIM
+		cudaGetDevice(&devId);
+#endif
+		bool& attrSet = attrSetOn[devId & 63];
 		const size_t smemBytes = sizeof(WarpSmem) * WARPS_PER_BLOCK;
 		if (!attrSet)
 		{

@@ -20,18 +20,22 @@ def u16len(s: str) -> int:
     return len(s.encode("utf-16-le", "surrogatepass")) // 2
 
 
-def synth_batch(n: int, seed: int = SEED) -> List[str]:
+def synth_batch(n: int, seed: int = SEED, typo_frac: float = 0.0) -> List[str]:
+    """typo_frac > 0 (BASELINE.json config 4: 0.3): that share of the sentences draws its eojeols from web_with_typos.txt instead
+    (tests/golden/inputs_web_typos.txt); with typo_frac == 0 the random stream is the one round 1 used."""
     web = _lines("inputs_web.txt")
     written = _lines("inputs_written.txt")
     lengths = [u16len(l) for l in web]
     words = [w for l in web + written for w in l.split(" ") if w]
+    typo_words = [w for l in _lines("inputs_web_typos.txt") for w in l.split(" ") if w] if typo_frac > 0 else None
     rng = random.Random(seed)
     out = []
     for _ in range(n):
         target = rng.choice(lengths)
+        src = typo_words if (typo_words and rng.random() < typo_frac) else words
         parts, cur = [], 0
         while cur < target:
-            w = rng.choice(words)
+            w = rng.choice(src)
             add = u16len(w) + (1 if parts else 0)
             if parts and cur + add > target:
                 break

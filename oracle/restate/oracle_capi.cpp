@@ -132,11 +132,16 @@ uint32_t orc_cong_step(void* p, int32_t* node, uint32_t wid)
 	return h->an->viterbi.cg.step(*node, wid);
 }
 
-// work counters accumulated since open: {lmSteps, pairs, inserts, pathsOut, candEvals, evalCalls}
+// work counters accumulated since open: {lmSteps, pairs, inserts, pathsOut, candEvals, evalCalls}; orc_counters2 adds {top1Mode, bucketFull, mediumMode, maxIncoming}
 void orc_counters(void* p, uint64_t* out)
 {
 	auto* h = reinterpret_cast<OrcHandle*>(p);
 	out[0] = h->cnt.lmSteps; out[1] = h->cnt.pairs; out[2] = h->cnt.inserts; out[3] = h->cnt.pathsOut; out[4] = h->cnt.candEvals; out[5] = h->cnt.evalCalls;
+}
+void orc_counters2(void* p, uint64_t* out)
+{
+	auto* h = reinterpret_cast<OrcHandle*>(p);
+	out[0] = h->cnt.top1Mode; out[1] = h->cnt.bucketFull; out[2] = h->cnt.mediumMode; out[3] = h->cnt.maxIncoming;
 }
 
 

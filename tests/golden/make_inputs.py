@@ -50,3 +50,9 @@ for s in edge: add(s)
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'inputs_ref_tests.txt'), 'w', encoding='utf-8', errors='surrogatepass') as f:
     for s in out: f.write(s + '\n')
 print(len(out), 'inputs')
+
+# ---- round 2: tests/golden/inputs_web_typos.txt = first column of eval_data/web_with_typos.txt (the typo'd sentences BASELINE.json
+# config 4 draws 30 % of its synthetic batch from)
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'inputs_web_typos.txt'), 'w', encoding='utf-8') as f:
+    for line in open('/root/reference/eval_data/web_with_typos.txt', encoding='utf-8'):
+        if line.strip(): f.write(line.split('\t')[0].rstrip('\n') + '\n')

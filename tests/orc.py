@@ -77,6 +77,14 @@ class Oracle:
         self.lib.orc_counters(self.h, out.ctypes.data)
         return dict(zip(["lmSteps", "pairs", "inserts", "pathsOut", "candEvals", "evalCalls"], [int(x) for x in out]))
 
+    def counters2(self):
+        """{top1Mode, bucketFull, mediumMode, maxIncoming}: how often the > 512-path `top1` container, the 'container is full' rule and
+        the 4-bucket medium container were used since open"""
+        out = np.zeros(4, np.uint64)
+        self.lib.orc_counters2.argtypes = [C.c_void_p, C.c_void_p]
+        self.lib.orc_counters2(self.h, out.ctypes.data)
+        return dict(zip(["top1Mode", "bucketFull", "mediumMode", "maxIncoming"], [int(x) for x in out]))
+
     WORK_FIELDS = ["sentences", "rawUnits", "normUnits", "trieVisits", "trieProbes", "trieHits", "candForms", "nodesBuilt", "nodesFinal",
                    "candEntries", "candEvals", "lmSteps", "lmHops", "lmProbes", "pairs", "pathsWritten", "pathsKept", "tokens"]
 
