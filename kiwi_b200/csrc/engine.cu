@@ -191,6 +191,7 @@ namespace kb
 		vv.paths = (DPath*)alloc(((size_t)ppu * capU + (size_t)pc * capB) * sizeof(DPath));
 		vv.node_path_off = (uint32_t*)alloc(capU * npu * 4);
 		vv.node_path_cnt = (uint32_t*)alloc(capU * npu * 4);
+		vv.node_cand = (uint2*)alloc(capU * npu * 8);
 		vv.reachable = (uint8_t*)alloc(capU * npu);
 		vv.recs = (DRec*)alloc(2 * chunkSlots * sizeof(DRec));
 		vv.tokens = (DToken*)alloc(capU * sizeof(DToken));

@@ -73,6 +73,7 @@ namespace kb
 		DPath* paths;                // pool, index pbase = paths_per_unit * wbase + paths_const * s
 		uint32_t* node_path_off;     // per lattice node (nbase + chunk.node_off + i)
 		uint32_t* node_path_cnt;
+		uint2* node_cand;            // per lattice node: {first row of the node's candidate block in DevModel::cands, row count | DForm::flags << 16}
 		uint8_t* reachable;          // per lattice node
 		DRec* recs;                  // 2 per chunk slot: 2 * ((wbase >> 2) + 2 * s)
 		DToken* tokens;              // output, W_s per sentence at wbase

@@ -26,6 +26,7 @@
 #include <math_constants.h>
 #include "kb_model.h"
 #include "kb_batch.h"
+#include "std_sort_emu.h"
 
 // This file is compiled twice (csrc/Makefile): KB_CONG=0 -> viterbi_kernel for Knlm images (the code described above),
 // KB_CONG=1 -> viterbi_cong_kernel for quantized CoNg images.  The CoNg build replaces, behind `#if KB_CONG`:
@@ -98,7 +99,9 @@ namespace KB_VIT_NS
 
 	struct WarpSmem
 	{
-		alignas(16) DCand dcand[GROUP];         // static candidate rows of the current group (bulk copy of the form's contiguous block, or lane stores)
+		alignas(16) DCand dcandBuf[2][GROUP];   // static candidate rows of the current group, double buffered: the NEXT node's block arrives by one
+		                                        // bulk copy (cp.async.bulk -> mbarrier) while the current node is evaluated; other groups by lane stores
+		alignas(8) unsigned long long mbar[2];  // one transaction barrier per buffer
 		CandDyn cdyn[GROUP];
 		uint8_t pcls[STAGE_CAP];                // class index of every incoming path (classes = distinct filter words)
 		uint32_t fclass[32];                    // the distinct filter words: FW_* bits | combine_socket << 16
@@ -158,9 +161,10 @@ namespace KB_VIT_NS
 			h = (h + 1) & c_m.kn_hash_mask;
 		}
 	}
-	__device__ __noinline__ float knProgress(int32_t& nodeIdx, uint32_t next, uint32_t site = 0)
+	// (state in, {log-probability, state} out - both in registers: a reference parameter would pin the caller's state to local memory)
+	struct KnRes { float ll; int32_t node; };
+	__device__ __noinline__ KnRes knProgressV(int32_t nodeIdx, uint32_t next)
 	{
-		(void)site;
 		float acc = 0;
 		while (true)
 		{
@@ -171,7 +175,7 @@ namespace KB_VIT_NS
 				if (v == 0)
 				{
 					if (c_m.kn_htx) nodeIdx = c_m.kn_root[c_m.kn_htx[next]];
-					return acc + c_m.kn_unk_ll;
+					return KnRes{ acc + c_m.kn_unk_ll, nodeIdx };
 				}
 				cll = c_m.kn_root_ll[next];
 			}
@@ -188,7 +192,7 @@ namespace KB_VIT_NS
 			if (v > 0)
 			{
 				nodeIdx += v;
-				return acc + cll;
+				return KnRes{ acc + cll, nodeIdx };
 			}
 			// leaf: next state = deepest suffix state that continues with `next`
 			int32_t cur = nodeIdx;
@@ -202,12 +206,18 @@ namespace KB_VIT_NS
 				if (found && lv > 0)
 				{
 					nodeIdx = cur + lv;
-					return acc + asFloat(v);
+					return KnRes{ acc + asFloat(v), nodeIdx };
 				}
 			}
 			nodeIdx = c_m.kn_htx ? c_m.kn_root[c_m.kn_htx[next]] : 0;
-			return acc + asFloat(v);
+			return KnRes{ acc + asFloat(v), nodeIdx };
 		}
+	}
+	__device__ __forceinline__ float knProgress(int32_t& nodeIdx, uint32_t next, uint32_t = 0)
+	{
+		const KnRes r = knProgressV(nodeIdx, next);
+		nodeIdx = r.node;
+		return r.ll;
 	}
 
 
@@ -391,6 +401,8 @@ namespace KB_VIT_NS
 		uint32_t* npOff; uint32_t* npCnt; uint8_t* reach;
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
+		DCand* dcur = nullptr; uint32_t curBuf = 0, pfPhase = 0; const DCand* pfBase[2] = { nullptr, nullptr };      // candidate-row staging (see prefetchCands)
+		uint2* nodeCand = nullptr;
 		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0, nFw = 1;
 		uint32_t nClasses = 0, classCommon = 0; bool classOverflow = false;
 		volatile uint32_t* sActive = nullptr; uint32_t roundCnt = 0;       // block-level lockstep over lattice nodes (see viterbi_kernel)
@@ -856,6 +868,50 @@ namespace KB_VIT_NS
 		}
 
 
+		// ---- candidate rows: TMA-style bulk staging --------------------------------------------------------------------
+		// The candidate rows of a lattice node are one contiguous block of DevModel::cands, known before the node is evaluated
+		// (node_cand, filled per chunk by lane-parallel loads).  While node i is evaluated, lane 0 issues ONE bulk copy
+		// (cp.async.bulk.shared.global with an mbarrier transaction count) of node i+1's first 32 rows into the other buffer; node
+		// i+1 then only waits on the barrier's phase.  Groups beyond the first 32 candidates, the unknown-form re-evaluations and the
+		// CoNg build (reordered candidates) store their rows from registers instead.
+#if !KB_CONG && !defined(KB_HOSTSIM) && !defined(KB_NO_TMA)
+#define KB_TMA_ROWS 1
+		static __device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+		__device__ void pfInit()
+		{
+			if (lane == 0)
+			{
+				asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smemAddr(&sm->mbar[0])) : "memory");
+				asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smemAddr(&sm->mbar[1])) : "memory");
+				asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+			}
+			__syncwarp();
+		}
+		// issue the copy of `cnt` rows (1..32) into buffer `buf`; every issue is matched by exactly one pfWait on that buffer
+		__device__ __forceinline__ void pfIssue(const DCand* base, uint32_t cnt, uint32_t buf)
+		{
+			__syncwarp();      // all lanes are done reading the buffer's previous contents
+			if (lane == 0)
+			{
+				const uint32_t bytes = cnt * (uint32_t)sizeof(DCand), bar = smemAddr(&sm->mbar[buf]);
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					:: "r"(smemAddr(&sm->dcandBuf[buf][0])), "l"(base), "r"(bytes), "r"(bar) : "memory");
+			}
+			pfBase[buf] = base;
+		}
+		__device__ __forceinline__ void pfWait(uint32_t buf)
+		{
+			const uint32_t bar = smemAddr(&sm->mbar[buf]), parity = (pfPhase >> buf) & 1u;
+			asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" :: "r"(bar), "r"(parity) : "memory");
+			pfPhase ^= 1u << buf;
+			pfBase[buf] = nullptr;
+		}
+#else
+#define KB_TMA_ROWS 0
+#endif
+
 		// ---- the item pipeline (containers of <= 512 incoming paths: the reference's top1Small / top1Medium) --------
 		// Every path carries its filter word (DPath::fw, computed when the path was created); the distinct words of a node's
 		// incoming paths become "path classes" (a handful per node).  Candidates are classified 32 at a time, one lane per
@@ -925,7 +981,7 @@ namespace KB_VIT_NS
 				const bool valid = i < nItems;
 				uint32_t slot = 0, q = 0, r = 0, fwIdx = 0; bool condFail = false, spacePen = false;
 				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 0x1FFFF; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
-				const DCand* cs = &sm->dcand[slot];
+				const DCand* cs = &dcur[slot];
 				const CandDyn cd = sm->cdyn[slot];
 				const uint32_t csFeat = cs->feat;
 				const int32_t csCurId = cs->cur_id;
@@ -1302,7 +1358,7 @@ namespace KB_VIT_NS
 		__device__ __noinline__ void evalGeneralCand(uint32_t k, const DNode& node, const GenCtx& g)
 		{
 			const uint32_t P = g.inEnd - g.inBeg, inBeg = g.inBeg;
-			const DCand dk = sm->dcand[k];
+			const DCand dk = dcur[k];
 			const CandDyn cd = sm->cdyn[k];
 			const int32_t curId = dk.cur_id;
 			const DMorph cur = c_m.morphs[curId];
@@ -1376,8 +1432,19 @@ namespace KB_VIT_NS
 		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
 		// candBase: the node's static candidate rows (a form's block of c_m.cands, or the unknown NNG / NNP rows)
 		__device__ __noinline__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const DCand* candBase, uint32_t nCandsIn,
-			float unkFormDiscount, uint32_t ownOff, uint32_t ownLen, uint32_t inBeg, uint32_t inEnd)
+			float unkFormDiscount, uint32_t ownOff, uint32_t ownLen, uint32_t inBeg, uint32_t inEnd, bool first)
 		{
+			// `first`: the node's first evaluation - its candidate block may be waiting in the other staging buffer
+			bool rowsStaged = false;
+#if KB_TMA_ROWS
+			if (first)
+			{
+				curBuf ^= 1u; dcur = sm->dcandBuf[curBuf];
+				if (pfBase[curBuf] != nullptr) { const bool hit = pfBase[curBuf] == candBase; pfWait(curBuf); rowsStaged = hit; }
+			}
+#else
+			(void)first;
+#endif
 			const DNode node = nodes[nodeIdx];
 			float whitespaceDiscount = 0;
 			if (node.uform_len == 0 && node.form >= 0 && c_m.forms[node.form].str_len && node.space_errors)
@@ -1430,9 +1497,14 @@ namespace KB_VIT_NS
 #else
 							const DCand* src = candBase + gb + lane;
 #endif
-							const uint4 r0 = reinterpret_cast<const uint4*>(src)[0], r1 = reinterpret_cast<const uint4*>(src)[1], r2 = reinterpret_cast<const uint4*>(src)[2];
-							uint4* dst = reinterpret_cast<uint4*>(&sm->dcand[lane]);
-							dst[0] = r0; dst[1] = r1; dst[2] = r2;
+							uint4 r0, r1, r2;
+							uint4* dst = reinterpret_cast<uint4*>(&dcur[lane]);
+							if (rowsStaged && gb == 0 && (ignoreCond == 0 || nCands <= GROUP)) { r1 = dst[1]; r2 = dst[2]; }      // the block is already in shared memory (bulk copy)
+							else
+							{
+								r0 = reinterpret_cast<const uint4*>(src)[0]; r1 = reinterpret_cast<const uint4*>(src)[1]; r2 = reinterpret_cast<const uint4*>(src)[2];
+								dst[0] = r0; dst[1] = r1; dst[2] = r2;
+							}
 							feat = r1.x;
 							flags = (uint8_t)(r2.x >> 8); curSocket = r2.y & 0xFF; kind = (r2.y >> 8) & 0xFF;
 							const uint32_t tagClean = (r2.y >> 16) & 0xFF;
@@ -1513,8 +1585,8 @@ namespace KB_VIT_NS
 					uint32_t dotMask = 0;
 					{
 						const CandDyn cdl = sm->cdyn[lane];
-						const bool regular = lane < gcount && (cdl.cls == CLS_GENERAL || cdl.cls == CLS_ITEM) && sm->dcand[lane].cur_socket == 0 && !(sm->dcand[lane].kind & DK_FIRST_IS_P);
-						sm->colWid[lane] = lane < gcount ? sm->dcand[lane].first_wid : 0u;
+						const bool regular = lane < gcount && (cdl.cls == CLS_GENERAL || cdl.cls == CLS_ITEM) && dcur[lane].cur_socket == 0 && !(dcur[lane].kind & DK_FIRST_IS_P);
+						sm->colWid[lane] = lane < gcount ? dcur[lane].first_wid : 0u;
 						dotMask = __ballot_sync(FULL, regular);
 						__syncwarp();
 						if (dotMask && cgn.nU && cgn.epFirst != CG_E_SCALAR) congGroupDots(cgn.nU, dotMask);
@@ -1565,7 +1637,7 @@ namespace KB_VIT_NS
 							const uint32_t perRound = 32u >> rshift;
 							const bool spacePen = socketChunk && spaceBefore;          // only socket matches survive `spaceBefore` (with tolerance) and they pay the penalty
 							uint32_t fwCarry = 0;                     // index into fwTab of the inherited first-wid override, 0 = none
-							const bool firstIsP = socketChunk && (sm->dcand[k].kind & DK_FIRST_IS_P) != 0;
+							const bool firstIsP = socketChunk && (dcur[k].kind & DK_FIRST_IS_P) != 0;
 							#pragma unroll 1
 							for (uint32_t qb = 0; qb < P; qb += perRound)
 							{
@@ -1783,22 +1855,42 @@ namespace KB_VIT_NS
 			top += 1;
 			__syncwarp();
 
+			// per node: where its candidate rows are (a form's block of the static table, or the unknown NNG / NNP rows) - lane-parallel
+			for (uint32_t j = 1 + lane; j + 1 < N; j += 32)
+			{
+				const int32_t fm = nodes[j].form;
+				uint2 ci;
+				if (fm >= 0) { const DForm f = c_m.forms[fm]; ci.x = f.cand_off; ci.y = (uint32_t)f.cand_cnt | ((uint32_t)f.flags << 16); }
+				else { ci.x = c_m.cand_unk; ci.y = 2u; }
+				nodeCand[j] = ci;
+			}
+			__syncwarp();
+#if KB_TMA_ROWS
+			if (N > 2) { const uint2 c1 = nodeCand[1]; pfIssue(c_m.cands + c1.x, min(c1.y & 0xFFFFu, GROUP), curBuf ^ 1u); }
+#endif
+
 			for (uint32_t i = 1; i + 1 < N; ++i)
 			{
 				const DNode node = nodes[i];
+				const uint2 ci = nodeCand[i];
 				uint32_t inBeg, inEnd;
 				incoming(i, inBeg, inEnd);
 				const uint32_t nodeBeg = top;
+#if KB_TMA_ROWS
+				// node i's rows sit in buffer curBuf ^ 1 (issued one node ago); node i + 1's go to curBuf, whose last reader was node i - 1
+				if (i + 2 < N) { const uint2 cn = nodeCand[i + 1]; pfIssue(c_m.cands + cn.x, min(cn.y & 0xFFFFu, GROUP), curBuf); }
+#endif
 				if (node.form >= 0)
 				{
-					const DForm f = c_m.forms[node.form];
-					evaluate(i, nodeBeg, c_m.cands + f.cand_off, f.cand_cnt, 0.f, node.uform_off, node.uform_len, inBeg, inEnd);
+					const uint32_t fflags = ci.y >> 16;
+					evaluate(i, nodeBeg, c_m.cands + ci.x, ci.y & 0xFFFFu, 0.f, node.uform_off, node.uform_len, inBeg, inEnd, true);
 					if (err) return 0;
-					if (node.typo_cost == 0.f && (f.flags & FF_ALL_PARTIAL))
+					if (node.typo_cost == 0.f && (fflags & FF_ALL_PARTIAL))
 					{
+						const DForm f = c_m.forms[node.form];
 						const uint16_t* fs = c_m.form_chars + c_m.forms_raw[node.form].str_off;
 						const float unkScore = unkFormScore(fs, f.str_len);
-						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk + 1, 1, unkScore, ~(uint32_t)node.form, f.str_len, inBeg, inEnd);
+						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk + 1, 1, unkScore, ~(uint32_t)node.form, f.str_len, inBeg, inEnd, false);
 						if (err) return 0;
 					}
 					const bool r = anyNonSocket(nodeBeg, top);
@@ -1808,14 +1900,14 @@ namespace KB_VIT_NS
 					{
 						const uint32_t len = node.end_pos - node.start_pos;
 						const float unkScore = unkFormScore(norm + node.start_pos, len);
-						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.start_pos, len, inBeg, inEnd);
+						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.start_pos, len, inBeg, inEnd, false);
 						if (err) return 0;
 					}
 				}
 				else
 				{
 					const float unkScore = unkFormScore(norm + node.uform_off, node.uform_len);
-					evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.uform_off, node.uform_len, inBeg, inEnd);
+					evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.uform_off, node.uform_len, inBeg, inEnd, true);
 					if (err) return 0;
 				}
 				if (lane == 0) { npOff[i] = nodeBeg; npCnt[i] = top - nodeBeg; }
@@ -1897,68 +1989,61 @@ namespace KB_VIT_NS
 			}
 			__syncwarp();
 			const uint32_t nRec = nCand * perPath;      // records with wid == 1 are real candidates, in the reference's emplace order
-			// distinct (rootId, spState) groups, ascending
-			uint32_t groups[MAX_RESULTS]; uint32_t nGroups = 0;
+			// sort(cand) by (rootId, spState, score desc) EXACTLY as libstdc++'s std::sort does (std_sort_emu.h): equal-score candidates
+			// - two morphemes with the same LM id - tie regularly, and which one comes first decides the emitted morpheme id
+			SortRec* sr = reinterpret_cast<SortRec*>(pool + candBeg + nRec);
+			uint32_t nReal = 0;
 			for (uint32_t eb = 0; eb < nRec; eb += 32)
 			{
 				const uint32_t e = eb + lane;
-				uint32_t gk = NPOS;
-				if (e < nRec) { const DPath* r = pool + candBeg + e; if (r->wid) gk = ((uint32_t)r->root_id << 8) | r->sp_state; }
-				unsigned rem = __ballot_sync(FULL, gk != NPOS);
-				while (rem)
+				bool real = false; unsigned long long key = 0;
+				if (e < nRec)
 				{
-					const int src = __ffs(rem) - 1;
-					const uint32_t k = __shfl_sync(FULL, gk, src);
-					bool seen = false;
-					for (uint32_t g = 0; g < nGroups; ++g) if (groups[g] == k) seen = true;
-					if (!seen)
-					{
-						if (nGroups >= MAX_RESULTS) { err = ST_INTERNAL; return 0; }
-						groups[nGroups++] = k;
-					}
-					rem &= ~__ballot_sync(FULL, gk == k);
+					const DPath* r = pool + candBeg + e;
+					real = r->wid != 0;
+					uint32_t o = __float_as_uint(r->acc_score);
+					o = (o & 0x80000000u) ? ~o : (o | 0x80000000u);
+					key = ((unsigned long long)r->root_id << 40) | ((unsigned long long)r->sp_state << 32) | (unsigned long long)(~o);
 				}
+				const unsigned rm = __ballot_sync(FULL, real);
+				const uint32_t k = nReal + __popc(rm & ((1u << lane) - 1));
+				if ((size_t)(candBeg + nRec) * sizeof(DPath) + (size_t)(nReal + __popc(rm)) * sizeof(SortRec) > (size_t)poolCap * sizeof(DPath)) { err = ST_PATH_OVERFLOW; return 0; }
+				if (real) { SortRec x; x.key = key; x.idx = e; x.pad = 0; sr[k] = x; }
+				nReal += __popc(rm);
 			}
-			if (nGroups == 0) return 0;
-			// insertion sort of the few group keys
-			for (uint32_t a = 1; a < nGroups; ++a) { const uint32_t k = groups[a]; uint32_t b = a; while (b && groups[b - 1] > k) { groups[b] = groups[b - 1]; --b; } groups[b] = k; }
+			if (nReal == 0) return 0;
+			__syncwarp();
+			if (lane == 0) stdSortEmu(sr, (long)nReal);
+			__syncwarp();
+			// groups = runs of equal (rootId, spState) in the sorted order; keep the first ceil(2 / #groups) of every group
+			uint32_t nGroups = 0;
+			for (uint32_t eb = 0; eb < nReal; eb += 32)
+			{
+				const uint32_t e = eb + lane;
+				const bool start = e < nReal && (e == 0 || (sr[e].key >> 32) != (sr[e - 1].key >> 32));
+				nGroups += __popc(__ballot_sync(FULL, start));
+			}
 			const uint32_t perGroup = (2 + nGroups - 1) / nGroups;        // ceil(topN * 2 / numUniq), topN == 1
 			uint32_t nRes = 0;
-			for (uint32_t g = 0; g < nGroups; ++g)
+			for (uint32_t eb = 0; eb < nReal; eb += 32)
 			{
-				uint32_t taken1 = NPOS;
-				for (uint32_t k = 0; k < perGroup; ++k)
+				const uint32_t e = eb + lane;
+				bool take = false;
+				if (e < nReal)
 				{
-					// best remaining record of the group: max score, earliest index on ties
-					uint32_t bestOrd = 0, bestIdx = NPOS;
-					for (uint32_t eb = 0; eb < nRec; eb += 32)
-					{
-						const uint32_t e = eb + lane;
-						uint32_t ord = 0; bool ok = false;
-						if (e < nRec && e != taken1)
-						{
-							const DPath* r = pool + candBeg + e;
-							if (r->wid && ((((uint32_t)r->root_id << 8) | r->sp_state) == groups[g]))
-							{
-								ok = true;
-								ord = __float_as_uint(r->acc_score);
-								ord = (ord & 0x80000000u) ? ~ord : (ord | 0x80000000u);
-							}
-						}
-						const uint32_t mxo = __reduce_max_sync(FULL, ok ? ord : 0u);
-						if (mxo > bestOrd || (bestIdx == NPOS && mxo))
-						{
-							const unsigned bm = __ballot_sync(FULL, ok && ord == mxo);
-							if (bm && (mxo > bestOrd || bestIdx == NPOS)) { bestOrd = mxo; bestIdx = eb + __ffs(bm) - 1; }
-						}
-					}
-					if (bestIdx == NPOS) break;
+					const unsigned long long g = sr[e].key >> 32;
+					take = e == 0 || (sr[e - 1].key >> 32) != g;                                    // first of its group
+					if (!take && perGroup == 2) take = e == 1 || (sr[e - 2].key >> 32) != g;       // second of its group (single-group case only)
+				}
+				unsigned tm = __ballot_sync(FULL, take);
+				while (tm)
+				{
+					const uint32_t src = __ffs(tm) - 1; tm &= tm - 1;
 					if (nRes >= MAX_RESULTS) { err = ST_INTERNAL; return 0; }
-					const DPath* r = pool + candBeg + bestIdx;
+					const DPath* r = pool + candBeg + sr[eb + src].idx;
 					res[nRes].score = r->acc_score; res[nRes].endParent = r->parent;
 					res[nRes].prevState = uniq[r->root_id]; res[nRes].curState = r->sp_state;
 					++nRes;
-					taken1 = bestIdx;
 				}
 			}
 			// sort(ret) by score desc (<= 16 elements: libstdc++ std::sort is an insertion sort -> stable)
@@ -2026,11 +2111,15 @@ namespace KB_VIT_NS
 		v.poolCap = vv.paths_per_unit * W + vv.paths_const;
 		v.top = 0;
 		v.sm = &smAll[wib]; v.ht = smAll[wib].ht; v.htUsed = 1;
+		v.dcur = smAll[wib].dcandBuf[0];
 #ifdef KB_LOCKSTEP
 		v.sActive = &sActiveCount; v.roundCnt = sActiveCount;
 #endif
 		v.splitComplex = (bv.match_options >> 22) & 1; v.splitSaisiot = (bv.match_options >> 25) & 1; v.mergeSaisiot = (bv.match_options >> 26) & 1;
 		v.htClear();
+#if KB_TMA_ROWS
+		v.pfInit();
+#endif
 
 		const DChunk* chunks = bv.chunks + (wbase >> 2) + 2 * (size_t)s;
 		const uint32_t nChunks = bv.n_chunks[s];
@@ -2047,6 +2136,7 @@ namespace KB_VIT_NS
 			v.nodes = bv.nodes + nbase + ch.node_off; v.N = ch.n_nodes;
 			v.npOff = vv.node_path_off + nbase + ch.node_off; v.npCnt = vv.node_path_cnt + nbase + ch.node_off;
 			v.reach = vv.reachable + nbase + ch.node_off;
+			v.nodeCand = vv.node_cand + nbase + ch.node_off;
 			// uniqStates = sorted unique of spStatesByRet, or {0} (PathEvaluator.hpp:1212-1218)
 			if (retN == 0) { v.uniq[0] = 0; v.nUniq = 1; }
 			else if (retN == 1 || retSp[0] == retSp[1]) { v.uniq[0] = retSp[0]; v.nUniq = 1; }

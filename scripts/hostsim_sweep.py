@@ -31,10 +31,43 @@ def _handle(mode):
     return _H[mode]
 
 
+_BENCH = {}
+
+
+def _bench_case(mode, n):
+    """sentences of the bench batch of this mode + the ORACLE's analysis of them (no golden vectors exist for synthetic text)"""
+    key = (mode, n)
+    if key not in _BENCH:
+        import bench
+        from kiwi_b200.synth import SEED
+        from tests.orc import Oracle, TypoOracle
+        cfg = bench.CONFIGS[{"plain": 2, "cong": 3, "typo": 4}[mode]]
+        o = Oracle(bench.image_path(cfg["model"]))
+        if cfg["typo"]: o.set_typo(TypoOracle(TYPO_IMAGES[cfg["typo"]]))
+        _BENCH[key] = (bench.gen_sentences(cfg, 0, n, SEED), o)
+    return _BENCH[key]
+
+
 def work(args):
     mode, name, idxs = args
     cong = mode == "cong"; typo = mode == "typo"
     lib, h = _handle(mode)
+    if name.startswith("bench:"):
+        texts, orc = _bench_case(mode, int(name[6:]))
+        cap = 8192
+        morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
+        bad = []
+        for i in idxs:
+            t = texts[i]
+            u = np.ascontiguousarray(np.frombuffer(t.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
+            s = C.c_float(0); nn = C.c_int(0)
+            n = lib.hs32_analyze(h, u.ctypes.data, len(u), MATCH_ALL, morph.ctypes.data, tag.ctypes.data, pos.ctypes.data, ln.ctypes.data, sc.ctypes.data, cap, C.byref(s), C.byref(nn), None)
+            otoks, oscore = orc.analyze(t)
+            if n < 0: bad.append((name, i, "status %d" % n)); continue
+            got = [(int(morph[k]), int(tag[k]), int(pos[k]), int(ln[k])) for k in range(n)]
+            if got != [x[:4] for x in otoks]: bad.append((name, i, "tokens")); continue
+            if not (all(np.float32(sc[k]) == np.float32(otoks[k][4]) for k in range(n)) and np.float32(s.value) == np.float32(oscore)): bad.append((name, i, "scores"))
+        return len(idxs), bad
     cap = 8192
     morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
     texts = read_inputs(name); gold = read_golden(("cong_" if cong else "") + ("typo6_" if typo else "") + name)
@@ -61,6 +94,10 @@ def main():
     a = ap.parse_args()
     tasks = []
     for name in a.files.split(","):
+        if name.startswith("bench:"):      # --files bench:8192 : the first N sentences of the mode's bench batch against the oracle
+            idx = list(range(0, int(name[6:]), a.stride)); per = max(1, len(idx) // (a.jobs * 4))
+            for k in range(0, len(idx), per): tasks.append((a.mode, name, idx[k:k + per]))
+            continue
         texts = read_inputs(name)
         idx = [i for i in range(0, len(texts), a.stride) if len(texts[i]) <= a.maxlen]
         per = max(1, len(idx) // (a.jobs * 4))

@@ -88,10 +88,10 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 		bv.norm = norm.data(); bv.norm_len = normLen.data(); bv.pos_table = posTable.data(); bv.ns_to_pos = nsToPos.data(); bv.pos_to_ns = posToNs.data();
 		bv.end_pos_map = endPosMap.data(); bv.ctr = ctr.data(); bv.patterns = pats.data(); bv.build_nodes = build.data(); bv.nodes = nodes.data();
 		bv.new_index = newIndex.data(); bv.chunks = chunks.data(); bv.n_chunks = nChunks.data(); bv.status = status.data(); bv.debug = debug.data();
-		auto paths = buf<DPath>(ppu * U + pc); auto npOff = buf<uint32_t>(U * npu), npCnt = buf<uint32_t>(U * npu); auto reach = buf<uint8_t>(U * npu);
+		auto paths = buf<DPath>(ppu * U + pc); auto npOff = buf<uint32_t>(U * npu), npCnt = buf<uint32_t>(U * npu); auto nodeCand = buf<uint2>(U * npu); auto reach = buf<uint8_t>(U * npu);
 		auto recs = buf<DRec>(2 * chunkSlots); auto toks = buf<DToken>(U); auto nTok = buf<uint32_t>(2); auto bestRec = buf<int32_t>(1); auto sc = buf<float>(1);
 		auto timing = buf<unsigned long long>(2);
-		vv.paths_per_unit = (uint32_t)ppu; vv.paths_const = (uint32_t)pc; vv.paths = paths.data(); vv.node_path_off = npOff.data(); vv.node_path_cnt = npCnt.data();
+		vv.paths_per_unit = (uint32_t)ppu; vv.paths_const = (uint32_t)pc; vv.paths = paths.data(); vv.node_path_off = npOff.data(); vv.node_path_cnt = npCnt.data(); vv.node_cand = nodeCand.data();
 		vv.reachable = reach.data(); vv.recs = recs.data(); vv.tokens = toks.data(); vv.n_tokens = nTok.data(); vv.best_rec = bestRec.data(); vv.score = sc.data(); vv.timing = timing.data();
 		std::vector<DTypoNode> tgTmp, tg; std::vector<uint32_t> tgRemap; std::vector<uint2> tgRange; std::vector<DTypoState> tgStates; std::vector<DTypoMatch> tgMatches;
 		if (!s.typo.empty())
