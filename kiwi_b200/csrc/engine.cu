@@ -40,6 +40,10 @@ namespace kb
 	}
 
 	static constexpr uint32_t DEFAULT_PATHS_PER_UNIT = 128, DEFAULT_PATHS_CONST = 8192;
+#ifndef KB_DEFAULT_TEAM_PERMILLE
+#define KB_DEFAULT_TEAM_PERMILLE 0
+#endif
+	static uint32_t teamPermille();
 	// typo graph nodes / search states per normalised-unit slot (W_s = 2 n + 4 slots per sentence): the basic typo set needs < 4
 	// on the reference's evaluation texts (tests/test_hostsim_lattice.py); overflow -> ST_TYPO_OVERFLOW -> retry arena
 	static constexpr uint32_t DEFAULT_TYPO_GRAPH_PER_UNIT = 6, DEFAULT_TYPO_STATES_PER_UNIT = 6;
@@ -50,6 +54,37 @@ namespace kb
 		if (s >= nSent) return;
 		keys[s] = textOff[s + 1] - textOff[s];
 		idx[s] = s;
+	}
+
+	// predicted Viterbi cost of a sentence = sum over its lattice nodes of (candidate count)^2: the launch order of the Viterbi kernel
+	// (heaviest first) and the choice of the sentences that get a team of warps.  Measured on the bench batch against the oracle's work
+	// counters: correlation 0.92 with the LM-step count (sentence length: 0.87); the top 20 % by this key hold 91 % of the heaviest 5 %.
+	__global__ void cost_kernel(BatchView bv, const DForm* __restrict__ forms, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx)
+	{
+		const uint32_t lane = threadIdx.x & 31;
+		const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+		if (s >= bv.n_sent) return;
+		unsigned long long cost = 0;
+		if (!bv.status[s])
+		{
+			const size_t wbase = 2 * (size_t)bv.text_off[s] + 4 * (size_t)s;
+			const size_t nbase = (size_t)bv.nodes_per_unit * wbase;
+			const DChunk* chunks = bv.chunks + (wbase >> 2) + 2 * (size_t)s;
+			const uint32_t nChunks = bv.n_chunks[s];
+			for (uint32_t c = 0; c < nChunks; ++c)
+			{
+				const DChunk ch = chunks[c];
+				const DNode* nodes = bv.nodes + nbase + ch.node_off;
+				for (uint32_t j = 1 + lane; j + 1 < ch.n_nodes; j += 32)
+				{
+					const int32_t fm = nodes[j].form;
+					const unsigned long long k = fm >= 0 ? forms[fm].cand_cnt : 2u;
+					cost += k * k;
+				}
+			}
+		}
+		for (int d = 16; d; d >>= 1) cost += __shfl_xor_sync(0xFFFFFFFFu, cost, d);
+		if (lane == 0) { keys[s] = cost > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cost; idx[s] = s; }
 	}
 
 	__global__ void pack_kernel(uint32_t nSent, const uint32_t* __restrict__ textOff, const uint32_t* __restrict__ nTokens,
@@ -206,7 +241,7 @@ namespace kb
 		size_t tb = 0;
 		cub::DeviceScan::ExclusiveSum(nullptr, tb, vv.n_tokens, sc.tokOff, (int)(capB + 1), st);
 		sc.cubTempBytes = tb; sc.cubTemp = alloc(tb);
-		sc.lenKeys = (uint32_t*)alloc(capB * 4); sc.lenKeysOut = (uint32_t*)alloc(capB * 4); sc.idxIn = (uint32_t*)alloc(capB * 4); sc.order = (uint32_t*)alloc(capB * 4);
+		sc.lenKeys = (uint32_t*)alloc(capB * 4); sc.lenKeysOut = (uint32_t*)alloc(capB * 4); sc.idxIn = (uint32_t*)alloc(capB * 4); sc.order = (uint32_t*)alloc(capB * 4); sc.orderVit = (uint32_t*)alloc(capB * 4);
 		size_t sb = 0;
 		cub::DeviceRadixSort::SortPairsDescending(nullptr, sb, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.order, (int)capB, 0, 32, st);
 		sc.sortTempBytes = sb; sc.sortTemp = alloc(sb);
@@ -249,6 +284,16 @@ namespace kb
 		ck(cub::DeviceRadixSort::SortPairsDescending(sc.sortTemp, sb, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.order, (int)n, 0, 32, st), "cub sort");
 		sc.bv.order = sc.order;
 		ck(launch_lattice(model.dev, sc.bv, st), "lattice_kernel launch");
+		// Viterbi launch order: heaviest predicted sentence first; the first n_team of them get a team of warps each
+		{
+			const uint32_t threads = 256, blocks = (n * 32 + threads - 1) / threads;
+			cost_kernel<<<blocks, threads, 0, st>>>(sc.bv, model.dev.forms, sc.lenKeys, sc.idxIn);
+			ck(cudaGetLastError(), "cost_kernel launch");
+			size_t sb2 = sc.sortTempBytes;
+			ck(cub::DeviceRadixSort::SortPairsDescending(sc.sortTemp, sb2, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.orderVit, (int)n, 0, 32, st), "cub sort");
+			sc.bv.order = sc.orderVit;
+			sc.vv.n_team = (uint32_t)((unsigned long long)n * teamPermille() / 1000);
+		}
 		ck(cudaEventRecord(ev[2], st), "event");
 		ck(model.dev.model_type == 4 ? launch_viterbi_cong(model.dev, sc.bv, sc.vv, st) : launch_viterbi(model.dev, sc.bv, sc.vv, st), "viterbi_kernel launch");
 		ck(cudaEventRecord(ev[3], st), "event");
@@ -260,6 +305,13 @@ namespace kb
 		pack_kernel<<<blocks, threads, 0, st>>>(n, sc.bv.text_off, sc.vv.n_tokens, sc.tokOff, sc.vv.tokens, sc.packed);
 		ck(cudaGetLastError(), "pack_kernel launch");
 		ck(cudaEventRecord(ev[4], st), "event");
+	}
+
+	// KIWI_B200_TEAM_PERMILLE: share (in 1/1000) of a pass's sentences, heaviest first, that are analysed by a team of warps
+	static uint32_t teamPermille()
+	{
+		static const uint32_t v = [] { const char* e = std::getenv("KIWI_B200_TEAM_PERMILLE"); const long x = e ? std::atol(e) : KB_DEFAULT_TEAM_PERMILLE; return (uint32_t)std::min<long>(std::max<long>(x, 0), 1000); }();
+		return v;
 	}
 
 	static void growPinned(void** p, size_t* cap, size_t bytes)
@@ -318,7 +370,7 @@ namespace kb
 		ck(cudaEventRecord(s.ev[5], s.stream), "event");
 		s.busy = true; s.i0 = i0; s.n = pn; s.rawUnits = pT; s.units = U; s.tokCopied = est;
 		last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4;
-		last.kernelLaunches += 5;
+		last.kernelLaunches += 6;
 	}
 
 	// waits for the slot's pass, appends its sentences (they are the next ones in input order) to `out`
@@ -406,7 +458,7 @@ namespace kb
 				r.toks.resize(r.tokOff[pn]);
 				if (!r.toks.empty()) ck(cudaMemcpy(r.toks.data(), retry_.packed, r.toks.size() * sizeof(DToken), cudaMemcpyDeviceToHost), "D2H tokens");
 				float ms = 0; cudaEventElapsedTime(&ms, s.ev[1], s.ev[4]); out.msTotal += ms;
-				last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4; last.d2hBytes += ((size_t)pn * 3 + 1) * 4 + r.toks.size() * sizeof(DToken); last.kernelLaunches += 5;
+				last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4; last.d2hBytes += ((size_t)pn * 3 + 1) * 4 + r.toks.size() * sizeof(DToken); last.kernelLaunches += 6;
 				const uint32_t ri = (uint32_t)results.size();
 				for (uint32_t k = 0; k < pn; ++k)
 				{
@@ -560,7 +612,7 @@ namespace kb
 			cudaEventElapsedTime(&a, s.ev[2], s.ev[3]); last.msViterbi += a;
 			cudaEventElapsedTime(&a, s.ev[3], s.ev[4]); last.msPack += a;
 			total += *hTotal;
-			last.kernelLaunches += 5; last.d2hBytes += 4 + (size_t)pn * 4;
+			last.kernelLaunches += 6; last.d2hBytes += 4 + (size_t)pn * 4;
 			for (uint32_t k = 0; k < pn; ++k) if (hStatus[k]) failed.push_back(i0 + k);
 			i0 = i1;
 		}

@@ -95,7 +95,7 @@ namespace kb
 			DToken* packed = nullptr;        // [capUnits]
 			void* cubTemp = nullptr; size_t cubTempBytes = 0;
 			uint16_t* dText = nullptr; uint32_t* dOff = nullptr;
-			uint32_t* lenKeys = nullptr; uint32_t* lenKeysOut = nullptr; uint32_t* idxIn = nullptr; uint32_t* order = nullptr; void* sortTemp = nullptr; size_t sortTempBytes = 0;
+			uint32_t* lenKeys = nullptr; uint32_t* lenKeysOut = nullptr; uint32_t* idxIn = nullptr; uint32_t* order = nullptr; uint32_t* orderVit = nullptr; void* sortTemp = nullptr; size_t sortTempBytes = 0;
 		};
 		// one in-flight pass: its own scratch arena, stream, events and pinned staging
 		struct Slot

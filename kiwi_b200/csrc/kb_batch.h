@@ -70,6 +70,7 @@ namespace kb
 	struct VitView
 	{
 		uint32_t paths_per_unit, paths_const;   // path capacity of sentence s = paths_per_unit * W_s + paths_const
+		uint32_t n_team;             // the first n_team sentences of the launch order are analysed by a team of warps each (viterbi.cu, team mode)
 		DPath* paths;                // pool, index pbase = paths_per_unit * wbase + paths_const * s
 		uint32_t* node_path_off;     // per lattice node (nbase + chunk.node_off + i)
 		uint32_t* node_path_cnt;

@@ -27,6 +27,7 @@
 #include "kb_model.h"
 #include "kb_batch.h"
 #include "std_sort_emu.h"
+#include "unordered_emu.h"
 
 // This file is compiled twice (csrc/Makefile): KB_CONG=0 -> viterbi_kernel for Knlm images (the code described above),
 // KB_CONG=1 -> viterbi_cong_kernel for quantized CoNg images.  The CoNg build replaces, behind `#if KB_CONG`:
@@ -102,6 +103,8 @@ namespace KB_VIT_NS
 		alignas(16) DCand dcandBuf[2][GROUP];   // static candidate rows of the current group, double buffered: the NEXT node's block arrives by one
 		                                        // bulk copy (cp.async.bulk -> mbarrier) while the current node is evaluated; other groups by lane stores
 		alignas(8) unsigned long long mbar[2];  // one transaction barrier per buffer
+		alignas(16) DCand dcandGen[GROUP];      // rows stored from registers (groups that were not bulk-staged): the bulk buffers are only ever
+		                                        // written by the copy engine, so no generic-to-async proxy fence is needed before a copy
 		CandDyn cdyn[GROUP];
 		uint8_t pcls[STAGE_CAP];                // class index of every incoming path (classes = distinct filter words)
 		uint32_t fclass[32];                    // the distinct filter words: FW_* bits | combine_socket << 16
@@ -387,6 +390,26 @@ namespace KB_VIT_NS
 	// ------------------------------------------------------------------------------------------------
 	struct PathRes { float score; uint32_t endParent; uint8_t prevState, curState; };
 
+	// ---- team mode ------------------------------------------------------------------------------------------------------
+	// A batch's kernel time is the time of its heaviest sentence (10 x the mean work in the bench batch).  The first
+	// VitView::n_team sentences of the launch order are therefore analysed by TEAMS of KB_TEAM warps: all warps of a team walk the
+	// lattice together; the candidates of a node are dealt round-robin to the warps, each warp evaluates its candidates
+	// (classification, enumeration, LM chase, de-duplication: all per-candidate state) into a private staging region of the
+	// sentence's path pool, and after a team barrier the per-candidate segments are copied to their final places in candidate
+	// order - the pool ends up byte-identical to the single-warp result.  Order-dependent steps (shortcut / general candidates,
+	// pruning, reachability, the end node, stitching) stay on the team's first warp and their results are broadcast.
+#ifndef KB_TEAM
+#define KB_TEAM 4
+#endif
+	static constexpr uint32_t TEAM = KB_TEAM, TEAMS_PER_BLOCK = KB_VIT_WARPS / KB_TEAM > 0 ? KB_VIT_WARPS / KB_TEAM : 1;
+	static_assert(KB_VIT_WARPS % KB_TEAM == 0 || KB_VIT_WARPS < KB_TEAM, "teams tile the block");
+	struct TeamSmem
+	{
+		uint32_t cnt[GROUP];         // entries per candidate of the current group (written by the owning warp)
+		uint32_t val[2][4];          // broadcast slots (alternating, see Vit::teamBroadcast)
+		uint32_t err;
+	};
+
 	struct Vit
 	{
 		const BatchView& bv;
@@ -401,14 +424,42 @@ namespace KB_VIT_NS
 		uint32_t* npOff; uint32_t* npCnt; uint8_t* reach;
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
+		uint32_t top1Buckets = 1;           // bucket count of the reference's `top1` unordered_set, per sentence (unordered_emu.h)
 		DCand* dcur = nullptr; uint32_t curBuf = 0, pfPhase = 0; const DCand* pfBase[2] = { nullptr, nullptr };      // candidate-row staging (see prefetchCands)
 		uint2* nodeCand = nullptr;
 		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0, nFw = 1;
 		uint32_t nClasses = 0, classCommon = 0; bool classOverflow = false;
-		volatile uint32_t* sActive = nullptr; uint32_t roundCnt = 0;       // block-level lockstep over lattice nodes (see viterbi_kernel)
+		// team mode (the heaviest sentences): KB_TEAM warps share one sentence, see TeamSmem
+		uint32_t teamRank = 0, teamSize = 1, teamBar = 0, teamSeq = 0; struct TeamSmem* tm = nullptr;
 		bool splitComplex, splitSaisiot, mergeSaisiot;
 
 		__device__ Vit(const BatchView& _bv, const VitView& _vv, uint32_t _lane) : bv{ _bv }, vv{ _vv }, lane{ _lane } {}
+
+		// ---- team primitives (no-ops for a single warp)
+		__device__ __forceinline__ bool leader() const { return teamRank == 0; }
+		__device__ __forceinline__ void teamSync()
+		{
+			if (teamSize == 1) return;
+			__syncwarp();
+#ifdef KB_HOSTSIM
+			simt::bar_sync(teamBar, teamSize * 32);
+#else
+			asm volatile("bar.sync %0, %1;" :: "r"(teamBar), "r"(teamSize * 32) : "memory");
+#endif
+		}
+		// the first warp's (a, b, c) and the team's error state become everybody's: one barrier; the two slots alternate so that a
+		// slot is rewritten only after every reader has passed one more barrier
+		__device__ __forceinline__ void teamBroadcast(uint32_t& a, uint32_t& b, uint32_t& c)
+		{
+			if (teamSize == 1) return;
+			uint32_t* slot = tm->val[teamSeq & 1]; ++teamSeq;
+			if (leader() && lane == 0) { slot[0] = a; slot[1] = b; slot[2] = c; }
+			if (err && lane == 0) atomicMax(&tm->err, err);
+			teamSync();
+			a = slot[0]; b = slot[1]; c = slot[2];
+			err = tm->err;
+		}
+		__device__ __forceinline__ void teamBroadcast(uint32_t& a) { uint32_t b = 0, c = 0; teamBroadcast(a, b, c); }
 
 		// ---- left-form features of a path (what FormEvaluator will see), uniform per candidate ------
 		__device__ __noinline__ void leftFeat(uint32_t ownOff, uint32_t ownLen, uint32_t wid, int32_t morpheme, uint16_t& last, uint8_t& pol) const
@@ -504,6 +555,44 @@ namespace KB_VIT_NS
 			int32_t dotCol;          // column of this candidate in sm->dots, -1 = not computed
 #endif
 		};
+
+		// writeTo of the `top1` container (BestPathContainer.hpp:229-276): the candidate's E entries [candBeg, candBeg + E) are in
+		// first-insertion order; the reference emits them in its unordered_set's iteration order (unordered_emu.h)
+		__device__ __noinline__ void reorderTop1(uint32_t candBeg, uint32_t E)
+		{
+			if (E == 0) return;
+			const uint32_t Bafter = unorderedBucketsAfter(top1Buckets, E);
+			if (!Bafter) { err = ST_INTERNAL; return; }
+			if (E == 1) { top1Buckets = Bafter; return; }
+			const size_t need = (size_t)2 * E * sizeof(DPath) + (size_t)E * 16 + (size_t)Bafter * 4;
+			if ((size_t)candBeg * sizeof(DPath) + need > (size_t)poolCap * sizeof(DPath)) { err = ST_PATH_OVERFLOW; return; }
+			DPath* tmp = pool + candBeg + E;
+			unsigned long long* codes = reinterpret_cast<unsigned long long*>(pool + candBeg + 2 * (size_t)E);
+			int32_t* next = reinterpret_cast<int32_t*>(codes + E); int32_t* order = next + E; int32_t* buckets = order + E;
+			#pragma unroll 1
+			for (uint32_t e = lane; e < E; e += 32)
+			{
+				const DPath p = pool[candBeg + e];
+				tmp[e] = p;
+				// Hash<WordLL> (BestPathContainer.hpp:79-84) over Hash<LmState>: std::hash<int32_t> for Knlm (Knlm.hpp:1170-1178), Hash<uint32_t>(node) for CoNg
+#if KB_CONG
+				const unsigned long long v = (uint32_t)p.lm_state;
+				unsigned long long h = (v * 2305843009213693951ull) ^ ((v << 33) | (v >> 31));
+#else
+				unsigned long long h = (unsigned long long)(long long)p.lm_state;
+#endif
+				codes[e] = (unsigned long long)((uint32_t)p.prev_root_id | ((uint32_t)p.sp_state << 8)) ^ ((h << 3) | (h >> 61));
+			}
+			__syncwarp();
+			uint32_t B = top1Buckets;
+			if (lane == 0) { if (!unorderedSetOrder(codes, (int32_t)E, B, next, buckets, order)) order[0] = -1; }
+			__syncwarp();
+			if (order[0] < 0) { err = ST_INTERNAL; return; }
+			#pragma unroll 1
+			for (uint32_t j = lane; j < E; j += 32) pool[candBeg + j] = tmp[order[j]];
+			__syncwarp();
+			top1Buckets = Bafter;
+		}
 
 		__device__ __noinline__ void evalCand(uint32_t nodeIdx, const DNode& node, const CandCtx& cc, uint32_t inBeg, uint32_t inEnd, uint32_t mode)
 		{
@@ -851,6 +940,7 @@ namespace KB_VIT_NS
 				for (uint32_t e = lane; e < E; e += 32) pool[candBeg + e] = pool[candBeg + E + e];
 				__syncwarp();
 			}
+			if (mode == 2) { reorderTop1(candBeg, E); if (err) return; }
 			top = candBeg + E;
 		}
 
@@ -894,7 +984,6 @@ namespace KB_VIT_NS
 			if (lane == 0)
 			{
 				const uint32_t bytes = cnt * (uint32_t)sizeof(DCand), bar = smemAddr(&sm->mbar[buf]);
-				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 				asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 					:: "r"(smemAddr(&sm->dcandBuf[buf][0])), "l"(base), "r"(bytes), "r"(bar) : "memory");
@@ -1222,6 +1311,7 @@ namespace KB_VIT_NS
 					kept += min(inBucket, 128u);
 				}
 				__syncwarp();
+				if (lane == 0) sm->candNew[k] = kept;      // (team mode publishes the final per-candidate counts)
 				w += kept; r += cnt;
 			}
 			// every lane has read sm->cdyn / sm->candNew of this group: the caller overwrites them for the next group
@@ -1439,7 +1529,7 @@ namespace KB_VIT_NS
 #if KB_TMA_ROWS
 			if (first)
 			{
-				curBuf ^= 1u; dcur = sm->dcandBuf[curBuf];
+				curBuf ^= 1u;
 				if (pfBase[curBuf] != nullptr) { const bool hit = pfBase[curBuf] == candBase; pfWait(curBuf); rowsStaged = hit; }
 			}
 #else
@@ -1459,12 +1549,12 @@ namespace KB_VIT_NS
 #ifndef KB_CONG_PIPELINE
 #define KB_CONG_PIPELINE 1
 #endif
-			const bool itemOK = KB_CONG_PIPELINE && P <= STAGE_CAP;      // else every candidate goes through evalCand; always in the transposed evaluator's order
+			const bool itemOK = KB_CONG_PIPELINE && P <= 512;      // else (the reference's `top1` container) every candidate goes through evalCand; always in the transposed evaluator's order
 			const CongNode cgn = congPrepare(node, spaceBefore, candBase, nCandsIn, inBeg, P);
 			if (err) return;
 			const uint32_t nCands = cgn.nOrdered;
 #else
-			const bool itemOK = P <= STAGE_CAP;          // modes 0 / 1 always; mode 2 (top1) up to the staging capacity
+			const bool itemOK = P <= 512;                // modes 0 / 1: the item pipeline; mode 2 (`top1`, an unordered_set in the reference): evalCand + reorderTop1
 			const uint32_t nCands = nCandsIn;
 #endif
 			FlushCtx fc;
@@ -1484,6 +1574,9 @@ namespace KB_VIT_NS
 				for (uint32_t gb = 0; gb < nCands; gb += GROUP)
 				{
 					const uint32_t gcount = min(GROUP, nCands - gb);
+#if KB_TMA_ROWS
+					dcur = (rowsStaged && gb == 0) ? sm->dcandBuf[curBuf] : sm->dcandGen;
+#endif
 					// ---- classification, one lane per candidate (PathEvaluator.hpp:382-448 + evalSingleMorpheme head 531-560), from the static rows
 					uint32_t myPack = CLS_SKIP, myValid = 0, myCondFail = 0, mySets = 0;
 					{
@@ -1499,7 +1592,7 @@ namespace KB_VIT_NS
 #endif
 							uint4 r0, r1, r2;
 							uint4* dst = reinterpret_cast<uint4*>(&dcur[lane]);
-							if (rowsStaged && gb == 0 && (ignoreCond == 0 || nCands <= GROUP)) { r1 = dst[1]; r2 = dst[2]; }      // the block is already in shared memory (bulk copy)
+							if (rowsStaged && gb == 0) { r1 = dst[1]; r2 = dst[2]; }      // the block is already in shared memory (bulk copy)
 							else
 							{
 								r0 = reinterpret_cast<const uint4*>(src)[0]; r1 = reinterpret_cast<const uint4*>(src)[1]; r2 = reinterpret_cast<const uint4*>(src)[2];
@@ -1594,7 +1687,20 @@ namespace KB_VIT_NS
 						fc.epFirst = cgn.epFirst; fc.dotMask = dotMask;
 					}
 #endif
-					const uint32_t groupBase = top;
+					// team mode: a group whose candidates all take the item pipeline is dealt to the warps of the team (candidate k -> warp k mod
+					// team size), every warp writing into its own staging region of the pool; any other group is the first warp's alone
+					const bool teamGroup = teamSize > 1 && !__any_sync(FULL, (myPack & 0xFF) >= CLS_GENERAL);
+					const uint32_t groupBase = top, poolCap0 = poolCap;
+					uint32_t half = 0, myBase = top;
+					if (teamGroup)
+					{
+						half = (poolCap0 - top) / 2;
+						const uint32_t regionSize = half / teamSize;
+						myBase = top + half + teamRank * regionSize;
+						poolCap = myBase + regionSize; top = myBase;
+					}
+					auto walk = [&]()
+					{
 					resetIndex();
 					nFw = 1;
 
@@ -1605,6 +1711,7 @@ namespace KB_VIT_NS
 						const uint32_t packK = __shfl_sync(FULL, myPack, k);
 						const uint32_t cls = packK & 0xFF, kfl = packK >> 8;
 						if (cls == CLS_SKIP) continue;
+						if (teamGroup && (k % teamSize) != teamRank) continue;
 						if (cls == CLS_ITEM)
 						{
 							const uint32_t vmK = __shfl_sync(FULL, myValid, k), setsK = __shfl_sync(FULL, mySets, k);
@@ -1713,13 +1820,54 @@ namespace KB_VIT_NS
 						resetIndex();
 					}
 					flushItems(fc); if (err) return;
-					if (itemOK) { fixupGroup(groupBase, gcount, mode); if (err) return; }
+					if (itemOK) { fixupGroup(myBase, gcount, mode); if (err) return; }
+					};
+					if (teamSize == 1) { walk(); if (err) return; }
+					else if (teamGroup)
+					{
+						walk();
+						// publish the per-candidate entry counts of my candidates, then place every segment in candidate order
+						if (lane < gcount && (lane % teamSize) == teamRank) tm->cnt[lane] = sm->candNew[lane];
+						if (err && lane == 0) atomicMax(&tm->err, err);
+						teamSync();
+						err = tm->err; poolCap = poolCap0;
+						if (err) return;
+						const uint32_t cnt = lane < gcount ? tm->cnt[lane] : 0;
+						uint32_t incl = cnt;
+						for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += t; }
+						const uint32_t total = __shfl_sync(FULL, incl, 31), excl = incl - cnt;
+						if (total > half) { err = ST_PATH_OVERFLOW; return; }
+						uint32_t src = myBase;
+						#pragma unroll 1
+						for (uint32_t k = teamRank; k < gcount; k += teamSize)
+						{
+							const uint32_t c = __shfl_sync(FULL, cnt, k), dst = groupBase + __shfl_sync(FULL, excl, k);
+							#pragma unroll 1
+							for (uint32_t e = lane; e < c; e += 32)
+							{
+								const uint4* sp = reinterpret_cast<const uint4*>(pool + src + e); uint4* dp = reinterpret_cast<uint4*>(pool + dst + e);
+								const uint4 a = sp[0], b = sp[1], cc = sp[2];
+								dp[0] = a; dp[1] = b; dp[2] = cc;
+							}
+							src += c;
+						}
+						teamSync();
+						top = groupBase + total;
+					}
+					else
+					{
+						if (leader()) walk();
+						uint32_t t = top; teamBroadcast(t); top = t;
+						if (err) return;
+					}
 				}
 				if (top > nodeBeg) break;
 			}
 
 			// prune (PathEvaluator.hpp:475-511): per root slot the best score of the paths whose morpheme has no combine socket;
 			// scores are compared as order-preserving unsigned keys, the threshold test itself stays a float comparison
+			if (leader())
+			{
 			const uint32_t cntAll = top - nodeBeg;
 			const uint32_t NEG_INF_ORD = 0x007FFFFFu;      // key of -inf
 			uint32_t mxo0 = NEG_INF_ORD, mxo1 = NEG_INF_ORD, mxo2 = NEG_INF_ORD;
@@ -1772,6 +1920,8 @@ namespace KB_VIT_NS
 				valid += __popc(km);
 			}
 			top = nodeBeg + valid;
+			}
+			if (teamSize > 1) { uint32_t t = top; teamBroadcast(t); top = t; }
 		}
 
 		// PathEvaluator.hpp:1159-1176; predecessors of a node are the contiguous group [k - prev, ...] linked by sibling == 1
@@ -1828,7 +1978,7 @@ namespace KB_VIT_NS
 			stagedNode = NPOS;
 			// BOS path (PathEvaluator.hpp:1224-1226)
 			if (top + 1 > poolCap) { err = ST_PATH_OVERFLOW; return 0; }
-			if (lane == 0)
+			if (lane == 0 && leader())
 			{
 				DPath b;
 #if KB_CONG
@@ -1851,12 +2001,12 @@ namespace KB_VIT_NS
 				pool[top] = b;
 				npOff[0] = top; npCnt[0] = 1; reach[0] = 1;
 			}
-			for (uint32_t i = lane + 1; i < N; i += 32) reach[i] = 0;
+			if (leader()) for (uint32_t i = lane + 1; i < N; i += 32) reach[i] = 0;
 			top += 1;
 			__syncwarp();
 
 			// per node: where its candidate rows are (a form's block of the static table, or the unknown NNG / NNP rows) - lane-parallel
-			for (uint32_t j = 1 + lane; j + 1 < N; j += 32)
+			if (leader()) for (uint32_t j = 1 + lane; j + 1 < N; j += 32)
 			{
 				const int32_t fm = nodes[j].form;
 				uint2 ci;
@@ -1865,6 +2015,7 @@ namespace KB_VIT_NS
 				nodeCand[j] = ci;
 			}
 			__syncwarp();
+			teamSync();
 #if KB_TMA_ROWS
 			if (N > 2) { const uint2 c1 = nodeCand[1]; pfIssue(c_m.cands + c1.x, min(c1.y & 0xFFFFu, GROUP), curBuf ^ 1u); }
 #endif
@@ -1893,10 +2044,17 @@ namespace KB_VIT_NS
 						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk + 1, 1, unkScore, ~(uint32_t)node.form, f.str_len, inBeg, inEnd, false);
 						if (err) return 0;
 					}
-					const bool r = anyNonSocket(nodeBeg, top);
-					if (lane == 0) reach[i] = r ? 1 : 0;
-					__syncwarp();
-					if (isDisconnected(i + 1))
+					uint32_t disc = 0;
+					if (leader())
+					{
+						const bool r = anyNonSocket(nodeBeg, top);
+						if (lane == 0) reach[i] = r ? 1 : 0;
+						__syncwarp();
+						disc = isDisconnected(i + 1) ? 1u : 0u;
+					}
+					teamBroadcast(disc);
+					if (err) return 0;
+					if (disc)
 					{
 						const uint32_t len = node.end_pos - node.start_pos;
 						const float unkScore = unkFormScore(norm + node.start_pos, len);
@@ -1910,20 +2068,11 @@ namespace KB_VIT_NS
 					evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.uform_off, node.uform_len, inBeg, inEnd, true);
 					if (err) return 0;
 				}
-				if (lane == 0) { npOff[i] = nodeBeg; npCnt[i] = top - nodeBeg; }
+				if (lane == 0 && leader()) { npOff[i] = nodeBeg; npCnt[i] = top - nodeBeg; }
 				__syncwarp();
-#ifdef KB_LOCKSTEP
-				// keep the warps of the block at the same lattice-node phase: they then share instruction-cache lines
-#ifndef KB_LOCKSTEP_EVERY
-#define KB_LOCKSTEP_EVERY 1
-#endif
-				if (KB_LOCKSTEP_EVERY == 1 || (i % KB_LOCKSTEP_EVERY) == 0)
-				{
-					asm volatile("bar.sync 1, %0;" :: "r"(roundCnt) : "memory");
-					roundCnt = *sActive;
-				}
-#endif
+				teamSync();
 			}
+			if (!leader()) return 0;      // the end node and the stitching are the first warp's; the others wait for its broadcast
 
 			// ---- end node (PathEvaluator.hpp:1320-1357): candidates go to the pool tail as temporary records
 			uint32_t inBeg, inEnd;
@@ -2013,6 +2162,9 @@ namespace KB_VIT_NS
 			}
 			if (nReal == 0) return 0;
 			__syncwarp();
+#ifdef KB_HOSTSIM
+			if (lane == 0 && std::getenv("HS32_TRACE_END")) { std::fprintf(stderr, "[hs32] end cands %u:", nReal); for (uint32_t z = 0; z < nReal; ++z) { const DPath* r = pool + candBeg + sr[z].idx; std::fprintf(stderr, " (%d,%d,%a,n%d,p%u)", r->root_id, r->sp_state, r->acc_score, pool[r->parent].node, r->parent); } std::fprintf(stderr, "\n"); }
+#endif
 			if (lane == 0) stdSortEmu(sr, (long)nReal);
 			__syncwarp();
 			// groups = runs of equal (rootId, spState) in the sorted order; keep the first ceil(2 / #groups) of every group
@@ -2063,40 +2215,36 @@ namespace KB_VIT_NS
 	#ifndef KB_VIT_MIN_BLOCKS
 #define KB_VIT_MIN_BLOCKS (KB_CONG ? 3 : 4)
 #endif
-#ifndef KB_SOLO
-#define KB_SOLO 0
-#endif
 	__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, KB_VIT_MIN_BLOCKS) KB_VIT_KERNEL(const BatchView bv, const VitView vv)
 	{
 #ifdef KB_HOSTSIM
-		alignas(16) static unsigned char smRaw[sizeof(WarpSmem) * WARPS_PER_BLOCK];      // tests/hostsim: one static arena
+		alignas(16) static unsigned char smRaw[sizeof(WarpSmem) * WARPS_PER_BLOCK + sizeof(TeamSmem) * TEAMS_PER_BLOCK];      // tests/hostsim: one static arena
 #else
 		extern __shared__ __align__(16) unsigned char smRaw[];
 #endif
 		WarpSmem* smAll = reinterpret_cast<WarpSmem*>(smRaw);
+		TeamSmem* teamSm = reinterpret_cast<TeamSmem*>(smRaw + sizeof(WarpSmem) * WARPS_PER_BLOCK);
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-		// The first KB_SOLO blocks (the longest sentences in LPT order) hold ONE sentence each: the kernel time is the time of
-		// its heaviest sentence, and alone in its block that sentence never waits at the lockstep barrier for a block mate.
-		const uint32_t slot = blockIdx.x < KB_SOLO ? (wib == 0 ? blockIdx.x : 0xFFFFFFFFu) : KB_SOLO + (blockIdx.x - KB_SOLO) * WARPS_PER_BLOCK + wib;
-#ifdef KB_LOCKSTEP
-		__shared__ uint32_t sActiveCount;
-		if (threadIdx.x == 0) sActiveCount = 0;
+		// The first n_team sentences of the launch order (the heaviest) get a TEAM of warps each: the blocks [0, nTeamBlocks) hold
+		// TEAMS_PER_BLOCK teams; every other sentence gets one warp.
+		const uint32_t nTeam = min(vv.n_team, bv.n_sent);
+		const uint32_t nTeamBlocks = (nTeam + TEAMS_PER_BLOCK - 1) / TEAMS_PER_BLOCK;
+		if (threadIdx.x < TEAMS_PER_BLOCK) teamSm[threadIdx.x].err = 0;
 		__syncthreads();
-		const bool inRange = slot < bv.n_sent;
-		const uint32_t s = inRange ? bv.order[slot] : 0;
-		const bool failed = inRange && bv.status[s] != 0;
-		if (inRange && !failed && lane == 0) atomicAdd(&sActiveCount, 32u);
-		__syncthreads();
-		if (!inRange) return;
-		if (failed) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
-#else
+		uint32_t slot, teamRank = 0, teamSize = 1, teamIdx = 0;
+		if (blockIdx.x < nTeamBlocks)
+		{
+			teamIdx = wib / TEAM; teamRank = wib % TEAM; teamSize = TEAM;
+			slot = blockIdx.x * TEAMS_PER_BLOCK + teamIdx;
+			if (slot >= nTeam || wib >= TEAMS_PER_BLOCK * TEAM) return;      // (whole teams leave together)
+		}
+		else slot = nTeam + (blockIdx.x - nTeamBlocks) * WARPS_PER_BLOCK + wib;
 		if (slot >= bv.n_sent) return;
 		const uint32_t s = bv.order[slot];
-		if (bv.status[s]) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
-#endif
+		if (bv.status[s]) { if (lane == 0 && teamRank == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
 
 #ifndef KB_HOSTSIM
-		if (lane == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s] = tns; }
+		if (lane == 0 && teamRank == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s] = tns; }
 #endif
 		const uint32_t t0 = bv.text_off[s], t1 = bv.text_off[s + 1];
 		const uint32_t n = t1 - t0;
@@ -2111,10 +2259,8 @@ namespace KB_VIT_NS
 		v.poolCap = vv.paths_per_unit * W + vv.paths_const;
 		v.top = 0;
 		v.sm = &smAll[wib]; v.ht = smAll[wib].ht; v.htUsed = 1;
-		v.dcur = smAll[wib].dcandBuf[0];
-#ifdef KB_LOCKSTEP
-		v.sActive = &sActiveCount; v.roundCnt = sActiveCount;
-#endif
+		v.dcur = smAll[wib].dcandGen;
+		v.teamRank = teamRank; v.teamSize = teamSize; v.teamBar = 1 + teamIdx; v.tm = &teamSm[teamIdx];
 		v.splitComplex = (bv.match_options >> 22) & 1; v.splitSaisiot = (bv.match_options >> 25) & 1; v.mergeSaisiot = (bv.match_options >> 26) & 1;
 		v.htClear();
 #if KB_TMA_ROWS
@@ -2144,9 +2290,10 @@ namespace KB_VIT_NS
 
 			PathRes res[MAX_RESULTS];
 			const uint32_t K = v.findBestPath(ch, res, false);
-			if (v.err) break;
 
-			// ---- insertPathIntoResults, topN == 1 (src/Kiwi.cpp:629-782), all lanes redundantly
+			// ---- insertPathIntoResults, topN == 1 (src/Kiwi.cpp:629-782), all lanes redundantly (team mode: the first warp's lanes)
+			auto stitch = [&]()
+			{
 			struct Ret { float score; uint8_t sp; int32_t rec; uint32_t parent; };
 			Ret ret[2 + MAX_RESULTS]; uint32_t nRet = 0;
 			if (retN == 0)      // `ret.empty()` in the reference: also true again after a chunk that kept nothing
@@ -2181,7 +2328,7 @@ namespace KB_VIT_NS
 					else { v.err = ST_INTERNAL; break; }
 				}
 			}
-			if (v.err) break;
+			if (v.err) return;
 			// keep the first path per curState, accumulate, then sort by score and keep 2
 			Ret kept[2 + MAX_RESULTS]; uint32_t nKept = 0;
 			uint8_t seenSt[2 + MAX_RESULTS]; uint32_t nSeen = 0;
@@ -2211,21 +2358,24 @@ namespace KB_VIT_NS
 				++nRecs;
 			}
 			__syncwarp();
+			};
+			if (v.leader() && !v.err) stitch();
+			if (v.teamSize > 1)
+			{
+				// what the other warps of the team need for the next chunk: how many results survive and their special states, the pool top
+				uint32_t a = retN | ((uint32_t)retSp[0] << 8) | ((uint32_t)retSp[1] << 16), b = v.top, cc = 0;
+				v.teamBroadcast(a, b, cc);
+				retN = a & 0xFF; retSp[0] = (uint8_t)(a >> 8); retSp[1] = (uint8_t)(a >> 16); v.top = b;
+			}
+			if (v.err) break;
 		}
 
 		// the best stitched result (ret[0]); tokens are materialised by emit_kernel
 		(void)normLen;
-#ifdef KB_LOCKSTEP
-		// leave the lockstep: shrink the participant count for the next round and satisfy the current one without waiting
-		if (lane == 0) atomicSub(&sActiveCount, 32u);
-		__threadfence_block();
-		__syncwarp();
-		asm volatile("bar.arrive 1, %0;" :: "r"(v.roundCnt) : "memory");
-#endif
 #ifndef KB_HOSTSIM
-		if (lane == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s + 1] = tns; }
+		if (lane == 0 && teamRank == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s + 1] = tns; }
 #endif
-		if (lane == 0)
+		if (lane == 0 && teamRank == 0)
 		{
 			vv.best_rec[s] = (!v.err && retN) ? retRec[0] : -1;
 			vv.score[s] = (!v.err && retN) ? retScore[0] : 0.f;
@@ -2288,14 +2438,15 @@ namespace KB_VIT_NS
 	cudaError_t KB_LAUNCH(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
-		const uint32_t blocks = bv.n_sent <= KB_SOLO ? bv.n_sent : KB_SOLO + (bv.n_sent - KB_SOLO + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+		const uint32_t nTeam = vv.n_team < bv.n_sent ? vv.n_team : bv.n_sent;
+		const uint32_t blocks = (nTeam + TEAMS_PER_BLOCK - 1) / TEAMS_PER_BLOCK + (bv.n_sent - nTeam + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 		static bool attrSetOn[64] = {};      // function attributes are per device (the caller holds that device's lock)
 		int devId = 0;
 #ifndef KB_HOSTSIM
 		cudaGetDevice(&devId);
 #endif
 		bool& attrSet = attrSetOn[devId & 63];
-		const size_t smemBytes = sizeof(WarpSmem) * WARPS_PER_BLOCK;
+		const size_t smemBytes = sizeof(WarpSmem) * WARPS_PER_BLOCK + sizeof(TeamSmem) * TEAMS_PER_BLOCK;
 		if (!attrSet)
 		{
 			cudaFuncSetAttribute(KB_VIT_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
@@ -2304,10 +2455,10 @@ namespace KB_VIT_NS
 			attrSet = true;
 		}
 #ifdef KB_HOSTSIM
-		// tests/hostsim (32 threads = one warp per block): blocks of one warp own the slots blockIdx * WARPS_PER_BLOCK only
+		// tests/hostsim: one sentence, one block of WARPS_PER_BLOCK warps (one warp works, or - n_team == 1 - one team)
 		if (bv.n_sent != 1) return 1;
 		(void)stream; (void)smemBytes;
-		simt::launch(blocks, 32, [&] { KB_VIT_KERNEL(bv, vv); });
+		simt::launch(blocks, WARPS_PER_BLOCK * 32, [&] { KB_VIT_KERNEL(bv, vv); });
 		return cudaSuccess;
 #else
 		KB_VIT_KERNEL<<<blocks, WARPS_PER_BLOCK * 32, smemBytes, stream>>>(bv, vv);

@@ -980,6 +980,7 @@ namespace orc
 					else { w.spState = p.spState; cand.push_back(w); }
 				}
 			}
+			if (std::getenv("ORC_TRACE_END")) { std::fprintf(stderr, "[orc] end cands %zu:", cand.size()); for (auto& c : cand) std::fprintf(stderr, " (%d,%d,%a,n%d,i%d)", c.rootId, c.spState, c.accScore, c.parentNode, c.parentIdx); std::fprintf(stderr, "\n"); }
 			std::sort(cand.begin(), cand.end(), [](const WordLL& a, const WordLL& b)
 			{
 				if (a.rootId < b.rootId) return true;

@@ -66,10 +66,12 @@ template<class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, 
 
 namespace simt
 {
-	constexpr uint32_t W = 32;
+	constexpr uint32_t W = 32;          // lanes of a warp
+	constexpr uint32_t TMAX = 512;      // threads of a block (multi-warp blocks: collectives are per warp, barriers per block)
 	struct Dim { uint32_t x = 0, y = 0, z = 0; };
 	// one fiber per lane inside ONE OS thread: the per-lane "registers" below are swapped by the scheduler at every switch
-	inline uint32_t lane = 0;
+	inline uint32_t lane = 0;           // lane inside the warp
+	inline uint32_t tid = 0;            // thread inside the block (fiber index)
 	inline Dim threadIdx, blockIdx;
 	inline Dim blockDim, gridDim;
 
@@ -110,18 +112,19 @@ kb_simt_switch:
 	ret
 	.size kb_simt_switch,.-kb_simt_switch
 )");
-	enum St : uint8_t { RUN, WAIT_FULL, WAIT_PART, DONE };
+	enum St : uint8_t { RUN, WAIT_FULL, WAIT_PART, WAIT_BAR, DONE };
 	struct Sched
 	{
-		Ctx mainCtx; Ctx ctx[W];
+		Ctx mainCtx; Ctx ctx[TMAX];
 		std::vector<char> stacks;
-		uint32_t nLanes = W;
-		St st[W];
-		void* site[W];
-		uint64_t fullVal[W], fullRes[W];
-		uint64_t partTag[W]; unsigned partGrp[W]; uint32_t partVal[W]; uint32_t partSnap[W][W];
-		uint64_t collectives = 0; uint64_t ep[W];
-		uint64_t epochOf[W], subEpochOf[W], subCountOf[W];
+		uint32_t nLanes = W;                 // threads of the block
+		St st[TMAX];
+		void* site[TMAX];
+		uint64_t fullVal[TMAX], fullRes[TMAX];
+		uint64_t partTag[TMAX]; unsigned partGrp[TMAX]; uint32_t partVal[TMAX]; uint32_t partSnap[TMAX][W];
+		uint32_t barId[TMAX], barCount[TMAX];      // bar.sync id, count (count 0 = every thread that has not exited: __syncthreads)
+		uint64_t collectives = 0; uint64_t ep[TMAX];
+		uint64_t epochOf[TMAX], subEpochOf[TMAX], subCountOf[TMAX];
 	};
 	inline Sched* sched = nullptr;
 	inline const bool ascending = std::getenv("HS32_ASCENDING") != nullptr;      // experiment: lowest runnable lane first
@@ -141,27 +144,60 @@ kb_simt_switch:
 	}
 
 	// main context.  Releases complete collectives, then returns the highest runnable lane (-1: all lanes done).
+	// completion checks for the things thread `me` may have just completed by arriving (or by exiting)
+	inline void onArrive(Sched& sc, uint32_t me)
+	{
+		const uint32_t wb = me & ~(W - 1), we = std::min(wb + W, sc.nLanes);
+		// full-warp collective of my warp: every lane of the warp that has not exited waits in one
+		{
+			bool allFull = true, any = false;
+			for (uint32_t l = wb; l < we; ++l) if (sc.st[l] != DONE) { any = true; if (sc.st[l] != WAIT_FULL) allFull = false; }
+			if (any && allFull)
+			{
+				// (call sites are not compared: the compiler duplicates one source-level collective into several branches)
+				for (uint32_t l = wb; l < we; ++l) sc.fullRes[l] = sc.fullVal[l];
+				for (uint32_t l = wb; l < we; ++l) if (sc.st[l] == WAIT_FULL) sc.st[l] = RUN;
+				++sc.collectives;
+			}
+		}
+		if (sc.st[me] == WAIT_PART)
+		{
+			const uint32_t l = me;
+			bool ready = true;
+			for (uint32_t k = 0; k < W; ++k) if ((sc.partGrp[l] >> k & 1) && !(wb + k < sc.nLanes && sc.st[wb + k] == WAIT_PART && sc.partTag[wb + k] == sc.partTag[l])) ready = false;
+			if (ready)
+			{
+				const unsigned grp = sc.partGrp[l];
+				for (uint32_t k = 0; k < W; ++k) if (grp >> k & 1) for (uint32_t j = 0; j < W; ++j) if (grp >> j & 1) sc.partSnap[wb + k][j] = sc.partVal[wb + j];
+				for (uint32_t k = 0; k < W; ++k) if (grp >> k & 1) sc.st[wb + k] = RUN;
+			}
+		}
+		// block barriers (bar.sync id, count): complete when `count` threads wait on the id (count 0: all threads that have not exited)
+		if (sc.st[me] == WAIT_BAR || sc.st[me] == DONE)
+		{
+			for (uint32_t pass = 0; pass < 1; ++pass)
+			{
+				uint32_t alive = 0;
+				for (uint32_t k = 0; k < sc.nLanes; ++k) if (sc.st[k] != DONE) ++alive;
+				// ids that may complete: mine (arrival), or any id-0 style barrier when a thread exited
+				for (uint32_t l = 0; l < sc.nLanes; ++l)
+				{
+					if (sc.st[l] != WAIT_BAR) continue;
+					if (sc.st[me] == WAIT_BAR && sc.barId[l] != sc.barId[me]) continue;
+					const uint32_t id = sc.barId[l];
+					uint32_t waiting = 0;
+					for (uint32_t k = 0; k < sc.nLanes; ++k) if (sc.st[k] == WAIT_BAR && sc.barId[k] == id) ++waiting;
+					const uint32_t need = sc.barCount[l] ? sc.barCount[l] : alive;
+					if (waiting >= need) for (uint32_t k = 0; k < sc.nLanes; ++k) if (sc.st[k] == WAIT_BAR && sc.barId[k] == id) sc.st[k] = RUN;
+					if (sc.st[me] == WAIT_BAR || sc.st[me] == RUN) break;      // my id has been checked
+				}
+			}
+		}
+	}
+
+	// main context.  Returns the highest runnable lane (-1: all lanes done).
 	inline int reschedule(Sched& sc)
 	{
-		bool allFull = true, any = false;
-		for (uint32_t l = 0; l < sc.nLanes; ++l) if (sc.st[l] != DONE) { any = true; if (sc.st[l] != WAIT_FULL) allFull = false; }
-		if (any && allFull)
-		{
-			// (call sites are not compared: the compiler duplicates one source-level collective into several branches)
-			for (uint32_t l = 0; l < sc.nLanes; ++l) sc.fullRes[l] = sc.fullVal[l];
-			for (uint32_t l = 0; l < sc.nLanes; ++l) if (sc.st[l] == WAIT_FULL) sc.st[l] = RUN;
-			++sc.collectives;
-		}
-		for (uint32_t l = 0; l < sc.nLanes; ++l)
-		{
-			if (sc.st[l] != WAIT_PART) continue;
-			bool ready = true;
-			for (uint32_t k = 0; k < W; ++k) if ((sc.partGrp[l] >> k & 1) && !(k < sc.nLanes && sc.st[k] == WAIT_PART && sc.partTag[k] == sc.partTag[l])) ready = false;
-			if (!ready) continue;
-			const unsigned grp = sc.partGrp[l];
-			for (uint32_t k = 0; k < W; ++k) if (grp >> k & 1) for (uint32_t j = 0; j < W; ++j) if (grp >> j & 1) sc.partSnap[k][j] = sc.partVal[j];
-			for (uint32_t k = 0; k < W; ++k) if (grp >> k & 1) sc.st[k] = RUN;
-		}
 		int next = -1;
 		if (ascending) { for (int l = 0; l < (int)sc.nLanes; ++l) if (sc.st[l] == RUN) { next = l; break; } }
 		else for (int l = (int)sc.nLanes - 1; l >= 0; --l) if (sc.st[l] == RUN) { next = l; break; }
@@ -178,9 +214,17 @@ kb_simt_switch:
 	inline void blockAs(St state, void* site)
 	{
 		Sched& sc = *sched;
-		const uint32_t me = lane;
+		const uint32_t me = tid;
 		sc.st[me] = state; sc.site[me] = site; sc.ep[me] = epoch;
 		sc.epochOf[me] = epoch; sc.subEpochOf[me] = subEpoch; sc.subCountOf[me] = subCount;
+		onArrive(sc, me);
+		if (sc.st[me] == RUN && !ascending)
+		{
+			// I completed the collective: the highest runnable lane goes next - keep running when that is me
+			bool higher = false;
+			for (uint32_t l = sc.nLanes; l-- > me + 1;) if (sc.st[l] == RUN) { higher = true; break; }
+			if (!higher) return;
+		}
 		kb_simt_switch(&sc.ctx[me].sp, sc.mainCtx.sp);
 	}
 
@@ -188,17 +232,25 @@ kb_simt_switch:
 	{
 		static_assert(sizeof(T) <= 8, "exchange of <= 8-byte values");
 		uint64_t raw = 0; std::memcpy(&raw, &v, sizeof(T));
-		sched->fullVal[lane] = raw;
+		sched->fullVal[tid] = raw;
 		++epoch;
 		blockAs(WAIT_FULL, __builtin_return_address(0));
-		for (uint32_t i = 0; i < W; ++i) std::memcpy(&out[i], &sched->fullRes[i], sizeof(T));
+		const uint32_t wb = tid & ~(W - 1);
+		for (uint32_t i = 0; i < W; ++i) std::memcpy(&out[i], &sched->fullRes[wb + i], sizeof(T));
 	}
 
 	__attribute__((noinline)) inline void sync()
 	{
-		sched->fullVal[lane] = 0;
+		sched->fullVal[tid] = 0;
 		++epoch;
 		blockAs(WAIT_FULL, __builtin_return_address(0));
+	}
+
+	// bar.sync id, count (count in threads; 0 = __syncthreads over the threads that have not exited)
+	__attribute__((noinline)) inline void bar_sync(uint32_t id, uint32_t count)
+	{
+		sched->barId[tid] = id; sched->barCount[tid] = count;
+		blockAs(WAIT_BAR, __builtin_return_address(0));
 	}
 
 	// partial-mask collectives: a lane calls with the mask of ITS group; lanes outside any multi-member group may skip the call.
@@ -213,11 +265,11 @@ kb_simt_switch:
 			return r;
 		}
 		if (subEpoch != epoch) { subEpoch = epoch; subCount = 0; }
-		sched->partTag[lane] = ((epoch + 1) << 16) | ++subCount;
-		sched->partGrp[lane] = grp; sched->partVal[lane] = v;
+		sched->partTag[tid] = ((epoch + 1) << 16) | ++subCount;
+		sched->partGrp[tid] = grp; sched->partVal[tid] = v;
 		blockAs(WAIT_PART, __builtin_return_address(0));
 		uint32_t r = init;
-		for (uint32_t l = 0; l < W; ++l) if (grp >> l & 1) r = fn(r, sched->partSnap[lane][l]);
+		for (uint32_t l = 0; l < W; ++l) if (grp >> l & 1) r = fn(r, sched->partSnap[tid][l]);
 		return r;
 	}
 
@@ -258,25 +310,26 @@ kb_simt_switch:
 	inline void fiberEntry()
 	{
 		fiberBody(fiberArg);
-		sched->st[lane] = DONE; sched->site[lane] = nullptr;
-		kb_simt_switch(&sched->ctx[lane].sp, sched->mainCtx.sp);
+		sched->st[tid] = DONE; sched->site[tid] = nullptr;
+		onArrive(*sched, tid);
+		kb_simt_switch(&sched->ctx[tid].sp, sched->mainCtx.sp);
 		std::abort();      // a finished lane is never resumed
 	}
 	template<class F> inline void launch(uint32_t blocks, uint32_t blockDimX, F&& body)
 	{
-		const uint32_t lanes = std::min(blockDimX, W);
+		const uint32_t lanes = std::min(blockDimX, TMAX);
 		blockDim.x = blockDimX; gridDim.x = blocks;
 		constexpr size_t STACK = 1u << 20;
 		static Sched* scp = new Sched;          // lane stacks are allocated once per process and reused by every launch
 		Sched& sc = *scp;
-		if (sc.stacks.size() < STACK * W) sc.stacks.resize(STACK * W);
+		if (sc.stacks.size() < STACK * lanes) sc.stacks.resize(STACK * lanes);
 		using Fn = std::remove_reference_t<F>;
 		fiberBody = [](void* a) { (*reinterpret_cast<Fn*>(a))(); };
 		fiberArg = (void*)&body;
 		for (uint32_t b = 0; b < blocks; ++b)
 		{
 			sc.nLanes = lanes; sc.collectives = 0;
-			for (uint32_t l = 0; l < W; ++l) { sc.st[l] = l < lanes ? RUN : DONE; sc.site[l] = nullptr; sc.partTag[l] = 0; sc.epochOf[l] = sc.subEpochOf[l] = sc.subCountOf[l] = 0; }
+			for (uint32_t l = 0; l < TMAX; ++l) { sc.st[l] = l < lanes ? RUN : DONE; sc.site[l] = nullptr; sc.partTag[l] = 0; sc.epochOf[l] = sc.subEpochOf[l] = sc.subCountOf[l] = 0; }
 			for (uint32_t l = 0; l < lanes; ++l)
 			{
 				// initial frame: [mxcsr/fpcw][r15 r14 r13 r12 rbx rbp][return address = fiberEntry][alignment slot]
@@ -293,7 +346,7 @@ kb_simt_switch:
 			{
 				const int next = reschedule(sc);
 				if (next < 0) break;
-				lane = (uint32_t)next; threadIdx.x = (uint32_t)next; blockIdx.x = b;
+				tid = (uint32_t)next; lane = tid & (W - 1); threadIdx.x = tid; blockIdx.x = b;
 				epoch = sc.epochOf[next]; subEpoch = sc.subEpochOf[next]; subCount = sc.subCountOf[next];
 				kb_simt_switch(&sc.mainCtx.sp, sc.ctx[next].sp);
 			}
@@ -317,7 +370,7 @@ inline uint32_t __reduce_min_sync(unsigned grp, uint32_t v) { return simt::group
 inline uint32_t __reduce_or_sync(unsigned grp, uint32_t v) { return simt::groupReduce(grp, v, 0u, [](uint32_t a, uint32_t b) { return a | b; }); }
 inline uint32_t __reduce_add_sync(unsigned grp, uint32_t v) { return simt::groupReduce(grp, v, 0u, [](uint32_t a, uint32_t b) { return a + b; }); }
 inline void __syncwarp(unsigned = 0xFFFFFFFFu) { simt::sync(); }
-inline void __syncthreads() { simt::sync(); }      // one warp per block
+inline void __syncthreads() { simt::bar_sync(0, 0); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
