@@ -291,7 +291,8 @@ namespace kb
 			ck(cudaGetLastError(), "cost_kernel launch");
 			size_t sb2 = sc.sortTempBytes;
 			ck(cub::DeviceRadixSort::SortPairsDescending(sc.sortTemp, sb2, sc.lenKeys, sc.lenKeysOut, sc.idxIn, sc.orderVit, (int)n, 0, 32, st), "cub sort");
-			sc.bv.order = sc.orderVit;
+			static const bool byLength = [] { const char* e = std::getenv("KIWI_B200_LPT"); return e && std::string(e) == "len"; }();      // experiments: keep the length order
+			if (!byLength) sc.bv.order = sc.orderVit;
 			sc.vv.n_team = (uint32_t)((unsigned long long)n * teamPermille() / 1000);
 		}
 		ck(cudaEventRecord(ev[2], st), "event");

@@ -330,6 +330,8 @@ namespace kb
 			if (es.x == es.y) return false;
 			const uint32_t newId = nOut;
 			if (newId >= outCap) { err = ST_NODE_OVERFLOW; return false; }
+			// relative links (DNode::prev / sibling) and DPath::node are 16-bit: a chunk with more nodes is reported, never wrapped
+			if (newId >= 0xFFFFu) { err = ST_TOO_LONG; return false; }
 			// the scans that decided this append (hasFormAlready / isZFollowable / `es`) read endPosMap and out[]: every lane
 			// must be past them before lane 0 changes those arrays (found by the 32-lane host simulation, tests/hostsim)
 			__syncwarp();

@@ -430,7 +430,11 @@ namespace KB_VIT_NS
 		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0, nFw = 1;
 		uint32_t nClasses = 0, classCommon = 0; bool classOverflow = false;
 		// team mode (the heaviest sentences): KB_TEAM warps share one sentence, see TeamSmem
+#if KB_TEAM > 1
 		uint32_t teamRank = 0, teamSize = 1, teamBar = 0, teamSeq = 0; struct TeamSmem* tm = nullptr;
+#else
+		static constexpr uint32_t teamRank = 0, teamSize = 1, teamBar = 0; uint32_t teamSeq = 0; struct TeamSmem* tm = nullptr;      // KB_TEAM=1: every team branch folds away
+#endif
 		bool splitComplex, splitSaisiot, mergeSaisiot;
 
 		__device__ Vit(const BatchView& _bv, const VitView& _vv, uint32_t _lane) : bv{ _bv }, vv{ _vv }, lane{ _lane } {}
@@ -558,16 +562,18 @@ namespace KB_VIT_NS
 
 		// writeTo of the `top1` container (BestPathContainer.hpp:229-276): the candidate's E entries [candBeg, candBeg + E) are in
 		// first-insertion order; the reference emits them in its unordered_set's iteration order (unordered_emu.h)
-		__device__ __noinline__ void reorderTop1(uint32_t candBeg, uint32_t E)
+		// `bucketsBefore`: the set's bucket count before this container's first insertion; returns the count after it.  `scratch`: first
+		// free pool slot (the segment may be followed by other candidates' entries)
+		__device__ __noinline__ uint32_t reorderTop1(uint32_t candBeg, uint32_t E, uint32_t bucketsBefore, uint32_t scratch)
 		{
-			if (E == 0) return;
-			const uint32_t Bafter = unorderedBucketsAfter(top1Buckets, E);
-			if (!Bafter) { err = ST_INTERNAL; return; }
-			if (E == 1) { top1Buckets = Bafter; return; }
-			const size_t need = (size_t)2 * E * sizeof(DPath) + (size_t)E * 16 + (size_t)Bafter * 4;
-			if ((size_t)candBeg * sizeof(DPath) + need > (size_t)poolCap * sizeof(DPath)) { err = ST_PATH_OVERFLOW; return; }
-			DPath* tmp = pool + candBeg + E;
-			unsigned long long* codes = reinterpret_cast<unsigned long long*>(pool + candBeg + 2 * (size_t)E);
+			if (E == 0) return bucketsBefore;
+			const uint32_t Bafter = unorderedBucketsAfter(bucketsBefore, E);
+			if (!Bafter) { err = ST_INTERNAL; return bucketsBefore; }
+			if (E == 1) return Bafter;
+			const size_t need = (size_t)E * sizeof(DPath) + (size_t)E * 16 + (size_t)Bafter * 4;
+			if ((size_t)scratch * sizeof(DPath) + need > (size_t)poolCap * sizeof(DPath)) { err = ST_PATH_OVERFLOW; return bucketsBefore; }
+			DPath* tmp = pool + scratch;
+			unsigned long long* codes = reinterpret_cast<unsigned long long*>(pool + scratch + (size_t)E);
 			int32_t* next = reinterpret_cast<int32_t*>(codes + E); int32_t* order = next + E; int32_t* buckets = order + E;
 			#pragma unroll 1
 			for (uint32_t e = lane; e < E; e += 32)
@@ -584,14 +590,14 @@ namespace KB_VIT_NS
 				codes[e] = (unsigned long long)((uint32_t)p.prev_root_id | ((uint32_t)p.sp_state << 8)) ^ ((h << 3) | (h >> 61));
 			}
 			__syncwarp();
-			uint32_t B = top1Buckets;
+			uint32_t B = bucketsBefore;
 			if (lane == 0) { if (!unorderedSetOrder(codes, (int32_t)E, B, next, buckets, order)) order[0] = -1; }
 			__syncwarp();
-			if (order[0] < 0) { err = ST_INTERNAL; return; }
+			if (order[0] < 0) { err = ST_INTERNAL; return bucketsBefore; }
 			#pragma unroll 1
 			for (uint32_t j = lane; j < E; j += 32) pool[candBeg + j] = tmp[order[j]];
 			__syncwarp();
-			top1Buckets = Bafter;
+			return Bafter;
 		}
 
 		__device__ __noinline__ void evalCand(uint32_t nodeIdx, const DNode& node, const CandCtx& cc, uint32_t inBeg, uint32_t inEnd, uint32_t mode)
@@ -940,8 +946,7 @@ namespace KB_VIT_NS
 				for (uint32_t e = lane; e < E; e += 32) pool[candBeg + e] = pool[candBeg + E + e];
 				__syncwarp();
 			}
-			if (mode == 2) { reorderTop1(candBeg, E); if (err) return; }
-			top = candBeg + E;
+			top = candBeg + E;      // (mode 2: the container's write-out order is applied per candidate segment by fixupGroup)
 		}
 
 		__device__ __forceinline__ bool atomicCAS_u16(uint32_t slot, uint32_t val)
@@ -1249,8 +1254,25 @@ namespace KB_VIT_NS
 		}
 
 		// capacity + write-out order per candidate segment (see the comment above stagePaths)
-		__device__ __noinline__ void fixupGroup(uint32_t groupBase, uint32_t gcount, uint32_t mode)
+		__device__ __noinline__ void fixupGroup(uint32_t groupBase, uint32_t gcount, uint32_t mode, bool deferTop1)
 		{
+			if (mode == 2)
+			{
+				// `top1` container: no buckets, no capacity, but the write-out order of an unordered_set - per candidate segment, in candidate
+				// order (the set's bucket count carries over from one candidate to the next).  Team mode defers this until every warp's
+				// entry counts are known (evaluate).
+				if (deferTop1) return;
+				uint32_t r = groupBase;
+				#pragma unroll 1
+				for (uint32_t k = 0; k < gcount; ++k)
+				{
+					const uint32_t cnt = sm->candNew[k];
+					if (!cnt) continue;
+					if (sm->cdyn[k].cls != CLS_SHORTCUT) { top1Buckets = reorderTop1(r, cnt, top1Buckets, top); if (err) return; }
+					r += cnt;
+				}
+				return;
+			}
 			// is any fix-up needed at all?
 			bool need = false;
 			{
@@ -1549,12 +1571,12 @@ namespace KB_VIT_NS
 #ifndef KB_CONG_PIPELINE
 #define KB_CONG_PIPELINE 1
 #endif
-			const bool itemOK = KB_CONG_PIPELINE && P <= 512;      // else (the reference's `top1` container) every candidate goes through evalCand; always in the transposed evaluator's order
+			const bool itemOK = KB_CONG_PIPELINE && P <= STAGE_CAP;      // else every candidate goes through evalCand; always in the transposed evaluator's order
 			const CongNode cgn = congPrepare(node, spaceBefore, candBase, nCandsIn, inBeg, P);
 			if (err) return;
 			const uint32_t nCands = cgn.nOrdered;
 #else
-			const bool itemOK = P <= 512;                // modes 0 / 1: the item pipeline; mode 2 (`top1`, an unordered_set in the reference): evalCand + reorderTop1
+			const bool itemOK = P <= STAGE_CAP;          // modes 0 / 1 always; mode 2 (`top1`, an unordered_set in the reference) up to the staging capacity
 			const uint32_t nCands = nCandsIn;
 #endif
 			FlushCtx fc;
@@ -1820,19 +1842,40 @@ namespace KB_VIT_NS
 						resetIndex();
 					}
 					flushItems(fc); if (err) return;
-					if (itemOK) { fixupGroup(myBase, gcount, mode); if (err) return; }
+					if (itemOK || mode == 2) { fixupGroup(myBase, gcount, mode, teamGroup); if (err) return; }
 					};
-					if (teamSize == 1) { walk(); if (err) return; }
+					if (teamSize == 1 || teamGroup || leader()) walk();      // (one call site: the walk is the bulk of this function's code)
+					if (teamSize == 1) { if (err) return; }
 					else if (teamGroup)
 					{
-						walk();
 						// publish the per-candidate entry counts of my candidates, then place every segment in candidate order
 						if (lane < gcount && (lane % teamSize) == teamRank) tm->cnt[lane] = sm->candNew[lane];
 						if (err && lane == 0) atomicMax(&tm->err, err);
 						teamSync();
-						err = tm->err; poolCap = poolCap0;
-						if (err) return;
+						err = tm->err;
+						if (err) { poolCap = poolCap0; return; }
 						const uint32_t cnt = lane < gcount ? tm->cnt[lane] : 0;
+						if (mode == 2)
+						{
+							// write-out order of the `top1` container for my candidates: candidate k starts with the bucket count the set has after
+							// the candidates before it (of any warp) - it only grows, so that is a function of their largest entry count
+							uint32_t pmax = cnt;
+							for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, pmax, d); if (lane >= (uint32_t)d) pmax = max(pmax, t); }
+							const uint32_t before = __shfl_up_sync(FULL, pmax, 1);      // max entry count of the candidates before lane's
+							uint32_t seg = myBase;
+							#pragma unroll 1
+							for (uint32_t k = teamRank; k < gcount; k += teamSize)
+							{
+								const uint32_t c = __shfl_sync(FULL, cnt, k), mb = k ? __shfl_sync(FULL, before, k) : 0u;
+								if (c) { reorderTop1(seg, c, unorderedBucketsAfter(top1Buckets, mb), top); seg += c; }
+							}
+							top1Buckets = unorderedBucketsAfter(top1Buckets, __shfl_sync(FULL, pmax, 31));
+							if (err && lane == 0) atomicMax(&tm->err, err);
+							teamSync();
+							err = tm->err;
+							if (err) { poolCap = poolCap0; return; }
+						}
+						poolCap = poolCap0;
 						uint32_t incl = cnt;
 						for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, incl, d); if (lane >= (uint32_t)d) incl += t; }
 						const uint32_t total = __shfl_sync(FULL, incl, 31), excl = incl - cnt;
@@ -1856,7 +1899,6 @@ namespace KB_VIT_NS
 					}
 					else
 					{
-						if (leader()) walk();
 						uint32_t t = top; teamBroadcast(t); top = t;
 						if (err) return;
 					}
@@ -2227,12 +2269,12 @@ namespace KB_VIT_NS
 		const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 		// The first n_team sentences of the launch order (the heaviest) get a TEAM of warps each: the blocks [0, nTeamBlocks) hold
 		// TEAMS_PER_BLOCK teams; every other sentence gets one warp.
-		const uint32_t nTeam = min(vv.n_team, bv.n_sent);
+		const uint32_t nTeam = TEAM > 1 ? min(vv.n_team, bv.n_sent) : 0u;
 		const uint32_t nTeamBlocks = (nTeam + TEAMS_PER_BLOCK - 1) / TEAMS_PER_BLOCK;
 		if (threadIdx.x < TEAMS_PER_BLOCK) teamSm[threadIdx.x].err = 0;
 		__syncthreads();
 		uint32_t slot, teamRank = 0, teamSize = 1, teamIdx = 0;
-		if (blockIdx.x < nTeamBlocks)
+		if (TEAM > 1 && blockIdx.x < nTeamBlocks)
 		{
 			teamIdx = wib / TEAM; teamRank = wib % TEAM; teamSize = TEAM;
 			slot = blockIdx.x * TEAMS_PER_BLOCK + teamIdx;
@@ -2260,7 +2302,9 @@ namespace KB_VIT_NS
 		v.top = 0;
 		v.sm = &smAll[wib]; v.ht = smAll[wib].ht; v.htUsed = 1;
 		v.dcur = smAll[wib].dcandGen;
+#if KB_TEAM > 1
 		v.teamRank = teamRank; v.teamSize = teamSize; v.teamBar = 1 + teamIdx; v.tm = &teamSm[teamIdx];
+#endif
 		v.splitComplex = (bv.match_options >> 22) & 1; v.splitSaisiot = (bv.match_options >> 25) & 1; v.mergeSaisiot = (bv.match_options >> 26) & 1;
 		v.htClear();
 #if KB_TMA_ROWS
@@ -2438,7 +2482,7 @@ namespace KB_VIT_NS
 	cudaError_t KB_LAUNCH(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
-		const uint32_t nTeam = vv.n_team < bv.n_sent ? vv.n_team : bv.n_sent;
+		const uint32_t nTeam = TEAM > 1 ? (vv.n_team < bv.n_sent ? vv.n_team : bv.n_sent) : 0u;
 		const uint32_t blocks = (nTeam + TEAMS_PER_BLOCK - 1) / TEAMS_PER_BLOCK + (bv.n_sent - nTeam + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 		static bool attrSetOn[64] = {};      // function attributes are per device (the caller holds that device's lock)
 		int devId = 0;
