@@ -247,7 +247,7 @@ def main():
         return kw.analyze_device(d_blob.data_ptr(), d_off.data_ptr(), len(off) - 1, int(blob.size), option)
 
     dev_ms = 0.0; ms_vit = 0.0; ms_lat = 0.0; launches = 0; tokens = 0; retried = 0; wall = 0.0
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)      # (clocks are sampled during the device-timed region only: nvidia-smi polling disturbs the host-timed e2e loop)
     if not inproc:
         for i in range(args.warmup): step_device(i)
         sampler.start()
@@ -261,6 +261,7 @@ def main():
         torch.cuda.synchronize()
         if dist: dist.barrier()
         wall = time.time() - t0
+        sampler.stop_flag = True; sampler.join(timeout=2)      # (nvidia-smi polling disturbs the host-timed e2e loop below)
     else:
         sampler.start()
 

@@ -216,6 +216,79 @@ namespace KB_VIT_NS
 			return KnRes{ acc + asFloat(v), nodeIdx };
 		}
 	}
+	// The same walk, with the FIRST hash probe and the first node's back-off pair already loaded by the caller (flushItems issues them
+	// one round ahead, so their latency overlaps the previous round's work).  e0 = kn_hash[knHashFn(node, next) & mask], bo0 = kn_backoff[node].
+	__device__ __noinline__ KnRes knProgressPre(int32_t nodeIdx, uint32_t next, uint4 e0, float2 bo0)
+	{
+		float acc = 0;
+		bool first = true;
+		while (true)
+		{
+			int32_t v; float cll;
+			if (nodeIdx == 0)
+			{
+				v = c_m.kn_root[next];
+				if (v == 0)
+				{
+					if (c_m.kn_htx) nodeIdx = c_m.kn_root[c_m.kn_htx[next]];
+					return KnRes{ acc + c_m.kn_unk_ll, nodeIdx };
+				}
+				cll = c_m.kn_root_ll[next];
+			}
+			else
+			{
+				float2 bo; bool found;
+				if (first)
+				{
+					bo = bo0;
+					uint32_t h = knHashFn((uint32_t)nodeIdx, next) & c_m.kn_hash_mask;
+					uint4 e = e0;
+					while (true)
+					{
+						if (e.x == (uint32_t)nodeIdx && e.y == next) { v = (int32_t)e.z; cll = __uint_as_float(e.w); found = true; break; }
+						if (e.x == 0xFFFFFFFFu) { found = false; break; }
+						h = (h + 1) & c_m.kn_hash_mask;
+						e = c_m.kn_hash[h];
+					}
+				}
+				else
+				{
+					bo = c_m.kn_backoff[nodeIdx];
+					found = knLookup((uint32_t)nodeIdx, next, v, cll);
+				}
+				first = false;
+				if (!found)
+				{
+					acc += bo.y;
+					nodeIdx += __float_as_int(bo.x);
+					continue;
+				}
+			}
+			first = false;
+			if (v > 0)
+			{
+				nodeIdx += v;
+				return KnRes{ acc + cll, nodeIdx };
+			}
+			// leaf: next state = deepest suffix state that continues with `next`
+			int32_t cur = nodeIdx;
+			while (true)
+			{
+				const int32_t lower = __float_as_int(c_m.kn_backoff[cur].x);
+				if (!lower) break;
+				cur += lower;
+				int32_t lv; float dummy;
+				const bool found = cur == 0 ? ((lv = c_m.kn_root[next]) != 0) : knLookup((uint32_t)cur, next, lv, dummy);
+				if (found && lv > 0)
+				{
+					nodeIdx = cur + lv;
+					return KnRes{ acc + asFloat(v), nodeIdx };
+				}
+			}
+			nodeIdx = c_m.kn_htx ? c_m.kn_root[c_m.kn_htx[next]] : 0;
+			return KnRes{ acc + asFloat(v), nodeIdx };
+		}
+	}
 	__device__ __forceinline__ float knProgress(int32_t& nodeIdx, uint32_t next, uint32_t = 0)
 	{
 		const KnRes r = knProgressV(nodeIdx, next);
@@ -1068,13 +1141,45 @@ namespace KB_VIT_NS
 		{
 			if (!nItems) return;
 			__syncwarp();
+			// Software pipeline (Knlm build): the loads a round depends on first - the item's path record, and with its LM state the first
+			// probe of the Knlm edge table and the node's back-off pair - are issued ONE ROUND AHEAD, so that their L2 latency overlaps the
+			// previous round's pointer chase, de-duplication and stores.
+			struct Pre { uint32_t it; uint4 s0; uint32_t meta; uint32_t firstWid; uint4 e; float2 bo; };
+			auto preload = [&](uint32_t i, Pre& p)
+			{
+				p.it = 0; p.s0 = make_uint4(0, 0, 0, 0); p.meta = 0; p.firstWid = 0; p.e = make_uint4(0, 0, 0, 0); p.bo = make_float2(0.f, 0.f);
+				if (i >= nItems) return;
+				p.it = sm->item[i];
+				const uint32_t slotP = p.it >> 27, fwIdxP = (p.it >> 20) & 63, qP = (p.it >> 3) & 0x1FFFF;
+				const DPath* pp = pool + fc.inBeg + qP;
+				p.s0 = *reinterpret_cast<const uint4*>(&pp->lm_state);      // lm_state, acc_score, acc_typo_cost, wid_feat
+				p.meta = *reinterpret_cast<const uint32_t*>(&pp->sp_state);   // sp_state | root_id << 8 | prev_root_id << 16 | morph_tag << 24
+				p.firstWid = fwIdxP ? sm->fwTab[fwIdxP] : dcur[slotP].first_wid;
+#if !KB_CONG
+				if (p.s0.x != 0 && !(sm->cdyn[slotP].flags & CS_NO_LM))
+				{
+					p.e = c_m.kn_hash[knHashFn(p.s0.x, p.firstWid) & c_m.kn_hash_mask];
+					p.bo = c_m.kn_backoff[p.s0.x];
+				}
+#endif
+			};
+#ifndef KB_NO_PRELOAD
+			Pre cur; preload(lane, cur);
+#endif
 			#pragma unroll 1
 			for (uint32_t ib = 0; ib < nItems; ib += 32)
 			{
 				const uint32_t i = ib + lane;
 				const bool valid = i < nItems;
+#ifdef KB_NO_PRELOAD
+				Pre pre; preload(i, pre);      // (experiment: no look-ahead)
+#else
+				Pre nxt; preload(i + 32, nxt);
+				const Pre pre = cur; cur = nxt;
+#endif
 				uint32_t slot = 0, q = 0, r = 0, fwIdx = 0; bool condFail = false, spacePen = false;
-				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 0x1FFFF; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
+				if (valid) { const uint32_t it = pre.it; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 0x1FFFF; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
+				(void)fwIdx;
 				const DCand* cs = &dcur[slot];
 				const CandDyn cd = sm->cdyn[slot];
 				const uint32_t csFeat = cs->feat;
@@ -1085,9 +1190,8 @@ namespace KB_VIT_NS
 #endif
 				if (valid)
 				{
-					const DPath* pp = pool + fc.inBeg + q;
-					const uint4 s0 = *reinterpret_cast<const uint4*>(&pp->lm_state);      // lm_state, acc_score, acc_typo_cost, wid_feat
-					const uint32_t meta = *reinterpret_cast<const uint32_t*>(&pp->sp_state);   // sp_state | root_id << 8 | prev_root_id << 16 | morph_tag << 24
+					const uint4 s0 = pre.s0;
+					const uint32_t meta = pre.meta;
 					prevRoot = (meta >> 8) & 0xFF;
 					const bool doFork = (cd.flags & CS_FORK) && prevRoot == COMMON_ROOT;
 					spState = doFork ? uniq[r] : (uint8_t)(meta & 0xFF);
@@ -1101,13 +1205,13 @@ namespace KB_VIT_NS
 					const bool cgRegular = !(cd.flags & (CS_NO_LM | CS_SOCKET_CHUNK));
 					if (condFail && !cgRegular) candScore += fc.ignoreCondScore;
 					ctxIdx = s0.w;
-					const uint32_t pf = c_m.morphs[pp->wid].feat;
+					const uint32_t pf = c_m.morphs[pool[fc.inBeg + q].wid].feat;
 #else
 					if (condFail) candScore += fc.ignoreCondScore;
 					const uint32_t pf = s0.w;
 #endif
 					lmState = (int32_t)s0.x;
-					const uint32_t firstWid = fwIdx ? sm->fwTab[fwIdx] : cs->first_wid;
+					const uint32_t firstWid = pre.firstWid;
 #if KB_CONG
 					if (!(cd.flags & CS_NO_LM))
 					{
@@ -1132,7 +1236,9 @@ namespace KB_VIT_NS
 #else
 					if (!(cd.flags & CS_NO_LM))
 					{
-						float ll = knProgress(lmState, firstWid, 1);
+						const KnRes kr = knProgressPre(lmState, firstWid, pre.e, pre.bo);
+						lmState = kr.node;
+						float ll = kr.ll;
 						candScore += ll; firstChunkScore += ll;
 						if (!(cd.flags & CS_SINGLE))
 						{
@@ -1587,6 +1693,18 @@ namespace KB_VIT_NS
 			nItems = 0;
 			const bool snPoint = node.uform_len && norm[node.uform_off + node.uform_len - 1] == '.';
 			const uint32_t nWords = (P + 31) >> 5;
+			// class of lane's path in each of the first 6 words of 32 incoming paths, 5 bits each (+ which words have a path for this lane): the
+			// enumeration below tests (candidate's valid-class mask >> class) per word without touching shared memory
+			uint32_t clsPack = 0, clsHave = 0;
+			if (itemOK)
+			{
+				#pragma unroll
+				for (uint32_t w = 0; w < 6; ++w)
+				{
+					const uint32_t q = (w << 5) | lane;
+					if (q < P) { clsPack |= (uint32_t)sm->pcls[q] << (5 * w); clsHave |= 1u << w; }
+				}
+			}
 
 			#pragma unroll 1
 			for (int ignoreCond = 0; ignoreCond < 2; ++ignoreCond)
@@ -1748,8 +1866,9 @@ namespace KB_VIT_NS
 								for (uint32_t w = 0; w < nWords; ++w)
 								{
 									const uint32_t q = (w << 5) | lane;
-									const uint32_t c = q < P ? sm->pcls[q] : 31u;
-									const bool on = q < P && ((vmK >> c) & 1u);
+									uint32_t c; bool on;
+									if (w < 6) { c = (clsPack >> (5 * w)) & 31u; on = ((clsHave >> w) & (vmK >> c) & 1u) != 0; }
+									else { c = q < P ? sm->pcls[q] : 31u; on = q < P && ((vmK >> c) & 1u); }
 									const unsigned m = __ballot_sync(FULL, on);
 									if (!m) continue;
 									const uint32_t cnt = __popc(m);
