@@ -231,7 +231,12 @@ def main():
         from kiwi_b200.shard import shard_indices
         all_texts = gen_sentences(cfg, 0, cfg["batch"], SEED)
         mine = [all_texts[i] for i in shard_indices(len(all_texts), rank, world)] if world > 1 else all_texts
-        blob, off = kiwi_b200.encode_batch(mine)
+        cache = os.path.join(tempfile.gettempdir(), "kiwi_b200_cfg%d_%d_r%dof%d.npz" % (args.config, cfg["batch"], rank, world))      # (encoding 1 M strings takes a while)
+        if os.path.exists(cache):
+            z = np.load(cache); blob, off = z["blob"], z["off"]
+        else:
+            blob, off = kiwi_b200.encode_batch(mine)
+            np.savez(cache, blob=blob, off=off)
         batches.append((mine, blob, off, torch.from_numpy(blob.view(np.int16)).cuda(), torch.from_numpy(off.view(np.int32)).cuda()))
     else:
         nblk = (cfg["batch"] + BLOCK - 1) // BLOCK

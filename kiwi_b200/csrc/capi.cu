@@ -312,6 +312,27 @@ static int analyzeMulti(kiwi_h handle, ReadFn&& readOne, kiwi_receiver_t receive
 }
 
 
+// result buffers of kiwi_b200_analyze_batch are recycled (a 5 MB allocation + first-touch page faults per 8192-sentence call otherwise);
+// the pool outlives the handle for batches the caller frees late
+struct BatchHolder;
+struct BatchPool
+{
+	std::mutex m; std::vector<BatchHolder*> free; bool closed = false;
+	~BatchPool();
+};
+struct BatchHolder { kiwi_b200_batch_t pub; BatchOutput bo; std::shared_ptr<BatchPool> pool; };
+BatchPool::~BatchPool() { for (auto* h : free) delete h; }
+static std::mutex g_poolMapMtx;
+static std::map<kiwi_s*, std::shared_ptr<BatchPool>> g_pools;
+static std::shared_ptr<BatchPool> poolOf(kiwi_s* h)
+{
+	std::lock_guard<std::mutex> lk(g_poolMapMtx);
+	auto& p = g_pools[h];
+	if (!p) p = std::make_shared<BatchPool>();
+	return p;
+}
+
+
 extern "C" {
 #pragma GCC visibility push(default)
 
@@ -474,6 +495,11 @@ int kiwi_prepared_typo_close(kiwi_prepared_typo_h handle)
 int kiwi_close(kiwi_h handle)
 {
 	if (!handle) return KIWIERR_INVALID_HANDLE;
+	{
+		std::shared_ptr<BatchPool> pool;
+		{ std::lock_guard<std::mutex> lk(g_poolMapMtx); auto it = g_pools.find(handle); if (it != g_pools.end()) { pool = it->second; g_pools.erase(it); } }
+		if (pool) { std::lock_guard<std::mutex> lk(pool->m); pool->closed = true; for (auto* h : pool->free) delete h; pool->free.clear(); }
+	}
 	try { delete handle; return 0; }
 	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
 }
@@ -551,8 +577,6 @@ float kiwi_res_score(kiwi_res_h result, int index, int num) { KB_TOK_OR(0.f) ret
 float kiwi_res_typo_cost(kiwi_res_h result, int index, int num) { KB_TOK_OR(0.f) return result->toks[num].info.typo_cost; }
 int kiwi_res_close(kiwi_res_h result) { if (!result) return KIWIERR_INVALID_HANDLE; delete result; return 0; }
 
-struct BatchHolder { kiwi_b200_batch_t pub; BatchOutput bo; };
-
 const kiwi_b200_batch_t* kiwi_b200_analyze_batch(kiwi_h handle, const kchar16_t* text, const uint32_t* offsets, int n, kiwi_analyze_option_t option)
 {
 	if (!handle) { setError("invalid handle"); return nullptr; }
@@ -560,7 +584,14 @@ const kiwi_b200_batch_t* kiwi_b200_analyze_batch(kiwi_h handle, const kchar16_t*
 	{
 		checkOption(option, 1, nullptr);
 		if (n < 0) throw std::invalid_argument("n < 0");
-		auto* h = new BatchHolder;
+		auto pool = poolOf(handle);
+		BatchHolder* h = nullptr;
+		{
+			std::lock_guard<std::mutex> lk(pool->m);
+			if (!pool->free.empty()) { h = pool->free.back(); pool->free.pop_back(); }
+		}
+		if (!h) h = new BatchHolder;
+		h->pool = pool;
 		try
 		{
 			std::lock_guard<std::mutex> lk(handle->mtx);
@@ -583,7 +614,14 @@ const kiwi_b200_batch_t* kiwi_b200_analyze_batch(kiwi_h handle, const kchar16_t*
 void kiwi_b200_batch_free(const kiwi_b200_batch_t* batch)
 {
 	if (!batch) return;
-	delete reinterpret_cast<BatchHolder*>(const_cast<kiwi_b200_batch_t*>(batch));
+	auto* h = reinterpret_cast<BatchHolder*>(const_cast<kiwi_b200_batch_t*>(batch));
+	std::shared_ptr<BatchPool> pool = std::move(h->pool);
+	if (pool)
+	{
+		std::lock_guard<std::mutex> lk(pool->m);
+		if (!pool->closed && pool->free.size() < 4) { pool->free.push_back(h); return; }
+	}
+	delete h;
 }
 
 float kiwi_b200_analyze_device(kiwi_h handle, const void* d_text, const void* d_offsets, int n, uint64_t total_units, kiwi_analyze_option_t option, uint64_t* out_tokens, uint64_t* out_launches)

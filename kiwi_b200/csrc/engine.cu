@@ -338,10 +338,10 @@ namespace kb
 	}
 
 	// Layout of a slot's pinned output buffer: [tokOff n+1][scores n][status n][debug flag 2 words][tokens ...].  Everything is
-	// enqueued behind the kernels in ONE go: the head arrays and an ESTIMATE of the packed tokens (3/4 token per raw UTF-16 unit
-	// + 16 per sentence; web text needs ~0.55), so a pass normally needs a single stream synchronisation.  finishPass fetches
+	// enqueued behind the kernels in ONE go: the head arrays and an ESTIMATE of the packed tokens (5/8 token per raw UTF-16 unit
+	// + 8 per sentence; web text needs ~0.55), so a pass normally needs a single stream synchronisation.  finishPass fetches
 	// the rest when the estimate was too small.
-	static size_t tokenEstimate(size_t rawUnits, uint32_t n) { return rawUnits * 3 / 4 + 16 * (size_t)n + 64; }
+	static size_t tokenEstimate(size_t rawUnits, uint32_t n) { return rawUnits * 5 / 8 + 8 * (size_t)n + 64; }
 
 	void Engine::submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t pn, uint32_t matchOptions)
 	{
@@ -489,13 +489,14 @@ namespace kb
 	{
 		DeviceGuard g{ device };
 		last = Stats{};
-		out = BatchOutput{};
-		out.tokOff.assign(1, 0);
+		// (the caller may hand in a recycled BatchOutput: keep the vectors' capacity)
+		out.tokOff.assign(1, 0); out.tokens.clear(); out.scores.clear(); out.status.clear();
+		out.msH2D = out.msLattice = out.msViterbi = out.msPack = out.msD2H = out.msTotal = 0;
 		if (n == 0) return;
 		if (offsets[0] != 0) throw std::runtime_error("offsets[0] must be 0");
 		for (uint32_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) throw std::runtime_error("offsets must be non-decreasing");
 		out.tokOff.reserve((size_t)n + 1); out.scores.reserve(n); out.status.reserve(n);
-		out.tokens.reserve(tokenEstimate(offsets[n], n) * 3 / 4);
+		out.tokens.reserve(tokenEstimate(offsets[n], n));
 		std::vector<uint32_t> failed;
 		const size_t sentLimit = passSentLimit();
 		uint32_t i0 = 0, k = 0;
@@ -530,7 +531,7 @@ namespace kb
 			std::vector<PassResult> results; std::vector<uint32_t> resultOf(n, 0xFFFFFFFFu);
 			runRetry(text, offsets, failed, matchOptions, out, results, resultOf);
 			// splice the retried sentences into the token stream (rare path: rebuild)
-			std::vector<DToken> toks; std::vector<uint32_t> tokOff(1, 0);
+			TokenVec toks; std::vector<uint32_t> tokOff(1, 0);
 			toks.reserve(out.tokens.size());
 			for (uint32_t i = 0; i < n; ++i)
 			{

@@ -1,7 +1,9 @@
 // kiwi_b200: host engine (model residency, batch marshalling, kernel launches, result packing).
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 #include <cuda_runtime.h>
 #include "kb_model.h"
@@ -36,10 +38,21 @@ namespace kb
 		~TypoDev();
 	};
 
+	// vector whose resize() leaves trivially-constructible elements uninitialised: the token rows are memcpy'd in right after
+	template<class T> struct NoInitAlloc : std::allocator<T>
+	{
+		template<class U> struct rebind { using other = NoInitAlloc<U>; };
+		template<class U, class... A> void construct(U* p, A&&... a)
+		{
+			if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+		}
+	};
+	using TokenVec = std::vector<DToken, NoInitAlloc<DToken>>;
+
 	struct BatchOutput
 	{
 		std::vector<uint32_t> tokOff;      // [n + 1]
-		std::vector<DToken> tokens;
+		TokenVec tokens;
 		std::vector<float> scores;
 		std::vector<uint32_t> status;
 		float msH2D = 0, msLattice = 0, msViterbi = 0, msPack = 0, msD2H = 0, msTotal = 0;
@@ -118,7 +131,7 @@ namespace kb
 		void bind(Scratch& sc, const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint32_t matchOptions, uint32_t capMul);
 		void uploadConstants();
 		void launchAll(Scratch& sc, cudaStream_t st, cudaEvent_t* ev, uint32_t n);
-		struct PassResult { std::vector<uint32_t> tokOff; std::vector<DToken> toks; std::vector<float> scores; std::vector<uint32_t> status; };
+		struct PassResult { std::vector<uint32_t> tokOff; TokenVec toks; std::vector<float> scores; std::vector<uint32_t> status; };
 		void submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t n, uint32_t matchOptions);
 		void finishPass(Slot& s, BatchOutput& out, std::vector<uint32_t>& failed);
 		void runRetry(const uint16_t* text, const uint32_t* offsets, const std::vector<uint32_t>& failed, uint32_t matchOptions, BatchOutput& out, std::vector<PassResult>& results, std::vector<uint32_t>& resultOf);

@@ -216,79 +216,6 @@ namespace KB_VIT_NS
 			return KnRes{ acc + asFloat(v), nodeIdx };
 		}
 	}
-	// The same walk, with the FIRST hash probe and the first node's back-off pair already loaded by the caller (flushItems issues them
-	// one round ahead, so their latency overlaps the previous round's work).  e0 = kn_hash[knHashFn(node, next) & mask], bo0 = kn_backoff[node].
-	__device__ __noinline__ KnRes knProgressPre(int32_t nodeIdx, uint32_t next, uint4 e0, float2 bo0)
-	{
-		float acc = 0;
-		bool first = true;
-		while (true)
-		{
-			int32_t v; float cll;
-			if (nodeIdx == 0)
-			{
-				v = c_m.kn_root[next];
-				if (v == 0)
-				{
-					if (c_m.kn_htx) nodeIdx = c_m.kn_root[c_m.kn_htx[next]];
-					return KnRes{ acc + c_m.kn_unk_ll, nodeIdx };
-				}
-				cll = c_m.kn_root_ll[next];
-			}
-			else
-			{
-				float2 bo; bool found;
-				if (first)
-				{
-					bo = bo0;
-					uint32_t h = knHashFn((uint32_t)nodeIdx, next) & c_m.kn_hash_mask;
-					uint4 e = e0;
-					while (true)
-					{
-						if (e.x == (uint32_t)nodeIdx && e.y == next) { v = (int32_t)e.z; cll = __uint_as_float(e.w); found = true; break; }
-						if (e.x == 0xFFFFFFFFu) { found = false; break; }
-						h = (h + 1) & c_m.kn_hash_mask;
-						e = c_m.kn_hash[h];
-					}
-				}
-				else
-				{
-					bo = c_m.kn_backoff[nodeIdx];
-					found = knLookup((uint32_t)nodeIdx, next, v, cll);
-				}
-				first = false;
-				if (!found)
-				{
-					acc += bo.y;
-					nodeIdx += __float_as_int(bo.x);
-					continue;
-				}
-			}
-			first = false;
-			if (v > 0)
-			{
-				nodeIdx += v;
-				return KnRes{ acc + cll, nodeIdx };
-			}
-			// leaf: next state = deepest suffix state that continues with `next`
-			int32_t cur = nodeIdx;
-			while (true)
-			{
-				const int32_t lower = __float_as_int(c_m.kn_backoff[cur].x);
-				if (!lower) break;
-				cur += lower;
-				int32_t lv; float dummy;
-				const bool found = cur == 0 ? ((lv = c_m.kn_root[next]) != 0) : knLookup((uint32_t)cur, next, lv, dummy);
-				if (found && lv > 0)
-				{
-					nodeIdx = cur + lv;
-					return KnRes{ acc + asFloat(v), nodeIdx };
-				}
-			}
-			nodeIdx = c_m.kn_htx ? c_m.kn_root[c_m.kn_htx[next]] : 0;
-			return KnRes{ acc + asFloat(v), nodeIdx };
-		}
-	}
 	__device__ __forceinline__ float knProgress(int32_t& nodeIdx, uint32_t next, uint32_t = 0)
 	{
 		const KnRes r = knProgressV(nodeIdx, next);
@@ -483,6 +410,12 @@ namespace KB_VIT_NS
 		uint32_t err;
 	};
 
+	// functions with ONE call site: inlined with -DKB_INLINE_MORE (kernel experiments), out of line otherwise
+#ifdef KB_INLINE_MORE
+#define KB_INL1 __forceinline__
+#else
+#define KB_INL1 __noinline__
+#endif
 	struct Vit
 	{
 		const BatchView& bv;
@@ -1091,7 +1024,7 @@ namespace KB_VIT_NS
 		// per-candidate containers.  Keys are independent of each other, so the 128-slot capacity of a container
 		// bucket ("skip insertion if container is full", BestPathContainer.hpp:363-367) and the bucket-major order of
 		// the 4 x 128 medium container are applied afterwards per candidate segment (fixupGroup).
-		__device__ __noinline__ void stagePaths(uint32_t nodeIdx, uint32_t inBeg, uint32_t P)
+		__device__ KB_INL1 void stagePaths(uint32_t nodeIdx, uint32_t inBeg, uint32_t P)
 		{
 			if (stagedNode == nodeIdx) return;
 			nClasses = 0; classCommon = 0; classOverflow = false;
@@ -1141,45 +1074,13 @@ namespace KB_VIT_NS
 		{
 			if (!nItems) return;
 			__syncwarp();
-			// Software pipeline (Knlm build): the loads a round depends on first - the item's path record, and with its LM state the first
-			// probe of the Knlm edge table and the node's back-off pair - are issued ONE ROUND AHEAD, so that their L2 latency overlaps the
-			// previous round's pointer chase, de-duplication and stores.
-			struct Pre { uint32_t it; uint4 s0; uint32_t meta; uint32_t firstWid; uint4 e; float2 bo; };
-			auto preload = [&](uint32_t i, Pre& p)
-			{
-				p.it = 0; p.s0 = make_uint4(0, 0, 0, 0); p.meta = 0; p.firstWid = 0; p.e = make_uint4(0, 0, 0, 0); p.bo = make_float2(0.f, 0.f);
-				if (i >= nItems) return;
-				p.it = sm->item[i];
-				const uint32_t slotP = p.it >> 27, fwIdxP = (p.it >> 20) & 63, qP = (p.it >> 3) & 0x1FFFF;
-				const DPath* pp = pool + fc.inBeg + qP;
-				p.s0 = *reinterpret_cast<const uint4*>(&pp->lm_state);      // lm_state, acc_score, acc_typo_cost, wid_feat
-				p.meta = *reinterpret_cast<const uint32_t*>(&pp->sp_state);   // sp_state | root_id << 8 | prev_root_id << 16 | morph_tag << 24
-				p.firstWid = fwIdxP ? sm->fwTab[fwIdxP] : dcur[slotP].first_wid;
-#if !KB_CONG
-				if (p.s0.x != 0 && !(sm->cdyn[slotP].flags & CS_NO_LM))
-				{
-					p.e = c_m.kn_hash[knHashFn(p.s0.x, p.firstWid) & c_m.kn_hash_mask];
-					p.bo = c_m.kn_backoff[p.s0.x];
-				}
-#endif
-			};
-#ifndef KB_NO_PRELOAD
-			Pre cur; preload(lane, cur);
-#endif
 			#pragma unroll 1
 			for (uint32_t ib = 0; ib < nItems; ib += 32)
 			{
 				const uint32_t i = ib + lane;
 				const bool valid = i < nItems;
-#ifdef KB_NO_PRELOAD
-				Pre pre; preload(i, pre);      // (experiment: no look-ahead)
-#else
-				Pre nxt; preload(i + 32, nxt);
-				const Pre pre = cur; cur = nxt;
-#endif
 				uint32_t slot = 0, q = 0, r = 0, fwIdx = 0; bool condFail = false, spacePen = false;
-				if (valid) { const uint32_t it = pre.it; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 0x1FFFF; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
-				(void)fwIdx;
+				if (valid) { const uint32_t it = sm->item[i]; slot = it >> 27; fwIdx = (it >> 20) & 63; q = (it >> 3) & 0x1FFFF; spacePen = (it >> 2) & 1; r = (it >> 1) & 1; condFail = it & 1; }
 				const DCand* cs = &dcur[slot];
 				const CandDyn cd = sm->cdyn[slot];
 				const uint32_t csFeat = cs->feat;
@@ -1190,8 +1091,9 @@ namespace KB_VIT_NS
 #endif
 				if (valid)
 				{
-					const uint4 s0 = pre.s0;
-					const uint32_t meta = pre.meta;
+					const DPath* pp = pool + fc.inBeg + q;
+					const uint4 s0 = *reinterpret_cast<const uint4*>(&pp->lm_state);      // lm_state, acc_score, acc_typo_cost, wid_feat
+					const uint32_t meta = *reinterpret_cast<const uint32_t*>(&pp->sp_state);   // sp_state | root_id << 8 | prev_root_id << 16 | morph_tag << 24
 					prevRoot = (meta >> 8) & 0xFF;
 					const bool doFork = (cd.flags & CS_FORK) && prevRoot == COMMON_ROOT;
 					spState = doFork ? uniq[r] : (uint8_t)(meta & 0xFF);
@@ -1205,13 +1107,13 @@ namespace KB_VIT_NS
 					const bool cgRegular = !(cd.flags & (CS_NO_LM | CS_SOCKET_CHUNK));
 					if (condFail && !cgRegular) candScore += fc.ignoreCondScore;
 					ctxIdx = s0.w;
-					const uint32_t pf = c_m.morphs[pool[fc.inBeg + q].wid].feat;
+					const uint32_t pf = c_m.morphs[pp->wid].feat;
 #else
 					if (condFail) candScore += fc.ignoreCondScore;
 					const uint32_t pf = s0.w;
 #endif
 					lmState = (int32_t)s0.x;
-					const uint32_t firstWid = pre.firstWid;
+					const uint32_t firstWid = fwIdx ? sm->fwTab[fwIdx] : cs->first_wid;
 #if KB_CONG
 					if (!(cd.flags & CS_NO_LM))
 					{
@@ -1236,9 +1138,7 @@ namespace KB_VIT_NS
 #else
 					if (!(cd.flags & CS_NO_LM))
 					{
-						const KnRes kr = knProgressPre(lmState, firstWid, pre.e, pre.bo);
-						lmState = kr.node;
-						float ll = kr.ll;
+						float ll = knProgress(lmState, firstWid, 1);
 						candScore += ll; firstChunkScore += ll;
 						if (!(cd.flags & CS_SINGLE))
 						{
@@ -1360,7 +1260,7 @@ namespace KB_VIT_NS
 		}
 
 		// capacity + write-out order per candidate segment (see the comment above stagePaths)
-		__device__ __noinline__ void fixupGroup(uint32_t groupBase, uint32_t gcount, uint32_t mode, bool deferTop1)
+		__device__ KB_INL1 void fixupGroup(uint32_t groupBase, uint32_t gcount, uint32_t mode, bool deferTop1)
 		{
 			if (mode == 2)
 			{
