@@ -216,6 +216,56 @@ namespace KB_VIT_NS
 			return KnRes{ acc + asFloat(v), nodeIdx };
 		}
 	}
+	__device__ __forceinline__ KnRes knProgressI(int32_t nodeIdx, uint32_t next)
+	{
+		float acc = 0;
+		while (true)
+		{
+			int32_t v; float cll;
+			if (nodeIdx == 0)
+			{
+				v = c_m.kn_root[next];
+				if (v == 0)
+				{
+					if (c_m.kn_htx) nodeIdx = c_m.kn_root[c_m.kn_htx[next]];
+					return KnRes{ acc + c_m.kn_unk_ll, nodeIdx };
+				}
+				cll = c_m.kn_root_ll[next];
+			}
+			else
+			{
+				const float2 bo = c_m.kn_backoff[nodeIdx];            // issued together with the probe
+				if (!knLookup((uint32_t)nodeIdx, next, v, cll))
+				{
+					acc += bo.y;
+					nodeIdx += __float_as_int(bo.x);
+					continue;
+				}
+			}
+			if (v > 0)
+			{
+				nodeIdx += v;
+				return KnRes{ acc + cll, nodeIdx };
+			}
+			// leaf: next state = deepest suffix state that continues with `next`
+			int32_t cur = nodeIdx;
+			while (true)
+			{
+				const int32_t lower = __float_as_int(c_m.kn_backoff[cur].x);
+				if (!lower) break;
+				cur += lower;
+				int32_t lv; float dummy;
+				const bool found = cur == 0 ? ((lv = c_m.kn_root[next]) != 0) : knLookup((uint32_t)cur, next, lv, dummy);
+				if (found && lv > 0)
+				{
+					nodeIdx = cur + lv;
+					return KnRes{ acc + asFloat(v), nodeIdx };
+				}
+			}
+			nodeIdx = c_m.kn_htx ? c_m.kn_root[c_m.kn_htx[next]] : 0;
+			return KnRes{ acc + asFloat(v), nodeIdx };
+		}
+	}
 	__device__ __forceinline__ float knProgress(int32_t& nodeIdx, uint32_t next, uint32_t = 0)
 	{
 		const KnRes r = knProgressV(nodeIdx, next);
@@ -415,6 +465,11 @@ namespace KB_VIT_NS
 #define KB_INL1 __forceinline__
 #else
 #define KB_INL1 __noinline__
+#endif
+#ifdef KB_INLINE_EVAL
+#define KB_INL_EVAL __forceinline__
+#else
+#define KB_INL_EVAL __noinline__
 #endif
 	struct Vit
 	{
@@ -1138,7 +1193,12 @@ namespace KB_VIT_NS
 #else
 					if (!(cd.flags & CS_NO_LM))
 					{
+#ifdef KB_INLINE_KN
+						const KnRes kr0 = knProgressI(lmState, firstWid); lmState = kr0.node;
+						float ll = kr0.ll;
+#else
 						float ll = knProgress(lmState, firstWid, 1);
+#endif
 						candScore += ll; firstChunkScore += ll;
 						if (!(cd.flags & CS_SINGLE))
 						{
@@ -1549,7 +1609,7 @@ namespace KB_VIT_NS
 
 		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
 		// candBase: the node's static candidate rows (a form's block of c_m.cands, or the unknown NNG / NNP rows)
-		__device__ __noinline__ void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const DCand* candBase, uint32_t nCandsIn,
+		__device__ KB_INL_EVAL void evaluate(uint32_t nodeIdx, uint32_t nodeBeg, const DCand* candBase, uint32_t nCandsIn,
 			float unkFormDiscount, uint32_t ownOff, uint32_t ownLen, uint32_t inBeg, uint32_t inEnd, bool first)
 		{
 			// `first`: the node's first evaluation - its candidate block may be waiting in the other staging buffer
@@ -2092,41 +2152,45 @@ namespace KB_VIT_NS
 				// node i's rows sit in buffer curBuf ^ 1 (issued one node ago); node i + 1's go to curBuf, whose last reader was node i - 1
 				if (i + 2 < N) { const uint2 cn = nodeCand[i + 1]; pfIssue(c_m.cands + cn.x, min(cn.y & 0xFFFFu, GROUP), curBuf); }
 #endif
-				if (node.form >= 0)
+				// up to three evaluations of the node (PathEvaluator.hpp:1255-1306), ONE call site: (0) the form's candidates, or NNG + NNP for an
+				// unknown span; (1) a form whose candidates are all partial: additionally as an unknown NNP; (2) a form node after which the
+				// rest of the lattice is unreachable: the raw substring as unknown NNG + NNP
+				const uint32_t fflags = ci.y >> 16;
+				#pragma unroll 1
+				for (uint32_t pass = 0; pass < 3; ++pass)
 				{
-					const uint32_t fflags = ci.y >> 16;
-					evaluate(i, nodeBeg, c_m.cands + ci.x, ci.y & 0xFFFFu, 0.f, node.uform_off, node.uform_len, inBeg, inEnd, true);
-					if (err) return 0;
-					if (node.typo_cost == 0.f && (fflags & FF_ALL_PARTIAL))
+					const DCand* cb; uint32_t cn, oo, ol; float disc;
+					if (pass == 0)
 					{
+						if (node.form >= 0) { cb = c_m.cands + ci.x; cn = ci.y & 0xFFFFu; disc = 0.f; }
+						else { cb = c_m.cands + c_m.cand_unk; cn = 2; disc = unkFormScore(norm + node.uform_off, node.uform_len); }
+						oo = node.uform_off; ol = node.uform_len;
+					}
+					else if (pass == 1)
+					{
+						if (node.form < 0) break;
+						if (!(node.typo_cost == 0.f && (fflags & FF_ALL_PARTIAL))) continue;
 						const DForm f = c_m.forms[node.form];
-						const uint16_t* fs = c_m.form_chars + c_m.forms_raw[node.form].str_off;
-						const float unkScore = unkFormScore(fs, f.str_len);
-						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk + 1, 1, unkScore, ~(uint32_t)node.form, f.str_len, inBeg, inEnd, false);
-						if (err) return 0;
+						cb = c_m.cands + c_m.cand_unk + 1; cn = 1; disc = unkFormScore(c_m.form_chars + c_m.forms_raw[node.form].str_off, f.str_len);
+						oo = ~(uint32_t)node.form; ol = f.str_len;
 					}
-					uint32_t disc = 0;
-					if (leader())
+					else
 					{
-						const bool r = anyNonSocket(nodeBeg, top);
-						if (lane == 0) reach[i] = r ? 1 : 0;
-						__syncwarp();
-						disc = isDisconnected(i + 1) ? 1u : 0u;
-					}
-					teamBroadcast(disc);
-					if (err) return 0;
-					if (disc)
-					{
-						const uint32_t len = node.end_pos - node.start_pos;
-						const float unkScore = unkFormScore(norm + node.start_pos, len);
-						evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.start_pos, len, inBeg, inEnd, false);
+						uint32_t dc = 0;
+						if (leader())
+						{
+							const bool r = anyNonSocket(nodeBeg, top);
+							if (lane == 0) reach[i] = r ? 1 : 0;
+							__syncwarp();
+							dc = isDisconnected(i + 1) ? 1u : 0u;
+						}
+						teamBroadcast(dc);
 						if (err) return 0;
+						if (!dc) break;
+						ol = node.end_pos - node.start_pos; oo = node.start_pos;
+						cb = c_m.cands + c_m.cand_unk; cn = 2; disc = unkFormScore(norm + node.start_pos, ol);
 					}
-				}
-				else
-				{
-					const float unkScore = unkFormScore(norm + node.uform_off, node.uform_len);
-					evaluate(i, nodeBeg, c_m.cands + c_m.cand_unk, 2, unkScore, node.uform_off, node.uform_len, inBeg, inEnd, true);
+					evaluate(i, nodeBeg, cb, cn, disc, oo, ol, inBeg, inEnd, pass == 0);
 					if (err) return 0;
 				}
 				if (lane == 0 && leader()) { npOff[i] = nodeBeg; npCnt[i] = top - nodeBeg; }
