@@ -399,7 +399,7 @@ namespace kb
 		{
 			out.tokOff.push_back((uint32_t)(base + hTokOff[k + 1]));
 			out.scores.push_back(hScore[k]); out.status.push_back(hStatus[k]);
-			if (hStatus[k]) failed.push_back(s.i0 + k);
+			if (hStatus[k] && hStatus[k] != ST_TOO_LONG) failed.push_back(s.i0 + k);      // (a chunk beyond the 16-bit node index does not fit any arena)
 		}
 		float ms;
 		cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); out.msH2D += ms;
@@ -444,7 +444,15 @@ namespace kb
 				}
 				const uint32_t pn = (uint32_t)(f1 - f0);
 				const size_t pT = subText.size(), U = 2 * pT + 4 * (size_t)pn;
-				ensureScratch(retry_, s.stream, U, pn, ppu, pc, npu);
+				try { ensureScratch(retry_, s.stream, U, pn, ppu, pc, npu); }
+				catch (const std::exception&)
+				{
+					// the escalated arena does not fit the device: these sentences keep their overflow status (no tokens), the batch goes on
+					cudaGetLastError();
+					freeScratch(retry_);
+					f0 = f1;
+					continue;
+				}
 				ck(cudaMemcpyAsync(retry_.dText, subText.data(), pT * 2, cudaMemcpyHostToDevice, s.stream), "H2D text");
 				ck(cudaMemcpyAsync(retry_.dOff, subOff.data(), ((size_t)pn + 1) * 4, cudaMemcpyHostToDevice, s.stream), "H2D offsets");
 				bind(retry_, retry_.dText, retry_.dOff, pn, matchOptions, nodeMul[round]);

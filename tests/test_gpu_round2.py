@@ -231,3 +231,16 @@ def test_top1_container_and_full_bucket_cases_match_reference(kiwi, oracle):
     sub = [texts[i] for i in hard]
     res = kiwi.analyze_batch(sub)
     _compare_with_reference(res, *_reference_dump("knlm", sub), sub, "top1 / full-bucket sentences")
+
+
+def test_input_text_never_fails_the_batch(kiwi, oracle):
+    """ADVICE r1 (medium / low): a sentence whose lattice does not fit the device structures (here: one chunk with more than 65535
+    nodes - 'a b a b ...' never meets the chunk-break condition) comes back with a non-zero status and no tokens; its neighbours in
+    the batch are analysed normally and nothing throws."""
+    texts = ["안녕하세요. 반갑습니다!", "a b " * 40000, "형태소 분석기입니다."]
+    res = kiwi.analyze_batch(texts)
+    assert int(res.status[0]) == 0 and int(res.status[2]) == 0
+    assert int(res.status[1]) != 0 and len(res.sentence(1)) == 0
+    for i in (0, 2):
+        otoks, oscore = oracle.analyze(texts[i])
+        assert [(int(k["morph_id"]), int(k["tag"]), int(k["position"]), int(k["length"])) for k in res.sentence(i)] == [x[:4] for x in otoks]
