@@ -5,6 +5,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <chrono>
 #include <thread>
 #include <stdexcept>
 #include <string>
@@ -20,6 +21,9 @@ struct kiwi_s
 	std::unique_ptr<Engine> engine;                      // primary engine (device of kiwi_init / first device of kiwi_b200_init_multi)
 	std::vector<std::unique_ptr<Engine>> extra;          // kiwi_b200_init_multi: one more engine per further device; batches are sharded round-robin
 	std::mutex mtx;           // scratch arenas and streams belong to the handle: calls on one handle are serialised
+	// result scratch that lives with the handle (used under mtx): the token arrays are page-locked, so they are made once and reused
+	std::vector<BatchOutput> shardOut;                   // per device of a sharded batch
+	BatchOutput callOut;                                 // single-sentence calls and the reader-driven batches
 	int numThreads = 0;
 	float oovChrBias = 0, oovGlobalWeight = 35, oovLocalWeight = 3, oovGlobalMinFreq = 4;      // KiwiConfig defaults of the chr-model oov scorers (stored only)
 };
@@ -209,22 +213,31 @@ static void analyzeSharded(kiwi_s* h, const uint16_t* text, const uint32_t* offs
 		h->engine->analyze(text, offsets, n, (uint32_t)option.match_options, out);
 		return;
 	}
-	std::vector<BatchOutput> part(N);
+	if (h->shardOut.size() != N) h->shardOut.resize(N);
+	std::vector<BatchOutput>& part = h->shardOut;
 	std::vector<std::string> errors(N);
+	static const bool trace = std::getenv("KIWI_B200_TRACE") != nullptr;      // stderr: where the host time of a sharded batch goes
+	using Clock = std::chrono::steady_clock;
+	const auto tStart = Clock::now();
+	std::vector<double> msGather(N, 0.0), msEngine(N, 0.0);
 	std::vector<Stats> stats(N);
 	auto work = [&](uint32_t r)
 	{
 		try
 		{
 			Engine* e = r == 0 ? h->engine.get() : h->extra[r - 1].get();
+			const auto t0 = Clock::now();
 			std::vector<uint16_t> sub; std::vector<uint32_t> off{ 0 };
 			size_t units = 0;
 			for (uint32_t i = r; i < n; i += N) units += offsets[i + 1] - offsets[i];
 			sub.reserve(units); off.reserve(n / N + 2);
 			for (uint32_t i = r; i < n; i += N) { sub.insert(sub.end(), text + offsets[i], text + offsets[i + 1]); off.push_back((uint32_t)sub.size()); }
+			const auto t1 = Clock::now();
 			TypoScope ts{ e, option };
 			e->analyze(sub.data(), off.data(), (uint32_t)off.size() - 1, (uint32_t)option.match_options, part[r]);
 			stats[r] = e->last;
+			msGather[r] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+			msEngine[r] = std::chrono::duration<double, std::milli>(Clock::now() - t1).count();
 		}
 		catch (const std::exception& ex) { errors[r] = ex.what(); if (errors[r].empty()) errors[r] = "error"; }
 	};
@@ -234,7 +247,10 @@ static void analyzeSharded(kiwi_s* h, const uint16_t* text, const uint32_t* offs
 	for (auto& t : th) t.join();
 	for (auto& e : errors) if (!e.empty()) throw std::runtime_error(e);
 	// ordered merge: token offsets by prefix sum over the round-robin order, then every shard scatters its rows
-	out = BatchOutput{};
+	// (`out` may be a recycled holder: its arrays keep their capacity)
+	const auto tMerge = Clock::now();
+	out.msH2D = out.msLattice = out.msViterbi = out.msPack = out.msD2H = out.msTotal = 0;
+	out.tokens.clear();
 	out.tokOff.assign((size_t)n + 1, 0); out.scores.resize(n); out.status.resize(n);
 	for (uint32_t i = 0; i < n; ++i)
 	{
@@ -267,6 +283,13 @@ static void analyzeSharded(kiwi_s* h, const uint16_t* text, const uint32_t* offs
 	}
 	agg.nSentences = n; agg.tokens = out.tokens.size(); agg.msLattice = out.msLattice; agg.msViterbi = out.msViterbi; agg.msPack = out.msPack;
 	h->engine->last = agg;
+	if (trace)
+	{
+		const double msAll = std::chrono::duration<double, std::milli>(Clock::now() - tStart).count(), msM = std::chrono::duration<double, std::milli>(Clock::now() - tMerge).count();
+		std::fprintf(stderr, "[kiwi_b200] sharded batch n=%u devices=%u: total %.1f ms, merge %.1f ms, per device gather/engine/device-busy ms:", n, N, msAll, msM);
+		for (uint32_t r = 0; r < N; ++r) std::fprintf(stderr, " %.1f/%.1f/%.1f", msGather[r], msEngine[r], part[r].msTotal);
+		std::fprintf(stderr, "\n");
+	}
 }
 
 // Drains the reader into batches (the reference primes pool->size()*2 futures, include/kiwi/Kiwi.h:402-454);
@@ -281,6 +304,7 @@ static int analyzeMulti(kiwi_h handle, ReadFn&& readOne, kiwi_receiver_t receive
 		const size_t maxBatch = 65536, maxUnits = 16u << 20;
 		int idx = 0, delivered = 0;
 		bool done = false;
+		BatchOutput bo;      // (page-locked token array: one per call, reused by every batch of it)
 		while (!done)
 		{
 			std::vector<uint16_t> text; std::vector<uint32_t> off{ 0 };
@@ -294,7 +318,6 @@ static int analyzeMulti(kiwi_h handle, ReadFn&& readOne, kiwi_receiver_t receive
 			}
 			const uint32_t n = (uint32_t)off.size() - 1;
 			if (!n) break;
-			BatchOutput bo;
 			{
 				std::lock_guard<std::mutex> lk(handle->mtx);
 				analyzeSharded(handle, text.data(), off.data(), n, option, bo);
@@ -514,7 +537,7 @@ kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_
 		while (text[len]) ++len;
 		const uint32_t off[2] = { 0, len };
 		std::lock_guard<std::mutex> lk(handle->mtx);
-		BatchOutput bo;
+		BatchOutput& bo = handle->callOut;
 		TypoScope ts{ handle->engine.get(), option };
 		handle->engine->analyze(text, off, 1, (uint32_t)option.match_options, bo);
 		return makeRes(handle, text, len, bo, 0, (uint32_t)option.match_options);
@@ -619,7 +642,9 @@ void kiwi_b200_batch_free(const kiwi_b200_batch_t* batch)
 	if (pool)
 	{
 		std::lock_guard<std::mutex> lk(pool->m);
-		if (!pool->closed && pool->free.size() < 4) { pool->free.push_back(h); return; }
+		// (large holders - hundreds of MB of page-locked memory each - are kept more sparingly)
+		const size_t keep = h->bo.tokens.capacity() * sizeof(DToken) > ((size_t)256 << 20) ? 2 : 4;
+		if (!pool->closed && pool->free.size() < keep) { pool->free.push_back(h); return; }
 	}
 	delete h;
 }

@@ -40,10 +40,15 @@ namespace kb
 	}
 
 	static constexpr uint32_t DEFAULT_PATHS_PER_UNIT = 128, DEFAULT_PATHS_CONST = 8192;
+#ifndef KB_DEFAULT_SOLO_BLOCKS
+#define KB_DEFAULT_SOLO_BLOCKS 0
+#define KB_DEFAULT_SOLO_WARPS 1
+#endif
 #ifndef KB_DEFAULT_TEAM_PERMILLE
 #define KB_DEFAULT_TEAM_PERMILLE 0
 #endif
 	static uint32_t teamPermille();
+	static std::pair<uint32_t, uint32_t> soloConfig();
 	// typo graph nodes / search states per normalised-unit slot (W_s = 2 n + 4 slots per sentence): the basic typo set needs < 4
 	// on the reference's evaluation texts (tests/test_hostsim_lattice.py); overflow -> ST_TYPO_OVERFLOW -> retry arena
 	static constexpr uint32_t DEFAULT_TYPO_GRAPH_PER_UNIT = 6, DEFAULT_TYPO_STATES_PER_UNIT = 6;
@@ -234,6 +239,7 @@ namespace kb
 		vv.best_rec = (int32_t*)alloc(capB * 4);
 		vv.score = (float*)alloc(capB * 4);
 		vv.timing = (unsigned long long*)alloc(capB * 16);
+		vv.work_counter = (uint32_t*)alloc(16);
 		sc.tokOff = (uint32_t*)alloc((capB + 1) * 4);
 		sc.packed = (DToken*)alloc(capU * sizeof(DToken));
 		sc.dText = (uint16_t*)alloc(capT * 2 + 64);
@@ -294,6 +300,7 @@ namespace kb
 			static const bool byLength = [] { const char* e = std::getenv("KIWI_B200_LPT"); return e && std::string(e) == "len"; }();      // experiments: keep the length order
 			if (!byLength) sc.bv.order = sc.orderVit;
 			sc.vv.n_team = (uint32_t)((unsigned long long)n * teamPermille() / 1000);
+			sc.vv.solo_blocks = soloConfig().first; sc.vv.solo_warps = soloConfig().second;
 		}
 		ck(cudaEventRecord(ev[2], st), "event");
 		ck(model.dev.model_type == 4 ? launch_viterbi_cong(model.dev, sc.bv, sc.vv, st) : launch_viterbi(model.dev, sc.bv, sc.vv, st), "viterbi_kernel launch");
@@ -306,6 +313,19 @@ namespace kb
 		pack_kernel<<<blocks, threads, 0, st>>>(n, sc.bv.text_off, sc.vv.n_tokens, sc.tokOff, sc.vv.tokens, sc.packed);
 		ck(cudaGetLastError(), "pack_kernel launch");
 		ck(cudaEventRecord(ev[4], st), "event");
+	}
+
+	// KIWI_B200_SOLO=<blocks>,<warps> (work-queue kernel build): the first <blocks> blocks of the Viterbi wave keep only <warps> warps,
+	// which start with the heaviest sentences of the launch order
+	static std::pair<uint32_t, uint32_t> soloConfig()
+	{
+		static const std::pair<uint32_t, uint32_t> v = []
+		{
+			unsigned b = KB_DEFAULT_SOLO_BLOCKS, w = KB_DEFAULT_SOLO_WARPS;
+			if (const char* e = std::getenv("KIWI_B200_SOLO")) { if (std::sscanf(e, "%u,%u", &b, &w) != 2) { b = KB_DEFAULT_SOLO_BLOCKS; w = KB_DEFAULT_SOLO_WARPS; } }
+			return std::make_pair((uint32_t)std::min(b, 64u), (uint32_t)std::min(w, 32u));
+		}();
+		return v;
 	}
 
 	// KIWI_B200_TEAM_PERMILLE: share (in 1/1000) of a pass's sentences, heaviest first, that are analysed by a team of warps
@@ -337,13 +357,16 @@ namespace kb
 		}
 	}
 
-	// Layout of a slot's pinned output buffer: [tokOff n+1][scores n][status n][debug flag 2 words][tokens ...].  Everything is
-	// enqueued behind the kernels in ONE go: the head arrays and an ESTIMATE of the packed tokens (5/8 token per raw UTF-16 unit
-	// + 8 per sentence; web text needs ~0.55), so a pass normally needs a single stream synchronisation.  finishPass fetches
-	// the rest when the estimate was too small.
+	// Layout of a slot's pinned head buffer: [tokOff n+1][scores n][status n][debug flag 2 words].  The packed tokens go straight into
+	// the caller's (page-locked) result array:
+	//  - the FIRST pass of a call knows where its tokens start (offset 0), so an ESTIMATE of them (5/8 token per raw UTF-16 unit + 8 per
+	//    sentence; web text needs ~0.55) is enqueued behind the kernels together with the head - a single-pass call needs one stream
+	//    synchronisation and no host copy; finishPass fetches the rest when the estimate was too small;
+	//  - a later pass starts where its predecessor ends, which is known only when that one has finished: finishPass enqueues its token
+	//    copy then and does not wait for it (drainTokenCopies at the end of the call, or before the array has to grow).
 	static size_t tokenEstimate(size_t rawUnits, uint32_t n) { return rawUnits * 5 / 8 + 8 * (size_t)n + 64; }
 
-	void Engine::submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t pn, uint32_t matchOptions)
+	void Engine::submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t pn, uint32_t matchOptions, DToken* directDst)
 	{
 		const size_t t0 = off[i0], pT = off[i0 + pn] - t0;
 		const size_t U = 2 * pT + 4 * (size_t)pn;
@@ -358,20 +381,32 @@ namespace kb
 		bind(s.sc, s.sc.dText, s.sc.dOff, pn, matchOptions, 1);
 		launchAll(s.sc, s.stream, s.ev, pn);
 		const size_t headWords = ((size_t)pn + 1) + 2 * (size_t)pn + 2;
-		const size_t est = std::min(tokenEstimate(pT, pn), (size_t)U);
-		growPinned(&s.hPinOut, &s.pinOutCap, headWords * 4 + 16 + est * sizeof(DToken));
+		const size_t est = directDst ? std::min(tokenEstimate(pT, pn), (size_t)U) : 0;
+		growPinned(&s.hPinOut, &s.pinOutCap, headWords * 4 + 16);
 		uint32_t* hTokOff = (uint32_t*)s.hPinOut; float* hScore = (float*)(hTokOff + pn + 1); uint32_t* hStatus = (uint32_t*)(hScore + pn); uint32_t* hDbg = hStatus + pn;
 		ck(cudaMemcpyAsync(hTokOff, s.sc.tokOff, ((size_t)pn + 1) * 4, cudaMemcpyDeviceToHost, s.stream), "D2H offsets");
 		ck(cudaMemcpyAsync(hScore, s.sc.vv.score, (size_t)pn * 4, cudaMemcpyDeviceToHost, s.stream), "D2H scores");
 		ck(cudaMemcpyAsync(hStatus, s.sc.bv.status, (size_t)pn * 4, cudaMemcpyDeviceToHost, s.stream), "D2H status");
 		ck(cudaMemcpyAsync(hDbg, s.sc.bv.debug, 4, cudaMemcpyDeviceToHost, s.stream), "D2H debug");
 		ck(cudaMemcpyAsync(hDbg + 1, model.dev.debug, 4, cudaMemcpyDeviceToHost, s.stream), "D2H debug");
-		char* hTok = (char*)s.hPinOut + ((headWords * 4 + 15) & ~(size_t)15);
-		ck(cudaMemcpyAsync(hTok, s.sc.packed, est * sizeof(DToken), cudaMemcpyDeviceToHost, s.stream), "D2H tokens");
+		if (est) ck(cudaMemcpyAsync(directDst, s.sc.packed, est * sizeof(DToken), cudaMemcpyDeviceToHost, s.stream), "D2H tokens");
 		ck(cudaEventRecord(s.ev[5], s.stream), "event");
 		s.busy = true; s.i0 = i0; s.n = pn; s.rawUnits = pT; s.units = U; s.tokCopied = est;
 		last.h2dBytes += pT * 2 + ((size_t)pn + 1) * 4;
 		last.kernelLaunches += 6;
+	}
+
+	// waits for the token copies still in flight into `out.tokens` (their time counts as D2H)
+	void Engine::drainTokenCopies(BatchOutput& out)
+	{
+		for (auto& s : slot_)
+		{
+			if (!s.tokPending) continue;
+			ck(cudaEventSynchronize(s.ev[7]), "sync (token copy)");
+			s.tokPending = false;
+			float ms = 0;
+			cudaEventElapsedTime(&ms, s.ev[6], s.ev[7]); out.msD2H += ms; out.msTotal += ms;
+		}
 	}
 
 	// waits for the slot's pass, appends its sentences (they are the next ones in input order) to `out`
@@ -380,20 +415,29 @@ namespace kb
 		if (!s.busy) return;
 		ck(cudaStreamSynchronize(s.stream), "sync (a kernel fault surfaces here)");
 		s.busy = false;
+		if (s.tokPending)      // (the stream is idle: the slot's previous token copy is done as well)
+		{
+			s.tokPending = false;
+			float ms = 0;
+			cudaEventElapsedTime(&ms, s.ev[6], s.ev[7]); out.msD2H += ms; out.msTotal += ms;
+		}
 		const uint32_t pn = s.n;
 		const size_t headWords = ((size_t)pn + 1) + 2 * (size_t)pn + 2;
 		const uint32_t* hTokOff = (const uint32_t*)s.hPinOut; const float* hScore = (const float*)(hTokOff + pn + 1); const uint32_t* hStatus = (const uint32_t*)(hScore + pn); const uint32_t* hDbg = hStatus + pn;
 		if (hDbg[0] || hDbg[1]) checkDebug(s.sc);
 		const uint32_t total = hTokOff[pn];
-		const char* hTok = (const char*)s.hPinOut + ((headWords * 4 + 15) & ~(size_t)15);
 		const size_t base = out.tokens.size();
-		out.tokens.resize(base + total);
+		// what the first pass copied on its own is in place already (base == 0 there); make it part of the array before anything can move it
 		const size_t first = std::min<size_t>(total, s.tokCopied);
-		if (first) std::memcpy(out.tokens.data() + base, hTok, first * sizeof(DToken));
+		if (first) out.tokens.resize(base + first);
 		if (total > first)
 		{
-			ck(cudaMemcpyAsync(out.tokens.data() + base + first, s.sc.packed + first, (size_t)(total - first) * sizeof(DToken), cudaMemcpyDeviceToHost, s.stream), "D2H tokens (rest)");
-			ck(cudaStreamSynchronize(s.stream), "sync");
+			if (base + total > out.tokens.capacity()) drainTokenCopies(out);      // the array is about to move
+			out.tokens.resize(base + total);
+			ck(cudaEventRecord(s.ev[6], s.stream), "event");
+			ck(cudaMemcpyAsync(out.tokens.data() + base + first, s.sc.packed + first, (size_t)(total - first) * sizeof(DToken), cudaMemcpyDeviceToHost, s.stream), "D2H tokens");
+			ck(cudaEventRecord(s.ev[7], s.stream), "event");
+			s.tokPending = true;
 		}
 		for (uint32_t k = 0; k < pn; ++k)
 		{
@@ -522,15 +566,16 @@ namespace kb
 				Slot& s = slot_[k & 1];
 				// results are appended in input order: the slot's previous pass (k - 2) is older than the other slot's (k - 1)
 				finishPass(s, out, failed);
-				submitPass(s, text, offsets, i0, i1 - i0, matchOptions);
+				submitPass(s, text, offsets, i0, i1 - i0, matchOptions, k == 0 ? out.tokens.data() : nullptr);      // (capacity reserved above)
 				i0 = i1; ++k;
 			}
 			finishPass(slot_[k & 1], out, failed);
 			finishPass(slot_[(k + 1) & 1], out, failed);
+			drainTokenCopies(out);
 		}
 		catch (...)
 		{
-			for (auto& sl : slot_) { if (sl.busy) { cudaStreamSynchronize(sl.stream); sl.busy = false; } }
+			for (auto& sl : slot_) { if (sl.busy || sl.tokPending) { cudaStreamSynchronize(sl.stream); sl.busy = false; sl.tokPending = false; } }
 			throw;
 		}
 		last.retried += failed.size();

@@ -38,16 +38,29 @@ namespace kb
 		~TypoDev();
 	};
 
-	// vector whose resize() leaves trivially-constructible elements uninitialised: the token rows are memcpy'd in right after
-	template<class T> struct NoInitAlloc : std::allocator<T>
+	// Allocator of the result token arrays: page-locked host memory (any device of the process can copy into it), and resize() leaves
+	// the trivially-constructible rows uninitialised - the device-to-host copies of a pass land in the caller's result array itself,
+	// there is no staging copy on the host.  Result holders are recycled (capi.cu), so the page-locking cost is paid once per holder.
+	template<class T> struct PinnedNoInitAlloc
 	{
-		template<class U> struct rebind { using other = NoInitAlloc<U>; };
+		using value_type = T;
+		PinnedNoInitAlloc() = default;
+		template<class U> PinnedNoInitAlloc(const PinnedNoInitAlloc<U>&) {}
+		T* allocate(size_t n)
+		{
+			void* p = nullptr;
+			if (cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); throw std::bad_alloc(); }
+			return static_cast<T*>(p);
+		}
+		void deallocate(T* p, size_t) { cudaFreeHost(p); }
 		template<class U, class... A> void construct(U* p, A&&... a)
 		{
 			if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
 		}
+		template<class U> bool operator==(const PinnedNoInitAlloc<U>&) const { return true; }
+		template<class U> bool operator!=(const PinnedNoInitAlloc<U>&) const { return false; }
 	};
-	using TokenVec = std::vector<DToken, NoInitAlloc<DToken>>;
+	using TokenVec = std::vector<DToken, PinnedNoInitAlloc<DToken>>;
 
 	struct BatchOutput
 	{
@@ -115,11 +128,12 @@ namespace kb
 		{
 			Scratch sc;
 			cudaStream_t stream = nullptr;
-			cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+			cudaEvent_t ev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };      // [6], [7]: around the deferred token copy
 			uint16_t* hPinText = nullptr; uint32_t* hPinOff = nullptr; size_t pinTextCap = 0, pinOffCap = 0;
 			void* hPinOut = nullptr; size_t pinOutCap = 0;
 			// the pass in flight
 			bool busy = false; uint32_t i0 = 0, n = 0; size_t rawUnits = 0, units = 0, tokCopied = 0;
+			bool tokPending = false;      // a token copy into the caller's result array is still in flight on `stream`
 		};
 		const TypoDev* typo_ = nullptr; float typoThreshold_ = 2.5f;
 		void ensureTypoScratch(Scratch& sc, uint32_t graphPerUnit, uint32_t statesPerUnit, uint32_t mul);
@@ -132,7 +146,8 @@ namespace kb
 		void uploadConstants();
 		void launchAll(Scratch& sc, cudaStream_t st, cudaEvent_t* ev, uint32_t n);
 		struct PassResult { std::vector<uint32_t> tokOff; TokenVec toks; std::vector<float> scores; std::vector<uint32_t> status; };
-		void submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t n, uint32_t matchOptions);
+		void submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t n, uint32_t matchOptions, DToken* directDst);
+		void drainTokenCopies(BatchOutput& out);
 		void finishPass(Slot& s, BatchOutput& out, std::vector<uint32_t>& failed);
 		void runRetry(const uint16_t* text, const uint32_t* offsets, const std::vector<uint32_t>& failed, uint32_t matchOptions, BatchOutput& out, std::vector<PassResult>& results, std::vector<uint32_t>& resultOf);
 		void checkDebug(Scratch& sc);

@@ -71,6 +71,8 @@ namespace kb
 	{
 		uint32_t paths_per_unit, paths_const;   // path capacity of sentence s = paths_per_unit * W_s + paths_const
 		uint32_t n_team;             // the first n_team sentences of the launch order are analysed by a team of warps each (viterbi.cu, team mode)
+		uint32_t solo_blocks, solo_warps;   // work-queue build: the first solo_blocks blocks keep only solo_warps warps, which start with the heaviest sentences
+		uint32_t* work_counter;      // work-queue build: next position of the launch order to hand out (zeroed before every launch)
 		DPath* paths;                // pool, index pbase = paths_per_unit * wbase + paths_const * s
 		uint32_t* node_path_off;     // per lattice node (nbase + chunk.node_off + i)
 		uint32_t* node_path_cnt;

@@ -451,6 +451,9 @@ namespace KB_VIT_NS
 #ifndef KB_TEAM
 #define KB_TEAM 4
 #endif
+#ifndef KB_QUEUE
+#define KB_QUEUE 0      // 1: persistent warps draw sentences from a work queue (needs KB_TEAM=1)
+#endif
 	static constexpr uint32_t TEAM = KB_TEAM, TEAMS_PER_BLOCK = KB_VIT_WARPS / KB_TEAM > 0 ? KB_VIT_WARPS / KB_TEAM : 1;
 	static_assert(KB_VIT_WARPS % KB_TEAM == 0 || KB_VIT_WARPS < KB_TEAM, "teams tile the block");
 	struct TeamSmem
@@ -1063,6 +1066,8 @@ namespace KB_VIT_NS
 			pfPhase ^= 1u << buf;
 			pfBase[buf] = nullptr;
 		}
+		// a sentence that stopped on an error may leave a copy in flight: wait for it before the buffers serve the next sentence
+		__device__ void pfDrain() { if (pfBase[0] != nullptr) pfWait(0); if (pfBase[1] != nullptr) pfWait(1); }
 #else
 #define KB_TMA_ROWS 0
 #endif
@@ -2357,6 +2362,35 @@ namespace KB_VIT_NS
 		if (threadIdx.x < TEAMS_PER_BLOCK) teamSm[threadIdx.x].err = 0;
 		__syncthreads();
 		uint32_t slot, teamRank = 0, teamSize = 1, teamIdx = 0;
+#if KB_QUEUE
+		// Work queue: the grid is one wave of resident blocks; every warp analyses one sentence after the other, taking the next position
+		// of the launch order (heaviest predicted sentence first) from a global counter - a warp that drew a light sentence is back for
+		// more at once, so the launch ends when its heaviest sentence does, not when the last statically assigned block has been scheduled.
+		// The first solo_blocks blocks keep only solo_warps warps, which start with the very heaviest sentences (positions
+		// 0 .. solo_blocks * solo_warps - 1) and so run them with little competition for their SM's issue slots and instruction cache.
+		static_assert(TEAM == 1, "the work queue hands sentences to single warps");
+		const uint32_t nSolo = min(vv.solo_blocks * vv.solo_warps, bv.n_sent);
+		const bool soloBlock = blockIdx.x < vv.solo_blocks;
+		if (soloBlock && wib >= vv.solo_warps) return;
+		bool firstDraw = true;
+		uint32_t pfPhaseKeep = 0, curBufKeep = 0;
+#if KB_TMA_ROWS
+		{ Vit v0{ bv, vv, lane }; v0.sm = &smAll[wib]; v0.pfInit(); }
+#endif
+		for (;;)
+		{
+		if (soloBlock && firstDraw && blockIdx.x * vv.solo_warps + wib < nSolo) slot = blockIdx.x * vv.solo_warps + wib;
+		else
+		{
+			uint32_t d = 0;
+			if (lane == 0) d = atomicAdd(vv.work_counter, 1u);
+			slot = nSolo + __shfl_sync(0xFFFFFFFFu, d, 0);
+		}
+		firstDraw = false;
+		if (slot >= bv.n_sent) return;
+		const uint32_t s = bv.order[slot];
+		if (bv.status[s]) { if (lane == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } continue; }
+#else
 		if (TEAM > 1 && blockIdx.x < nTeamBlocks)
 		{
 			teamIdx = wib / TEAM; teamRank = wib % TEAM; teamSize = TEAM;
@@ -2367,6 +2401,7 @@ namespace KB_VIT_NS
 		if (slot >= bv.n_sent) return;
 		const uint32_t s = bv.order[slot];
 		if (bv.status[s]) { if (lane == 0 && teamRank == 0) { vv.best_rec[s] = -1; vv.score[s] = 0; } return; }
+#endif
 
 #ifndef KB_HOSTSIM
 		if (lane == 0 && teamRank == 0) { unsigned long long tns; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns)); vv.timing[2 * s] = tns; }
@@ -2391,7 +2426,11 @@ namespace KB_VIT_NS
 		v.splitComplex = (bv.match_options >> 22) & 1; v.splitSaisiot = (bv.match_options >> 25) & 1; v.mergeSaisiot = (bv.match_options >> 26) & 1;
 		v.htClear();
 #if KB_TMA_ROWS
+#if KB_QUEUE
+		v.pfPhase = pfPhaseKeep; v.curBuf = curBufKeep;      // the warp's transaction barriers live across its sentences
+#else
 		v.pfInit();
+#endif
 #endif
 
 		const DChunk* chunks = bv.chunks + (wbase >> 2) + 2 * (size_t)s;
@@ -2508,6 +2547,13 @@ namespace KB_VIT_NS
 			vv.score[s] = (!v.err && retN) ? retScore[0] : 0.f;
 			if (v.err) bv.status[s] = v.err;
 		}
+#if KB_QUEUE
+#if KB_TMA_ROWS
+		v.pfDrain(); pfPhaseKeep = v.pfPhase; curBufKeep = v.curBuf;
+#endif
+		__syncwarp();
+		}      // next sentence of the queue
+#endif
 	}
 
 #if KB_CONG
@@ -2581,14 +2627,44 @@ namespace KB_VIT_NS
 			if (const char* co = getenv("KIWI_B200_CARVEOUT")) cudaFuncSetAttribute(KB_VIT_KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co));
 			attrSet = true;
 		}
+#if KB_QUEUE
+		// work queue: one wave of resident blocks (SM count x blocks per SM at this register / shared-memory footprint)
+		VitView vq = vv;
+		if (!vq.work_counter) return (cudaError_t)1;      // cudaErrorInvalidValue
+		uint32_t grid = blocks;
+#ifndef KB_HOSTSIM
+		static int residentOn[64] = {};
+		int& resident = residentOn[devId & 63];
+		if (!resident)
+		{
+			int perSm = 0, sms = 0;
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, KB_VIT_KERNEL, WARPS_PER_BLOCK * 32, smemBytes);
+			cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devId);
+			resident = perSm > 0 && sms > 0 ? perSm * sms : 148;
+		}
+		if (vq.solo_warps == 0 || vq.solo_warps > WARPS_PER_BLOCK) vq.solo_blocks = 0;
+		// the solo blocks' missing warps are made up for by as many extra blocks only if they would still be resident: they are not, so the
+		// wave stays at `resident` blocks and the solo blocks trade (WARPS_PER_BLOCK - solo_warps) warp slots each for an undisturbed SM
+		grid = blocks + vq.solo_blocks < (uint32_t)resident ? blocks + vq.solo_blocks : (uint32_t)resident;
+		if (vq.solo_blocks > grid / 2) vq.solo_blocks = grid / 2;
+		if (cudaError_t e = cudaMemsetAsync(vq.work_counter, 0, sizeof(uint32_t), stream)) return e;
+#else
+		vq.solo_blocks = 0; *vq.work_counter = 0;
+#endif
+#define KB_VV vq
+#define KB_GRID grid
+#else
+#define KB_VV vv
+#define KB_GRID blocks
+#endif
 #ifdef KB_HOSTSIM
 		// tests/hostsim: one sentence, one block of WARPS_PER_BLOCK warps (one warp works, or - n_team == 1 - one team)
 		if (bv.n_sent != 1) return 1;
 		(void)stream; (void)smemBytes;
-		simt::launch(blocks, WARPS_PER_BLOCK * 32, [&] { KB_VIT_KERNEL(bv, vv); });
+		simt::launch(KB_GRID, WARPS_PER_BLOCK * 32, [&] { KB_VIT_KERNEL(bv, KB_VV); });
 		return cudaSuccess;
 #else
-		KB_VIT_KERNEL<<<blocks, WARPS_PER_BLOCK * 32, smemBytes, stream>>>(bv, vv);
+		KB_VIT_KERNEL<<<KB_GRID, WARPS_PER_BLOCK * 32, smemBytes, stream>>>(bv, KB_VV);
 		return cudaGetLastError();
 #endif
 	}

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <thread>
 #include <kiwi/Kiwi.h>
 #include <kiwi/TypoTransformer.h>
 #include "StrUtils.h"
@@ -68,8 +69,15 @@ int main(int argc, char** argv)
 			option.typoTransformer = &ptt;
 		}
 		const KiwiConfig config = kw.globalConfig;
+		// KB_FRESH_THREAD=1: every sentence is analysed on a thread of its own.  The reference keeps its `top1` path container (an
+		// std::unordered_set, BestPathContainer.hpp:229-276) in thread-local storage; its bucket count - and with it the order in which a
+		// later sentence's paths come out - depends on the sentences the thread has analysed before.  A fresh thread gives every sentence the
+		// state of a thread's first analysis, which is the definition the oracle and the CUDA path use.
+		const bool freshThread = getenv("KB_FRESH_THREAD") != nullptr;
 		while (std::getline(ifs, line) && idx < maxLines)
 		{
+			auto body = [&]()
+			{
 			if (!line.empty() && line.back() == '\r') line.pop_back();
 			const auto tab = line.find('\t');
 			if (tab != line.npos) line = line.substr(0, tab);
@@ -202,6 +210,8 @@ int main(int argc, char** argv)
 					}
 				}
 			}
+			};
+			if (freshThread) { std::thread th(body); th.join(); } else body();
 			++idx;
 		}
 		std::fclose(fo);

@@ -78,7 +78,7 @@ namespace orc
 			if (matchOptions & (1u << 16)) normalizeCoda(norm);
 			res.normLen = norm.size();
 			work.sentences++; work.rawUnits += len; work.normUnits += norm.size();
-			viterbi.resetHistory();      // every sentence starts with a fresh `top1` container (see viterbi.hpp)
+			if (!std::getenv("ORC_KEEP_TOP1_HISTORY")) viterbi.resetHistory();      // every sentence starts with a fresh `top1` container (see viterbi.hpp)
 
 			std::vector<Ret> ret;
 			std::vector<uint8_t> spStatesByRet;

@@ -29,6 +29,7 @@ namespace orc
 		SbHist sb;                    // SkipBigram only: ring of the last valid tokens, part of the state's identity
 		uint64_t hashv = 0;           // Hash<WordLL> of the reference, kept for the `top1` container (an std::unordered_set there)
 		uint8_t cmpSb = 0;
+		uint8_t hashByte = 0;         // BucketedHashContainer::hashes: low byte of the hash the entry was APPENDED with (not refreshed by an overwrite)
 		uint8_t prevRootId = 0, spState = 0, rootId = 0;
 		int32_t morpheme = -1;
 		float accScore = 0, firstChunkScore = 0, accTypoCost = 0, accDialectCost = 0;
@@ -243,10 +244,41 @@ namespace orc
 			}
 			const size_t bucket = cont.mode == 1 ? ((h >> 8) & 3) : 0;
 			auto& value = cont.buckets[bucket];
-			size_t it = 0;
-			for (; it < value.size(); ++it)
+			// insertOptimized<avx2> (BestPathContainer.hpp:316-383 with nst::findAll<avx2>, search.cpp:948-968), as it BEHAVES on x86-64:
+			//  - the candidates of the first 64 entries are findAll(hash, min(n, 64), h): a byte-compare mask ANDed with ((size_t)1 << size) - 1.
+			//    For size == 64 that shift is by the register width: x86 masks the count to 0, the mask becomes 0 and NO entry of the first
+			//    64 is ever a candidate once the bucket holds 64 entries;
+			//  - the candidates of entries 64.. are findAll(hash + 64, n - 64, h) (again empty when n - 64 == 64), and the equality test of
+			//    candidate i looks at value[i] where it means value[64 + i]: when value[i] is the new state, entry 64 + i - some other state
+			//    with the same hash byte, or an earlier duplicate - is the one that gets compared by score and overwritten;
+			//  - for 32 < size < 64 the low movemask is sign-extended: when byte 31 matches, every position 32 .. size-1 becomes a candidate.
+			//  - no candidate matches: the state is appended (a second time, if it lives among the first 64) while there is room.
+			// Knlm / CoNg buckets rarely reach 64 states; SkipBigram states (8-token ring) rarely merge and live in this regime.
+			static const bool searchAll = std::getenv("ORC_BUCKET_SEARCH_ALL") != nullptr;      // (experiments: what the code comments intend)
+			const size_t nVal = value.size();
+			auto eq = [&](size_t k) { return value[k].prevRootId == prevRootId && value[k].spState == spState && value[k].lmState == lmState && (!(sbg && sbh) || value[k].sb == *sbh); };
+			auto candMask = [&](size_t from, size_t size) -> uint64_t      // findAllAVX2(hash + from, size, h)
 			{
-				if (value[it].prevRootId == prevRootId && value[it].spState == spState && value[it].lmState == lmState && (!(sbg && sbh) || value[it].sb == *sbh)) break;
+				uint64_t lo = 0, hi = 0;
+				for (size_t k = 0; k < size && k < 32; ++k) if (value[from + k].hashByte == (uint8_t)h) lo |= 1ull << k;
+				if (size <= 32) return lo & ((1ull << size) - 1);
+				for (size_t k = 32; k < size; ++k) if (value[from + k].hashByte == (uint8_t)h) hi |= 1ull << k;
+				// NB: the reference loads 32 bytes past `size` as well (stale hash bytes of the array); they fall to the final mask
+				if (lo & 0x80000000ull) lo |= 0xFFFFFFFF00000000ull;      // (size_t)(int)movemask: sign extension
+				const uint64_t mask = size >= 64 ? 0ull : ((1ull << size) - 1);      // shift count taken mod 64 by the hardware
+				return (lo | hi) & mask;
+			};
+			size_t it = nVal;
+			if (searchAll) { for (size_t k = 0; k < nVal; ++k) if (eq(k)) { it = k; break; } }
+			else
+			{
+				uint64_t b0 = candMask(0, std::min<size_t>(nVal, 64));
+				for (; b0 && it == nVal; b0 &= b0 - 1) { const size_t k = (size_t)__builtin_ctzll(b0); if (eq(k)) it = k; }
+				if (it == nVal && nVal > 64)
+				{
+					uint64_t b1 = candMask(64, nVal - 64);
+					for (; b1 && it == nVal; b1 &= b1 - 1) { const size_t k = (size_t)__builtin_ctzll(b1); if (eq(k)) it = k + 64; }
+				}
 			}
 			if (it >= value.size())
 			{
@@ -259,6 +291,7 @@ namespace orc
 					w.rootId = parentRootId;
 					w.prevRootId = prevRootId;
 					if (rootId != commonRootId) w.rootId = rootId;
+					w.hashByte = (uint8_t)h;
 					value.push_back(w);
 				}
 				else if (cnt) cnt->bucketFull++;

@@ -91,6 +91,8 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 		auto paths = buf<DPath>(ppu * U + pc); auto npOff = buf<uint32_t>(U * npu), npCnt = buf<uint32_t>(U * npu); auto nodeCand = buf<uint2>(U * npu); auto reach = buf<uint8_t>(U * npu);
 		auto recs = buf<DRec>(2 * chunkSlots); auto toks = buf<DToken>(U); auto nTok = buf<uint32_t>(2); auto bestRec = buf<int32_t>(1); auto sc = buf<float>(1);
 		auto timing = buf<unsigned long long>(2);
+		auto workCounter = buf<uint32_t>(4);
+		vv.work_counter = workCounter.data(); vv.solo_blocks = 0; vv.solo_warps = 1;
 		vv.n_team = std::getenv("HS32_TEAM") ? 1u : 0u;      // HS32_TEAM=1: the sentence is analysed by a team of warps (viterbi.cu team mode)
 		vv.paths_per_unit = (uint32_t)ppu; vv.paths_const = (uint32_t)pc; vv.paths = paths.data(); vv.node_path_off = npOff.data(); vv.node_path_cnt = npCnt.data(); vv.node_cand = nodeCand.data();
 		vv.reachable = reach.data(); vv.recs = recs.data(); vv.tokens = toks.data(); vv.n_tokens = nTok.data(); vv.best_rec = bestRec.data(); vv.score = sc.data(); vv.timing = timing.data();
