@@ -25,6 +25,7 @@ CONFIGS = {
     3: dict(model="cong", batch=65536, typo=None, typo_frac=0.0, rotate=1, steps=5, scaling="weak"),
     4: dict(model="knlm", batch=65536, typo="basic", typo_frac=0.3, rotate=1, steps=5, scaling="weak"),
     5: dict(model="cong", batch=1 << 20, typo=None, typo_frac=0.0, rotate=1, steps=3, scaling="strong"),
+    6: dict(model="sbg", batch=2048, typo=None, typo_frac=0.0, rotate=1, steps=3, scaling="weak"),      # not a BASELINE.json config: the SkipBigram model type
 }
 BLOCK = 8192      # synthetic sentences are generated in seeded blocks of 8192 (block b: seed SEED + b)
 
@@ -35,7 +36,7 @@ def ref_model_dir(model): return os.path.join(ROOT, "oracle", "_ref", "models", 
 
 def workload_string(cfg, cid):
     s = "config %d: batch=%d synthetic Korean sentences (web.txt length dist), fabricated %s model (%s_small), top-1" % (
-        cid, cfg["batch"], "Knlm" if cfg["model"] == "knlm" else "CoNg", cfg["model"])
+        cid, cfg["batch"], {"knlm": "Knlm", "cong": "CoNg", "sbg": "SkipBigram"}[cfg["model"]], cfg["model"])
     if cfg["typo"]: s += ", typo lattice (%s typo set, typoCostWeight 6, threshold 2.5), %d %% of the sentences from web_with_typos eojeols" % (cfg["typo"], round(100 * cfg["typo_frac"]))
     if cfg["scaling"] == "strong": s += ", sharded round-robin (sentence i -> GPU i mod N)"
     return s
@@ -158,7 +159,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="override the configuration's batch size (experiments)")
-    ap.add_argument("--model", default=None, choices=["knlm", "cong"], help="override the configuration's model (experiments)")
+    ap.add_argument("--model", default=None, choices=["knlm", "cong", "sbg"], help="override the configuration's model (experiments)")
     ap.add_argument("--typo", default=None, choices=["basic", "none"], help="override the configuration's typo set (experiments)")
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (kernel experiments)")
@@ -325,7 +326,7 @@ def main():
     value = total_sent / (dev_ms / 1000.0)
     peak, peak_kind = load_peaks()
     c, lat_b, vit_b, csrc = work_counters(cfg, args.config, batches[0][0], SEED)
-    kernel = "viterbi_kernel" if cfg["model"] == "knlm" else "viterbi_cong_kernel"
+    kernel = {"knlm": "viterbi_kernel", "cong": "viterbi_cong_kernel", "sbg": "viterbi_sbg_kernel"}[cfg["model"]]
     vit_per_step_ms = ms_vit / steps if steps else 0.0
     achieved = vit_b * n_local / (vit_per_step_ms / 1000.0) / 1e9 if vit_per_step_ms else None
     prof = {}

@@ -104,7 +104,10 @@ namespace kb
 		const size_t wbase = 2 * (size_t)t0 + 4 * (size_t)s;
 		const size_t nbase = (size_t)bv.nodes_per_unit * wbase;
 		const size_t pbase = (size_t)vv.paths_per_unit * wbase + (size_t)vv.paths_const * s;
-		const DPath* pool = vv.paths + pbase;
+		// (records of vv.path_stride bytes: the SkipBigram build appends its history to DPath)
+		const char* poolBytes = reinterpret_cast<const char*>(vv.paths) + pbase * (size_t)vv.path_stride;
+		const uint32_t stride = vv.path_stride;
+		auto P = [&](uint32_t i) -> const DPath& { return *reinterpret_cast<const DPath*>(poolBytes + (size_t)i * stride); };
 		const DChunk* chunks = bv.chunks + (wbase >> 2) + 2 * (size_t)s;
 		const DRec* recs = vv.recs + 2 * ((wbase >> 2) + 2 * (size_t)s);
 		const bool splitSaisiot = (bv.match_options >> 25) & 1;
@@ -123,17 +126,17 @@ namespace kb
 			const DChunk ch = chunks[rec.chunk];
 			const DNode* gnodes = bv.nodes + nbase + ch.node_off;
 			uint32_t nSteps = 0;
-			for (uint32_t p = rec.end_parent; pool[p].parent != NPOS; p = pool[p].parent)
+			for (uint32_t p = rec.end_parent; P(p).parent != NPOS; p = P(p).parent)
 			{
 				if (nSteps >= W) { e.err = ST_TOKEN_OVERFLOW; break; }
 				steps[nSteps++] = p;
 			}
 			if (e.err || !nSteps) break;
-			uint32_t prevIdx = pool[steps[nSteps - 1]].parent;
+			uint32_t prevIdx = P(steps[nSteps - 1]).parent;
 			for (int32_t si = (int32_t)nSteps - 1; si >= 0 && !e.err; --si)
 			{
-				const DPath cur = pool[steps[si]];
-				const float prevAcc = pool[prevIdx].acc_score, prevTypo = pool[prevIdx].acc_typo_cost;
+				const DPath cur = P(steps[si]);
+				const float prevAcc = P(prevIdx).acc_score, prevTypo = P(prevIdx).acc_typo_cost;
 				const float scoreDiff = cur.acc_score - prevAcc;
 				const float typoCostDiff = cur.acc_typo_cost - prevTypo;
 				const DMorph mm = c_m.morphs[cur.morpheme];

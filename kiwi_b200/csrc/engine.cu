@@ -30,6 +30,8 @@ namespace kb
 	cudaError_t set_model_viterbi(const DevModel& m);
 	cudaError_t launch_viterbi_cong(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
 	cudaError_t set_model_viterbi_cong(const DevModel& m);
+	cudaError_t launch_viterbi_sbg(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
+	cudaError_t set_model_viterbi_sbg(const DevModel& m);
 	cudaError_t launch_cong_debug(uint32_t n, const uint32_t* ctx, const uint32_t* wid, const int32_t* node,
 		int32_t* outDot, float* outEps, int32_t* outNode, uint32_t* outCtx, int32_t* outTile, cudaStream_t stream);
 	cudaError_t set_model_emit(const DevModel& m);
@@ -228,7 +230,8 @@ namespace kb
 		bv.debug = (uint32_t*)alloc(64 * 4);
 		ck(cudaMemset(bv.debug, 0, 64 * 4), "memset");
 		vv.paths_per_unit = ppu; vv.paths_const = pc;
-		vv.paths = (DPath*)alloc(((size_t)ppu * capU + (size_t)pc * capB) * sizeof(DPath));
+		vv.path_stride = pathStride();
+		vv.paths = (DPath*)alloc(((size_t)ppu * capU + (size_t)pc * capB) * vv.path_stride);
 		vv.node_path_off = (uint32_t*)alloc(capU * npu * 4);
 		vv.node_path_cnt = (uint32_t*)alloc(capU * npu * 4);
 		vv.node_cand = (uint2*)alloc(capU * npu * 8);
@@ -275,7 +278,7 @@ namespace kb
 	{
 		DevState& ds = g_devState[device < 0 || device >= 64 ? 0 : device];
 		if (ds.owner == &model) return;
-		ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
+		ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : model.dev.model_type == 3 ? set_model_viterbi_sbg(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
 		ds.owner = &model;
 	}
 
@@ -303,7 +306,7 @@ namespace kb
 			sc.vv.solo_blocks = soloConfig().first; sc.vv.solo_warps = soloConfig().second;
 		}
 		ck(cudaEventRecord(ev[2], st), "event");
-		ck(model.dev.model_type == 4 ? launch_viterbi_cong(model.dev, sc.bv, sc.vv, st) : launch_viterbi(model.dev, sc.bv, sc.vv, st), "viterbi_kernel launch");
+		ck(model.dev.model_type == 4 ? launch_viterbi_cong(model.dev, sc.bv, sc.vv, st) : model.dev.model_type == 3 ? launch_viterbi_sbg(model.dev, sc.bv, sc.vv, st) : launch_viterbi(model.dev, sc.bv, sc.vv, st), "viterbi_kernel launch");
 		ck(cudaEventRecord(ev[3], st), "event");
 		ck(launch_emit(model.dev, sc.bv, sc.vv, st), "emit_kernel launch");
 		ck(cudaMemsetAsync(sc.vv.n_tokens + n, 0, 4, st), "memset");
@@ -370,7 +373,7 @@ namespace kb
 	{
 		const size_t t0 = off[i0], pT = off[i0 + pn] - t0;
 		const size_t U = 2 * pT + 4 * (size_t)pn;
-		ensureScratch(s.sc, s.stream, U, pn, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
+		ensureScratch(s.sc, s.stream, U, pn, DEFAULT_PATHS_PER_UNIT * pathScale(), DEFAULT_PATHS_CONST * pathScale(), KB_DEFAULT_NODES_PER_UNIT);
 		growPinned((void**)&s.hPinText, &s.pinTextCap, pT * 2 + 64);
 		growPinned((void**)&s.hPinOff, &s.pinOffCap, ((size_t)pn + 1) * 4);
 		std::memcpy(s.hPinText, text + t0, pT * 2);
@@ -467,7 +470,7 @@ namespace kb
 		Slot& s = slot_[0];
 		for (int round = 0; round < 2 && !failed.empty(); ++round)
 		{
-			const uint32_t ppu = DEFAULT_PATHS_PER_UNIT * pathMul[round], pc = DEFAULT_PATHS_CONST * pathMul[round], npu = KB_DEFAULT_NODES_PER_UNIT * nodeMul[round];
+			const uint32_t ppu = DEFAULT_PATHS_PER_UNIT * pathScale() * pathMul[round], pc = DEFAULT_PATHS_CONST * pathScale() * pathMul[round], npu = KB_DEFAULT_NODES_PER_UNIT * nodeMul[round];
 			std::vector<uint32_t> still;
 			size_t f0 = 0;
 			while (f0 < failed.size())
@@ -476,7 +479,7 @@ namespace kb
 				while (f1 < failed.size())
 				{
 					const size_t u = 2 * (size_t)(offsets[failed[f1] + 1] - offsets[failed[f1]]) + 4;
-					if (f1 > f0 && ((units + u) * ppu + (f1 - f0 + 1) * (size_t)pc) * sizeof(DPath) > budget) break;
+					if (f1 > f0 && ((units + u) * ppu + (f1 - f0 + 1) * (size_t)pc) * pathStride() > budget) break;
 					units += u; ++f1;
 				}
 				std::vector<uint16_t> subText; std::vector<uint32_t> subOff{ 0 };
@@ -550,7 +553,7 @@ namespace kb
 		out.tokOff.reserve((size_t)n + 1); out.scores.reserve(n); out.status.reserve(n);
 		out.tokens.reserve(tokenEstimate(offsets[n], n));
 		std::vector<uint32_t> failed;
-		const size_t sentLimit = passSentLimit();
+		const size_t sentLimit = std::max<size_t>(passSentLimit() / passDivisor(), 1), unitLimit = MAX_UNITS_PER_PASS / passDivisor();
 		uint32_t i0 = 0, k = 0;
 		try
 		{
@@ -560,7 +563,7 @@ namespace kb
 				while (i1 < n && i1 - i0 < sentLimit)
 				{
 					const size_t u = 2 * (size_t)(offsets[i1 + 1] - offsets[i1]) + 4;
-					if (i1 > i0 && units + u > MAX_UNITS_PER_PASS) break;
+					if (i1 > i0 && units + u > unitLimit) break;
 					units += u; ++i1;
 				}
 				Slot& s = slot_[k & 1];
@@ -621,7 +624,8 @@ namespace kb
 		Slot& s = slot_[0];
 		std::vector<uint32_t> off;
 		const size_t Uall = 2 * (size_t)totalUnits + 4 * (size_t)n;
-		const bool single = Uall <= 4 * MAX_UNITS_PER_PASS && n <= 4 * MAX_SENT_PER_PASS;      // (one launch set keeps the longest-first order over the whole batch)
+		const size_t devUnits = 4 * MAX_UNITS_PER_PASS / passDivisor(), devSent = 4 * MAX_SENT_PER_PASS / passDivisor();
+		const bool single = Uall <= devUnits && n <= devSent;      // (one launch set keeps the longest-first order over the whole batch)
 		if (!single)
 		{
 			off.resize((size_t)n + 1);
@@ -636,17 +640,17 @@ namespace kb
 			if (!single)
 			{
 				i1 = i0; size_t units = 0;
-				while (i1 < n && i1 - i0 < 4 * MAX_SENT_PER_PASS)
+				while (i1 < n && i1 - i0 < devSent)
 				{
 					const size_t u = 2 * (size_t)(off[i1 + 1] - off[i1]) + 4;
-					if (i1 > i0 && units + u > 4 * MAX_UNITS_PER_PASS) break;
+					if (i1 > i0 && units + u > devUnits) break;
 					units += u; ++i1;
 				}
 				pT = off[i1] - off[i0];
 			}
 			const uint32_t pn = i1 - i0;
 			const size_t U = 2 * pT + 4 * (size_t)pn;
-			ensureScratch(s.sc, s.stream, U, pn, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
+			ensureScratch(s.sc, s.stream, U, pn, DEFAULT_PATHS_PER_UNIT * pathScale(), DEFAULT_PATHS_CONST * pathScale(), KB_DEFAULT_NODES_PER_UNIT);
 			const uint16_t* pText = dText; const uint32_t* pOff = dOffsets;
 			if (!single)
 			{
@@ -750,7 +754,7 @@ namespace kb
 		const size_t U = 2 * (size_t)len + 4;
 		DeviceGuard g{ device };
 		Scratch& sc = slot_[0].sc;
-		ensureScratch(sc, stream, U, 1, DEFAULT_PATHS_PER_UNIT, DEFAULT_PATHS_CONST, KB_DEFAULT_NODES_PER_UNIT);
+		ensureScratch(sc, stream, U, 1, DEFAULT_PATHS_PER_UNIT * pathScale(), DEFAULT_PATHS_CONST * pathScale(), KB_DEFAULT_NODES_PER_UNIT);
 		ck(cudaMemcpyAsync(sc.dText, text, (size_t)len * 2, cudaMemcpyHostToDevice, stream), "H2D");
 		ck(cudaMemcpyAsync(sc.dOff, off, 8, cudaMemcpyHostToDevice, stream), "H2D");
 		bind(sc, sc.dText, sc.dOff, 1, matchOptions, 1);

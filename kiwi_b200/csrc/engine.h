@@ -148,6 +148,11 @@ namespace kb
 		struct PassResult { std::vector<uint32_t> tokOff; TokenVec toks; std::vector<float> scores; std::vector<uint32_t> status; };
 		void submitPass(Slot& s, const uint16_t* text, const uint32_t* off, uint32_t i0, uint32_t n, uint32_t matchOptions, DToken* directDst);
 		void drainTokenCopies(BatchOutput& out);
+		// SkipBigram states (Knlm node + 8-token history) rarely merge: 8 x the paths per sentence from the start (the first retry round of the
+		// other models), passes 16 x smaller so that the arena stays the same size
+		uint32_t pathScale() const { return model.dev.model_type == 3 ? 8u : 1u; }
+		size_t passDivisor() const { return model.dev.model_type == 3 ? 16 : 1; }
+		size_t pathStride() const { return model.dev.model_type == 3 ? 96 : sizeof(DPath); }      // SkipBigram paths carry their 8-token history (viterbi.cu PathS)
 		void finishPass(Slot& s, BatchOutput& out, std::vector<uint32_t>& failed);
 		void runRetry(const uint16_t* text, const uint32_t* offsets, const std::vector<uint32_t>& failed, uint32_t matchOptions, BatchOutput& out, std::vector<PassResult>& results, std::vector<uint32_t>& resultOf);
 		void checkDebug(Scratch& sc);

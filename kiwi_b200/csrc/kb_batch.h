@@ -70,6 +70,7 @@ namespace kb
 	struct VitView
 	{
 		uint32_t paths_per_unit, paths_const;   // path capacity of sentence s = paths_per_unit * W_s + paths_const
+		uint32_t path_stride;        // bytes per path record: sizeof(DPath), or 96 for SkipBigram images (DPath + the 8-token history, viterbi.cu PathS)
 		uint32_t n_team;             // the first n_team sentences of the launch order are analysed by a team of warps each (viterbi.cu, team mode)
 		uint32_t solo_blocks, solo_warps;   // work-queue build: the first solo_blocks blocks keep only solo_warps warps, which start with the heaviest sentences
 		uint32_t* work_counter;      // work-queue build: next position of the launch order to hand out (zeroed before every launch)

@@ -193,7 +193,11 @@ namespace kb
 		const uint32_t* cg_inv_vocab;  // nullptr when absent
 		const float* cg_out_bias;      // nullptr when absent
 		uint32_t cg_dim, cg_stride, cg_key_size, cg_root_size, cg_context_size;
-		uint32_t model_type;           // (int)ModelType: 2 knlm, 4 cong
+		// SkipBigram (model_type sbg; null / 0 otherwise): the image sections as they are (src/SkipBigramModel.hpp:24-32) - per target token a
+		// sorted list of history tokens with their compensations, per token a discount and the validity flag
+		const uint32_t* sb_ptrs; const uint32_t* sb_keys; const float* sb_comps; const float* sb_discnts; const uint8_t* sb_valid;
+		uint32_t sb_vocab_size; float sb_log_window;
+		uint32_t model_type;           // (int)ModelType: 2 knlm, 3 sbg, 4 cong
 		// scalars
 		uint32_t n_chr_runs, n_morphs, n_forms, n_trie_nodes;
 		uint32_t default_tag_size, lang_vocab_size;

@@ -2,6 +2,7 @@
 // tables described in kb_model.h and uploads everything to the current device.
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -88,7 +89,8 @@ namespace kb
 		if (h->magic != KB2_IMAGE_MAGIC) throw std::runtime_error("not a kiwi_b200 model image (bad magic)");
 		if (h->version != KB2_IMAGE_VERSION) throw std::runtime_error("model image version mismatch: rebuild the image with this build's flatten tool");
 		if (h->total_bytes != size) throw std::runtime_error("model image is truncated");
-		if (h->model_type != 2 && h->model_type != 4) throw std::runtime_error("only Knlm and CoNg (quantized, no window) images are supported by this build");
+		if (h->model_type != 2 && h->model_type != 3 && h->model_type != 4) throw std::runtime_error("only Knlm, SkipBigram and CoNg (quantized, no window) images are supported by this build");
+		if (h->model_type == 3 && (h->sb_window_size != 8 || h->sb_vocab_size == 0)) throw std::runtime_error("SkipBigram image: window size must be 8");
 		const bool cong = h->model_type == 4;
 		if (cong && (h->cg_dim == 0 || h->cg_dim % 32 != 0 || h->cg_dim > 1024)) throw std::runtime_error("CoNg image: dim must be a multiple of 32 (tensor-core tile depth)");
 		header = *h;
@@ -384,6 +386,13 @@ namespace kb
 			d.cg_inv_vocab = h->sec[KB2_SEC_CG_INV_VOCAB].nbytes ? reinterpret_cast<const uint32_t*>(dsec(KB2_SEC_CG_INV_VOCAB)) : nullptr;
 			d.cg_out_bias = h->sec[KB2_SEC_CG_OUT_BIAS].nbytes ? reinterpret_cast<const float*>(dsec(KB2_SEC_CG_OUT_BIAS)) : nullptr;
 			d.cg_dim = h->cg_dim; d.cg_stride = h->cg_dim + 8; d.cg_key_size = h->cg_key_size; d.cg_root_size = h->cg_root_size; d.cg_context_size = h->cg_context_size;
+		}
+		if (h->model_type == 3)
+		{
+			d.sb_ptrs = reinterpret_cast<const uint32_t*>(dsec(KB2_SEC_SB_PTRS)); d.sb_keys = reinterpret_cast<const uint32_t*>(dsec(KB2_SEC_SB_KEYS));
+			d.sb_comps = reinterpret_cast<const float*>(dsec(KB2_SEC_SB_COMPS)); d.sb_discnts = reinterpret_cast<const float*>(dsec(KB2_SEC_SB_DISCNTS));
+			d.sb_valid = reinterpret_cast<const uint8_t*>(dsec(KB2_SEC_SB_VALID));
+			d.sb_vocab_size = h->sb_vocab_size; d.sb_log_window = std::log((float)h->sb_window_size);      // (SkipBigramModel.hpp:104)
 		}
 		d.n_chr_runs = h->n_chr_runs; d.n_morphs = h->n_morphs; d.n_forms = h->n_forms; d.n_trie_nodes = h->n_trie_nodes;
 		d.default_tag_size = h->default_tag_size; d.lang_vocab_size = h->lang_vocab_size;

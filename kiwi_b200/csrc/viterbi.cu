@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include "kb_model.h"
+#include "sbg_math.h"
 #include "kb_batch.h"
 #include "std_sort_emu.h"
 #include "unordered_emu.h"
@@ -39,10 +40,25 @@
 //   * progressMatrix (src/CoNgramModel.cpp:1494-1611): the (unique context x candidate) int8 products of a node are
 //     computed as warp-level tensor-core tiles (mma.sync m16n8k32 u8 x s8 -> s32) into shared memory, `congGroupDots`.
 // A CoNg path keeps CoNgramState::contextIdx in the DPath::wid_feat slot (the feature word is re-read from morphs[wid]).
+// KB_SBG=1 -> viterbi_sbg_kernel for SkipBigram images (Knlm + an 8-token history per path, src/SkipBigramModel.hpp:113-185).  Its states
+// rarely merge, which puts the path containers of the reference into the regime where BucketedHashContainer::insertOptimized behaves
+// unlike its comments (see sbgInsertRound); that is restated exactly, item by item, so the build takes the per-candidate path
+// `evalCand` for every candidate and leaves the item pipeline to the other two builds.
 #ifndef KB_CONG
 #define KB_CONG 0
 #endif
-#if KB_CONG
+#ifndef KB_SBG
+#define KB_SBG 0
+#endif
+#if KB_SBG
+#define KB_VIT_NS vit_sbg
+#define KB_VIT_KERNEL viterbi_sbg_kernel
+#define P_WID_FEAT(p) ((p).wid_feat)
+#define KB_NO_TMA 1
+#ifndef KB_TEAM
+#define KB_TEAM 1      // (team mode moves 48-byte records)
+#endif
+#elif KB_CONG
 #define KB_VIT_NS vit_cong
 #define KB_VIT_KERNEL viterbi_cong_kernel
 #define P_WID_FEAT(p) (c_m.morphs[(p).wid].feat)
@@ -59,6 +75,16 @@ namespace KB_VIT_NS
 {
 	// the model view lives in constant memory: every `c_m.field` is an immediate-offset constant-bank load
 	__constant__ DevModel c_m;
+
+	// a path record: DPath (kb_batch.h); the SkipBigram build appends the rest of the LM state - the ring of the last 8 valid tokens
+	// and its position - and the container hash the entry was appended with (VitView::path_stride tells emit.cu the record size)
+#if KB_SBG
+	struct alignas(16) PathS : DPath { uint32_t hist[8]; uint32_t hpos; uint32_t hpad; unsigned long long hcode; };
+	static_assert(sizeof(PathS) == 96, "SkipBigram path record");
+	using PathT = PathS;
+#else
+	using PathT = DPath;
+#endif
 
 	static constexpr unsigned FULL = 0xFFFFFFFFu;
 	static constexpr uint32_t NPOS = 0xFFFFFFFFu;
@@ -482,7 +508,7 @@ namespace KB_VIT_NS
 		uint32_t err = 0;
 		// sentence
 		const uint16_t* norm;
-		DPath* pool; uint32_t poolCap, top;
+		PathT* pool; uint32_t poolCap, top;
 		// chunk
 		const DNode* nodes; uint32_t N;
 		uint32_t* npOff; uint32_t* npCnt; uint8_t* reach;
@@ -608,6 +634,192 @@ namespace KB_VIT_NS
 			return h & (HT_SIZE - 1);
 		}
 
+#if KB_SBG
+		// ---- SkipBigram LM step: SbgState::nextImpl + SkipBigramModel::evaluate (src/SkipBigramModel.hpp:113-142, 169-182) ------------
+		__device__ __noinline__ float sbgEvaluate(const uint32_t* hist, uint32_t next, float base)
+		{
+			float arr[16];
+			#pragma unroll
+			for (int i = 0; i < 8; ++i) { arr[i] = base; arr[8 + i] = -CUDART_INF_F; }
+			const uint32_t b = c_m.sb_ptrs[next], e = c_m.sb_ptrs[next + 1];
+			#pragma unroll 1
+			for (int i = 0; i < 8; ++i)
+			{
+				const uint32_t hv = hist[i];
+				arr[i] = c_m.sb_discnts[hv] + base;
+				// nst::search over the target's key list = exact lookup; the image keeps the keys ascending
+				uint32_t lo = b, hi = e;
+				while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (c_m.sb_keys[mid] < hv) lo = mid + 1; else hi = mid; }
+				if (lo < e && c_m.sb_keys[lo] == hv) arr[8 + i] = c_m.sb_comps[lo];
+			}
+			return sbgLogSumExp16(arr) - c_m.sb_log_window;
+		}
+		__device__ __forceinline__ float sbgNext(int32_t& node, uint32_t* hist, uint32_t& hpos, uint32_t wid)
+		{
+			float ll = knProgress(node, wid, 6);
+			if (wid < c_m.sb_vocab_size && c_m.sb_valid[wid])
+			{
+#ifdef KB_HOSTSIM
+				const float ll0 = ll;
+#endif
+				if (ll > -13.f) ll = sbgEvaluate(hist, wid, ll);
+#ifdef KB_HOSTSIM
+				if (std::getenv("HS32_TRACE_SBG")) std::fprintf(stderr, "[hs32] sbg wid %u base %a -> %a hist %u %u %u %u %u %u %u %u pos %u\n", wid, ll0, ll, hist[0], hist[1], hist[2], hist[3], hist[4], hist[5], hist[6], hist[7], hpos);
+#endif
+				#pragma unroll
+				for (int i = 0; i < 8; ++i) if ((uint32_t)i == hpos) hist[i] = wid;      // (no dynamic register indexing)
+				hpos = (hpos + 1) & 7;
+			}
+			return ll;
+		}
+
+		// ---- the path container of one candidate, item by item (BestPathContainer.hpp) -------------------------------------------------
+		// The reference inserts a candidate's paths one after the other, and with SkipBigram states the outcome depends on that order in
+		// ways the parallel insert of the other builds does not model:
+		//  modes 0 / 1 (BucketedHashContainer::insertOptimized<avx2>, 316-383, with nst::findAll<avx2>, search.cpp:948-968), as the code
+		//  BEHAVES on x86-64:
+		//   - a bucket with fewer than 64 entries is searched properly (hash byte, then equalTo);
+		//   - from 64 entries on, the candidate mask of the first 64 is ANDed with ((size_t)1 << 64) - 1, which the hardware evaluates as 0:
+		//     none of them is ever found again;
+		//   - the candidates among entries 64.. are tested with value[i] where value[64 + i] is meant: when entry i IS the new state,
+		//     entry 64 + i (some other state with the same hash byte, or an earlier duplicate) is compared by score and overwritten;
+		//   - 32 < size < 64: a match at byte 31 sign-extends the low mask, every position 32 .. size-1 becomes a candidate;
+		//   - nothing found: the state is appended (again) while the bucket has room (128), else dropped.
+		//  mode 2 (`top1`, an unordered_set, 229-276): plain set semantics, the better score replaces the entry.
+		// Shared memory (the hash index `ht` of the other builds, unused here): modes 0 / 1 keep per bucket the entry index of every position
+		// (bIdx) and the hash byte it was appended with (hb); mode 2 keeps an open-addressing index over the first HT_MAX_ENTRIES entries and
+		// scans the rest.
+		__device__ __noinline__ void sbgInsertRound(unsigned vmask, const PathT& np, uint32_t candBeg, uint32_t& E, uint32_t* bucketCnt, uint32_t mode)
+		{
+			uint16_t* bIdx = sm->ht;                                             // [4][128]
+			uint8_t* hb = reinterpret_cast<uint8_t*>(sm->ht + 512);              // [4][128]
+			static_assert(HT_SIZE >= 768, "bucket index fits the hash-index array");
+			htUsed = 1;      // (the next htClear must really clear: the array holds bucket positions or index slots from here on)
+			#pragma unroll 1
+			while (vmask)
+			{
+				const int L = __ffs(vmask) - 1; vmask &= vmask - 1;
+				const int32_t lm = __shfl_sync(FULL, np.lm_state, L);
+				const uint32_t idw = __shfl_sync(FULL, (uint32_t)np.prev_root_id | ((uint32_t)np.sp_state << 8) | (np.hpos << 16), L);
+				uint32_t hh[8];
+				#pragma unroll
+				for (int i = 0; i < 8; ++i) hh[i] = __shfl_sync(FULL, np.hist[i], L);
+				const unsigned long long h = __shfl_sync(FULL, np.hcode, L);
+				const float sc = __shfl_sync(FULL, np.acc_score, L);
+				auto eq = [&](const PathT* t)
+				{
+					if (t->lm_state != lm || ((uint32_t)t->prev_root_id | ((uint32_t)t->sp_state << 8) | (t->hpos << 16)) != idw) return false;
+					bool same = true;
+					#pragma unroll
+					for (int i = 0; i < 8; ++i) same = same && t->hist[i] == hh[i];
+					return same;
+				};
+				uint32_t target = NPOS; bool append = false;
+				uint32_t b = 0, n = 0;
+				if (mode == 2)
+				{
+					uint32_t slot = ((uint32_t)(h ^ (h >> 29)) * 0x9E3779B1u) >> 7 & (HT_SIZE - 1);
+					const uint32_t slot0 = slot;
+					#pragma unroll 1
+					while (true)
+					{
+						const uint32_t e = sm->ht[slot];
+						if (!e) break;
+						const PathT* t = pool + candBeg + (e - 1);
+						if (t->hcode == h && eq(t)) { target = e - 1; break; }
+						slot = (slot + 1) & (HT_SIZE - 1);
+					}
+					if (target == NPOS && E > HT_MAX_ENTRIES)
+					{
+						#pragma unroll 1
+						for (uint32_t base = HT_MAX_ENTRIES; base < E && target == NPOS; base += 32)
+						{
+							const uint32_t e = base + lane;
+							bool hit = false;
+							if (e < E) { const PathT* t = pool + candBeg + e; hit = t->hcode == h && eq(t); }
+							const unsigned m = __ballot_sync(FULL, hit);
+							if (m) target = base + __ffs(m) - 1;
+						}
+					}
+					append = target == NPOS;
+					if (append && E < HT_MAX_ENTRIES)
+					{
+						// (all lanes walk the same probe sequence; lane 0 stores)
+						uint32_t s2 = slot0;
+						while (sm->ht[s2]) s2 = (s2 + 1) & (HT_SIZE - 1);
+						if (lane == 0) sm->ht[s2] = (uint16_t)(E + 1);
+					}
+				}
+				else
+				{
+					b = mode == 1 ? ((uint32_t)(h >> 8) & 3u) : 0u; n = bucketCnt[b];
+					const uint8_t hbNew = (uint8_t)h;
+					const uint16_t* bi = bIdx + b * 128; const uint8_t* hv = hb + b * 128;
+					uint32_t pos = NPOS;
+					if (n < 64)
+					{
+						bool c0 = false;
+						if (lane < n && hv[lane] == hbNew) c0 = eq(pool + candBeg + bi[lane]);
+						const unsigned m0 = __ballot_sync(FULL, c0);
+						if (m0) pos = __ffs(m0) - 1;
+						else if (n > 32)
+						{
+							const uint32_t i = 32 + lane;
+							bool c1 = false;
+							if (i < n && (hv[i] == hbNew || hv[31] == hbNew)) c1 = eq(pool + candBeg + bi[i]);
+							const unsigned m1 = __ballot_sync(FULL, c1);
+							if (m1) pos = 32 + __ffs(m1) - 1;
+						}
+					}
+					else
+					{
+						const uint32_t m = n - 64;
+						if (m > 0 && m < 64)
+						{
+							bool c0 = false;
+							if (lane < m && hv[64 + lane] == hbNew) c0 = eq(pool + candBeg + bi[lane]);      // value[i], as the reference reads it
+							const unsigned m0 = __ballot_sync(FULL, c0);
+							if (m0) pos = 64 + __ffs(m0) - 1;
+							else if (m > 32)
+							{
+								const uint32_t i = 32 + lane;
+								bool c1 = false;
+								if (i < m && (hv[64 + i] == hbNew || hv[64 + 31] == hbNew)) c1 = eq(pool + candBeg + bi[i]);
+								const unsigned m1 = __ballot_sync(FULL, c1);
+								if (m1) pos = 64 + 32 + __ffs(m1) - 1;
+							}
+						}
+					}
+					if (pos != NPOS) target = bi[pos];
+					append = target == NPOS && n < 128;
+				}
+				if (target != NPOS)
+				{
+					const PathT* t = pool + candBeg + target;
+					if (sc > t->acc_score && lane == (uint32_t)L)
+					{
+						PathT w = np;
+						if (mode != 2) { w.prev_root_id = t->prev_root_id; w.hcode = t->hcode; }      // neither prevRootId nor the stored hash byte is refreshed (370-381)
+						pool[candBeg + target] = w;
+					}
+				}
+				else if (append)
+				{
+					if (candBeg + E + 1 > poolCap) { err = ST_PATH_OVERFLOW; return; }
+					if (E >= 0xFFFEu && mode != 2) { err = ST_PATH_OVERFLOW; return; }
+					if (lane == (uint32_t)L) pool[candBeg + E] = np;
+					if (mode != 2)
+					{
+						if (lane == 0) { bIdx[b * 128 + n] = (uint16_t)E; hb[b * 128 + n] = (uint8_t)h; }
+						bucketCnt[b] = n + 1;
+					}
+					++E;
+				}
+				__syncwarp();
+			}
+		}
+#endif
+
 		// ---- evalSingleMorpheme, PathEvaluator.hpp:514-634 -------------------------------------------
 		struct CandCtx
 		{
@@ -634,17 +846,20 @@ namespace KB_VIT_NS
 			const uint32_t Bafter = unorderedBucketsAfter(bucketsBefore, E);
 			if (!Bafter) { err = ST_INTERNAL; return bucketsBefore; }
 			if (E == 1) return Bafter;
-			const size_t need = (size_t)E * sizeof(DPath) + (size_t)E * 16 + (size_t)Bafter * 4;
-			if ((size_t)scratch * sizeof(DPath) + need > (size_t)poolCap * sizeof(DPath)) { err = ST_PATH_OVERFLOW; return bucketsBefore; }
-			DPath* tmp = pool + scratch;
+			const size_t need = (size_t)E * sizeof(PathT) + (size_t)E * 16 + (size_t)Bafter * 4;
+			if ((size_t)scratch * sizeof(PathT) + need > (size_t)poolCap * sizeof(PathT)) { err = ST_PATH_OVERFLOW; return bucketsBefore; }
+			PathT* tmp = pool + scratch;
 			unsigned long long* codes = reinterpret_cast<unsigned long long*>(pool + scratch + (size_t)E);
 			int32_t* next = reinterpret_cast<int32_t*>(codes + E); int32_t* order = next + E; int32_t* buckets = order + E;
 			#pragma unroll 1
 			for (uint32_t e = lane; e < E; e += 32)
 			{
-				const DPath p = pool[candBeg + e];
+				const PathT p = pool[candBeg + e];
 				tmp[e] = p;
 				// Hash<WordLL> (BestPathContainer.hpp:79-84) over Hash<LmState>: std::hash<int32_t> for Knlm (Knlm.hpp:1170-1178), Hash<uint32_t>(node) for CoNg
+#if KB_SBG
+				codes[e] = p.hcode;
+#else
 #if KB_CONG
 				const unsigned long long v = (uint32_t)p.lm_state;
 				unsigned long long h = (v * 2305843009213693951ull) ^ ((v << 33) | (v >> 31));
@@ -652,6 +867,7 @@ namespace KB_VIT_NS
 				unsigned long long h = (unsigned long long)(long long)p.lm_state;
 #endif
 				codes[e] = (unsigned long long)((uint32_t)p.prev_root_id | ((uint32_t)p.sp_state << 8)) ^ ((h << 3) | (h >> 61));
+#endif
 			}
 			__syncwarp();
 			uint32_t B = bucketsBefore;
@@ -681,7 +897,7 @@ namespace KB_VIT_NS
 				const uint32_t pr = lane / nRoot, rr = lane % nRoot;
 				const uint32_t q = qb + pr;
 				bool valid = pr < pairsPerRound && q < P;
-				DPath pp;
+				PathT pp;
 				if (valid) pp = pool[inBeg + q];
 				float candScore = 0, firstChunkScore = 0;
 				bool setsFW = false; uint32_t fwVal = 0;
@@ -794,6 +1010,13 @@ namespace KB_VIT_NS
 					}
 				}
 #else
+#if KB_SBG
+				uint32_t hist[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }, hpos = 0;
+				if (valid) { for (int i = 0; i < 8; ++i) hist[i] = pp.hist[i]; hpos = pp.hpos; }
+#define KB_LM_STEP(w, site) sbgNext(lmState, hist, hpos, (w))
+#else
+#define KB_LM_STEP(w, site) knProgress(lmState, (w), (site))
+#endif
 				if (valid)
 				{
 					lmState = pp.lm_state;
@@ -803,7 +1026,7 @@ namespace KB_VIT_NS
 						if ((c_m.morphs[firstWid].feat & MF_TAG_MASK) == T_p) valid = false;
 						else
 						{
-							float ll = knProgress(lmState, firstWid, 3);
+							float ll = KB_LM_STEP(firstWid, 3);
 							candScore += ll;
 							firstChunkScore += ll;
 							if (!cc.single)
@@ -812,7 +1035,7 @@ namespace KB_VIT_NS
 								{
 									const uint32_t wid = c_m.morphs[c_m.chunks[cc.cur.chunk_off + i].morph].lm_id;
 									if ((c_m.morphs[wid].feat & MF_TAG_MASK) == T_p) { valid = false; break; }
-									ll = knProgress(lmState, wid, 4);
+									ll = KB_LM_STEP(wid, 4);
 									candScore += ll;
 								}
 							}
@@ -864,6 +1087,32 @@ namespace KB_VIT_NS
 				const uint32_t prevRoot = pp.root_id;
 				const unsigned vmask = __ballot_sync(FULL, valid);
 				if (!vmask) continue;
+#if KB_SBG
+				{
+					// every valid lane prepares its path record; the container takes them one at a time, in pair order (sbgInsertRound)
+					PathT np;
+					if (valid)
+					{
+						np.lm_state = lmState; np.acc_score = accScore; np.first_chunk_score = fcs; np.wid = cc.lastSeqId;
+						np.morpheme = cc.curId; np.parent = inBeg + q; np.own_off = cc.single ? cc.ownOff : 0; np.acc_typo_cost = pp.acc_typo_cost + node.typo_cost;
+						np.own_len = cc.single ? (uint16_t)cc.ownLen : 0; np.node = (uint16_t)nodeIdx;
+						np.sp_state = spState;
+						np.root_id = rootId != COMMON_ROOT ? rootId : pp.root_id;
+						np.fw = cc.fwNew | (np.root_id == COMMON_ROOT ? (uint32_t)FW_COMMON_ROOT : 0u);
+						np.prev_root_id = (uint8_t)prevRoot; np.morph_tag = cc.morphTag;
+						np.wid_feat = cc.widFeat;
+						for (int i = 0; i < 8; ++i) np.hist[i] = hist[i];
+						np.hpos = hpos; np.hpad = 0;
+						// Hash<WordLL<SbgState>>: Knlm node, the 8 ring slots, then prevRootId | spState << 8 (SkipBigramModel.hpp:188-203, BestPathContainer.hpp:79-84)
+						unsigned long long h = (unsigned long long)(long long)lmState;
+						for (int i = 0; i < 8; ++i) h = (unsigned long long)hist[i] ^ ((h << 3) | (h >> 61));
+						np.hcode = (unsigned long long)((prevRoot & 0xFFu) | ((uint32_t)spState << 8)) ^ ((h << 3) | (h >> 61));
+					}
+					sbgInsertRound(vmask, np, candBeg, E, bucketCnt, mode);
+					if (err) return;
+					continue;
+				}
+#endif
 				const unsigned long long key = valid
 					? ((unsigned long long)(uint32_t)lmState | ((unsigned long long)prevRoot << 32) | ((unsigned long long)spState << 40))
 					: (0xFFFF000000000000ull | lane);
@@ -891,7 +1140,7 @@ namespace KB_VIT_NS
 					{
 						const uint32_t e = ht[slot];
 						if (!e) break;
-						const DPath* t = pool + candBeg + (e - 1);
+						const PathT* t = pool + candBeg + (e - 1);
 						if (t->lm_state == lmState && t->prev_root_id == prevRoot && t->sp_state == spState) { found = e - 1; break; }
 						slot = (slot + 1) & (HT_SIZE - 1);
 					}
@@ -964,7 +1213,7 @@ namespace KB_VIT_NS
 						if (write && tgtOld != NPOS) write = accScore > pool[candBeg + tgt].acc_score;
 						if (write)
 						{
-							DPath np;
+							PathT np;
 							np.lm_state = lmState; np.acc_score = accScore; np.first_chunk_score = fcs; np.wid = cc.lastSeqId;
 							np.morpheme = cc.curId; np.parent = inBeg + q; np.own_off = cc.single ? cc.ownOff : 0; np.acc_typo_cost = pp.acc_typo_cost + node.typo_cost;
 							np.own_len = cc.single ? (uint16_t)cc.ownLen : 0; np.node = (uint16_t)nodeIdx;
@@ -992,8 +1241,10 @@ namespace KB_VIT_NS
 				for (uint32_t eb = 0; eb < E; eb += 32)
 				{
 					const uint32_t e = eb + lane;
-					DPath p; uint32_t b = 0xFF;
-#if KB_CONG
+					PathT p; uint32_t b = 0xFF;
+#if KB_SBG
+					if (e < E) { p = pool[candBeg + e]; b = (uint32_t)(p.hcode >> 8) & 3; }
+#elif KB_CONG
 					if (e < E) { p = pool[candBeg + e]; b = (p.sp_state ^ ((0u - (uint32_t)p.lm_state) >> 5)) & 3; }
 #else
 					if (e < E) { p = pool[candBeg + e]; b = (p.sp_state ^ ((uint32_t)p.lm_state >> 5)) & 3; }
@@ -1010,6 +1261,9 @@ namespace KB_VIT_NS
 				for (uint32_t e = lane; e < E; e += 32) pool[candBeg + e] = pool[candBeg + E + e];
 				__syncwarp();
 			}
+#ifdef KB_HOSTSIM
+			if (lane == 0 && std::getenv("HS32_TRACE_CAND")) std::fprintf(stderr, "[cand] node %u cand %d mode %u E %u buckets %u %u %u %u\n", nodeIdx, cc.curId, mode, E, bucketCnt[0], bucketCnt[1], bucketCnt[2], bucketCnt[3]);
+#endif
 			top = candBeg + E;      // (mode 2: the container's write-out order is applied per candidate segment by fixupGroup)
 		}
 
@@ -1151,7 +1405,7 @@ namespace KB_VIT_NS
 #endif
 				if (valid)
 				{
-					const DPath* pp = pool + fc.inBeg + q;
+					const PathT* pp = pool + fc.inBeg + q;
 					const uint4 s0 = *reinterpret_cast<const uint4*>(&pp->lm_state);      // lm_state, acc_score, acc_typo_cost, wid_feat
 					const uint32_t meta = *reinterpret_cast<const uint32_t*>(&pp->sp_state);   // sp_state | root_id << 8 | prev_root_id << 16 | morph_tag << 24
 					prevRoot = (meta >> 8) & 0xFF;
@@ -1265,7 +1519,7 @@ namespace KB_VIT_NS
 					{
 						const uint32_t e = ht[hs];
 						if (!e) break;
-						const DPath* tp = pool + htBase + (e - 1);
+						const PathT* tp = pool + htBase + (e - 1);
 						if (tp->lm_state == lmState && tp->morpheme == csCurId && tp->prev_root_id == prevRoot && tp->sp_state == spState) { found = e - 1; break; }
 						hs = (hs + 1) & (HT_SIZE - 1);
 					}
@@ -1296,7 +1550,7 @@ namespace KB_VIT_NS
 					{
 						const bool own = (cd.flags & CS_SINGLE) && fc.ownLen;
 						const uint8_t tag = (uint8_t)(csFeat & MF_TAG_MASK);
-						DPath np;
+						PathT np;
 						np.lm_state = lmState; np.acc_score = accScore; np.acc_typo_cost = typoAcc + fc.nodeTypoCost;
 #if KB_CONG
 						P_CTX(np) = ctxIdx;
@@ -1367,7 +1621,7 @@ namespace KB_VIT_NS
 						#pragma unroll 1
 						for (uint32_t e = 0; e < cnt; e += 32)
 						{
-							DPath p; const bool ok = e + lane < cnt;
+							PathT p; const bool ok = e + lane < cnt;
 							if (ok) p = pool[r + e + lane];
 							__syncwarp();
 							if (ok) pool[w + e + lane] = p;
@@ -1390,7 +1644,7 @@ namespace KB_VIT_NS
 					#pragma unroll 1
 					for (uint32_t e = 0; e < cnt; e += 32)
 					{
-						DPath p; bool ok = e + lane < cnt;
+						PathT p; bool ok = e + lane < cnt;
 #if KB_CONG
 						if (ok) { p = pool[tmp + e + lane]; if (mode == 1) ok = ((p.sp_state ^ ((0u - (uint32_t)p.lm_state) >> 5)) & 3) == b; }
 #else
@@ -1433,7 +1687,7 @@ namespace KB_VIT_NS
 			{
 				const uint32_t q = qb + lane;
 				bool reg = false; uint32_t ctx = 0;
-				if (q < P) { const DPath* pth = pool + inBeg + q; reg = (pth->fw >> FW_SOCKET_SHIFT) == 0; ctx = P_CTX(*pth); }
+				if (q < P) { const PathT* pth = pool + inBeg + q; reg = (pth->fw >> FW_SOCKET_SHIFT) == 0; ctx = P_CTX(*pth); }
 				unsigned rem = __ballot_sync(FULL, reg);
 				Preg += __popc(rem);
 				uint32_t mySlot = 0xFFu;
@@ -1555,7 +1809,7 @@ namespace KB_VIT_NS
 				for (uint32_t qb = 0; qb < P; qb += 32)
 				{
 					const uint32_t q = qb + lane;
-					DPath p; bool ok = false;
+					PathT p; bool ok = false;
 					if (q < P)
 					{
 						p = pool[inBeg + q];
@@ -1566,7 +1820,7 @@ namespace KB_VIT_NS
 					if (top + __popc(om) > poolCap) { err = ST_PATH_OVERFLOW; return; }
 					if (ok)
 					{
-						DPath np = p;
+						PathT np = p;
 						np.acc_score += add;
 						np.acc_typo_cost -= cur.user_score;
 						np.parent = inBeg + q;
@@ -1647,7 +1901,7 @@ namespace KB_VIT_NS
 			if (err) return;
 			const uint32_t nCands = cgn.nOrdered;
 #else
-			const bool itemOK = P <= STAGE_CAP;          // modes 0 / 1 always; mode 2 (`top1`, an unordered_set in the reference) up to the staging capacity
+			const bool itemOK = !KB_SBG && P <= STAGE_CAP;          // modes 0 / 1 always; mode 2 (`top1`, an unordered_set in the reference) up to the staging capacity
 			const uint32_t nCands = nCandsIn;
 #endif
 			FlushCtx fc;
@@ -1975,6 +2229,7 @@ namespace KB_VIT_NS
 								const uint4* sp = reinterpret_cast<const uint4*>(pool + src + e); uint4* dp = reinterpret_cast<uint4*>(pool + dst + e);
 								const uint4 a = sp[0], b = sp[1], cc = sp[2];
 								dp[0] = a; dp[1] = b; dp[2] = cc;
+								static_assert(!KB_SBG || TEAM == 1, "team mode moves 48-byte records");
 							}
 							src += c;
 						}
@@ -2004,7 +2259,7 @@ namespace KB_VIT_NS
 				uint32_t o = 0, slot = 3;
 				if (e < cntAll)
 				{
-					const DPath* p = pool + nodeBeg + e;
+					const PathT* p = pool + nodeBeg + e;
 					const uint32_t meta = *reinterpret_cast<const uint32_t*>(&p->sp_state);
 					const uint32_t root = (meta >> 8) & 0xFF;
 					slot = root == COMMON_ROOT ? 0 : root + 1;
@@ -2026,7 +2281,7 @@ namespace KB_VIT_NS
 				bool keep = false;
 				if (e < cntAll)
 				{
-					const DPath* p = pool + nodeBeg + e;
+					const PathT* p = pool + nodeBeg + e;
 					const uint32_t root = p->root_id;
 					const float mxs = root == COMMON_ROOT ? mx0 : (root == 0 ? mx1 : mx2);
 					keep = !(p->acc_score + c_m.cfg.cut_off_threshold < mxs);
@@ -2037,10 +2292,11 @@ namespace KB_VIT_NS
 				if (valid != eb || km != (remE >= 32 ? FULL : ((1u << remE) - 1)))
 				{
 					// something was dropped at or before this round: move the survivors down (read all, then write)
-					uint4 a, b, c;
-					if (keep) { const uint4* sp = reinterpret_cast<const uint4*>(pool + nodeBeg + e); a = sp[0]; b = sp[1]; c = sp[2]; }
+					constexpr uint32_t SEGS = sizeof(PathT) / 16;      // 3 (DPath), 6 with the SkipBigram history
+					uint4 seg[SEGS];
+					if (keep) { const uint4* sp = reinterpret_cast<const uint4*>(pool + nodeBeg + e); for (uint32_t z = 0; z < SEGS; ++z) seg[z] = sp[z]; }
 					__syncwarp();
-					if (keep && dst != e) { uint4* dp = reinterpret_cast<uint4*>(pool + nodeBeg + dst); dp[0] = a; dp[1] = b; dp[2] = c; }
+					if (keep && dst != e) { uint4* dp = reinterpret_cast<uint4*>(pool + nodeBeg + dst); for (uint32_t z = 0; z < SEGS; ++z) dp[z] = seg[z]; }
 					__syncwarp();
 				}
 				valid += __popc(km);
@@ -2106,11 +2362,15 @@ namespace KB_VIT_NS
 			if (top + 1 > poolCap) { err = ST_PATH_OVERFLOW; return 0; }
 			if (lane == 0 && leader())
 			{
-				DPath b;
+				PathT b;
 #if KB_CONG
 				b.lm_state = 0;            // CoNgramState(const ILangModel*): node 0, contextIdx 0 (CoNgramModel.hpp:479-485)
 #else
 				b.lm_state = c_m.kn_bos_node;
+#if KB_SBG
+				for (int i = 0; i < 8; ++i) b.hist[i] = 0;      // SbgState(const ILangModel*): empty ring (SkipBigramModel.hpp:144-154)
+				b.hpos = 0; b.hpad = 0; b.hcode = 0;
+#endif
 #endif
 				b.acc_score = 0; b.first_chunk_score = 0; b.wid = 0; b.morpheme = 0; b.parent = NPOS; b.own_off = 0; b.acc_typo_cost = 0;
 				b.own_len = 0; b.node = 0; b.sp_state = 0; b.root_id = COMMON_ROOT; b.prev_root_id = 0;
@@ -2215,7 +2475,7 @@ namespace KB_VIT_NS
 			for (uint32_t qb = 0; qb < P; qb += 32)
 			{
 				const uint32_t q = qb + lane;
-				DPath p; bool ok = false; float c = 0;
+				PathT p; bool ok = false; float c = 0;
 				if (q < P)
 				{
 					p = pool[inBeg + q];
@@ -2236,6 +2496,10 @@ namespace KB_VIT_NS
 #if KB_CONG
 							uint32_t sctx = P_CTX(p);
 							c += cgNext(st, sctx, 1);
+#elif KB_SBG
+							uint32_t eh[8]; for (int i = 0; i < 8; ++i) eh[i] = p.hist[i];
+							uint32_t ep = p.hpos;
+							c += sbgNext(st, eh, ep, 1);
 #else
 							c += knProgress(st, 1, 5);
 #endif
@@ -2248,20 +2512,20 @@ namespace KB_VIT_NS
 				const uint32_t before = __popc(om & ((1u << lane) - 1));
 				if (ok)
 				{
-					// cand record reuses DPath: acc_score = c, parent, root_id, sp_state
+					// cand record reuses PathT: acc_score = c, parent, root_id, sp_state
 					if (p.root_id == COMMON_ROOT)
 					{
 						for (uint32_t r = 0; r < nUniq; ++r)
 						{
-							DPath cnd = p; cnd.acc_score = c; cnd.parent = inBeg + q; cnd.root_id = (uint8_t)r; cnd.sp_state = uniq[r]; cnd.wid = 1;
+							PathT cnd = p; cnd.acc_score = c; cnd.parent = inBeg + q; cnd.root_id = (uint8_t)r; cnd.sp_state = uniq[r]; cnd.wid = 1;
 							pool[candBeg + (nCand + before) * perPath + r] = cnd;
 						}
 					}
 					else
 					{
-						DPath cnd = p; cnd.acc_score = c; cnd.parent = inBeg + q; cnd.wid = 1;
+						PathT cnd = p; cnd.acc_score = c; cnd.parent = inBeg + q; cnd.wid = 1;
 						pool[candBeg + (nCand + before) * perPath] = cnd;
-						for (uint32_t r = 1; r < nUniq; ++r) { DPath z = cnd; z.wid = 0; pool[candBeg + (nCand + before) * perPath + r] = z; }
+						for (uint32_t r = 1; r < nUniq; ++r) { PathT z = cnd; z.wid = 0; pool[candBeg + (nCand + before) * perPath + r] = z; }
 					}
 				}
 				nCand += __popc(om);
@@ -2278,7 +2542,7 @@ namespace KB_VIT_NS
 				bool real = false; unsigned long long key = 0;
 				if (e < nRec)
 				{
-					const DPath* r = pool + candBeg + e;
+					const PathT* r = pool + candBeg + e;
 					real = r->wid != 0;
 					uint32_t o = __float_as_uint(r->acc_score);
 					o = (o & 0x80000000u) ? ~o : (o | 0x80000000u);
@@ -2286,14 +2550,14 @@ namespace KB_VIT_NS
 				}
 				const unsigned rm = __ballot_sync(FULL, real);
 				const uint32_t k = nReal + __popc(rm & ((1u << lane) - 1));
-				if ((size_t)(candBeg + nRec) * sizeof(DPath) + (size_t)(nReal + __popc(rm)) * sizeof(SortRec) > (size_t)poolCap * sizeof(DPath)) { err = ST_PATH_OVERFLOW; return 0; }
+				if ((size_t)(candBeg + nRec) * sizeof(PathT) + (size_t)(nReal + __popc(rm)) * sizeof(SortRec) > (size_t)poolCap * sizeof(PathT)) { err = ST_PATH_OVERFLOW; return 0; }
 				if (real) { SortRec x; x.key = key; x.idx = e; x.pad = 0; sr[k] = x; }
 				nReal += __popc(rm);
 			}
 			if (nReal == 0) return 0;
 			__syncwarp();
 #ifdef KB_HOSTSIM
-			if (lane == 0 && std::getenv("HS32_TRACE_END")) { std::fprintf(stderr, "[hs32] end cands %u:", nReal); for (uint32_t z = 0; z < nReal; ++z) { const DPath* r = pool + candBeg + sr[z].idx; std::fprintf(stderr, " (%d,%d,%a,n%d,p%u)", r->root_id, r->sp_state, r->acc_score, pool[r->parent].node, r->parent); } std::fprintf(stderr, "\n"); }
+			if (lane == 0 && std::getenv("HS32_TRACE_END")) { std::fprintf(stderr, "[hs32] end cands %u:", nReal); for (uint32_t z = 0; z < nReal; ++z) { const PathT* r = pool + candBeg + sr[z].idx; std::fprintf(stderr, " (%d,%d,%a,n%d,p%u)", r->root_id, r->sp_state, r->acc_score, pool[r->parent].node, r->parent); } std::fprintf(stderr, "\n"); }
 #endif
 			if (lane == 0) stdSortEmu(sr, (long)nReal);
 			__syncwarp();
@@ -2322,7 +2586,7 @@ namespace KB_VIT_NS
 				{
 					const uint32_t src = __ffs(tm) - 1; tm &= tm - 1;
 					if (nRes >= MAX_RESULTS) { err = ST_INTERNAL; return 0; }
-					const DPath* r = pool + candBeg + sr[eb + src].idx;
+					const PathT* r = pool + candBeg + sr[eb + src].idx;
 					res[nRes].score = r->acc_score; res[nRes].endParent = r->parent;
 					res[nRes].prevState = uniq[r->root_id]; res[nRes].curState = r->sp_state;
 					++nRes;
@@ -2415,7 +2679,7 @@ namespace KB_VIT_NS
 
 		Vit v{ bv, vv, lane };
 		v.norm = bv.norm + wbase;
-		v.pool = vv.paths + pbase;
+		v.pool = reinterpret_cast<PathT*>(vv.paths) + pbase;      // (records of VitView::path_stride bytes)
 		v.poolCap = vv.paths_per_unit * W + vv.paths_const;
 		v.top = 0;
 		v.sm = &smAll[wib]; v.ht = smAll[wib].ht; v.htUsed = 1;
@@ -2599,7 +2863,10 @@ namespace KB_VIT_NS
 	}
 #endif
 
-#if KB_CONG
+#if KB_SBG
+#define KB_SET_MODEL set_model_viterbi_sbg
+#define KB_LAUNCH launch_viterbi_sbg
+#elif KB_CONG
 #define KB_SET_MODEL set_model_viterbi_cong
 #define KB_LAUNCH launch_viterbi_cong
 #else
@@ -2611,6 +2878,7 @@ namespace KB_VIT_NS
 	cudaError_t KB_LAUNCH(const DevModel&, const BatchView& bv, const VitView& vv, cudaStream_t stream)
 	{
 		if (bv.n_sent == 0) return cudaSuccess;
+		if (vv.path_stride != sizeof(PathT)) return (cudaError_t)1;      // the arena was sized for another record type
 		const uint32_t nTeam = TEAM > 1 ? (vv.n_team < bv.n_sent ? vv.n_team : bv.n_sent) : 0u;
 		const uint32_t blocks = (nTeam + TEAMS_PER_BLOCK - 1) / TEAMS_PER_BLOCK + (bv.n_sent - nTeam + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
 		static bool attrSetOn[64] = {};      // function attributes are per device (the caller holds that device's lock)

@@ -94,7 +94,9 @@ namespace orc
 			float ll = lm.progress(node, wid);
 			if (isValidVocab(wid))
 			{
+				const float ll0 = ll;
 				if (ll > -13) ll = evaluate(st.hist, wid, ll);
+				if (std::getenv("ORC_TRACE_SBG")) std::fprintf(stderr, "[orc] sbg wid %u base %a -> %a hist %u %u %u %u %u %u %u %u pos %u\n", wid, ll0, ll, st.hist[0], st.hist[1], st.hist[2], st.hist[3], st.hist[4], st.hist[5], st.hist[6], st.hist[7], (unsigned)st.pos);
 				st.hist[st.pos] = wid;
 				st.pos = (uint8_t)((st.pos + 1) % 8);
 			}

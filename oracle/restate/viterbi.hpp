@@ -442,6 +442,7 @@ namespace orc
 				np.wid = lastSeqId;
 				if (isSingle(cur)) { np.combineSocket = cur.combine_socket; np.ownFormId = (uint16_t)ownFormId; }
 			};
+			if (std::getenv("ORC_TRACE_CAND")) std::fprintf(stderr, "[cand] node %zu cand %d mode %d E %zu buckets %zu %zu %zu %zu\n", nodeIdx, curId, cont.mode, cont.mode == 2 ? cont.top1.size() : cont.buckets[0].size() + cont.buckets[1].size() + cont.buckets[2].size() + cont.buckets[3].size(), cont.buckets[0].size(), cont.buckets[1].size(), cont.buckets[2].size(), cont.buckets[3].size());
 			if (cont.mode == 2) { for (auto& p : cont.top1) emit(p); }      // libstdc++ iteration order, as in the reference
 			else for (auto& bk : cont.buckets) for (auto& p : bk) emit(p);
 		}
@@ -972,7 +973,10 @@ namespace orc
 				}
 				if (cnt) cnt->pathsOut += cache[i].size();
 				if (wc) wc->pathsKept += cache[i].size();
+				if (std::getenv("ORC_TRACE_NODES")) std::fprintf(stderr, " %zu", cache[i].size());
+				if (const char* dn = std::getenv("ORC_DUMP_NODE")) if ((size_t)std::atoi(dn) == i) for (auto& q : cache[i]) std::fprintf(stderr, "[path] morph %d lm %d acc %a root %u sp %u hist %u %u %u %u %u %u %u %u pos %u\n", q.morpheme, q.lmState, q.accScore, q.rootId, q.spState, q.sb.hist[0], q.sb.hist[1], q.sb.hist[2], q.sb.hist[3], q.sb.hist[4], q.sb.hist[5], q.sb.hist[6], q.sb.hist[7], (unsigned)q.sb.pos);
 			}
+			if (std::getenv("ORC_TRACE_NODES")) std::fprintf(stderr, " <- [orc] paths per node (1..)\n");
 
 			// end node
 			auto& cand = cache.back();

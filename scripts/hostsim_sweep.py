@@ -10,7 +10,7 @@ from concurrent.futures import ProcessPoolExecutor
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tests.goldenio import read_golden, read_inputs
-from tests.orc import IMAGE, TYPO_IMAGES, CONG_IMAGE
+from tests.orc import IMAGE, TYPO_IMAGES, CONG_IMAGE, SBG_IMAGE
 
 MATCH_ALL = (1 << 0) | (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4) | (1 << 5) | (1 << 23) | (1 << 16)
 
@@ -24,7 +24,7 @@ def _handle(mode):
     lib.hs32_open.restype = C.c_void_p; lib.hs32_open.argtypes = [C.c_char_p]
     lib.hs32_set_typo.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
     lib.hs32_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p]
-    h = lib.hs32_open(os.fsencode(CONG_IMAGE if mode == "cong" else IMAGE))
+    h = lib.hs32_open(os.fsencode(CONG_IMAGE if mode == "cong" else SBG_IMAGE if mode == "sbg" else IMAGE))
     assert h
     if mode == "typo": assert lib.hs32_set_typo(h, os.fsencode(TYPO_IMAGES["basic"]), 2.5) == 0
     _H[mode] = (lib, h)
@@ -70,7 +70,7 @@ def work(args):
         return len(idxs), bad
     cap = 8192
     morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
-    texts = read_inputs(name); gold = read_golden(("cong_" if cong else "") + ("typo6_" if typo else "") + name)
+    texts = read_inputs(name); gold = read_golden(("cong_" if cong else "") + ("sbg_" if mode == "sbg" else "") + ("typo6_" if typo else "") + name)
     bad = []
     for i in idxs:
         t, g = texts[i], gold[i]
@@ -86,7 +86,7 @@ def work(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", nargs="?", default="plain", choices=["plain", "typo", "cong"])
+    ap.add_argument("mode", nargs="?", default="plain", choices=["plain", "typo", "cong", "sbg"])
     ap.add_argument("--files", default="inputs_web,inputs_written,inputs_ref_tests,inputs_dialect_typos")
     ap.add_argument("--stride", type=int, default=1)
     ap.add_argument("--maxlen", type=int, default=400, help="skip longer inputs (the pathological reference tests take minutes)")
@@ -99,7 +99,8 @@ def main():
             for k in range(0, len(idx), per): tasks.append((a.mode, name, idx[k:k + per]))
             continue
         texts = read_inputs(name)
-        idx = [i for i in range(0, len(texts), a.stride) if len(texts[i]) <= a.maxlen]
+        nGold = len(read_golden("sbg_" + name)) if a.mode == "sbg" else len(texts)      # (the sbg vectors of inputs_ref_tests stop before the pathological inputs)
+        idx = [i for i in range(0, min(len(texts), nGold), a.stride) if len(texts[i]) <= a.maxlen]
         per = max(1, len(idx) // (a.jobs * 4))
         for k in range(0, len(idx), per): tasks.append((a.mode, name, idx[k:k + per]))
     t0 = time.time(); total = 0; bad = []

@@ -4,6 +4,9 @@
 // tests/test_hostsim_pipeline.py, which compares tokens and scores with the reference's golden vectors without a GPU.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -19,6 +22,8 @@ namespace kb
 	cudaError_t set_model_emit(const DevModel& m);
 	cudaError_t launch_viterbi_cong(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
 	cudaError_t set_model_viterbi_cong(const DevModel& m);
+	cudaError_t launch_viterbi_sbg(const DevModel& m, const BatchView& bv, const VitView& vv, cudaStream_t stream);
+	cudaError_t set_model_viterbi_sbg(const DevModel& m);
 }
 
 namespace
@@ -34,6 +39,8 @@ namespace
 	template<class T> std::vector<T> buf(size_t n) { return std::vector<T>(n); }
 }
 
+static void hs32SegvHandler(int sig) { void* bt[64]; const int n = backtrace(bt, 64); backtrace_symbols_fd(bt, n, 2); _exit(139); }
+
 extern "C" {
 
 void* hs32_open(const char* imagePath)
@@ -43,7 +50,7 @@ void* hs32_open(const char* imagePath)
 		auto blob = kb::readImageFile(imagePath);
 		auto* s = new Sim;
 		s->model.load(blob.data(), blob.size());
-		if (s->model.dev.model_type != 2 && s->model.dev.model_type != 4) { delete s; return nullptr; }      // Knlm and CoNg builds of viterbi.cu
+		if (s->model.dev.model_type != 2 && s->model.dev.model_type != 3 && s->model.dev.model_type != 4) { delete s; return nullptr; }      // Knlm, SkipBigram and CoNg builds of viterbi.cu
 		return s;
 	}
 	catch (...) { return nullptr; }
@@ -77,7 +84,9 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 		Sim& s = *reinterpret_cast<Sim*>(p);
 		using namespace kb;
 		const uint32_t off[2] = { 0, (uint32_t)len }, order[1] = { 0 };
-		const size_t U = 2 * (size_t)len + 4, npu = KB_DEFAULT_NODES_PER_UNIT, ppu = 128, pc = 8192;
+		// (SkipBigram paths rarely merge: the arena of the engine's first retry round, 8 x, from the start)
+		const size_t capMul = s.model.dev.model_type == 3 ? 8 : 1;
+		const size_t U = 2 * (size_t)len + 4, npu = KB_DEFAULT_NODES_PER_UNIT, ppu = 128 * capMul, pc = 8192 * capMul;
 		BatchView bv{}; VitView vv{};
 		bv.n_sent = 1; bv.text = text; bv.text_off = off; bv.match_options = matchOptions; bv.nodes_per_unit = (uint32_t)npu; bv.order = order;
 		auto norm = buf<uint16_t>(U + 32); auto normLen = buf<uint32_t>(1); auto posTable = buf<uint32_t>(len + 2);
@@ -88,13 +97,14 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 		bv.norm = norm.data(); bv.norm_len = normLen.data(); bv.pos_table = posTable.data(); bv.ns_to_pos = nsToPos.data(); bv.pos_to_ns = posToNs.data();
 		bv.end_pos_map = endPosMap.data(); bv.ctr = ctr.data(); bv.patterns = pats.data(); bv.build_nodes = build.data(); bv.nodes = nodes.data();
 		bv.new_index = newIndex.data(); bv.chunks = chunks.data(); bv.n_chunks = nChunks.data(); bv.status = status.data(); bv.debug = debug.data();
-		auto paths = buf<DPath>(ppu * U + pc); auto npOff = buf<uint32_t>(U * npu), npCnt = buf<uint32_t>(U * npu); auto nodeCand = buf<uint2>(U * npu); auto reach = buf<uint8_t>(U * npu);
+		const size_t pathStride = s.model.dev.model_type == 3 ? 96 : sizeof(DPath);      // (SkipBigram records carry the history, viterbi.cu PathS)
+		auto paths = buf<DPath>((ppu * U + pc) * pathStride / sizeof(DPath)); auto npOff = buf<uint32_t>(U * npu), npCnt = buf<uint32_t>(U * npu); auto nodeCand = buf<uint2>(U * npu); auto reach = buf<uint8_t>(U * npu);
 		auto recs = buf<DRec>(2 * chunkSlots); auto toks = buf<DToken>(U); auto nTok = buf<uint32_t>(2); auto bestRec = buf<int32_t>(1); auto sc = buf<float>(1);
 		auto timing = buf<unsigned long long>(2);
 		auto workCounter = buf<uint32_t>(4);
 		vv.work_counter = workCounter.data(); vv.solo_blocks = 0; vv.solo_warps = 1;
 		vv.n_team = std::getenv("HS32_TEAM") ? 1u : 0u;      // HS32_TEAM=1: the sentence is analysed by a team of warps (viterbi.cu team mode)
-		vv.paths_per_unit = (uint32_t)ppu; vv.paths_const = (uint32_t)pc; vv.paths = paths.data(); vv.node_path_off = npOff.data(); vv.node_path_cnt = npCnt.data(); vv.node_cand = nodeCand.data();
+		vv.paths_per_unit = (uint32_t)ppu; vv.paths_const = (uint32_t)pc; vv.path_stride = (uint32_t)pathStride; vv.paths = paths.data(); vv.node_path_off = npOff.data(); vv.node_path_cnt = npCnt.data(); vv.node_cand = nodeCand.data();
 		vv.reachable = reach.data(); vv.recs = recs.data(); vv.tokens = toks.data(); vv.n_tokens = nTok.data(); vv.best_rec = bestRec.data(); vv.score = sc.data(); vv.timing = timing.data();
 		std::vector<DTypoNode> tgTmp, tg; std::vector<uint32_t> tgRemap; std::vector<uint2> tgRange; std::vector<DTypoState> tgStates; std::vector<DTypoMatch> tgMatches;
 		if (!s.typo.empty())
@@ -117,15 +127,29 @@ int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, 
 		}
 		const bool cong = s.model.dev.model_type == 4;
 		set_model_lattice(s.model.dev); set_model_emit(s.model.dev);
-		if (cong) set_model_viterbi_cong(s.model.dev); else set_model_viterbi(s.model.dev);
+		const bool sbgModel = s.model.dev.model_type == 3;
+		if (cong) set_model_viterbi_cong(s.model.dev); else if (sbgModel) set_model_viterbi_sbg(s.model.dev); else set_model_viterbi(s.model.dev);
 		const bool trace = std::getenv("HS32_TRACE") != nullptr;
+		if (std::getenv("HS32_BT")) signal(SIGSEGV, hs32SegvHandler);      // debugging aid: symbolised backtrace of a faulting lane
 		if (trace) std::fprintf(stderr, "[hs32] lattice\n");
 		if (launch_lattice(s.model.dev, bv, nullptr)) return -100;
 		if (trace) std::fprintf(stderr, "[hs32] lattice done: status %u chunks %u\n", status[0], nChunks[0]);
 		if (status[0]) return -(int)status[0];
 		*nNodes = 0;
 		for (uint32_t c = 0; c < nChunks[0]; ++c) *nNodes += (int)chunks[c].n_nodes;
-		if (cong ? launch_viterbi_cong(s.model.dev, bv, vv, nullptr) : launch_viterbi(s.model.dev, bv, vv, nullptr)) return -100;
+		if (cong ? launch_viterbi_cong(s.model.dev, bv, vv, nullptr) : sbgModel ? launch_viterbi_sbg(s.model.dev, bv, vv, nullptr) : launch_viterbi(s.model.dev, bv, vv, nullptr)) return -100;
+		if (const char* dn = std::getenv("HS32_DUMP_NODE"))
+		{
+			const int i = std::atoi(dn);
+			for (uint32_t k = 0; k < npCnt[i]; ++k)
+			{
+				const char* rec = reinterpret_cast<const char*>(paths.data()) + (size_t)(npOff[i] + k) * pathStride;
+				const DPath& q = *reinterpret_cast<const DPath*>(rec);
+				std::fprintf(stderr, "[path] morph %d lm %d acc %a root %u sp %u", q.morpheme, q.lm_state, q.acc_score, q.root_id, q.sp_state);
+				if (pathStride == 96) { const uint32_t* hx = reinterpret_cast<const uint32_t*>(rec + 48); std::fprintf(stderr, " hist %u %u %u %u %u %u %u %u pos %u", hx[0], hx[1], hx[2], hx[3], hx[4], hx[5], hx[6], hx[7], hx[8]); }
+				std::fprintf(stderr, "\n");
+			}
+		}
 		if (trace) { std::fprintf(stderr, "[hs32] paths per node:"); for (int i = 0; i < *nNodes; ++i) std::fprintf(stderr, " %u", npCnt[i]); std::fprintf(stderr, "\n"); }
 		if (trace && bestRec[0] >= 0)
 		{

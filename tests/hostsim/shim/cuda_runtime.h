@@ -43,6 +43,9 @@ typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+enum { cudaHostAllocPortable = 1 };
+inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { *p = std::malloc(n ? n : 1); return *p ? 0 : 2; }
+inline cudaError_t cudaFreeHost(void* p) { std::free(p); return 0; }
 inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }

@@ -123,3 +123,16 @@ def test_hostsim_full_golden_sweep(mode):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), mode], capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "1273 sentences, 0 mismatches" in r.stdout, r.stdout
+
+
+def test_hostsim_sbg_golden_subset():
+    """The SkipBigram build of viterbi.cu (viterbi_sbg_kernel: Knlm + 8-token history, sbg_math.h, the item-by-item path container
+    sbgInsertRound) through the simulator on every twelfth sentence of inputs_written / inputs_web (the shorter ones): tokens identical and scores bit-exact
+    against the unmodified reference's ModelType::sbg vectors.  (The whole files - 33 + 158 sentences, 0 mismatches - take ten minutes:
+    `python scripts/hostsim_sweep.py sbg --files inputs_written,inputs_web`.)"""
+    import subprocess, sys
+    from tests.orc import SBG_IMAGE
+    if not os.path.exists(LIB) or not os.path.exists(SBG_IMAGE):
+        pytest.skip("tests/hostsim/libpipeline_sim32.so or the SkipBigram model image missing: run __graft_entry__.build()")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "sbg", "--files", "inputs_written,inputs_web", "--stride", "12", "--maxlen", "70"], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout and "sbg: 0 sentences" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
