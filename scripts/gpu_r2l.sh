@@ -6,7 +6,6 @@ mkdir -p gpurun_out; O=gpurun_out
 echo "pytest rc=$?" >> $O/r2l_pytest_sbg.log
 tail -n 15 $O/r2l_pytest_sbg.log
 ( timeout 600 python bench.py --config 6 --steps 3 --warmup 3 --cpu-sample 1024 ) > $O/r2l_bench_cfg6.json 2> $O/r2l_bench_cfg6.err
-( timeout 600 python bench.py --impl reference --config 6 --steps 3 --warmup 1 ) > $O/r2l_ref_cfg6.json 2> $O/r2l_ref_cfg6.err
 ( time timeout 1200 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --deselect tests/test_gpu_sbg.py ) > $O/r2l_pytest.log 2>&1
 echo "pytest rc=$?" >> $O/r2l_pytest.log
 tail -n 6 $O/r2l_pytest.log
