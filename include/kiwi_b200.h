@@ -206,6 +206,34 @@ kiwi_h kiwi_b200_init_multi(const void* bytes, uint64_t size, const int* devices
 int kiwi_b200_num_devices(kiwi_h handle);
 void kiwi_b200_free(void* p);
 
+/* ---- native model loading, first pieces -------------------------------------------------------------------------
+ * Read the reference's language-model FILES without the reference library and return the corresponding sections of the model image
+ * (kiwi_b200_image.h) - byte for byte what oracle/ref_build/tools/flatten_model.cpp dumps from the reference's in-memory model:
+ *   sj.knlm         KnLangModel constructor, /root/reference/src/Knlm.hpp:1003-1167 (header include/kiwi/Knlm.h:10-16)
+ *   skipbigram.mdl  SkipBigramModel constructor, src/SkipBigramModel.hpp:40-105 (header include/kiwi/SkipBigramModel.h:9-13)
+ * out: a malloc'ed blob that starts with the struct below; offsets are from the blob's start; release with kiwi_b200_free.
+ * Returns 0, or -1 with a message in kiwi_b200_native_error().  Host code only (no GPU needed). */
+typedef struct kiwi_b200_native_knlm_t {
+	uint32_t num_nodes, num_edges, htx_vocab, has_htx, order, vocab_size;   /* = kb2_header kn_* / lang_vocab_size */
+	int32_t  bos_node; float unk_ll;
+	uint64_t nodes_off, nodes_bytes;     /* KB2_SEC_KN_NODES  kb2_kn_node[num_nodes] */
+	uint64_t keys_off, keys_bytes;       /* KB2_SEC_KN_KEYS   uint32_t[num_edges]    */
+	uint64_t values_off, values_bytes;   /* KB2_SEC_KN_VALUES int32_t[num_edges]     */
+	uint64_t root_off, root_bytes;       /* KB2_SEC_KN_ROOT   int32_t[htx_vocab]     */
+	uint64_t htx_off, htx_bytes;         /* KB2_SEC_KN_HTX    uint32_t[vocab_size] or empty */
+} kiwi_b200_native_knlm_t;
+typedef struct kiwi_b200_native_sbg_t {
+	uint32_t vocab_size, window_size, num_pairs, pad;                       /* = kb2_header sb_* */
+	uint64_t ptrs_off, ptrs_bytes;       /* KB2_SEC_SB_PTRS    uint32_t[vocab_size + 1] */
+	uint64_t keys_off, keys_bytes;       /* KB2_SEC_SB_KEYS    uint32_t[num_pairs]      */
+	uint64_t comps_off, comps_bytes;     /* KB2_SEC_SB_COMPS   float[num_pairs]         */
+	uint64_t discnts_off, discnts_bytes; /* KB2_SEC_SB_DISCNTS float[vocab_size]        */
+	uint64_t valid_off, valid_bytes;     /* KB2_SEC_SB_VALID   uint8_t[vocab_size]      */
+} kiwi_b200_native_sbg_t;
+int kiwi_b200_native_knlm(const char* sj_knlm_path, void** out_bytes, uint64_t* out_size);
+int kiwi_b200_native_sbg(const char* skipbigram_mdl_path, void** out_bytes, uint64_t* out_size);
+const char* kiwi_b200_native_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -515,6 +515,9 @@ namespace KB_VIT_NS
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
 		uint32_t top1Buckets = 1;           // bucket count of the reference's `top1` unordered_set, per sentence (unordered_emu.h)
+#if KB_SBG
+		uint32_t sbIdxCap = 0;              // slots of the current candidate's `top1` index at the end of the sentence's pool region (0 = none yet)
+#endif
 		DCand* dcur = nullptr; uint32_t curBuf = 0, pfPhase = 0; const DCand* pfBase[2] = { nullptr, nullptr };      // candidate-row staging (see prefetchCands)
 		uint2* nodeCand = nullptr;
 		WarpSmem* sm; uint32_t stagedNode = 0xFFFFFFFFu; uint32_t nItems = 0; uint32_t htBase = 0, htCount = 0, nFw = 1;
@@ -687,8 +690,7 @@ namespace KB_VIT_NS
 		//   - nothing found: the state is appended (again) while the bucket has room (128), else dropped.
 		//  mode 2 (`top1`, an unordered_set, 229-276): plain set semantics, the better score replaces the entry.
 		// Shared memory (the hash index `ht` of the other builds, unused here): modes 0 / 1 keep per bucket the entry index of every position
-		// (bIdx) and the hash byte it was appended with (hb); mode 2 keeps an open-addressing index over the first HT_MAX_ENTRIES entries and
-		// scans the rest.
+		// (bIdx) and the hash byte it was appended with (hb); mode 2 keeps an open-addressing index over all entries in global memory.
 		__device__ __noinline__ void sbgInsertRound(unsigned vmask, const PathT& np, uint32_t candBeg, uint32_t& E, uint32_t* bucketCnt, uint32_t mode)
 		{
 			uint16_t* bIdx = sm->ht;                                             // [4][128]
@@ -718,37 +720,46 @@ namespace KB_VIT_NS
 				uint32_t b = 0, n = 0;
 				if (mode == 2)
 				{
-					uint32_t slot = ((uint32_t)(h ^ (h >> 29)) * 0x9E3779B1u) >> 7 & (HT_SIZE - 1);
-					const uint32_t slot0 = slot;
+					// open-addressing index over ALL entries of the candidate (slot = entry + 1), kept at the far end of the sentence's pool
+					// region and doubled (rebuilt by lane 0) when half full: a candidate with tens of thousands of distinct states stays linear
+					uint32_t* gi = reinterpret_cast<uint32_t*>(pool + poolCap) - sbIdxCap;
+					if (2 * (E + 1) > sbIdxCap)
+					{
+						uint32_t cap = sbIdxCap ? sbIdxCap * 2 : 2048u;
+						while (2 * (E + 1) > cap) cap *= 2;
+						uint32_t* ng = reinterpret_cast<uint32_t*>(pool + poolCap) - cap;
+						if (reinterpret_cast<const char*>(ng) < reinterpret_cast<const char*>(pool + candBeg + E + 2)) { err = ST_PATH_OVERFLOW; return; }
+						#pragma unroll 1
+						for (uint32_t i = lane; i < cap; i += 32) ng[i] = 0;
+						__syncwarp();
+						if (lane == 0)
+						{
+							#pragma unroll 1
+							for (uint32_t e = 0; e < E; ++e)
+							{
+								const unsigned long long hc = pool[candBeg + e].hcode;
+								uint32_t sl = ((uint32_t)(hc ^ (hc >> 29)) * 0x9E3779B1u) >> 7 & (cap - 1);
+								while (ng[sl]) sl = (sl + 1) & (cap - 1);
+								ng[sl] = e + 1;
+							}
+						}
+						__syncwarp();
+						sbIdxCap = cap; gi = ng;
+					}
+					else if (reinterpret_cast<const char*>(gi) < reinterpret_cast<const char*>(pool + candBeg + E + 2)) { err = ST_PATH_OVERFLOW; return; }
+					const uint32_t imask = sbIdxCap - 1;
+					uint32_t slot = ((uint32_t)(h ^ (h >> 29)) * 0x9E3779B1u) >> 7 & imask;
 					#pragma unroll 1
 					while (true)
 					{
-						const uint32_t e = sm->ht[slot];
+						const uint32_t e = gi[slot];
 						if (!e) break;
 						const PathT* t = pool + candBeg + (e - 1);
 						if (t->hcode == h && eq(t)) { target = e - 1; break; }
-						slot = (slot + 1) & (HT_SIZE - 1);
-					}
-					if (target == NPOS && E > HT_MAX_ENTRIES)
-					{
-						#pragma unroll 1
-						for (uint32_t base = HT_MAX_ENTRIES; base < E && target == NPOS; base += 32)
-						{
-							const uint32_t e = base + lane;
-							bool hit = false;
-							if (e < E) { const PathT* t = pool + candBeg + e; hit = t->hcode == h && eq(t); }
-							const unsigned m = __ballot_sync(FULL, hit);
-							if (m) target = base + __ffs(m) - 1;
-						}
+						slot = (slot + 1) & imask;
 					}
 					append = target == NPOS;
-					if (append && E < HT_MAX_ENTRIES)
-					{
-						// (all lanes walk the same probe sequence; lane 0 stores)
-						uint32_t s2 = slot0;
-						while (sm->ht[s2]) s2 = (s2 + 1) & (HT_SIZE - 1);
-						if (lane == 0) sm->ht[s2] = (uint16_t)(E + 1);
-					}
+					if (append && lane == 0) gi[slot] = E + 1;      // (the probe stopped at the first empty slot of this key's sequence)
 				}
 				else
 				{
@@ -890,6 +901,9 @@ namespace KB_VIT_NS
 			uint32_t bucketCnt[4] = { 0, 0, 0, 0 };
 			uint32_t fwCarry = cc.firstWid0;
 			htClear();
+#if KB_SBG
+			sbIdxCap = 0;      // (the `top1` index of the previous candidate is dead)
+#endif
 			const bool allowedSpaceBetweenChunk = c_m.cfg.space_tolerance > 0;
 
 			for (uint32_t qb = 0; qb < P; qb += pairsPerRound)
