@@ -230,7 +230,20 @@ typedef struct kiwi_b200_native_sbg_t {
 	uint64_t discnts_off, discnts_bytes; /* KB2_SEC_SB_DISCNTS float[vocab_size]        */
 	uint64_t valid_off, valid_bytes;     /* KB2_SEC_SB_VALID   uint8_t[vocab_size]      */
 } kiwi_b200_native_sbg_t;
+typedef struct kiwi_b200_native_cong_t {
+	uint32_t num_nodes, num_edges, root_size, dim, context_size, key_size, flags, vocab_size;   /* = kb2_header cg_* / lang_vocab_size */
+	uint64_t nodes_off, nodes_bytes;         /* KB2_SEC_CG_NODES     kb2_cg_node[num_nodes] */
+	uint64_t keys_off, keys_bytes;           /* KB2_SEC_CG_KEYS      uint32_t[num_edges]    */
+	uint64_t values_off, values_bytes;       /* KB2_SEC_CG_VALUES    int32_t[num_edges]     */
+	uint64_t root_off, root_bytes;           /* KB2_SEC_CG_ROOT      int32_t[root_size]     */
+	uint64_t ctx_emb_off, ctx_emb_bytes;     /* KB2_SEC_CG_CTX_EMB   */
+	uint64_t out_emb_off, out_emb_bytes;     /* KB2_SEC_CG_OUT_EMB   */
+	uint64_t inv_vocab_off, inv_vocab_bytes; /* KB2_SEC_CG_INV_VOCAB (may be empty) */
+	uint64_t out_bias_off, out_bias_bytes;   /* KB2_SEC_CG_OUT_BIAS  (may be empty) */
+} kiwi_b200_native_cong_t;
 int kiwi_b200_native_knlm(const char* sj_knlm_path, void** out_bytes, uint64_t* out_size);
+/*   cong.mdl        CoNgramModel<..., windowSize 0, quantized> constructor, src/CoNgramModel.cpp:425-790 (8-bit embedding rows) */
+int kiwi_b200_native_cong(const char* cong_mdl_path, void** out_bytes, uint64_t* out_size);
 int kiwi_b200_native_sbg(const char* skipbigram_mdl_path, void** out_bytes, uint64_t* out_size);
 const char* kiwi_b200_native_error(void);
 

@@ -6,11 +6,15 @@
 //   sj.knlm          KnLangModel<...>::KnLangModel(MemoryObject&&)      /root/reference/src/Knlm.hpp:1003-1167, header include/kiwi/Knlm.h:10-16
 //                    node-size codec QCode<0, 2, 8, 16>                  src/QEncoder.hpp:13-47,135-176,215-250; 8-bit tables src/Knlm.hpp:427-460
 //   skipbigram.mdl   SkipBigramModel<...>::SkipBigramModel(...)          src/SkipBigramModel.hpp:40-105, header include/kiwi/SkipBigramModel.h:9-13
+//   cong.mdl         CoNgramModel<..., windowSize 0, quantized>::CoNgramModel   src/CoNgramModel.cpp:425-790 (8-bit rows only), header
+//                    include/kiwi/CoNgramModel.h:18-33; integer codec: streamvbyte (fast-pack/streamvbyte @7c472d7d, absent from the
+//                    reference snapshot - its published format is restated below: 2-bit length codes first, then the little-endian bytes)
 // Host code only; no CUDA.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <deque>
 #include <fstream>
 #include <stdexcept>
@@ -359,6 +363,204 @@ namespace
 		return m;
 	}
 
+	struct CgHeader      // CoNgramModelHeader
+	{
+		uint64_t vocabSize, contextSize;
+		uint16_t dim, flags;
+		uint8_t keySize, windowSize, qbit, qgroup;
+		uint64_t numNodes, nodeOffset, keyOffset, valueOffset, embOffset;
+	};
+	static_assert(sizeof(CgHeader) == 64, "CoNgramModelHeader");
+
+	// streamvbyte: ceil(n / 4) control bytes (2 bits per value, first value in the low bits), then the data bytes.  The classic code maps
+	// the control value c to c + 1 bytes; the "0124" code maps 0, 1, 2, 3 to 0, 1, 2, 4 bytes.  Returns the bytes consumed.
+	size_t svbDecode(const uint8_t* in, const uint8_t* end, uint32_t* out, size_t n, bool code0124)
+	{
+		const size_t nc = (n + 3) / 4;
+		if (in + nc > end) throw std::runtime_error("cong.mdl: integer stream beyond the file");
+		const uint8_t* data = in + nc;
+		for (size_t i = 0; i < n; ++i)
+		{
+			const unsigned c = (in[i / 4] >> ((i % 4) * 2)) & 3;
+			const unsigned len = code0124 ? (c == 3 ? 4u : c) : c + 1;
+			if (data + len > end) throw std::runtime_error("cong.mdl: integer stream beyond the file");
+			uint32_t v = 0;
+			for (unsigned k = 0; k < len; ++k) v |= (uint32_t)data[k] << (8 * k);
+			out[i] = v; data += len;
+		}
+		return (size_t)(data - in);
+	}
+
+	float halfToFloat(uint16_t hv)
+	{
+		const uint32_t sign = (uint32_t)(hv >> 15) << 31, ex = (hv >> 10) & 31, man = hv & 1023;
+		uint32_t bits;
+		if (ex == 0)
+		{
+			if (!man) bits = sign;
+			else { int e = -1; uint32_t m = man; do { ++e; m <<= 1; } while (!(m & 1024)); bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 1023) << 13); }
+		}
+		else if (ex == 31) bits = sign | 0x7F800000u | (man << 13);
+		else bits = sign | ((ex - 15 + 127) << 23) | (man << 13);
+		float f; std::memcpy(&f, &bits, 4); return f;
+	}
+
+	struct Cong
+	{
+		std::vector<kb2_cg_node> nodes; std::vector<uint32_t> keys; std::vector<int32_t> values, root;
+		std::vector<uint8_t> ctxEmb, outEmb; std::vector<uint32_t> invVocab; std::vector<float> outBias;
+		CgHeader h{};
+		// child of `node` by key: > 0 inner child diff, < 0 leaf (-contextIdx), 0 = none (nst::searchKV)
+		int32_t search(int64_t node, uint32_t key) const
+		{
+			const kb2_cg_node& n = nodes[node];
+			size_t lo = n.next_offset, hi = lo + n.num_nexts;
+			while (lo < hi) { const size_t mid = (lo + hi) / 2; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+			return (lo < (size_t)n.next_offset + n.num_nexts && keys[lo] == key) ? values[lo] : 0;
+		}
+	};
+
+	Cong parseCong(const std::vector<char>& file)
+	{
+		if (file.size() < sizeof(CgHeader)) throw std::runtime_error("cong.mdl: too small");
+		Cong m; std::memcpy(&m.h, file.data(), sizeof(CgHeader));
+		const CgHeader& h = m.h;
+		const uint8_t* p = reinterpret_cast<const uint8_t*>(file.data()); const uint8_t* end = p + file.size();
+		if (h.qbit != 8) throw std::runtime_error("cong.mdl: only 8-bit embedding rows are read natively");
+		if (h.keySize != 2 && h.keySize != 3 && h.keySize != 4) throw std::runtime_error("cong.mdl: key size");      // (1-byte VL keys: not met)
+		if (h.dim == 0 || h.numNodes < 2 || h.numNodes > (1ull << 31) || h.vocabSize > (1ull << 31) || h.contextSize > (1ull << 31)) throw std::runtime_error("cong.mdl: header");
+		if (h.nodeOffset > file.size() || h.keyOffset > file.size() || h.valueOffset > file.size() || h.embOffset > file.size()) throw std::runtime_error("cong.mdl: section offset beyond the file");
+		if (h.flags & 4) throw std::runtime_error("cong.mdl: trie frequencies are not read natively");
+		if (h.flags && h.windowSize) throw std::runtime_error("cong.mdl: optional sections behind window data are not read natively");
+
+		std::vector<uint32_t> sizes(h.numNodes), keyData(h.numNodes - 1), vals(h.numNodes);
+		svbDecode(p + h.nodeOffset, end, sizes.data(), h.numNodes, true);
+		svbDecode(p + h.keyOffset, end, keyData.data(), h.numNodes - 1, false);
+		svbDecode(p + h.valueOffset, end, vals.data(), h.numNodes, true);
+		size_t nonLeaf = 0;
+		for (uint32_t s : sizes) if (s) ++nonLeaf;
+		if (!sizes[0]) throw std::runtime_error("cong.mdl: the root has no children");
+
+		// nodes and (key, value) pairs, the pairs of every node ascending by key (the image's order)
+		m.nodes.resize(nonLeaf); m.keys.resize(h.numNodes - 1); m.values.assign(h.numNodes - 1, 0);
+		struct Range { size_t node, cur, end; };
+		std::vector<Range> open;
+		size_t ni = 0, nextOff = 0;
+		for (size_t i = 0; i < h.numNodes; ++i)
+		{
+			if (sizes[i])
+			{
+				if (!open.empty()) m.values[open.back().cur] = (int32_t)(ni - open.back().node);
+				kb2_cg_node& n = m.nodes[ni];
+				n.lower = 0; n.value = vals[i]; n.next_offset = (uint32_t)nextOff; n.num_nexts = sizes[i];
+				open.push_back(Range{ ni, nextOff, nextOff + sizes[i] });
+				nextOff += sizes[i];
+				if (nextOff > h.numNodes - 1) throw std::runtime_error("cong.mdl: more children than keys");
+				++ni;
+			}
+			else
+			{
+				if (open.empty()) throw std::runtime_error("cong.mdl: a leaf without a parent");
+				m.values[open.back().cur] = -(int32_t)vals[i];
+				open.back().cur++;
+				while (open.back().cur == open.back().end) { open.pop_back(); if (open.empty()) break; open.back().cur++; }
+			}
+		}
+		for (size_t i = 0; i < h.numNodes - 1; ++i) m.keys[i] = keyData[i];
+		for (size_t n = 0; n < nonLeaf; ++n)
+		{
+			const kb2_cg_node& nd = m.nodes[n];
+			std::vector<std::pair<uint32_t, int32_t>> kv(nd.num_nexts);
+			for (uint32_t j = 0; j < nd.num_nexts; ++j) kv[j] = { m.keys[nd.next_offset + j], m.values[nd.next_offset + j] };
+			std::sort(kv.begin(), kv.end());
+			for (uint32_t j = 0; j < nd.num_nexts; ++j) { m.keys[nd.next_offset + j] = kv[j].first; m.values[nd.next_offset + j] = kv[j].second; }
+		}
+		m.root.assign(h.vocabSize, 0);
+		for (uint32_t i = 0; i < m.nodes[0].num_nexts; ++i) { if (m.keys[i] >= m.root.size()) throw std::runtime_error("cong.mdl: root key beyond the vocabulary"); m.root[m.keys[i]] = m.values[i]; }
+
+		// suffix links and inherited context ids, breadth first (CoNgramModel.cpp:547-570)
+		std::deque<uint32_t> dq;
+		for (dq.push_back(0); !dq.empty(); dq.pop_front())
+		{
+			const uint32_t pi = dq.front();
+			const kb2_cg_node pn = m.nodes[pi];
+			for (uint32_t i = 0; i < pn.num_nexts; ++i)
+			{
+				const uint32_t k = m.keys[pn.next_offset + i]; const int32_t v = m.values[pn.next_offset + i];
+				if (v <= 0) continue;
+				const uint32_t child = pi + (uint32_t)v;
+				int64_t node = pi;                                   // findLowerNode (CoNgramModel.hpp:186-203)
+				while (m.nodes[node].lower)
+				{
+					const int64_t low = node + m.nodes[node].lower;
+					const int32_t found = m.search(low, k);
+					if (found > 0) { node = low + found; goto linked; }
+					node = low;
+				}
+			linked:
+				m.nodes[child].lower = (int32_t)(node - (int64_t)child);
+				if (m.nodes[child].value == 0)                        // findLowerValue (205-229)
+				{
+					int64_t q = pi; uint32_t val = 0; bool got = false;
+					while (m.nodes[q].lower)
+					{
+						const int64_t low = q + m.nodes[q].lower;
+						const int32_t found = m.search(low, k);
+						if (found != 0) { val = found > 0 ? m.nodes[low + found].value : (uint32_t)(-found); got = true; break; }
+						q = low;
+					}
+					if (!got) val = m.nodes[q].value;
+					m.nodes[child].value = val;
+				}
+				dq.push_back(child);
+			}
+		}
+
+		// embedding rows (598-681): context rows u8 (= s8 + 128) + scale + bias, output rows s8 + scale + 128 * sum
+		const size_t stride = (size_t)h.dim + 8;
+		m.ctxEmb.assign(h.contextSize * stride, 0); m.outEmb.assign(h.vocabSize * stride, 0);
+		const uint8_t* e = p + h.embOffset;
+		auto need = [&](size_t n) { if ((size_t)(end - e) < n) throw std::runtime_error("cong.mdl: embeddings beyond the file"); };
+		for (size_t i = 0; i < h.contextSize; ++i)
+		{
+			need((size_t)h.dim + 4 + (h.windowSize ? 4 : 0));
+			uint8_t* o = m.ctxEmb.data() + i * stride;
+			for (size_t d = 0; d < h.dim; ++d) o[d] = (uint8_t)((int8_t)e[d] + 128);
+			uint16_t hs, hb; std::memcpy(&hs, e + h.dim, 2); std::memcpy(&hb, e + h.dim + 2, 2);
+			const float scale = halfToFloat(hs), bias = -halfToFloat(hb);
+			std::memcpy(o + h.dim, &scale, 4); std::memcpy(o + h.dim + 4, &bias, 4);
+			e += (size_t)h.dim + 4 + (h.windowSize ? 4 : 0);
+		}
+		for (size_t i = 0; i < h.vocabSize; ++i)
+		{
+			need((size_t)h.dim + 2);
+			uint8_t* o = m.outEmb.data() + i * stride;
+			int32_t sum = 0;
+			for (size_t d = 0; d < h.dim; ++d) { o[d] = e[d]; sum += (int8_t)e[d]; }
+			uint16_t hs; std::memcpy(&hs, e + h.dim, 2);
+			const float scale = halfToFloat(hs); const int32_t hsum = sum * 128;
+			std::memcpy(o + h.dim, &scale, 4); std::memcpy(o + h.dim + 4, &hsum, 4);
+			e += (size_t)h.dim + 2;
+		}
+		if (h.flags & 1)      // output bias: one byte per token, dequantised against the minimum stored behind them (765-774)
+		{
+			need(h.vocabSize + 2);
+			uint16_t hm; std::memcpy(&hm, e + h.vocabSize, 2);
+			const float minVal = halfToFloat(hm);
+			m.outBias.resize(h.vocabSize);
+			for (size_t i = 0; i < h.vocabSize; ++i) m.outBias[i] = (float)e[i] * (-minVal) / 255.f + minVal;
+			e += h.vocabSize + 2;
+		}
+		if (h.flags & 2)      // reordered vocabulary (776-780): KeyType entries (2 bytes for key sizes 2 / 3, else 4)
+		{
+			const size_t ks = h.keySize == 4 ? 4 : 2;
+			need(h.vocabSize * ks);
+			m.invVocab.resize(h.vocabSize);
+			for (size_t i = 0; i < h.vocabSize; ++i) m.invVocab[i] = (uint32_t)keyAt(reinterpret_cast<const char*>(e), (unsigned)ks, i);
+		}
+		return m;
+	}
+
 	template<class T> void put(std::vector<char>& blob, uint64_t& off, uint64_t& bytes, const std::vector<T>& v)
 	{
 		while (blob.size() % 16) blob.push_back(0);
@@ -406,6 +608,28 @@ int kiwi_b200_native_sbg(const char* skipbigram_mdl_path, void** out_bytes, uint
 		std::vector<char> blob(sizeof(hd), 0);
 		put(blob, hd.ptrs_off, hd.ptrs_bytes, m.ptrs); put(blob, hd.keys_off, hd.keys_bytes, m.keys); put(blob, hd.comps_off, hd.comps_bytes, m.comps);
 		put(blob, hd.discnts_off, hd.discnts_bytes, m.discnts); put(blob, hd.valid_off, hd.valid_bytes, m.valid);
+		std::memcpy(blob.data(), &hd, sizeof(hd));
+		void* p = std::malloc(blob.size());
+		if (!p) throw std::bad_alloc();
+		std::memcpy(p, blob.data(), blob.size());
+		*out_bytes = p; *out_size = blob.size();
+		return 0;
+	}
+	catch (const std::exception& e) { g_nativeError = e.what(); return -1; }
+}
+
+int kiwi_b200_native_cong(const char* cong_mdl_path, void** out_bytes, uint64_t* out_size)
+{
+	try
+	{
+		const Cong m = parseCong(readFile(cong_mdl_path));
+		kiwi_b200_native_cong_t hd{};
+		hd.num_nodes = (uint32_t)m.nodes.size(); hd.num_edges = (uint32_t)m.keys.size(); hd.root_size = (uint32_t)m.h.vocabSize; hd.dim = m.h.dim;
+		hd.context_size = (uint32_t)m.h.contextSize; hd.key_size = m.h.keySize; hd.flags = m.h.flags; hd.vocab_size = (uint32_t)m.h.vocabSize;
+		std::vector<char> blob(sizeof(hd), 0);
+		put(blob, hd.nodes_off, hd.nodes_bytes, m.nodes); put(blob, hd.keys_off, hd.keys_bytes, m.keys); put(blob, hd.values_off, hd.values_bytes, m.values);
+		put(blob, hd.root_off, hd.root_bytes, m.root); put(blob, hd.ctx_emb_off, hd.ctx_emb_bytes, m.ctxEmb); put(blob, hd.out_emb_off, hd.out_emb_bytes, m.outEmb);
+		put(blob, hd.inv_vocab_off, hd.inv_vocab_bytes, m.invVocab); put(blob, hd.out_bias_off, hd.out_bias_bytes, m.outBias);
 		std::memcpy(blob.data(), &hd, sizeof(hd));
 		void* p = std::malloc(blob.size());
 		if (!p) throw std::bad_alloc();

@@ -1,7 +1,8 @@
 // CPU check (tests/test_native_lm.py): the native readers of the reference's sj.knlm / skipbigram.mdl files (kiwi_b200/csrc/native_lm.cpp,
 // no reference library involved) against the sections of the model images that flatten_model dumped from the reference's own in-memory
 // models - byte for byte, including the suffix links, the BOS state and unk_ll that the reference computes at load time.
-//   native_lm_check <libkiwi_b200.so> <knlm image> <sj.knlm> [<sbg image> <skipbigram.mdl>]
+//   native_lm_check <libkiwi_b200.so> <knlm image> <sj.knlm> [<sbg image> <skipbigram.mdl> [<cong image> <cong.mdl>]]
+//   (pass - - for a pair to skip)
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
@@ -27,9 +28,10 @@ int main(int argc, char** argv)
 	if (!lib) { std::printf("dlopen: %s\n", dlerror()); return 2; }
 	auto knlm = (int (*)(const char*, void**, uint64_t*))dlsym(lib, "kiwi_b200_native_knlm");
 	auto sbg = (int (*)(const char*, void**, uint64_t*))dlsym(lib, "kiwi_b200_native_sbg");
+	auto cong = (int (*)(const char*, void**, uint64_t*))dlsym(lib, "kiwi_b200_native_cong");
 	auto err = (const char* (*)())dlsym(lib, "kiwi_b200_native_error");
 	auto freeFn = (void (*)(void*))dlsym(lib, "kiwi_b200_free");
-	if (!knlm || !sbg || !err || !freeFn) { std::printf("missing symbols\n"); return 2; }
+	if (!knlm || !sbg || !cong || !err || !freeFn) { std::printf("missing symbols\n"); return 2; }
 	int bad = 0;
 	{
 		const auto img = readAll(argv[2]);
@@ -48,7 +50,7 @@ int main(int argc, char** argv)
 		bad += sc ? 0 : 1;
 		freeFn(blob);
 	}
-	if (argc >= 6)
+	if (argc >= 6 && std::strcmp(argv[4], "-"))
 	{
 		const auto img = readAll(argv[4]);
 		const kb2_header* h = reinterpret_cast<const kb2_header*>(img.data());
@@ -62,6 +64,27 @@ int main(int argc, char** argv)
 		bad += cmp("SB_VALID", img, h, KB2_SEC_SB_VALID, b, n->valid_off, n->valid_bytes);
 		const bool sc = n->vocab_size == h->sb_vocab_size && n->window_size == h->sb_window_size && n->num_pairs == h->sb_num_pairs;
 		std::printf("sbg scalars %s\n", sc ? "identical" : "DIFFER");
+		bad += sc ? 0 : 1;
+		freeFn(blob);
+	}
+	if (argc >= 8 && std::strcmp(argv[6], "-"))
+	{
+		const auto img = readAll(argv[6]);
+		const kb2_header* h = reinterpret_cast<const kb2_header*>(img.data());
+		void* blob = nullptr; uint64_t size = 0;
+		if (cong(argv[7], &blob, &size)) { std::printf("native cong failed: %s\n", err()); return 1; }
+		const auto* n = static_cast<const kiwi_b200_native_cong_t*>(blob); const char* b = static_cast<const char*>(blob);
+		bad += cmp("CG_NODES", img, h, KB2_SEC_CG_NODES, b, n->nodes_off, n->nodes_bytes);
+		bad += cmp("CG_KEYS", img, h, KB2_SEC_CG_KEYS, b, n->keys_off, n->keys_bytes);
+		bad += cmp("CG_VALUES", img, h, KB2_SEC_CG_VALUES, b, n->values_off, n->values_bytes);
+		bad += cmp("CG_ROOT", img, h, KB2_SEC_CG_ROOT, b, n->root_off, n->root_bytes);
+		bad += cmp("CG_CTX_EMB", img, h, KB2_SEC_CG_CTX_EMB, b, n->ctx_emb_off, n->ctx_emb_bytes);
+		bad += cmp("CG_OUT_EMB", img, h, KB2_SEC_CG_OUT_EMB, b, n->out_emb_off, n->out_emb_bytes);
+		bad += cmp("CG_INV_VOCAB", img, h, KB2_SEC_CG_INV_VOCAB, b, n->inv_vocab_off, n->inv_vocab_bytes);
+		bad += cmp("CG_OUT_BIAS", img, h, KB2_SEC_CG_OUT_BIAS, b, n->out_bias_off, n->out_bias_bytes);
+		const bool sc = n->num_nodes == h->cg_num_nodes && n->num_edges == h->cg_num_edges && n->root_size == h->cg_root_size && n->dim == h->cg_dim
+			&& n->context_size == h->cg_context_size && n->key_size == h->cg_key_size && n->flags == h->cg_flags && n->vocab_size == h->lang_vocab_size;
+		std::printf("cong scalars %s (nodes %u edges %u dim %u contexts %u key size %u)\n", sc ? "identical" : "DIFFER", n->num_nodes, n->num_edges, n->dim, n->context_size, n->key_size);
 		bad += sc ? 0 : 1;
 		freeFn(blob);
 	}

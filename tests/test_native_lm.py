@@ -1,6 +1,6 @@
 """CPU: native readers of the reference's language-model files (kiwi_b200/csrc/native_lm.cpp, exported as kiwi_b200_native_knlm /
-kiwi_b200_native_sbg; SURVEY 8f-2, first pieces of a loader that does not link the reference).  tests/native/native_lm_check.cpp
-compares their output with the Knlm / SkipBigram sections of the model images that flatten_model dumped from the reference's own
+kiwi_b200_native_sbg / kiwi_b200_native_cong; SURVEY 8f-2, first pieces of a loader that does not link the reference).  tests/native/native_lm_check.cpp
+compares their output with the Knlm / SkipBigram / CoNg sections of the model images that flatten_model dumped from the reference's own
 in-memory models: every section byte for byte, and the scalars the reference computes at load time (suffix links, BOS state, unk_ll)."""
 import os, subprocess, tempfile
 import pytest
@@ -18,10 +18,13 @@ def test_native_knlm_and_sbg_sections_equal_the_flattened_image():
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "native", "native_lm_check.cpp"), "-ldl"], check=True)
     args = [exe, lib, knlm_img, knlm_file]
     sbg_img = os.path.join(MODELS, "sbg_small.img"); sbg_file = os.path.join(MODELS, "sbg_small", "skipbigram.mdl")
-    if os.path.exists(sbg_img) and os.path.exists(sbg_file): args += [sbg_img, sbg_file]
+    args += [sbg_img, sbg_file] if os.path.exists(sbg_img) and os.path.exists(sbg_file) else ["-", "-"]
+    cong_img = os.path.join(MODELS, "cong_small.img"); cong_file = os.path.join(MODELS, "cong_small", "cong.mdl")
+    args += [cong_img, cong_file] if os.path.exists(cong_img) and os.path.exists(cong_file) else ["-", "-"]
     out = subprocess.run(args, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "mismatching sections 0" in out.stdout, out.stdout + out.stderr
     assert "KN_NODES" in out.stdout and "knlm scalars identical" in out.stdout
+    if os.path.exists(cong_file): assert "CG_OUT_EMB" in out.stdout and "cong scalars identical" in out.stdout
 
 
 def test_native_reader_rejects_damaged_files(tmp_path):
