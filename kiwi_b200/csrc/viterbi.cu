@@ -515,6 +515,7 @@ namespace KB_VIT_NS
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
 		uint32_t top1Buckets = 1;           // bucket count of the reference's `top1` unordered_set, per sentence (unordered_emu.h)
+		bool exactInsert = KB_SBG != 0;     // evalCand inserts item by item (exactInsertRound): always in the SkipBigram build, during a group redo in the others
 #if KB_SBG
 		uint32_t sbIdxCap = 0;              // slots of the current candidate's `top1` index at the end of the sentence's pool region (0 = none yet)
 #endif
@@ -676,9 +677,12 @@ namespace KB_VIT_NS
 			return ll;
 		}
 
+#endif
+
 		// ---- the path container of one candidate, item by item (BestPathContainer.hpp) -------------------------------------------------
-		// The reference inserts a candidate's paths one after the other, and with SkipBigram states the outcome depends on that order in
-		// ways the parallel insert of the other builds does not model:
+		// The reference inserts a candidate's paths one after the other, and once a bucket holds 64 states the outcome depends on that order
+		// in ways the parallel insert cannot model.  The SkipBigram build (states rarely merge) inserts every candidate this way; the Knlm /
+		// CoNg builds re-run a group of candidates this way when one of their buckets has reached 64 states (evaluate: `exactInsert`):
 		//  modes 0 / 1 (BucketedHashContainer::insertOptimized<avx2>, 316-383, with nst::findAll<avx2>, search.cpp:948-968), as the code
 		//  BEHAVES on x86-64:
 		//   - a bucket with fewer than 64 entries is searched properly (hash byte, then equalTo);
@@ -691,7 +695,7 @@ namespace KB_VIT_NS
 		//  mode 2 (`top1`, an unordered_set, 229-276): plain set semantics, the better score replaces the entry.
 		// Shared memory (the hash index `ht` of the other builds, unused here): modes 0 / 1 keep per bucket the entry index of every position
 		// (bIdx) and the hash byte it was appended with (hb); mode 2 keeps an open-addressing index over all entries in global memory.
-		__device__ __noinline__ void sbgInsertRound(unsigned vmask, const PathT& np, uint32_t candBeg, uint32_t& E, uint32_t* bucketCnt, uint32_t mode)
+		__device__ __noinline__ void exactInsertRound(unsigned vmask, const PathT& np, uint32_t candBeg, uint32_t& E, uint32_t* bucketCnt, uint32_t mode)
 		{
 			uint16_t* bIdx = sm->ht;                                             // [4][128]
 			uint8_t* hb = reinterpret_cast<uint8_t*>(sm->ht + 512);              // [4][128]
@@ -702,12 +706,13 @@ namespace KB_VIT_NS
 			{
 				const int L = __ffs(vmask) - 1; vmask &= vmask - 1;
 				const int32_t lm = __shfl_sync(FULL, np.lm_state, L);
+				const float sc = __shfl_sync(FULL, np.acc_score, L);
+#if KB_SBG
 				const uint32_t idw = __shfl_sync(FULL, (uint32_t)np.prev_root_id | ((uint32_t)np.sp_state << 8) | (np.hpos << 16), L);
 				uint32_t hh[8];
 				#pragma unroll
 				for (int i = 0; i < 8; ++i) hh[i] = __shfl_sync(FULL, np.hist[i], L);
 				const unsigned long long h = __shfl_sync(FULL, np.hcode, L);
-				const float sc = __shfl_sync(FULL, np.acc_score, L);
 				auto eq = [&](const PathT* t)
 				{
 					if (t->lm_state != lm || ((uint32_t)t->prev_root_id | ((uint32_t)t->sp_state << 8) | (t->hpos << 16)) != idw) return false;
@@ -716,8 +721,25 @@ namespace KB_VIT_NS
 					for (int i = 0; i < 8; ++i) same = same && t->hist[i] == hh[i];
 					return same;
 				};
+#else
+				// WordLL::equalTo: prevRootId, spState, LM state (the Knlm node; CoNg: the context-trie node only, CoNgramModel.hpp:491-494)
+				const uint32_t idw = __shfl_sync(FULL, (uint32_t)np.prev_root_id | ((uint32_t)np.sp_state << 8), L);
+				unsigned long long h;
+				{
+					// Hash<WordLL> (BestPathContainer.hpp:79-84) over Hash<LmState>: std::hash<int32_t> (Knlm.hpp:1170-1178) / Hash<uint32_t>(node) (CoNg)
+#if KB_CONG
+					const unsigned long long v = (uint32_t)lm;
+					const unsigned long long h0 = (v * 2305843009213693951ull) ^ ((v << 33) | (v >> 31));
+#else
+					const unsigned long long h0 = (unsigned long long)(long long)lm;
+#endif
+					h = (unsigned long long)idw ^ ((h0 << 3) | (h0 >> 61));
+				}
+				auto eq = [&](const PathT* t) { return t->lm_state == lm && ((uint32_t)t->prev_root_id | ((uint32_t)t->sp_state << 8)) == idw; };
+#endif
 				uint32_t target = NPOS; bool append = false;
 				uint32_t b = 0, n = 0;
+#if KB_SBG
 				if (mode == 2)
 				{
 					// open-addressing index over ALL entries of the candidate (slot = entry + 1), kept at the far end of the sentence's pool
@@ -762,6 +784,7 @@ namespace KB_VIT_NS
 					if (append && lane == 0) gi[slot] = E + 1;      // (the probe stopped at the first empty slot of this key's sequence)
 				}
 				else
+#endif
 				{
 					b = mode == 1 ? ((uint32_t)(h >> 8) & 3u) : 0u; n = bucketCnt[b];
 					const uint8_t hbNew = (uint8_t)h;
@@ -810,7 +833,11 @@ namespace KB_VIT_NS
 					if (sc > t->acc_score && lane == (uint32_t)L)
 					{
 						PathT w = np;
+#if KB_SBG
 						if (mode != 2) { w.prev_root_id = t->prev_root_id; w.hcode = t->hcode; }      // neither prevRootId nor the stored hash byte is refreshed (370-381)
+#else
+						w.prev_root_id = t->prev_root_id;
+#endif
 						pool[candBeg + target] = w;
 					}
 				}
@@ -829,7 +856,6 @@ namespace KB_VIT_NS
 				__syncwarp();
 			}
 		}
-#endif
 
 		// ---- evalSingleMorpheme, PathEvaluator.hpp:514-634 -------------------------------------------
 		struct CandCtx
@@ -1101,9 +1127,9 @@ namespace KB_VIT_NS
 				const uint32_t prevRoot = pp.root_id;
 				const unsigned vmask = __ballot_sync(FULL, valid);
 				if (!vmask) continue;
-#if KB_SBG
+				if (KB_SBG || (exactInsert && mode != 2))
 				{
-					// every valid lane prepares its path record; the container takes them one at a time, in pair order (sbgInsertRound)
+					// every valid lane prepares its path record; the container takes them one at a time, in pair order (exactInsertRound)
 					PathT np;
 					if (valid)
 					{
@@ -1114,19 +1140,24 @@ namespace KB_VIT_NS
 						np.root_id = rootId != COMMON_ROOT ? rootId : pp.root_id;
 						np.fw = cc.fwNew | (np.root_id == COMMON_ROOT ? (uint32_t)FW_COMMON_ROOT : 0u);
 						np.prev_root_id = (uint8_t)prevRoot; np.morph_tag = cc.morphTag;
+#if KB_CONG
+						P_CTX(np) = ctxIdx;
+#else
 						np.wid_feat = cc.widFeat;
+#endif
+#if KB_SBG
 						for (int i = 0; i < 8; ++i) np.hist[i] = hist[i];
 						np.hpos = hpos; np.hpad = 0;
 						// Hash<WordLL<SbgState>>: Knlm node, the 8 ring slots, then prevRootId | spState << 8 (SkipBigramModel.hpp:188-203, BestPathContainer.hpp:79-84)
 						unsigned long long h = (unsigned long long)(long long)lmState;
 						for (int i = 0; i < 8; ++i) h = (unsigned long long)hist[i] ^ ((h << 3) | (h >> 61));
 						np.hcode = (unsigned long long)((prevRoot & 0xFFu) | ((uint32_t)spState << 8)) ^ ((h << 3) | (h >> 61));
+#endif
 					}
-					sbgInsertRound(vmask, np, candBeg, E, bucketCnt, mode);
+					exactInsertRound(vmask, np, candBeg, E, bucketCnt, mode);
 					if (err) return;
 					continue;
 				}
-#endif
 				const unsigned long long key = valid
 					? ((unsigned long long)(uint32_t)lmState | ((unsigned long long)prevRoot << 32) | ((unsigned long long)spState << 40))
 					: (0xFFFF000000000000ull | lane);
@@ -1592,6 +1623,51 @@ namespace KB_VIT_NS
 			htBase = top; htCount = 0;
 		}
 
+#ifndef KB_EXACT_FROM
+#define KB_EXACT_FROM 64u      // (tests lower it to drive the redo path through every golden sentence)
+#endif
+		// has a bucket of one of the group's containers reached 64 (distinct) states?  Segments: candidate k's entries follow candidate k - 1's,
+		// sm->candNew[k] of them, in first-insertion order
+		__device__ __noinline__ bool groupNeedsExact(uint32_t groupBase, uint32_t gcount, uint32_t mode)
+		{
+			const uint32_t cn = lane < gcount ? sm->candNew[lane] : 0;
+			const uint8_t cl = lane < gcount ? sm->cdyn[lane].cls : CLS_SKIP;
+			const unsigned big = __ballot_sync(FULL, cn >= KB_EXACT_FROM && (cl == CLS_ITEM || cl == CLS_GENERAL));
+			if (!big) return false;
+			if (mode == 0) return true;
+			// medium mode: 4 buckets, count the largest one of every big candidate
+			uint32_t r = groupBase;
+			bool need = false;
+			#pragma unroll 1
+			for (uint32_t k = 0; k < gcount && !need; ++k)
+			{
+				const uint32_t cnt = sm->candNew[k];
+				if ((big >> k) & 1u)
+				{
+					uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+					#pragma unroll 1
+					for (uint32_t e = 0; e < cnt; e += 32)
+					{
+						uint32_t b = 0xFF;
+						if (e + lane < cnt)
+						{
+							const PathT* p = pool + r + e + lane;
+#if KB_CONG
+							b = (p->sp_state ^ ((0u - (uint32_t)p->lm_state) >> 5)) & 3;
+#else
+							b = (p->sp_state ^ ((uint32_t)p->lm_state >> 5)) & 3;
+#endif
+						}
+						c0 += __popc(__ballot_sync(FULL, b == 0)); c1 += __popc(__ballot_sync(FULL, b == 1));
+						c2 += __popc(__ballot_sync(FULL, b == 2)); c3 += __popc(__ballot_sync(FULL, b == 3));
+					}
+					need = max(max(c0, c1), max(c2, c3)) >= KB_EXACT_FROM;
+				}
+				r += cnt;
+			}
+			return need;
+		}
+
 		// capacity + write-out order per candidate segment (see the comment above stagePaths)
 		__device__ KB_INL1 void fixupGroup(uint32_t groupBase, uint32_t gcount, uint32_t mode, bool deferTop1)
 		{
@@ -1879,6 +1955,41 @@ namespace KB_VIT_NS
 #endif
 			evalCand(g.nodeIdx, node, cc, g.inBeg, g.inEnd, g.mode);
 		}
+
+#if !KB_SBG
+		// (cold) the group's candidates once more, one after the other, with the item-by-item container (see evaluate)
+		__device__ __noinline__ void redoGroupExact(const DNode& node, const FlushCtx& fc, uint32_t groupBase, uint32_t gcount, uint32_t inEnd, uint32_t mode, bool spaceBefore)
+		{
+#ifdef KB_HOSTSIM
+			if (lane == 0 && std::getenv("HS32_TRACE_REDO")) std::fprintf(stderr, "[redo] node %u mode %u group of %u\n", fc.nodeIdx, mode, gcount);
+#endif
+			top = groupBase;
+			resetIndex();
+			exactInsert = true;
+			#pragma unroll 1
+			for (uint32_t k = 0; k < gcount; ++k)
+			{
+				const uint8_t cls = sm->cdyn[k].cls;
+				const uint32_t before = top;
+				if (cls != CLS_SKIP)
+				{
+					GenCtx g;
+					g.nodeIdx = fc.nodeIdx; g.inBeg = fc.inBeg; g.inEnd = inEnd; g.mode = mode; g.ownOff = fc.ownOff; g.ownLen = fc.ownLen; g.ownFw = fc.ownFw;
+					g.ignoreCondScore = fc.ignoreCondScore; g.spaceBefore = spaceBefore;
+#if KB_CONG
+					g.epFirst = fc.epFirst; g.dotCol = ((fc.dotMask >> k) & 1u) ? (int32_t)k : -1;
+#endif
+					evalGeneralCand(k, node, g);
+					if (err) { exactInsert = false; return; }
+				}
+				__syncwarp();
+				if (lane == 0) { sm->candNew[k] = top - before; if (cls == CLS_ITEM) sm->cdyn[k].cls = CLS_GENERAL; }      // capacity and order are final
+				__syncwarp();
+				resetIndex();
+			}
+			exactInsert = false;
+		}
+#endif
 
 		// ---- PathEvaluator::operator(), PathEvaluator.hpp:347-512 ------------------------------------
 		// candBase: the node's static candidate rows (a form's block of c_m.cands, or the unknown NNG / NNP rows)
@@ -2194,6 +2305,16 @@ namespace KB_VIT_NS
 						resetIndex();
 					}
 					flushItems(fc); if (err) return;
+#if !KB_SBG
+					// The parallel insert above is the reference's container as long as no bucket reaches 64 states (0.02 % of the containers
+					// of the bench batches do).  Beyond that the reference's insertOptimized behaves differently (exactInsertRound): the
+					// group's output is dropped and its candidates are evaluated again, one after the other, item by item.
+					if (mode != 2 && teamSize == 1 && groupNeedsExact(myBase, gcount, mode))
+					{
+						redoGroupExact(node, fc, myBase, gcount, inEnd, mode, spaceBefore);
+						if (err) return;
+					}
+#endif
 					if (itemOK || mode == 2) { fixupGroup(myBase, gcount, mode, teamGroup); if (err) return; }
 					};
 					if (teamSize == 1 || teamGroup || leader()) walk();      // (one call site: the walk is the bulk of this function's code)

@@ -442,6 +442,7 @@ namespace orc
 				np.wid = lastSeqId;
 				if (isSingle(cur)) { np.combineSocket = cur.combine_socket; np.ownFormId = (uint16_t)ownFormId; }
 			};
+			{ static const bool tb = std::getenv("ORC_TRACE_BIG") != nullptr; if (tb && cont.mode != 2) { size_t mx = 0, tot = 0; for (auto& b : cont.buckets) { mx = std::max(mx, b.size()); tot += b.size(); } std::fprintf(stderr, "[cont] mode %d total %zu maxbucket %zu\n", cont.mode, tot, mx); } }
 			if (std::getenv("ORC_TRACE_CAND")) std::fprintf(stderr, "[cand] node %zu cand %d mode %d E %zu buckets %zu %zu %zu %zu\n", nodeIdx, curId, cont.mode, cont.mode == 2 ? cont.top1.size() : cont.buckets[0].size() + cont.buckets[1].size() + cont.buckets[2].size() + cont.buckets[3].size(), cont.buckets[0].size(), cont.buckets[1].size(), cont.buckets[2].size(), cont.buckets[3].size());
 			if (cont.mode == 2) { for (auto& p : cont.top1) emit(p); }      // libstdc++ iteration order, as in the reference
 			else for (auto& bk : cont.buckets) for (auto& p : bk) emit(p);

@@ -136,3 +136,15 @@ def test_hostsim_sbg_golden_subset():
         pytest.skip("tests/hostsim/libpipeline_sim32.so or the SkipBigram model image missing: run __graft_entry__.build()")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "sbg", "--files", "inputs_written,inputs_web", "--stride", "12", "--maxlen", "70"], capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and "0 mismatches" in r.stdout and "sbg: 0 sentences" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_knlm_kernel_follows_the_reference_container_behaviour():
+    """once a bucket of a path container holds 64 states the reference's insertOptimized stops finding its
+    first 64 entries and appends states again.  On the bench sentences where that changes the per-node path counts, the simulated Knlm
+    kernel (parallel insert + the item-by-item redo of such groups) must give the counts of the oracle's default (reference-behaviour)
+    mode, not those of its ORC_BUCKET_SEARCH_ALL mode (scripts/container_check.py)."""
+    import subprocess, sys
+    if not os.path.exists(LIB) or not os.path.exists(IMAGE):
+        pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "container_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "6/6 sentences follow the reference's behaviour" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
