@@ -26,7 +26,7 @@ CONFIGS = {
     4: dict(model="knlm", batch=65536, typo="basic", typo_frac=0.3, rotate=1, steps=5, scaling="weak"),
     5: dict(model="cong", batch=1 << 20, typo=None, typo_frac=0.0, rotate=1, steps=3, scaling="strong"),
     # not a BASELINE.json config: the SkipBigram model type.  Its kernel inserts paths one at a time (viterbi.cu
-    # sbgInsertRound): correct on hardware, but 11 passes over 2048 sentences did not finish in 600 s (round 2, GPU call L) - no measured line yet
+    # exactInsertRound): correct on hardware, but 11 passes over 2048 sentences did not finish in 600 s (round 2, GPU call L) - no measured line yet
     6: dict(model="sbg", batch=256, typo=None, typo_frac=0.0, rotate=1, steps=1, scaling="weak"),
 }
 BLOCK = 8192      # synthetic sentences are generated in seeded blocks of 8192 (block b: seed SEED + b)

@@ -42,7 +42,7 @@
 // A CoNg path keeps CoNgramState::contextIdx in the DPath::wid_feat slot (the feature word is re-read from morphs[wid]).
 // KB_SBG=1 -> viterbi_sbg_kernel for SkipBigram images (Knlm + an 8-token history per path, src/SkipBigramModel.hpp:113-185).  Its states
 // rarely merge, which puts the path containers of the reference into the regime where BucketedHashContainer::insertOptimized behaves
-// unlike its comments (see sbgInsertRound); that is restated exactly, item by item, so the build takes the per-candidate path
+// unlike its comments (see exactInsertRound); that is restated exactly, item by item, so the build takes the per-candidate path
 // `evalCand` for every candidate and leaves the item pipeline to the other two builds.
 #ifndef KB_CONG
 #define KB_CONG 0

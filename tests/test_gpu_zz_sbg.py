@@ -2,7 +2,7 @@
 called through the C ABI, against the golden vectors of the unmodified reference (ModelType::sbg, tests/golden/sbg_*: one fresh
 thread per sentence, see tests/golden/make_golden.py) and the oracle restatement.  Bit-exact: morpheme ids, tags, positions, lengths
 and every float score - the device restates the AVX2 exp polynomial, glibc's logf and the reference's path containers as they behave
-(kiwi_b200/csrc/sbg_math.h, viterbi.cu sbgInsertRound)."""
+(kiwi_b200/csrc/sbg_math.h, viterbi.cu exactInsertRound)."""
 import numpy as np
 import pytest
 from tests.goldenio import read_golden, read_inputs

@@ -127,7 +127,7 @@ def test_hostsim_full_golden_sweep(mode):
 
 def test_hostsim_sbg_golden_subset():
     """The SkipBigram build of viterbi.cu (viterbi_sbg_kernel: Knlm + 8-token history, sbg_math.h, the item-by-item path container
-    sbgInsertRound) through the simulator on every twelfth sentence of inputs_written / inputs_web (the shorter ones): tokens identical and scores bit-exact
+    exactInsertRound) through the simulator on every twelfth sentence of inputs_written / inputs_web (the shorter ones): tokens identical and scores bit-exact
     against the unmodified reference's ModelType::sbg vectors.  (The whole files - 33 + 158 sentences, 0 mismatches - take ten minutes:
     `python scripts/hostsim_sweep.py sbg --files inputs_written,inputs_web`.)"""
     import subprocess, sys
