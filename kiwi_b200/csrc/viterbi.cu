@@ -151,6 +151,9 @@ namespace KB_VIT_NS
 #define KB_VIT_WARPS 4
 #endif
 	static constexpr uint32_t WARPS_PER_BLOCK = KB_VIT_WARPS;
+#ifndef KB_EXACT_FROM
+#define KB_EXACT_FROM 64u      // states per bucket from which a group is re-run item by item (tests lower it to drive that path through every sentence)
+#endif
 	static constexpr uint32_t MAX_RESULTS = 16;
 
 	__device__ __forceinline__ float asFloat(int32_t v) { return __int_as_float(v); }
@@ -1623,9 +1626,6 @@ namespace KB_VIT_NS
 			htBase = top; htCount = 0;
 		}
 
-#ifndef KB_EXACT_FROM
-#define KB_EXACT_FROM 64u      // (tests lower it to drive the redo path through every golden sentence)
-#endif
 		// has a bucket of one of the group's containers reached 64 (distinct) states?  Segments: candidate k's entries follow candidate k - 1's,
 		// sm->candNew[k] of them, in first-insertion order
 		__device__ __noinline__ bool groupNeedsExact(uint32_t groupBase, uint32_t gcount, uint32_t mode)
@@ -2309,7 +2309,7 @@ namespace KB_VIT_NS
 					// The parallel insert above is the reference's container as long as no bucket reaches 64 states (0.02 % of the containers
 					// of the bench batches do).  Beyond that the reference's insertOptimized behaves differently (exactInsertRound): the
 					// group's output is dropped and its candidates are evaluated again, one after the other, item by item.
-					if (mode != 2 && teamSize == 1 && groupNeedsExact(myBase, gcount, mode))
+					if (mode != 2 && teamSize == 1 && __any_sync(FULL, lane < gcount && sm->candNew[lane] >= KB_EXACT_FROM) && groupNeedsExact(myBase, gcount, mode))
 					{
 						redoGroupExact(node, fc, myBase, gcount, inEnd, mode, spaceBefore);
 						if (err) return;
