@@ -139,6 +139,7 @@ namespace KB_VIT_NS
 		CandMask cmask[GROUP];                  // per candidate: which path classes survive the filter / fail the soft condition / override firstWid
 		uint32_t candNew[GROUP];                // entries created per candidate of the current group
 		uint32_t fwTab[FWTAB_CAP];              // first-wid overrides of socket chunks (PathEvaluator.hpp:590), index 0 unused
+		uint32_t exactInsert;                   // != 0: evalCand inserts item by item (exactInsertRound) - set while a group is re-run (redoGroupExact)
 #if KB_CONG
 		int32_t dots[KB_CG_UCAP][33];           // (unique context, candidate of the group) -> sum u8*s8 - hsum, from the tensor-core tiles
 		uint32_t uctx[KB_CG_UCAP];              // the node's unique context ids (regular incoming paths)
@@ -518,7 +519,6 @@ namespace KB_VIT_NS
 		uint8_t uniq[2]; uint32_t nUniq;
 		uint16_t* ht; uint32_t htUsed;
 		uint32_t top1Buckets = 1;           // bucket count of the reference's `top1` unordered_set, per sentence (unordered_emu.h)
-		bool exactInsert = KB_SBG != 0;     // evalCand inserts item by item (exactInsertRound): always in the SkipBigram build, during a group redo in the others
 #if KB_SBG
 		uint32_t sbIdxCap = 0;              // slots of the current candidate's `top1` index at the end of the sentence's pool region (0 = none yet)
 #endif
@@ -1130,7 +1130,7 @@ namespace KB_VIT_NS
 				const uint32_t prevRoot = pp.root_id;
 				const unsigned vmask = __ballot_sync(FULL, valid);
 				if (!vmask) continue;
-				if (KB_SBG || (exactInsert && mode != 2))
+				if (KB_SBG || (mode != 2 && sm->exactInsert))
 				{
 					// every valid lane prepares its path record; the container takes them one at a time, in pair order (exactInsertRound)
 					PathT np;
@@ -1427,6 +1427,7 @@ namespace KB_VIT_NS
 		{
 			uint32_t nodeIdx; uint32_t inBeg; float ignoreCondScore; float nodeTypoCost; uint32_t ownOff, ownLen;
 			uint32_t ownFw;      // left-form part of the filter word of a path that keeps the node's own form
+			uint32_t inEnd, mode, spaceBefore;      // (for the cold group redo: kept here, not in registers)
 #if KB_CONG
 			uint32_t epFirst, dotMask;      // epilogue of the node's gather GEMM; candidates of the current group that have a column in sm->dots
 #endif
@@ -1958,14 +1959,16 @@ namespace KB_VIT_NS
 
 #if !KB_SBG
 		// (cold) the group's candidates once more, one after the other, with the item-by-item container (see evaluate)
-		__device__ __noinline__ void redoGroupExact(const DNode& node, const FlushCtx& fc, uint32_t groupBase, uint32_t gcount, uint32_t inEnd, uint32_t mode, bool spaceBefore)
+		__device__ __noinline__ void redoGroupExact(const DNode& node, const FlushCtx& fc, uint32_t groupBase, uint32_t gcount)
 		{
+			const uint32_t inEnd = fc.inEnd, mode = fc.mode; const bool spaceBefore = fc.spaceBefore != 0;
 #ifdef KB_HOSTSIM
 			if (lane == 0 && std::getenv("HS32_TRACE_REDO")) std::fprintf(stderr, "[redo] node %u mode %u group of %u\n", fc.nodeIdx, mode, gcount);
 #endif
 			top = groupBase;
 			resetIndex();
-			exactInsert = true;
+			if (lane == 0) sm->exactInsert = 1;
+			__syncwarp();
 			#pragma unroll 1
 			for (uint32_t k = 0; k < gcount; ++k)
 			{
@@ -1980,14 +1983,15 @@ namespace KB_VIT_NS
 					g.epFirst = fc.epFirst; g.dotCol = ((fc.dotMask >> k) & 1u) ? (int32_t)k : -1;
 #endif
 					evalGeneralCand(k, node, g);
-					if (err) { exactInsert = false; return; }
+					if (err) { __syncwarp(); if (lane == 0) sm->exactInsert = 0; __syncwarp(); return; }
 				}
 				__syncwarp();
 				if (lane == 0) { sm->candNew[k] = top - before; if (cls == CLS_ITEM) sm->cdyn[k].cls = CLS_GENERAL; }      // capacity and order are final
 				__syncwarp();
 				resetIndex();
 			}
-			exactInsert = false;
+			if (lane == 0) sm->exactInsert = 0;
+			__syncwarp();
 		}
 #endif
 
@@ -2031,6 +2035,7 @@ namespace KB_VIT_NS
 #endif
 			FlushCtx fc;
 			fc.nodeIdx = nodeIdx; fc.inBeg = inBeg; fc.nodeTypoCost = node.typo_cost; fc.ownOff = ownOff; fc.ownLen = ownLen; fc.ownFw = 0;
+			fc.inEnd = inEnd; fc.mode = mode; fc.spaceBefore = spaceBefore ? 1u : 0u;
 			if (itemOK) stagePaths(nodeIdx, inBeg, P);
 			const bool itemOK2 = itemOK && !classOverflow;
 			if (ownLen) { uint16_t ol; uint8_t op; leftFeat(ownOff, ownLen, 0, 0, ol, op); fc.ownFw = fwOfLeft(ol, op); }
@@ -2305,13 +2310,13 @@ namespace KB_VIT_NS
 						resetIndex();
 					}
 					flushItems(fc); if (err) return;
-#if !KB_SBG
+#if !KB_SBG && !defined(KB_NO_EXACT_REDO)
 					// The parallel insert above is the reference's container as long as no bucket reaches 64 states (0.02 % of the containers
 					// of the bench batches do).  Beyond that the reference's insertOptimized behaves differently (exactInsertRound): the
 					// group's output is dropped and its candidates are evaluated again, one after the other, item by item.
 					if (mode != 2 && teamSize == 1 && __any_sync(FULL, lane < gcount && sm->candNew[lane] >= KB_EXACT_FROM) && groupNeedsExact(myBase, gcount, mode))
 					{
-						redoGroupExact(node, fc, myBase, gcount, inEnd, mode, spaceBefore);
+						redoGroupExact(node, fc, myBase, gcount);
 						if (err) return;
 					}
 #endif
@@ -2824,6 +2829,8 @@ namespace KB_VIT_NS
 #endif
 		v.splitComplex = (bv.match_options >> 22) & 1; v.splitSaisiot = (bv.match_options >> 25) & 1; v.mergeSaisiot = (bv.match_options >> 26) & 1;
 		v.htClear();
+		if (lane == 0) smAll[wib].exactInsert = 0;
+		__syncwarp();
 #if KB_TMA_ROWS
 #if KB_QUEUE
 		v.pfPhase = pfPhaseKeep; v.curBuf = curBufKeep;      // the warp's transaction barriers live across its sentences
