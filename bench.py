@@ -34,6 +34,7 @@ BLOCK = 8192      # synthetic sentences are generated in seeded blocks of 8192 (
 
 def image_path(model): return os.path.join(ROOT, "oracle", "_ref", "models", model + "_small.img")
 def ref_model_dir(model): return os.path.join(ROOT, "oracle", "_ref", "models", model + "_small")
+def typo_image_path(tset): return os.path.join(ROOT, "oracle", "_ref", "models", "typo_%s.img" % tset)
 
 
 def workload_string(cfg, cid):
@@ -222,8 +223,7 @@ def main():
     kw = kiwi_b200.Kiwi(image_bytes=image_bytes, devices=list(range(args.gpus))) if inproc else kiwi_b200.Kiwi(image_bytes=image_bytes, device=local_rank)
     typo = None
     if cfg["typo"]:
-        from tests.orc import TYPO_IMAGES
-        typo = kiwi_b200.PreparedTypo(path=TYPO_IMAGES[cfg["typo"]])
+        typo = kiwi_b200.PreparedTypo(path=typo_image_path(cfg["typo"]))      # (a flat typo image next to the model images; nothing of the oracle is imported on the product arm)
     option = kiwi_b200.default_option(typo=typo)
 
     # ---- synthetic batches.  weak scaling: every rank works on `batch` sentences per step (its own seeds);
