@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
 
 def work_counters(cfg, cid, texts, seed):
     """Per-sentence algorithmic bytes from the instrumented oracle: committed under profiles/counters_r2.json for the bench batches
-    (scripts/make_counters.py, every rotating seed); recomputed on a 256-sentence sample when absent."""
+    (scripts/make_counters.py, every rotating seed); none committed for the workload: no roofline figure (the oracle is not run here)."""
     from kiwi_b200 import bytemodel
     path = os.path.join(ROOT, "profiles", "counters_r2.json")
     key = "cfg%d" % cid
@@ -111,15 +111,8 @@ def work_counters(cfg, cid, texts, seed):
         if key in d:
             c = d[key]
             return c, c["lattice_bytes_per_sentence"], c["viterbi_bytes_per_sentence"], "profiles/counters_r2.json[%s] (%s)" % (key, c.get("coverage", ""))
-    from tests.orc import Oracle, TypoOracle, TYPO_IMAGES
-    o = Oracle(image_path(cfg["model"]))
-    if cfg["typo"]: o.set_typo(TypoOracle(TYPO_IMAGES[cfg["typo"]]))
-    for s in texts[:256]: o.analyze(s)
-    c = o.work_counters()
-    if cfg["model"] == "cong": c.update(o.cong_counters())
-    o.close()
-    extra = bytemodel.cong_bytes(c) if cfg["model"] == "cong" else 0.0
-    return c, bytemodel.lattice_bytes(c) / c["sentences"], (bytemodel.viterbi_bytes(c) + extra) / c["sentences"], "oracle sample of 256 sentences"
+    # (no oracle on the product arm: a workload without committed counters reports no algorithmic-byte roofline)
+    return {"sentences": 1}, None, None, "no committed work counters for this workload (scripts/make_counters.py writes profiles/counters_r2.json)"
 
 
 def run_reference_cpu(cfg, texts, threads, repeats, single_sample=0, dump=None):
@@ -330,7 +323,7 @@ def main():
     c, lat_b, vit_b, csrc = work_counters(cfg, args.config, batches[0][0], SEED)
     kernel = {"knlm": "viterbi_kernel", "cong": "viterbi_cong_kernel", "sbg": "viterbi_sbg_kernel"}[cfg["model"]]
     vit_per_step_ms = ms_vit / steps if steps else 0.0
-    achieved = vit_b * n_local / (vit_per_step_ms / 1000.0) / 1e9 if vit_per_step_ms else None
+    achieved = vit_b * n_local / (vit_per_step_ms / 1000.0) / 1e9 if (vit_per_step_ms and vit_b) else None
     prof = {}
     pp = os.path.join(ROOT, "profiles", "ncu_r2.json")
     if os.path.exists(pp): prof = json.load(open(pp)).get(kernel, {})
