@@ -20,7 +20,7 @@ _H = {}      # one simulator handle per worker process and mode (opening the 135
 
 def _handle(mode):
     if mode in _H: return _H[mode]
-    lib = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libpipeline_sim32.so"))
+    lib = C.CDLL(os.path.join(ROOT, "tests", "hostsim", os.environ.get("HS32_LIB", "libpipeline_sim32.so")))      # HS32_LIB=libpipeline_sim32_redo.so: forced group redo
     lib.hs32_open.restype = C.c_void_p; lib.hs32_open.argtypes = [C.c_char_p]
     lib.hs32_set_typo.argtypes = [C.c_void_p, C.c_char_p, C.c_float]
     lib.hs32_analyze.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32] + [C.c_void_p] * 5 + [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_void_p]

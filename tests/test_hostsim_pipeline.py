@@ -148,3 +148,16 @@ def test_knlm_kernel_follows_the_reference_container_behaviour():
         pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "container_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "6/6 sentences follow the reference's behaviour" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_forced_group_redo_keeps_every_golden_sentence():
+    """tests/hostsim/libpipeline_sim32_redo.so = the Knlm kernel built with KB_EXACT_FROM=4: every group whose containers hold 4 states is
+    evaluated a second time item by item (redoGroupExact / exactInsertRound - below 64 states per bucket that must reproduce the parallel
+    insert exactly).  All 1 273 golden sentences: tokens identical, scores bit-exact."""
+    import subprocess, sys
+    redo = os.path.join(ROOT, "tests", "hostsim", "libpipeline_sim32_redo.so")
+    if not os.path.exists(redo) or not os.path.exists(IMAGE):
+        pytest.skip("tests/hostsim/libpipeline_sim32_redo.so or the model image missing: run __graft_entry__.build()")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "plain"], capture_output=True, text=True, timeout=1500,
+                       env=dict(os.environ, HS32_LIB="libpipeline_sim32_redo.so"))
+    assert r.returncode == 0 and "1273 sentences, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
