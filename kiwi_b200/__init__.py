@@ -38,9 +38,9 @@ class AnalyzeOption(C.Structure):
                 ("dialect_cost", C.c_float), ("typo_transformer", C.c_void_p), ("typo_threshold", C.c_float)]
 
 
-def default_option(match_options: int = MATCH_ALL_WITH_NORMALIZING, typo: "PreparedTypo" = None, typo_threshold: float = 2.5) -> AnalyzeOption:
-    """AnalyzeOption{match} / .withTypoTransformer(typo, typo_threshold) (include/kiwi/Kiwi.h:69-133); keep `typo` alive while the option is used"""
-    return AnalyzeOption(match_options, None, 0, 0, 3.0, typo.handle if typo is not None else None, typo_threshold)
+def default_option(match_options: int = MATCH_ALL_WITH_NORMALIZING, typo: "PreparedTypo" = None, typo_threshold: float = 2.5, open_ending: bool = False) -> AnalyzeOption:
+    """AnalyzeOption{match} / .withTypoTransformer(typo, typo_threshold) / .openEnding (include/kiwi/Kiwi.h:69-133); keep `typo` alive while the option is used"""
+    return AnalyzeOption(match_options, None, 1 if open_ending else 0, 0, 3.0, typo.handle if typo is not None else None, typo_threshold)
 
 
 TYPO_WITHOUT, TYPO_BASIC, TYPO_CONTINUAL, TYPO_BASIC_WITH_CONTINUAL, TYPO_LENGTHENING, TYPO_BASIC_WITH_CONTINUAL_AND_LENGTHENING, TYPO_DIALECT = range(7)   # capi.h:484-492

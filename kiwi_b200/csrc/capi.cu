@@ -124,12 +124,14 @@ static std::string utf16To8(const std::u16string& s)
 	}
 	return out;
 }
+// the kernels' option word: the reference's Match bits (include/kiwi/Types.h) + bit 31 = AnalyzeOption::openEnding (no Match flag lives there)
+static uint32_t optionWord(const kiwi_analyze_option_t& o) { return ((uint32_t)o.match_options & 0x7FFFFFFFu) | (o.open_ending ? 0x80000000u : 0u); }
+
 static void checkOption(const kiwi_analyze_option_t& o, int topN, kiwi_pretokenized_h pt)
 {
 	if (topN != 1) throw std::invalid_argument("kiwi_b200 implements the top_n == 1 path only");
 	if (o.blocklist) throw std::invalid_argument("blocklist is outside the kiwi_b200 hot path");
 	if (o.allowed_dialects) throw std::invalid_argument("dialects other than standard are outside the kiwi_b200 hot path");
-	if (o.open_ending) throw std::invalid_argument("open_ending is not supported by this build");
 	if (pt) throw std::invalid_argument("pretokenized spans are outside the kiwi_b200 hot path");
 	const uint32_t unsupported = (3u << 8) | (1u << 17) | (1u << 18) | (1u << 19) | (1u << 20) | (1u << 21) | (1u << 24) | (1u << 26) | (1u << 27) | (1u << 30);
 	if ((uint32_t)o.match_options & unsupported) throw std::invalid_argument("match_options contain a flag outside the kiwi_b200 hot path (oov models, join*, compatibleJamo, mergeSaisiot, useOldSplitter)");
@@ -210,7 +212,7 @@ static void analyzeSharded(kiwi_s* h, const uint16_t* text, const uint32_t* offs
 	if (N == 1 || n < 2 * N)
 	{
 		TypoScope ts{ h->engine.get(), option };
-		h->engine->analyze(text, offsets, n, (uint32_t)option.match_options, out);
+		h->engine->analyze(text, offsets, n, optionWord(option), out);
 		return;
 	}
 	if (h->shardOut.size() != N) h->shardOut.resize(N);
@@ -234,7 +236,7 @@ static void analyzeSharded(kiwi_s* h, const uint16_t* text, const uint32_t* offs
 			for (uint32_t i = r; i < n; i += N) { sub.insert(sub.end(), text + offsets[i], text + offsets[i + 1]); off.push_back((uint32_t)sub.size()); }
 			const auto t1 = Clock::now();
 			TypoScope ts{ e, option };
-			e->analyze(sub.data(), off.data(), (uint32_t)off.size() - 1, (uint32_t)option.match_options, part[r]);
+			e->analyze(sub.data(), off.data(), (uint32_t)off.size() - 1, optionWord(option), part[r]);
 			stats[r] = e->last;
 			msGather[r] = std::chrono::duration<double, std::milli>(t1 - t0).count();
 			msEngine[r] = std::chrono::duration<double, std::milli>(Clock::now() - t1).count();
@@ -539,7 +541,7 @@ kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_
 		std::lock_guard<std::mutex> lk(handle->mtx);
 		BatchOutput& bo = handle->callOut;
 		TypoScope ts{ handle->engine.get(), option };
-		handle->engine->analyze(text, off, 1, (uint32_t)option.match_options, bo);
+		handle->engine->analyze(text, off, 1, optionWord(option), bo);
 		return makeRes(handle, text, len, bo, 0, (uint32_t)option.match_options);
 	}
 	catch (const std::exception& e) { setError(e); return nullptr; }
@@ -657,7 +659,7 @@ float kiwi_b200_analyze_device(kiwi_h handle, const void* d_text, const void* d_
 		checkOption(option, 1, nullptr);
 		std::lock_guard<std::mutex> lk(handle->mtx);
 		TypoScope ts{ handle->engine.get(), option };
-		const float ms = handle->engine->analyzeDevice(reinterpret_cast<const uint16_t*>(d_text), reinterpret_cast<const uint32_t*>(d_offsets), (uint32_t)n, total_units, (uint32_t)option.match_options, out_tokens);
+		const float ms = handle->engine->analyzeDevice(reinterpret_cast<const uint16_t*>(d_text), reinterpret_cast<const uint32_t*>(d_offsets), (uint32_t)n, total_units, optionWord(option), out_tokens);
 		if (out_launches) *out_launches = handle->engine->last.kernelLaunches;
 		return ms;
 	}

@@ -2861,7 +2861,8 @@ namespace KB_VIT_NS
 			else { v.uniq[0] = min(retSp[0], retSp[1]); v.uniq[1] = max(retSp[0], retSp[1]); v.nUniq = 2; }
 
 			PathRes res[MAX_RESULTS];
-			const uint32_t K = v.findBestPath(ch, res, false);
+			// AnalyzeOption::openEnding (bit 31 of the option word, capi.cu): no end-of-sentence step on the chunk that ends the text (src/Kiwi.cpp:1122-1131)
+			const uint32_t K = v.findBestPath(ch, res, (bv.match_options >> 31) != 0 && ch.end == normLen);
 
 			// ---- insertPathIntoResults, topN == 1 (src/Kiwi.cpp:629-782), all lanes redundantly (team mode: the first warp's lanes)
 			auto stitch = [&]()

@@ -61,6 +61,7 @@ int main(int argc, char** argv)
 		std::string line;
 		size_t idx = 0;
 		AnalyzeOption option;
+		if (getenv("KB_OPEN_ENDING")) option.openEnding = true;      // (vectors open_<name>: AnalyzeOption::openEnding)
 		PreparedTypoTransformer ptt;
 		if (const char* ty = getenv("KB_TYPO"))
 		{

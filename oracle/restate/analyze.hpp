@@ -70,6 +70,7 @@ namespace orc
 			}
 		}
 
+		bool openEnding = false;
 		AnalyzeResult analyze(const u16* text, size_t len)
 		{
 			AnalyzeResult res;
@@ -91,7 +92,8 @@ namespace orc
 				ch.end = splitEnd;
 				if (ch.nodes.size() > 2)
 				{
-					ch.paths = viterbi.findBestPath(spStatesByRet, norm.data(), ch.nodes.data(), ch.nodes.size(), false, matchOptions);
+					// AnalyzeOption::openEnding: no end-of-sentence step on the chunk that ends the text (src/Kiwi.cpp:1122-1131)
+					ch.paths = viterbi.findBestPath(spStatesByRet, norm.data(), ch.nodes.data(), ch.nodes.size(), openEnding && splitEnd == norm.size(), matchOptions);
 					// insertPathIntoResults, topN == 1
 					const auto& pathes = ch.paths;
 					std::vector<size_t> parentMap;

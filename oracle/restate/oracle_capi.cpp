@@ -157,6 +157,8 @@ void orc_typo_close(void* p) { delete reinterpret_cast<OrcTypo*>(p); }
 
 // AnalyzeOption::withTypoTransformer (include/kiwi/Kiwi.h:127-133): analyse with a typo lattice from now on (typo == nullptr: off).
 // The typo handle must outlive the analyzer's use of it.
+void orc_set_open_ending(void* p, int on) { reinterpret_cast<OrcHandle*>(p)->an->openEnding = on != 0; }
+
 void orc_set_typo(void* p, void* typo, float threshold)
 {
 	auto* h = reinterpret_cast<OrcHandle*>(p);

@@ -70,13 +70,13 @@ def work(args):
         return len(idxs), bad
     cap = 8192
     morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
-    texts = read_inputs(name); gold = read_golden(("cong_" if cong else "") + ("sbg_" if mode == "sbg" else "") + ("typo6_" if typo else "") + name)
+    texts = read_inputs(name); gold = read_golden(("cong_" if cong else "") + ("sbg_" if mode == "sbg" else "") + ("open_" if mode == "open" else "") + ("typo6_" if typo else "") + name)
     bad = []
     for i in idxs:
         t, g = texts[i], gold[i]
         u = np.ascontiguousarray(np.frombuffer(t.encode("utf-16-le", "surrogatepass"), dtype="<u2"))
         s = C.c_float(0); nn = C.c_int(0)
-        n = lib.hs32_analyze(h, u.ctypes.data, len(u), MATCH_ALL, morph.ctypes.data, tag.ctypes.data, pos.ctypes.data, ln.ctypes.data, sc.ctypes.data, cap, C.byref(s), C.byref(nn), None)
+        n = lib.hs32_analyze(h, u.ctypes.data, len(u), MATCH_ALL | (0x80000000 if mode == "open" else 0), morph.ctypes.data, tag.ctypes.data, pos.ctypes.data, ln.ctypes.data, sc.ctypes.data, cap, C.byref(s), C.byref(nn), None)
         if n < 0: bad.append((name, i, "status %d" % n)); continue
         got = [(int(morph[k]), int(tag[k]), int(pos[k]), int(ln[k])) for k in range(n)]
         if got != [x[:4] for x in g["tokens"]]: bad.append((name, i, "tokens")); continue
@@ -86,7 +86,7 @@ def work(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", nargs="?", default="plain", choices=["plain", "typo", "cong", "sbg"])
+    ap.add_argument("mode", nargs="?", default="plain", choices=["plain", "typo", "cong", "sbg", "open"])
     ap.add_argument("--files", default="inputs_web,inputs_written,inputs_ref_tests,inputs_dialect_typos")
     ap.add_argument("--stride", type=int, default=1)
     ap.add_argument("--maxlen", type=int, default=400, help="skip longer inputs (the pathological reference tests take minutes)")

@@ -33,6 +33,15 @@ for model, mtype, prefix in [("knlm_small", "knlm", ""), ("cong_small", "cong", 
         with gzip.GzipFile(os.path.join(HERE, prefix + name + ".golden.txt.gz"), "wb", mtime=0) as f:
             f.write(data)
         manifest["files"][prefix + name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
+# AnalyzeOption::openEnding (no end-of-sentence step on the chunk that ends the text) with the Knlm model: open_<name>.golden.txt.gz
+for name in ["inputs_written", "inputs_web"]:
+    tmp = os.path.join("/tmp", "open_" + name + ".golden.txt")
+    env = dict(os.environ, KIWI_ARCH_TYPE="avx2", KB_MODEL_TYPE="knlm", KB_OPEN_ENDING="1")
+    subprocess.run([os.path.join(REFDIR, "dump_golden"), os.path.join(REFDIR, "models", "knlm_small"), os.path.join(HERE, name + ".txt"), tmp], check=True, env=env, timeout=600)
+    data = open(tmp, "rb").read()
+    with gzip.GzipFile(os.path.join(HERE, "open_" + name + ".golden.txt.gz"), "wb", mtime=0) as f:
+        f.write(data)
+    manifest["files"]["open_" + name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
 # typo-tolerant analysis (BASELINE.json config 4: AnalyzeOption::typoTransformer = basicTypoSet.prepare(true), typoThreshold 2.5,
 # typoCostWeight 6) with the Knlm model: typo6_<name>.golden.txt.gz
 for name in ["inputs_ref_tests", "inputs_web", "inputs_written", "inputs_dialect_typos"]:

@@ -72,6 +72,11 @@ class Oracle:
             raise RuntimeError("oracle lattice failed")
         return rows[:n].copy()
 
+    def set_open_ending(self, on=True):
+        """AnalyzeOption::openEnding (no end-of-sentence step on the last chunk)"""
+        self.lib.orc_set_open_ending.argtypes = [C.c_void_p, C.c_int]
+        self.lib.orc_set_open_ending(self.h, 1 if on else 0)
+
     def counters(self):
         out = np.zeros(6, np.uint64)
         self.lib.orc_counters(self.h, out.ctypes.data)

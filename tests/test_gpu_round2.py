@@ -176,6 +176,22 @@ def test_small_passes_overlap_and_keep_order():
     assert (outs[0]["off"] == outs[1]["off"]).all() and outs[0]["tok"].tobytes() == outs[1]["tok"].tobytes() and (outs[0]["sc"] == outs[1]["sc"]).all()
 
 
+def test_open_ending_matches_reference_golden(kiwi):
+    """AnalyzeOption::openEnding through the C ABI (kiwi_analyze_option_t::open_ending, capi.h:662-670): tokens and float scores of
+    inputs_written against the unmodified reference's open-ending vectors (tests/golden/open_inputs_written)."""
+    from tests.goldenio import read_golden, read_inputs
+    texts = read_inputs("inputs_written"); gold = read_golden("open_inputs_written")
+    res = kiwi.analyze_batch(texts, kiwi_b200.default_option(open_ending=True))
+    plain = kiwi.analyze_batch(texts)
+    differs = 0
+    for i, (t, g) in enumerate(zip(texts, gold)):
+        got = res.sentence(i)
+        assert [(int(k["morph_id"]), int(k["tag"]), int(k["position"]), int(k["length"])) for k in got] == [x[:4] for x in g["tokens"]], (i, t)
+        assert np.float32(res.scores[i]) == np.float32(g["score"]), (i, t, float(res.scores[i]), g["score"])
+        differs += int(res.scores[i] != plain.scores[i])
+    assert differs > len(texts) // 2      # (the end-of-sentence step is really gone)
+
+
 def test_utf8_entry_points_and_position_accessors(kiwi, oracle):
     """kiwi_analyze (UTF-8), kiwi_analyze_m (UTF-8 reader) and kiwi_res_word_position / kiwi_res_sent_position (capi.h:698, 724, 897, 907)"""
     lib = kiwi_b200.load_library()

@@ -161,3 +161,13 @@ def test_forced_group_redo_keeps_every_golden_sentence():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "plain"], capture_output=True, text=True, timeout=1500,
                        env=dict(os.environ, HS32_LIB="libpipeline_sim32_redo.so"))
     assert r.returncode == 0 and "1273 sentences, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_hostsim_open_ending_matches_reference():
+    """AnalyzeOption::openEnding through the simulated kernels (bit 31 of the option word): all 33 + 158 sentences of inputs_written /
+    inputs_web against the unmodified reference's open-ending vectors, tokens identical and scores bit-exact."""
+    import subprocess, sys
+    if not os.path.exists(LIB) or not os.path.exists(IMAGE):
+        pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "open", "--files", "inputs_written,inputs_web"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "191 sentences, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
