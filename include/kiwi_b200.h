@@ -113,6 +113,14 @@ kiwi_typo_h kiwi_typo_get_basic(void);
 int kiwi_typo_close(kiwi_typo_h handle);
 kiwi_prepared_typo_h kiwi_typo_prepare(kiwi_typo_h handle);
 int kiwi_prepared_typo_close(kiwi_prepared_typo_h handle);
+
+/* ---- morpheme sets: kiwi_analyze_option_t::blocklist (capi.h:660, 1243-1263; src/capi/kiwi_c.cpp:851-864, 1780-1825) --------------
+ * kiwi_morphset_add[_w] resolves (form, tag) like Kiwi::findMorphemes (src/Kiwi.cpp:1281-1297; tag NULL = any tag) and returns the number
+ * of morphemes added; the analysis skips every candidate for which Morpheme::hasMorpheme(blocklist) holds (src/PathEvaluator.hpp:385). */
+kiwi_morphset_h kiwi_new_morphset(kiwi_h handle);
+int kiwi_morphset_add(kiwi_morphset_h handle, const char* form, const char* tag);
+int kiwi_morphset_add_w(kiwi_morphset_h handle, const kchar16_t* form, const char* tag);
+int kiwi_morphset_close(kiwi_morphset_h handle);
 /* additive: a prepared transformer straight from a flat typo image (file / memory) */
 kiwi_prepared_typo_h kiwi_b200_typo_load(const char* typo_image_path);
 kiwi_prepared_typo_h kiwi_b200_typo_from_image(const void* bytes, size_t size);
@@ -245,6 +253,9 @@ int kiwi_b200_native_knlm(const char* sj_knlm_path, void** out_bytes, uint64_t* 
 /*   cong.mdl        CoNgramModel<..., windowSize 0, quantized> constructor, src/CoNgramModel.cpp:425-790 (8-bit embedding rows) */
 int kiwi_b200_native_cong(const char* cong_mdl_path, void** out_bytes, uint64_t* out_size);
 int kiwi_b200_native_sbg(const char* skipbigram_mdl_path, void** out_bytes, uint64_t* out_size);
+/* host-only helper behind kiwi_morphset_add (no GPU needed): the morpheme ids (form, tag) resolves to in a model image; returns the count
+ * (at most `cap` ids are written), -1 on error */
+int kiwi_b200_image_find_morphemes(const void* image_bytes, uint64_t size, const kchar16_t* form, const char* tag, uint32_t* out_ids, int cap);
 const char* kiwi_b200_native_error(void);
 
 #ifdef __cplusplus

@@ -38,9 +38,40 @@ class AnalyzeOption(C.Structure):
                 ("dialect_cost", C.c_float), ("typo_transformer", C.c_void_p), ("typo_threshold", C.c_float)]
 
 
-def default_option(match_options: int = MATCH_ALL_WITH_NORMALIZING, typo: "PreparedTypo" = None, typo_threshold: float = 2.5, open_ending: bool = False) -> AnalyzeOption:
-    """AnalyzeOption{match} / .withTypoTransformer(typo, typo_threshold) / .openEnding (include/kiwi/Kiwi.h:69-133); keep `typo` alive while the option is used"""
-    return AnalyzeOption(match_options, None, 1 if open_ending else 0, 0, 3.0, typo.handle if typo is not None else None, typo_threshold)
+def default_option(match_options: int = MATCH_ALL_WITH_NORMALIZING, typo: "PreparedTypo" = None, typo_threshold: float = 2.5, open_ending: bool = False,
+                   blocklist: "MorphSet" = None) -> AnalyzeOption:
+    """AnalyzeOption{match} / .withTypoTransformer(typo, typo_threshold) / .openEnding / .blocklist (include/kiwi/Kiwi.h:69-133); keep `typo` and
+    `blocklist` alive while the option is used"""
+    return AnalyzeOption(match_options, blocklist.handle if blocklist is not None else None, 1 if open_ending else 0, 0, 3.0,
+                         typo.handle if typo is not None else None, typo_threshold)
+
+
+class MorphSet:
+    """kiwi_morphset_h (capi.h:36, 660, 1243-1263): a set of morphemes for AnalyzeOption::blocklist.  `add(form, tag)` resolves like
+    Kiwi::findMorphemes and returns how many morphemes it added (tag None = any tag)."""
+
+    def __init__(self, kiwi: "Kiwi"):
+        self._lib = load_library()
+        self.handle = self._lib.kiwi_new_morphset(kiwi._h)
+        if not self.handle:
+            raise KiwiError(_last_error(self._lib))
+
+    def add(self, form: str, tag: str = None) -> int:
+        n = self._lib.kiwi_morphset_add(self.handle, form.encode("utf-8"), tag.encode("ascii") if tag else None)
+        if n < 0:
+            raise KiwiError(_last_error(self._lib))
+        return n
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.kiwi_morphset_close(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 TYPO_WITHOUT, TYPO_BASIC, TYPO_CONTINUAL, TYPO_BASIC_WITH_CONTINUAL, TYPO_LENGTHENING, TYPO_BASIC_WITH_CONTINUAL_AND_LENGTHENING, TYPO_DIALECT = range(7)   # capi.h:484-492
@@ -130,6 +161,10 @@ def load_library() -> C.CDLL:
     lib.kiwi_b200_debug_lattice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, AnalyzeOption]
     lib.kiwi_b200_debug_cong.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 8
     lib.kiwi_b200_model_type.argtypes = [C.c_void_p]
+    lib.kiwi_new_morphset.restype = C.c_void_p
+    lib.kiwi_new_morphset.argtypes = [C.c_void_p]
+    lib.kiwi_morphset_add.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    lib.kiwi_morphset_close.argtypes = [C.c_void_p]
     lib.kiwi_get_global_config.argtypes = [C.c_void_p]
     lib.kiwi_get_global_config.restype = Config
     lib.kiwi_set_global_config.argtypes = [C.c_void_p, Config]

@@ -2,6 +2,8 @@
 // C API (/root/reference/src/capi/kiwi_c.cpp:84-113): nothing is thrown across the ABI, failures return
 // NULL / KIWIERR_* and leave a message for the calling thread in kiwi_error().
 #include <cstring>
+#include <algorithm>
+#include <cctype>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -58,6 +60,39 @@ struct TypoScope      // AnalyzeOption::typoTransformer for the calls made while
 	Engine* e;
 	TypoScope(Engine* _e, const kiwi_analyze_option_t& o) : e{ _e } { e->setTypo(o.typo_transformer ? o.typo_transformer->forDevice(e->device) : nullptr, o.typo_threshold); }
 	~TypoScope() { e->setTypo(nullptr, 2.5f); }
+};
+
+// kiwi_morphset (capi.h:36): morpheme ids + one patched candidate table per engine that has used the set (device memory of that engine's device)
+struct kiwi_morphset
+{
+	kiwi_s* inst;
+	std::vector<uint32_t> ids;      // sorted, unique
+	uint64_t version = 0;
+	std::mutex m;
+	struct Table { void* dev = nullptr; uint64_t version = ~0ull; int device = 0; };
+	std::map<Engine*, Table> tables;
+	const DCand* forEngine(Engine* e)
+	{
+		std::lock_guard<std::mutex> lk(m);
+		Table& t = tables[e];
+		if (t.version != version)
+		{
+			const std::vector<DCand> rows = e->model.blockedCands(ids);
+			DeviceGuard g{ e->device };
+			if (!t.dev && cudaMalloc(&t.dev, rows.size() * sizeof(DCand)) != cudaSuccess) { cudaGetLastError(); throw std::runtime_error("cudaMalloc(blocklist candidate table) failed"); }
+			e->setCandsOverride(nullptr);      // (nothing reads the table while it is rewritten)
+			if (cudaMemcpy(t.dev, rows.data(), rows.size() * sizeof(DCand), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); throw std::runtime_error("upload of the blocklist candidate table failed"); }
+			t.version = version; t.device = e->device;
+		}
+		return static_cast<const DCand*>(t.dev);
+	}
+	~kiwi_morphset() { for (auto& kv : tables) if (kv.second.dev) { DeviceGuard g{ kv.second.device }; cudaFree(kv.second.dev); } }
+};
+struct BlockScope      // AnalyzeOption::blocklist for the calls made while the handle's mutex is held
+{
+	Engine* e;
+	BlockScope(Engine* _e, const kiwi_analyze_option_t& o) : e{ _e } { e->setCandsOverride(o.blocklist && !o.blocklist->ids.empty() ? o.blocklist->forEngine(e) : nullptr); }
+	~BlockScope() { e->setCandsOverride(nullptr); }
 };
 
 struct kiwi_res
@@ -130,7 +165,6 @@ static uint32_t optionWord(const kiwi_analyze_option_t& o) { return ((uint32_t)o
 static void checkOption(const kiwi_analyze_option_t& o, int topN, kiwi_pretokenized_h pt)
 {
 	if (topN != 1) throw std::invalid_argument("kiwi_b200 implements the top_n == 1 path only");
-	if (o.blocklist) throw std::invalid_argument("blocklist is outside the kiwi_b200 hot path");
 	if (o.allowed_dialects) throw std::invalid_argument("dialects other than standard are outside the kiwi_b200 hot path");
 	if (pt) throw std::invalid_argument("pretokenized spans are outside the kiwi_b200 hot path");
 	const uint32_t unsupported = (3u << 8) | (1u << 17) | (1u << 18) | (1u << 19) | (1u << 20) | (1u << 21) | (1u << 24) | (1u << 26) | (1u << 27) | (1u << 30);
@@ -212,6 +246,7 @@ static void analyzeSharded(kiwi_s* h, const uint16_t* text, const uint32_t* offs
 	if (N == 1 || n < 2 * N)
 	{
 		TypoScope ts{ h->engine.get(), option };
+		BlockScope bs{ h->engine.get(), option };
 		h->engine->analyze(text, offsets, n, optionWord(option), out);
 		return;
 	}
@@ -236,6 +271,7 @@ static void analyzeSharded(kiwi_s* h, const uint16_t* text, const uint32_t* offs
 			for (uint32_t i = r; i < n; i += N) { sub.insert(sub.end(), text + offsets[i], text + offsets[i + 1]); off.push_back((uint32_t)sub.size()); }
 			const auto t1 = Clock::now();
 			TypoScope ts{ e, option };
+			BlockScope bs{ e, option };
 			e->analyze(sub.data(), off.data(), (uint32_t)off.size() - 1, optionWord(option), part[r]);
 			stats[r] = e->last;
 			msGather[r] = std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -517,6 +553,84 @@ int kiwi_prepared_typo_close(kiwi_prepared_typo_h handle)
 	return 0;
 }
 
+// POSTag names (include/kiwi/Types.h:39-93, toPOSTag in src/TagUtils.cpp): the index is the enum value; "-I" marks the irregular variants
+static uint8_t parseTag(const char* tag)
+{
+	static const char* names[] = { "UN", "NNG", "NNP", "NNB", "VV", "VA", "MAG", "NR", "NP", "VX", "MM", "MAJ", "IC", "XPN", "XSN", "XSV", "XSA", "XSM", "XR",
+		"VCP", "VCN", "SF", "SP", "SS", "SSO", "SSC", "SE", "SO", "SW", "SB", "SL", "SH", "SN", "W_URL", "W_EMAIL", "W_MENTION", "W_HASHTAG", "W_SERIAL", "W_EMOJI",
+		"JKS", "JKC", "JKG", "JKO", "JKB", "JKV", "JKQ", "JX", "JC", "EP", "EF", "EC", "ETN", "ETM", "Z_CODA", "Z_SIOT", "USER0", "USER1", "USER2", "USER3", "USER4", "P" };
+	if (!tag) return 0;
+	std::string t{ tag };
+	for (auto& c : t) c = (char)std::toupper((unsigned char)c);
+	bool irregular = false;
+	if (t.size() > 2 && t.compare(t.size() - 2, 2, "-I") == 0) { irregular = true; t.resize(t.size() - 2); }
+	for (size_t i = 0; i < sizeof(names) / sizeof(names[0]); ++i) if (t == names[i]) return (uint8_t)(i | (irregular ? 0x80 : 0));
+	throw std::invalid_argument(std::string{ "Unknown POSTag : " } + tag);
+}
+
+kiwi_morphset_h kiwi_new_morphset(kiwi_h handle)
+{
+	if (!handle) return nullptr;
+	try { auto* s = new kiwi_morphset; s->inst = handle; return s; }
+	catch (const std::exception& e) { setError(e); return nullptr; }
+}
+
+int kiwi_morphset_add_w(kiwi_morphset_h handle, const kchar16_t* form, const char* tag)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	try
+	{
+		size_t len = 0; while (form[len]) ++len;
+		const std::vector<uint32_t> found = handle->inst->engine->model.findMorphemes(reinterpret_cast<const uint16_t*>(form), len, parseTag(tag));
+		std::lock_guard<std::mutex> lk(handle->m);
+		handle->ids.insert(handle->ids.end(), found.begin(), found.end());
+		std::sort(handle->ids.begin(), handle->ids.end());
+		handle->ids.erase(std::unique(handle->ids.begin(), handle->ids.end()), handle->ids.end());
+		++handle->version;
+		return (int)found.size();
+	}
+	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+
+int kiwi_morphset_add(kiwi_morphset_h handle, const char* form, const char* tag)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	try
+	{
+		const std::u16string w = utf8To16(form);
+		return kiwi_morphset_add_w(handle, reinterpret_cast<const kchar16_t*>(w.c_str()), tag);
+	}
+	catch (const std::exception& e) { setError(e); return KIWIERR_FAIL; }
+}
+
+int kiwi_morphset_close(kiwi_morphset_h handle)
+{
+	if (!handle) return KIWIERR_INVALID_HANDLE;
+	delete handle;
+	return 0;
+}
+
+int kiwi_b200_image_find_morphemes(const void* image_bytes, uint64_t size, const kchar16_t* form, const char* tag, uint32_t* out_ids, int cap)
+{
+	try
+	{
+		// host-side view of the image only: the sections findMorphemes reads (no device, no derived tables)
+		if (size < sizeof(kb2_header)) throw std::runtime_error("model image too small");
+		Model m;
+		m.blob.assign(static_cast<const char*>(image_bytes), static_cast<const char*>(image_bytes) + size);
+		std::memcpy(&m.header, m.blob.data(), sizeof(kb2_header));
+		if (m.header.magic != KB2_IMAGE_MAGIC || m.header.total_bytes != size) throw std::runtime_error("not a kiwi_b200 model image");
+		m.hForms = reinterpret_cast<const kb2_form*>(m.blob.data() + m.header.sec[KB2_SEC_FORMS].offset);
+		m.hFormChars = reinterpret_cast<const uint16_t*>(m.blob.data() + m.header.sec[KB2_SEC_FORM_CHARS].offset);
+		m.hMorphs = reinterpret_cast<const kb2_morph*>(m.blob.data() + m.header.sec[KB2_SEC_MORPHS].offset);
+		size_t len = 0; while (form[len]) ++len;
+		const std::vector<uint32_t> found = m.findMorphemes(reinterpret_cast<const uint16_t*>(form), len, parseTag(tag));
+		for (size_t i = 0; i < found.size() && (int)i < cap; ++i) out_ids[i] = found[i];
+		return (int)found.size();
+	}
+	catch (const std::exception& e) { setError(e); return -1; }
+}
+
 int kiwi_close(kiwi_h handle)
 {
 	if (!handle) return KIWIERR_INVALID_HANDLE;
@@ -541,6 +655,7 @@ kiwi_res_h kiwi_analyze_w(kiwi_h handle, const kchar16_t* text, int top_n, kiwi_
 		std::lock_guard<std::mutex> lk(handle->mtx);
 		BatchOutput& bo = handle->callOut;
 		TypoScope ts{ handle->engine.get(), option };
+		BlockScope bs{ handle->engine.get(), option };
 		handle->engine->analyze(text, off, 1, optionWord(option), bo);
 		return makeRes(handle, text, len, bo, 0, (uint32_t)option.match_options);
 	}
@@ -659,6 +774,7 @@ float kiwi_b200_analyze_device(kiwi_h handle, const void* d_text, const void* d_
 		checkOption(option, 1, nullptr);
 		std::lock_guard<std::mutex> lk(handle->mtx);
 		TypoScope ts{ handle->engine.get(), option };
+		BlockScope bs{ handle->engine.get(), option };
 		const float ms = handle->engine->analyzeDevice(reinterpret_cast<const uint16_t*>(d_text), reinterpret_cast<const uint32_t*>(d_offsets), (uint32_t)n, total_units, optionWord(option), out_tokens);
 		if (out_launches) *out_launches = handle->engine->last.kernelLaunches;
 		return ms;

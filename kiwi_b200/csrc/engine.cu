@@ -278,8 +278,19 @@ namespace kb
 	{
 		DevState& ds = g_devState[device < 0 || device >= 64 ? 0 : device];
 		if (ds.owner == &model) return;
-		ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(model.dev) : model.dev.model_type == 3 ? set_model_viterbi_sbg(model.dev) : set_model_viterbi(model.dev), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
+		DevModel vm = model.dev;
+		if (candsOverride_) vm.cands = candsOverride_;      // (AnalyzeOption::blocklist: only the Viterbi kernels read the candidate table)
+		ck(set_model_lattice(model.dev), "constant upload"); ck(model.dev.model_type == 4 ? set_model_viterbi_cong(vm) : model.dev.model_type == 3 ? set_model_viterbi_sbg(vm) : set_model_viterbi(vm), "constant upload"); ck(set_model_emit(model.dev), "constant upload");
 		ds.owner = &model;
+	}
+
+	void Engine::setCandsOverride(const DCand* deviceTable)
+	{
+		if (deviceTable == candsOverride_) return;
+		DeviceGuard g{ device };
+		for (auto& sl : slot_) if (sl.stream) cudaStreamSynchronize(sl.stream);      // (no kernel of this engine may still read the old table)
+		candsOverride_ = deviceTable;
+		g_devState[device < 0 || device >= 64 ? 0 : device].owner = nullptr;      // the next launch uploads the model view again
 	}
 
 	void Engine::launchAll(Scratch& sc, cudaStream_t st, cudaEvent_t* ev, uint32_t n)

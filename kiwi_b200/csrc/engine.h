@@ -5,6 +5,8 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <unordered_map>
+#include <string>
 #include <cuda_runtime.h>
 #include "kb_model.h"
 #include "kb_batch.h"
@@ -22,6 +24,14 @@ namespace kb
 		size_t deviceBytes = 0;
 		const kb2_form* hForms = nullptr; const uint16_t* hFormChars = nullptr; const kb2_morph* hMorphs = nullptr;
 		std::vector<uint32_t> hChrBmp;      // host copy of chr_bmp (cls | script << 8 | flags << 16) for result assembly
+		std::vector<DCand> hCands;          // host copy of the static candidate table (AnalyzeOption::blocklist patches a copy of it)
+		// AnalyzeOption::blocklist: the candidate table with every candidate that Morpheme::hasMorpheme(blocklist) would reject marked like a
+		// non-standard dialect candidate (DK_DIALECT: the kernels skip it at the very place the reference tests the blocklist, PathEvaluator.hpp:384-386)
+		std::vector<DCand> blockedCands(const std::vector<uint32_t>& sortedMorphemeIds) const;
+		// Kiwi::findMorphemes (src/Kiwi.cpp:1281-1297): the morphemes of the form spelled `form` (any code units; codas are normalised here) with tag
+		// `tag` (0 = any; the irregular bit is ignored), combining-socket candidates left out
+		std::vector<uint32_t> findMorphemes(const uint16_t* form, size_t len, uint8_t tag) const;
+		mutable std::unordered_map<std::u16string, uint32_t> formIndex_;      // form string -> first form of that spelling (built on first use)
 		uint32_t hostChrAttr(uint16_t c) const { return hChrBmp[c]; }
 		void load(const void* bytes, size_t size);
 		~Model();
@@ -93,6 +103,9 @@ namespace kb
 		// between two scratch arenas on two streams: pass k+1's H2D and kernels overlap pass k's tail and D2H.
 		// A sentence that overflows even the escalated retry capacity keeps a non-zero status and an empty token list (no throw).
 		void analyze(const uint16_t* text, const uint32_t* offsets, uint32_t n, uint32_t matchOptions, BatchOutput& out);
+		// AnalyzeOption::blocklist: a patched copy of the candidate table (device memory of this engine's device, Model::blockedCands) replaces
+		// the model's for the calls that follow; nullptr = the model's own table
+		void setCandsOverride(const DCand* deviceTable);
 		// device-resident inputs; results stay on the device.  returns elapsed ms (CUDA events on the engine stream)
 		float analyzeDevice(const uint16_t* dText, const uint32_t* dOffsets, uint32_t n, uint64_t totalUnits, uint32_t matchOptions, uint64_t* nTokens);
 		// lattice of one sentence for stage-level parity tests
@@ -136,6 +149,7 @@ namespace kb
 			bool tokPending = false;      // a token copy into the caller's result array is still in flight on `stream`
 		};
 		const TypoDev* typo_ = nullptr; float typoThreshold_ = 2.5f;
+		const DCand* candsOverride_ = nullptr;
 		void ensureTypoScratch(Scratch& sc, uint32_t graphPerUnit, uint32_t statesPerUnit, uint32_t mul);
 		Slot slot_[2];
 		Scratch retry_;                  // larger per-sentence capacity, only for sentences that overflowed a main arena

@@ -2,6 +2,7 @@
 // tables described in kb_model.h and uploads everything to the current device.
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <cmath>
 #include <stdexcept>
 #include <string>
@@ -368,6 +369,7 @@ namespace kb
 		d.morphs = upload(dmorphs, owned);
 		d.morphx = upload(dmx, owned);
 		d.cands = upload(dcands, owned); d.cand_unk = nFormCands;
+		hCands = dcands;
 		d.chunk_lm = upload(chunkLm, owned);
 		d.kn_hash = upload(knHash, owned); d.kn_hash_mask = hashSize - 1;
 		d.kn_backoff = upload(knBackoff, owned);
@@ -403,6 +405,57 @@ namespace kb
 		d.cfg = h->config;
 		std::memcpy(d.tag_left_boundary, h->tag_left_boundary, sizeof(d.tag_left_boundary));
 		deviceBytes = size + dmorphs.size() * sizeof(DMorph) + dforms.size() * sizeof(DForm) + bmp.size() * 4 + rootNext.size() * 4;
+	}
+
+	std::vector<DCand> Model::blockedCands(const std::vector<uint32_t>& ids) const
+	{
+		std::vector<DCand> out = hCands;
+		if (ids.empty()) return out;
+		const kb2_chunk* chunksH = reinterpret_cast<const kb2_chunk*>(blob.data() + header.sec[KB2_SEC_MORPH_CHUNKS].offset);
+		auto listed = [&](uint32_t m) { return std::binary_search(ids.begin(), ids.end(), m); };
+		for (DCand& c : out)
+		{
+			const kb2_morph& m = hMorphs[c.cur_id];
+			bool hit = listed((uint32_t)(c.cur_id + m.combined));      // Morpheme::hasMorpheme (include/kiwi/Form.h:187-196): getCombined() or a chunk
+			for (uint32_t k = 0; k < m.chunk_cnt && !hit; ++k) hit = listed(chunksH[m.chunk_off + k].morph);
+			if (hit) c.kind |= DK_DIALECT;
+		}
+		return out;
+	}
+
+	std::vector<uint32_t> Model::findMorphemes(const uint16_t* form, size_t len, uint8_t tag) const
+	{
+		// normalizeHangul (src/StrUtils.h:493-520): a syllable with a coda becomes the open syllable + the coda jamo
+		std::u16string key;
+		for (size_t i = 0; i < len; ++i)
+		{
+			const uint16_t c = form[i];
+			if (c >= 0xAC00 && c <= 0xD7A3 && (c - 0xAC00) % 28) { const uint16_t t = (uint16_t)((c - 0xAC00) % 28); key.push_back((char16_t)(c - t)); key.push_back((char16_t)(0x11A7 + t)); }
+			else key.push_back((char16_t)c);
+		}
+		if (formIndex_.empty())
+		{
+			formIndex_.reserve(header.n_forms * 2);
+			for (uint32_t i = 0; i < header.n_forms; ++i)
+			{
+				const kb2_form& f = hForms[i];
+				formIndex_.emplace(std::u16string(reinterpret_cast<const char16_t*>(hFormChars + f.str_off), f.str_len), i);      // (the trie keeps the first form of a spelling)
+			}
+		}
+		std::vector<uint32_t> out;
+		const auto it = formIndex_.find(key);
+		if (it == formIndex_.end()) return out;
+		const uint32_t* formCands = reinterpret_cast<const uint32_t*>(blob.data() + header.sec[KB2_SEC_FORM_CANDS].offset);
+		const kb2_form& f = hForms[it->second];
+		tag &= 0x7F;
+		for (uint32_t c = 0; c < f.cand_cnt; ++c)
+		{
+			const uint32_t id = formCands[f.cand_off + c];
+			const kb2_morph& m = hMorphs[id];
+			if (m.combine_socket || (tag != 0 && (m.tag & 0x7F) != tag)) continue;
+			out.push_back(id);
+		}
+		return out;
 	}
 
 	Model::~Model()

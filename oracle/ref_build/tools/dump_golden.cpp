@@ -21,6 +21,8 @@
 #include <fstream>
 #include <iostream>
 #include <thread>
+#include <unordered_set>
+#include <algorithm>
 #include <kiwi/Kiwi.h>
 #include <kiwi/TypoTransformer.h>
 #include "StrUtils.h"
@@ -62,6 +64,26 @@ int main(int argc, char** argv)
 		size_t idx = 0;
 		AnalyzeOption option;
 		if (getenv("KB_OPEN_ENDING")) option.openEnding = true;      // (vectors open_<name>: AnalyzeOption::openEnding)
+		// KB_BLOCKLIST="form/TAG;form/TAG": AnalyzeOption::blocklist built like kiwi_morphset_add does (capi/kiwi_c.cpp:1796-1811); the resolved
+		// morpheme ids go to stdout as one line `BLOCKLIST id id ...`
+		std::unordered_set<const Morpheme*> blockSet;
+		if (const char* bl = getenv("KB_BLOCKLIST"))
+		{
+			std::string spec{ bl }; size_t pos = 0;
+			while (pos < spec.size())
+			{
+				size_t e = spec.find(';', pos); if (e == spec.npos) e = spec.size();
+				const std::string item = spec.substr(pos, e - pos); pos = e + 1;
+				const size_t sl = item.rfind('/');
+				const std::u16string form = utf8To16(item.substr(0, sl));
+				const POSTag tag = sl == item.npos ? POSTag::unknown : toPOSTag(utf8To16(item.substr(sl + 1)));
+				for (auto* m : kw.findMorphemes(form, tag)) blockSet.insert(m);
+			}
+			std::vector<size_t> ids; for (auto* m : blockSet) ids.push_back(kw.morphToId(m));
+			std::sort(ids.begin(), ids.end());
+			std::printf("BLOCKLIST"); for (auto i : ids) std::printf(" %zu", i); std::printf("\n");
+			option.blocklist = &blockSet;
+		}
 		PreparedTypoTransformer ptt;
 		if (const char* ty = getenv("KB_TYPO"))
 		{

@@ -1,5 +1,6 @@
 // ORACLE C API (test infrastructure; loaded only by tests/, __graft_entry__.smoke() and bench.py's cpu legs).
 // Thin extern "C" wrapper over the CPU restatement so Python can compare it with the CUDA path through ctypes.
+#include <algorithm>
 #include "analyze.hpp"
 #include "typo.hpp"
 
@@ -157,6 +158,8 @@ void orc_typo_close(void* p) { delete reinterpret_cast<OrcTypo*>(p); }
 
 // AnalyzeOption::withTypoTransformer (include/kiwi/Kiwi.h:127-133): analyse with a typo lattice from now on (typo == nullptr: off).
 // The typo handle must outlive the analyzer's use of it.
+void orc_set_blocklist(void* p, const uint32_t* ids, int n) { auto& b = reinterpret_cast<OrcHandle*>(p)->an->viterbi.blocklist; b.assign(ids, ids + n); std::sort(b.begin(), b.end()); }
+
 void orc_set_open_ending(void* p, int on) { reinterpret_cast<OrcHandle*>(p)->an->openEnding = on != 0; }
 
 void orc_set_typo(void* p, void* typo, float threshold)

@@ -5,7 +5,7 @@
 //   BucketedHashContainer (top1Small / top1Medium)  src/BestPathContainer.hpp:291-483
 //   generateTokenList / isDisconnected  PathEvaluator.hpp:1038-1176
 //   FeatureTestor  src/FeatureTestor.cpp:6-104,  UnkFormScorer::ruleBasedScore  src/UnkFormScorer.cpp:28-51
-// Not restated (out of the top-1 default path): topN > 1 heaps, blocklist, dialects, pretokenized spans,
+// Not restated (out of the top-1 default path): topN > 1 heaps, dialects, pretokenized spans,
 // chr-model OOV scorers.  The > 512-incoming-path `top1` mode iterates a thread_local unordered_set whose
 // bucket count depends on previously analysed sentences; it is restated with insertion order and counted.
 #pragma once
@@ -105,6 +105,16 @@ namespace orc
 		bool isSingle(const kb2_morph& m) const { return m.chunk_cnt == 0 || (m.flags & (KB2_MORPH_COMPLEX | KB2_MORPH_SAISIOT)); }
 		const u16* kformPtr(const kb2_morph& m) const { return m.form_idx >= 0 ? im.formStr(m.form_idx) : nullptr; }
 		uint32_t kformLen(const kb2_morph& m) const { return m.form_idx >= 0 ? im.formLen(m.form_idx) : 0; }
+		// AnalyzeOption::blocklist, Morpheme::hasMorpheme (include/kiwi/Form.h:187-196): the candidate's combined morpheme or one of its chunks is listed
+		std::vector<uint32_t> blocklist;      // sorted morpheme ids; empty = none
+		bool blocked(int32_t id) const
+		{
+			if (blocklist.empty()) return false;
+			const auto& m = M(id);
+			if (std::binary_search(blocklist.begin(), blocklist.end(), (uint32_t)(id + m.combined))) return true;
+			for (uint32_t c = 0; c < m.chunk_cnt; ++c) if (std::binary_search(blocklist.begin(), blocklist.end(), (uint32_t)im.chunks[m.chunk_off + c].morph)) return true;
+			return false;
+		}
 		bool hasComplex(int32_t id) const                                                   // Form.h:176-185
 		{
 			const auto& m = M(id);
@@ -659,6 +669,7 @@ namespace orc
 				const int32_t curId = (int32_t)cands[ci];
 				const auto& cur = M(curId);
 				if (splitComplex && hasComplex(curId)) continue;
+				if (blocked(curId)) continue;
 				if (cur.dialect != 0) continue;
 				if (cur.tag == T_z_coda) { zCodaMorph = curId; continue; }
 				if (cur.tag == T_z_siot) { zSiotMorph = curId; continue; }
@@ -747,6 +758,7 @@ namespace orc
 					const int32_t curId = (int32_t)cands[ci];
 					const auto& cur = M(curId);
 					if (splitComplex && hasComplex(curId)) continue;
+					if (blocked(curId)) continue;
 					if (cur.dialect != 0) continue;          // allowedDialect == standard
 					if (cur.tag == T_z_coda || cur.tag == T_z_siot)
 					{

@@ -27,6 +27,11 @@ def _handle(mode):
     h = lib.hs32_open(os.fsencode(CONG_IMAGE if mode == "cong" else SBG_IMAGE if mode == "sbg" else IMAGE))
     assert h
     if mode == "typo": assert lib.hs32_set_typo(h, os.fsencode(TYPO_IMAGES["basic"]), 2.5) == 0
+    if mode == "block":      # AnalyzeOption::blocklist: the morpheme ids the reference resolved for the vectors (tests/golden/MANIFEST.json)
+        import json
+        ids = np.array(json.load(open(os.path.join(ROOT, "tests", "golden", "MANIFEST.json")))["blocklist"]["morpheme_ids"], dtype=np.uint32)
+        lib.hs32_set_blocklist.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        assert lib.hs32_set_blocklist(h, ids.ctypes.data, len(ids)) == 0
     _H[mode] = (lib, h)
     return _H[mode]
 
@@ -70,7 +75,7 @@ def work(args):
         return len(idxs), bad
     cap = 8192
     morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
-    texts = read_inputs(name); gold = read_golden(("cong_" if cong else "") + ("sbg_" if mode == "sbg" else "") + ("open_" if mode == "open" else "") + ("typo6_" if typo else "") + name)
+    texts = read_inputs(name); gold = read_golden(("cong_" if cong else "") + ("sbg_" if mode == "sbg" else "") + ("open_" if mode == "open" else "") + ("block_" if mode == "block" else "") + ("typo6_" if typo else "") + name)
     bad = []
     for i in idxs:
         t, g = texts[i], gold[i]
@@ -86,7 +91,7 @@ def work(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", nargs="?", default="plain", choices=["plain", "typo", "cong", "sbg", "open"])
+    ap.add_argument("mode", nargs="?", default="plain", choices=["plain", "typo", "cong", "sbg", "open", "block"])
     ap.add_argument("--files", default="inputs_web,inputs_written,inputs_ref_tests,inputs_dialect_typos")
     ap.add_argument("--stride", type=int, default=1)
     ap.add_argument("--maxlen", type=int, default=400, help="skip longer inputs (the pathological reference tests take minutes)")

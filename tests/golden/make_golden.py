@@ -42,6 +42,18 @@ for name in ["inputs_written", "inputs_web"]:
     with gzip.GzipFile(os.path.join(HERE, "open_" + name + ".golden.txt.gz"), "wb", mtime=0) as f:
         f.write(data)
     manifest["files"]["open_" + name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
+# AnalyzeOption::blocklist with the Knlm model: block_<name>.golden.txt.gz; the (form, tag) list and the morpheme ids the reference resolved
+# it to are recorded in the manifest
+BLOCK_SPEC = "하/VV;이/VCP;는/JX;을/JKO;것/NNB;있/VV;에서/JKB"
+for name in ["inputs_written", "inputs_web"]:
+    tmp = os.path.join("/tmp", "block_" + name + ".golden.txt")
+    env = dict(os.environ, KIWI_ARCH_TYPE="avx2", KB_MODEL_TYPE="knlm", KB_BLOCKLIST=BLOCK_SPEC)
+    out = subprocess.run([os.path.join(REFDIR, "dump_golden"), os.path.join(REFDIR, "models", "knlm_small"), os.path.join(HERE, name + ".txt"), tmp], check=True, env=env, timeout=600, capture_output=True, text=True).stdout
+    manifest["blocklist"] = {"spec": BLOCK_SPEC, "morpheme_ids": [int(x) for x in [l for l in out.splitlines() if l.startswith("BLOCKLIST")][0].split()[1:]]}
+    data = open(tmp, "rb").read()
+    with gzip.GzipFile(os.path.join(HERE, "block_" + name + ".golden.txt.gz"), "wb", mtime=0) as f:
+        f.write(data)
+    manifest["files"]["block_" + name] = {"lines": data.count(b"\nS ") + (1 if data.startswith(b"S ") else 0), "md5": hashlib.md5(data).hexdigest()}
 # typo-tolerant analysis (BASELINE.json config 4: AnalyzeOption::typoTransformer = basicTypoSet.prepare(true), typoThreshold 2.5,
 # typoCostWeight 6) with the Knlm model: typo6_<name>.golden.txt.gz
 for name in ["inputs_ref_tests", "inputs_web", "inputs_written", "inputs_dialect_typos"]:

@@ -3,7 +3,9 @@
 // threads that meet at a barrier for every warp collective.  One sentence per call, behind a small C API for
 // tests/test_hostsim_pipeline.py, which compares tokens and scores with the reference's golden vectors without a GPU.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <execinfo.h>
 #include <signal.h>
 #include <unistd.h>
@@ -75,6 +77,23 @@ int hs32_set_typo(void* p, const char* path, float threshold)
 
 // one sentence through lattice -> viterbi -> emit; tokens as (morph, tag, position, length, score); returns the token count,
 // -status on a kernel status, -100 on an error.  nodes = number of lattice nodes (all chunks)
+// AnalyzeOption::blocklist for the simulated kernels: the model's candidate table ("device" memory is host memory here) is rewritten in place
+// with Model::blockedCands - the table the engine uploads for a call with a blocklist; n == 0 restores the model's own table
+int hs32_set_blocklist(void* p, const uint32_t* ids, int n)
+{
+	try
+	{
+		std::lock_guard<std::mutex> lk(g_mtx);
+		Sim& s = *reinterpret_cast<Sim*>(p);
+		std::vector<uint32_t> v(ids, ids + n);
+		std::sort(v.begin(), v.end());
+		const std::vector<kb::DCand> rows = s.model.blockedCands(v);
+		std::memcpy(const_cast<kb::DCand*>(s.model.dev.cands), rows.data(), rows.size() * sizeof(kb::DCand));
+		return 0;
+	}
+	catch (...) { return -1; }
+}
+
 int hs32_analyze(void* p, const uint16_t* text, int len, uint32_t matchOptions, uint32_t* morph, uint8_t* tag, uint32_t* pos, uint16_t* length, float* score,
 	int maxTokens, float* sentScore, int* nNodes, uint8_t* flags)
 {

@@ -72,6 +72,12 @@ class Oracle:
             raise RuntimeError("oracle lattice failed")
         return rows[:n].copy()
 
+    def set_blocklist(self, ids):
+        """AnalyzeOption::blocklist as morpheme ids (what kiwi_morphset_add resolves to)"""
+        a = np.ascontiguousarray(np.asarray(list(ids), dtype=np.uint32))
+        self.lib.orc_set_blocklist.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.orc_set_blocklist(self.h, a.ctypes.data, len(a))
+
     def set_open_ending(self, on=True):
         """AnalyzeOption::openEnding (no end-of-sentence step on the last chunk)"""
         self.lib.orc_set_open_ending.argtypes = [C.c_void_p, C.c_int]

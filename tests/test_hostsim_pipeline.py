@@ -171,3 +171,13 @@ def test_hostsim_open_ending_matches_reference():
         pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "open", "--files", "inputs_written,inputs_web"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "191 sentences, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_hostsim_blocklist_matches_reference():
+    """AnalyzeOption::blocklist through the simulated kernels: the candidate table patched by Model::blockedCands (what the engine uploads for
+    such a call; the kernels themselves are unchanged) - all 191 sentences of inputs_written / inputs_web against the reference's vectors."""
+    import subprocess, sys
+    if not os.path.exists(LIB) or not os.path.exists(IMAGE):
+        pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "block", "--files", "inputs_written,inputs_web"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "191 sentences, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
