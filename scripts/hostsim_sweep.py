@@ -39,6 +39,31 @@ def _handle(mode):
 _BENCH = {}
 
 
+def _fuzz_texts(n, seed=20240917):
+    """random strings that look nothing like the bench text: random Hangul syllables / jamo / compatibility jamo, ASCII words, digits and
+    punctuation runs, emoji and surrogate pairs, URLs / mentions / hashtags, odd whitespace, repeated characters, lengths 0 .. 120"""
+    rs = np.random.RandomState(seed)
+    pools = [lambda: "".join(chr(0xAC00 + int(rs.randint(0, 11172))) for _ in range(rs.randint(1, 8))),
+             lambda: "".join(chr(0xAC00 + 588 * int(rs.randint(0, 19)) + 28 * int(rs.randint(0, 21))) for _ in range(rs.randint(1, 6))),
+             lambda: "".join(chr(int(rs.choice([0x1100, 0x1161, 0x11A8, 0x3131, 0x314F, 0x3147])) + int(rs.randint(0, 12))) for _ in range(rs.randint(1, 4))),
+             lambda: "".join(chr(int(rs.randint(97, 123))) for _ in range(rs.randint(1, 9))),
+             lambda: "".join(chr(int(rs.randint(48, 58))) for _ in range(rs.randint(1, 7))) + rs.choice(["", ".", ",000", "%", "년", "개", "-1"]),
+             lambda: rs.choice([".", "..", "...", "!", "?!", ",", "\"", "'", "(", ")", "[", "]", "~", "-", "·", "ㅋㅋㅋ", "ㅠㅠ", "^^", "※", "①", "●", "1)"]),
+             lambda: rs.choice(["\U0001F600", "\U0001F44D\U0001F3FD", "\u2764\uFE0F", "\U0001F1F0\U0001F1F7", "\u263A"]),
+             lambda: rs.choice(["https://a.b/c?d=1", "www.kiwi.co.kr", "a@b.com", "@user_1", "#태그", "#tag2", "010-1234-5678", "2024.01.02.", "3:45"]),
+             lambda: rs.choice(["하다", "했다", "합니다", "이다", "것", "수", "있다", "없다", "에서", "으로", "는", "을", "를", "이", "가", "도", "만", "요", "죠", "네요"]),
+             lambda: chr(0xAC00 + int(rs.randint(0, 11172))) * int(rs.randint(2, 12))]
+    seps = [" ", " ", " ", "", "", "  ", "\t", "\n", "\u00A0", "\u3000"]
+    out = []
+    for _ in range(n):
+        k = int(rs.randint(0, 14)); t = ""
+        for _j in range(k):
+            t += pools[int(rs.randint(0, len(pools)))]() + seps[int(rs.randint(0, len(seps)))]
+            if len(t) > 120: break
+        out.append(t[:120])
+    return out
+
+
 def _bench_case(mode, n):
     """sentences of the bench batch of this mode + the ORACLE's analysis of them (no golden vectors exist for synthetic text)"""
     key = (mode, n)
@@ -57,8 +82,11 @@ def work(args):
     mode, name, idxs = args
     cong = mode == "cong"; typo = mode == "typo"
     lib, h = _handle(mode)
-    if name.startswith("bench:"):
-        texts, orc = _bench_case(mode, int(name[6:]))
+    if name.startswith("bench:") or name.startswith("fuzz:"):
+        if name.startswith("fuzz:"):
+            _, orc = _bench_case(mode, 1); texts = _fuzz_texts(int(name[5:]))
+        else:
+            texts, orc = _bench_case(mode, int(name[6:]))
         cap = 8192
         morph = np.zeros(cap, np.uint32); tag = np.zeros(cap, np.uint8); pos = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint16); sc = np.zeros(cap, np.float32)
         bad = []
@@ -99,8 +127,8 @@ def main():
     a = ap.parse_args()
     tasks = []
     for name in a.files.split(","):
-        if name.startswith("bench:"):      # --files bench:8192 : the first N sentences of the mode's bench batch against the oracle
-            idx = list(range(0, int(name[6:]), a.stride)); per = max(1, len(idx) // (a.jobs * 4))
+        if name.startswith("bench:") or name.startswith("fuzz:"):      # --files bench:8192 : the first N sentences of the mode's bench batch against the oracle; fuzz:N : N random strings
+            idx = list(range(0, int(name.split(":")[1]), a.stride)); per = max(1, len(idx) // (a.jobs * 4))
             for k in range(0, len(idx), per): tasks.append((a.mode, name, idx[k:k + per]))
             continue
         texts = read_inputs(name)

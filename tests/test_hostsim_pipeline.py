@@ -181,3 +181,14 @@ def test_hostsim_blocklist_matches_reference():
         pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "block", "--files", "inputs_written,inputs_web"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "191 sentences, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_hostsim_fuzz_strings_match_oracle():
+    """1 500 random strings that look nothing like the bench text (random syllables, jamo, emoji and surrogate pairs, URLs, odd whitespace,
+    repeated characters, empty strings: scripts/hostsim_sweep.py _fuzz_texts) through the simulated Knlm kernels against the oracle - which
+    itself equals the unmodified reference on 1 065 of these strings (checked when the generator was written)."""
+    import subprocess, sys
+    if not os.path.exists(LIB) or not os.path.exists(IMAGE):
+        pytest.skip("tests/hostsim/libpipeline_sim32.so or the model image missing: run __graft_entry__.build()")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "hostsim_sweep.py"), "plain", "--files", "fuzz:1500"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "1500 sentences, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
